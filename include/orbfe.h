@@ -1,0 +1,195 @@
+/* include/orbfe.h -- C ABI of the B200-native ORB front-end (libORBfe_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of ORB-SLAM3 (reference = LY-zhang-yi-hao/ORB-SLAM3_byZyh):
+ * ORB extraction and Hamming matching.  The reference has no FFI/plugin layer; these entry
+ * points are what a header-only adapter (orb-slam3_byzyh_b200/host/ORBextractor.h,
+ * ORBmatcher_b200.h) binds so that Tracking / Frame / LocalMapping link unchanged.  Each entry
+ * point cites the reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types; `int` status (ORBFE_OK == 0,
+ * errors < -1) unless the reference function itself returns a count; every function is
+ * synchronous on return unless it takes an explicit stream.  There is NO CPU fallback: when
+ * no CUDA device is usable every call fails with ORBFE_ERR_CUDA.
+ */
+#ifndef ORBFE_H
+#define ORBFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBFE_OK 0
+#define ORBFE_EMPTY_IMAGE (-1)   /* operator() returns -1 on an empty image (ORBextractor.cc:1561) */
+#define ORBFE_ERR_INVALID (-2)   /* bad argument / unsupported geometry */
+#define ORBFE_ERR_CUDA (-3)      /* CUDA runtime error or no device */
+#define ORBFE_ERR_CAPACITY (-4)  /* caller buffer too small */
+
+#define ORBFE_MAX_LEVELS 16
+#define ORBFE_EDGE 19            /* EDGE_THRESHOLD, ORBextractor.cc:78 */
+
+/* Byte-compatible with cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id). */
+typedef struct OrbfeKeyPoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} OrbfeKeyPoint;
+
+typedef struct OrbfeExtractor OrbfeExtractor; /* opaque; one instance == one ORBextractor */
+
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * include/ORBextractor.h:49-50, src/ORBextractor.cc:468-571.  `device` = CUDA ordinal. */
+int orbfe_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                           int minThFAST, int device, OrbfeExtractor** out);
+void orbfe_extractor_destroy(OrbfeExtractor* h);
+const char* orbfe_last_error(void);
+
+/* GetLevels / GetScaleFactor(s) / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares, include/ORBextractor.h:61-81.  Arrays hold nlevels floats. */
+int orbfe_get_levels(const OrbfeExtractor* h);
+float orbfe_get_scale_factor(const OrbfeExtractor* h);
+int orbfe_scale_tables(const OrbfeExtractor* h, float* scale, float* inv_scale, float* sigma2,
+                       float* inv_sigma2);
+int orbfe_features_per_level(const OrbfeExtractor* h, int* n_per_level);
+/* Upper bound of keypoints one frame can return (octree may overshoot the per-level target). */
+int orbfe_max_keypoints(const OrbfeExtractor* h);
+
+/* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
+ * include/ORBextractor.h:57-59, src/ORBextractor.cc:1557-1682.  image = rows x cols CV_8UC1,
+ * `step` bytes per row (host memory).  Writes *n_out keypoints (cv::KeyPoint layout) and
+ * n_out x 32 descriptor bytes; returns monoIndex (>= 0), ORBFE_EMPTY_IMAGE, or an error. */
+int orbfe_extract(OrbfeExtractor* h, const uint8_t* image, int rows, int cols, size_t step,
+                  int lap0, int lap1, OrbfeKeyPoint* keypoints, uint8_t* descriptors,
+                  int capacity, int* n_out);
+
+/* Batched form of the same call: B frames of identical size, frame b at images +
+ * b*frame_stride (host memory, pinned for best throughput).  Outputs are per-frame slabs of
+ * `capacity` entries: keypoints[b*capacity + i], descriptors[(b*capacity + i)*32].
+ * n_out[b] / mono_out[b] = keypoint count / monoIndex of frame b.  Frames are independent
+ * (reference: one operator() call per frame, src/Frame.cc:513-523). */
+int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols,
+                        size_t step, size_t frame_stride, int lap0, int lap1,
+                        OrbfeKeyPoint* keypoints, uint8_t* descriptors, int capacity,
+                        int* n_out, int* mono_out);
+
+/* Same, with inputs and outputs already resident in device memory (device pointers) and the
+ * work enqueued on `stream` (a cudaStream_t; NULL = the extractor's own stream).  Does not
+ * synchronise: results are valid after the stream is synchronised. */
+int orbfe_extract_batch_device(OrbfeExtractor* h, const uint8_t* d_images, int B, int rows,
+                               int cols, size_t step, size_t frame_stride, int lap0, int lap1,
+                               OrbfeKeyPoint* d_keypoints, uint8_t* d_descriptors, int capacity,
+                               int* d_n_out, int* d_mono_out, void* stream);
+
+/* std::vector<cv::Mat> ORBextractor::mvImagePyramid (include/ORBextractor.h:83): level `level`
+ * of frame `frame` of the last extract call.  with_border = 0 copies the w x h ROI, 1 copies
+ * the (w+38) x (h+38) bordered buffer the ROI lives in.  dst is host memory. */
+int orbfe_level_size(const OrbfeExtractor* h, int rows, int cols, int level, int* w, int* hgt);
+int orbfe_pyramid_level(OrbfeExtractor* h, int frame, int level, int with_border, uint8_t* dst,
+                        size_t dst_step);
+
+/* Stage taps for parity tests (values of the last extract call, frame `frame`). */
+int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys, int capacity,
+                           int* n_out); /* FAST candidates (x,y,score) window coords, emission order */
+int orbfe_debug_level_keypoints(OrbfeExtractor* h, int frame, int level, int32_t* xys,
+                                int capacity, int* n_out); /* octree-retained, list order */
+int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step);
+/* Run only DistributeOctTree (src/ORBextractor.cc:711-1057) on caller-supplied candidates. */
+int orbfe_debug_octree(OrbfeExtractor* h, const int32_t* xys, int n, int minX, int maxX, int minY,
+                       int maxY, int N, int32_t* keep_idx, int capacity, int* n_out);
+/* Per-stage device milliseconds of the last batch call (needs orbfe_set_profiling(h,1)).
+ * Order: h2d, pyramid, fast, octree, layout, blur, describe, d2h. */
+#define ORBFE_NUM_STAGES 8
+int orbfe_set_profiling(OrbfeExtractor* h, int enable);
+int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
+/* Number of kernel launches issued by this extractor since creation. */
+long long orbfe_launch_count(const OrbfeExtractor* h);
+
+/* ------------------------------- Hamming matching ---------------------------------------- */
+
+/* static int ORBmatcher::DescriptorDistance(a, b)  include/ORBmatcher.h:43,
+ * src/ORBmatcher.cc:2384-2404, batched: out[i] = hamming256(a[i], b[i]) for n pairs (host). */
+int orbfe_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* out, int device);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) + the `d0 < d1*0.7` ratio test of
+ * Frame::ComputeStereoFishEyeMatches, src/Frame.cc:47,1553,1562.  idx2/dist2 are nq x 2
+ * (best, second; -1 when train has < 2 rows); match[i] = accepted train index or -1.
+ * `train_offset` is added to every returned index (map sharding). Host pointers. */
+int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int train_offset,
+               int32_t* idx2, int32_t* dist2, int32_t* match, int device);
+/* Device-pointer form on `stream`, no synchronisation. */
+int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
+                      int train_offset, int32_t* d_idx2, int32_t* d_dist2, void* stream);
+/* Merge G per-shard (idx2, dist2) tables [G][nq][2] into the global best two (ties -> lower
+ * index) and apply the ratio test; host pointers. */
+int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, int G, int nq,
+                     int32_t* idx2, int32_t* dist2, int32_t* match);
+
+/* The part of ORB_SLAM3::Frame the projection matchers read (Nleft == -1 layout):
+ * mvKeysUn, mvuRight, mDescriptors, mnMinX..mnMaxY, mfGridElement{Width,Height}Inv,
+ * mvScaleFactors (include/Frame.h), plus the 64x48 grid that AssignFeaturesToGrid builds
+ * (src/Frame.cc:469-504) -- rebuilt on the device from `keys`. */
+typedef struct OrbfeFrameView {
+    int32_t n;
+    const OrbfeKeyPoint* keys;
+    const float* uright;      /* may be NULL (monocular) */
+    const uint8_t* desc;      /* n x 32 */
+    float min_x, min_y, max_x, max_y;
+    float grid_w_inv, grid_h_inv;
+} OrbfeFrameView;
+
+/* One entry per candidate map point, structure of arrays, all of length m.  The caller has
+ * already projected the points (camera model + pose stay on the host side of the boundary,
+ * SURVEY 8c) and evaluated the reference's early `continue`s into `valid`. */
+typedef struct OrbfeProjPoints {
+    int32_t m;
+    const float* u;          /* mTrackProjX / uv(0) */
+    const float* v;          /* mTrackProjY / uv(1) */
+    const float* ur;         /* mTrackProjXR / uv(0)-mbf*invz (stereo gate) */
+    const float* radius;     /* r * mvScaleFactors[level]   (ORBmatcher.cc:76-83, 2010) */
+    const int32_t* min_level;
+    const int32_t* max_level;
+    const float* angle;      /* source keypoint angle (rotation histogram); may be NULL */
+    const uint8_t* valid;
+    const uint8_t* blocks;   /* MapPoint::Observations() > 0 */
+    const uint8_t* desc;     /* m x 32, MapPoint::GetDescriptor() */
+} OrbfeProjPoints;
+
+#define ORBFE_SEARCH_MAPPOINTS 0 /* SearchByProjection(Frame&, vector<MapPoint*>&, th, ...)   ORBmatcher.cc:46   */
+#define ORBFE_SEARCH_LASTFRAME 1 /* SearchByProjection(Frame&, const Frame&, th, bMono)       ORBmatcher.cc:1951 */
+#define ORBFE_SEARCH_KEYFRAME 2  /* SearchByProjection(Frame&, KeyFrame*, set<>&, th, ORBdist) ORBmatcher.cc:2197 */
+
+typedef struct OrbfeSearchParams {
+    int32_t mode;
+    int32_t th_accept;         /* TH_HIGH (modes 0,1) or ORBdist (mode 2) */
+    float nnratio;             /* ORBmatcher::mfNNratio */
+    int32_t check_orientation; /* ORBmatcher::mbCheckOrientation */
+} OrbfeSearchParams;
+
+/* claimed[i] != 0 <=> F.mvpMapPoints[i] already holds a point that blocks (see modes).
+ * assigned[i] (in/out, length F.n): index of the map point now held by keypoint i (-1 = the
+ * reference would store NULL; entries never touched keep their input value).
+ * best_idx/best_dist (length m, may be NULL): per map point accepted keypoint (-1 = none)
+ * and best distance.  Returns nmatches (>= 0) exactly as the reference function does, or an
+ * error (< -1).  Host pointers. */
+int orbfe_search_by_projection(const OrbfeFrameView* frame, const OrbfeProjPoints* pts,
+                               const OrbfeSearchParams* prm, const uint8_t* claimed,
+                               int32_t* assigned, int32_t* best_idx, int32_t* best_dist,
+                               int device);
+
+/* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
+ * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
+ * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.
+ * Writes mvuRight / mvDepth (length nl). Host pointers. */
+int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame,
+                       const OrbfeKeyPoint* keys_l, const uint8_t* desc_l, int nl,
+                       const OrbfeKeyPoint* keys_r, const uint8_t* desc_r, int nr, float mbf,
+                       float mb, float* u_right, float* depth);
+
+/* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
+const char* orbfe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBFE_H */

@@ -1,0 +1,278 @@
+// oracle/match_oracle.cpp -- TEST INFRASTRUCTURE ONLY. See match_oracle.h.
+#include "match_oracle.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <utility>
+
+#include "cvprims.h"
+
+namespace match_oracle {
+
+// reference src/ORBmatcher.cc:2384-2404 (bit-hack popcount over 8 x 32-bit words)
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t pa, pb;
+        memcpy(&pa, a + 4 * i, 4);
+        memcpy(&pb, b + 4 * i, 4);
+        unsigned int v = pa ^ pb;
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// reference src/Frame.cc:469-504 with PosInGrid :962-978
+void FrameView::assign_features_to_grid() {
+    for (int i = 0; i < GRID_COLS; i++)
+        for (int j = 0; j < GRID_ROWS; j++) grid[i][j].clear();
+    for (int i = 0; i < N; i++) {
+        const OrbKp& kp = keys[i];
+        int posX = (int)roundf((kp.x - minX) * gridWInv);
+        int posY = (int)roundf((kp.y - minY) * gridHInv);
+        if (posX < 0 || posX >= GRID_COLS || posY < 0 || posY >= GRID_ROWS) continue;
+        grid[posX][posY].push_back(i);
+    }
+}
+
+// reference src/Frame.cc:859-951
+std::vector<int> FrameView::features_in_area(float x, float y, float r, int minLevel,
+                                             int maxLevel) const {
+    std::vector<int> vIndices;
+    float factorX = r, factorY = r;
+    const int nMinCellX = std::max(0, (int)floorf((x - minX - factorX) * gridWInv));
+    if (nMinCellX >= GRID_COLS) return vIndices;
+    const int nMaxCellX = std::min((int)GRID_COLS - 1, (int)ceilf((x - minX + factorX) * gridWInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)floorf((y - minY - factorY) * gridHInv));
+    if (nMinCellY >= GRID_ROWS) return vIndices;
+    const int nMaxCellY = std::min((int)GRID_ROWS - 1, (int)ceilf((y - minY + factorY) * gridHInv));
+    if (nMaxCellY < 0) return vIndices;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const std::vector<int>& vCell = grid[ix][iy];
+            for (size_t j = 0; j < vCell.size(); j++) {
+                const OrbKp& kpUn = keys[vCell[j]];
+                if (bCheckLevels) {
+                    if (kpUn.octave < minLevel) continue;
+                    if (maxLevel >= 0)
+                        if (kpUn.octave > maxLevel) continue;
+                }
+                const float distx = kpUn.x - x;
+                const float disty = kpUn.y - y;
+                if (fabsf(distx) < factorX && fabsf(disty) < factorY) vIndices.push_back(vCell[j]);
+            }
+        }
+    return vIndices;
+}
+
+// reference src/ORBmatcher.cc:2336-2378
+static void compute_three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2,
+                                 int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) {
+            max3 = max2; max2 = max1; max1 = s;
+            ind3 = ind2; ind2 = ind1; ind1 = i;
+        } else if (s > max2) {
+            max3 = max2; max2 = s;
+            ind3 = ind2; ind2 = i;
+        } else if (s > max3) {
+            max3 = s; ind3 = i;
+        }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// reference src/ORBmatcher.cc:46-170 (mode 0), :1951-2088 + :2157-2185 (mode 1),
+// :2197-2325 (mode 2); Nleft == -1 branches.
+int search_by_projection(FrameView& F, const std::vector<ProjPoint>& pts, const uint8_t* pdesc,
+                         const SearchParams& prm, const uint8_t* claimed0, int* assigned,
+                         int* best_idx, int* best_dist) {
+    int nmatches = 0;
+    std::vector<uint8_t> claimed(claimed0, claimed0 + F.N);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    for (size_t j = 0; j < pts.size(); j++) {
+        const ProjPoint& p = pts[j];
+        best_idx[j] = -1;
+        best_dist[j] = 256;
+        if (!p.valid) continue;
+        const std::vector<int> vIndices = F.features_in_area(p.u, p.v, p.radius, p.minLevel, p.maxLevel);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = pdesc + 32 * j;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (claimed[idx]) continue;
+            if (prm.mode != 2 && F.uright && F.uright[idx] > 0) {
+                const float er = fabsf(p.ur - F.uright[idx]);
+                if (er > p.radius) continue;
+            }
+            const int dist = descriptor_distance(dMP, F.desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F.keys[idx].octave;
+                bestIdx = idx;
+            } else if (prm.mode == 0 && dist < bestDist2) {
+                bestLevel2 = F.keys[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+        best_dist[j] = bestDist;
+        if (bestDist <= prm.thAccept) {
+            if (prm.mode == 0) {
+                if (bestLevel == bestLevel2 && bestDist > prm.nnratio * bestDist2) continue;
+            }
+            assigned[bestIdx] = (int)j;
+            claimed[bestIdx] = prm.mode == 2 ? 1 : p.blocks;
+            best_idx[j] = bestIdx;
+            nmatches++;
+            if (prm.mode != 0 && prm.checkOrientation) {
+                float rot = p.angle - F.keys[bestIdx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rotHist[bin].push_back(bestIdx);
+            }
+        }
+    }
+    if (prm.mode != 0 && prm.checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int k : rotHist[i]) {
+                    assigned[k] = -1;
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
+// reference src/Frame.cc:1102-1358
+void compute_stereo_matches(const OrbKp* keysL, const uint8_t* descL, int N, const OrbKp* keysR,
+                            const uint8_t* descR, int Nr, const PyrLevelView* pyrL,
+                            const PyrLevelView* pyrR, const float* mvScaleFactors,
+                            const float* mvInvScaleFactors, float mbf, float mb, float* mvuRight,
+                            float* mvDepth) {
+    for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = pyrL[0].h;
+    std::vector<std::vector<size_t>> vRowIndices(nRows);
+    for (int iR = 0; iR < Nr; iR++) {
+        const OrbKp& kp = keysR[iR];
+        const float kpY = kp.y;
+        const float r = 2.0f * mvScaleFactors[kp.octave];
+        const int maxr = (int)ceilf(kpY + r);
+        const int minr = (int)floorf(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows)  // the reference indexes unchecked (UB outside)
+                vRowIndices[yi].push_back(iR);
+    }
+    const float minZ = mb;
+    const float minD = 0;
+    const float maxD = mbf / minZ;
+    std::vector<std::pair<int, int>> vDistIdx;
+    for (int iL = 0; iL < N; iL++) {
+        const OrbKp& kpL = keysL[iL];
+        const int levelL = kpL.octave;
+        const float vL = kpL.y;
+        const float uL = kpL.x;
+        if ((int)vL < 0 || (int)vL >= nRows) continue;
+        const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        size_t bestIdxR = 0;
+        const uint8_t* dL = descL + 32 * (size_t)iL;
+        for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+            const size_t iR = vCandidates[iC];
+            const OrbKp& kpR = keysR[iR];
+            if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+            const float uR = kpR.x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dL, descR + 32 * iR);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < thOrbDist) {
+            const float uR0 = keysR[bestIdxR].x;
+            const float scaleFactor = mvInvScaleFactors[kpL.octave];
+            const float scaleduL = roundf(kpL.x * scaleFactor);
+            const float scaledvL = roundf(kpL.y * scaleFactor);
+            const float scaleduR0 = roundf(uR0 * scaleFactor);
+            const int w = 5;
+            const PyrLevelView& PL = pyrL[kpL.octave];
+            const PyrLevelView& PR = pyrR[kpL.octave];
+            int bestDistS = INT_MAX;
+            int bestincR = 0;
+            const int L = 5;
+            float vDists[2 * 5 + 1];
+            const float iniu = scaleduR0 + L - w;
+            const float endu = scaleduR0 + L + w + 1;
+            if (iniu < 0 || endu >= PR.w) continue;
+            const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w);
+            for (int incR = -L; incR <= +L; incR++) {
+                const int xr0 = (int)(scaleduR0 + incR - w);
+                int sad = 0;  // cv::norm(IL, IR, NORM_L1) on CV_8U
+                for (int yy = 0; yy < 2 * w + 1; yy++)
+                    for (int xx = 0; xx < 2 * w + 1; xx++)
+                        sad += std::abs((int)PL.roi[(y0 + yy) * PL.step + xl0 + xx] -
+                                        (int)PR.roi[(y0 + yy) * PR.step + xr0 + xx]);
+                float dist = (float)(double)sad;
+                if (dist < bestDistS) { bestDistS = (int)dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = mvScaleFactors[kpL.octave] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= minD && disparity < maxD) {
+                if (disparity <= 0) {
+                    disparity = 0.01;
+                    bestuR = uL - 0.01;
+                }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return;  // the reference reads vDistIdx[0] here (upstream bug)
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1;
+        mvDepth[vDistIdx[i].second] = -1;
+    }
+}
+
+// reference src/Frame.cc:1553-1562
+void fisheye_ratio_matches(const uint8_t* q, int nq, const uint8_t* t, int nt, int* match,
+                           int* idx2, int* dist2) {
+    cvp::bf_knn2(q, nq, t, nt, idx2, dist2);
+    for (int i = 0; i < nq; i++) {
+        match[i] = -1;
+        if (idx2[2 * i] >= 0 && idx2[2 * i + 1] >= 0) {
+            const float d0 = (float)dist2[2 * i], d1 = (float)dist2[2 * i + 1];
+            if (d0 < d1 * 0.7) match[i] = idx2[2 * i];
+        }
+    }
+}
+
+}  // namespace match_oracle

@@ -1,0 +1,266 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front for oracle/liborb_oracle.so, the CPU restatement of the reference's ORB
+front-end (see oracle/orb_oracle.h, oracle/match_oracle.h, oracle/cvprims.h for the
+reference file:line each function follows).  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module; the product path
+(orb-slam3_byzyh_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborb_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liborb_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_extractor_create.restype = C.c_void_p
+        _LIB.oracle_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        _LIB.oracle_extractor_destroy.argtypes = [C.c_void_p]
+        _LIB.oracle_ic_angle.restype = C.c_float
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("uright", C.c_void_p),
+                ("desc", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("max_x", C.c_float), ("max_y", C.c_float), ("grid_w_inv", C.c_float),
+                ("grid_h_inv", C.c_float)]
+
+
+class ProjPointsC(C.Structure):
+    _fields_ = [("m", C.c_int32), ("u", C.c_void_p), ("v", C.c_void_p), ("ur", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
+                ("angle", C.c_void_p), ("valid", C.c_void_p), ("blocks", C.c_void_p),
+                ("desc", C.c_void_p)]
+
+
+class SearchParamsC(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("th_accept", C.c_int32), ("nnratio", C.c_float),
+                ("check_orientation", C.c_int32)]
+
+
+# ---------------------------------------------------------------- primitives
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().oracle_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border101(src, pad):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * pad, w + 2 * pad), np.uint8)
+    lib().oracle_border101(_p(src), w, h, src.strides[0], _p(dst), dst.strides[0], pad)
+    return dst
+
+
+def fast(img, th, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.empty((cap, 3), np.int32)
+    n = lib().oracle_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], th, int(nms), _p(out), cap)
+    return out[:n].copy()
+
+
+def blur7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    dst = np.empty_like(img)
+    lib().oracle_blur7(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.empty_like(y)
+    lib().oracle_fast_atan2(_p(y), _p(x), _p(out), y.size)
+    return out
+
+
+def hamming(a, b):
+    return lib().oracle_descriptor_distance(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)))
+
+
+def knn2(q, t):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    idx = np.empty((len(q), 2), np.int32)
+    dist = np.empty((len(q), 2), np.int32)
+    lib().oracle_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def fisheye_matches(q, t):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    idx = np.empty((len(q), 2), np.int32)
+    dist = np.empty((len(q), 2), np.int32)
+    match = np.empty(len(q), np.int32)
+    lib().oracle_fisheye_matches(_p(q), len(q), _p(t), len(t), _p(match), _p(idx), _p(dist))
+    return match, idx, dist
+
+
+def octree(xys, minX, maxX, minY, maxY, N):
+    xys = np.ascontiguousarray(xys, np.int32)
+    keep = np.empty(max(len(xys), 8), np.int32)
+    n = lib().oracle_octree(_p(xys), len(xys), minX, maxX, minY, maxY, N, _p(keep), len(keep))
+    return keep[:n].copy()
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(lib().oracle_ic_angle(_p(img), img.strides[0], int(x), int(y)))
+
+
+def descriptor(img, x, y, angle):
+    img = np.ascontiguousarray(img, np.uint8)
+    d = np.empty(32, np.uint8)
+    lib().oracle_descriptor(_p(img), img.strides[0], int(x), int(y), C.c_float(angle), _p(d))
+    return d
+
+
+# ---------------------------------------------------------------- extractor
+class Extractor:
+    """Mirror of ORB_SLAM3::ORBextractor on the CPU oracle."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = lib().oracle_extractor_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_extractor_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, inv, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        nf = np.empty(n, np.int32)
+        um = np.empty(16, np.int32)
+        lib().oracle_tables(C.c_void_p(self.h), _p(sc), _p(inv), _p(s2), _p(is2), _p(nf), _p(um))
+        return dict(scale=sc, inv_scale=inv, sigma2=s2, inv_sigma2=is2, nfeatures=nf, umax=um)
+
+    def __call__(self, image, lapping=(0, 0)):
+        image = np.ascontiguousarray(image, np.uint8)
+        cap = self.nfeatures + 64 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        rows, cols = image.shape if image.size else (0, 0)
+        mono = lib().oracle_extract(C.c_void_p(self.h), _p(image), rows, cols,
+                                    image.strides[0] if image.size else 0, lapping[0], lapping[1],
+                                    _p(kps), _p(desc), cap, C.byref(n))
+        assert n.value <= cap
+        return mono, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level(self, lvl):
+        """Intermediates of the last call for one level."""
+        w, h, nc, nk, ncell = (C.c_int() for _ in range(5))
+        lib().oracle_level_dims(C.c_void_p(self.h), lvl, C.byref(w), C.byref(h), C.byref(nc),
+                                C.byref(nk), C.byref(ncell))
+        padded = np.empty((h.value + 38, w.value + 38), np.uint8)
+        blurred = np.zeros((h.value, w.value), np.uint8)
+        lib().oracle_level_images(C.c_void_p(self.h), lvl, _p(padded), _p(blurred))
+        cands = np.empty((nc.value, 3), np.int32)
+        retry = np.empty(ncell.value, np.uint8)
+        kps = np.empty(nk.value, KP_DTYPE)
+        lib().oracle_level_lists(C.c_void_p(self.h), lvl, _p(cands), _p(retry), _p(kps))
+        return dict(w=w.value, h=h.value, padded=padded, blurred=blurred, cands=cands,
+                    cell_retry=retry, kps=kps)
+
+
+# ---------------------------------------------------------------- matchers
+def make_frame_view(keys, desc, uright, bounds, keep):
+    """bounds = (minX, minY, maxX, maxY).  `keep` collects arrays that must stay alive."""
+    keys = np.ascontiguousarray(keys)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    keep += [keys, desc]
+    fv = FrameViewC()
+    fv.n = len(keys)
+    fv.keys = keys.ctypes.data
+    fv.desc = desc.ctypes.data
+    if uright is not None:
+        uright = np.ascontiguousarray(uright, np.float32)
+        keep.append(uright)
+        fv.uright = uright.ctypes.data
+    fv.min_x, fv.min_y, fv.max_x, fv.max_y = [np.float32(b) for b in bounds]
+    # reference src/Frame.cc:303-305
+    fv.grid_w_inv = np.float32(64) / np.float32(np.float32(bounds[2]) - np.float32(bounds[0]))
+    fv.grid_h_inv = np.float32(48) / np.float32(np.float32(bounds[3]) - np.float32(bounds[1]))
+    return fv
+
+
+def make_proj_points(pts, keep):
+    """pts: dict of arrays u,v,ur,radius,min_level,max_level,angle,valid,blocks,desc."""
+    pp = ProjPointsC()
+    m = len(pts["u"])
+    pp.m = m
+    for name, dt in [("u", np.float32), ("v", np.float32), ("ur", np.float32),
+                     ("radius", np.float32), ("min_level", np.int32), ("max_level", np.int32),
+                     ("angle", np.float32), ("valid", np.uint8), ("blocks", np.uint8),
+                     ("desc", np.uint8)]:
+        a = np.ascontiguousarray(pts[name], dt)
+        keep.append(a)
+        setattr(pp, name, a.ctypes.data)
+    return pp
+
+
+def search_by_projection(keys, desc, uright, bounds, pts, mode, th_accept, nnratio,
+                         check_orientation, claimed, assigned, scale_factors):
+    keep = []
+    fv = make_frame_view(keys, desc, uright, bounds, keep)
+    pp = make_proj_points(pts, keep)
+    prm = SearchParamsC(mode, th_accept, nnratio, int(check_orientation))
+    claimed = np.ascontiguousarray(claimed, np.uint8)
+    assigned = np.ascontiguousarray(assigned, np.int32).copy()
+    bi = np.empty(pp.m, np.int32)
+    bd = np.empty(pp.m, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    n = lib().oracle_search_by_projection(C.byref(fv), C.byref(pp), C.byref(prm), _p(sf), len(sf),
+                                          _p(claimed), _p(assigned), _p(bi), _p(bd))
+    return n, assigned, bi, bd
+
+
+def features_in_area(keys, bounds, x, y, r, min_level, max_level):
+    keep = []
+    fv = make_frame_view(keys, np.zeros((len(keys), 32), np.uint8), None, bounds, keep)
+    out = np.empty(len(keys) + 1, np.int32)
+    n = lib().oracle_features_in_area(C.byref(fv), C.c_float(x), C.c_float(y), C.c_float(r),
+                                      min_level, max_level, _p(out), len(out))
+    return out[:n].copy()
+
+
+def stereo_match(exL, exR, keysL, descL, keysR, descR, mbf, mb):
+    keysL = np.ascontiguousarray(keysL); keysR = np.ascontiguousarray(keysR)
+    descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+    ur = np.empty(len(keysL), np.float32)
+    dp = np.empty(len(keysL), np.float32)
+    lib().oracle_stereo_match(C.c_void_p(exL.h), C.c_void_p(exR.h), _p(keysL), _p(descL), len(keysL),
+                              _p(keysR), _p(descR), len(keysR), C.c_float(mbf), C.c_float(mb),
+                              _p(ur), _p(dp))
+    return ur, dp

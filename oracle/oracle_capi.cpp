@@ -1,0 +1,179 @@
+// oracle/oracle_capi.cpp -- TEST INFRASTRUCTURE ONLY: flat C entry points so that tests/
+// and bench.py's cpu_baseline leg can drive the CPU oracle through ctypes.
+#include <cstring>
+#include <vector>
+
+#include "../include/orbfe.h"
+#include "cvprims.h"
+#include "match_oracle.h"
+#include "orb_oracle.h"
+
+using orb_oracle::Extractor;
+using orb_oracle::OrbKp;
+
+extern "C" {
+
+// ---- OpenCV primitives ------------------------------------------------------------------
+void oracle_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstep, uint8_t* dst, int dw,
+                             int dh, int dstep) {
+    cvp::resize_linear_u8(src, sw, sh, sstep, dst, dw, dh, dstep);
+}
+void oracle_border101(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep,
+                      int pad) {
+    cvp::copy_make_border_reflect101(src, w, h, sstep, dst, dstep, pad, pad, pad, pad);
+}
+int oracle_fast(const uint8_t* img, int w, int h, int step, int th, int nms, int* xys, int cap) {
+    std::vector<cvp::FastKP> out;
+    cvp::fast9_16(img, w, h, step, th, nms != 0, out);
+    int n = (int)out.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        xys[3 * i] = out[i].x; xys[3 * i + 1] = out[i].y; xys[3 * i + 2] = out[i].score;
+    }
+    return n;
+}
+void oracle_blur7(const uint8_t* src, int w, int h, int sstep, uint8_t* dst, int dstep) {
+    cvp::gaussian_blur_7x7_s2(src, w, h, sstep, dst, dstep);
+}
+void oracle_fast_atan2(const float* y, const float* x, float* out, int n) {
+    for (int i = 0; i < n; i++) out[i] = cvp::fast_atan2(y[i], x[i]);
+}
+int oracle_hamming(const uint8_t* a, const uint8_t* b) { return cvp::hamming256(a, b); }
+void oracle_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist) {
+    cvp::bf_knn2(q, nq, t, nt, idx, dist);
+}
+
+// ---- extractor --------------------------------------------------------------------------
+void* oracle_extractor_create(int nf, float sf, int nl, int ini, int mn) {
+    return new Extractor(nf, sf, nl, ini, mn);
+}
+void oracle_extractor_destroy(void* h) { delete (Extractor*)h; }
+
+int oracle_extract(void* h, const uint8_t* img, int rows, int cols, int step, int lap0, int lap1,
+                   OrbKp* kps, uint8_t* desc, int cap, int* n_out) {
+    Extractor* e = (Extractor*)h;
+    std::vector<OrbKp> k;
+    std::vector<uint8_t> d;
+    int mono = e->extract(img, rows, cols, step, lap0, lap1, k, d);
+    if (mono < 0) { *n_out = 0; return -1; }
+    *n_out = (int)k.size();
+    int n = (int)k.size() < cap ? (int)k.size() : cap;
+    if (n) {
+        memcpy(kps, k.data(), sizeof(OrbKp) * n);
+        memcpy(desc, d.data(), 32 * (size_t)n);
+    }
+    return mono;
+}
+void oracle_tables(void* h, float* scale, float* inv, float* sig2, float* invsig2, int* nfeat,
+                   int* umax16) {
+    Extractor* e = (Extractor*)h;
+    for (int i = 0; i < e->nlevels; i++) {
+        scale[i] = e->mvScaleFactor[i]; inv[i] = e->mvInvScaleFactor[i];
+        sig2[i] = e->mvLevelSigma2[i]; invsig2[i] = e->mvInvLevelSigma2[i];
+        nfeat[i] = e->mnFeaturesPerLevel[i];
+    }
+    for (int i = 0; i < 16; i++) umax16[i] = e->umax[i];
+}
+void oracle_level_dims(void* h, int lvl, int* w, int* hh, int* ncand, int* nkp, int* ncells) {
+    const orb_oracle::Level& L = ((Extractor*)h)->levels[lvl];
+    *w = L.w; *hh = L.h; *ncand = (int)L.cands.size(); *nkp = (int)L.kps.size();
+    *ncells = (int)L.cell_retry.size();
+}
+// padded: (h+38)*(w+38) bytes; blurred: h*w bytes (may be null)
+void oracle_level_images(void* h, int lvl, uint8_t* padded, uint8_t* blurred) {
+    const orb_oracle::Level& L = ((Extractor*)h)->levels[lvl];
+    if (padded) memcpy(padded, L.padded.data(), L.padded.size());
+    if (blurred && !L.blurred.empty()) memcpy(blurred, L.blurred.data(), L.blurred.size());
+}
+void oracle_level_lists(void* h, int lvl, int* cands_xys, uint8_t* cell_retry, OrbKp* kps) {
+    const orb_oracle::Level& L = ((Extractor*)h)->levels[lvl];
+    if (cands_xys)
+        for (size_t i = 0; i < L.cands.size(); i++) {
+            cands_xys[3 * i] = L.cands[i].x; cands_xys[3 * i + 1] = L.cands[i].y;
+            cands_xys[3 * i + 2] = L.cands[i].score;
+        }
+    if (cell_retry && !L.cell_retry.empty()) memcpy(cell_retry, L.cell_retry.data(), L.cell_retry.size());
+    if (kps && !L.kps.empty()) memcpy(kps, L.kps.data(), sizeof(OrbKp) * L.kps.size());
+}
+// Stand-alone octree: cands (x,y,score) in window coordinates -> retained indices.
+int oracle_octree(const int* xys, int n, int minX, int maxX, int minY, int maxY, int N, int* keep,
+                  int cap) {
+    std::vector<orb_oracle::Cand> c(n);
+    for (int i = 0; i < n; i++) c[i] = {xys[3 * i], xys[3 * i + 1], xys[3 * i + 2]};
+    std::vector<int> r = orb_oracle::distribute_octtree(c, minX, maxX, minY, maxY, N);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++) keep[i] = r[i];
+    return (int)r.size();
+}
+float oracle_ic_angle(const uint8_t* img, int step, int x, int y) {
+    static Extractor e(1000, 1.2f, 8, 20, 7);
+    return orb_oracle::ic_angle(img + (size_t)y * step + x, step, e.umax);
+}
+void oracle_descriptor(const uint8_t* img, int step, int x, int y, float angle, uint8_t* desc) {
+    orb_oracle::orb_descriptor(img + (size_t)y * step + x, step, angle, desc);
+}
+
+
+// ---- matchers (struct layouts shared with include/orbfe.h) -----------------------------
+int oracle_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    return match_oracle::descriptor_distance(a, b);
+}
+
+int oracle_search_by_projection(const OrbfeFrameView* fv, const OrbfeProjPoints* pp,
+                                const OrbfeSearchParams* prm, const float* scale_factors,
+                                int nlevels, const uint8_t* claimed, int32_t* assigned,
+                                int32_t* best_idx, int32_t* best_dist) {
+    match_oracle::FrameView F;
+    F.N = fv->n; F.keys = (const OrbKp*)fv->keys; F.uright = fv->uright; F.desc = fv->desc;
+    F.minX = fv->min_x; F.minY = fv->min_y; F.maxX = fv->max_x; F.maxY = fv->max_y;
+    F.gridWInv = fv->grid_w_inv; F.gridHInv = fv->grid_h_inv;
+    F.scaleFactors = scale_factors; F.nlevels = nlevels;
+    F.assign_features_to_grid();
+    std::vector<match_oracle::ProjPoint> pts(pp->m);
+    for (int j = 0; j < pp->m; j++) {
+        match_oracle::ProjPoint& p = pts[j];
+        p.u = pp->u[j]; p.v = pp->v[j]; p.ur = pp->ur ? pp->ur[j] : 0.f;
+        p.radius = pp->radius[j]; p.minLevel = pp->min_level[j]; p.maxLevel = pp->max_level[j];
+        p.angle = pp->angle ? pp->angle[j] : 0.f;
+        p.valid = pp->valid ? pp->valid[j] : 1; p.blocks = pp->blocks ? pp->blocks[j] : 1;
+    }
+    match_oracle::SearchParams sp{prm->mode, prm->th_accept, prm->nnratio, prm->check_orientation};
+    std::vector<int> bi(pp->m), bd(pp->m);
+    int n = match_oracle::search_by_projection(F, pts, pp->desc, sp, claimed, assigned, bi.data(), bd.data());
+    if (best_idx) memcpy(best_idx, bi.data(), sizeof(int) * pp->m);
+    if (best_dist) memcpy(best_dist, bd.data(), sizeof(int) * pp->m);
+    return n;
+}
+
+// Grid query tap: indices returned by GetFeaturesInArea, in the reference's order.
+int oracle_features_in_area(const OrbfeFrameView* fv, float x, float y, float r, int minLevel,
+                            int maxLevel, int32_t* out, int cap) {
+    match_oracle::FrameView F;
+    F.N = fv->n; F.keys = (const OrbKp*)fv->keys;
+    F.minX = fv->min_x; F.minY = fv->min_y; F.maxX = fv->max_x; F.maxY = fv->max_y;
+    F.gridWInv = fv->grid_w_inv; F.gridHInv = fv->grid_h_inv;
+    F.assign_features_to_grid();
+    std::vector<int> v = F.features_in_area(x, y, r, minLevel, maxLevel);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+// Stereo: both extractors must hold the pyramids of the pair (oracle_extract called on each).
+void oracle_stereo_match(void* hl, void* hr, const OrbKp* kl, const uint8_t* dl, int nl,
+                         const OrbKp* kr, const uint8_t* dr, int nr, float mbf, float mb,
+                         float* uright, float* depth) {
+    Extractor* L = (Extractor*)hl; Extractor* R = (Extractor*)hr;
+    std::vector<match_oracle::PyrLevelView> pl(L->nlevels), pr(R->nlevels);
+    for (int i = 0; i < L->nlevels; i++) {
+        pl[i] = {L->levels[i].roi(), L->levels[i].w, L->levels[i].h, L->levels[i].step};
+        pr[i] = {R->levels[i].roi(), R->levels[i].w, R->levels[i].h, R->levels[i].step};
+    }
+    match_oracle::compute_stereo_matches(kl, dl, nl, kr, dr, nr, pl.data(), pr.data(),
+                                         L->mvScaleFactor.data(), L->mvInvScaleFactor.data(), mbf,
+                                         mb, uright, depth);
+}
+
+void oracle_fisheye_matches(const uint8_t* q, int nq, const uint8_t* t, int nt, int* match,
+                            int* idx2, int* dist2) {
+    match_oracle::fisheye_ratio_matches(q, nq, t, nt, match, idx2, dist2);
+}
+
+}  // extern "C"
