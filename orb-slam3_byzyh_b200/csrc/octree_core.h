@@ -1,0 +1,426 @@
+// octree_core.h -- DistributeOctTree as a CTA-parallel algorithm.
+//
+// Reproduces, bit for bit (retained set AND list order), the reference's sequential quadtree
+// culling: ExtractorNode::DivideNode (/root/reference/src/ORBextractor.cc:602-674),
+// compareNodes (:676-697) and ORBextractor::DistributeOctTree (:711-1057), including
+//   * std::list push_front ordering of children and in-place survival of bNoMore nodes,
+//   * the per-pass nToExpand counter and the `size + 3*nToExpand > N` switch (:932),
+//   * the phase-2 loop driven by an UNSTABLE std::sort: libstdc++'s introsort
+//     (median-of-3, threshold 16, heapsort fallback, final insertion sort) is emulated
+//     step for step (GCC 13 bits/stl_algo.h:1848-1951, bits/stl_heap.h) so equal-key nodes
+//     land where the reference's binary puts them,
+//   * first-wins max-response selection per node (:1028-1053).
+//
+// The sequential list algorithm is re-expressed as whole-list passes: every pass computes
+// the four child populations of all expandable nodes with one data-parallel sweep over the
+// points, then one thread rebuilds the (small) node list with the exact order the reference's
+// push_front/erase sequence would produce, then all points are re-labelled in parallel.
+//
+// One CTA solves one (frame, level).  The same source compiles for the host (single
+// "thread") so the logic is unit-tested on CPU against the reference; on the device
+// OC_PAR_FOR strides over threadIdx.x and OC_SYNC is __syncthreads().
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OC_HD __host__ __device__ __forceinline__
+#else
+#define OC_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define OC_TID ((int)threadIdx.x)
+#define OC_NT ((int)blockDim.x)
+#define OC_SYNC() __syncthreads()
+#define OC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define OC_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define OC_ATOMIC_MIN(p, v) atomicMin((p), (v))
+#define OC_FMUL(a, b) __fmul_rn((a), (b))
+#define OC_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define OC_TID 0
+#define OC_NT 1
+#define OC_SYNC() ((void)0)
+#define OC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define OC_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
+#define OC_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
+#define OC_FMUL(a, b) ((a) * (b))
+#define OC_FDIV(a, b) ((a) / (b))
+#endif
+#define OC_PAR_FOR(i, n) for (int i = OC_TID; i < (n); i += OC_NT)
+
+// Packed FAST candidate: score[31:24] | y[23:12] | x[11:0] (window coordinates).
+#define OC_PK_X(p) ((int)((p) & 0xFFFu))
+#define OC_PK_Y(p) ((int)(((p) >> 12) & 0xFFFu))
+#define OC_PK_S(p) ((int)((p) >> 24))
+#define OC_PACK(x, y, s) (((uint32_t)(s) << 24) | ((uint32_t)(y) << 12) | (uint32_t)(x))
+
+struct OcNodes {  // one node-list buffer (structure of arrays, capacity M)
+    short* x0;
+    short* x1;
+    short* y0;
+    short* y1;
+    int* cnt;
+};
+
+struct OcWork {
+    const uint32_t* pk;  // n packed candidates, emission order (index == tie-break key)
+    uint32_t* pnode;     // n: node index [23:0] | quadrant [31:30]
+    int n;
+    int M;               // node capacity: max(N + 3, 4 * nIni) + 1
+    OcNodes nb[2];       // double-buffered node list
+    int* cc;             // [4M] child populations of the current pass
+    int* cpos;           // [4M] child -> index in the next list (-1 = empty)
+    int* remap;          // [M]  undivided node -> index in the next list (-1 = divided)
+    uint64_t* vs;        // [M]  expandable nodes, creation order: key<<32 | node
+    uint64_t* vs2;       // [M]  scratch for the next creation-order list
+    int* sc;             // [8]  shared scalars
+};
+enum { OC_SIZE = 0, OC_CUR = 1, OC_NV = 2, OC_STATE = 3, OC_NTOEXP = 4 };
+enum { OC_ST_PHASE1 = 0, OC_ST_PHASE2 = 1, OC_ST_DONE = 2 };
+
+static OC_HD size_t oc_shared_bytes(int M) {
+    // 2 buffers x (4 shorts + 1 int) + cc + cpos (4 ints each) + remap + vs + vs2 + scalars
+    return (size_t)M * (2 * (4 * sizeof(short) + sizeof(int)) + 8 * sizeof(int) + sizeof(int) +
+                        2 * sizeof(uint64_t)) + 16 * sizeof(int) + 64;
+}
+
+// ---- libstdc++ std::sort emulation on key<<32|payload words (compare on the key only) ----
+#define OC_LESS(a, b) (((a) >> 32) < ((b) >> 32))
+
+static OC_HD void oc_unguarded_linear_insert(uint64_t* a, int last) {
+    uint64_t val = a[last];
+    int next = last - 1;
+    while (OC_LESS(val, a[next])) {
+        a[last] = a[next];
+        last = next;
+        --next;
+    }
+    a[last] = val;
+}
+static OC_HD void oc_insertion_sort(uint64_t* a, int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (OC_LESS(a[i], a[first])) {
+            uint64_t val = a[i];
+            for (int k = i; k > first; --k) a[k] = a[k - 1];
+            a[first] = val;
+        } else {
+            oc_unguarded_linear_insert(a, i);
+        }
+    }
+}
+static OC_HD void oc_adjust_heap(uint64_t* a /*first*/, int hole, int len, uint64_t value) {
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+        second = 2 * (second + 1);
+        if (OC_LESS(a[second], a[second - 1])) second--;
+        a[hole] = a[second];
+        hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+        second = 2 * (second + 1);
+        a[hole] = a[second - 1];
+        hole = second - 1;
+    }
+    int parent = (hole - 1) / 2;  // __push_heap
+    while (hole > top && OC_LESS(a[parent], value)) {
+        a[hole] = a[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    a[hole] = value;
+}
+static OC_HD void oc_heap_sort(uint64_t* a, int n) {  // __partial_sort(first, last, last)
+    if (n >= 2) {
+        int parent = (n - 2) / 2;
+        while (true) {
+            uint64_t v = a[parent];
+            oc_adjust_heap(a, parent, n, v);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int last = n;
+    while (last > 1) {
+        --last;
+        uint64_t v = a[last];
+        a[last] = a[0];
+        oc_adjust_heap(a, 0, last, v);
+    }
+}
+static OC_HD void oc_swap(uint64_t* a, int i, int j) {
+    uint64_t t = a[i];
+    a[i] = a[j];
+    a[j] = t;
+}
+static OC_HD void oc_std_sort(uint64_t* a, int n) {
+    if (n <= 0) return;
+    int lg = 0;
+    while ((n >> (lg + 1)) != 0) lg++;
+    // explicit stack instead of the recursion on the right-hand partition
+    int stF[64], stL[64], stD[64];
+    int sp = 0;
+    stF[0] = 0; stL[0] = n; stD[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        int first = stF[sp], last = stL[sp], depth = stD[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                oc_heap_sort(a + first, last - first);
+                break;
+            }
+            --depth;
+            // __unguarded_partition_pivot
+            const int mid = first + (last - first) / 2;
+            {   // __move_median_to_first(first, first+1, mid, last-1)
+                const int A = first + 1, B = mid, C = last - 1;
+                if (OC_LESS(a[A], a[B])) {
+                    if (OC_LESS(a[B], a[C])) oc_swap(a, first, B);
+                    else if (OC_LESS(a[A], a[C])) oc_swap(a, first, C);
+                    else oc_swap(a, first, A);
+                } else if (OC_LESS(a[A], a[C])) oc_swap(a, first, A);
+                else if (OC_LESS(a[B], a[C])) oc_swap(a, first, C);
+                else oc_swap(a, first, B);
+            }
+            int lo = first + 1, hi = last;
+            while (true) {  // __unguarded_partition(first+1, last, pivot = first)
+                while (OC_LESS(a[lo], a[first])) ++lo;
+                --hi;
+                while (OC_LESS(a[first], a[hi])) --hi;
+                if (!(lo < hi)) break;
+                oc_swap(a, lo, hi);
+                ++lo;
+            }
+            const int cut = lo;
+            if (sp < 64) { stF[sp] = cut; stL[sp] = last; stD[sp] = depth; ++sp; }
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        oc_insertion_sort(a, 0, 16);
+        for (int i = 16; i != n; ++i) oc_unguarded_linear_insert(a, i);
+    } else {
+        oc_insertion_sort(a, 0, n);
+    }
+}
+
+// ---- DivideNode geometry (:608-637) -------------------------------------------------------
+static OC_HD int oc_half(int lo, int hi) {  // ceil(static_cast<float>(hi-lo)/2), exact in int
+    const int d = hi - lo;
+    return d >= 0 ? (d + 1) / 2 : -((-d) / 2);
+}
+static OC_HD void oc_make_child(const OcNodes& src, int j, int q, const OcNodes& dst, int pos,
+                                int count) {
+    const int X0 = src.x0[j], X1 = src.x1[j], Y0 = src.y0[j], Y1 = src.y1[j];
+    const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
+    dst.x0[pos] = (short)((q & 1) ? mx : X0);
+    dst.x1[pos] = (short)((q & 1) ? X1 : mx);
+    dst.y0[pos] = (short)((q & 2) ? my : Y0);
+    dst.y1[pos] = (short)((q & 2) ? Y1 : my);
+    dst.cnt[pos] = count;
+}
+static OC_HD void oc_copy_node(const OcNodes& src, int j, const OcNodes& dst, int pos) {
+    dst.x0[pos] = src.x0[j]; dst.x1[pos] = src.x1[j];
+    dst.y0[pos] = src.y0[j]; dst.y1[pos] = src.y1[j];
+    dst.cnt[pos] = src.cnt[j];
+}
+
+// One sweep over the points: quadrant of every point that sits in an expandable node.
+static OC_HD void oc_count_children(const OcWork& w) {
+    const int cur = w.sc[OC_CUR];
+    const OcNodes& nd = w.nb[cur];
+    const int size = w.sc[OC_SIZE];
+    OC_PAR_FOR(k, 4 * size) w.cc[k] = 0;
+    OC_SYNC();
+    OC_PAR_FOR(i, w.n) {
+        const int j = (int)(w.pnode[i] & 0xFFFFFFu);
+        if (nd.cnt[j] > 1) {
+            const uint32_t p = w.pk[i];
+            const int X0 = nd.x0[j], X1 = nd.x1[j], Y0 = nd.y0[j], Y1 = nd.y1[j];
+            const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
+            const int q = (OC_PK_X(p) < mx ? 0 : 1) + (OC_PK_Y(p) < my ? 0 : 2);
+            w.pnode[i] = (uint32_t)j | ((uint32_t)q << 30);
+            OC_ATOMIC_ADD(&w.cc[4 * j + q], 1);
+        }
+    }
+    OC_SYNC();
+}
+
+// Re-label every point after the list was rebuilt by thread 0.
+static OC_HD void oc_relabel(const OcWork& w) {
+    OC_PAR_FOR(i, w.n) {
+        const uint32_t v = w.pnode[i];
+        const int j = (int)(v & 0xFFFFFFu);
+        const int r = w.remap[j];
+        w.pnode[i] = (uint32_t)(r >= 0 ? r : w.cpos[4 * j + (int)(v >> 30)]);
+    }
+    OC_SYNC();
+}
+
+// Runs the whole distribution.  Output: out_idx[k] = candidate index retained by the k-th
+// node of the final list (front to back); returns the number of nodes via *out_n (thread 0
+// writes it; visible to all threads after the final OC_SYNC).
+//   width/height = maxX-minX / maxY-minY of the level window, N = mnFeaturesPerLevel[level].
+static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni, float hX, int N,
+                                int* out_idx, int* out_n, int* best_score /*[M] scratch*/) {
+    // ---- roots (:718-790) ----
+    if (OC_TID == 0) {
+        const OcNodes& nd = w.nb[0];
+        for (int i = 0; i < nIni; i++) {
+            nd.x0[i] = (short)(int)OC_FMUL(hX, (float)i);
+            nd.x1[i] = (short)(int)OC_FMUL(hX, (float)(i + 1));
+            nd.y0[i] = 0;
+            nd.y1[i] = (short)height;
+            nd.cnt[i] = 0;
+        }
+        w.sc[OC_CUR] = 0;
+    }
+    OC_SYNC();
+    OC_PAR_FOR(i, w.n) {
+        int r = (int)OC_FDIV((float)OC_PK_X(w.pk[i]), hX);
+        w.pnode[i] = (uint32_t)r;
+        OC_ATOMIC_ADD(&w.nb[0].cnt[r], 1);
+    }
+    OC_SYNC();
+    if (OC_TID == 0) {  // erase empty roots, keep order
+        const OcNodes& s = w.nb[0];
+        const OcNodes& d = w.nb[1];
+        int pos = 0;
+        for (int i = 0; i < nIni; i++) {
+            w.cpos[4 * i] = w.cpos[4 * i + 1] = w.cpos[4 * i + 2] = w.cpos[4 * i + 3] = -1;
+            if (s.cnt[i] > 0) { oc_copy_node(s, i, d, pos); w.remap[i] = pos++; }
+            else w.remap[i] = -1;
+        }
+        w.sc[OC_CUR] = 1;
+        w.sc[OC_SIZE] = pos;
+        w.sc[OC_STATE] = OC_ST_PHASE1;
+        w.sc[OC_NV] = 0;
+    }
+    OC_SYNC();
+    oc_relabel(w);
+
+    // ---- main loop (:805-1020) ----
+    while (true) {
+        OC_SYNC();
+        const int state = w.sc[OC_STATE];
+        if (state == OC_ST_DONE) break;
+        oc_count_children(w);
+        if (OC_TID == 0) {
+            const int cur = w.sc[OC_CUR];
+            const OcNodes& s = w.nb[cur];
+            const OcNodes& d = w.nb[cur ^ 1];
+            const int size = w.sc[OC_SIZE];
+            int pos = 0, nv = 0, newSize = size;
+            if (state == OC_ST_PHASE1) {
+                // children of later-visited nodes end up nearer the front (push_front)
+                for (int j = size - 1; j >= 0; j--) {
+                    if (s.cnt[j] > 1) {
+                        w.remap[j] = -1;
+                        for (int q = 3; q >= 0; q--) {
+                            const int c = w.cc[4 * j + q];
+                            if (c > 0) { oc_make_child(s, j, q, d, pos, c); w.cpos[4 * j + q] = pos++; }
+                            else w.cpos[4 * j + q] = -1;
+                        }
+                    }
+                }
+                for (int j = 0; j < size; j++)
+                    if (s.cnt[j] <= 1) { oc_copy_node(s, j, d, pos); w.remap[j] = pos++; }
+                newSize = pos;
+                int nToExpand = 0;
+                for (int j = 0; j < size; j++)
+                    if (s.cnt[j] > 1)
+                        for (int q = 0; q < 4; q++) {
+                            const int c = w.cc[4 * j + q];
+                            if (c > 1) {
+                                nToExpand++;
+                                const int cp = w.cpos[4 * j + q];
+                                w.vs[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)d.x0[cp]) << 32) | (uint32_t)cp;
+                            }
+                        }
+                int st = OC_ST_PHASE1;
+                if (newSize >= N || newSize == size) st = OC_ST_DONE;
+                else if (newSize + nToExpand * 3 > N) st = OC_ST_PHASE2;
+                w.sc[OC_STATE] = st;
+            } else {
+                // phase 2 (:934-1015): largest nodes first, one at a time, stop at N
+                const int np = w.sc[OC_NV];
+                oc_std_sort(w.vs, np);
+                int ndiv = 0;
+                for (int k = np - 1; k >= 0; k--) {
+                    const int j = (int)(w.vs[k] & 0xFFFFFFFFu);
+                    int ne = 0;
+                    for (int q = 0; q < 4; q++) ne += (w.cc[4 * j + q] > 0);
+                    newSize += ne - 1;
+                    ndiv++;
+                    if (newSize >= N) break;
+                }
+                // vs[np-1 .. np-ndiv] were divided, in that order; the last one divided owns
+                // the front of the list.
+                for (int j = 0; j < size; j++) w.remap[j] = 0;
+                for (int t = ndiv - 1; t >= 0; t--) {
+                    const int j = (int)(w.vs[np - 1 - t] & 0xFFFFFFFFu);
+                    w.remap[j] = -1;
+                    for (int q = 3; q >= 0; q--) {
+                        const int c = w.cc[4 * j + q];
+                        if (c > 0) { oc_make_child(s, j, q, d, pos, c); w.cpos[4 * j + q] = pos++; }
+                        else w.cpos[4 * j + q] = -1;
+                    }
+                }
+                for (int j = 0; j < size; j++)
+                    if (w.remap[j] != -1) { oc_copy_node(s, j, d, pos); w.remap[j] = pos++; }
+                for (int t = 0; t < ndiv; t++) {
+                    const int j = (int)(w.vs[np - 1 - t] & 0xFFFFFFFFu);
+                    for (int q = 0; q < 4; q++) {
+                        const int c = w.cc[4 * j + q];
+                        if (c > 1) {
+                            const int cp = w.cpos[4 * j + q];
+                            w.vs2[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)d.x0[cp]) << 32) | (uint32_t)cp;
+                        }
+                    }
+                }
+                for (int k = 0; k < nv; k++) w.vs[k] = w.vs2[k];
+                if (newSize >= N || newSize == size) w.sc[OC_STATE] = OC_ST_DONE;
+            }
+            w.sc[OC_NV] = nv;
+            w.sc[OC_SIZE] = newSize;
+            w.sc[OC_CUR] = cur ^ 1;
+        }
+        OC_SYNC();
+        oc_relabel(w);
+    }
+
+    // ---- best response per node, first candidate wins ties (:1028-1053) ----
+    const int size = w.sc[OC_SIZE];
+    OC_PAR_FOR(k, size) { best_score[k] = -1; out_idx[k] = 0x7FFFFFFF; }
+    OC_SYNC();
+    OC_PAR_FOR(i, w.n) OC_ATOMIC_MAX(&best_score[w.pnode[i] & 0xFFFFFFu], OC_PK_S(w.pk[i]));
+    OC_SYNC();
+    OC_PAR_FOR(i, w.n) {
+        const int j = (int)(w.pnode[i] & 0xFFFFFFu);
+        if (OC_PK_S(w.pk[i]) == best_score[j]) OC_ATOMIC_MIN(&out_idx[j], i);
+    }
+    if (OC_TID == 0) *out_n = size;
+    OC_SYNC();
+}
+
+// Carve the node tables out of one contiguous (shared-memory) block of oc_shared_bytes(M).
+static OC_HD void oc_carve(OcWork& w, void* mem, int M) {
+    char* p = (char*)mem;
+    w.M = M;
+    w.vs = (uint64_t*)p; p += sizeof(uint64_t) * M;
+    w.vs2 = (uint64_t*)p; p += sizeof(uint64_t) * M;
+    w.cc = (int*)p; p += sizeof(int) * 4 * M;
+    w.cpos = (int*)p; p += sizeof(int) * 4 * M;
+    w.remap = (int*)p; p += sizeof(int) * M;
+    for (int b = 0; b < 2; b++) { w.nb[b].cnt = (int*)p; p += sizeof(int) * M; }
+    w.sc = (int*)p; p += sizeof(int) * 16;
+    for (int b = 0; b < 2; b++) {
+        w.nb[b].x0 = (short*)p; p += sizeof(short) * M;
+        w.nb[b].x1 = (short*)p; p += sizeof(short) * M;
+        w.nb[b].y0 = (short*)p; p += sizeof(short) * M;
+        w.nb[b].y1 = (short*)p; p += sizeof(short) * M;
+    }
+}
