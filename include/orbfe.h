@@ -94,6 +94,9 @@ int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys
 int orbfe_debug_level_keypoints(OrbfeExtractor* h, int frame, int level, int32_t* xys,
                                 int capacity, int* n_out); /* octree-retained, list order */
 int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step);
+/* FAST arc score map ("best": corner at threshold t <=> best > t, response = best-1; 0 where
+ * best <= minThFAST), w x h ROI of the level. */
+int orbfe_debug_score(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step);
 /* Run only DistributeOctTree (src/ORBextractor.cc:711-1057) on caller-supplied candidates. */
 int orbfe_debug_octree(OrbfeExtractor* h, const int32_t* xys, int n, int minX, int maxX, int minY,
                        int maxY, int N, int32_t* keep_idx, int capacity, int* n_out);
@@ -104,6 +107,13 @@ int orbfe_set_profiling(OrbfeExtractor* h, int enable);
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
 /* Number of kernel launches issued by this extractor since creation. */
 long long orbfe_launch_count(const OrbfeExtractor* h);
+/* Device-memory budget of the per-chunk intermediates (default 6 GiB, env ORBFE_MAX_BYTES);
+ * batches larger than one chunk are processed chunk after chunk. */
+int orbfe_set_max_bytes(OrbfeExtractor* h, unsigned long long bytes);
+/* Geometry of the last image size seen: FAST cells, candidate slots and keypoint slots per
+ * frame, bytes of one frame's padded pyramid, device bytes of all intermediates per frame. */
+int orbfe_frame_geometry(const OrbfeExtractor* h, int* cells, int* slots, int* kpcap,
+                         unsigned long long* pyr_stride, unsigned long long* per_frame_bytes);
 
 /* ------------------------------- Hamming matching ---------------------------------------- */
 
@@ -120,10 +130,14 @@ int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int t
 /* Device-pointer form on `stream`, no synchronisation. */
 int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
                       int train_offset, int32_t* d_idx2, int32_t* d_dist2, void* stream);
-/* Merge G per-shard (idx2, dist2) tables [G][nq][2] into the global best two (ties -> lower
- * index) and apply the ratio test; host pointers. */
+/* Merge G per-shard (idx2, dist2) tables [G][nq][2] (global indices, e.g. the all-gathered
+ * results of a map sharded over G GPUs) into the global best two (ties -> lower
+ * index) and apply the ratio test.  Host-pointer and device-pointer forms. */
 int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, int G, int nq,
-                     int32_t* idx2, int32_t* dist2, int32_t* match);
+                     int32_t* idx2, int32_t* dist2, int32_t* match, int device);
+int orbfe_knn2_merge_device(const int32_t* d_idx2_shards, const int32_t* d_dist2_shards, int G,
+                            int nq, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match,
+                            void* stream);
 
 /* The part of ORB_SLAM3::Frame the projection matchers read (Nleft == -1 layout):
  * mvKeysUn, mvuRight, mDescriptors, mnMinX..mnMaxY, mfGridElement{Width,Height}Inv,

@@ -1,0 +1,248 @@
+// describe.cu -- the back half of ORBextractor::operator() (/root/reference/src/ORBextractor.cc):
+//   k_blur     GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) of every level (:1629-1637)
+//   k_layout   output ordering: level-major list order, scale to level-0 coordinates and the
+//              vLappingArea front/back split (:1616-1678), as a block-wide scan per frame
+//   k_describe IC_Angle (:91-138, computeOrientation :580-591) + steered BRIEF-256
+//              (computeOrbDescriptor :150-203), one warp per retained keypoint
+//
+// OpenCV (not vendored by the reference) supplies GaussianBlur and fastAtan2; the arithmetic
+// restated here is cv2 4.13's: the CV_8U blur is the 8.8 fixed-point kernel [18 34 48 56 48 34 18]
+// with one rounding (sum + 32768) >> 16, and fastAtan2 is a 7th-order odd polynomial evaluated in
+// fp32 WITHOUT fused multiply-add (oracle/cvprims.cpp; pinned by tests/test_oracle_cvprims.py).
+// The 19-px reflect-101 border of the pyramid level is exactly the BORDER_REFLECT_101
+// extrapolation GaussianBlur applies to the cloned ROI, so the blur reads the padded level.
+#include <float.h>
+
+#include "octree_core.h"  // OC_PK_*
+#include "orbfe_internal.h"
+
+namespace {
+
+__device__ const int8_t d_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// ------------------------------------------------------------------------------------------
+constexpr int BW = ORBFE_BLUR_TW, BH = ORBFE_BLUR_TH, BSP = 72;
+
+__global__ void __launch_bounds__(256)
+k_blur(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
+    __shared__ __align__(16) uint8_t tin[(BH + 6) * BSP];
+    __shared__ __align__(16) uint16_t hb[(BH + 6) * BW];
+    int l = 0;
+    const int t = blockIdx.x;
+    while (l + 1 < g.nlevels && t >= g.lv[l + 1].blurTileBase) l++;
+    const OrbfeLevelGeom& L = g.lv[l];
+    const int tl = t - L.blurTileBase;
+    const int ty = tl / L.blurTilesX, tx = tl - ty * L.blurTilesX;
+    const int ox = tx * BW, oy = ty * BH;
+    const size_t fo = (size_t)blockIdx.y * g.pyrStride + L.off;
+    const uint8_t* src = pyr + fo;
+    const int maxx = L.w + 18, maxy = L.h + 18;
+    for (int i = threadIdx.x; i < (BH + 6) * (BW + 6); i += 256) {
+        const int r = i / (BW + 6), c = i - r * (BW + 6);
+        const int x = min(ox - 3 + c, maxx), y = min(oy - 3 + r, maxy);
+        tin[r * BSP + c] = src[(size_t)(ORBFE_YOFF + y) * L.pitch + ORBFE_XOFF + x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (BH + 6) * BW; i += 256) {
+        const int r = i / BW, c = i - r * BW;
+        const uint8_t* p = &tin[r * BSP + c];
+        hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    uint8_t* dst = blur + fo;
+    for (int i = threadIdx.x; i < BH * BW; i += 256) {
+        const int r = i / BW, c = i - r * BW;
+        const int x = ox + c, y = oy + r;
+        if (x >= L.w || y >= L.h) continue;
+        const uint16_t* p = &hb[r * BW + c];
+        const unsigned acc = 18u * (p[0] + p[6 * BW]) + 34u * (p[BW] + p[5 * BW]) +
+                             48u * (p[2 * BW] + p[4 * BW]) + 56u * p[3 * BW];
+        dst[(size_t)(ORBFE_YOFF + y) * L.pitch + ORBFE_XOFF + x] = (uint8_t)((acc + 32768u) >> 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_layout(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ kp,
+         const int* __restrict__ kpCount, OrbfeWork* __restrict__ work, int lap0, int lap1,
+         OrbfeKeyPoint* __restrict__ outKps, int capacity, int* __restrict__ outN, int* __restrict__ outMono) {
+    __shared__ int cnt[ORBFE_MAX_LEVELS];
+    __shared__ int wsumS[8], wsumM[8];
+    const int frame = blockIdx.x;
+    if (threadIdx.x < g.nlevels) cnt[threadIdx.x] = kpCount[frame * g.nlevels + threadIdx.x];
+    __syncthreads();
+    int n = 0;
+    for (int l = 0; l < g.nlevels; l++) n += cnt[l];
+    const uint32_t* kpf = kp + (size_t)frame * g.kpCapFrame;
+    OrbfeWork* wf = work + (size_t)frame * g.kpCapFrame;
+    OrbfeKeyPoint* okp = outKps + (size_t)frame * capacity;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const float flap0 = (float)lap0, flap1 = (float)lap1;
+    int runS = 0, runM = 0;  // stereo / mono keypoints placed so far (slot order == reference order)
+    for (int base = 0; base < g.kpCapFrame; base += 256) {
+        const int s = base + threadIdx.x;
+        bool valid = false, stereo = false;
+        int l = 0, px = 0, py = 0, sc = 0;
+        float fx = 0.f, fy = 0.f;
+        if (s < g.kpCapFrame) {
+            while (l + 1 < g.nlevels && s >= g.lv[l + 1].kpBase) l++;
+            valid = (s - g.lv[l].kpBase) < cnt[l];
+            if (valid) {
+                const uint32_t p = kpf[s];
+                px = OC_PK_X(p) + ORBFE_FAST_BORDER;   // :1184-1189
+                py = OC_PK_Y(p) + ORBFE_FAST_BORDER;
+                sc = OC_PK_S(p);
+                fx = (float)px;
+                fy = (float)py;
+                if (l != 0) {                          // :1662-1665
+                    fx = __fmul_rn(fx, g.lv[l].scale);
+                    fy = __fmul_rn(fy, g.lv[l].scale);
+                }
+                stereo = fx >= flap0 && fx <= flap1;   // :1667
+            }
+        }
+        const unsigned bS = __ballot_sync(0xffffffffu, valid && stereo);
+        const unsigned bM = __ballot_sync(0xffffffffu, valid && !stereo);
+        if (lane == 0) { wsumS[wid] = __popc(bS); wsumM[wid] = __popc(bM); }
+        __syncthreads();
+        int preS = 0, preM = 0, totS = 0, totM = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; w8++) {
+            if (w8 < wid) { preS += wsumS[w8]; preM += wsumM[w8]; }
+            totS += wsumS[w8];
+            totM += wsumM[w8];
+        }
+        const unsigned lower = (1u << lane) - 1;
+        if (s < g.kpCapFrame) {
+            OrbfeWork wk;
+            wk.x = (short)px; wk.y = (short)py; wk.level = (short)l; wk.pad = 0; wk.angle = -1.f;
+            wk.dst = -1;
+            if (valid) {
+                const int dst = stereo ? n - 1 - (runS + preS + __popc(bS & lower))
+                                       : runM + preM + __popc(bM & lower);
+                if (dst < capacity) {
+                    wk.dst = dst;
+                    OrbfeKeyPoint k;
+                    k.x = fx; k.y = fy; k.size = g.lv[l].kpsize; k.angle = -1.f;
+                    k.response = (float)sc; k.octave = l; k.class_id = -1;
+                    okp[dst] = k;
+                }
+            }
+            wf[s] = wk;
+        }
+        runS += totS;
+        runM += totM;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        outN[frame] = n;
+        outMono[frame] = runM;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// cv::fastAtan2 (degrees), fp32, no FMA contraction.
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+    const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256)
+k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr,
+           const uint8_t* __restrict__ blur, const OrbfeWork* __restrict__ work,
+           OrbfeKeyPoint* __restrict__ outKps, uint8_t* __restrict__ outDesc, int capacity) {
+    __shared__ __align__(16) int8_t pat[1024];
+    for (int i = threadIdx.x; i < 256; i += 256)
+        reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(d_pattern)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (s >= g.kpCapFrame) return;
+    const int frame = blockIdx.y;
+    const OrbfeWork wk = work[(size_t)frame * g.kpCapFrame + s];
+    if (wk.dst < 0) return;
+    const OrbfeLevelGeom& L = g.lv[wk.level];
+    const size_t co = (size_t)frame * g.pyrStride + L.off + (size_t)(ORBFE_YOFF + wk.y) * L.pitch + ORBFE_XOFF + wk.x;
+
+    // ---- IC_Angle on the un-blurred level (:91-138) ----
+    const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ctor :542-570
+    const uint8_t* c = pyr + co;
+    int m10 = 0, m01 = 0;
+    const int u = lane - ORBFE_HALF_PATCH;
+    const int au = u < 0 ? -u : u;
+#pragma unroll
+    for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; v++) {
+        const int d = umax[v < 0 ? -v : v];
+        if (au <= d) {   // lane 31 has au == 16 > 15: idle
+            const int val = c[v * L.pitch + u];
+            m10 += u * val;
+            m01 += v * val;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    // ---- steered BRIEF on the blurred level (:150-203) ----
+    const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :141
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* bc = blur + co;
+    const int8_t* pp = pat + 32 * lane;
+    unsigned val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1];
+        const float x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bc[r0 * L.pitch + c0], t1 = bc[r1 * L.pitch + c1];
+        val |= (unsigned)(t0 < t1) << k;
+    }
+    outDesc[((size_t)frame * capacity + wk.dst) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) outKps[(size_t)frame * capacity + wk.dst].angle = angle;
+}
+
+}  // namespace
+
+void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                       long long* launches) {
+    k_blur<<<dim3(g.blurTiles, B), 256, 0, st>>>(g, b.pyr, b.blur);
+    ++*launches;
+}
+
+void orbfe_launch_layout(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, int lap0, int lap1,
+                         OrbfeKeyPoint* d_kps, int capacity, int* d_n, int* d_mono, cudaStream_t st,
+                         long long* launches) {
+    k_layout<<<B, 256, 0, st>>>(g, b.kp, b.kpCount, b.work, lap0, lap1, d_kps, capacity, d_n, d_mono);
+    ++*launches;
+}
+
+void orbfe_launch_describe(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B,
+                           OrbfeKeyPoint* d_kps, uint8_t* d_desc, int capacity, cudaStream_t st,
+                           long long* launches) {
+    k_describe<<<dim3((g.kpCapFrame + 7) / 8, B), 256, 0, st>>>(g, b.pyr, b.blur, b.work, d_kps, d_desc, capacity);
+    ++*launches;
+}

@@ -1,0 +1,279 @@
+// match.cu -- Hamming matching kernels and their C ABI (include/orbfe.h):
+//   ORBmatcher::DescriptorDistance          /root/reference/src/ORBmatcher.cc:2384-2404
+//   cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame::ComputeStereoFishEyeMatches
+//                                            src/Frame.cc:47, 1553, 1562
+// 256-bit descriptors are 8 x 32-bit words: XOR (LOP3) + POPC on the integer pipes.  Best and
+// second best are tracked as packed keys (distance << 23 | train index): the minimum of such
+// keys is "smallest distance, ties -> lowest train index", which is BFMatcher's order and the
+// reference's strict-`<` scan order, so top-2 is three VIMNMX per pair and merges (across train
+// chunks, and across GPUs when the map is sharded) are associative.
+#include <stdio.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "orbfe_internal.h"
+
+namespace {
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int KEY_SHIFT = 23;                   // train indices < 2^23 per launch
+constexpr int KNN_THREADS = 128, KNN_QPT = 2;   // queries per thread
+constexpr int KNN_QB = KNN_THREADS * KNN_QPT;   // queries per CTA
+constexpr int KNN_TILE = 256;                   // train descriptors staged per iteration
+constexpr int KNN_CHUNK = 4096;                 // train descriptors per CTA
+
+__device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+    return d;
+}
+
+__device__ __forceinline__ void top2_insert(uint32_t& b0, uint32_t& b1, uint32_t k) {
+    const uint32_t hi = max(b0, k);
+    b0 = min(b0, k);
+    b1 = min(b1, hi);
+}
+
+__global__ void k_hamming_pairs(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n,
+                                int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x[8], y[8];
+    const uint4* pa = reinterpret_cast<const uint4*>(a + 8 * (size_t)i);
+    const uint4* pb = reinterpret_cast<const uint4*>(b + 8 * (size_t)i);
+    *reinterpret_cast<uint4*>(x) = pa[0]; *reinterpret_cast<uint4*>(x + 4) = pa[1];
+    *reinterpret_cast<uint4*>(y) = pb[0]; *reinterpret_cast<uint4*>(y + 4) = pb[1];
+    out[i] = hamming256(x, y);
+}
+
+// partial[q][chunk][2] = two smallest keys of query q over train chunk `chunk`
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn2_partial(const uint32_t* __restrict__ query, int nq, const uint32_t* __restrict__ train, int nt,
+               int nchunks, uint32_t* __restrict__ partial) {
+    __shared__ __align__(16) uint32_t tile[KNN_TILE * 8];
+    const int q0 = blockIdx.x * KNN_QB + threadIdx.x;
+    uint32_t qv[KNN_QPT][8];
+    uint32_t b0[KNN_QPT], b1[KNN_QPT];
+#pragma unroll
+    for (int r = 0; r < KNN_QPT; r++) {
+        const int q = min(q0 + r * KNN_THREADS, nq - 1);
+        const uint4* p = reinterpret_cast<const uint4*>(query + 8 * (size_t)q);
+        *reinterpret_cast<uint4*>(qv[r]) = p[0];
+        *reinterpret_cast<uint4*>(qv[r] + 4) = p[1];
+        b0[r] = KEY_NONE;
+        b1[r] = KEY_NONE;
+    }
+    const int c0 = blockIdx.y * KNN_CHUNK, c1 = min(c0 + KNN_CHUNK, nt);
+    for (int t0 = c0; t0 < c1; t0 += KNN_TILE) {
+        const int cnt = min(KNN_TILE, c1 - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += KNN_THREADS)
+            reinterpret_cast<uint4*>(tile)[i] = reinterpret_cast<const uint4*>(train + 8 * (size_t)t0)[i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            uint32_t tv[8];
+            *reinterpret_cast<uint4*>(tv) = reinterpret_cast<const uint4*>(tile)[2 * j];
+            *reinterpret_cast<uint4*>(tv + 4) = reinterpret_cast<const uint4*>(tile)[2 * j + 1];
+            const uint32_t jj = (uint32_t)(t0 + j);
+#pragma unroll
+            for (int r = 0; r < KNN_QPT; r++) {
+                const uint32_t key = ((uint32_t)hamming256(qv[r], tv) << KEY_SHIFT) | jj;
+                top2_insert(b0[r], b1[r], key);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KNN_QPT; r++) {
+        const int q = q0 + r * KNN_THREADS;
+        if (q < nq) {
+            uint32_t* o = partial + ((size_t)q * nchunks + blockIdx.y) * 2;
+            o[0] = b0[r];
+            o[1] = b1[r];
+        }
+    }
+}
+
+// One warp per query: merge `nparts` (key0,key1) pairs into idx2/dist2 (+ratio-tested match).
+__global__ void __launch_bounds__(256)
+k_knn2_merge_keys(const uint32_t* __restrict__ partial, int nq, int nparts, int train_offset,
+                  int32_t* __restrict__ idx2, int32_t* __restrict__ dist2, int32_t* __restrict__ match) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    uint32_t b0 = KEY_NONE, b1 = KEY_NONE;
+    const uint32_t* p = partial + (size_t)q * nparts * 2;
+    for (int i = lane; i < nparts * 2; i += 32) top2_insert(b0, b1, p[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+        top2_insert(b0, b1, o0);
+        top2_insert(b0, b1, o1);
+    }
+    if (lane == 0) {
+        const int i0 = b0 == KEY_NONE ? -1 : (int)(b0 & ((1u << KEY_SHIFT) - 1)) + train_offset;
+        const int i1 = b1 == KEY_NONE ? -1 : (int)(b1 & ((1u << KEY_SHIFT) - 1)) + train_offset;
+        const int d0 = b0 == KEY_NONE ? -1 : (int)(b0 >> KEY_SHIFT), d1 = b1 == KEY_NONE ? -1 : (int)(b1 >> KEY_SHIFT);
+        idx2[2 * q] = i0; idx2[2 * q + 1] = i1;
+        dist2[2 * q] = d0; dist2[2 * q + 1] = d1;
+        if (match) {
+            // Frame.cc:1562  `(*it)[0].distance < (*it)[1].distance * 0.7` (float * double)
+            const bool ok = i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7;
+            match[q] = ok ? i0 : -1;
+        }
+    }
+}
+
+// Merge G per-shard (idx2, dist2) tables [G][nq][2] with global indices: order (dist, idx).
+__global__ void k_knn2_merge_tables(const int32_t* __restrict__ idxS, const int32_t* __restrict__ distS,
+                                    int G, int nq, int32_t* __restrict__ idx2, int32_t* __restrict__ dist2,
+                                    int32_t* __restrict__ match) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long b0 = ~0ull, b1 = ~0ull;
+    for (int s = 0; s < G; s++)
+        for (int k = 0; k < 2; k++) {
+            const int i = idxS[((size_t)s * nq + q) * 2 + k], d = distS[((size_t)s * nq + q) * 2 + k];
+            if (i < 0) continue;
+            const unsigned long long key = ((unsigned long long)(unsigned)d << 32) | (unsigned)i;
+            const unsigned long long hi = b0 > key ? b0 : key;
+            b0 = b0 < key ? b0 : key;
+            b1 = b1 < hi ? b1 : hi;
+        }
+    const int i0 = b0 == ~0ull ? -1 : (int)(b0 & 0xFFFFFFFFu), i1 = b1 == ~0ull ? -1 : (int)(b1 & 0xFFFFFFFFu);
+    const int d0 = b0 == ~0ull ? -1 : (int)(b0 >> 32), d1 = b1 == ~0ull ? -1 : (int)(b1 >> 32);
+    idx2[2 * q] = i0; idx2[2 * q + 1] = i1;
+    dist2[2 * q] = d0; dist2[2 * q + 1] = d1;
+    if (match) match[q] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
+}
+
+int mfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
+#define MCK(call)                                                        \
+    do {                                                                 \
+        cudaError_t e_ = (call);                                         \
+        if (e_ != cudaSuccess) return mfail(ORBFE_ERR_CUDA, #call, e_);  \
+    } while (0)
+
+int set_device(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return mfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", e);
+    if (device < 0 || device >= ndev) return mfail(ORBFE_ERR_INVALID, "bad device ordinal");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return mfail(ORBFE_ERR_CUDA, "cudaSetDevice", e);
+    return ORBFE_OK;
+}
+
+struct DevBuf {  // RAII device allocation for the host-pointer entry points
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+}  // namespace
+
+// Enqueue kNN-2 on `st`: idx2/dist2 (and match when non-null) for nq queries against nt train rows.
+int orbfe_knn2_enqueue(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int train_offset,
+                       int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, uint32_t* d_partial,
+                       cudaStream_t st) {
+    const int nchunks = std::max(1, (nt + KNN_CHUNK - 1) / KNN_CHUNK);
+    if (nt > 0) {
+        dim3 grid((nq + KNN_QB - 1) / KNN_QB, nchunks);
+        k_knn2_partial<<<grid, KNN_THREADS, 0, st>>>((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt,
+                                                     nchunks, d_partial);
+    } else {
+        cudaMemsetAsync(d_partial, 0xFF, sizeof(uint32_t) * 2 * (size_t)nq, st);
+    }
+    k_knn2_merge_keys<<<(nq + 7) / 8, 256, 0, st>>>(d_partial, nq, nchunks, train_offset, d_idx2, d_dist2, d_match);
+    return 2;
+}
+
+size_t orbfe_knn2_partial_bytes(int nq, int nt) {
+    const int nchunks = std::max(1, (nt + KNN_CHUNK - 1) / KNN_CHUNK);
+    return sizeof(uint32_t) * 2 * (size_t)nq * nchunks;
+}
+
+extern "C" {
+
+int orbfe_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* out, int device) {
+    int rc = set_device(device);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!a || !b || !out))) return mfail(ORBFE_ERR_INVALID, "bad arguments");
+    if (n == 0) return ORBFE_OK;
+    DevBuf da, db, dout;
+    MCK(da.alloc(32 * (size_t)n)); MCK(db.alloc(32 * (size_t)n)); MCK(dout.alloc(4 * (size_t)n));
+    MCK(cudaMemcpy(da.p, a, 32 * (size_t)n, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(db.p, b, 32 * (size_t)n, cudaMemcpyHostToDevice));
+    k_hamming_pairs<<<(n + 255) / 256, 256>>>(da.as<uint32_t>(), db.as<uint32_t>(), n, dout.as<int32_t>());
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(out, dout.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int train_offset,
+                      int32_t* d_idx2, int32_t* d_dist2, void* stream) {
+    if (nq <= 0) return ORBFE_OK;
+    if (nt < 0 || nt >= (1 << KEY_SHIFT) || !d_query || !d_idx2 || !d_dist2)
+        return mfail(ORBFE_ERR_INVALID, "bad arguments (nt must be < 2^23 per call: shard larger maps)");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* partial = nullptr;
+    MCK(cudaMallocAsync((void**)&partial, orbfe_knn2_partial_bytes(nq, nt), st));
+    orbfe_knn2_enqueue(d_query, nq, d_train, nt, train_offset, d_idx2, d_dist2, nullptr, partial, st);
+    MCK(cudaGetLastError());
+    MCK(cudaFreeAsync(partial, st));
+    return ORBFE_OK;
+}
+
+int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int train_offset, int32_t* idx2,
+               int32_t* dist2, int32_t* match, int device) {
+    int rc = set_device(device);
+    if (rc) return rc;
+    if (nq < 0 || nt < 0 || nt >= (1 << KEY_SHIFT)) return mfail(ORBFE_ERR_INVALID, "bad sizes (nt must be < 2^23 per call)");
+    if (nq == 0) return ORBFE_OK;
+    if (!query || (nt > 0 && !train) || !idx2 || !dist2) return mfail(ORBFE_ERR_INVALID, "null argument");
+    DevBuf dq, dt, di, dd, dm, dp;
+    MCK(dq.alloc(32 * (size_t)nq)); MCK(dt.alloc(32 * (size_t)nt));
+    MCK(di.alloc(8 * (size_t)nq)); MCK(dd.alloc(8 * (size_t)nq)); MCK(dm.alloc(4 * (size_t)nq));
+    MCK(dp.alloc(orbfe_knn2_partial_bytes(nq, nt)));
+    MCK(cudaMemcpy(dq.p, query, 32 * (size_t)nq, cudaMemcpyHostToDevice));
+    if (nt) MCK(cudaMemcpy(dt.p, train, 32 * (size_t)nt, cudaMemcpyHostToDevice));
+    orbfe_knn2_enqueue(dq.as<uint8_t>(), nq, dt.as<uint8_t>(), nt, train_offset, di.as<int32_t>(),
+                       dd.as<int32_t>(), dm.as<int32_t>(), dp.as<uint32_t>(), 0);
+    MCK(cudaGetLastError());
+    MCK(cudaMemcpy(idx2, di.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(dist2, dd.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
+    if (match) MCK(cudaMemcpy(match, dm.p, 4 * (size_t)nq, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_merge_device(const int32_t* d_idx2_shards, const int32_t* d_dist2_shards, int G, int nq,
+                            int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, void* stream) {
+    if (nq <= 0 || G <= 0) return ORBFE_OK;
+    k_knn2_merge_tables<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_idx2_shards, d_dist2_shards, G, nq,
+                                                                           d_idx2, d_dist2, d_match);
+    MCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, int G, int nq, int32_t* idx2,
+                     int32_t* dist2, int32_t* match, int device) {
+    int rc = set_device(device);
+    if (rc) return rc;
+    if (nq <= 0 || G <= 0) return ORBFE_OK;
+    const size_t tb = 8 * (size_t)nq * G;
+    DevBuf si, sd, di, dd, dm;
+    MCK(si.alloc(tb)); MCK(sd.alloc(tb)); MCK(di.alloc(8 * (size_t)nq)); MCK(dd.alloc(8 * (size_t)nq)); MCK(dm.alloc(4 * (size_t)nq));
+    MCK(cudaMemcpy(si.p, idx2_shards, tb, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(sd.p, dist2_shards, tb, cudaMemcpyHostToDevice));
+    rc = orbfe_knn2_merge_device(si.as<int32_t>(), sd.as<int32_t>(), G, nq, di.as<int32_t>(), dd.as<int32_t>(), dm.as<int32_t>(), 0);
+    if (rc) return rc;
+    MCK(cudaMemcpy(idx2, di.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(dist2, dd.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
+    if (match) MCK(cudaMemcpy(match, dm.p, 4 * (size_t)nq, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
+}
+
+}  // extern "C"

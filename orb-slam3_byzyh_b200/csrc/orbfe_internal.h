@@ -1,19 +1,23 @@
 // orbfe_internal.h -- geometry shared by the host planner (orbfe_api.cu) and the kernels.
 #pragma once
+#include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+
+#include <vector>
 
 #include "../../include/orbfe.h"
 
 #define ORBFE_XOFF 32  // column of the ROI origin inside a padded row (keeps ROI rows 16B aligned)
 #define ORBFE_YOFF 19  // row of the ROI origin (EDGE_THRESHOLD)
 #define ORBFE_FAST_BORDER 16  // minBorderX/Y = EDGE_THRESHOLD-3, ORBextractor.cc:1076-1079
+#define ORBFE_HALF_PATCH 15   // HALF_PATCH_SIZE, ORBextractor.cc:77
 
 // Per-level constants, all derived on the host exactly as the reference derives them
 // (src/ORBextractor.cc:468-571 ctor, :1076-1095 FAST grid, :718-754 octree roots, :1692 sizes).
 struct OrbfeLevelGeom {
     int w, h;            // ROI size
-    int pitch;           // bytes per padded row
+    int pitch;           // bytes per padded row (multiple of 16)
     unsigned off;        // byte offset of the padded level inside one frame's pyramid slab
     int nCols, nRows, wCell, hCell;  // FAST cell grid
     int maxBX, maxBY;    // w-16, h-16
@@ -27,27 +31,33 @@ struct OrbfeLevelGeom {
     int ocM;             // octree node capacity
     int kpBase, kpCap;   // retained-keypoint slots (frame-wide numbering)
     float scale;         // mvScaleFactor[level]
+    float invScale;      // mvInvScaleFactor[level]
     float kpsize;        // (float)(int)(PATCH_SIZE*mvScaleFactor[level])
     unsigned xtab, ytab; // offsets (in entries) of the resize tables of this level
-    int areaFast;        // exact 2x decimation -> OpenCV's area path
+    int mode;            // resize path: 0 = bilinear taps, 1 = exact 2x2 area, 2 = identity copy
+    int fastTileBase, fastTilesX, fastTilesY;   // tile numbering of the FAST score kernel
+    int blurTileBase, blurTilesX, blurTilesY;   // tile numbering of the blur kernel
 };
 
 struct OrbfeFrameGeom {
     int nlevels, rows, cols;
     int iniTh, minTh;
-    unsigned long long pyrStride;   // bytes per frame in the pyramid / blurred slabs
+    unsigned long long pyrStride;   // bytes per frame in the pyramid / blurred / score slabs
     int cellsPerFrame;
     unsigned slotsPerFrame;
     int kpCapFrame;
+    int fastTiles, blurTiles;
+    int ocShared;                   // dynamic shared bytes of the octree kernel (0 = tables in global)
+    int ocMmax;
     OrbfeLevelGeom lv[ORBFE_MAX_LEVELS];
 };
 
-// One bilinear tap table entry (per destination column or row): source index and the two
+// One bilinear tap table entry (per destination column or row): source indices and the two
 // 11-bit weights, computed on the host in double precision exactly like OpenCV's resize.
 struct OrbfeTap {
     short s;   // source index (clamped)
     short a0;  // weight of src[s]
-    short a1;  // weight of src[s+1]
+    short a1;  // weight of src[s1]
     short s1;  // second source index (== s when clamped)
 };
 
@@ -57,4 +67,96 @@ struct OrbfeWork {
     short level;
     short pad;
     int dst;           // index into the frame's output slab
+    float angle;       // degrees
 };
+
+#define ORBFE_FAST_TW 64
+#define ORBFE_FAST_TH 16
+#define ORBFE_BLUR_TW 64
+#define ORBFE_BLUR_TH 16
+
+// Device buffers of one chunk of frames (all frame-major).
+struct OrbfeChunkBufs {
+    uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
+    uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
+    uint8_t* score;      // [B][pyrStride]  FAST arc score ("best", 0 when <= minTh)
+    uint32_t* slots;     // [B][slotsPerFrame] per-cell candidate slots (packed)
+    int* cellCount;      // [B][cellsPerFrame]
+    uint32_t* cand;      // [B][slotsPerFrame] per-level compacted candidates (emission order)
+    uint32_t* pnode;     // [B][slotsPerFrame] octree point labels
+    int* candCount;      // [B][nlevels]
+    uint32_t* kp;        // [B][kpCapFrame] retained candidates (packed), list order
+    int* kpCount;        // [B][nlevels]
+    OrbfeWork* work;     // [B][kpCapFrame]
+    char* ocGlobal;      // octree tables when they do not fit in shared memory (else null)
+    size_t ocGlobalStride;
+};
+
+// Records the thread's last error string (orbfe_last_error) and returns `code`.
+int orbfe_fail(int code, const char* what, cudaError_t e);
+
+// ---- kernel launchers (each enqueues on `st`, no synchronisation) ----------------------------
+void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
+                          size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
+                          cudaStream_t st, long long* launches);
+void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                       long long* launches);
+void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                         long long* launches);
+void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                       long long* launches);
+void orbfe_launch_layout(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, int lap0, int lap1,
+                         OrbfeKeyPoint* d_kps, int capacity, int* d_n, int* d_mono, cudaStream_t st,
+                         long long* launches);
+void orbfe_launch_describe(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B,
+                           OrbfeKeyPoint* d_kps, uint8_t* d_desc, int capacity, cudaStream_t st,
+                           long long* launches);
+int orbfe_octree_prepare(OrbfeFrameGeom& g);  // fills ocShared/ocMmax, sets the func attribute
+size_t orbfe_octree_table_bytes(int M);
+void orbfe_launch_octree_debug(const uint32_t* d_pk, uint32_t* d_pnode, int n, int width, int height,
+                               int nIni, float hX, int N, int M, int* d_out, int* d_outn, char* d_tables,
+                               cudaStream_t st);
+
+// One ORBextractor instance (opaque to the C ABI).
+struct OrbfeExtractor {
+    int nfeatures, nlevels, iniTh, minTh, device;
+    double scaleFactor;  // the reference stores the float ctor argument in a double member
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> nfeat;
+
+    bool haveGeom = false;
+    OrbfeFrameGeom g;
+    OrbfeTap* d_taps = nullptr;
+    size_t perFrameBytes = 0;
+
+    OrbfeChunkBufs bufs = {};
+    int chunkCap = 0;       // frames the chunk buffers hold
+    void* slab = nullptr;   // one allocation behind bufs
+
+    // staging of the host-pointer API (double buffered)
+    uint8_t* d_in[2] = {nullptr, nullptr};
+    size_t inBytes = 0;
+    OrbfeKeyPoint* d_okps[2] = {nullptr, nullptr};
+    uint8_t* d_odesc[2] = {nullptr, nullptr};
+    int* d_on[2] = {nullptr, nullptr};
+    int* d_omono[2] = {nullptr, nullptr};
+    int outFrames = 0;
+    size_t outElems = 0;
+
+    cudaStream_t sCompute = nullptr, sH2D = nullptr, sD2H = nullptr;
+    cudaEvent_t evIn[2] = {}, evInFree[2] = {}, evDone[2] = {}, evOutFree[2] = {};
+    bool profiling = false;
+    cudaEvent_t evStage[ORBFE_NUM_STAGES + 1] = {};
+    float stageMs[ORBFE_NUM_STAGES] = {};
+    bool stagesPending = false;
+    int lastFrames = 0;
+    long long launches = 0;
+    size_t maxBytes = (size_t)6 << 30;
+};
+
+
+// Frame::ComputeStereoMatches kernels (stereo.cu); pointers are device pointers.
+void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
+                         const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
+                         const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
+                         int* sad, cudaStream_t st);

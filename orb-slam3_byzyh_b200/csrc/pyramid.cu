@@ -1,0 +1,118 @@
+// pyramid.cu -- ORBextractor::ComputePyramid (/root/reference/src/ORBextractor.cc:1687-1740).
+//
+// Level 0 is copyMakeBorder(image, 19 px, BORDER_REFLECT_101) (:1734-1736); level l > 0 is
+// cv::resize(level l-1, INTER_LINEAR) into the centre of a (w+38) x (h+38) buffer followed by
+// an in-place reflect-101 border (:1702-1716).  OpenCV is not vendored by the reference; the
+// fixed-point bilinear arithmetic restated here (11-bit taps computed on the host in double,
+// horizontal pass in int32, vertical pass (((b0*(H0>>4))>>16)+((b1*(H1>>4))>>16)+2)>>2) is the
+// cv2 4.13 CV_8U path (oracle/cvprims.cpp, pinned against cv2 by tests/test_oracle_cvprims.py).
+//
+// Design: resize and border are ONE pass.  Every thread owns one aligned 4-byte word of the
+// padded destination row; border pixels are produced by reflecting the destination coordinate
+// into the ROI and evaluating the same bilinear tap there, so no second pass (and no
+// synchronisation) is needed and every store is a coalesced 32-bit word.
+#include "orbfe_internal.h"
+
+namespace {
+
+__device__ __forceinline__ int reflect101_clamped(int p, int len) {
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * (len - 1) - p;
+    return max(0, min(p, len - 1));
+}
+
+__global__ void __launch_bounds__(256)
+k_level0(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8_t* __restrict__ pyr,
+         unsigned long long pyrStride, int w, int h, int pitch) {
+    const int words = pitch >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = h + 2 * ORBFE_YOFF;
+    if (idx >= words * H) return;
+    const int py = idx / words, wc = idx - py * words;
+    const uint8_t* src = img + (size_t)blockIdx.y * frameStride +
+                         (size_t)reflect101_clamped(py - ORBFE_YOFF, h) * step;
+    const int x0 = 4 * wc - ORBFE_XOFF;
+    uint32_t out;
+    if (x0 >= 0 && x0 + 3 < w && ((reinterpret_cast<size_t>(src + x0) & 3) == 0)) {
+        out = __ldg(reinterpret_cast<const uint32_t*>(src + x0));
+    } else {
+        out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            out |= (uint32_t)__ldg(src + reflect101_clamped(x0 + i, w)) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)blockIdx.y * pyrStride + (size_t)py * pitch + 4 * wc) = out;
+}
+
+// mode 0: bilinear taps; 1: exact 2x2 area average; 2: identity
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_resize(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict__ xtab,
+         const OrbfeTap* __restrict__ ytab, unsigned srcOff, int srcPitch, unsigned dstOff, int w,
+         int h, int pitch) {
+    const int words = pitch >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = h + 2 * ORBFE_YOFF;
+    if (idx >= words * H) return;
+    const int py = idx / words, wc = idx - py * words;
+    uint8_t* base = pyr + (size_t)blockIdx.y * pyrStride;
+    const uint8_t* sroi = base + srcOff + (size_t)ORBFE_YOFF * srcPitch + ORBFE_XOFF;
+    const int ry = reflect101_clamped(py - ORBFE_YOFF, h);
+    const int x0 = 4 * wc - ORBFE_XOFF;
+    uint32_t out = 0;
+    if (MODE == 0) {
+        const OrbfeTap ty = ytab[ry];
+        const uint8_t* r0 = sroi + (size_t)ty.s * srcPitch;
+        const uint8_t* r1 = sroi + (size_t)ty.s1 * srcPitch;
+        const int b0 = ty.a0, b1 = ty.a1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const OrbfeTap tx = xtab[reflect101_clamped(x0 + i, w)];
+            const int h0 = (int)r0[tx.s] * tx.a0 + (int)r0[tx.s1] * tx.a1;
+            const int h1 = (int)r1[tx.s] * tx.a0 + (int)r1[tx.s1] * tx.a1;
+            const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            out |= (uint32_t)(v & 255) << (8 * i);
+        }
+    } else if (MODE == 1) {
+        const uint8_t* r0 = sroi + (size_t)(2 * ry) * srcPitch;
+        const uint8_t* r1 = r0 + srcPitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int rx = 2 * reflect101_clamped(x0 + i, w);
+            const int v = ((int)r0[rx] + (int)r0[rx + 1] + (int)r1[rx] + (int)r1[rx + 1] + 2) >> 2;
+            out |= (uint32_t)v << (8 * i);
+        }
+    } else {
+        const uint8_t* r0 = sroi + (size_t)ry * srcPitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) out |= (uint32_t)r0[reflect101_clamped(x0 + i, w)] << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(base + dstOff + (size_t)py * pitch + 4 * wc) = out;
+}
+
+}  // namespace
+
+void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
+                          size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
+                          cudaStream_t st, long long* launches) {
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbfeLevelGeom& L = g.lv[l];
+        const int total = (L.pitch >> 2) * (L.h + 2 * ORBFE_YOFF);
+        dim3 grid((total + 255) / 256, B);
+        if (l == 0) {
+            k_level0<<<grid, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride,
+                                           L.w, L.h, L.pitch);
+        } else {
+            const OrbfeLevelGeom& S = g.lv[l - 1];
+            const OrbfeTap* xt = taps + L.xtab;
+            const OrbfeTap* yt = taps + L.ytab;
+            if (L.mode == 0)
+                k_resize<0><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
+            else if (L.mode == 1)
+                k_resize<1><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
+            else
+                k_resize<2><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
+        }
+        ++*launches;
+    }
+}

@@ -1,0 +1,173 @@
+// stereo.cu -- Frame::ComputeStereoMatches (/root/reference/src/Frame.cc:1102-1358): rectified
+// stereo association of left and right keypoints on the device-resident pyramids of the two
+// extractors (the reference reads mpORBextractor{Left,Right}->mvImagePyramid, :1249-1275).
+//
+// One warp per LEFT keypoint.  The reference's per-row candidate table (:1132-1155) is only an
+// index: right keypoint iR is a candidate of row (int)vL iff floor(yR-r) <= row <= ceil(yR+r),
+// r = 2*mvScaleFactors[octave].  The warp evaluates that predicate plus the octave and disparity
+// gates for all right keypoints (lanes stride iR), takes the Hamming minimum as a packed key
+// (dist << 16 | iR: strict `<` in ascending-iR order == lowest iR among equal distances, start
+// value TH_HIGH), then slides the 11x11 SAD window (+-5 px) with the 121 pixels spread over the
+// lanes, fits the parabola and writes mvuRight / mvDepth.  A second single-CTA kernel applies
+// the median-based outlier cut (:1343-1357) with a rank selection instead of a sort.
+#include <limits.h>
+
+#include "orbfe_internal.h"
+
+namespace {
+
+constexpr int TH_HIGH = 100, TH_LOW = 50;  // ORBmatcher.cc:36-37
+
+__global__ void __launch_bounds__(256)
+k_stereo(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL,
+         const uint8_t* __restrict__ pyrR, const OrbfeKeyPoint* __restrict__ keysL,
+         const uint32_t* __restrict__ descL, int N, const OrbfeKeyPoint* __restrict__ keysR,
+         const uint32_t* __restrict__ descR, int Nr, float mbf, float mb, float* __restrict__ uRight,
+         float* __restrict__ depth, int* __restrict__ sadOut) {
+    const int lane = threadIdx.x & 31;
+    const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (iL >= N) return;
+    if (lane == 0) { uRight[iL] = -1.0f; depth[iL] = -1.0f; sadOut[iL] = -1; }
+    const int thOrbDist = (TH_HIGH + TH_LOW) / 2;
+    const int nRows = g.lv[0].h;
+    const OrbfeKeyPoint kpL = keysL[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    const int row = (int)vL;
+    if (row < 0 || row >= nRows || levelL < 0 || levelL >= g.nlevels) return;
+    const float minZ = mb, minD = 0.f, maxD = mbf / minZ;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) return;
+    uint32_t dl[8];
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(descL + 8 * (size_t)iL);
+        *reinterpret_cast<uint4*>(dl) = p[0];
+        *reinterpret_cast<uint4*>(dl + 4) = p[1];
+    }
+    uint32_t key = (uint32_t)TH_HIGH << 16;
+    for (int iR = lane; iR < Nr; iR += 32) {
+        const OrbfeKeyPoint kpR = keysR[iR];
+        if (kpR.octave < 0 || kpR.octave >= g.nlevels) continue;
+        const float r = 2.0f * g.lv[kpR.octave].scale;
+        const int maxr = (int)ceilf(kpR.y + r), minr = (int)floorf(kpR.y - r);
+        if (row < minr || row > maxr) continue;
+        if (kpR.octave < levelL - 1 || kpR.octave > levelL + 1) continue;
+        const float uR = kpR.x;
+        if (!(uR >= minU && uR <= maxU)) continue;
+        const uint4* p = reinterpret_cast<const uint4*>(descR + 8 * (size_t)iR);
+        const uint4 a = p[0], b = p[1];
+        const int dist = __popc(dl[0] ^ a.x) + __popc(dl[1] ^ a.y) + __popc(dl[2] ^ a.z) + __popc(dl[3] ^ a.w) +
+                         __popc(dl[4] ^ b.x) + __popc(dl[5] ^ b.y) + __popc(dl[6] ^ b.z) + __popc(dl[7] ^ b.w);
+        key = min(key, ((uint32_t)dist << 16) | (uint32_t)iR);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    const int bestDist = (int)(key >> 16);
+    if (bestDist >= thOrbDist) return;
+    const int bestIdxR = (int)(key & 0xFFFFu);
+
+    // ---- sub-pixel refinement by sliding an 11x11 SAD window (:1233-1313) ----
+    const float uR0 = keysR[bestIdxR].x;
+    const float scaleFactor = g.lv[levelL].invScale;
+    const float scaleduL = roundf(kpL.x * scaleFactor);
+    const float scaledvL = roundf(kpL.y * scaleFactor);
+    const float scaleduR0 = roundf(uR0 * scaleFactor);
+    const int w = 5, Lw = 5;
+    const OrbfeLevelGeom& G = g.lv[levelL];
+    const float iniu = scaleduR0 + Lw - w;
+    const float endu = scaleduR0 + Lw + w + 1;
+    if (iniu < 0 || endu >= (float)G.w) return;
+    const int y0 = (int)(scaledvL - w), xl0 = (int)(scaleduL - w);
+    // Coordinates are ROI-relative; the 19-px border keeps small excursions inside the buffer.
+    if (y0 < -ORBFE_YOFF || y0 + 10 >= G.h + ORBFE_YOFF || xl0 < -ORBFE_EDGE || xl0 + 10 >= G.w + ORBFE_EDGE) return;
+    const uint8_t* PL = pyrL + G.off + (size_t)ORBFE_YOFF * G.pitch + ORBFE_XOFF;
+    const uint8_t* PR = pyrR + G.off + (size_t)ORBFE_YOFF * G.pitch + ORBFE_XOFF;
+    int lv[4], yy[4], xx[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int p = lane + 32 * t;
+        yy[t] = p / 11;
+        xx[t] = p - yy[t] * 11;
+        lv[t] = p < 121 ? (int)PL[(y0 + yy[t]) * G.pitch + xl0 + xx[t]] : 0;
+    }
+    int bestSad = INT_MAX, bestincR = 0;
+    float vDists[11];
+#pragma unroll
+    for (int incR = -Lw; incR <= Lw; incR++) {
+        const int xr0 = (int)(scaleduR0 + (float)incR - (float)w);
+        int sad = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int p = lane + 32 * t;
+            if (p < 121) sad += abs(lv[t] - (int)PR[(y0 + yy[t]) * G.pitch + xr0 + xx[t]]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+        const float dist = (float)sad;  // cv::norm(IL, IR, NORM_L1) on CV_8U
+        if (dist < (float)bestSad) { bestSad = (int)dist; bestincR = incR; }
+        vDists[Lw + incR] = dist;
+    }
+    if (lane != 0) return;
+    if (bestincR == -Lw || bestincR == Lw) return;
+    float dist1 = 0.f, dist2 = 0.f, dist3 = 0.f;
+#pragma unroll
+    for (int k = 1; k < 10; k++)
+        if (k == Lw + bestincR) { dist1 = vDists[k - 1]; dist2 = vDists[k]; dist3 = vDists[k + 1]; }
+    const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+    if (deltaR < -1 || deltaR > 1) return;
+    float bestuR = G.scale * ((float)scaleduR0 + (float)bestincR + deltaR);
+    float disparity = uL - bestuR;
+    if (disparity >= minD && disparity < maxD) {
+        if (disparity <= 0) {
+            disparity = 0.01f;
+            bestuR = (float)((double)uL - 0.01);
+        }
+        depth[iL] = mbf / disparity;
+        uRight[iL] = bestuR;
+        sadOut[iL] = bestSad;
+    }
+}
+
+// Median-based outlier cut (:1343-1357): median = sorted (SAD, iL) pairs [size/2].first.
+__global__ void __launch_bounds__(1024)
+k_stereo_median(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad) {
+    __shared__ int s_cnt, s_median;
+    if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
+    __syncthreads();
+    int local = 0;
+    for (int i = threadIdx.x; i < N; i += 1024) local += sad[i] >= 0;
+    atomicAdd(&s_cnt, local);
+    __syncthreads();
+    const int n = s_cnt;
+    if (n == 0) return;
+    const int k = n / 2;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const int v = sad[i];
+        if (v < 0) continue;
+        int less = 0, leq = 0;
+        for (int j = 0; j < N; j++) {
+            const int o = sad[j];
+            if (o < 0) continue;
+            less += o < v;
+            leq += o <= v;
+        }
+        if (less <= k && k < leq) s_median = v;  // all writers store the same value
+    }
+    __syncthreads();
+    const float median = (float)s_median;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = threadIdx.x; i < N; i += 1024) {
+        const int v = sad[i];
+        if (v >= 0 && !((float)v < thDist)) { uRight[i] = -1.f; depth[i] = -1.f; }
+    }
+}
+
+}  // namespace
+
+void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
+                         const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
+                         const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
+                         int* sad, cudaStream_t st) {
+    k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad);
+    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+}

@@ -1,0 +1,119 @@
+"""ctypes binding of libORBfe_b200.so (the C ABI declared in include/orbfe.h).
+
+The library is the product: if it is missing, or no CUDA device is usable, every entry point
+fails loudly -- there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libORBfe_b200.so")
+
+OK, EMPTY_IMAGE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY = 0, -1, -2, -3, -4
+NUM_STAGES = 8
+STAGE_NAMES = ("h2d", "pyramid", "fast", "octree", "layout", "blur", "describe", "d2h")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint
+assert KP_DTYPE.itemsize == 28
+
+
+class OrbfeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"orbfe error {code}: {msg}")
+        self.code = code
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("uright", C.c_void_p),
+                ("desc", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("max_x", C.c_float), ("max_y", C.c_float), ("grid_w_inv", C.c_float),
+                ("grid_h_inv", C.c_float)]
+
+
+class ProjPoints(C.Structure):
+    _fields_ = [("m", C.c_int32), ("u", C.c_void_p), ("v", C.c_void_p), ("ur", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
+                ("angle", C.c_void_p), ("valid", C.c_void_p), ("blocks", C.c_void_p),
+                ("desc", C.c_void_p)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("th_accept", C.c_int32), ("nnratio", C.c_float),
+                ("check_orientation", C.c_int32)]
+
+
+_lib = None
+
+_vp, _i, _f, _sz, _ull = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
+_SIGS = {
+    "orbfe_extractor_create": (_i, [_i, _f, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "orbfe_extractor_destroy": (None, [_vp]),
+    "orbfe_last_error": (C.c_char_p, []),
+    "orbfe_version": (C.c_char_p, []),
+    "orbfe_get_levels": (_i, [_vp]),
+    "orbfe_get_scale_factor": (_f, [_vp]),
+    "orbfe_scale_tables": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "orbfe_features_per_level": (_i, [_vp, _vp]),
+    "orbfe_max_keypoints": (_i, [_vp]),
+    "orbfe_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
+    "orbfe_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbfe_extract_batch_device": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "orbfe_level_size": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "orbfe_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz]),
+    "orbfe_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
+    "orbfe_debug_level_keypoints": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
+    "orbfe_debug_blurred": (_i, [_vp, _i, _i, _vp, _sz]),
+    "orbfe_debug_score": (_i, [_vp, _i, _i, _vp, _sz]),
+    "orbfe_debug_octree": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(_i)]),
+    "orbfe_set_profiling": (_i, [_vp, _i]),
+    "orbfe_stage_ms": (_i, [_vp, _vp]),
+    "orbfe_launch_count": (C.c_longlong, [_vp]),
+    "orbfe_set_max_bytes": (_i, [_vp, _ull]),
+    "orbfe_frame_geometry": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ull), C.POINTER(_ull)]),
+    "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i]),
+    "orbfe_knn2": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "orbfe_knn2_device": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "orbfe_knn2_merge": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "orbfe_knn2_merge_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbfe_search_by_projection": (_i, [C.POINTER(FrameView), C.POINTER(ProjPoints), C.POINTER(SearchParams),
+                                        _vp, _vp, _vp, _vp, _i]),
+    "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load libORBfe_b200.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OrbfeError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                                       "g.build()'` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError here == the ABI in include/orbfe.h is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().orbfe_last_error().decode("utf-8", "replace")
+
+
+def check(rc, allow=()):
+    if rc < 0 and rc not in allow:
+        raise OrbfeError(rc, last_error())
+    return rc
+
+
+def ptr(a):
+    """void* of a numpy array (host) or a torch tensor (device or pinned host)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())

@@ -1,0 +1,121 @@
+"""ORBmatcher: the Frame-based hot-path subset of ORB_SLAM3::ORBmatcher
+(/root/reference/include/ORBmatcher.h:33-104, src/ORBmatcher.cc) plus the two stereo associators
+of ORB_SLAM3::Frame (src/Frame.cc:1102-1358, 1530-1587), over the C ABI."""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._lib import FrameView, ProjPoints, SearchParams, check, lib, ptr
+
+MODE_MAPPOINTS, MODE_LASTFRAME, MODE_KEYFRAME = 0, 1, 2
+
+
+@dataclass
+class FrameData:
+    """The part of ORB_SLAM3::Frame the matchers read (include/Frame.h; Nleft == -1 layout)."""
+    keys: np.ndarray                    # mvKeysUn, KP_DTYPE[N]
+    desc: np.ndarray                    # mDescriptors, uint8[N,32]
+    bounds: tuple                       # (mnMinX, mnMinY, mnMaxX, mnMaxY)
+    uright: Optional[np.ndarray] = None  # mvuRight
+
+    def view(self, keep):
+        keys = np.ascontiguousarray(self.keys)
+        desc = np.ascontiguousarray(self.desc, np.uint8)
+        keep += [keys, desc]
+        fv = FrameView()
+        fv.n = len(keys)
+        fv.keys, fv.desc = keys.ctypes.data, desc.ctypes.data
+        if self.uright is not None:
+            ur = np.ascontiguousarray(self.uright, np.float32)
+            keep.append(ur)
+            fv.uright = ur.ctypes.data
+        b = [np.float32(v) for v in self.bounds]
+        fv.min_x, fv.min_y, fv.max_x, fv.max_y = b
+        # mfGridElementWidthInv / HeightInv, src/Frame.cc:303-305 (FRAME_GRID_COLS=64, ROWS=48)
+        fv.grid_w_inv = np.float32(64) / np.float32(b[2] - b[0])
+        fv.grid_h_inv = np.float32(48) / np.float32(b[3] - b[1])
+        return fv
+
+
+class ORBmatcher:
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # ORBmatcher.cc:36-38
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self.mfNNratio, self.mbCheckOrientation, self.device = float(nnratio), bool(checkOri), device
+
+    # static int DescriptorDistance(a, b), ORBmatcher.cc:2384-2404 (batched over rows)
+    @staticmethod
+    def DescriptorDistance(a, b, device=0):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.empty(len(a), np.int32)
+        check(lib().orbfe_descriptor_distance(ptr(a), ptr(b), len(a), ptr(out), device))
+        return int(out[0]) if len(out) == 1 else out
+
+    def _search(self, F, pts, mode, th_accept, claimed, assigned):
+        keep = []
+        fv = F.view(keep)
+        pp = ProjPoints()
+        m = len(pts["u"])
+        pp.m = m
+        for name, dt in [("u", np.float32), ("v", np.float32), ("ur", np.float32), ("radius", np.float32),
+                         ("min_level", np.int32), ("max_level", np.int32), ("angle", np.float32),
+                         ("valid", np.uint8), ("blocks", np.uint8), ("desc", np.uint8)]:
+            if pts.get(name) is None:
+                continue
+            a = np.ascontiguousarray(pts[name], dt)
+            keep.append(a)
+            setattr(pp, name, a.ctypes.data)
+        prm = SearchParams(mode, th_accept, self.mfNNratio, int(self.mbCheckOrientation))
+        claimed = np.ascontiguousarray(claimed, np.uint8)
+        assigned = np.ascontiguousarray(assigned, np.int32).copy()
+        bi, bd = np.empty(m, np.int32), np.empty(m, np.int32)
+        n = check(lib().orbfe_search_by_projection(C.byref(fv), C.byref(pp), C.byref(prm), ptr(claimed),
+                                                   ptr(assigned), ptr(bi), ptr(bd), self.device))
+        return n, assigned, bi, bd
+
+    # SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints), ORBmatcher.cc:46
+    def SearchByProjection(self, F, pts, claimed, assigned):
+        return self._search(F, pts, MODE_MAPPOINTS, self.TH_HIGH, claimed, assigned)
+
+    # SearchByProjection(Frame& Cur, const Frame& Last, th, bMono), ORBmatcher.cc:1951
+    def SearchByProjectionLastFrame(self, F, pts, claimed, assigned):
+        return self._search(F, pts, MODE_LASTFRAME, self.TH_HIGH, claimed, assigned)
+
+    # SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, ORBdist), ORBmatcher.cc:2197
+    def SearchByProjectionKeyFrame(self, F, pts, claimed, assigned, ORBdist):
+        return self._search(F, pts, MODE_KEYFRAME, int(ORBdist), claimed, assigned)
+
+    # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
+    def knn2(self, query, train, train_offset=0):
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+        idx, dist = np.empty((len(q), 2), np.int32), np.empty((len(q), 2), np.int32)
+        match = np.empty(len(q), np.int32)
+        check(lib().orbfe_knn2(ptr(q), len(q), ptr(t), len(t), train_offset, ptr(idx), ptr(dist), ptr(match),
+                               self.device))
+        return idx, dist, match
+
+    def knn2_merge(self, idx_shards, dist_shards):
+        idx_shards = np.ascontiguousarray(idx_shards, np.int32)
+        dist_shards = np.ascontiguousarray(dist_shards, np.int32)
+        G, nq = idx_shards.shape[:2]
+        idx, dist = np.empty((nq, 2), np.int32), np.empty((nq, 2), np.int32)
+        match = np.empty(nq, np.int32)
+        check(lib().orbfe_knn2_merge(ptr(idx_shards), ptr(dist_shards), G, nq, ptr(idx), ptr(dist), ptr(match),
+                                     self.device))
+        return idx, dist, match
+
+    # Frame::ComputeStereoMatches, Frame.cc:1102-1358
+    @staticmethod
+    def ComputeStereoMatches(exL, exR, keysL, descL, keysR, descR, mbf, mb, frame=0):
+        keysL, keysR = np.ascontiguousarray(keysL), np.ascontiguousarray(keysR)
+        descL = np.ascontiguousarray(descL, np.uint8)
+        descR = np.ascontiguousarray(descR, np.uint8)
+        ur, dp = np.empty(len(keysL), np.float32), np.empty(len(keysL), np.float32)
+        check(lib().orbfe_stereo_match(exL.handle, exR.handle, frame, ptr(keysL), ptr(descL), len(keysL), ptr(keysR),
+                                       ptr(descR), len(keysR), mbf, mb, ptr(ur), ptr(dp)))
+        return ur, dp

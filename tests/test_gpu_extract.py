@@ -1,0 +1,171 @@
+"""GPU parity: the CUDA extraction path (through the C ABI) against the CPU oracle, stage by
+stage and end to end, on the BASELINE configs' shapes.  Bit-exact everywhere (pyramid bytes, FAST
+candidate lists, retained keypoints, angles, blurred bytes, descriptors, output order)."""
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [  # (h, w, nfeatures, lapping)  -- BASELINE.json configs C1, C2, C3 (two lapping ranges), C4
+    (480, 752, 1000, (0, 1000)),
+    (480, 752, 1200, (0, 0)),
+    (512, 512, 1500, (0, 511)),
+    (512, 512, 1500, (100, 411)),
+    (720, 1280, 2000, (0, 1000)),
+]
+
+
+@pytest.fixture(scope="module")
+def orbfe():
+    import orbfe as m
+    m.lib()
+    return m
+
+
+def _check_frame(ex_gpu, ex_cpu, img, lap, stages=True):
+    mono_o, kps_o, desc_o = ex_cpu(img, lap)
+    mono_g, kps_g, desc_g = ex_gpu(img, None, lap)
+    if stages:
+        for lvl in range(ex_cpu.nlevels):
+            L = ex_cpu.level(lvl)
+            assert np.array_equal(ex_gpu.pyramid_level(lvl, with_border=True), L["padded"]), f"pyramid level {lvl}"
+            assert np.array_equal(ex_gpu.pyramid_level(lvl), L["padded"][19:-19, 19:-19])
+            cg = ex_gpu.debug_candidates(lvl)
+            assert np.array_equal(cg, L["cands"]), f"FAST candidates level {lvl}: {len(cg)} vs {len(L['cands'])}"
+            kg = ex_gpu.debug_level_keypoints(lvl)
+            ko = np.stack([L["kps"]["x"] - 16, L["kps"]["y"] - 16, L["kps"]["response"]], 1).astype(np.int32)
+            assert np.array_equal(kg, ko), f"octree level {lvl}"
+            if len(L["kps"]):
+                assert np.array_equal(ex_gpu.debug_blurred(lvl), L["blurred"]), f"blur level {lvl}"
+    assert mono_g == mono_o
+    assert len(kps_g) == len(kps_o)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kps_g[f], kps_o[f]), f
+    assert np.array_equal(kps_g["angle"].view(np.uint32), kps_o["angle"].view(np.uint32)), "angles bit-exact"
+    bad = np.flatnonzero((desc_g != desc_o).any(axis=1))
+    assert len(bad) <= 1e-3 * len(desc_o), f"{len(bad)} of {len(desc_o)} descriptors differ"
+    return len(bad)
+
+
+@pytest.mark.parametrize("h,w,nf,lap", CONFIGS)
+def test_extract_parity_stagewise(orbfe, h, w, nf, lap):
+    ex_g, ex_c = orbfe.ORBextractor(nf), O.Extractor(nf)
+    assert np.array_equal(ex_g.GetScaleFactors(), ex_c.tables()["scale"])
+    assert np.array_equal(ex_g.GetInverseScaleFactors(), ex_c.tables()["inv_scale"])
+    assert np.array_equal(ex_g.GetScaleSigmaSquares(), ex_c.tables()["sigma2"])
+    assert np.array_equal(ex_g.GetInverseScaleSigmaSquares(), ex_c.tables()["inv_sigma2"])
+    assert np.array_equal(ex_g.features_per_level(), ex_c.tables()["nfeatures"])
+    nbad = 0
+    for seed in (0, 1):
+        nbad += _check_frame(ex_g, ex_c, synth.synth_frame(h, w, seed), lap)
+    assert nbad == 0, "descriptor mismatches on these seeds would need an explanation"
+
+
+def test_noise_frames_and_odd_sizes(orbfe):
+    for (h, w, nf, seed) in [(200, 260, 300, 3), (241, 323, 50, 4), (480, 640, 3000, 5), (333, 777, 777, 6)]:
+        img = synth.noise_frame(h, w, seed) if seed % 2 else synth.synth_frame(h, w, seed)
+        _check_frame(orbfe.ORBextractor(nf), O.Extractor(nf), img, (0, 0))
+
+
+def test_other_pyramid_parameters(orbfe):
+    img = synth.synth_frame(480, 640, 9)
+    for (nf, sf, nl, ini, mn) in [(800, 2.0, 3, 20, 7), (600, 1.5, 4, 30, 10), (500, 1.1, 10, 12, 5), (400, 1.2, 1, 20, 7)]:
+        ex_g = orbfe.ORBextractor(nf, sf, nl, ini, mn)
+        ex_c = O.Extractor(nf, sf, nl, ini, mn)
+        _check_frame(ex_g, ex_c, img, (0, 0))
+
+
+def test_strided_input_and_reuse_across_sizes(orbfe):
+    ex_g, ex_c = orbfe.ORBextractor(700), O.Extractor(700)
+    big = synth.synth_frame(500, 800, 2)
+    view = big[10:490, 20:772]          # non-contiguous rows: step != cols
+    _check_frame(ex_g, ex_c, view, (0, 1000), stages=False)
+    _check_frame(ex_g, ex_c, synth.synth_frame(300, 400, 3), (0, 0), stages=False)   # same handle, new geometry
+    _check_frame(ex_g, ex_c, view, (0, 1000), stages=False)
+
+
+def test_empty_and_error_paths(orbfe):
+    ex = orbfe.ORBextractor(500)
+    mono, k, d = ex(np.zeros((0, 0), np.uint8))
+    assert mono == -1 and len(k) == 0
+    import ctypes as C
+    n = C.c_int(0)
+    rc = orbfe.lib().orbfe_extract(ex.handle, None, 0, 0, 0, 0, 0, None, None, 0, C.byref(n))
+    assert rc == orbfe.EMPTY_IMAGE                     # ORBextractor.cc:1561-1562
+    with pytest.raises(orbfe.OrbfeError):             # a level without a single 35-px FAST cell
+        ex(np.zeros((60, 60), np.uint8))
+    flat = np.full((480, 752), 97, np.uint8)           # no corners anywhere
+    mono, k, d = ex(flat)
+    assert mono == 0 and len(k) == 0 and d.shape == (0, 32)
+
+
+def test_batch_host_and_device_paths(orbfe):
+    import torch
+    nf, h, w, B = 1000, 480, 752, 6
+    frames = np.stack([synth.synth_frame(h, w, 20 + i) for i in range(B)])
+    ex_g, ex_c = orbfe.ORBextractor(nf), O.Extractor(nf)
+    ref = [ex_c(frames[i], (0, 1000)) for i in range(B)]
+    ex_g.set_max_bytes(64 << 20)                       # forces several chunks: exercises the pipeline
+    pinned = torch.from_numpy(frames).pin_memory()
+    n, mono, kps, desc = ex_g.extract_batch(pinned, (0, 1000))
+    for i in range(B):
+        assert mono[i] == ref[i][0] and n[i] == len(ref[i][1])
+        assert kps[i, :n[i]].tobytes() == ref[i][1].tobytes()
+        assert np.array_equal(desc[i, :n[i]], ref[i][2])
+    # device-resident path on a torch stream
+    ex_g.set_max_bytes(6 << 30)
+    dev = torch.device("cuda:0")
+    d_img = pinned.to(dev)
+    cap = ex_g.capacity
+    d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(B, dtype=torch.int32, device=dev)
+    d_mono = torch.empty(B, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        ex_g.extract_batch_device(d_img, (0, 1000), d_kps, d_desc, d_n, d_mono, st)
+    st.synchronize()
+    n2 = d_n.cpu().numpy()
+    k2 = d_kps.cpu().numpy().view(orbfe.KP_DTYPE).reshape(B, cap)
+    de2 = d_desc.cpu().numpy()
+    for i in range(B):
+        assert n2[i] == len(ref[i][1]) and int(d_mono[i]) == ref[i][0]
+        assert k2[i, :n2[i]].tobytes() == ref[i][1].tobytes()
+        assert np.array_equal(de2[i, :n2[i]], ref[i][2])
+    assert ex_g.launch_count() > 0
+
+
+def test_octree_kernel_alone(orbfe):
+    ex = orbfe.ORBextractor(1000)
+    for seed in range(12):
+        rng = np.random.default_rng(seed)
+        W, H = int(rng.integers(100, 1300)), int(rng.integers(100, 700))
+        if W < H // 2 + 1:
+            W = H
+        n = int(rng.integers(1, min(9000, W * H // 4)))
+        pos = rng.choice(W * H, size=n, replace=False)
+        xys = np.stack([pos % W, pos // W, rng.integers(7, 40, n)], 1).astype(np.int32)
+        xys = xys[np.lexsort((xys[:, 0], xys[:, 1]))]
+        N = int(rng.integers(1, 700))
+        assert np.array_equal(ex.debug_octree(xys, 16, 16 + W, 16, 16 + H, N), O.octree(xys, 16, 16 + W, 16, 16 + H, N))
+
+
+def test_two_instances_from_two_threads(orbfe):
+    """The reference runs the left and right extractors concurrently (Frame.cc:136-141)."""
+    import threading
+    left, right = synth.stereo_pair(480, 752, 4)
+    exs = [orbfe.ORBextractor(1200), orbfe.ORBextractor(1200)]
+    outs = [None, None]
+
+    def run(i, img):
+        for _ in range(3):
+            outs[i] = exs[i](img, None, (0, 0))
+    ts = [threading.Thread(target=run, args=(0, left)), threading.Thread(target=run, args=(1, right))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i, img in enumerate((left, right)):
+        mo, ko, do = O.Extractor(1200)(img, (0, 0))
+        assert outs[i][0] == mo and outs[i][1].tobytes() == ko.tobytes() and np.array_equal(outs[i][2], do)

@@ -1,0 +1,157 @@
+"""GPU parity of the Hamming matchers (C ABI) against the CPU oracle: DescriptorDistance, kNN-2 +
+ratio, the three SearchByProjection modes (incl. sequential claim semantics and the rotation
+histogram), rectified stereo matching with SAD sub-pixel refinement.  All outputs bit-exact."""
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def orbfe():
+    import orbfe as m
+    m.lib()
+    return m
+
+
+def test_descriptor_distance(orbfe):
+    a, b = synth.random_descriptors(5000, 1), synth.random_descriptors(5000, 2)
+    b[:10] = a[:10]
+    b[10] = ~a[10]
+    got = orbfe.ORBmatcher.DescriptorDistance(a, b)
+    exp = np.unpackbits(a ^ b, axis=1).sum(1)
+    assert np.array_equal(got, exp) and got[0] == 0 and got[10] == 256
+    assert orbfe.ORBmatcher.DescriptorDistance(a[3], b[77]) == O.hamming(a[3], b[77])
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (3, 2), (300, 1), (1500, 1500), (257, 4097), (2000, 20000), (40, 0)])
+def test_knn2_vs_oracle(orbfe, nq, nt):
+    rng = np.random.default_rng(nq * 7 + nt)
+    q, t = synth.random_descriptors(nq, nq), synth.random_descriptors(nt, nt + 1)
+    if nt > 8:
+        t[5] = t[3]                 # exact duplicates: tie -> lower train index
+        t[nt - 1] = q[0]
+        t[2] = q[0]
+        for i in range(0, min(nq, 100)):   # near matches so the ratio test fires both ways
+            t[int(rng.integers(0, nt))] = synth.flip_bits(q[i], int(rng.integers(0, 80)), rng)
+    m = orbfe.ORBmatcher()
+    idx, dist, match = m.knn2(q, t)
+    em, eidx, edist = O.fisheye_matches(q, t)
+    assert np.array_equal(idx, eidx) and np.array_equal(dist, edist) and np.array_equal(match, em)
+
+
+def test_knn2_sharded_merge_equals_whole(orbfe):
+    q, t = synth.random_descriptors(500, 3), synth.random_descriptors(30000, 4)
+    t[100] = q[7]; t[25000] = q[7]
+    m = orbfe.ORBmatcher()
+    whole = m.knn2(q, t)
+    G = 4
+    bounds = np.linspace(0, len(t), G + 1).astype(int)
+    parts = [m.knn2(q, t[bounds[g]:bounds[g + 1]], train_offset=int(bounds[g])) for g in range(G)]
+    idx, dist, match = m.knn2_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    assert np.array_equal(idx, whole[0]) and np.array_equal(dist, whole[1]) and np.array_equal(match, whole[2])
+
+
+def _pts_from_map(d, n_map, th, sf, rng, with_angle=True):
+    lvl = d["level"][:n_map]
+    r = np.where(d["view_cos"][:n_map] > 0.998, 2.5, 4.0).astype(np.float32)
+    if th != 1.0:
+        r = (r * np.float32(th)).astype(np.float32)
+    radius = (r * sf[lvl]).astype(np.float32)
+    angle = rng.uniform(0, 360, n_map)
+    src = d["src"][:n_map]
+    has = src >= 0      # true matches rotate coherently (+35 deg), so the histogram keeps most of them
+    angle[has] = (d["keys"]["angle"][src[has]] + 35.0 + rng.normal(0, 12, has.sum())) % 360.0
+    return dict(u=d["u"][:n_map], v=d["v"][:n_map], ur=(d["u"][:n_map] - 5).astype(np.float32), radius=radius,
+                min_level=(lvl - 1).astype(np.int32), max_level=lvl.astype(np.int32),
+                angle=angle.astype(np.float32),
+                valid=(rng.uniform(size=n_map) < 0.97).astype(np.uint8),
+                blocks=(rng.uniform(size=n_map) < 0.8).astype(np.uint8), desc=d["mdesc"][:n_map])
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n_map,n_frame,seed", [(3000, 800, 1), (60000, 2000, 2)])
+def test_search_by_projection(orbfe, mode, n_map, n_frame, seed):
+    d = synth.map_vs_frame(n_map, n_frame, seed)
+    rng = np.random.default_rng(seed + 50)
+    sf = d["scale_factors"]
+    pts = _pts_from_map(d, n_map, 3.0, sf, rng)
+    if mode == 1:   # last-frame search uses forward/backward octave windows
+        fw = rng.uniform(size=n_map) < 0.3
+        pts["min_level"] = np.where(fw, d["level"][:n_map], d["level"][:n_map] - 1).astype(np.int32)
+        pts["max_level"] = np.where(fw, -1, d["level"][:n_map] + 1).astype(np.int32)
+    uright = np.where(rng.uniform(size=n_frame) < 0.5, d["keys"]["x"] - 5 + rng.normal(0, 3, n_frame), -1).astype(np.float32)
+    claimed = (rng.uniform(size=n_frame) < 0.05).astype(np.uint8)
+    assigned = np.full(n_frame, -1, np.int32)
+    assigned[claimed > 0] = 10 ** 6
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], uright)
+    m = orbfe.ORBmatcher(nnratio=0.8, checkOri=True)
+    th_acc = 100 if mode < 2 else 90
+    fn = [m.SearchByProjection, m.SearchByProjectionLastFrame, lambda *a: m.SearchByProjectionKeyFrame(*a, 90)][mode]
+    n, asg, bi, bd = fn(F, pts, claimed, assigned)
+    en, easg, ebi, ebd = O.search_by_projection(d["keys"], d["fdesc"], uright, d["bounds"], pts, mode, th_acc, 0.8,
+                                                True, claimed, assigned, sf)
+    assert n == en and n > 0.2 * min(n_frame, n_map)
+    assert np.array_equal(bi, ebi) and np.array_equal(bd, ebd) and np.array_equal(asg, easg)
+
+
+def test_search_conflict_chains(orbfe):
+    """Many map points compete for few keypoints: deep claim chains must resolve like the loop."""
+    rng = np.random.default_rng(5)
+    n_frame, n_map = 40, 4000
+    d = synth.map_vs_frame(n_map, n_frame, 9, w=200, h=150)
+    base = d["fdesc"][rng.integers(0, n_frame, n_map)]
+    mdesc = np.stack([synth.flip_bits(b, int(rng.integers(0, 50)), rng) for b in base])
+    pts = dict(u=rng.uniform(0, 200, n_map).astype(np.float32), v=rng.uniform(0, 150, n_map).astype(np.float32),
+               ur=np.zeros(n_map, np.float32), radius=np.full(n_map, 60, np.float32),
+               min_level=np.zeros(n_map, np.int32), max_level=np.full(n_map, -1, np.int32),
+               angle=np.zeros(n_map, np.float32), valid=np.ones(n_map, np.uint8),
+               blocks=(rng.uniform(size=n_map) < 0.5).astype(np.uint8), desc=mdesc)
+    claimed = np.zeros(n_frame, np.uint8)
+    assigned = np.full(n_frame, -1, np.int32)
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], None)
+    m = orbfe.ORBmatcher(nnratio=0.9, checkOri=False)
+    for mode, fn in enumerate([m.SearchByProjection, m.SearchByProjectionLastFrame]):
+        n, asg, bi, bd = fn(F, pts, claimed, assigned)
+        en, easg, ebi, ebd = O.search_by_projection(d["keys"], d["fdesc"], None, d["bounds"], pts, mode, 100, 0.9,
+                                                    False, claimed, assigned, d["scale_factors"])
+        assert n == en and np.array_equal(bi, ebi) and np.array_equal(bd, ebd) and np.array_equal(asg, easg)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_stereo_matches(orbfe, seed):
+    """C2: EuRoC-shaped rectified pair, nFeatures 1200, lapping {0,0}."""
+    left, right = synth.stereo_pair(480, 752, seed)
+    gl, gr = orbfe.ORBextractor(1200), orbfe.ORBextractor(1200)
+    cl, cr = O.Extractor(1200), O.Extractor(1200)
+    _, kl, dl = gl(left, None, (0, 0))
+    _, kr, dr = gr(right, None, (0, 0))
+    _, okl, odl = cl(left, (0, 0))
+    _, okr, odr = cr(right, (0, 0))
+    assert kl.tobytes() == okl.tobytes() and kr.tobytes() == okr.tobytes()
+    mbf, fx = 47.90639384423901, 435.2046959714599
+    mb = mbf / fx
+    ur, dp = orbfe.ORBmatcher.ComputeStereoMatches(gl, gr, kl, dl, kr, dr, mbf, mb)
+    eur, edp = O.stereo_match(cl, cr, okl, odl, okr, odr, mbf, mb)
+    assert (eur > 0).sum() > 200
+    assert np.array_equal(ur.view(np.uint32), eur.view(np.uint32))
+    assert np.array_equal(dp.view(np.uint32), edp.view(np.uint32))
+
+
+def test_fisheye_stereo_c3(orbfe):
+    """C3: 512x512 pair, nFeatures 1500, lapping area {0,511}: kNN-2 + 0.7 ratio on the stereo halves."""
+    a, b = synth.shifted_pair(512, 512, 3)
+    ga, gb = orbfe.ORBextractor(1500), orbfe.ORBextractor(1500)
+    ma, ka, da = ga(a, None, (0, 511))
+    mb_, kb, db = gb(b, None, (0, 511))
+    oa = O.Extractor(1500)(a, (0, 511))
+    ob = O.Extractor(1500)(b, (0, 511))
+    assert ma == oa[0] and mb_ == ob[0] and np.array_equal(da, oa[2]) and np.array_equal(db, ob[2])
+    m = orbfe.ORBmatcher()
+    idx, dist, match = m.knn2(da[ma:], db[mb_:])       # Frame.cc:1534-1553
+    em, eidx, edist = O.fisheye_matches(oa[2][oa[0]:], ob[2][ob[0]:])
+    assert np.array_equal(match, em) and np.array_equal(idx, eidx) and np.array_equal(dist, edist)
+    assert (match >= 0).sum() > 100
