@@ -5,6 +5,19 @@
 // ring = Bresenham circle r=3, corner at threshold t  <=>  best > t, response = best-1, with
 //   best = max over the 16 arcs of 9 contiguous ring pixels of
 //          max( min(centre - ring), min(ring - centre) ).
+//
+// Two pixels are processed per 32-bit register as 16-bit lanes (Blackwell has native 2- and
+// 3-input packed min/max: VIMNMX.U16x2 / VIMNMX3.U16x2).  Differences are kept BIASED,
+//   e_k = centre + 256 - ring_k  in [1, 511]  per lane,
+// so one plain 32-bit subtract serves both lanes (no borrow can cross) and unsigned packed
+// min/max order them like the signed differences.  With the 3-wise sliding scheme
+//   m3_k = min(e_k, e_k+1, e_k+2),  min9_k = min(m3_k, m3_k+3, m3_k+6)
+// an arc minimum costs two 3-input ops.  best = max(0, max_k min9_k - 256, 256 - min_k max9_k).
+//
+// NOTE (measured on B200, nvcc 12.9): a formulation that folds `max(best, -mx)` into the running
+// maximum is MISCOMPILED for sm_100a (ptxas drops the negation when it fuses into VIMNMX3); this
+// formulation negates once, outside the min/max network, and is checked on the device against
+// the CPU oracle by tests/test_gpu_extract.py.
 #pragma once
 #include <stdint.h>
 
@@ -18,52 +31,67 @@
 #define FC_RING_DX(k) ((k) == 0 ? 0 : (k) == 1 ? 1 : (k) == 2 ? 2 : (k) == 3 ? 3 : (k) == 4 ? 3 : (k) == 5 ? 3 : (k) == 6 ? 2 : (k) == 7 ? 1 : (k) == 8 ? 0 : (k) == 9 ? -1 : (k) == 10 ? -2 : (k) == 11 ? -3 : (k) == 12 ? -3 : (k) == 13 ? -3 : (k) == 14 ? -2 : -1)
 #define FC_RING_DY(k) ((k) == 0 ? 3 : (k) == 1 ? 3 : (k) == 2 ? 2 : (k) == 3 ? 1 : (k) == 4 ? 0 : (k) == 5 ? -1 : (k) == 6 ? -2 : (k) == 7 ? -3 : (k) == 8 ? -3 : (k) == 9 ? -3 : (k) == 10 ? -2 : (k) == 11 ? -1 : (k) == 12 ? 0 : (k) == 13 ? 1 : (k) == 14 ? 2 : 3)
 
-static FC_HD int fc_min(int a, int b) { return a < b ? a : b; }
-static FC_HD int fc_max(int a, int b) { return a > b ? a : b; }
+// ---- packed 16-bit lane helpers (device: DPX/video instructions; host: emulation) ----------
+#if defined(__CUDA_ARCH__)
+static __device__ __forceinline__ uint32_t fc_min3u(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+static __device__ __forceinline__ uint32_t fc_max3u(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+static __device__ __forceinline__ uint32_t fc_minu(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+static __device__ __forceinline__ uint32_t fc_maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+static __device__ __forceinline__ uint32_t fc_add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+static __device__ __forceinline__ uint32_t fc_sub2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+static __device__ __forceinline__ uint32_t fc_max3s_relu(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2_relu(a, b, c); }
+#else
+#define FC_LANES(expr_lo, expr_hi) (((uint32_t)(uint16_t)(expr_lo)) | ((uint32_t)(uint16_t)(expr_hi) << 16))
+static inline uint32_t fc_lo(uint32_t a) { return a & 0xFFFFu; }
+static inline uint32_t fc_hi(uint32_t a) { return a >> 16; }
+static inline uint32_t fc_mn(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t fc_mx(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t fc_minu(uint32_t a, uint32_t b) { return FC_LANES(fc_mn(fc_lo(a), fc_lo(b)), fc_mn(fc_hi(a), fc_hi(b))); }
+static inline uint32_t fc_maxu(uint32_t a, uint32_t b) { return FC_LANES(fc_mx(fc_lo(a), fc_lo(b)), fc_mx(fc_hi(a), fc_hi(b))); }
+static inline uint32_t fc_min3u(uint32_t a, uint32_t b, uint32_t c) { return fc_minu(fc_minu(a, b), c); }
+static inline uint32_t fc_max3u(uint32_t a, uint32_t b, uint32_t c) { return fc_maxu(fc_maxu(a, b), c); }
+static inline uint32_t fc_add2(uint32_t a, uint32_t b) { return FC_LANES(fc_lo(a) + fc_lo(b), fc_hi(a) + fc_hi(b)); }
+static inline uint32_t fc_sub2(uint32_t a, uint32_t b) { return FC_LANES(fc_lo(a) - fc_lo(b), fc_hi(a) - fc_hi(b)); }
+static inline int fc_s16(uint32_t v) { return (int)(int16_t)(uint16_t)v; }
+static inline int fc_mx3s0(int a, int b, int c) { int m = a > b ? a : b; m = m > c ? m : c; return m > 0 ? m : 0; }
+static inline uint32_t fc_max3s_relu(uint32_t a, uint32_t b, uint32_t c) {
+    return FC_LANES(fc_mx3s0(fc_s16(fc_lo(a)), fc_s16(fc_lo(b)), fc_s16(fc_lo(c))),
+                    fc_mx3s0(fc_s16(fc_hi(a)), fc_s16(fc_hi(b)), fc_s16(fc_hi(c))));
+}
+#endif
 
-// Quick reject (OpenCV's pair test): a 9-arc contains one pixel of every opposite ring pair,
-// so each pair needs a member darker than v-t (bit 0) or brighter than v+t (bit 1).
-template <int PITCH>
-static FC_HD bool fc_may_be_corner(const uint8_t* p, int th) {
-    const int v = p[0], lo = v - th, hi = v + th;
-    int d = 3;
+#define FC_BIAS2 0x01000100u  // +256 in both lanes
+
+// e[k] = biased packed differences (centre + 256 - ring_k per lane), k = 0..15 in ring order.
+// Returns per lane  max(best - sub, 0)  where `sub2` holds `sub` in both lanes (sub = minThFAST:
+// the score map stores the margin over the low threshold, 0 = "not a corner at minThFAST").
+static FC_HD uint32_t fc_margin2(const uint32_t* e, uint32_t sub2) {
+    uint32_t mn3[16], mx3[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        // visit the pairs in OpenCV's order 0,4,2,6,1,3,5,7 so flat regions exit early
-        const int kk = (k == 0) ? 0 : (k == 1) ? 4 : (k == 2) ? 2 : (k == 3) ? 6 : (k == 4) ? 1 : (k == 5) ? 3 : (k == 6) ? 5 : 7;
-        const int a = p[FC_RING_DX(kk) + FC_RING_DY(kk) * PITCH];
-        const int b = p[FC_RING_DX(kk + 8) + FC_RING_DY(kk + 8) * PITCH];
-        d &= ((a < lo ? 1 : 0) | (a > hi ? 2 : 0)) | ((b < lo ? 1 : 0) | (b > hi ? 2 : 0));
-        if (d == 0) return false;
+    for (int k = 0; k < 16; k++) {
+        mn3[k] = fc_min3u(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        mx3[k] = fc_max3u(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
     }
-    return true;
+    uint32_t A = 0u, B = 0xFFFFFFFFu;  // max_k min9_k, min_k max9_k (biased, unsigned lanes)
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        A = fc_maxu(A, fc_min3u(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+        B = fc_minu(B, fc_max3u(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+    }
+    // best = max(0, A-256, 256-B); margin = max(0, best - sub)
+    const uint32_t a = fc_sub2(A, fc_add2(FC_BIAS2, sub2));
+    const uint32_t b = fc_sub2(fc_sub2(FC_BIAS2, sub2), B);
+    return fc_max3s_relu(a, b, 0u);
 }
 
-// best (see header comment); sliding 9-window min / max over the circular 16-ring by doubling.
+// Scalar convenience (host tests, small kernels): best of one pixel of a byte image.
 template <int PITCH>
-static FC_HD int fc_arc_best(const uint8_t* p) {
-    int d[16];
-    const int v = p[0];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - (int)p[FC_RING_DX(k) + FC_RING_DY(k) * PITCH];
-    int mn2[16], mx2[16];
+static FC_HD int fc_best_scalar(const uint8_t* p) {
+    uint32_t e[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn2[k] = fc_min(d[k], d[(k + 1) & 15]);
-        mx2[k] = fc_max(d[k], d[(k + 1) & 15]);
+        const uint32_t r = p[FC_RING_DX(k) + FC_RING_DY(k) * PITCH];
+        e[k] = ((uint32_t)p[0] + 256u - r) * 0x00010001u;
     }
-    int mn4[16], mx4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mn4[k] = fc_min(mn2[k], mn2[(k + 2) & 15]);
-        mx4[k] = fc_max(mx2[k], mx2[(k + 2) & 15]);
-    }
-    int best = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int mn9 = fc_min(fc_min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = fc_max(fc_max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = fc_max(best, fc_max(mn9, -mx9));
-    }
-    return best;
+    return (int)(fc_margin2(e, 0u) & 0xFFFFu);
 }

@@ -117,13 +117,17 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
         L.h = cv_round((float)rows * sc);
         L.maxBX = L.w - ORBFE_FAST_BORDER;  // :1076-1079
         L.maxBY = L.h - ORBFE_FAST_BORDER;
+        if (L.w < 1 || L.h < 1) return fail(ORBFE_ERR_INVALID, "image too small for nlevels (a pyramid level is empty)");
         const float width = (float)(L.maxBX - ORBFE_FAST_BORDER), height = (float)(L.maxBY - ORBFE_FAST_BORDER);
-        if (width < 35.f || height < 35.f)
-            return fail(ORBFE_ERR_INVALID, "image too small for nlevels (a level has no 35-px FAST cell)");
-        L.nCols = (int)(width / 35.f);  // :1087-1095
-        L.nRows = (int)(height / 35.f);
-        L.wCell = (int)ceilf(width / L.nCols);
-        L.hCell = (int)ceilf(height / L.nRows);
+        if (width <= 0.f || height <= 0.f)
+            return fail(ORBFE_ERR_INVALID, "a pyramid level is smaller than the 16-px FAST border (the reference aborts there)");
+        // A level narrower than one 35-px cell has nCols or nRows == 0 in the reference: its cell
+        // loops do not run and the level simply yields no keypoints (:1087-1098).
+        const bool hasCells = width >= 35.f && height >= 35.f;
+        L.nCols = hasCells ? (int)(width / 35.f) : 0;  // :1087-1095
+        L.nRows = hasCells ? (int)(height / 35.f) : 0;
+        L.wCell = hasCells ? (int)ceilf(width / L.nCols) : 0;
+        L.hCell = hasCells ? (int)ceilf(height / L.nRows) : 0;
         L.pitch = (int)align_up(ORBFE_XOFF + L.w + ORBFE_EDGE, 16);
         L.off = (unsigned)off;
         off += align_up((size_t)L.pitch * (L.h + 2 * ORBFE_YOFF), 256);
@@ -134,9 +138,9 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
         L.candCap = L.nCols * L.nRows * L.cellCap;
         slot += (unsigned)L.candCap;
         L.nfeat = e->nfeat[l];
-        L.nIni = (int)roundf(width / (float)(L.maxBY - ORBFE_FAST_BORDER));  // :718
+        L.nIni = hasCells ? (int)roundf(width / (float)(L.maxBY - ORBFE_FAST_BORDER)) : 1;  // :718
         if (L.nIni < 1) return fail(ORBFE_ERR_INVALID, "aspect ratio < 0.5 (the reference divides by zero)");
-        L.hX = width / L.nIni;
+        L.hX = hasCells ? width / L.nIni : 1.f;
         L.ocM = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
         L.kpBase = kpBase;
         L.kpCap = L.ocM;
@@ -158,8 +162,8 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
             tapOff += (unsigned)(L.w + L.h);
         }
         L.fastTileBase = fastTile;
-        L.fastTilesX = (L.w - 38 + ORBFE_FAST_TW - 1) / ORBFE_FAST_TW;
-        L.fastTilesY = (L.h - 38 + ORBFE_FAST_TH - 1) / ORBFE_FAST_TH;
+        L.fastTilesX = hasCells ? (L.w - 38 + ORBFE_FAST_TW - 1) / ORBFE_FAST_TW : 0;
+        L.fastTilesY = hasCells ? (L.h - 38 + ORBFE_FAST_TH - 1) / ORBFE_FAST_TH : 0;
         fastTile += L.fastTilesX * L.fastTilesY;
         L.blurTileBase = blurTile;
         L.blurTilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;
@@ -232,7 +236,7 @@ int chunk_frames(const OrbfeExtractor* e, int B) {
 }
 
 void stage_mark(OrbfeExtractor* e, int i, cudaStream_t st) {
-    if (e->profiling) cudaEventRecord(e->evStage[i], st);
+    if (e->profiling) cudaEventRecord(e->evStage[e->profCount % OrbfeExtractor::kProfSets][i], st);
 }
 
 // Enqueue the whole extraction of `B` (<= chunkCap) frames on `st`.
@@ -243,16 +247,19 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
     stage_mark(e, 1, st);
     orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, e->bufs, B, st, &e->launches);
     stage_mark(e, 2, st);
-    orbfe_launch_fast(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_fast_score(g, e->bufs, B, st, &e->launches);
     stage_mark(e, 3, st);
-    orbfe_launch_octree(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_fast_cells(g, e->bufs, B, st, &e->launches);
     stage_mark(e, 4, st);
-    orbfe_launch_layout(g, e->bufs, B, lap0, lap1, d_kps, capacity, d_n, d_mono, st, &e->launches);
+    orbfe_launch_octree(g, e->bufs, B, st, &e->launches);
     stage_mark(e, 5, st);
-    orbfe_launch_blur(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_layout(g, e->bufs, B, lap0, lap1, d_kps, capacity, d_n, d_mono, st, &e->launches);
     stage_mark(e, 6, st);
-    orbfe_launch_describe(g, e->bufs, B, d_kps, d_desc, capacity, st, &e->launches);
+    orbfe_launch_blur(g, e->bufs, B, st, &e->launches);
     stage_mark(e, 7, st);
+    orbfe_launch_describe(g, e->bufs, B, d_kps, d_desc, capacity, st, &e->launches);
+    stage_mark(e, 8, st);
+    if (e->profiling) e->profCount++;
     e->lastFrames = B;
 }
 
@@ -331,7 +338,8 @@ int orbfe_extractor_create(int nfeatures, float scaleFactor, int nlevels, int in
         if (er == cudaSuccess) er = cudaEventCreateWithFlags(&e->evDone[s], cudaEventDisableTiming);
         if (er == cudaSuccess) er = cudaEventCreateWithFlags(&e->evOutFree[s], cudaEventDisableTiming);
     }
-    for (int i = 0; i <= ORBFE_NUM_STAGES && er == cudaSuccess; i++) er = cudaEventCreate(&e->evStage[i]);
+    for (int k = 0; k < OrbfeExtractor::kProfSets && er == cudaSuccess; k++)
+        for (int i = 0; i <= ORBFE_NUM_STAGES && er == cudaSuccess; i++) er = cudaEventCreate(&e->evStage[k][i]);
     if (er != cudaSuccess) {
         orbfe_extractor_destroy(e);
         return fail(ORBFE_ERR_CUDA, "stream/event creation", er);
@@ -359,8 +367,9 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
         if (e->evDone[s]) cudaEventDestroy(e->evDone[s]);
         if (e->evOutFree[s]) cudaEventDestroy(e->evOutFree[s]);
     }
-    for (int i = 0; i <= ORBFE_NUM_STAGES; i++)
-        if (e->evStage[i]) cudaEventDestroy(e->evStage[i]);
+    for (int k = 0; k < OrbfeExtractor::kProfSets; k++)
+        for (int i = 0; i <= ORBFE_NUM_STAGES; i++)
+            if (e->evStage[k][i]) cudaEventDestroy(e->evStage[k][i]);
     if (e->sCompute) cudaStreamDestroy(e->sCompute);
     if (e->sH2D) cudaStreamDestroy(e->sH2D);
     if (e->sD2H) cudaStreamDestroy(e->sD2H);
@@ -426,7 +435,6 @@ int orbfe_extract_batch_device(OrbfeExtractor* h, const uint8_t* d_images, int B
                       d_keypoints + (size_t)b0 * capacity, d_descriptors + (size_t)b0 * capacity * 32,
                       capacity, d_n_out + b0, d_mono_out + b0, st);
     }
-    h->stagesPending = h->profiling;
     CK(cudaGetLastError());
     return ORBFE_OK;
 }
@@ -450,7 +458,6 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         const int nb = std::min(chunk, B - b0), s = ci & 1;
         // H2D of this chunk overlaps the kernels of the previous one
         if (ci >= 2) CK(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
-        if (h->profiling && b0 + nb >= B) cudaEventRecord(h->evStage[0], h->sH2D);
         const uint8_t* src = images + (size_t)b0 * frame_stride;
         if (packed) {
             CK(cudaMemcpyAsync(h->d_in[s], src, fbytes * nb, cudaMemcpyHostToDevice, h->sH2D));
@@ -462,11 +469,8 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         CK(cudaEventRecord(h->evIn[s], h->sH2D));
         CK(cudaStreamWaitEvent(h->sCompute, h->evIn[s], 0));
         if (ci >= 2) CK(cudaStreamWaitEvent(h->sCompute, h->evOutFree[s], 0));
-        const bool prof = h->profiling;
-        if (prof && b0 + nb < B) h->profiling = false;  // stage events describe the last chunk only
         enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
                       h->d_on[s], h->d_omono[s], h->sCompute);
-        h->profiling = prof;
         CK(cudaEventRecord(h->evInFree[s], h->sCompute));
         CK(cudaEventRecord(h->evDone[s], h->sCompute));
         CK(cudaStreamWaitEvent(h->sD2H, h->evDone[s], 0));
@@ -476,13 +480,11 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
                            cudaMemcpyDeviceToHost, h->sD2H));
         CK(cudaMemcpyAsync(n_out + b0, h->d_on[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
         CK(cudaMemcpyAsync(mono_out + b0, h->d_omono[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
-        if (h->profiling && b0 + nb >= B) cudaEventRecord(h->evStage[8], h->sD2H);
         CK(cudaEventRecord(h->evOutFree[s], h->sD2H));
     }
     CK(cudaStreamSynchronize(h->sD2H));
     CK(cudaStreamSynchronize(h->sCompute));
     CK(cudaGetLastError());
-    h->stagesPending = h->profiling;
     for (int b = 0; b < B; b++)
         if (n_out[b] > capacity) return fail(ORBFE_ERR_CAPACITY, "capacity smaller than the keypoint count (see orbfe_max_keypoints)");
     return ORBFE_OK;
@@ -538,7 +540,13 @@ int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, s
 int orbfe_debug_score(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step) {
     int rc = tap_check(h, frame, level);
     if (rc) return rc;
-    return copy_level(h, h->bufs.score, frame, level, 0, dst, dst_step);
+    // only the FAST domain [19,w-19) x [19,h-19) of the score map is ever written
+    const OrbfeLevelGeom& L = h->g.lv[level];
+    for (int y = 0; y < L.h; y++) memset(dst + (size_t)y * dst_step, 0, L.w);
+    const uint8_t* base = h->bufs.score + (size_t)frame * h->g.pyrStride + L.off;
+    CK(cudaMemcpy2D(dst + 19 * dst_step + 19, dst_step, base + (size_t)(ORBFE_YOFF + 19) * L.pitch + ORBFE_SXOFF + 19,
+                    L.pitch, L.w - 38, L.h - 38, cudaMemcpyDeviceToHost));
+    return ORBFE_OK;
 }
 
 int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys, int capacity, int* n_out) {
@@ -616,20 +624,28 @@ int orbfe_debug_octree(OrbfeExtractor* h, const int32_t* xys, int n, int minX, i
 int orbfe_set_profiling(OrbfeExtractor* h, int enable) {
     if (!h) return fail(ORBFE_ERR_INVALID, "null extractor");
     h->profiling = enable != 0;
+    h->profCount = 0;
     return ORBFE_OK;
 }
 
+// Mean per-kernel milliseconds over the chunks enqueued since orbfe_set_profiling(h, 1) (at most
+// the last 64), CUDA events recorded on the launching stream around every kernel.
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms) {
     int rc = check_handle(h);
     if (rc) return rc;
     if (!ms) return fail(ORBFE_ERR_INVALID, "null ms");
     for (int i = 0; i < ORBFE_NUM_STAGES; i++) ms[i] = 0.f;
-    if (!h->stagesPending) return fail(ORBFE_ERR_INVALID, "profiling was not enabled for the last call");
-    CK(cudaStreamSynchronize(h->sCompute));
-    // stage i (1..6) spans evStage[i]..evStage[i+1] on the compute stream; h2d/d2h are not timed
-    // per stage here (they overlap the kernels of neighbouring chunks).
-    for (int i = 1; i <= 6; i++) CK(cudaEventElapsedTime(&ms[i], h->evStage[i], h->evStage[i + 1]));
-    return ORBFE_OK;
+    const int sets = std::min(h->profCount, (int)OrbfeExtractor::kProfSets);
+    if (!h->profiling || sets == 0) return fail(ORBFE_ERR_INVALID, "no profiled call since orbfe_set_profiling(h, 1)");
+    for (int k = 0; k < sets; k++) {
+        CK(cudaEventSynchronize(h->evStage[k][8]));
+        for (int i = 1; i <= 7; i++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, h->evStage[k][i], h->evStage[k][i + 1]));
+            ms[i] += t / sets;
+        }
+    }
+    return sets;
 }
 
 long long orbfe_launch_count(const OrbfeExtractor* h) { return h ? h->launches : 0; }

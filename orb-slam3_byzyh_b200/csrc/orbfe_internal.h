@@ -10,6 +10,7 @@
 
 #define ORBFE_XOFF 32  // column of the ROI origin inside a padded row (keeps ROI rows 16B aligned)
 #define ORBFE_YOFF 19  // row of the ROI origin (EDGE_THRESHOLD)
+#define ORBFE_SXOFF 13 // score map only: column of ROI x=0 (FAST domain x=19 lands on column 32)
 #define ORBFE_FAST_BORDER 16  // minBorderX/Y = EDGE_THRESHOLD-3, ORBextractor.cc:1076-1079
 #define ORBFE_HALF_PATCH 15   // HALF_PATCH_SIZE, ORBextractor.cc:77
 
@@ -70,7 +71,7 @@ struct OrbfeWork {
     float angle;       // degrees
 };
 
-#define ORBFE_FAST_TW 64
+#define ORBFE_FAST_TW 128
 #define ORBFE_FAST_TH 16
 #define ORBFE_BLUR_TW 64
 #define ORBFE_BLUR_TH 16
@@ -79,7 +80,7 @@ struct OrbfeWork {
 struct OrbfeChunkBufs {
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
-    uint8_t* score;      // [B][pyrStride]  FAST arc score ("best", 0 when <= minTh)
+    uint8_t* score;      // [B][pyrStride]  FAST margin max(best - minThFAST, 0), column = ROI x + ORBFE_SXOFF
     uint32_t* slots;     // [B][slotsPerFrame] per-cell candidate slots (packed)
     int* cellCount;      // [B][cellsPerFrame]
     uint32_t* cand;      // [B][slotsPerFrame] per-level compacted candidates (emission order)
@@ -99,8 +100,10 @@ int orbfe_fail(int code, const char* what, cudaError_t e);
 void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
                           size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
                           cudaStream_t st, long long* launches);
-void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
-                       long long* launches);
+void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                             long long* launches);
+void orbfe_launch_fast_cells(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                             long long* launches);
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches);
 void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
@@ -146,9 +149,10 @@ struct OrbfeExtractor {
     cudaStream_t sCompute = nullptr, sH2D = nullptr, sD2H = nullptr;
     cudaEvent_t evIn[2] = {}, evInFree[2] = {}, evDone[2] = {}, evOutFree[2] = {};
     bool profiling = false;
-    cudaEvent_t evStage[ORBFE_NUM_STAGES + 1] = {};
-    float stageMs[ORBFE_NUM_STAGES] = {};
-    bool stagesPending = false;
+    // per-kernel timing: a ring of event sets, one set per enqueued chunk while profiling is on
+    static const int kProfSets = 64;
+    cudaEvent_t evStage[kProfSets][ORBFE_NUM_STAGES + 1] = {};
+    int profCount = 0;      // chunks recorded since profiling was switched on
     int lastFrames = 0;
     long long launches = 0;
     size_t maxBytes = (size_t)6 << 30;

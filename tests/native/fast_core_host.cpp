@@ -1,0 +1,26 @@
+// tests/native/fast_core_host.cpp -- compiles the product's packed FAST-9/16 arithmetic
+// (orb-slam3_byzyh_b200/csrc/fast_core.h) for the host (lane emulation) so it can be unit-tested
+// on CPU against the oracle's plain restatement.  A test of product logic, not a CPU path.
+#include <cstdint>
+
+#include "../../orb-slam3_byzyh_b200/csrc/fast_core.h"
+
+// img: h x w bytes.  out[y*w+x] = margin max(best - sub, 0) for interior pixels, two pixels per call.
+extern "C" void fast_core_margins(const uint8_t* img, int w, int h, int sub, uint8_t* out) {
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x + 1 < w - 3; x += 2) {
+            const uint8_t* p = img + y * w + x;
+            uint32_t e[16];
+            const uint32_t c = ((uint32_t)p[0] | ((uint32_t)p[1] << 16)) + FC_BIAS2;
+            for (int k = 0; k < 16; k++) {
+                const uint8_t* q = p + dx[k] + dy[k] * w;
+                e[k] = c - ((uint32_t)q[0] | ((uint32_t)q[1] << 16));
+            }
+            const uint32_t m = fc_margin2(e, (uint32_t)sub * 0x00010001u);
+            out[y * w + x] = (uint8_t)(m & 0xFFFF);
+            out[y * w + x + 1] = (uint8_t)(m >> 16);
+        }
+}
+extern "C" int fast_core_best_scalar72(const uint8_t* p) { return fc_best_scalar<72>(p); }

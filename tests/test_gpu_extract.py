@@ -95,8 +95,13 @@ def test_empty_and_error_paths(orbfe):
     n = C.c_int(0)
     rc = orbfe.lib().orbfe_extract(ex.handle, None, 0, 0, 0, 0, 0, None, None, 0, C.byref(n))
     assert rc == orbfe.EMPTY_IMAGE                     # ORBextractor.cc:1561-1562
-    with pytest.raises(orbfe.OrbfeError):             # a level without a single 35-px FAST cell
-        ex(np.zeros((60, 60), np.uint8))
+    for shape in [(2, 2), (90, 120)]:                  # a level smaller than the 16-px border window:
+        with pytest.raises(orbfe.OrbfeError):          # the reference itself aborts there (negative nIni)
+            ex(np.zeros(shape, np.uint8))
+    tiny = synth.noise_frame(150, 200, 1)              # top levels have no 35-px FAST cell: no keypoints there
+    mo, ko, do = O.Extractor(500)(tiny, (0, 0))
+    mg, kg, dg = ex(tiny, None, (0, 0))
+    assert mg == mo and kg.tobytes() == ko.tobytes() and np.array_equal(dg, do) and len(kg) > 20
     flat = np.full((480, 752), 97, np.uint8)           # no corners anywhere
     mono, k, d = ex(flat)
     assert mono == 0 and len(k) == 0 and d.shape == (0, 32)
