@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- ORB extraction frames/s (752x480, 1000 kp, 8 levels) and Hamming matches/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the ORB front-end over a batch of synthetic 752x480 frames per GPU
+(EuRoC mono settings: nFeatures 1000, scaleFactor 1.2, 8 levels, FAST 20/7, lapping {0,1000}).
+  value : frames/s with the batch resident in HBM (orbfe_extract_batch_device on a CUDA stream,
+          CUDA events on that stream, max over ranks).
+  e2e   : frames/s through the host-pointer C-ABI call orbfe_extract_batch (pinned host frames
+          in, keypoints + descriptors out; H2D/D2H copies inside the timed region).
+Frames shard over ranks with no collective (weak scaling).  The matching leg (C5: 2000 frame
+descriptors vs a 1 M descriptor map, sharded over ranks, NCCL all-gather of the per-shard best
+two + merge) is reported in the same JSON line under "matching".
+--impl reference times the reference's own CPU ORBextractor (oracle/_ref, its ORBextractor.cc
+compiled verbatim; falls back to the oracle port) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "orb-slam3_byzyh_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H, W, NF = 480, 752, 1000
+LAP = (0, 1000)
+METRIC = "ORB extract frames/s (752x480,1000kp,8lvl)"
+
+
+def make_frames(n, seed0=7, nbase=12):
+    """n distinct 752x480 frames: `nbase` synthetic scenes (tests/synth.py), the rest are
+    translated / mirrored variants (different pixel content per frame, same statistics)."""
+    import synth
+    base = [synth.synth_frame(H, W, seed0 + i) for i in range(min(nbase, n))]
+    rng = np.random.default_rng(seed0)
+    out = np.empty((n, H, W), np.uint8)
+    for i in range(n):
+        f = base[i % len(base)]
+        if i >= len(base):
+            f = np.roll(f, (int(rng.integers(1, H)), int(rng.integers(1, W))), axis=(0, 1))
+            if rng.uniform() < 0.5:
+                f = f[:, ::-1]
+        out[i] = f
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(frames_per_thread, threads, frames):
+    """Times the reference CPU ORBextractor (one instance per thread, as Frame.cc:136-141 does for
+    stereo) on `threads` host threads.  Returns (frames/s, kind)."""
+    try:
+        from oracle import ref as R
+        if R.available():
+            R.lib()
+            mk, kind = (lambda: R.RefExtractor(NF)), "reference"
+        else:
+            raise RuntimeError
+    except Exception:
+        from oracle import oracle as O
+        O.lib()
+        mk, kind = (lambda: O.Extractor(NF)), "port"
+    exs = [mk() for _ in range(threads)]
+
+    def work(t):
+        for i in range(frames_per_thread):
+            exs[t](frames[(t * frames_per_thread + i) % len(frames)], LAP)   # ctypes releases the GIL
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    return threads * frames_per_thread / dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = make_frames(16)
+    one, kind = cpu_reference_run(1, 1, frames)                 # calibrate: single-thread frames/s
+    per = int(max(2, min(64, round(8.0 * one))))                # ~8 s of CPU work per thread and step
+    for _ in range(args.warmup):
+        cpu_reference_run(1, cores, frames)
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        cpu_reference_run(per, cores, frames)
+        tot += per * cores
+    dt = time.perf_counter() - t0
+    v = tot / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C1 752x480 nFeatures=1000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}",
+                   "frames_per_step": per * cores},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": f"{per} frames per thread x {cores} threads per step, one ORBextractor per thread"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import orbfe
+    from orbfe import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    orbfe.lib()
+    B = args.frames
+    frames = make_frames(B, seed0=7 + 1000 * rank)
+    pinned = torch.from_numpy(frames).pin_memory()
+    ex = orbfe.ORBextractor(NF, 1.2, 8, 20, 7, device=local)
+    cap = ex.capacity
+    ex.set_max_bytes(64 << 30)                        # one chunk: the whole batch per launch set
+    d_img = pinned.to(dev)
+    d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(B, dtype=torch.int32, device=dev)
+    d_mono = torch.empty(B, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+
+    def step_device():
+        ex.extract_batch_device(d_img, LAP, d_kps, d_desc, d_n, d_mono, st)
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    st.synchronize()
+    geo = ex.frame_geometry()
+    n_kp = d_n.cpu().numpy().astype(np.int64)
+    cands = sum(len(ex.debug_candidates(l, frame=0)) for l in range(8))
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ex.set_profiling(True)
+    l0 = ex.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(st)
+    st.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ex.launch_count() - l0
+    stage = ex.stage_ms()
+    ex.set_profiling(False)
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the host-pointer C ABI (e2e) ----
+    ex.set_max_bytes(int(geo["per_frame_bytes"]) * args.chunk)   # pipeline H2D / kernels / D2H per chunk
+    out = (torch.empty(B, dtype=torch.int32).pin_memory().numpy(), torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+           torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory().numpy().view(_lib.KP_DTYPE).reshape(B, cap),
+           torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory().numpy())
+    for _ in range(2):
+        ex.extract_batch(pinned, LAP, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ex.extract_batch(pinned, LAP, out=out)        # synchronous: returns with results in host memory
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    e2e_ms = max_over_ranks(dt * 1e3)
+    e2e = world * B * args.steps / (e2e_ms / 1e3)
+    assert np.array_equal(out[0].astype(np.int64), n_kp), "host and device paths disagree"
+    h2d = B * H * W
+    d2h = B * (cap * 28 + cap * 32 + 8)
+
+    # ---- matching leg: 2000 frame descriptors vs 1 M map descriptors, map sharded over ranks ----
+    matching = None
+    if not args.no_match:
+        nq, nmap = 2000, 1000000
+        rng = np.random.default_rng(5)
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        lo, hi = rank * nmap // world, (rank + 1) * nmap // world
+        shard = np.random.default_rng(100 + rank).integers(0, 256, (hi - lo, 32), dtype=np.uint8)
+        d_q, d_t = torch.from_numpy(q).to(dev), torch.from_numpy(shard).to(dev)
+        d_idx = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        d_dist = torch.empty((nq, 2), dtype=torch.int32, device=dev)
+        g_idx = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+        g_dist = torch.empty((world, nq, 2), dtype=torch.int32, device=dev)
+        f_idx, f_dist = torch.empty_like(d_idx), torch.empty_like(d_dist)
+        f_match = torch.empty(nq, dtype=torch.int32, device=dev)
+        L = orbfe.lib()
+
+        def step_match():
+            cs = torch.cuda.current_stream(dev)
+            _lib.check(L.orbfe_knn2_device(_lib.ptr(d_q), nq, _lib.ptr(d_t), hi - lo, lo, _lib.ptr(d_idx),
+                                           _lib.ptr(d_dist), cs.cuda_stream))
+            if world > 1:
+                dist.all_gather_into_tensor(g_idx, d_idx)
+                dist.all_gather_into_tensor(g_dist, d_dist)
+            else:
+                g_idx[0].copy_(d_idx); g_dist[0].copy_(d_dist)
+            _lib.check(L.orbfe_knn2_merge_device(_lib.ptr(g_idx), _lib.ptr(g_dist), world, nq, _lib.ptr(f_idx),
+                                                 _lib.ptr(f_dist), _lib.ptr(f_match), cs.cuda_stream))
+        for _ in range(3):
+            step_match()
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(args.steps):
+            step_match()
+        m1.record()
+        torch.cuda.synchronize()
+        barrier()
+        mms = max_over_ranks(m0.elapsed_time(m1))
+        pairs = nq * nmap * args.steps / (mms / 1e3)
+        matching = {"metric": "Hamming matches/s (2000 frame x 1M map descriptors, kNN-2 + ratio)", "value": pairs,
+                    "unit": "descriptor pairs/s", "ms_per_step": mms / args.steps,
+                    "map_shards": world, "gather": "nccl all_gather of per-shard best two" if world > 1 else "none"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per launch) ----
+    sizes = [ex.level_size(l, (H, W)) for l in range(8)]
+    P = sum(w * h for w, h in sizes)
+    P06 = sum(w * h for w, h in sizes[:7])
+    Ppad = sum((w + 38) * (h + 38) for w, h in sizes)
+    K = float(n_kp.mean())
+    C = float(cands)
+    alg = {"pyramid": P06 + Ppad, "fast_score": P, "fast_cells": 12 * C, "octree": 12 * C + 12 * K,
+           "layout": 28 * K, "blur": 2 * P, "describe": (749 + 4 + 512 + 32) * K}
+    frame_bytes = 3 * P + P06 + Ppad + 24 * C + 1337 * K
+    kern = {k: v for k, v in stage.items() if k in alg}
+    top = max(kern, key=kern.get)
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = alg[top] * B / (kern[top] / 1e3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        traffic = json.load(open(tfile)).get(top, {}).get("dram_bytes_per_frame")
+        traffic = traffic * B if traffic is not None else None
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[top] * B, "launch_ms": kern[top],
+                "kernel_ms_per_step": kern, "pipeline_bytes_per_frame": frame_bytes,
+                "pipeline_frac": value / world * frame_bytes / 1e9 / peak}
+
+    # ---- CPU baseline: the reference's ORBextractor on the host cores (bounded sample) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        one, kind = cpu_reference_run(1, 1, frames)
+        per = int(max(2, min(64, round(12.0 * one))))
+        v, kind = cpu_reference_run(per, cores, frames)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "single_thread_frames_per_s": one,
+               "sample": f"{per} frames per thread x {cores} threads of the same workload, one ORBextractor per thread"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C1 752x480 nFeatures=1000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}",
+                   "frames_per_gpu_per_step": B, "keypoints_per_frame": K, "fast_candidates_per_frame": C,
+                   "l2": f"inputs+intermediates per step = {B * geo['per_frame_bytes'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                   "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around synchronous C-ABI calls, max over ranks"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "matching": matching,
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=64, help="frames per pipelined chunk on the host-pointer path")
+    ap.add_argument("--no-match", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
