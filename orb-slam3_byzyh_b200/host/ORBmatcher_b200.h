@@ -1,0 +1,108 @@
+// host/ORBmatcher_b200.h -- the Hamming-matching entry points of ORB-SLAM3 on the C ABI.
+//
+// ORBmatcher::SearchByProjection and Frame::ComputeStereoMatches are member functions that walk
+// Frame / MapPoint / KeyFrame object graphs (Eigen, Sophus, mutexes); the boundary
+// keeps that walking on the host and hands plain arrays to the device.  This header provides the
+// array-level calls the three-line patches in INTEGRATION.md insert into src/ORBmatcher.cc and
+// src/Frame.cc; it depends only on <vector>, OpenCV core types and include/orbfe.h.
+#ifndef ORBMATCHER_B200_H
+#define ORBMATCHER_B200_H
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <opencv2/opencv.hpp>
+
+#include "ORBextractor.h"
+#include "orbfe.h"
+
+namespace ORB_SLAM3 {
+namespace b200 {
+
+inline int device() {
+    const char* d = getenv("ORBFE_DEVICE");
+    return d ? atoi(d) : 0;
+}
+
+// static int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b)   ORBmatcher.h:43
+inline int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    int32_t out = 0;
+    if (orbfe_descriptor_distance(a.ptr(), b.ptr(), 1, &out, device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("DescriptorDistance (B200): ") + orbfe_last_error());
+    return out;
+}
+
+// One projected candidate as the reference loops see it; the caller evaluates the early
+// `continue`s of its loop (bad point, not in view, depth, out of image) into `valid`.
+struct ProjPoints {
+    std::vector<float> u, v, ur, radius, angle;
+    std::vector<int32_t> minLevel, maxLevel;
+    std::vector<uint8_t> valid, blocks, desc;  // desc: 32 bytes per point (MapPoint::GetDescriptor())
+    void push(float u_, float v_, float ur_, float r_, int minL, int maxL, float ang, bool ok, bool blk,
+              const cv::Mat& d) {
+        u.push_back(u_); v.push_back(v_); ur.push_back(ur_); radius.push_back(r_); angle.push_back(ang);
+        minLevel.push_back(minL); maxLevel.push_back(maxL); valid.push_back(ok); blocks.push_back(blk);
+        const unsigned char* p = d.ptr();
+        desc.insert(desc.end(), p, p + 32);
+    }
+    size_t size() const { return u.size(); }
+};
+
+// keys = F.mvKeysUn, uright = F.mvuRight (empty for monocular), desc = F.mDescriptors (N x 32,
+// continuous), bounds = F.mnMinX/MinY/MaxX/MaxY, inv = F.mfGridElementWidthInv/HeightInv.
+// claimed[i] != 0 <=> F.mvpMapPoints[i] && Observations() > 0 (modes 0/1) or non-null (mode 2).
+// assigned[i] receives the index (into pts) of the point the reference would store in
+// F.mvpMapPoints[i]; -1 = cleared by the rotation check; untouched entries keep their value.
+inline int SearchByProjection(const std::vector<cv::KeyPoint>& keys, const std::vector<float>& uright,
+                              const cv::Mat& desc, float minX, float minY, float maxX, float maxY, float wInv,
+                              float hInv, const ProjPoints& pts, int mode, int thAccept, float nnratio,
+                              bool checkOrientation, const std::vector<uint8_t>& claimed,
+                              std::vector<int32_t>& assigned) {
+    OrbfeFrameView fv;
+    fv.n = (int32_t)keys.size();
+    fv.keys = reinterpret_cast<const OrbfeKeyPoint*>(keys.data());
+    fv.uright = uright.empty() ? nullptr : uright.data();
+    fv.desc = desc.ptr();
+    fv.min_x = minX; fv.min_y = minY; fv.max_x = maxX; fv.max_y = maxY;
+    fv.grid_w_inv = wInv; fv.grid_h_inv = hInv;
+    OrbfeProjPoints pp;
+    pp.m = (int32_t)pts.size();
+    pp.u = pts.u.data(); pp.v = pts.v.data(); pp.ur = pts.ur.data(); pp.radius = pts.radius.data();
+    pp.min_level = pts.minLevel.data(); pp.max_level = pts.maxLevel.data(); pp.angle = pts.angle.data();
+    pp.valid = pts.valid.data(); pp.blocks = pts.blocks.data(); pp.desc = pts.desc.data();
+    OrbfeSearchParams prm = {mode, thAccept, nnratio, checkOrientation ? 1 : 0};
+    const int n = orbfe_search_by_projection(&fv, &pp, &prm, claimed.data(), assigned.data(), nullptr, nullptr, device());
+    if (n < 0) throw std::runtime_error(std::string("SearchByProjection (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// void Frame::ComputeStereoMatches()   Frame.h:116, Frame.cc:1102-1358
+inline void ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& keysL,
+                                 const cv::Mat& descL, const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,
+                                 float mbf, float mb, std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    mvuRight.assign(keysL.size(), -1.0f);
+    mvDepth.assign(keysL.size(), -1.0f);
+    if (keysL.empty()) return;
+    if (orbfe_stereo_match(left->handle(), right->handle(), 0, reinterpret_cast<const OrbfeKeyPoint*>(keysL.data()),
+                           descL.ptr(), (int)keysL.size(), reinterpret_cast<const OrbfeKeyPoint*>(keysR.data()),
+                           descR.ptr(), (int)keysR.size(), mbf, mb, mvuRight.data(), mvDepth.data()) != ORBFE_OK)
+        throw std::runtime_error(std::string("ComputeStereoMatches (B200): ") + orbfe_last_error());
+}
+
+// cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + `d0 < d1*0.7`  (Frame::ComputeStereoFishEyeMatches,
+// Frame.cc:1553-1562): match[i] = accepted train row or -1.
+inline void KnnRatioMatch(const cv::Mat& query, const cv::Mat& train, std::vector<int32_t>& match,
+                          std::vector<int32_t>& idx2, std::vector<int32_t>& dist2) {
+    match.assign(query.rows, -1);
+    idx2.assign((size_t)query.rows * 2, -1);
+    dist2.assign((size_t)query.rows * 2, -1);
+    if (orbfe_knn2(query.ptr(), query.rows, train.ptr(), train.rows, 0, idx2.data(), dist2.data(), match.data(),
+                   device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("KnnRatioMatch (B200): ") + orbfe_last_error());
+}
+
+}  // namespace b200
+}  // namespace ORB_SLAM3
+
+#endif
