@@ -102,9 +102,9 @@ int orbfe_debug_octree(OrbfeExtractor* h, const int32_t* xys, int n, int minX, i
                        int maxY, int N, int32_t* keep_idx, int capacity, int* n_out);
 /* Per-kernel device milliseconds of the last chunk of the last batch call (CUDA events on the
  * launching stream; needs orbfe_set_profiling(h,1)).  Order: h2d, pyramid (nlevels launches),
- * fast_score, fast_cells, octree, layout, blur, describe, d2h; h2d/d2h are reported as 0 (they
+ * fast_score, fast_nms, fast_cells, octree, layout, blur, describe, d2h; h2d/d2h are reported as 0 (they
  * overlap neighbouring chunks on their own streams). */
-#define ORBFE_NUM_STAGES 9
+#define ORBFE_NUM_STAGES 10
 int orbfe_set_profiling(OrbfeExtractor* h, int enable);
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
 /* Number of kernel launches issued by this extractor since creation. */

@@ -23,43 +23,66 @@ __device__ const int8_t d_pattern[1024] = {
 };
 
 // ------------------------------------------------------------------------------------------
-constexpr int BW = ORBFE_BLUR_TW, BH = ORBFE_BLUR_TH, BSP = 72;
+// k_blur: separable 7x7 fixed-point Gaussian, vertical pass first.
+// A lane owns 4 adjacent pixels (one aligned 32-bit word of the padded level) and walks down a
+// strip of BLUR_ROWS rows with a 7-row window in registers.  The vertical pass works on 16-bit
+// lanes, two pixels per IMAD (column sums are <= 256*255 < 2^16, so nothing crosses a lane); the
+// horizontal pass needs 24 bits and runs per pixel, its +-3 neighbours coming from the adjacent
+// lanes by shuffle.  Warps overlap by one lane on each side (lanes 0 and 31 only feed halos), so
+// a warp produces 120 columns.  No shared memory, every global access is a coalesced word.
+constexpr int BLUR_ROWS = ORBFE_BLUR_TH, BLUR_WARPS = 4, BLUR_COLS = ORBFE_BLUR_TW;   // 32 rows, 120 columns per warp
+static_assert(BLUR_COLS == 120, "one warp = 30 producing lanes x 4 pixels");
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * BLUR_WARPS)
 k_blur(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-    __shared__ __align__(16) uint8_t tin[(BH + 6) * BSP];
-    __shared__ __align__(16) uint16_t hb[(BH + 6) * BW];
     int l = 0;
     const int t = blockIdx.x;
     while (l + 1 < g.nlevels && t >= g.lv[l + 1].blurTileBase) l++;
     const OrbfeLevelGeom& L = g.lv[l];
     const int tl = t - L.blurTileBase;
     const int ty = tl / L.blurTilesX, tx = tl - ty * L.blurTilesX;
-    const int ox = tx * BW, oy = ty * BH;
+    const int lane = threadIdx.x & 31;
+    const int y0 = (ty * BLUR_WARPS + (threadIdx.x >> 5)) * BLUR_ROWS;      // first output row (ROI)
+    if (y0 >= L.h) return;
+    const int x = BLUR_COLS * tx - 4 + 4 * lane;                             // ROI x of this lane's first pixel
     const size_t fo = (size_t)blockIdx.y * g.pyrStride + L.off;
-    const uint8_t* src = pyr + fo;
-    const int maxx = L.w + 18, maxy = L.h + 18;
-    for (int i = threadIdx.x; i < (BH + 6) * (BW + 6); i += 256) {
-        const int r = i / (BW + 6), c = i - r * (BW + 6);
-        const int x = min(ox - 3 + c, maxx), y = min(oy - 3 + r, maxy);
-        tin[r * BSP + c] = src[(size_t)(ORBFE_YOFF + y) * L.pitch + ORBFE_XOFF + x];
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (BH + 6) * BW; i += 256) {
-        const int r = i / BW, c = i - r * BW;
-        const uint8_t* p = &tin[r * BSP + c];
-        hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    uint8_t* dst = blur + fo;
-    for (int i = threadIdx.x; i < BH * BW; i += 256) {
-        const int r = i / BW, c = i - r * BW;
-        const int x = ox + c, y = oy + r;
-        if (x >= L.w || y >= L.h) continue;
-        const uint16_t* p = &hb[r * BW + c];
-        const unsigned acc = 18u * (p[0] + p[6 * BW]) + 34u * (p[BW] + p[5 * BW]) +
-                             48u * (p[2 * BW] + p[4 * BW]) + 56u * p[3 * BW];
-        dst[(size_t)(ORBFE_YOFF + y) * L.pitch + ORBFE_XOFF + x] = (uint8_t)((acc + 32768u) >> 16);
+    const int pw = L.pitch >> 2;
+    const int wcol = min((ORBFE_XOFF + x) >> 2, pw - 1);                     // x >= -4: column >= 28
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pyr + fo) + wcol;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(blur + fo) + wcol;
+    const int rmax = L.h + 2 * ORBFE_YOFF - 1;
+    const bool store = lane >= 1 && lane <= 30 && x < L.w;
+
+    uint32_t w01[7], w23[7];   // 7-row window, pixel pairs widened to 16-bit lanes
+#pragma unroll
+    for (int i = 0; i < BLUR_ROWS + 6; i++) {
+        // padded row of input row (y0 - 3 + i)
+        const uint32_t v = src[(size_t)min(ORBFE_YOFF + y0 - 3 + i, rmax) * pw];
+        w01[i % 7] = __byte_perm(v, 0u, 0x4140);
+        w23[i % 7] = __byte_perm(v, 0u, 0x4342);
+        if (i >= 6) {
+            // window rows (oldest..newest) = slots (i-6)%7 .. i%7
+            const int r0 = (i - 6) % 7, r1 = (i - 5) % 7, r2 = (i - 4) % 7, r3 = (i - 3) % 7, r4 = (i - 2) % 7,
+                      r5 = (i - 1) % 7, r6 = i % 7;
+            const uint32_t V01 = 18u * (w01[r0] + w01[r6]) + 34u * (w01[r1] + w01[r5]) + 48u * (w01[r2] + w01[r4]) + 56u * w01[r3];
+            const uint32_t V23 = 18u * (w23[r0] + w23[r6]) + 34u * (w23[r1] + w23[r5]) + 48u * (w23[r2] + w23[r4]) + 56u * w23[r3];
+            const uint32_t p01 = __shfl_up_sync(0xffffffffu, V01, 1), p23 = __shfl_up_sync(0xffffffffu, V23, 1);
+            const uint32_t n01 = __shfl_down_sync(0xffffffffu, V01, 1), n23 = __shfl_down_sync(0xffffffffu, V23, 1);
+            // V[-3..6] as 32-bit values
+            const uint32_t vm3 = p01 >> 16, vm2 = p23 & 0xFFFFu, vm1 = p23 >> 16;
+            const uint32_t v0 = V01 & 0xFFFFu, v1 = V01 >> 16, v2 = V23 & 0xFFFFu, v3 = V23 >> 16;
+            const uint32_t v4 = n01 & 0xFFFFu, v5 = n01 >> 16, v6 = n23 & 0xFFFFu;
+            const uint32_t o0 = 18u * (vm3 + v3) + 34u * (vm2 + v2) + 48u * (vm1 + v1) + 56u * v0 + 32768u;
+            const uint32_t o1 = 18u * (vm2 + v4) + 34u * (vm1 + v3) + 48u * (v0 + v2) + 56u * v1 + 32768u;
+            const uint32_t o2 = 18u * (vm1 + v5) + 34u * (v0 + v4) + 48u * (v1 + v3) + 56u * v2 + 32768u;
+            const uint32_t o3 = 18u * (v0 + v6) + 34u * (v1 + v5) + 48u * (v2 + v4) + 56u * v3 + 32768u;
+            const int y = y0 + i - 6;
+            if (store && y < L.h) {
+                // bytes 2 of each accumulator = (acc >> 16) & 255
+                const uint32_t lo = __byte_perm(o0, o1, 0x0062), hi = __byte_perm(o2, o3, 0x0062);
+                dst[(size_t)(ORBFE_YOFF + y) * pw] = __byte_perm(lo, hi, 0x5410);
+            }
+        }
     }
 }
 
@@ -229,7 +252,7 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
 
 void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                        long long* launches) {
-    k_blur<<<dim3(g.blurTiles, B), 256, 0, st>>>(g, b.pyr, b.blur);
+    k_blur<<<dim3(g.blurTiles, B), 32 * BLUR_WARPS, 0, st>>>(g, b.pyr, b.blur);
     ++*launches;
 }
 

@@ -6,16 +6,20 @@
 // B200 design.  OpenCV's FAST response is threshold independent: with
 //   best(p) = max over the 16 arcs of 9 contiguous ring pixels of max(min(c-ring), min(ring-c))
 // a pixel is a corner at threshold t iff best > t and its response is best-1.  The 700 tiny
-// per-cell cv::FAST calls of the reference therefore collapse into
-//   k_fast_score : ONE streaming pass per pyramid level that writes best(p) (0 when
-//                  best <= minThFAST) for every pixel of the level's FAST domain, and
-//   k_fast_cells : one warp per cell applying the per-cell 3x3 non-max suppression (neighbours
-//                  outside the cell's own 3-px-inset interior count as 0, exactly like the
-//                  reference's per-cell calls), the "empty at iniThFAST -> retry at minThFAST"
-//                  rule and the ordered emission (warp ballot + popc ranks).
-// NMS is threshold independent too: a non-corner neighbour has best_n <= t < best, so comparing
-// against its true score instead of 0 never changes the outcome; the only threshold-dependent
-// step is the final `best > t` filter, which lets one sweep serve both thresholds.
+// per-cell cv::FAST calls of the reference therefore collapse into three streaming kernels:
+//   k_fast_score : one pass per pyramid level writing the margin max(best - subTh, 0) of every
+//                  pixel of the level's FAST domain as u16 (subTh = max(minThFAST, 1));
+//   k_fast_nms   : 3x3 non-max suppression with the reference's per-cell semantics (a neighbour
+//                  outside the pixel's own cell interior counts as 0) on 16-bit lanes, two pixels
+//                  per instruction; writes two 1-bit-per-pixel maps: survivors at minThFAST and
+//                  survivors at iniThFAST;
+//   k_fast_cells : one warp per cell (lane = row): popcounts decide "empty at iniThFAST -> use
+//                  minThFAST" (:1141-1148), a warp scan gives every row its output rank, the set
+//                  bits are emitted in row-major order (= cv::FAST's order).
+// NMS is threshold independent: a non-corner neighbour has best_n <= t < best, so comparing
+// against its true margin instead of 0 never changes the outcome; cell interiors tile the FAST
+// domain exactly (cell j owns columns [19 + j*wCell, 19 + (j+1)*wCell)), so "outside the cell"
+// is a per-column / per-row mask.
 #include "fast_core.h"
 #include "octree_core.h"  // OC_PACK
 #include "orbfe_internal.h"
@@ -25,7 +29,7 @@ namespace {
 // ---- k_fast_score -------------------------------------------------------------------------------
 // Tile = 128 x 16 output pixels (+3 halo).  The tile is staged in shared memory already widened to
 // 16-bit lanes, in four copies shifted by 0..3 pixels, so that ANY run of four horizontally
-// adjacent pixels is one aligned LDS.64 (two s16x2 pairs) -- the 16 ring operands of four pixels
+// adjacent pixels is one aligned LDS.64 (two u16x2 pairs) -- the 16 ring operands of four pixels
 // cost 16 LDS.64 and no byte-extraction ALU work, leaving the ALU pipe to the packed min/max
 // network of fast_core.h (2 pixels per instruction).  Each thread scores 4 pixels on 2 rows.
 constexpr int TW = ORBFE_FAST_TW, TH = ORBFE_FAST_TH;
@@ -35,7 +39,7 @@ static_assert(TW == 128 && TH == 16, "thread mapping below assumes 128x16 tiles"
 
 __global__ void __launch_bounds__(256)
 k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr,
-             uint8_t* __restrict__ score) {
+             uint16_t* __restrict__ score) {
     __shared__ __align__(16) uint2 cp[4][TROWS][TG];
     int l = 0;
     const int t = blockIdx.x;
@@ -63,9 +67,9 @@ k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict
     const int gq = threadIdx.x & 31, rp = threadIdx.x >> 5;
     const int x = 19 + TW * tx + 4 * gq;       // ROI x of the first of this thread's 4 pixels
     if (x >= L.w - 19) return;
-    const uint32_t sub2 = (uint32_t)g.minTh * 0x00010001u;
-    // score map column = ROI x + 13, so that a 4-pixel group is one aligned 32-bit store
-    uint8_t* dst = score + fo + ORBFE_SXOFF + x;
+    const uint32_t sub2 = (uint32_t)g.subTh * 0x00010001u;
+    // score map column = ROI x + 13, so that a 4-pixel group is one aligned 64-bit store
+    uint16_t* dst = score + fo + ORBFE_SXOFF + x;
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const int orow = 2 * rp + rr, y = 19 + TH * ty + orow;
@@ -81,13 +85,127 @@ k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict
             e1[k] = c1 - v.y;
         }
         const uint32_t m0 = fc_margin2(e0, sub2), m1 = fc_margin2(e1, sub2);
-        *reinterpret_cast<uint32_t*>(dst + (size_t)(ORBFE_YOFF + y) * L.pitch) = __byte_perm(m0, m1, 0x6420);
+        *reinterpret_cast<uint2*>(dst + (size_t)(ORBFE_YOFF + y) * L.pitch) = make_uint2(m0, m1);
     }
 }
 
+// ---- k_fast_nms ---------------------------------------------------------------------------------
+// A warp owns a strip of 128 columns x NMS_ROWS rows of the FAST domain; lane = 4 adjacent pixels
+// held as two u16x2 registers; the strip is walked top to bottom with a 3-row window in registers.
+constexpr int NMS_ROWS = 16, NMS_WARPS = 8;   // CTA = 128 x 128 pixels
+
+struct NmsRow {   // per row, per thread: the horizontal 3-max with and without the centre
+    uint32_t A, B;          // centre pairs (p0,p1), (p2,p3)
+    uint32_t fullA, fullB;  // max(left, centre, right)
+    uint32_t lrA, lrB;      // max(left, right)
+};
+
+__global__ void __launch_bounds__(32 * NMS_WARPS)
+k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict__ score,
+           uint32_t* __restrict__ bits) {
+    int l = 0;
+    const int t = blockIdx.x;
+    while (l + 1 < g.nlevels && t >= g.lv[l + 1].nmsTileBase) l++;
+    const OrbfeLevelGeom& L = g.lv[l];
+    const int tl = t - L.nmsTileBase;
+    const int ty = tl / L.nmsTilesX, tx = tl - ty * L.nmsTilesX;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int dw = L.w - 38, dh = L.h - 38;                 // FAST domain size
+    const int dx0 = 128 * tx + 4 * lane;                    // domain x of this thread's first pixel
+    const int dy0 = (NMS_WARPS * ty + wid) * NMS_ROWS;      // first domain row of this warp's strip
+    if (dy0 >= dh) return;
+    const size_t fo = (size_t)blockIdx.y * g.pyrStride + L.off;
+    // element (domain x, domain y) lives at S[y*pitch + x]
+    const uint16_t* S = score + fo + (size_t)(ORBFE_YOFF + 19) * L.pitch + ORBFE_SXOFF + 19;
+    uint32_t* bmMin = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmMin;
+    uint32_t* bmIni = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmIni;
+
+    // column masks: a neighbour on the other side of a cell-interior boundary (or outside the
+    // domain) counts as 0.  first(x) <=> x % wCell == 0, last(x) <=> x % wCell == wCell-1 || x == dw-1
+    uint32_t mL_A, mR_A, mL_B, mR_B;
+    {
+        bool first[4], last[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = dx0 + i, r = x % L.wCell;
+            first[i] = r == 0;
+            last[i] = r == L.wCell - 1 || x >= dw - 1;
+        }
+        mL_A = (first[0] ? 0u : 0xFFFFu) | (first[1] ? 0u : 0xFFFF0000u);
+        mR_A = (last[0] ? 0u : 0xFFFFu) | (last[1] ? 0u : 0xFFFF0000u);
+        mL_B = (first[2] ? 0u : 0xFFFFu) | (first[3] ? 0u : 0xFFFF0000u);
+        mR_B = (last[2] ? 0u : 0xFFFFu) | (last[3] ? 0u : 0xFFFF0000u);
+    }
+    const bool colIn = dx0 < dw;           // this thread's group starts inside the domain
+    const uint32_t ini2 = ((uint32_t)max(g.iniTh - g.subTh, 0) * 0x00010001u) | 0x80008000u;
+
+    auto load_row = [&](int y, NmsRow& R) {
+        // rows -1 and dh are only read, never used (masked by the row flags below); they lie inside
+        // the score slab because the level keeps its 19-px border rows
+        const uint16_t* row = S + (ptrdiff_t)y * L.pitch;
+        uint2 c = make_uint2(0u, 0u);
+        if (colIn) c = *reinterpret_cast<const uint2*>(row + dx0);
+        uint32_t lw = __shfl_up_sync(0xffffffffu, c.y, 1), rw = __shfl_down_sync(0xffffffffu, c.x, 1);
+        if (lane == 0) lw = (colIn && dx0 > 0) ? *reinterpret_cast<const uint32_t*>(row + dx0 - 2) : 0u;
+        if (lane == 31) rw = dx0 + 4 < dw ? *reinterpret_cast<const uint32_t*>(row + dx0 + 4) : 0u;
+        const uint32_t s0 = __funnelshift_r(lw, c.x, 16) & mL_A;      // (p-1, p0): left of A
+        const uint32_t s1 = __funnelshift_r(c.x, c.y, 16);           // (p1, p2)
+        const uint32_t s2 = __funnelshift_r(c.y, rw, 16) & mR_B;      // (p3, p4): right of B
+        const uint32_t s1a = s1 & mR_A, s1b = s1 & mL_B;
+        R.A = c.x; R.B = c.y;
+        R.lrA = fc_maxu(s0, s1a); R.lrB = fc_maxu(s1b, s2);
+        R.fullA = fc_max3u(s0, s1a, c.x); R.fullB = fc_max3u(s1b, s2, c.y);
+    };
+
+    NmsRow up, cur, dn;
+    load_row(dy0 - 1, up);
+    load_row(dy0, cur);
+    const int yEnd = min(dy0 + NMS_ROWS, dh);
+    int ry = dy0 % L.hCell;                 // row index inside the cell interior
+    for (int y = dy0; y < yEnd; y++) {
+        load_row(y + 1, dn);
+        const bool rowFirst = ry == 0, rowLast = ry == L.hCell - 1 || y == dh - 1;
+        const uint32_t uA = rowFirst ? 0u : up.fullA, uB = rowFirst ? 0u : up.fullB;
+        const uint32_t dA = rowLast ? 0u : dn.fullA, dB = rowLast ? 0u : dn.fullB;
+        const uint32_t nbA = fc_max3u(uA, dA, cur.lrA), nbB = fc_max3u(uB, dB, cur.lrB);
+        // lane bit 15 of (x | 0x8000) - a is 0  <=>  a > x   (all values < 2^15, no cross-lane borrow)
+        const uint32_t kA = (nbA | 0x80008000u) - cur.A, kB = (nbB | 0x80008000u) - cur.B;
+        const uint32_t iA = (ini2 - cur.A) | kA, iB = (ini2 - cur.B) | kB;   // bit 15 set = NOT kept
+        // 4-bit nibbles (bit i = pixel i kept)
+        const uint32_t nMin = ((~kA >> 15) & 1u) | ((~kA >> 30) & 2u) | ((~kB >> 13) & 4u) | ((~kB >> 28) & 8u);
+        const uint32_t nIni = ((~iA >> 15) & 1u) | ((~iA >> 30) & 2u) | ((~iB >> 13) & 4u) | ((~iB >> 28) & 8u);
+        const unsigned grp = 0xFFu << (lane & 24);
+        const uint32_t wMin = __reduce_or_sync(grp, colIn ? nMin << (4 * (lane & 7)) : 0u);
+        const uint32_t wIni = __reduce_or_sync(grp, colIn ? nIni << (4 * (lane & 7)) : 0u);
+        if ((lane & 7) == 0) {
+            const size_t o = (size_t)y * L.bmPitch + 4 * tx + (lane >> 3);
+            bmMin[o] = wMin;
+            bmIni[o] = wIni;
+        }
+        up = cur;
+        cur = dn;
+        if (++ry == L.hCell) ry = 0;
+    }
+}
+
+// ---- k_fast_cells -------------------------------------------------------------------------------
+__device__ __forceinline__ void row_bits(const uint32_t* __restrict__ row, int pitchWords, int b0, int nb,
+                                         uint32_t& r0, uint32_t& r1, uint32_t& r2) {
+    const int k = b0 >> 5, sh = b0 & 31;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = k + i < pitchWords ? row[k + i] : 0u;
+    r0 = __funnelshift_r(w[0], w[1], sh);
+    r1 = __funnelshift_r(w[1], w[2], sh);
+    r2 = __funnelshift_r(w[2], w[3], sh);
+    if (nb < 32) { r0 &= (1u << nb) - 1u; r1 = 0u; r2 = 0u; }
+    else if (nb < 64) { r1 &= (1u << (nb - 32)) - 1u; r2 = 0u; }
+    else if (nb < 96) { r2 &= (1u << (nb - 64)) - 1u; }
+}
+
 __global__ void __launch_bounds__(256)
-k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ score,
-             uint32_t* __restrict__ slots, int* __restrict__ cellCount) {
+k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict__ score,
+             const uint32_t* __restrict__ bits, uint32_t* __restrict__ slots, int* __restrict__ cellCount) {
     const int lane = threadIdx.x & 31;
     const int cell = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (cell >= g.cellsPerFrame) return;
@@ -104,68 +222,52 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict
         if (lane == 0) *cnt = 0;
         return;
     }
-    const int x0 = iniX + 3, x1 = maxX - 3, y0 = iniY + 3, y1 = maxY - 3;  // FAST interior
-    // score map: margin = best - minThFAST (0 = no corner), column = ROI x + ORBFE_SXOFF
-    const uint8_t* S = score + (size_t)blockIdx.y * g.pyrStride + L.off + (size_t)ORBFE_YOFF * L.pitch + ORBFE_SXOFF;
-    const int iniMargin = g.iniTh - g.minTh;   // best > iniThFAST  <=>  margin > iniTh - minTh
+    const int x0 = iniX + 3, x1 = maxX - 3, y0 = iniY + 3, y1 = maxY - 3;  // FAST interior (ROI coords)
+    const int nbits = x1 - x0, b0 = x0 - 19;
+    const uint32_t* bmMin = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmMin;
+    const uint32_t* bmIni = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmIni;
+    // phase 1: is the cell empty at iniThFAST?
+    int nIni = 0;
+    for (int yb = y0; yb < y1; yb += 32) {
+        const int y = yb + lane;
+        uint32_t r0 = 0, r1 = 0, r2 = 0;
+        if (y < y1) row_bits(bmIni + (size_t)(y - 19) * L.bmPitch, L.bmPitch, b0, nbits, r0, r1, r2);
+        nIni += __popc(r0) + __popc(r1) + __popc(r2);
+    }
+    nIni = __reduce_add_sync(0xffffffffu, nIni);
+    const uint32_t* bm = nIni > 0 ? bmIni : bmMin;   // :1141-1148 retry at minThFAST only when empty
+    // phase 2: ordered emission
+    const uint16_t* S = score + (size_t)blockIdx.y * g.pyrStride + L.off + (size_t)ORBFE_YOFF * L.pitch + ORBFE_SXOFF;
     uint32_t* out = slots + (size_t)blockIdx.y * g.slotsPerFrame + L.slotBase + (size_t)ci * L.cellCap;
-    int nMin = 0, nIni = 0;
-    for (int y = y0; y < y1; y++) {
-        for (int xb = x0; xb < x1; xb += 32) {
-            const int x = xb + lane;
-            int c = 0;
-            if (x < x1) c = S[(size_t)y * L.pitch + x];
-            bool ok = false;
-            if (c > 0) {
-                // response (best-1) must also beat the 0 of empty neighbours: best > 1
-                int m = max(1 - g.minTh, 0);
+    int base = 0;
+    for (int yb = y0; yb < y1; yb += 32) {
+        const int y = yb + lane;
+        uint32_t r[3] = {0u, 0u, 0u};
+        if (y < y1) row_bits(bm + (size_t)(y - 19) * L.bmPitch, L.bmPitch, b0, nbits, r[0], r[1], r[2]);
+        const int c = __popc(r[0]) + __popc(r[1]) + __popc(r[2]);
+        int incl = c;
 #pragma unroll
-                for (int dy = -1; dy <= 1; dy++) {
-                    const int yy = y + dy;
-                    if (yy < y0 || yy >= y1) continue;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int pos = base + incl - c;
+        base += __shfl_sync(0xffffffffu, incl, 31);
 #pragma unroll
-                    for (int dx = -1; dx <= 1; dx++) {
-                        const int xx = x + dx;
-                        if ((dx | dy) == 0 || xx < x0 || xx >= x1) continue;
-                        m = max(m, (int)S[(size_t)yy * L.pitch + xx]);
-                    }
-                }
-                ok = c > m;
-            }
-            const unsigned bm = __ballot_sync(0xffffffffu, ok);
-            const unsigned bi = __ballot_sync(0xffffffffu, ok && c > iniMargin);
-            if (ok) {
-                const int pos = nMin + __popc(bm & ((1u << lane) - 1));
+        for (int k = 0; k < 3; k++) {
+            uint32_t m = r[k];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int x = x0 + 32 * k + b;
+                const int margin = S[(size_t)y * L.pitch + x];
                 if (pos < L.cellCap)
-                    out[pos] = OC_PACK(x - ORBFE_FAST_BORDER, y - ORBFE_FAST_BORDER, c + g.minTh - 1);
+                    out[pos] = OC_PACK(x - ORBFE_FAST_BORDER, y - ORBFE_FAST_BORDER, margin + g.subTh - 1);
+                pos++;
             }
-            nMin += __popc(bm);
-            nIni += __popc(bi);
         }
     }
-    nMin = min(nMin, L.cellCap);
-    int count = nMin;
-    if (nIni > 0 && nIni < nMin) {
-        // the cell was not empty at iniThFAST: keep only those corners (ordered compaction)
-        __syncwarp();
-        int wpos = 0;
-        for (int base = 0; base < nMin; base += 32) {
-            const int k = base + lane;
-            uint32_t v = 0;
-            bool keep = false;
-            if (k < nMin) {
-                v = out[k];
-                keep = OC_PK_S(v) + 1 > g.iniTh;
-            }
-            const unsigned bk = __ballot_sync(0xffffffffu, keep);
-            __syncwarp();
-            if (keep) out[wpos + __popc(bk & ((1u << lane) - 1))] = v;
-            wpos += __popc(bk);
-            __syncwarp();
-        }
-        count = wpos;
-    }
-    if (lane == 0) *cnt = count;
+    if (lane == 0) *cnt = min(base, L.cellCap);
 }
 
 }  // namespace
@@ -177,8 +279,15 @@ void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, i
     ++*launches;
 }
 
+void orbfe_launch_fast_nms(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                           long long* launches) {
+    if (g.nmsTiles <= 0) return;
+    k_fast_nms<<<dim3(g.nmsTiles, B), 32 * NMS_WARPS, 0, st>>>(g, b.score, b.nmsBits);
+    ++*launches;
+}
+
 void orbfe_launch_fast_cells(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches) {
-    k_fast_cells<<<dim3((g.cellsPerFrame + 7) / 8, B), 256, 0, st>>>(g, b.score, b.slots, b.cellCount);
+    k_fast_cells<<<dim3((g.cellsPerFrame + 7) / 8, B), 256, 0, st>>>(g, b.score, b.nmsBits, b.slots, b.cellCount);
     ++*launches;
 }

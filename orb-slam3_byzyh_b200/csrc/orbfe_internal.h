@@ -38,6 +38,9 @@ struct OrbfeLevelGeom {
     int mode;            // resize path: 0 = bilinear taps, 1 = exact 2x2 area, 2 = identity copy
     int fastTileBase, fastTilesX, fastTilesY;   // tile numbering of the FAST score kernel
     int blurTileBase, blurTilesX, blurTilesY;   // tile numbering of the blur kernel
+    int nmsTileBase, nmsTilesX, nmsTilesY;      // tile numbering of the NMS kernel (128 x 128 px)
+    int bmPitch;         // words per row of the NMS bitmaps (multiple of 4)
+    unsigned bmMin, bmIni;  // word offsets of the two bitmaps inside one frame's bitmap slab
 };
 
 struct OrbfeFrameGeom {
@@ -47,7 +50,9 @@ struct OrbfeFrameGeom {
     int cellsPerFrame;
     unsigned slotsPerFrame;
     int kpCapFrame;
-    int fastTiles, blurTiles;
+    int fastTiles, blurTiles, nmsTiles;
+    unsigned bmWordsPerFrame;
+    int subTh;                      // score map stores max(best - subTh, 0), subTh = max(minTh, 1)
     int ocShared;                   // dynamic shared bytes of the octree kernel (0 = tables in global)
     int ocMmax;
     OrbfeLevelGeom lv[ORBFE_MAX_LEVELS];
@@ -73,14 +78,16 @@ struct OrbfeWork {
 
 #define ORBFE_FAST_TW 128
 #define ORBFE_FAST_TH 16
-#define ORBFE_BLUR_TW 64
-#define ORBFE_BLUR_TH 16
+#define ORBFE_BLUR_TW 120  // output columns per warp of the blur kernel
+#define ORBFE_BLUR_TH 32   // output rows per warp strip
 
 // Device buffers of one chunk of frames (all frame-major).
 struct OrbfeChunkBufs {
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
-    uint8_t* score;      // [B][pyrStride]  FAST margin max(best - minThFAST, 0), column = ROI x + ORBFE_SXOFF
+    uint16_t* score;     // [B][pyrStride] u16: FAST margin max(best - subTh, 0), column = ROI x + ORBFE_SXOFF
+    uint32_t* nmsBits;   // [B][bmWordsPerFrame] per level two bitmaps over the FAST domain: survives NMS (a) at
+                         //                      minThFAST, (b) at iniThFAST; bit (x-19) of row (y-19)
     uint32_t* slots;     // [B][slotsPerFrame] per-cell candidate slots (packed)
     int* cellCount;      // [B][cellsPerFrame]
     uint32_t* cand;      // [B][slotsPerFrame] per-level compacted candidates (emission order)
@@ -102,6 +109,8 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
                           cudaStream_t st, long long* launches);
 void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches);
+void orbfe_launch_fast_nms(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                           long long* launches);
 void orbfe_launch_fast_cells(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches);
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,

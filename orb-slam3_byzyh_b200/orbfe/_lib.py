@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "libORBfe_b200.so")
 
 OK, EMPTY_IMAGE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY = 0, -1, -2, -3, -4
-NUM_STAGES = 9
-STAGE_NAMES = ("h2d", "pyramid", "fast_score", "fast_cells", "octree", "layout", "blur", "describe", "d2h")
+NUM_STAGES = 10
+STAGE_NAMES = ("h2d", "pyramid", "fast_score", "fast_nms", "fast_cells", "octree", "layout", "blur", "describe", "d2h")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint
