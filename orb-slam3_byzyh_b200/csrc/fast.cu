@@ -100,6 +100,52 @@ struct NmsRow {   // per row, per thread: the horizontal 3-max with and without 
     uint32_t lrA, lrB;      // max(left, right)
 };
 
+struct NmsMasks { uint32_t lA, rA, lB, rB; };
+
+// Loads one score-map row segment (4 pixels per lane) and forms its horizontal maxima.
+__device__ __forceinline__ void nms_load_row(const uint16_t* __restrict__ row, bool colIn, bool needL, bool needR,
+                                             const NmsMasks& m, NmsRow& R) {
+    uint2 c = make_uint2(0u, 0u);
+    if (colIn) c = *reinterpret_cast<const uint2*>(row);
+    uint32_t lw = __shfl_up_sync(0xffffffffu, c.y, 1), rw = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (needL) lw = *reinterpret_cast<const uint32_t*>(row - 2);     // lane 0: pixels left of the warp
+    if (needR) rw = *reinterpret_cast<const uint32_t*>(row + 4);     // lane 31: pixels right of the warp
+    const uint32_t s1 = __funnelshift_r(c.x, c.y, 16);               // (p1, p2)
+    const uint32_t s0 = __funnelshift_r(lw, c.x, 16) & m.lA;          // (p-1, p0): left neighbours of A
+    const uint32_t s2 = __funnelshift_r(c.y, rw, 16) & m.rB;          // (p3, p4): right neighbours of B
+    const uint32_t s1a = s1 & m.rA, s1b = s1 & m.lB;
+    R.A = c.x; R.B = c.y;
+    R.lrA = fc_maxu(s0, s1a); R.lrB = fc_maxu(s1b, s2);
+    R.fullA = fc_max3u(s0, s1a, c.x); R.fullB = fc_max3u(s1b, s2, c.y);
+}
+
+// One output row: 3x3 strict maximum test of `cur` against its eight neighbours.
+__device__ __forceinline__ void nms_emit_row(const NmsRow& up, const NmsRow& cur, const NmsRow& dn, bool rowFirst,
+                                             bool rowLast, uint32_t ini2, unsigned grp, int nibShift, uint32_t nibMask, bool writer,
+                                             uint32_t* __restrict__ oMin, uint32_t* __restrict__ oIni) {
+    const uint32_t uA = rowFirst ? 0u : up.fullA, uB = rowFirst ? 0u : up.fullB;
+    const uint32_t dA = rowLast ? 0u : dn.fullA, dB = rowLast ? 0u : dn.fullB;
+    const uint32_t nbA = fc_max3u(uA, dA, cur.lrA), nbB = fc_max3u(uB, dB, cur.lrB);
+    // bit 15 of a lane of (x | 0x8000) - a is 0  <=>  a > x   (values < 2^15: no cross-lane borrow)
+    const uint32_t kA = (nbA | 0x80008000u) - cur.A, kB = (nbB | 0x80008000u) - cur.B;
+    const uint32_t iA = (ini2 - cur.A) | kA, iB = (ini2 - cur.B) | kB;    // bit 15 set = NOT kept
+    // gather the four "not kept" flags (bits 15/31 of A, 15/31 of B) into a nibble, then invert
+    const uint32_t fMin = __byte_perm(kA, kB, 0x7531) & 0x80808080u;   // bytes: A.b1, A.b3, B.b1, B.b3
+    const uint32_t fIni = __byte_perm(iA, iB, 0x7531) & 0x80808080u;
+    // multiply packs the four flag bits (7,15,23,31) into bits 28..31: (f >> 7) * 0x10204080 >> 28
+    const uint32_t nMin = (~(((fMin >> 7) * 0x10204080u) >> 28)) & nibMask;
+    const uint32_t nIni = (~(((fIni >> 7) * 0x10204080u) >> 28)) & nibMask;
+    // OR the nibbles of 8 adjacent lanes into one 32-bit word per bitmap with three shuffles: both
+    // bitmaps ride in one register (min nibbles in the low half, ini nibbles in the high half) for
+    // the two steps inside a 4-lane group, the third step joins the two 16-bit halves.
+    uint32_t v = (nMin << nibShift) | (nIni << (nibShift + 16));      // nibShift = 4 * (lane & 3)
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    const uint32_t o = __shfl_xor_sync(0xffffffffu, v, 4);            // the other 4-lane group of the octet
+    const uint32_t wMin = __byte_perm(v, o, 0x5410), wIni = __byte_perm(v, o, 0x7632);   // valid on lanes 8k..8k+3
+    if (writer) { *oMin = wMin; *oIni = wIni; }
+}
+
 __global__ void __launch_bounds__(32 * NMS_WARPS)
 k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict__ score,
            uint32_t* __restrict__ bits) {
@@ -115,76 +161,63 @@ k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict_
     const int dy0 = (NMS_WARPS * ty + wid) * NMS_ROWS;      // first domain row of this warp's strip
     if (dy0 >= dh) return;
     const size_t fo = (size_t)blockIdx.y * g.pyrStride + L.off;
+    const int pitch = L.pitch;
     // element (domain x, domain y) lives at S[y*pitch + x]
-    const uint16_t* S = score + fo + (size_t)(ORBFE_YOFF + 19) * L.pitch + ORBFE_SXOFF + 19;
-    uint32_t* bmMin = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmMin;
-    uint32_t* bmIni = bits + (size_t)blockIdx.y * g.bmWordsPerFrame + L.bmIni;
+    const uint16_t* row = score + fo + (size_t)(ORBFE_YOFF + 19 + dy0 - 1) * pitch + ORBFE_SXOFF + 19 + dx0;
+    const size_t bo = (size_t)blockIdx.y * g.bmWordsPerFrame + (size_t)dy0 * L.bmPitch + 4 * tx + (lane >> 3);
+    uint32_t* oMin = bits + bo + L.bmMin;
+    uint32_t* oIni = bits + bo + L.bmIni;
 
     // column masks: a neighbour on the other side of a cell-interior boundary (or outside the
-    // domain) counts as 0.  first(x) <=> x % wCell == 0, last(x) <=> x % wCell == wCell-1 || x == dw-1
-    uint32_t mL_A, mR_A, mL_B, mR_B;
+    // domain) counts as 0.  first(x) <=> x % wCell == 0, last(x) <=> x % wCell == wCell-1 || x >= dw-1
+    NmsMasks m;
     {
-        bool first[4], last[4];
+        const int r0 = dx0 % L.wCell;
+        uint32_t f = 0, la = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const int x = dx0 + i, r = x % L.wCell;
-            first[i] = r == 0;
-            last[i] = r == L.wCell - 1 || x >= dw - 1;
+            int r = r0 + i;
+            if (r >= L.wCell) r -= L.wCell;
+            if (r == 0) f |= 1u << i;
+            if (r == L.wCell - 1 || dx0 + i >= dw - 1) la |= 1u << i;
         }
-        mL_A = (first[0] ? 0u : 0xFFFFu) | (first[1] ? 0u : 0xFFFF0000u);
-        mR_A = (last[0] ? 0u : 0xFFFFu) | (last[1] ? 0u : 0xFFFF0000u);
-        mL_B = (first[2] ? 0u : 0xFFFFu) | (first[3] ? 0u : 0xFFFF0000u);
-        mR_B = (last[2] ? 0u : 0xFFFFu) | (last[3] ? 0u : 0xFFFF0000u);
+        m.lA = ((f & 1) ? 0u : 0xFFFFu) | ((f & 2) ? 0u : 0xFFFF0000u);
+        m.lB = ((f & 4) ? 0u : 0xFFFFu) | ((f & 8) ? 0u : 0xFFFF0000u);
+        m.rA = ((la & 1) ? 0u : 0xFFFFu) | ((la & 2) ? 0u : 0xFFFF0000u);
+        m.rB = ((la & 4) ? 0u : 0xFFFFu) | ((la & 8) ? 0u : 0xFFFF0000u);
     }
     const bool colIn = dx0 < dw;           // this thread's group starts inside the domain
+    const bool needL = lane == 0 && colIn && dx0 > 0, needR = lane == 31 && dx0 + 4 < dw;
+    const bool writer = (lane & 7) == 0;
     const uint32_t ini2 = ((uint32_t)max(g.iniTh - g.subTh, 0) * 0x00010001u) | 0x80008000u;
+    const unsigned grp = 0xFFu << (lane & 24);
+    const int nibShift = 4 * (lane & 3);
+    const uint32_t nibMask = colIn ? 0xFu : 0u;            // lanes outside the domain add nothing
 
-    auto load_row = [&](int y, NmsRow& R) {
-        // rows -1 and dh are only read, never used (masked by the row flags below); they lie inside
-        // the score slab because the level keeps its 19-px border rows
-        const uint16_t* row = S + (ptrdiff_t)y * L.pitch;
-        uint2 c = make_uint2(0u, 0u);
-        if (colIn) c = *reinterpret_cast<const uint2*>(row + dx0);
-        uint32_t lw = __shfl_up_sync(0xffffffffu, c.y, 1), rw = __shfl_down_sync(0xffffffffu, c.x, 1);
-        if (lane == 0) lw = (colIn && dx0 > 0) ? *reinterpret_cast<const uint32_t*>(row + dx0 - 2) : 0u;
-        if (lane == 31) rw = dx0 + 4 < dw ? *reinterpret_cast<const uint32_t*>(row + dx0 + 4) : 0u;
-        const uint32_t s0 = __funnelshift_r(lw, c.x, 16) & mL_A;      // (p-1, p0): left of A
-        const uint32_t s1 = __funnelshift_r(c.x, c.y, 16);           // (p1, p2)
-        const uint32_t s2 = __funnelshift_r(c.y, rw, 16) & mR_B;      // (p3, p4): right of B
-        const uint32_t s1a = s1 & mR_A, s1b = s1 & mL_B;
-        R.A = c.x; R.B = c.y;
-        R.lrA = fc_maxu(s0, s1a); R.lrB = fc_maxu(s1b, s2);
-        R.fullA = fc_max3u(s0, s1a, c.x); R.fullB = fc_max3u(s1b, s2, c.y);
-    };
-
-    NmsRow up, cur, dn;
-    load_row(dy0 - 1, up);
-    load_row(dy0, cur);
-    const int yEnd = min(dy0 + NMS_ROWS, dh);
+    // Rows dy0-1 and dy0+n are only read as neighbours and masked by rowFirst/rowLast at the domain
+    // edge; they exist in memory because the level keeps its 19-px border rows.
+    NmsRow r0, r1, r2;
+    nms_load_row(row, colIn, needL, needR, m, r0);
+    row += pitch;
+    nms_load_row(row, colIn, needL, needR, m, r1);
+    const int n = min(NMS_ROWS, dh - dy0);
     int ry = dy0 % L.hCell;                 // row index inside the cell interior
-    for (int y = dy0; y < yEnd; y++) {
-        load_row(y + 1, dn);
-        const bool rowFirst = ry == 0, rowLast = ry == L.hCell - 1 || y == dh - 1;
-        const uint32_t uA = rowFirst ? 0u : up.fullA, uB = rowFirst ? 0u : up.fullB;
-        const uint32_t dA = rowLast ? 0u : dn.fullA, dB = rowLast ? 0u : dn.fullB;
-        const uint32_t nbA = fc_max3u(uA, dA, cur.lrA), nbB = fc_max3u(uB, dB, cur.lrB);
-        // lane bit 15 of (x | 0x8000) - a is 0  <=>  a > x   (all values < 2^15, no cross-lane borrow)
-        const uint32_t kA = (nbA | 0x80008000u) - cur.A, kB = (nbB | 0x80008000u) - cur.B;
-        const uint32_t iA = (ini2 - cur.A) | kA, iB = (ini2 - cur.B) | kB;   // bit 15 set = NOT kept
-        // 4-bit nibbles (bit i = pixel i kept)
-        const uint32_t nMin = ((~kA >> 15) & 1u) | ((~kA >> 30) & 2u) | ((~kB >> 13) & 4u) | ((~kB >> 28) & 8u);
-        const uint32_t nIni = ((~iA >> 15) & 1u) | ((~iA >> 30) & 2u) | ((~iB >> 13) & 4u) | ((~iB >> 28) & 8u);
-        const unsigned grp = 0xFFu << (lane & 24);
-        const uint32_t wMin = __reduce_or_sync(grp, colIn ? nMin << (4 * (lane & 7)) : 0u);
-        const uint32_t wIni = __reduce_or_sync(grp, colIn ? nIni << (4 * (lane & 7)) : 0u);
-        if ((lane & 7) == 0) {
-            const size_t o = (size_t)y * L.bmPitch + 4 * tx + (lane >> 3);
-            bmMin[o] = wMin;
-            bmIni[o] = wIni;
+    const int hLast = L.hCell - 1, bmPitch = L.bmPitch;
+    // three rows per iteration so that the 3-row window rotates without register moves
+    for (int i = 0; i < n; i += 3) {
+#define NMS_STEP(UP, CUR, DN, K)                                                                                  \
+        if (i + K < n) {                                                                                          \
+            row += pitch;                                                                                         \
+            nms_load_row(row, colIn, needL, needR, m, DN);                                                        \
+            nms_emit_row(UP, CUR, DN, ry == 0, ry == hLast || dy0 + i + K == dh - 1, ini2, grp, nibShift, nibMask, \
+                         writer, oMin, oIni);                                                                    \
+            oMin += bmPitch; oIni += bmPitch;                                                                     \
+            ry = ry == hLast ? 0 : ry + 1;                                                                        \
         }
-        up = cur;
-        cur = dn;
-        if (++ry == L.hCell) ry = 0;
+        NMS_STEP(r0, r1, r2, 0)
+        NMS_STEP(r1, r2, r0, 1)
+        NMS_STEP(r2, r0, r1, 2)
+#undef NMS_STEP
     }
 }
 
