@@ -228,6 +228,10 @@ static OC_HD void oc_copy_node(const OcNodes& src, int j, const OcNodes& dst, in
     dst.cnt[pos] = src.cnt[j];
 }
 
+// The point sweeps issue OC_ILP independent loads per thread before using any of them: the points
+// live in global memory (L2) and a dependent load chain per point would expose its latency.
+#define OC_ILP 4
+
 // One sweep over the points: quadrant of every point that sits in an expandable node.
 static OC_HD void oc_count_children(const OcWork& w) {
     const int cur = w.sc[OC_CUR];
@@ -235,15 +239,25 @@ static OC_HD void oc_count_children(const OcWork& w) {
     const int size = w.sc[OC_SIZE];
     OC_PAR_FOR(k, 4 * size) w.cc[k] = 0;
     OC_SYNC();
-    OC_PAR_FOR(i, w.n) {
-        const int j = (int)(w.pnode[i] & 0xFFFFFFu);
-        if (nd.cnt[j] > 1) {
-            const uint32_t p = w.pk[i];
-            const int X0 = nd.x0[j], X1 = nd.x1[j], Y0 = nd.y0[j], Y1 = nd.y1[j];
-            const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
-            const int q = (OC_PK_X(p) < mx ? 0 : 1) + (OC_PK_Y(p) < my ? 0 : 2);
-            w.pnode[i] = (uint32_t)j | ((uint32_t)q << 30);
-            OC_ATOMIC_ADD(&w.cc[4 * j + q], 1);
+    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
+        uint32_t lab[OC_ILP], p[OC_ILP];
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            lab[u] = i < w.n ? w.pnode[i] : 0u;
+            p[u] = i < w.n ? w.pk[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            const int j = (int)(lab[u] & 0xFFFFFFu);
+            if (i < w.n && nd.cnt[j] > 1) {
+                const int X0 = nd.x0[j], X1 = nd.x1[j], Y0 = nd.y0[j], Y1 = nd.y1[j];
+                const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
+                const int q = (OC_PK_X(p[u]) < mx ? 0 : 1) + (OC_PK_Y(p[u]) < my ? 0 : 2);
+                w.pnode[i] = (uint32_t)j | ((uint32_t)q << 30);
+                OC_ATOMIC_ADD(&w.cc[4 * j + q], 1);
+            }
         }
     }
     OC_SYNC();
@@ -251,11 +265,22 @@ static OC_HD void oc_count_children(const OcWork& w) {
 
 // Re-label every point after the list was rebuilt by thread 0.
 static OC_HD void oc_relabel(const OcWork& w) {
-    OC_PAR_FOR(i, w.n) {
-        const uint32_t v = w.pnode[i];
-        const int j = (int)(v & 0xFFFFFFu);
-        const int r = w.remap[j];
-        w.pnode[i] = (uint32_t)(r >= 0 ? r : w.cpos[4 * j + (int)(v >> 30)]);
+    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
+        uint32_t v[OC_ILP];
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            v[u] = i < w.n ? w.pnode[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            if (i < w.n) {
+                const int j = (int)(v[u] & 0xFFFFFFu);
+                const int r = w.remap[j];
+                w.pnode[i] = (uint32_t)(r >= 0 ? r : w.cpos[4 * j + (int)(v[u] >> 30)]);
+            }
+        }
     }
     OC_SYNC();
 }
@@ -396,11 +421,33 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
     const int size = w.sc[OC_SIZE];
     OC_PAR_FOR(k, size) { best_score[k] = -1; out_idx[k] = 0x7FFFFFFF; }
     OC_SYNC();
-    OC_PAR_FOR(i, w.n) OC_ATOMIC_MAX(&best_score[w.pnode[i] & 0xFFFFFFu], OC_PK_S(w.pk[i]));
+    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
+        uint32_t lab[OC_ILP], p[OC_ILP];
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            lab[u] = i < w.n ? w.pnode[i] : 0u;
+            p[u] = i < w.n ? w.pk[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++)
+            if (i0 + u * OC_NT < w.n) OC_ATOMIC_MAX(&best_score[lab[u] & 0xFFFFFFu], OC_PK_S(p[u]));
+    }
     OC_SYNC();
-    OC_PAR_FOR(i, w.n) {
-        const int j = (int)(w.pnode[i] & 0xFFFFFFu);
-        if (OC_PK_S(w.pk[i]) == best_score[j]) OC_ATOMIC_MIN(&out_idx[j], i);
+    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
+        uint32_t lab[OC_ILP], p[OC_ILP];
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            lab[u] = i < w.n ? w.pnode[i] : 0u;
+            p[u] = i < w.n ? w.pk[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < OC_ILP; u++) {
+            const int i = i0 + u * OC_NT;
+            const int j = (int)(lab[u] & 0xFFFFFFu);
+            if (i < w.n && OC_PK_S(p[u]) == best_score[j]) OC_ATOMIC_MIN(&out_idx[j], i);
+        }
     }
     if (OC_TID == 0) *out_n = size;
     OC_SYNC();

@@ -162,6 +162,21 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
             build_taps(S.w, L.w, true, taps.data() + L.xtab);
             build_taps(S.h, L.h, false, taps.data() + L.ytab);
             tapOff += (unsigned)(L.w + L.h);
+            // k_resize_fast precondition, checked on the padded (reflected) destination columns
+            L.fastTaps = 1;
+            for (int wc = 0; wc < L.pitch / 4 && L.fastTaps; wc++) {
+                int lo = 1 << 30, hi = 0;
+                for (int i = 0; i < 4; i++) {
+                    int p = 4 * wc - ORBFE_XOFF + i;
+                    if (p < 0) p = -p;
+                    if (p >= L.w) p = 2 * (L.w - 1) - p;
+                    p = std::max(0, std::min(p, L.w - 1));
+                    const OrbfeTap& t = taps[L.xtab + p];
+                    lo = std::min(lo, (int)t.s);
+                    hi = std::max(hi, (int)t.s1);
+                }
+                if (hi - lo > 7) L.fastTaps = 0;
+            }
         }
         L.fastTileBase = fastTile;
         L.fastTilesX = hasCells ? (L.w - 38 + ORBFE_FAST_TW - 1) / ORBFE_FAST_TW : 0;

@@ -36,6 +36,7 @@ struct OrbfeLevelGeom {
     float kpsize;        // (float)(int)(PATCH_SIZE*mvScaleFactor[level])
     unsigned xtab, ytab; // offsets (in entries) of the resize tables of this level
     int mode;            // resize path: 0 = bilinear taps, 1 = exact 2x2 area, 2 = identity copy
+    int fastTaps;        // mode 0: every aligned group of 4 destination columns taps <= 8 adjacent source bytes
     int fastTileBase, fastTilesX, fastTilesY;   // tile numbering of the FAST score kernel
     int blurTileBase, blurTilesX, blurTilesY;   // tile numbering of the blur kernel
     int nmsTileBase, nmsTilesX, nmsTilesY;      // tile numbering of the NMS kernel (128 x 128 px)

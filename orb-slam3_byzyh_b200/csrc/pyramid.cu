@@ -90,15 +90,16 @@ k_resize(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict_
     *reinterpret_cast<uint32_t*>(base + dstOff + (size_t)py * pitch + 4 * wc) = out;
 }
 
-// Fast bilinear path (scale <= 2, i.e. the four source taps of four adjacent destination pixels span
-// at most 8 source bytes).  A thread owns four adjacent PADDED destination columns and walks down
-// RS_ROWS destination rows: the x-taps live in registers, every source row segment is fetched as
-// three aligned 32-bit words and the eight tap bytes are pulled out with two PRMTs whose selectors
-// were computed once; the horizontal pass of a source row is reused when the next destination row
-// needs the same source row (at scale 1.2 that is 5 rows out of 6).  Border columns/rows are the
-// same computation on the reflected destination coordinate, so resize + copyMakeBorder stay one
-// pass with coalesced 32-bit stores.
-constexpr int RS_ROWS = 32, RS_WARPS = 4;
+// Fast bilinear path (the four source taps of four adjacent destination pixels span at most 8
+// source bytes, i.e. scale <= 2; the host checks this when it builds the tap tables).  A thread
+// owns four adjacent PADDED destination columns and walks down RS_ROWS destination rows: the x-taps
+// live in registers, every source row segment is fetched as three aligned 32-bit words, one PRMT
+// per pixel pulls its two tap bytes out of that 8-byte window and one IDP2A applies the two 11-bit
+// weights.  The horizontal pass of a source row is kept (already >> 4) and reused when the next
+// destination row needs the same source row (at scale 1.2 that is 5 rows out of 6).  Border
+// columns/rows are the same computation on the reflected destination coordinate, so resize +
+// copyMakeBorder stay one pass with coalesced 32-bit stores.
+constexpr int RS_ROWS = 16, RS_WARPS = 4;
 
 __global__ void __launch_bounds__(32 * RS_WARPS)
 k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict__ xtab,
@@ -111,68 +112,64 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
     const int py0 = (blockIdx.y * RS_WARPS + (threadIdx.x >> 5)) * RS_ROWS;
     if (py0 >= H) return;
     uint8_t* base = pyr + (size_t)blockIdx.z * pyrStride;
-    const uint8_t* sroi = base + srcOff + (size_t)ORBFE_YOFF * srcPitch;   // source row 0, padded column 0
-    int a0[4], a1[4], s[4], s1[4];
-    int lo = 1 << 30, hi = 0;
+    int lo = 1 << 30;
+    OrbfeTap tp[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const OrbfeTap t = xtab[reflect101_clamped(4 * wc - ORBFE_XOFF + i, w)];
-        s[i] = t.s; s1[i] = t.s1; a0[i] = t.a0; a1[i] = t.a1;
-        lo = min(lo, (int)t.s);
-        hi = max(hi, (int)t.s1);
+        tp[i] = xtab[reflect101_clamped(4 * wc - ORBFE_XOFF + i, w)];
+        lo = min(lo, (int)tp[i].s);
     }
-    const bool wide = hi - lo > 7;
-    unsigned selA = 0, selB = 0;
+    uint32_t wgt[4], sel[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        selA |= (unsigned)((s[i] - lo) & 7) << (4 * i);
-        selB |= (unsigned)((s1[i] - lo) & 7) << (4 * i);
+        wgt[i] = (uint32_t)(uint16_t)tp[i].a0 | ((uint32_t)(uint16_t)tp[i].a1 << 16);
+        sel[i] = (uint32_t)(tp[i].s - lo) | ((uint32_t)(tp[i].s1 - lo) << 4);   // byte0 = src[s], byte1 = src[s1]
     }
-    const int col = ORBFE_XOFF + lo, wi = col >> 2, sh = 8 * (col & 3);
+    const int col = ORBFE_XOFF + lo, sh = 8 * (col & 3);
     const int srcWords = srcPitch >> 2;
+    const int wi0 = col >> 2, wi1 = min(wi0 + 1, srcWords - 1), wi2 = min(wi0 + 2, srcWords - 1);
+    const uint32_t* sroi = reinterpret_cast<const uint32_t*>(base + srcOff + (size_t)ORBFE_YOFF * srcPitch);
 
-    auto hrow = [&](int r, int* Hout) {
-        const uint8_t* row = sroi + (size_t)r * srcPitch;
-        if (!wide) {
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(row);
-            const uint32_t w0 = rw[wi], w1 = rw[min(wi + 1, srcWords - 1)], w2 = rw[min(wi + 2, srcWords - 1)];
-            const uint32_t lo8 = __funnelshift_r(w0, w1, sh), hi8 = __funnelshift_r(w1, w2, sh);
-            const uint32_t A = __byte_perm(lo8, hi8, selA), Bv = __byte_perm(lo8, hi8, selB);
+    auto hrow = [&](int r, uint32_t* Hs) {   // horizontal pass of source row r, already >> 4
+        const uint32_t* rw = sroi + (size_t)r * srcWords;
+        const uint32_t w0 = rw[wi0], w1 = rw[wi1], w2 = rw[wi2];
+        const uint32_t lo8 = __funnelshift_r(w0, w1, sh), hi8 = __funnelshift_r(w1, w2, sh);
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                Hout[i] = (int)__byte_perm(A, 0u, 0x4440 + i) * a0[i] + (int)__byte_perm(Bv, 0u, 0x4440 + i) * a1[i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                Hout[i] = (int)row[ORBFE_XOFF + s[i]] * a0[i] + (int)row[ORBFE_XOFF + s1[i]] * a1[i];
-        }
+        for (int i = 0; i < 4; i++) Hs[i] = __dp2a_lo(wgt[i], __byte_perm(lo8, hi8, sel[i]), 0u) >> 4;
     };
 
-    int c0 = -1, c1 = -1, C0[4], C1[4];   // cached horizontal passes (source row index, values)
+    int c0 = -1, c1 = -1;
+    uint32_t C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0};   // cached horizontal passes of source rows c0, c1
     const int pyEnd = min(py0 + RS_ROWS, H);
-    uint8_t* dst = base + dstOff + 4 * wc;
-    for (int py = py0; py < pyEnd; py++) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(base + dstOff) + wc + (size_t)py0 * words;
+    for (int py = py0; py < pyEnd; py++, dst += words) {
         const OrbfeTap ty = ytab[reflect101_clamped(py - ORBFE_YOFF, h)];
         const int r0 = ty.s, r1 = ty.s1;
-        int H0[4], H1[4];
         // all threads of a warp share py, hence r0/r1/c0/c1: the branches below are warp-uniform
-        if (r0 == c0) { for (int i = 0; i < 4; i++) H0[i] = C0[i]; }
-        else if (r0 == c1) { for (int i = 0; i < 4; i++) H0[i] = C1[i]; }
-        else hrow(r0, H0);
-        if (r1 == r0) { for (int i = 0; i < 4; i++) H1[i] = H0[i]; }
-        else if (r1 == c1) { for (int i = 0; i < 4; i++) H1[i] = C1[i]; }
-        else if (r1 == c0) { for (int i = 0; i < 4; i++) H1[i] = C0[i]; }
-        else hrow(r1, H1);
-        c0 = r0; c1 = r1;
-        uint32_t out = 0;
-        const int b0 = ty.a0, b1 = ty.a1;
+        if (r0 != c0) {
+            if (r0 == c1) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            C0[i] = H0[i]; C1[i] = H1[i];
-            const int v = (((b0 * (H0[i] >> 4)) >> 16) + ((b1 * (H1[i] >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)(v & 255) << (8 * i);
+                for (int i = 0; i < 4; i++) C0[i] = C1[i];
+            } else {
+                hrow(r0, C0);
+            }
+            c0 = r0;
         }
-        *reinterpret_cast<uint32_t*>(dst + (size_t)py * pitch) = out;
+        if (r1 != c1) {
+            if (r1 == c0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) C1[i] = C0[i];
+            } else {
+                hrow(r1, C1);
+            }
+            c1 = r1;
+        }
+        // ((b*(H>>4))>>16) == umulhi(b << 16, H >> 4) for the non-negative 11-bit weights
+        const uint32_t b0 = (uint32_t)ty.a0 << 16, b1 = (uint32_t)ty.a1 << 16;
+        uint32_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = (__umulhi(b0, C0[i]) + __umulhi(b1, C1[i]) + 2u) >> 2;
+        *dst = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
 
@@ -192,10 +189,11 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
             const OrbfeLevelGeom& S = g.lv[l - 1];
             const OrbfeTap* xt = taps + L.xtab;
             const OrbfeTap* yt = taps + L.ytab;
-            if (L.mode == 0) {
+            if (L.mode == 0 && L.fastTaps) {
                 dim3 gf(((L.pitch >> 2) + 31) / 32, (L.h + 2 * ORBFE_YOFF + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS), B);
                 k_resize_fast<<<gf, 32 * RS_WARPS, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
-            }
+            } else if (L.mode == 0)
+                k_resize<0><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
             else if (L.mode == 1)
                 k_resize<1><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
             else
