@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=64, help="frames per pipelined chunk on the host-pointer path")
+    ap.add_argument("--chunk", type=int, default=128, help="frames per pipelined chunk on the host-pointer path")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
