@@ -483,9 +483,11 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
     if ((rc = ensure_staging(h, chunk, rows, cols, capacity))) return rc;
     const size_t fbytes = (size_t)rows * cols;
     const bool packed = step == (size_t)cols && frame_stride == fbytes;
-    int ci = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, ci++) {
-        const int nb = std::min(chunk, B - b0), s = ci & 1;
+    int ci = 0, nb = 0;
+    for (int b0 = 0; b0 < B; b0 += nb, ci++) {
+        // a short first chunk shortens the pipeline fill (its H2D cannot overlap any kernels)
+        nb = (ci == 0 && B > chunk) ? std::max(chunk / 4, 1) : std::min(chunk, B - b0);
+        const int s = ci & 1;
         // H2D of this chunk overlaps the kernels of the previous one
         if (ci >= 2) CK(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
         const uint8_t* src = images + (size_t)b0 * frame_stride;

@@ -174,3 +174,18 @@ def test_two_instances_from_two_threads(orbfe):
     for i, img in enumerate((left, right)):
         mo, ko, do = O.Extractor(1200)(img, (0, 0))
         assert outs[i][0] == mo and outs[i][1].tobytes() == ko.tobytes() and np.array_equal(outs[i][2], do)
+
+
+def test_c4_batch_1280x720(orbfe):
+    """C4 shape: a batch of 1280x720 frames, nFeatures 2000, through the batched host API in two
+    chunks; every frame equals the oracle (4096 frames at full size run in bench.py --frames)."""
+    B = 6
+    frames = np.stack([synth.synth_frame(720, 1280, 40 + i) for i in range(B)])
+    ex_g, ex_c = orbfe.ORBextractor(2000), O.Extractor(2000)
+    ex_g(frames[0], None, (0, 1000))
+    ex_g.set_max_bytes(int(ex_g.frame_geometry()["per_frame_bytes"]) * 4)
+    n, mono, kps, desc = ex_g.extract_batch(frames, (0, 1000))
+    for i in range(B):
+        mo, ko, do = ex_c(frames[i], (0, 1000))
+        assert mono[i] == mo and n[i] == len(ko) and 0 < mo < len(ko)       # lapping {0,1000} splits 1280-px frames
+        assert kps[i, :n[i]].tobytes() == ko.tobytes() and np.array_equal(desc[i, :n[i]], do)

@@ -155,3 +155,37 @@ def test_fisheye_stereo_c3(orbfe):
     em, eidx, edist = O.fisheye_matches(oa[2][oa[0]:], ob[2][ob[0]:])
     assert np.array_equal(match, em) and np.array_equal(idx, eidx) and np.array_equal(dist, edist)
     assert (match >= 0).sum() > 100
+
+
+def test_c5_full_size_search_and_knn(orbfe):
+    """C5 at BASELINE size: 1 M map points vs 2000 frame descriptors.  SearchByProjection against the
+    oracle (fast on CPU: few candidates per point); brute-force kNN-2 through size-independent
+    properties (sharded == whole) plus a numpy spot check of 24 queries."""
+    n_map, n_frame = 1000000, 2000
+    d = synth.map_vs_frame(n_map, n_frame, 5)
+    rng = np.random.default_rng(77)
+    pts = _pts_from_map(d, n_map, 1.0, d["scale_factors"], rng)
+    claimed = np.zeros(n_frame, np.uint8)
+    assigned = np.full(n_frame, -1, np.int32)
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], None)
+    m = orbfe.ORBmatcher(nnratio=0.8, checkOri=False)
+    n, asg, bi, bd = m.SearchByProjection(F, pts, claimed, assigned)
+    en, easg, ebi, ebd = O.search_by_projection(d["keys"], d["fdesc"], None, d["bounds"], pts, 0, 100, 0.8, False,
+                                                claimed, assigned, d["scale_factors"])
+    assert n == en and n > 1000
+    assert np.array_equal(bi, ebi) and np.array_equal(bd, ebd) and np.array_equal(asg, easg)
+    # brute force: whole map vs 8 shards merged (the multi-GPU decomposition), then spot check
+    idx, dist, match = m.knn2(d["fdesc"], d["mdesc"])
+    b = np.linspace(0, n_map, 9).astype(int)
+    parts = [m.knn2(d["fdesc"], d["mdesc"][b[g]:b[g + 1]], train_offset=int(b[g])) for g in range(8)]
+    midx, mdist, mmatch = m.knn2_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    assert np.array_equal(midx, idx) and np.array_equal(mdist, dist) and np.array_equal(mmatch, match)
+    lut = np.array([bin(i).count("1") for i in range(256)], np.int32)
+    for q in rng.choice(n_frame, 24, replace=False):
+        dd = lut[d["mdesc"] ^ d["fdesc"][q]].sum(1)
+        order = np.lexsort((np.arange(n_map), dd))[:2]
+        assert list(idx[q]) == list(order) and list(dist[q]) == [int(dd[order[0]]), int(dd[order[1]])]
+    has = np.flatnonzero(d["src"] >= 0)
+    true_of = {int(d["src"][j]): j for j in has[::-1]}
+    hit = sum(1 for q in range(n_frame) if q in true_of and dist[q, 0] <= 60)
+    assert hit > 0.95 * n_frame      # every frame descriptor has a planted near copy in the map
