@@ -102,14 +102,26 @@ struct NmsRow {   // per row, per thread: the horizontal 3-max with and without 
 
 struct NmsMasks { uint32_t lA, rA, lB, rB; };
 
-// Loads one score-map row segment (4 pixels per lane) and forms its horizontal maxima.
-__device__ __forceinline__ void nms_load_row(const uint16_t* __restrict__ row, bool colIn, bool needL, bool needR,
-                                             const NmsMasks& m, NmsRow& R) {
-    uint2 c = make_uint2(0u, 0u);
-    if (colIn) c = *reinterpret_cast<const uint2*>(row);
+struct NmsRaw { uint2 c; uint32_t el, er; };   // a lane's 4 pixels + the words beyond the warp's edges
+
+// Issues the loads of one score-map row segment (4 pixels per lane); nothing is consumed here, so
+// the caller can request row y+2 before it works on row y+1.
+__device__ __forceinline__ NmsRaw nms_fetch_row(const uint16_t* __restrict__ row, bool colIn, bool needL, bool needR) {
+    NmsRaw r;
+    r.c = make_uint2(0u, 0u);
+    r.el = 0u; r.er = 0u;
+    if (colIn) r.c = *reinterpret_cast<const uint2*>(row);
+    if (needL) r.el = *reinterpret_cast<const uint32_t*>(row - 2);     // lane 0: pixels left of the warp
+    if (needR) r.er = *reinterpret_cast<const uint32_t*>(row + 4);     // lane 31: pixels right of the warp
+    return r;
+}
+
+// Forms the horizontal maxima of a fetched row.
+__device__ __forceinline__ void nms_finish_row(const NmsRaw& raw, int lane, const NmsMasks& m, NmsRow& R) {
+    const uint2 c = raw.c;
     uint32_t lw = __shfl_up_sync(0xffffffffu, c.y, 1), rw = __shfl_down_sync(0xffffffffu, c.x, 1);
-    if (needL) lw = *reinterpret_cast<const uint32_t*>(row - 2);     // lane 0: pixels left of the warp
-    if (needR) rw = *reinterpret_cast<const uint32_t*>(row + 4);     // lane 31: pixels right of the warp
+    if (lane == 0) lw = raw.el;
+    if (lane == 31) rw = raw.er;
     const uint32_t s1 = __funnelshift_r(c.x, c.y, 16);               // (p1, p2)
     const uint32_t s0 = __funnelshift_r(lw, c.x, 16) & m.lA;          // (p-1, p0): left neighbours of A
     const uint32_t s2 = __funnelshift_r(c.y, rw, 16) & m.rB;          // (p3, p4): right neighbours of B
@@ -197,20 +209,28 @@ k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict_
     // Rows dy0-1 and dy0+n are only read as neighbours and masked by rowFirst/rowLast at the domain
     // edge; they exist in memory because the level keeps its 19-px border rows.
     NmsRow r0, r1, r2;
-    nms_load_row(row, colIn, needL, needR, m, r0);
-    row += pitch;
-    nms_load_row(row, colIn, needL, needR, m, r1);
+    {
+        const NmsRaw a0 = nms_fetch_row(row, colIn, needL, needR);
+        const NmsRaw a1 = nms_fetch_row(row + pitch, colIn, needL, needR);
+        nms_finish_row(a0, lane, m, r0);
+        nms_finish_row(a1, lane, m, r1);
+    }
+    row += 2 * pitch;                       // next row to fetch: dy0 + 1
     const int n = min(NMS_ROWS, dh - dy0);
     int ry = dy0 % L.hCell;                 // row index inside the cell interior
     const int hLast = L.hCell - 1, bmPitch = L.bmPitch;
-    // three rows per iteration so that the 3-row window rotates without register moves
+    NmsRaw nxt = nms_fetch_row(row, colIn, needL, needR);
+    // three rows per iteration so that the 3-row window rotates without register moves; the loads
+    // of the row after next are always in flight while a row is being processed
     for (int i = 0; i < n; i += 3) {
 #define NMS_STEP(UP, CUR, DN, K)                                                                                  \
         if (i + K < n) {                                                                                          \
+            const NmsRaw got = nxt;                                                                               \
             row += pitch;                                                                                         \
-            nms_load_row(row, colIn, needL, needR, m, DN);                                                        \
+            if (i + K + 1 < n) nxt = nms_fetch_row(row, colIn, needL, needR);                                     \
+            nms_finish_row(got, lane, m, DN);                                                                     \
             nms_emit_row(UP, CUR, DN, ry == 0, ry == hLast || dy0 + i + K == dh - 1, ini2, grp, nibShift, nibMask, \
-                         writer, oMin, oIni);                                                                    \
+                         writer, oMin, oIni);                                                                     \
             oMin += bmPitch; oIni += bmPitch;                                                                     \
             ry = ry == hLast ? 0 : ry + 1;                                                                        \
         }

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(32 * RS_WARPS)
 k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict__ xtab,
               const OrbfeTap* __restrict__ ytab, unsigned srcOff, int srcPitch, unsigned dstOff, int w, int h,
               int pitch) {
-    const int wc = blockIdx.x * 32 + (threadIdx.x & 31);
     const int words = pitch >> 2;
-    if (wc >= words) return;
+    const bool active = blockIdx.x * 32 + (int)(threadIdx.x & 31) < words;   // no early exit: the warp shuffles below
+    const int wc = min(blockIdx.x * 32 + (int)(threadIdx.x & 31), words - 1);
     const int H = h + 2 * ORBFE_YOFF;
     const int py0 = (blockIdx.y * RS_WARPS + (threadIdx.x >> 5)) * RS_ROWS;
     if (py0 >= H) return;
@@ -128,48 +128,72 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
     const int col = ORBFE_XOFF + lo, sh = 8 * (col & 3);
     const int srcWords = srcPitch >> 2;
     const int wi0 = col >> 2, wi1 = min(wi0 + 1, srcWords - 1), wi2 = min(wi0 + 2, srcWords - 1);
-    const uint32_t* sroi = reinterpret_cast<const uint32_t*>(base + srcOff + (size_t)ORBFE_YOFF * srcPitch);
+    const uint32_t* __restrict__ sroi = reinterpret_cast<const uint32_t*>(base + srcOff + (size_t)ORBFE_YOFF * srcPitch);
 
-    auto hrow = [&](int r, uint32_t* Hs) {   // horizontal pass of source row r, already >> 4
-        const uint32_t* rw = sroi + (size_t)r * srcWords;
-        const uint32_t w0 = rw[wi0], w1 = rw[wi1], w2 = rw[wi2];
+    // horizontal pass of one source row segment (three words), already >> 4
+    auto hpass = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t* Hs) {
         const uint32_t lo8 = __funnelshift_r(w0, w1, sh), hi8 = __funnelshift_r(w1, w2, sh);
 #pragma unroll
         for (int i = 0; i < 4; i++) Hs[i] = __dp2a_lo(wgt[i], __byte_perm(lo8, hi8, sel[i]), 0u) >> 4;
     };
 
+    // The y-taps of the strip are fetched once (lane i holds the tap of row py0+i) and handed out
+    // by shuffle; the source words of the NEXT destination row are requested before the current row
+    // is computed, so no global-load latency sits on the row-to-row dependency chain.
+    const int lane = threadIdx.x & 31;
+    OrbfeTap myTap = {0, 0, 0, 0};
+    if (lane < RS_ROWS) myTap = ytab[reflect101_clamped(min(py0 + lane, H - 1) - ORBFE_YOFF, h)];
+    const unsigned tapS = (uint32_t)(uint16_t)myTap.s | ((uint32_t)(uint16_t)myTap.s1 << 16);
+    const unsigned tapA = (uint32_t)(uint16_t)myTap.a0 | ((uint32_t)(uint16_t)myTap.a1 << 16);
+
     int c0 = -1, c1 = -1;
     uint32_t C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0};   // cached horizontal passes of source rows c0, c1
-    const int pyEnd = min(py0 + RS_ROWS, H);
+    const int n = min(RS_ROWS, H - py0);
     uint32_t* dst = reinterpret_cast<uint32_t*>(base + dstOff) + wc + (size_t)py0 * words;
-    for (int py = py0; py < pyEnd; py++, dst += words) {
-        const OrbfeTap ty = ytab[reflect101_clamped(py - ORBFE_YOFF, h)];
-        const int r0 = ty.s, r1 = ty.s1;
-        // all threads of a warp share py, hence r0/r1/c0/c1: the branches below are warp-uniform
+    unsigned rs = __shfl_sync(0xffffffffu, tapS, 0);
+    uint32_t p0[3], p1[3];   // prefetched words of source rows r0 and r1 of the current row
+    {
+        const uint32_t* ra = sroi + (size_t)(rs & 0xFFFFu) * srcWords;
+        const uint32_t* rb = sroi + (size_t)(rs >> 16) * srcWords;
+        p0[0] = ra[wi0]; p0[1] = ra[wi1]; p0[2] = ra[wi2];
+        p1[0] = rb[wi0]; p1[1] = rb[wi1]; p1[2] = rb[wi2];
+    }
+    for (int i = 0; i < n; i++, dst += words) {
+        const int r0 = (int)(rs & 0xFFFFu), r1 = (int)(rs >> 16);
+        const unsigned wa = __shfl_sync(0xffffffffu, tapA, i);
+        uint32_t q0[3] = {p0[0], p0[1], p0[2]}, q1[3] = {p1[0], p1[1], p1[2]};
+        if (i + 1 < n) {   // request the next row's source words now
+            rs = __shfl_sync(0xffffffffu, tapS, i + 1);
+            const uint32_t* ra = sroi + (size_t)(rs & 0xFFFFu) * srcWords;
+            const uint32_t* rb = sroi + (size_t)(rs >> 16) * srcWords;
+            p0[0] = ra[wi0]; p0[1] = ra[wi1]; p0[2] = ra[wi2];
+            p1[0] = rb[wi0]; p1[1] = rb[wi1]; p1[2] = rb[wi2];
+        }
+        // all threads of a warp share the row, hence r0/r1/c0/c1: the branches below are warp-uniform
         if (r0 != c0) {
             if (r0 == c1) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) C0[i] = C1[i];
+                for (int k = 0; k < 4; k++) C0[k] = C1[k];
             } else {
-                hrow(r0, C0);
+                hpass(q0[0], q0[1], q0[2], C0);
             }
             c0 = r0;
         }
         if (r1 != c1) {
             if (r1 == c0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) C1[i] = C0[i];
+                for (int k = 0; k < 4; k++) C1[k] = C0[k];
             } else {
-                hrow(r1, C1);
+                hpass(q1[0], q1[1], q1[2], C1);
             }
             c1 = r1;
         }
         // ((b*(H>>4))>>16) == umulhi(b << 16, H >> 4) for the non-negative 11-bit weights
-        const uint32_t b0 = (uint32_t)ty.a0 << 16, b1 = (uint32_t)ty.a1 << 16;
+        const uint32_t b0 = wa << 16, b1 = wa & 0xFFFF0000u;
         uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = (__umulhi(b0, C0[i]) + __umulhi(b1, C1[i]) + 2u) >> 2;
-        *dst = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, C0[k]) + __umulhi(b1, C1[k]) + 2u) >> 2;
+        if (active) *dst = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
     }
 }
 
