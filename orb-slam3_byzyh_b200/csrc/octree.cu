@@ -12,6 +12,7 @@
 namespace {
 
 constexpr int OC_THREADS = 128;
+static_assert(OC_THREADS <= OC_MAX_NT, "oc_rebuild_phase1 scratch");
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warpSums, int* total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -34,6 +35,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warpSums, int* t
     return base + incl - v;
 }
 
+// kShared: the node tables live in dynamic shared memory (the pointer provenance stays visible to
+// the compiler, so table accesses are LDS/STS/ATOMS instead of generic loads); otherwise in a
+// global scratch block (very large nfeatures).
+template <bool kShared>
 __global__ void __launch_bounds__(OC_THREADS)
 k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ slots,
          const int* __restrict__ cellCount, uint32_t* __restrict__ cand, uint32_t* __restrict__ pnode,
@@ -81,11 +86,11 @@ k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ 
 
     // ---- quadtree ----
     const int M = L.ocM;
-    char* mem = g.ocShared ? smem : ocGlobal + ((size_t)frame * g.nlevels + level) * ocGlobalStride;
+    char* mem = kShared ? smem : ocGlobal + ((size_t)frame * g.nlevels + level) * ocGlobalStride;
     OcWork w;
     oc_carve(w, mem, M);
-    int* out_idx = (int*)(mem + oc_shared_bytes(M));
-    int* best = out_idx + M;
+    int* out_idx = w.cc;     // the child tables are dead once the list is final: reuse them for the
+    int* best = w.cpos;      // per-node winner selection
     w.pk = pk;
     w.pnode = pn;
     w.n = n;
@@ -103,8 +108,8 @@ k_octree_debug(const uint32_t* pk, uint32_t* pnode, int n, int width, int height
                int N, int M, int* out, int* outn, char* tables) {
     OcWork w;
     oc_carve(w, tables, M);
-    int* out_idx = (int*)(tables + oc_shared_bytes(M));
-    int* best = out_idx + M;
+    int* out_idx = w.cc;
+    int* best = w.cpos;
     w.pk = pk;
     w.pnode = pnode;
     w.n = n;
@@ -114,7 +119,7 @@ k_octree_debug(const uint32_t* pk, uint32_t* pnode, int n, int width, int height
     if (threadIdx.x == 0) *outn = s_outn;
 }
 
-size_t oc_total_bytes(int M) { return oc_shared_bytes(M) + 2 * sizeof(int) * (size_t)M + 64; }
+size_t oc_total_bytes(int M) { return oc_shared_bytes(M) + 64; }
 
 }  // namespace
 
@@ -128,7 +133,7 @@ int orbfe_octree_prepare(OrbfeFrameGeom& g) {
     if (need <= 200 * 1024) {
         g.ocShared = (int)need;
         if (need > 48 * 1024 &&
-            cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            cudaFuncSetAttribute(k_octree<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return -1;
     } else {
         g.ocShared = 0;
@@ -138,8 +143,12 @@ int orbfe_octree_prepare(OrbfeFrameGeom& g) {
 
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches) {
-    k_octree<<<dim3(g.nlevels, B), OC_THREADS, g.ocShared, st>>>(
-        g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
+    if (g.ocShared)
+        k_octree<true><<<dim3(g.nlevels, B), OC_THREADS, g.ocShared, st>>>(
+            g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
+    else
+        k_octree<false><<<dim3(g.nlevels, B), OC_THREADS, 0, st>>>(
+            g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
     ++*launches;
 }
 

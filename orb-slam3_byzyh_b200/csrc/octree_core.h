@@ -55,7 +55,7 @@
 #define OC_PK_S(p) ((int)((p) >> 24))
 #define OC_PACK(x, y, s) (((uint32_t)(s) << 24) | ((uint32_t)(y) << 12) | (uint32_t)(x))
 
-struct OcNodes {  // one node-list buffer (structure of arrays, capacity M)
+struct OcNodes {  // the two node-list buffers (structure of arrays); buffer b = entries [b*M, (b+1)*M)
     short* x0;
     short* x1;
     short* y0;
@@ -68,21 +68,24 @@ struct OcWork {
     uint32_t* pnode;     // n: node index [23:0] | quadrant [31:30]
     int n;
     int M;               // node capacity: max(N + 3, 4 * nIni) + 1
-    OcNodes nb[2];       // double-buffered node list
+    OcNodes nd;          // double-buffered node list: buffer b lives at index offset b*M (no pointer tables
+                         // indexed at run time, which would push this struct into local memory)
     int* cc;             // [4M] child populations of the current pass
     int* cpos;           // [4M] child -> index in the next list (-1 = empty)
     int* remap;          // [M]  undivided node -> index in the next list (-1 = divided)
     uint64_t* vs;        // [M]  expandable nodes, creation order: key<<32 | node
     uint64_t* vs2;       // [M]  scratch for the next creation-order list
-    int* sc;             // [8]  shared scalars
+    int* sc;             // [16] shared scalars
+    int* part;           // [3 * OC_MAX_NT] per-thread partial sums of the parallel list rebuild
 };
 enum { OC_SIZE = 0, OC_CUR = 1, OC_NV = 2, OC_STATE = 3, OC_NTOEXP = 4 };
+#define OC_MAX_NT 128   // largest CTA size oc_distribute may be called with
 enum { OC_ST_PHASE1 = 0, OC_ST_PHASE2 = 1, OC_ST_DONE = 2 };
 
 static OC_HD size_t oc_shared_bytes(int M) {
     // 2 buffers x (4 shorts + 1 int) + cc + cpos (4 ints each) + remap + vs + vs2 + scalars
     return (size_t)M * (2 * (4 * sizeof(short) + sizeof(int)) + 8 * sizeof(int) + sizeof(int) +
-                        2 * sizeof(uint64_t)) + 16 * sizeof(int) + 64;
+                        2 * sizeof(uint64_t)) + 16 * sizeof(int) + 64 + 3 * OC_MAX_NT * sizeof(int);
 }
 
 // ---- libstdc++ std::sort emulation on key<<32|payload words (compare on the key only) ----
@@ -212,20 +215,20 @@ static OC_HD int oc_half(int lo, int hi) {  // ceil(static_cast<float>(hi-lo)/2)
     const int d = hi - lo;
     return d >= 0 ? (d + 1) / 2 : -((-d) / 2);
 }
-static OC_HD void oc_make_child(const OcNodes& src, int j, int q, const OcNodes& dst, int pos,
-                                int count) {
-    const int X0 = src.x0[j], X1 = src.x1[j], Y0 = src.y0[j], Y1 = src.y1[j];
+// `j` and `pos` are absolute table indices (buffer offset already added).
+static OC_HD void oc_make_child(const OcNodes& nd, int j, int q, int pos, int count) {
+    const int X0 = nd.x0[j], X1 = nd.x1[j], Y0 = nd.y0[j], Y1 = nd.y1[j];
     const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
-    dst.x0[pos] = (short)((q & 1) ? mx : X0);
-    dst.x1[pos] = (short)((q & 1) ? X1 : mx);
-    dst.y0[pos] = (short)((q & 2) ? my : Y0);
-    dst.y1[pos] = (short)((q & 2) ? Y1 : my);
-    dst.cnt[pos] = count;
+    nd.x0[pos] = (short)((q & 1) ? mx : X0);
+    nd.x1[pos] = (short)((q & 1) ? X1 : mx);
+    nd.y0[pos] = (short)((q & 2) ? my : Y0);
+    nd.y1[pos] = (short)((q & 2) ? Y1 : my);
+    nd.cnt[pos] = count;
 }
-static OC_HD void oc_copy_node(const OcNodes& src, int j, const OcNodes& dst, int pos) {
-    dst.x0[pos] = src.x0[j]; dst.x1[pos] = src.x1[j];
-    dst.y0[pos] = src.y0[j]; dst.y1[pos] = src.y1[j];
-    dst.cnt[pos] = src.cnt[j];
+static OC_HD void oc_copy_node(const OcNodes& nd, int j, int pos) {
+    nd.x0[pos] = nd.x0[j]; nd.x1[pos] = nd.x1[j];
+    nd.y0[pos] = nd.y0[j]; nd.y1[pos] = nd.y1[j];
+    nd.cnt[pos] = nd.cnt[j];
 }
 
 // The point sweeps issue OC_ILP independent loads per thread before using any of them: the points
@@ -234,8 +237,8 @@ static OC_HD void oc_copy_node(const OcNodes& src, int j, const OcNodes& dst, in
 
 // One sweep over the points: quadrant of every point that sits in an expandable node.
 static OC_HD void oc_count_children(const OcWork& w) {
-    const int cur = w.sc[OC_CUR];
-    const OcNodes& nd = w.nb[cur];
+    const OcNodes& nd = w.nd;
+    const int so = w.sc[OC_CUR] * w.M;     // offset of the current list buffer
     const int size = w.sc[OC_SIZE];
     OC_PAR_FOR(k, 4 * size) w.cc[k] = 0;
     OC_SYNC();
@@ -251,8 +254,8 @@ static OC_HD void oc_count_children(const OcWork& w) {
         for (int u = 0; u < OC_ILP; u++) {
             const int i = i0 + u * OC_NT;
             const int j = (int)(lab[u] & 0xFFFFFFu);
-            if (i < w.n && nd.cnt[j] > 1) {
-                const int X0 = nd.x0[j], X1 = nd.x1[j], Y0 = nd.y0[j], Y1 = nd.y1[j];
+            if (i < w.n && nd.cnt[so + j] > 1) {
+                const int X0 = nd.x0[so + j], X1 = nd.x1[so + j], Y0 = nd.y0[so + j], Y1 = nd.y1[so + j];
                 const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
                 const int q = (OC_PK_X(p[u]) < mx ? 0 : 1) + (OC_PK_Y(p[u]) < my ? 0 : 2);
                 w.pnode[i] = (uint32_t)j | ((uint32_t)q << 30);
@@ -285,6 +288,78 @@ static OC_HD void oc_relabel(const OcWork& w) {
     OC_SYNC();
 }
 
+// Phase-1 list rebuild (:805-930), all threads.  The reference walks the list once, replacing
+// every expandable node by its non-empty children (push_front) and leaving the others in place;
+// the resulting order is: children of node size-1 (n4..n1), ..., children of node 0, then the
+// undivided nodes in their old order.  Every position is therefore a prefix sum over the old list:
+// three scans (non-empty children, undivided nodes, children with more than one point) give all
+// threads their write offsets, so no thread walks the list alone.
+static OC_HD void oc_rebuild_phase1(const OcWork& w, int N) {
+    const int cur = w.sc[OC_CUR];
+    const OcNodes& nd = w.nd;
+    const int so = cur * w.M, dof = (cur ^ 1) * w.M;   // source / destination list buffers
+    const int size = w.sc[OC_SIZE];
+    const int nt = OC_NT, tid = OC_TID;
+    const int chunk = (size + nt - 1) / nt;
+    const int j0 = tid * chunk < size ? tid * chunk : size, j1 = j0 + chunk < size ? j0 + chunk : size;
+    int sk = 0, sne = 0, sm = 0;
+    for (int j = j0; j < j1; j++) {
+        if (nd.cnt[so + j] > 1) {
+            for (int q = 0; q < 4; q++) {
+                const int c = w.cc[4 * j + q];
+                sk += c > 0;
+                sm += c > 1;
+            }
+        } else {
+            sne++;
+        }
+    }
+    w.part[tid] = sk; w.part[nt + tid] = sne; w.part[2 * nt + tid] = sm;
+    OC_SYNC();
+    int preK = 0, preNE = 0, preM = 0, totK = 0, totNE = 0, totM = 0;
+    for (int t = 0; t < nt; t++) {
+        const int a = w.part[t], b = w.part[nt + t], c = w.part[2 * nt + t];
+        if (t < tid) { preK += a; preNE += b; preM += c; }
+        totK += a; totNE += b; totM += c;
+    }
+    for (int j = j0; j < j1; j++) {
+        if (nd.cnt[so + j] > 1) {
+            int k = 0;
+            for (int q = 0; q < 4; q++) k += w.cc[4 * j + q] > 0;
+            preK += k;
+            int pos = totK - preK;   // children of later nodes sit nearer the front (push_front)
+            w.remap[j] = -1;
+            for (int q = 3; q >= 0; q--) {
+                const int c = w.cc[4 * j + q];
+                if (c > 0) { oc_make_child(nd, so + j, q, dof + pos, c); w.cpos[4 * j + q] = pos++; }
+                else w.cpos[4 * j + q] = -1;
+            }
+            for (int q = 0; q < 4; q++) {
+                const int c = w.cc[4 * j + q];
+                if (c > 1) {
+                    const int cp = w.cpos[4 * j + q];
+                    w.vs[preM++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)nd.x0[dof + cp]) << 32) | (uint32_t)cp;
+                }
+            }
+        } else {
+            const int pos = totK + preNE++;
+            oc_copy_node(nd, so + j, dof + pos);
+            w.remap[j] = pos;
+        }
+    }
+    OC_SYNC();
+    if (tid == 0) {
+        const int newSize = totK + totNE;
+        int st = OC_ST_PHASE1;
+        if (newSize >= N || newSize == size) st = OC_ST_DONE;
+        else if (newSize + totM * 3 > N) st = OC_ST_PHASE2;   // :932, nToExpand == totM
+        w.sc[OC_STATE] = st;
+        w.sc[OC_NV] = totM;
+        w.sc[OC_SIZE] = newSize;
+        w.sc[OC_CUR] = cur ^ 1;
+    }
+}
+
 // Runs the whole distribution.  Output: out_idx[k] = candidate index retained by the k-th
 // node of the final list (front to back); returns the number of nodes via *out_n (thread 0
 // writes it; visible to all threads after the final OC_SYNC).
@@ -293,7 +368,7 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
                                 int* out_idx, int* out_n, int* best_score /*[M] scratch*/) {
     // ---- roots (:718-790) ----
     if (OC_TID == 0) {
-        const OcNodes& nd = w.nb[0];
+        const OcNodes& nd = w.nd;
         for (int i = 0; i < nIni; i++) {
             nd.x0[i] = (short)(int)OC_FMUL(hX, (float)i);
             nd.x1[i] = (short)(int)OC_FMUL(hX, (float)(i + 1));
@@ -307,16 +382,15 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
     OC_PAR_FOR(i, w.n) {
         int r = (int)OC_FDIV((float)OC_PK_X(w.pk[i]), hX);
         w.pnode[i] = (uint32_t)r;
-        OC_ATOMIC_ADD(&w.nb[0].cnt[r], 1);
+        OC_ATOMIC_ADD(&w.nd.cnt[r], 1);
     }
     OC_SYNC();
     if (OC_TID == 0) {  // erase empty roots, keep order
-        const OcNodes& s = w.nb[0];
-        const OcNodes& d = w.nb[1];
+        const OcNodes& nd = w.nd;
         int pos = 0;
         for (int i = 0; i < nIni; i++) {
             w.cpos[4 * i] = w.cpos[4 * i + 1] = w.cpos[4 * i + 2] = w.cpos[4 * i + 3] = -1;
-            if (s.cnt[i] > 0) { oc_copy_node(s, i, d, pos); w.remap[i] = pos++; }
+            if (nd.cnt[i] > 0) { oc_copy_node(nd, i, w.M + pos); w.remap[i] = pos++; }
             else w.remap[i] = -1;
         }
         w.sc[OC_CUR] = 1;
@@ -333,43 +407,15 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
         const int state = w.sc[OC_STATE];
         if (state == OC_ST_DONE) break;
         oc_count_children(w);
-        if (OC_TID == 0) {
+        if (state == OC_ST_PHASE1) {
+            oc_rebuild_phase1(w, N);
+        } else if (OC_TID == 0) {
             const int cur = w.sc[OC_CUR];
-            const OcNodes& s = w.nb[cur];
-            const OcNodes& d = w.nb[cur ^ 1];
+            const OcNodes& nd = w.nd;
+            const int so = cur * w.M, dof = (cur ^ 1) * w.M;
             const int size = w.sc[OC_SIZE];
             int pos = 0, nv = 0, newSize = size;
-            if (state == OC_ST_PHASE1) {
-                // children of later-visited nodes end up nearer the front (push_front)
-                for (int j = size - 1; j >= 0; j--) {
-                    if (s.cnt[j] > 1) {
-                        w.remap[j] = -1;
-                        for (int q = 3; q >= 0; q--) {
-                            const int c = w.cc[4 * j + q];
-                            if (c > 0) { oc_make_child(s, j, q, d, pos, c); w.cpos[4 * j + q] = pos++; }
-                            else w.cpos[4 * j + q] = -1;
-                        }
-                    }
-                }
-                for (int j = 0; j < size; j++)
-                    if (s.cnt[j] <= 1) { oc_copy_node(s, j, d, pos); w.remap[j] = pos++; }
-                newSize = pos;
-                int nToExpand = 0;
-                for (int j = 0; j < size; j++)
-                    if (s.cnt[j] > 1)
-                        for (int q = 0; q < 4; q++) {
-                            const int c = w.cc[4 * j + q];
-                            if (c > 1) {
-                                nToExpand++;
-                                const int cp = w.cpos[4 * j + q];
-                                w.vs[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)d.x0[cp]) << 32) | (uint32_t)cp;
-                            }
-                        }
-                int st = OC_ST_PHASE1;
-                if (newSize >= N || newSize == size) st = OC_ST_DONE;
-                else if (newSize + nToExpand * 3 > N) st = OC_ST_PHASE2;
-                w.sc[OC_STATE] = st;
-            } else {
+            {
                 // phase 2 (:934-1015): largest nodes first, one at a time, stop at N
                 const int np = w.sc[OC_NV];
                 oc_std_sort(w.vs, np);
@@ -390,19 +436,19 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
                     w.remap[j] = -1;
                     for (int q = 3; q >= 0; q--) {
                         const int c = w.cc[4 * j + q];
-                        if (c > 0) { oc_make_child(s, j, q, d, pos, c); w.cpos[4 * j + q] = pos++; }
+                        if (c > 0) { oc_make_child(nd, so + j, q, dof + pos, c); w.cpos[4 * j + q] = pos++; }
                         else w.cpos[4 * j + q] = -1;
                     }
                 }
                 for (int j = 0; j < size; j++)
-                    if (w.remap[j] != -1) { oc_copy_node(s, j, d, pos); w.remap[j] = pos++; }
+                    if (w.remap[j] != -1) { oc_copy_node(nd, so + j, dof + pos); w.remap[j] = pos++; }
                 for (int t = 0; t < ndiv; t++) {
                     const int j = (int)(w.vs[np - 1 - t] & 0xFFFFFFFFu);
                     for (int q = 0; q < 4; q++) {
                         const int c = w.cc[4 * j + q];
                         if (c > 1) {
                             const int cp = w.cpos[4 * j + q];
-                            w.vs2[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)d.x0[cp]) << 32) | (uint32_t)cp;
+                            w.vs2[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)nd.x0[dof + cp]) << 32) | (uint32_t)cp;
                         }
                     }
                 }
@@ -462,12 +508,11 @@ static OC_HD void oc_carve(OcWork& w, void* mem, int M) {
     w.cc = (int*)p; p += sizeof(int) * 4 * M;
     w.cpos = (int*)p; p += sizeof(int) * 4 * M;
     w.remap = (int*)p; p += sizeof(int) * M;
-    for (int b = 0; b < 2; b++) { w.nb[b].cnt = (int*)p; p += sizeof(int) * M; }
+    w.nd.cnt = (int*)p; p += sizeof(int) * 2 * M;
     w.sc = (int*)p; p += sizeof(int) * 16;
-    for (int b = 0; b < 2; b++) {
-        w.nb[b].x0 = (short*)p; p += sizeof(short) * M;
-        w.nb[b].x1 = (short*)p; p += sizeof(short) * M;
-        w.nb[b].y0 = (short*)p; p += sizeof(short) * M;
-        w.nb[b].y1 = (short*)p; p += sizeof(short) * M;
-    }
+    w.part = (int*)p; p += sizeof(int) * 3 * OC_MAX_NT;
+    w.nd.x0 = (short*)p; p += sizeof(short) * 2 * M;
+    w.nd.x1 = (short*)p; p += sizeof(short) * 2 * M;
+    w.nd.y0 = (short*)p; p += sizeof(short) * 2 * M;
+    w.nd.y1 = (short*)p; p += sizeof(short) * 2 * M;
 }

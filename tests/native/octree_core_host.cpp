@@ -21,10 +21,9 @@ extern "C" int octree_core_host(const int* xys, int n, int minX, int maxX, int m
     OcWork w;
     oc_carve(w, mem.data(), M);
     w.pk = pk.data(); w.pnode = pnode.data(); w.n = n;
-    std::vector<int> out(M), best(M);
     int outn = 0;
-    oc_distribute(w, width, height, nIni, hX, N, out.data(), &outn, best.data());
-    for (int i = 0; i < outn && i < cap; i++) keep[i] = out[i];
+    oc_distribute(w, width, height, nIni, hX, N, w.cc, &outn, w.cpos);   // same aliasing as the kernel
+    for (int i = 0; i < outn && i < cap; i++) keep[i] = w.cc[i];
     return outn;
 }
 
