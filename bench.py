@@ -208,7 +208,7 @@ def run_ours(args):
     clocks = ClockSampler(local)
     clocks.start()
     t_wait = time.time()
-    while not clocks.lines and time.time() - t_wait < 5.0:     # nvidia-smi needs ~1 s to start sampling
+    while len(clocks.lines) < 6 and time.time() - t_wait < 6.0:  # nvidia-smi needs ~1 s to start; sample under this load
         step_device()
         st.synchronize()
     barrier()
