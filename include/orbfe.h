@@ -193,6 +193,22 @@ int orbfe_search_by_projection(const OrbfeFrameView* frame, const OrbfeProjPoint
                                int32_t* assigned, int32_t* best_idx, int32_t* best_dist,
                                int device);
 
+/* The same search on a fisheye stereo frame (F.Nleft != -1): modes ORBFE_SEARCH_MAPPOINTS
+ * (src/ORBmatcher.cc:46-240 incl. the right-camera branch :171-237 and the mvLeftToRightMatch /
+ * mvRightToLeftMatch partner writes :159-163, :215-219) and ORBFE_SEARCH_LASTFRAME (:1951-2185
+ * incl. :2090-2155).  `left` = mvKeys + descriptor rows [0,Nleft), `right` = mvKeysRight + rows
+ * [Nleft,N) (both with the frame's grid bounds); l2r / r2l = mvLeftToRightMatch /
+ * mvRightToLeftMatch (-1 = none).  pts_left carries the left projections plus the shared angle /
+ * blocks / desc arrays, pts_right the right-camera projections (u, v, radius, levels, valid =
+ * mbTrackInViewR && mnTrackScaleLevelR != -1 for mode 0).  claimed / assigned are indexed like
+ * F.mvpMapPoints: [0,Nleft) left, [Nleft,N) right. */
+int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, const OrbfeFrameView* right,
+                                       const int32_t* l2r, const int32_t* r2l,
+                                       const OrbfeProjPoints* pts_left, const OrbfeProjPoints* pts_right,
+                                       const OrbfeSearchParams* prm, const uint8_t* claimed,
+                                       int32_t* assigned, int32_t* best_idx_left,
+                                       int32_t* best_idx_right, int device);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

@@ -156,6 +156,103 @@ int search_by_projection(FrameView& F, const std::vector<ProjPoint>& pts, const 
     return nmatches;
 }
 
+// reference src/ORBmatcher.cc:46-240 (mode 0) and :1951-2185 (mode 1) with F.Nleft != -1
+int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, const int* r2l,
+                                 const std::vector<ProjPoint>& ptsL, const std::vector<ProjPoint>& ptsR,
+                                 const uint8_t* pdesc, const SearchParams& prm, const uint8_t* claimed0,
+                                 int* assigned, int* best_idx_l, int* best_idx_r) {
+    const int Nl = FL.N, N = FL.N + FR.N;
+    int nmatches = 0;
+    std::vector<uint8_t> claimed(claimed0, claimed0 + N);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    // one window search; slotOff maps a keypoint index of `F` to its F.mvpMapPoints slot
+    auto window = [&](FrameView& F, int slotOff, const ProjPoint& p, const uint8_t* dMP, bool second, bool& had,
+                      int& bestDist, int& bestLevel, int& bestDist2, int& bestLevel2, int& bestIdx) {
+        bestDist = 256; bestLevel = -1; bestDist2 = 256; bestLevel2 = -1; bestIdx = -1;
+        const std::vector<int> vIndices = F.features_in_area(p.u, p.v, p.radius, p.minLevel, p.maxLevel);
+        had = !vIndices.empty();
+        for (int idx : vIndices) {
+            if (claimed[idx + slotOff]) continue;
+            const int dist = descriptor_distance(dMP, F.desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist;
+                bestLevel2 = bestLevel; bestLevel = F.keys[idx].octave;
+                bestIdx = idx;
+            } else if (second && dist < bestDist2) {
+                bestLevel2 = F.keys[idx].octave;
+                bestDist2 = dist;
+            }
+        }
+    };
+    auto vote = [&](float angLast, float angCur, int slot) {
+        float rot = angLast - angCur;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)roundf(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(slot);
+    };
+    for (size_t j = 0; j < ptsL.size(); j++) {
+        const ProjPoint &pL = ptsL[j], &pR = ptsR[j];
+        const uint8_t* dMP = pdesc + 32 * j;
+        best_idx_l[j] = -1;
+        best_idx_r[j] = -1;
+        int bD, bL, bD2, bL2, bI;
+        bool had = false;
+        if (prm.mode == 0) {
+            if (pL.valid) {
+                window(FL, 0, pL, dMP, true, had, bD, bL, bD2, bL2, bI);
+                if (had && bD <= prm.thAccept) {
+                    if (bL == bL2 && bD > prm.nnratio * bD2) continue;   // :154 skips the right camera too
+                    assigned[bI] = (int)j; claimed[bI] = pL.blocks;
+                    if (l2r[bI] != -1) { assigned[l2r[bI] + Nl] = (int)j; claimed[l2r[bI] + Nl] = pL.blocks; nmatches++; }
+                    nmatches++;
+                    best_idx_l[j] = bI;
+                }
+            }
+            if (pR.valid) {
+                window(FR, Nl, pR, dMP, true, had, bD, bL, bD2, bL2, bI);
+                if (!had) continue;
+                if (bD <= prm.thAccept) {
+                    if (bL == bL2 && bD > prm.nnratio * bD2) continue;
+                    if (r2l[bI] != -1) { assigned[r2l[bI]] = (int)j; claimed[r2l[bI]] = pL.blocks; nmatches++; }
+                    assigned[bI + Nl] = (int)j; claimed[bI + Nl] = pL.blocks;
+                    nmatches++;
+                    best_idx_r[j] = bI;
+                }
+            }
+        } else {
+            if (!pL.valid) continue;
+            window(FL, 0, pL, dMP, false, had, bD, bL, bD2, bL2, bI);
+            if (!had) continue;                                          // :2027 skips the right camera too
+            if (bD <= prm.thAccept) {
+                assigned[bI] = (int)j; claimed[bI] = pL.blocks;
+                nmatches++;
+                best_idx_l[j] = bI;
+                if (prm.checkOrientation) vote(pL.angle, FL.keys[bI].angle, bI);
+            }
+            window(FR, Nl, pR, dMP, false, had, bD, bL, bD2, bL2, bI);
+            if (bD <= prm.thAccept) {
+                assigned[bI + Nl] = (int)j; claimed[bI + Nl] = pL.blocks;
+                nmatches++;
+                best_idx_r[j] = bI;
+                if (prm.checkOrientation) vote(pL.angle, FR.keys[bI].angle, bI + Nl);
+            }
+        }
+    }
+    if (prm.mode != 0 && prm.checkOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int k : rotHist[i]) {
+                    assigned[k] = -1;
+                    nmatches--;
+                }
+    }
+    return nmatches;
+}
+
 // reference src/Frame.cc:1102-1358
 void compute_stereo_matches(const OrbKp* keysL, const uint8_t* descL, int N, const OrbKp* keysR,
                             const uint8_t* descR, int Nr, const PyrLevelView* pyrL,

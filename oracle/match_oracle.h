@@ -72,6 +72,16 @@ int search_by_projection(FrameView& F, const std::vector<ProjPoint>& pts, const 
                          const SearchParams& prm, const uint8_t* claimed, int* assigned,
                          int* best_idx, int* best_dist);
 
+// The same two overloads for a fisheye stereo frame (Nleft != -1): src/ORBmatcher.cc:46-240 incl. the
+// right-camera branch :171-237 and the mvLeftToRightMatch / mvRightToLeftMatch partner writes
+// (:159-163, :215-219), and :1951-2185 incl. the right-camera branch :2090-2155.  FL holds mvKeys /
+// left grid / descriptor rows [0,Nleft), FR holds mvKeysRight / right grid / rows [Nleft,N).
+// claimed / assigned are indexed like F.mvpMapPoints: [0,Nleft) left, [Nleft,N) right.
+int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, const int* r2l,
+                                 const std::vector<ProjPoint>& ptsL, const std::vector<ProjPoint>& ptsR,
+                                 const uint8_t* pdesc, const SearchParams& prm, const uint8_t* claimed,
+                                 int* assigned, int* best_idx_l, int* best_idx_r);
+
 // Frame::ComputeStereoMatches on two extractor pyramids.
 struct PyrLevelView {
     const uint8_t* roi;

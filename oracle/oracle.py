@@ -264,3 +264,27 @@ def stereo_match(exL, exR, keysL, descL, keysR, descR, mbf, mb):
                               _p(keysR), _p(descR), len(keysR), C.c_float(mbf), C.c_float(mb),
                               _p(ur), _p(dp))
     return ur, dp
+
+
+def search_by_projection_fisheye(keysL, descL, keysR, descR, bounds, l2r, r2l, ptsL, ptsR, mode, th_accept, nnratio,
+                                 check_orientation, claimed, assigned):
+    """ptsL: dict as for search_by_projection (u,v,radius,min_level,max_level,angle,valid,blocks,desc);
+    ptsR: dict with u,v,radius,min_level,max_level,valid for the right camera."""
+    keep = []
+    fl = make_frame_view(keysL, descL, None, bounds, keep)
+    fr = make_frame_view(keysR, descR, None, bounds, keep)
+    full = dict(ptsL)
+    full.setdefault("ur", np.zeros(len(ptsL["u"]), np.float32))
+    pl = make_proj_points(full, keep)
+    fr_pts = dict(full)
+    fr_pts.update(ptsR)
+    pr = make_proj_points(fr_pts, keep)
+    prm = SearchParamsC(mode, th_accept, nnratio, int(check_orientation))
+    l2r = np.ascontiguousarray(l2r, np.int32)
+    r2l = np.ascontiguousarray(r2l, np.int32)
+    claimed = np.ascontiguousarray(claimed, np.uint8)
+    assigned = np.ascontiguousarray(assigned, np.int32).copy()
+    bl, br = np.empty(pl.m, np.int32), np.empty(pl.m, np.int32)
+    n = lib().oracle_search_by_projection_fisheye(C.byref(fl), C.byref(fr), _p(l2r), _p(r2l), C.byref(pl), C.byref(pr),
+                                                  C.byref(prm), _p(claimed), _p(assigned), _p(bl), _p(br))
+    return n, assigned, bl, br

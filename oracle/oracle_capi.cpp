@@ -143,6 +143,36 @@ int oracle_search_by_projection(const OrbfeFrameView* fv, const OrbfeProjPoints*
     return n;
 }
 
+static void fill_view(match_oracle::FrameView& F, const OrbfeFrameView* fv) {
+    F.N = fv->n; F.keys = (const OrbKp*)fv->keys; F.uright = fv->uright; F.desc = fv->desc;
+    F.minX = fv->min_x; F.minY = fv->min_y; F.maxX = fv->max_x; F.maxY = fv->max_y;
+    F.gridWInv = fv->grid_w_inv; F.gridHInv = fv->grid_h_inv;
+    F.assign_features_to_grid();
+}
+static std::vector<match_oracle::ProjPoint> fill_pts(const OrbfeProjPoints* pp, const OrbfeProjPoints* shared) {
+    std::vector<match_oracle::ProjPoint> pts(pp->m);
+    for (int j = 0; j < pp->m; j++) {
+        match_oracle::ProjPoint& p = pts[j];
+        p.u = pp->u[j]; p.v = pp->v[j]; p.ur = 0.f;
+        p.radius = pp->radius[j]; p.minLevel = pp->min_level[j]; p.maxLevel = pp->max_level[j];
+        p.angle = shared->angle ? shared->angle[j] : 0.f;
+        p.valid = pp->valid ? pp->valid[j] : 1; p.blocks = shared->blocks ? shared->blocks[j] : 1;
+    }
+    return pts;
+}
+int oracle_search_by_projection_fisheye(const OrbfeFrameView* fl, const OrbfeFrameView* fr, const int32_t* l2r,
+                                        const int32_t* r2l, const OrbfeProjPoints* pl, const OrbfeProjPoints* pr,
+                                        const OrbfeSearchParams* prm, const uint8_t* claimed, int32_t* assigned,
+                                        int32_t* best_l, int32_t* best_r) {
+    match_oracle::FrameView FL, FR;
+    fill_view(FL, fl);
+    fill_view(FR, fr);
+    std::vector<match_oracle::ProjPoint> ptsL = fill_pts(pl, pl), ptsR = fill_pts(pr, pl);
+    match_oracle::SearchParams sp{prm->mode, prm->th_accept, prm->nnratio, prm->check_orientation};
+    return match_oracle::search_by_projection_fisheye(FL, FR, l2r, r2l, ptsL, ptsR, pl->desc, sp, claimed, assigned,
+                                                      best_l, best_r);
+}
+
 // Grid query tap: indices returned by GetFeaturesInArea, in the reference's order.
 int oracle_features_in_area(const OrbfeFrameView* fv, float x, float y, float r, int minLevel,
                             int maxLevel, int32_t* out, int cap) {

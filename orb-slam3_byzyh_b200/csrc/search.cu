@@ -240,6 +240,222 @@ __global__ void k_assign_prepare(const int* __restrict__ bestIdx, int m, int* __
     if (k >= 0) assigned[k] = -1;  // will be overwritten by atomicMax(j >= 0)
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fisheye stereo frames (F.Nleft != -1): every map point is searched in the left camera and then
+// in the right camera (ORBmatcher.cc:171-237, 2090-2155); F.mvpMapPoints slots are [0,Nleft) for
+// the left and [Nleft,N) for the right keypoints, and in the map-point overload an accepted match
+// also writes its stereo partner's slot (mvLeftToRightMatch / mvRightToLeftMatch, :159-163,
+// :215-219).  Claim times are 2j (left search of point j) and 2j+1 (right search), so the right
+// search of a point sees what its own left search claimed.
+struct FeDev {
+    GridDev L, R;
+    const int* l2r;
+    const int* r2l;
+    int Nl;
+};
+struct PtsFe {
+    PtsDev L;                      // left projections + shared angle / blocks / desc
+    const float *u, *v, *radius;   // right projections
+    const int *minLevel, *maxLevel;
+    const uint8_t* valid;
+};
+
+struct WinBest { int bD, bL, bD2, bL2, bI; bool had; };
+
+__device__ __forceinline__ WinBest win_search(const GridDev& F, int slotOff, float x, float y, float r, int minLevel,
+                                              int maxLevel, const uint32_t* d, const int* __restrict__ claimIn, int t,
+                                              bool second) {
+    WinBest w = {256, -1, 256, -1, -1, false};
+    const int c0x = max(0, (int)floorf((x - F.minX - r) * F.wInv));
+    const int c1x = min(GC - 1, (int)ceilf((x - F.minX + r) * F.wInv));
+    const int c0y = max(0, (int)floorf((y - F.minY - r) * F.hInv));
+    const int c1y = min(GR - 1, (int)ceilf((y - F.minY + r) * F.hInv));
+    if (!(c0x < GC && c1x >= 0 && c0y < GR && c1y >= 0)) return w;
+    const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = c0x; ix <= c1x; ix++)
+        for (int iy = c0y; iy <= c1y; iy++) {
+            const int cb = F.cellStart[ix * GR + iy], ce = F.cellStart[ix * GR + iy + 1];
+            for (int q = cb; q < ce; q++) {
+                const int idx = F.cellItems[q];
+                const OrbfeKeyPoint kp = F.keys[idx];
+                if (checkLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                if (!(fabsf(kp.x - x) < r && fabsf(kp.y - y) < r)) continue;
+                w.had = true;                                    // vIndices is not empty
+                if (claimIn[idx + slotOff] < t) continue;
+                const uint4* kd = reinterpret_cast<const uint4*>(F.desc + 8 * (size_t)idx);
+                const int dist = hamming8(d, kd[0], kd[1]);
+                if (dist < w.bD) { w.bD2 = w.bD; w.bD = dist; w.bL2 = w.bL; w.bL = kp.octave; w.bI = idx; }
+                else if (second && dist < w.bD2) { w.bL2 = kp.octave; w.bD2 = dist; }
+            }
+        }
+    return w;
+}
+
+__global__ void __launch_bounds__(128)
+k_search_pass_fe(FeDev F, PtsFe P, int mode, int thAccept, float nnratio, const int* __restrict__ claimIn,
+                 int* __restrict__ claimOut, int* __restrict__ bestL, int* __restrict__ bestR) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.L.m) return;
+    uint32_t d[8];
+    const uint4* pd = reinterpret_cast<const uint4*>(P.L.desc + 8 * (size_t)j);
+    *reinterpret_cast<uint4*>(d) = pd[0];
+    *reinterpret_cast<uint4*>(d + 4) = pd[1];
+    const bool blocks = P.L.blocks ? P.L.blocks[j] != 0 : true;
+    const bool m0 = mode == ORBFE_SEARCH_MAPPOINTS;
+    int bl = -1, br = -1;
+    bool doRight = m0 ? P.valid[j] != 0 : true;   // :2090 the last-frame overload always looks right
+    if (P.L.valid[j]) {
+        const WinBest w = win_search(F.L, 0, P.L.u[j], P.L.v[j], P.L.radius[j], P.L.minLevel[j], P.L.maxLevel[j], d,
+                                     claimIn, 2 * j, m0);
+        if (w.had && w.bD <= thAccept) {
+            if (m0 && w.bL == w.bL2 && (float)w.bD > nnratio * (float)w.bD2) doRight = false;   // :154 `continue`
+            else bl = w.bI;
+        }
+        if (!m0 && !w.had) doRight = false;                                                      // :2027 `continue`
+    } else if (!m0) {
+        doRight = false;
+    }
+    if (bl >= 0 && blocks) {
+        atomicMin(&claimOut[bl], 2 * j);
+        if (m0 && F.l2r[bl] != -1) atomicMin(&claimOut[F.Nl + F.l2r[bl]], 2 * j);
+    }
+    if (doRight) {
+        // this point's own left-camera claims carry time 2j < 2j+1: at the fixpoint they are in claimIn
+        const WinBest w = win_search(F.R, F.Nl, P.u[j], P.v[j], P.radius[j], P.minLevel[j], P.maxLevel[j], d, claimIn,
+                                     2 * j + 1, m0);
+        if (w.had && w.bD <= thAccept && !(m0 && w.bL == w.bL2 && (float)w.bD > nnratio * (float)w.bD2)) br = w.bI;
+        if (br >= 0 && blocks) {
+            atomicMin(&claimOut[F.Nl + br], 2 * j + 1);
+            if (m0 && F.r2l[br] != -1) atomicMin(&claimOut[F.r2l[br]], 2 * j + 1);
+        }
+    }
+    bestL[j] = bl;
+    bestR[j] = br;
+}
+
+// Slot writes in time order: the latest write wins (tmax holds the time of the latest write).
+__global__ void k_fe_assign(FeDev F, PtsFe P, int mode, int useHist, const int* __restrict__ bestL,
+                            const int* __restrict__ bestR, int* __restrict__ tmax, int* __restrict__ hist,
+                            int* __restrict__ binL, int* __restrict__ binR, int* __restrict__ nmatches) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.L.m) return;
+    const bool m0 = mode == ORBFE_SEARCH_MAPPOINTS;
+    int n = 0;
+    const int bl = bestL[j], br = bestR[j];
+    const float factor = 1.0f / HISTO;
+    if (bl >= 0) {
+        atomicMax(&tmax[bl], 2 * j); n++;
+        if (m0 && F.l2r[bl] != -1) { atomicMax(&tmax[F.Nl + F.l2r[bl]], 2 * j); n++; }
+        if (useHist) {
+            float rot = P.L.angle[j] - F.L.keys[bl].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            bin = min(max(bin, 0), HISTO - 1);
+            binL[j] = bin;
+            atomicAdd(&hist[bin], 1);
+        }
+    }
+    if (br >= 0) {
+        if (m0 && F.r2l[br] != -1) { atomicMax(&tmax[F.r2l[br]], 2 * j + 1); n++; }
+        atomicMax(&tmax[F.Nl + br], 2 * j + 1); n++;
+        if (useHist) {
+            float rot = P.L.angle[j] - F.R.keys[br].angle;
+            if (rot < 0.0f) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO) bin = 0;
+            bin = min(max(bin, 0), HISTO - 1);
+            binR[j] = bin;
+            atomicAdd(&hist[bin], 1);
+        }
+    }
+    if (n) atomicAdd(nmatches, n);
+}
+
+__global__ void k_fe_commit(int N, const int* __restrict__ tmax, int* __restrict__ assigned) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N && tmax[k] >= 0) assigned[k] = tmax[k] >> 1;
+}
+
+__global__ void k_fe_cull(int m, int Nl, const int* __restrict__ bestL, const int* __restrict__ bestR,
+                          const int* __restrict__ binL, const int* __restrict__ binR, const int* __restrict__ hist,
+                          int* __restrict__ assigned, int* __restrict__ nmatches) {
+    __shared__ int keep[3];
+    if (threadIdx.x == 0) {  // ComputeThreeMaxima, ORBmatcher.cc:2336-2378
+        int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO; i++) {
+            const int s = hist[i];
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        keep[0] = ind1; keep[1] = ind2; keep[2] = ind3;
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    int n = 0;
+    if (bestL[j] >= 0) {
+        const int b = binL[j];
+        if (b != keep[0] && b != keep[1] && b != keep[2]) { assigned[bestL[j]] = -1; n++; }
+    }
+    if (bestR[j] >= 0) {
+        const int b = binR[j];
+        if (b != keep[0] && b != keep[1] && b != keep[2]) { assigned[Nl + bestR[j]] = -1; n++; }
+    }
+    if (n) atomicSub(nmatches, n);
+}
+
+// Exact sequential form (one thread): used when a non-blocking point could overwrite -- and thereby
+// un-block -- a slot through a stereo partner write, which the claim-time fixpoint cannot express.
+__global__ void k_search_fe_sequential(FeDev F, PtsFe P, int mode, int thAccept, float nnratio,
+                                       int* __restrict__ claim /* INT_MAX = free, -1 = taken */,
+                                       int* __restrict__ assigned, int* __restrict__ bestL, int* __restrict__ bestR,
+                                       int* __restrict__ nmatches) {
+    if (blockIdx.x | threadIdx.x) return;
+    const bool m0 = mode == ORBFE_SEARCH_MAPPOINTS;
+    int n = 0;
+    for (int j = 0; j < P.L.m; j++) {
+        uint32_t d[8];
+        for (int i = 0; i < 8; i++) d[i] = P.L.desc[8 * (size_t)j + i];
+        const int taken = P.L.blocks ? (P.L.blocks[j] ? -1 : INT_MAX) : -1;
+        int bl = -1, br = -1;
+        bool doRight = m0 ? P.valid[j] != 0 : true;   // :2090 the last-frame overload always looks right
+        if (P.L.valid[j]) {
+            const WinBest w = win_search(F.L, 0, P.L.u[j], P.L.v[j], P.L.radius[j], P.L.minLevel[j], P.L.maxLevel[j],
+                                         d, claim, 0, m0);
+            if (w.had && w.bD <= thAccept) {
+                if (m0 && w.bL == w.bL2 && (float)w.bD > nnratio * (float)w.bD2) doRight = false;
+                else bl = w.bI;
+            }
+            if (!m0 && !w.had) doRight = false;
+        } else if (!m0) {
+            doRight = false;
+        }
+        if (bl >= 0) {
+            assigned[bl] = j; claim[bl] = taken; n++;
+            if (m0 && F.l2r[bl] != -1) { assigned[F.Nl + F.l2r[bl]] = j; claim[F.Nl + F.l2r[bl]] = taken; n++; }
+        }
+        if (doRight) {
+            const WinBest w = win_search(F.R, F.Nl, P.u[j], P.v[j], P.radius[j], P.minLevel[j], P.maxLevel[j], d,
+                                         claim, 0, m0);
+            if (w.had && w.bD <= thAccept && !(m0 && w.bL == w.bL2 && (float)w.bD > nnratio * (float)w.bD2)) br = w.bI;
+            if (br >= 0) {
+                if (m0 && F.r2l[br] != -1) { assigned[F.r2l[br]] = j; claim[F.r2l[br]] = taken; n++; }
+                assigned[F.Nl + br] = j; claim[F.Nl + br] = taken; n++;
+            }
+        }
+        bestL[j] = bl;
+        bestR[j] = br;
+    }
+    *nmatches = n;
+}
+
 int sfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
 #define SCK(call)                                                        \
     do {                                                                 \
@@ -352,5 +568,128 @@ extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const Orb
     SCK(cudaMemcpy(assigned, dAssigned.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
     if (best_idx) SCK(cudaMemcpy(best_idx, dBestIdx.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
     if (best_dist) SCK(cudaMemcpy(best_dist, dBestDist.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    return nmatches;
+}
+
+
+// SearchByProjection for a fisheye stereo frame (F.Nleft != -1), modes ORBFE_SEARCH_MAPPOINTS
+// (ORBmatcher.cc:46-240 incl. :171-237) and ORBFE_SEARCH_LASTFRAME (:1951-2185 incl. :2090-2155).
+extern "C" int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, const OrbfeFrameView* right,
+                                                  const int32_t* l2r, const int32_t* r2l,
+                                                  const OrbfeProjPoints* pl, const OrbfeProjPoints* pr,
+                                                  const OrbfeSearchParams* prm, const uint8_t* claimed,
+                                                  int32_t* assigned, int32_t* best_idx_left,
+                                                  int32_t* best_idx_right, int device) {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return sfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return sfail(ORBFE_ERR_INVALID, "bad device ordinal");
+    SCK(cudaSetDevice(device));
+    if (!left || !right || !pl || !pr || !prm || !assigned || !l2r || !r2l) return sfail(ORBFE_ERR_INVALID, "null argument");
+    const int Nl = left->n, Nr = right->n, N = Nl + Nr, m = pl->m;
+    if (Nl < 0 || Nr < 0 || m < 0 || pr->m != m || (prm->mode != ORBFE_SEARCH_MAPPOINTS && prm->mode != ORBFE_SEARCH_LASTFRAME))
+        return sfail(ORBFE_ERR_INVALID, "bad sizes or mode (fisheye search supports modes 0 and 1)");
+    for (int j = 0; j < m; j++) {
+        if (best_idx_left) best_idx_left[j] = -1;
+        if (best_idx_right) best_idx_right[j] = -1;
+    }
+    if (m == 0 || N == 0) return 0;
+    const bool useHist = prm->mode == ORBFE_SEARCH_LASTFRAME && prm->check_orientation;
+    if ((Nl && (!left->keys || !left->desc)) || (Nr && (!right->keys || !right->desc)) || !pl->u || !pl->v || !pl->radius ||
+        !pl->min_level || !pl->max_level || !pl->desc || !pr->u || !pr->v || !pr->radius || !pr->min_level ||
+        !pr->max_level || (useHist && !pl->angle))
+        return sfail(ORBFE_ERR_INVALID, "missing frame / map-point array");
+
+    DevBuf dKl, dKr, dDl, dDr, dL2R, dR2L, gOf, gStartL, gItemsL, gStartR, gItemsR;
+    SCK(dKl.upload(left->keys, sizeof(OrbfeKeyPoint) * (size_t)Nl)); SCK(dKr.upload(right->keys, sizeof(OrbfeKeyPoint) * (size_t)Nr));
+    SCK(dDl.upload(left->desc, 32 * (size_t)Nl)); SCK(dDr.upload(right->desc, 32 * (size_t)Nr));
+    SCK(dL2R.upload(l2r, 4 * (size_t)Nl)); SCK(dR2L.upload(r2l, 4 * (size_t)Nr));
+    SCK(gOf.alloc(4 * (size_t)std::max(Nl, Nr))); SCK(gStartL.alloc(4 * (GC * GR + 1))); SCK(gItemsL.alloc(4 * (size_t)Nl));
+    SCK(gStartR.alloc(4 * (GC * GR + 1))); SCK(gItemsR.alloc(4 * (size_t)Nr));
+    DevBuf lu, lv, lr, lmin, lmax, lval, lang, lblk, ldesc, ru, rv, rr, rmin, rmax, rval;
+    std::vector<uint8_t> ones(m, 1);
+    SCK(lu.upload(pl->u, 4 * (size_t)m)); SCK(lv.upload(pl->v, 4 * (size_t)m)); SCK(lr.upload(pl->radius, 4 * (size_t)m));
+    SCK(lmin.upload(pl->min_level, 4 * (size_t)m)); SCK(lmax.upload(pl->max_level, 4 * (size_t)m));
+    SCK(lval.upload(pl->valid ? pl->valid : ones.data(), (size_t)m));
+    if (pl->angle) SCK(lang.upload(pl->angle, 4 * (size_t)m));
+    if (pl->blocks) SCK(lblk.upload(pl->blocks, (size_t)m));
+    SCK(ldesc.upload(pl->desc, 32 * (size_t)m));
+    SCK(ru.upload(pr->u, 4 * (size_t)m)); SCK(rv.upload(pr->v, 4 * (size_t)m)); SCK(rr.upload(pr->radius, 4 * (size_t)m));
+    SCK(rmin.upload(pr->min_level, 4 * (size_t)m)); SCK(rmax.upload(pr->max_level, 4 * (size_t)m));
+    SCK(rval.upload(pr->valid ? pr->valid : ones.data(), (size_t)m));
+    DevBuf dClaimed, cA, cB, dBL, dBR, dAssigned, dTmax, dHist, dBinL, dBinR, dFlag;
+    if (claimed) SCK(dClaimed.upload(claimed, (size_t)N));
+    SCK(cA.alloc(4 * (size_t)N)); SCK(cB.alloc(4 * (size_t)N));
+    SCK(dBL.alloc(4 * (size_t)m)); SCK(dBR.alloc(4 * (size_t)m));
+    SCK(dAssigned.upload(assigned, 4 * (size_t)N));
+    SCK(dTmax.alloc(4 * (size_t)N)); SCK(cudaMemset(dTmax.p, 0xFF, 4 * (size_t)N));
+    SCK(dHist.alloc(4 * (HISTO + 2))); SCK(cudaMemset(dHist.p, 0, 4 * (HISTO + 2)));
+    SCK(dBinL.alloc(4 * (size_t)m)); SCK(dBinR.alloc(4 * (size_t)m)); SCK(dFlag.alloc(4));
+
+    FeDev F;
+    auto fill = [](GridDev& G, const OrbfeFrameView* fv, DevBuf& k, DevBuf& d, DevBuf& st, DevBuf& it) {
+        G.keys = k.as<OrbfeKeyPoint>(); G.uright = nullptr; G.desc = d.as<uint32_t>(); G.n = fv->n;
+        G.minX = fv->min_x; G.minY = fv->min_y; G.maxX = fv->max_x; G.maxY = fv->max_y;
+        G.wInv = fv->grid_w_inv; G.hInv = fv->grid_h_inv;
+        G.cellStart = st.as<int>(); G.cellItems = it.as<int>();
+    };
+    fill(F.L, left, dKl, dDl, gStartL, gItemsL);
+    fill(F.R, right, dKr, dDr, gStartR, gItemsR);
+    F.l2r = dL2R.as<int>(); F.r2l = dR2L.as<int>(); F.Nl = Nl;
+    PtsFe P;
+    P.L.m = m; P.L.u = lu.as<float>(); P.L.v = lv.as<float>(); P.L.ur = nullptr; P.L.radius = lr.as<float>();
+    P.L.angle = pl->angle ? lang.as<float>() : nullptr; P.L.minLevel = lmin.as<int>(); P.L.maxLevel = lmax.as<int>();
+    P.L.valid = lval.as<uint8_t>(); P.L.blocks = pl->blocks ? lblk.as<uint8_t>() : nullptr; P.L.desc = ldesc.as<uint32_t>();
+    P.u = ru.as<float>(); P.v = rv.as<float>(); P.radius = rr.as<float>(); P.minLevel = rmin.as<int>();
+    P.maxLevel = rmax.as<int>(); P.valid = rval.as<uint8_t>();
+
+    k_build_grid<<<1, 1024>>>(F.L.keys, Nl, F.L.minX, F.L.minY, F.L.wInv, F.L.hInv, gOf.as<int>(), gStartL.as<int>(), gItemsL.as<int>());
+    k_build_grid<<<1, 1024>>>(F.R.keys, Nr, F.R.minX, F.R.minY, F.R.wInv, F.R.hInv, gOf.as<int>(), gStartR.as<int>(), gItemsR.as<int>());
+    const uint8_t* dcl = claimed ? dClaimed.as<uint8_t>() : nullptr;
+    k_claims_init<<<(N + 255) / 256, 256>>>(dcl, N, cA.as<int>(), cB.as<int>());
+    const int gridM = (m + 127) / 128;
+    int* dN = dHist.as<int>() + HISTO;
+
+    // A non-blocking point that overwrites a slot through a stereo partner write un-blocks it: only
+    // the ordered pass expresses that (never happens for local-map points, which are all observed).
+    bool sequential = false;
+    if (prm->mode == ORBFE_SEARCH_MAPPOINTS && pl->blocks) {
+        bool anyFree = false, anyLink = false;
+        for (int j = 0; j < m && !anyFree; j++) anyFree = !pl->blocks[j];
+        for (int i = 0; i < Nl && !anyLink; i++) anyLink = l2r[i] != -1;
+        for (int i = 0; i < Nr && !anyLink; i++) anyLink = r2l[i] != -1;
+        sequential = anyFree && anyLink;
+    }
+    if (sequential) {
+        k_search_fe_sequential<<<1, 32>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cA.as<int>(), dAssigned.as<int>(),
+                                          dBL.as<int>(), dBR.as<int>(), dN);
+    } else {
+        int* cin = cA.as<int>();
+        int* cout = cB.as<int>();
+        int passes = 0;
+        for (;;) {
+            k_search_pass_fe<<<gridM, 128>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBL.as<int>(), dBR.as<int>());
+            SCK(cudaMemset(dFlag.p, 0, 4));
+            k_claims_diff<<<(N + 255) / 256, 256>>>(cout, cin, dcl, N, dFlag.as<int>());
+            int changed = 0;
+            SCK(cudaMemcpy(&changed, dFlag.p, 4, cudaMemcpyDeviceToHost));
+            passes++;
+            std::swap(cin, cout);
+            if (!changed) break;
+            if (passes > 2 * m + 2) return sfail(ORBFE_ERR_CUDA, "claim fixpoint did not converge");
+        }
+        k_fe_assign<<<gridM, 128>>>(F, P, prm->mode, useHist ? 1 : 0, dBL.as<int>(), dBR.as<int>(), dTmax.as<int>(),
+                                    dHist.as<int>(), dBinL.as<int>(), dBinR.as<int>(), dN);
+        k_fe_commit<<<(N + 255) / 256, 256>>>(N, dTmax.as<int>(), dAssigned.as<int>());
+        if (useHist)
+            k_fe_cull<<<gridM, 128>>>(m, Nl, dBL.as<int>(), dBR.as<int>(), dBinL.as<int>(), dBinR.as<int>(), dHist.as<int>(),
+                                      dAssigned.as<int>(), dN);
+    }
+    SCK(cudaGetLastError());
+    int nmatches = 0;
+    SCK(cudaMemcpy(&nmatches, dN, 4, cudaMemcpyDeviceToHost));
+    SCK(cudaMemcpy(assigned, dAssigned.p, 4 * (size_t)N, cudaMemcpyDeviceToHost));
+    if (best_idx_left) SCK(cudaMemcpy(best_idx_left, dBL.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    if (best_idx_right) SCK(cudaMemcpy(best_idx_right, dBR.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
     return nmatches;
 }

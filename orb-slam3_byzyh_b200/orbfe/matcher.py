@@ -89,6 +89,36 @@ class ORBmatcher:
     def SearchByProjectionKeyFrame(self, F, pts, claimed, assigned, ORBdist):
         return self._search(F, pts, MODE_KEYFRAME, int(ORBdist), claimed, assigned)
 
+    # The map-point (mode 0) and last-frame (mode 1) overloads on a fisheye stereo frame (Nleft != -1):
+    # ORBmatcher.cc:46-240 incl. :171-237, and :1951-2185 incl. :2090-2155
+    def SearchByProjectionFisheye(self, FL, FR, l2r, r2l, ptsL, ptsR, claimed, assigned, mode=MODE_MAPPOINTS):
+        keep = []
+        fl, fr = FL.view(keep), FR.view(keep)
+
+        def proj(d):
+            pp = ProjPoints()
+            pp.m = len(d["u"])
+            for name, dt in [("u", np.float32), ("v", np.float32), ("ur", np.float32), ("radius", np.float32),
+                             ("min_level", np.int32), ("max_level", np.int32), ("angle", np.float32),
+                             ("valid", np.uint8), ("blocks", np.uint8), ("desc", np.uint8)]:
+                if d.get(name) is None:
+                    continue
+                a = np.ascontiguousarray(d[name], dt)
+                keep.append(a)
+                setattr(pp, name, a.ctypes.data)
+            return pp
+        pl, pr = proj(ptsL), proj(ptsR)
+        prm = SearchParams(mode, self.TH_HIGH, self.mfNNratio, int(self.mbCheckOrientation))
+        l2r = np.ascontiguousarray(l2r, np.int32)
+        r2l = np.ascontiguousarray(r2l, np.int32)
+        claimed = np.ascontiguousarray(claimed, np.uint8)
+        assigned = np.ascontiguousarray(assigned, np.int32).copy()
+        bl, br = np.empty(pl.m, np.int32), np.empty(pl.m, np.int32)
+        n = check(lib().orbfe_search_by_projection_fisheye(C.byref(fl), C.byref(fr), ptr(l2r), ptr(r2l), C.byref(pl),
+                                                           C.byref(pr), C.byref(prm), ptr(claimed), ptr(assigned),
+                                                           ptr(bl), ptr(br), self.device))
+        return n, assigned, bl, br
+
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):
         q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)

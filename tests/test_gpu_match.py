@@ -189,3 +189,62 @@ def test_c5_full_size_search_and_knn(orbfe):
     true_of = {int(d["src"][j]): j for j in has[::-1]}
     hit = sum(1 for q in range(n_frame) if q in true_of and dist[q, 0] <= 60)
     assert hit > 0.95 * n_frame      # every frame descriptor has a planted near copy in the map
+
+
+def _fisheye_case(n_map, nl, nr, seed, all_block):
+    """A fisheye-stereo-shaped frame: left / right keypoint sets with their own descriptors, a partial
+    mvLeftToRightMatch table, map points projected into both cameras."""
+    rng = np.random.default_rng(seed)
+    d = synth.map_vs_frame(n_map, nl, seed, w=512, h=512)
+    keysL, descL = d["keys"], d["fdesc"]
+    # right camera: a shifted, noisy copy of part of the left set plus unrelated keypoints
+    keysR = np.zeros(nr, orbfe_kp())
+    descR = synth.random_descriptors(nr, seed + 9)
+    src = rng.choice(nl, size=nr // 2, replace=False)
+    keysR[:nr // 2] = keysL[src]
+    keysR["x"][:nr // 2] -= 25.0
+    for i, s_ in enumerate(src):
+        descR[i] = synth.flip_bits(descL[s_], int(rng.integers(0, 30)), rng)
+    keysR["x"][nr // 2:] = rng.uniform(10, 500, nr - nr // 2)
+    keysR["y"][nr // 2:] = rng.uniform(10, 500, nr - nr // 2)
+    keysR["octave"][nr // 2:] = rng.integers(0, 8, nr - nr // 2)
+    l2r = np.full(nl, -1, np.int32)
+    r2l = np.full(nr, -1, np.int32)
+    for i, s_ in enumerate(src):
+        if rng.uniform() < 0.6:
+            l2r[s_] = i
+            r2l[i] = s_
+    sf = d["scale_factors"]
+    ptsL = _pts_from_map(d, n_map, 3.0, sf, rng)
+    if all_block:
+        ptsL["blocks"] = np.ones(n_map, np.uint8)
+    ptsR = dict(u=(ptsL["u"] - 25.0 + rng.normal(0, 1, n_map)).astype(np.float32), v=ptsL["v"].copy(),
+                radius=ptsL["radius"].copy(), min_level=ptsL["min_level"].copy(), max_level=ptsL["max_level"].copy(),
+                valid=(rng.uniform(size=n_map) < 0.8).astype(np.uint8))
+    return d, keysL, descL, keysR, descR, l2r, r2l, ptsL, ptsR
+
+
+def orbfe_kp():
+    from oracle.oracle import KP_DTYPE
+    return KP_DTYPE
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("all_block", [True, False])
+def test_search_by_projection_fisheye(orbfe, mode, all_block):
+    """Nleft != -1 branches: left + right camera searches, stereo partner writes, shared rotation
+    histogram; with non-blocking points and partner links the ordered single-thread kernel is used."""
+    n_map, nl, nr = 6000, 900, 800
+    d, keysL, descL, keysR, descR, l2r, r2l, ptsL, ptsR = _fisheye_case(n_map, nl, nr, 21 + mode, all_block)
+    rng = np.random.default_rng(3)
+    claimed = (rng.uniform(size=nl + nr) < 0.05).astype(np.uint8)
+    assigned = np.full(nl + nr, -1, np.int32)
+    assigned[claimed > 0] = 10 ** 6
+    m = orbfe.ORBmatcher(nnratio=0.8, checkOri=True)
+    FL = orbfe.FrameData(keysL, descL, d["bounds"], None)
+    FR = orbfe.FrameData(keysR, descR, d["bounds"], None)
+    n, asg, bl, br = m.SearchByProjectionFisheye(FL, FR, l2r, r2l, ptsL, ptsR, claimed, assigned, mode)
+    en, easg, ebl, ebr = O.search_by_projection_fisheye(keysL, descL, keysR, descR, d["bounds"], l2r, r2l, ptsL, ptsR,
+                                                        mode, 100, 0.8, True, claimed, assigned)
+    assert n == en and n > 300 and (ebr >= 0).sum() > 100
+    assert np.array_equal(bl, ebl) and np.array_equal(br, ebr) and np.array_equal(asg, easg)
