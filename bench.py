@@ -245,6 +245,15 @@ def run_ours(args):
     e2e_ms = max_over_ranks(dt * 1e3)
     e2e = world * B * args.steps / (e2e_ms / 1e3)
     assert np.array_equal(out[0].astype(np.int64), n_kp), "host and device paths disagree"
+
+    # ---- one frame per call, as Frame::ExtractORB issues it (latency, not throughput) ----
+    one = frames[0]
+    for _ in range(5):
+        ex(one, None, LAP)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        ex(one, None, LAP)
+    single_ms = (time.perf_counter() - t0) / 50 * 1e3
     h2d = B * H * W
     d2h = B * (cap * 28 + cap * 32 + 8)
 
@@ -331,7 +340,7 @@ def run_ours(args):
                    "l2": f"inputs+intermediates per step = {B * geo['per_frame_bytes'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
                    "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around synchronous C-ABI calls, max over ranks"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps, "single_frame_call_ms": single_ms},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "matching": matching,
     }))
     if world > 1:
@@ -344,8 +353,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
-    ap.add_argument("--chunk", type=int, default=128, help="frames per pipelined chunk on the host-pointer path")
+    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--chunk", type=int, default=256, help="frames per pipelined chunk on the host-pointer path")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

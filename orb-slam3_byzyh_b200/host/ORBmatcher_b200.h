@@ -77,6 +77,40 @@ inline int SearchByProjection(const std::vector<cv::KeyPoint>& keys, const std::
     return n;
 }
 
+// The same two overloads on a fisheye stereo frame (F.Nleft != -1): keysL = F.mvKeys, keysR = F.mvKeysRight,
+// desc = F.mDescriptors (rows [0,Nleft) left, [Nleft,N) right), l2r / r2l = F.mvLeftToRightMatch /
+// F.mvRightToLeftMatch; ptsL carries the left projections and the shared angle / blocks / desc, ptsR the
+// right-camera projections (ORBmatcher.cc:171-237, 2090-2155).  claimed / assigned are indexed like
+// F.mvpMapPoints.  mode = ORBFE_SEARCH_MAPPOINTS or ORBFE_SEARCH_LASTFRAME.
+inline int SearchByProjectionFisheye(const std::vector<cv::KeyPoint>& keysL, const std::vector<cv::KeyPoint>& keysR,
+                                     const cv::Mat& desc, float minX, float minY, float maxX, float maxY, float wInv,
+                                     float hInv, const std::vector<int>& l2r, const std::vector<int>& r2l,
+                                     const ProjPoints& ptsL, const ProjPoints& ptsR, int mode, int thAccept,
+                                     float nnratio, bool checkOrientation, const std::vector<uint8_t>& claimed,
+                                     std::vector<int32_t>& assigned) {
+    OrbfeFrameView fl, fr;
+    fl.n = (int32_t)keysL.size(); fl.keys = reinterpret_cast<const OrbfeKeyPoint*>(keysL.data()); fl.uright = nullptr;
+    fl.desc = desc.ptr();
+    fr.n = (int32_t)keysR.size(); fr.keys = reinterpret_cast<const OrbfeKeyPoint*>(keysR.data()); fr.uright = nullptr;
+    fr.desc = desc.ptr() + (size_t)32 * keysL.size();
+    fl.min_x = fr.min_x = minX; fl.min_y = fr.min_y = minY; fl.max_x = fr.max_x = maxX; fl.max_y = fr.max_y = maxY;
+    fl.grid_w_inv = fr.grid_w_inv = wInv; fl.grid_h_inv = fr.grid_h_inv = hInv;
+    auto view = [](const ProjPoints& p, const ProjPoints& shared) {
+        OrbfeProjPoints pp;
+        pp.m = (int32_t)p.size();
+        pp.u = p.u.data(); pp.v = p.v.data(); pp.ur = nullptr; pp.radius = p.radius.data();
+        pp.min_level = p.minLevel.data(); pp.max_level = p.maxLevel.data(); pp.angle = shared.angle.data();
+        pp.valid = p.valid.data(); pp.blocks = shared.blocks.data(); pp.desc = shared.desc.data();
+        return pp;
+    };
+    const OrbfeProjPoints pl = view(ptsL, ptsL), pr = view(ptsR, ptsL);
+    OrbfeSearchParams prm = {mode, thAccept, nnratio, checkOrientation ? 1 : 0};
+    const int n = orbfe_search_by_projection_fisheye(&fl, &fr, l2r.data(), r2l.data(), &pl, &pr, &prm, claimed.data(),
+                                                     assigned.data(), nullptr, nullptr, device());
+    if (n < 0) throw std::runtime_error(std::string("SearchByProjection fisheye (B200): ") + orbfe_last_error());
+    return n;
+}
+
 // void Frame::ComputeStereoMatches()   Frame.h:116, Frame.cc:1102-1358
 inline void ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& keysL,
                                  const cv::Mat& descL, const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,
