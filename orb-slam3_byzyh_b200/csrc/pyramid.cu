@@ -21,27 +21,31 @@ __device__ __forceinline__ int reflect101_clamped(int p, int len) {
     return max(0, min(p, len - 1));
 }
 
+// Level 0 = copyMakeBorder(image, 19, REFLECT_101): a thread owns 16 bytes of one padded row; interior
+// groups are one aligned 16-byte load + store, border groups gather the reflected bytes.
 __global__ void __launch_bounds__(256)
 k_level0(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8_t* __restrict__ pyr,
          unsigned long long pyrStride, int w, int h, int pitch) {
-    const int words = pitch >> 2;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int H = h + 2 * ORBFE_YOFF;
-    if (idx >= words * H) return;
-    const int py = idx / words, wc = idx - py * words;
-    const uint8_t* src = img + (size_t)blockIdx.y * frameStride +
-                         (size_t)reflect101_clamped(py - ORBFE_YOFF, h) * step;
-    const int x0 = 4 * wc - ORBFE_XOFF;
-    uint32_t out;
-    if (x0 >= 0 && x0 + 3 < w && ((reinterpret_cast<size_t>(src + x0) & 3) == 0)) {
-        out = __ldg(reinterpret_cast<const uint32_t*>(src + x0));
+    const int gx = blockIdx.x * 64 + (threadIdx.x & 63);          // 16-byte group inside the padded row
+    const int py = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (gx >= (pitch >> 4) || py >= h + 2 * ORBFE_YOFF) return;
+    const uint8_t* src = img + (size_t)blockIdx.z * frameStride + (size_t)reflect101_clamped(py - ORBFE_YOFF, h) * step;
+    const int x0 = 16 * gx - ORBFE_XOFF;
+    uint4 out;
+    if (x0 >= 0 && x0 + 15 < w && ((reinterpret_cast<size_t>(src + x0) & 15) == 0)) {
+        out = __ldg(reinterpret_cast<const uint4*>(src + x0));
     } else {
-        out = 0;
+        uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            out |= (uint32_t)__ldg(src + reflect101_clamped(x0 + i, w)) << (8 * i);
+        for (int k = 0; k < 4; k++) {
+            v[k] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                v[k] |= (uint32_t)__ldg(src + reflect101_clamped(x0 + 4 * k + i, w)) << (8 * i);
+        }
+        out = make_uint4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<uint32_t*>(pyr + (size_t)blockIdx.y * pyrStride + (size_t)py * pitch + 4 * wc) = out;
+    *reinterpret_cast<uint4*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 16 * gx) = out;
 }
 
 // mode 0: bilinear taps; 1: exact 2x2 area average; 2: identity
@@ -92,108 +96,130 @@ k_resize(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict_
 
 // Fast bilinear path (the four source taps of four adjacent destination pixels span at most 8
 // source bytes, i.e. scale <= 2; the host checks this when it builds the tap tables).  A thread
-// owns four adjacent PADDED destination columns and walks down RS_ROWS destination rows: the x-taps
-// live in registers, every source row segment is fetched as three aligned 32-bit words, one PRMT
-// per pixel pulls its two tap bytes out of that 8-byte window and one IDP2A applies the two 11-bit
-// weights.  The horizontal pass of a source row is kept (already >> 4) and reused when the next
-// destination row needs the same source row (at scale 1.2 that is 5 rows out of 6).  Border
-// columns/rows are the same computation on the reflected destination coordinate, so resize +
-// copyMakeBorder stay one pass with coalesced 32-bit stores.
-constexpr int RS_ROWS = 16, RS_WARPS = 4;
+// owns EIGHT adjacent PADDED destination columns (two aligned words) and walks down RS_ROWS
+// destination rows: the x-taps live in registers, every source row segment is fetched as three
+// aligned 32-bit words per word of output, one PRMT per pixel pulls its two tap bytes out of that
+// 8-byte window and one IDP2A applies the two 11-bit weights.  The horizontal pass of a source row
+// is kept (already >> 4) and reused when the next destination row needs the same source row (at
+// scale 1.2 that is 5 rows out of 6); the y-taps of the strip are fetched once and handed out by
+// shuffle; the source row the NEXT destination row will need is requested before the current row
+// is computed.  Border columns/rows are the same computation on the reflected destination
+// coordinate, so resize + copyMakeBorder stay one pass with coalesced 64-bit stores.
+constexpr int RS_ROWS = 16, RS_WARPS = 4, RS_G = 2;   // rows per warp strip, warps per CTA, words per thread
 
 __global__ void __launch_bounds__(32 * RS_WARPS)
 k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict__ xtab,
               const OrbfeTap* __restrict__ ytab, unsigned srcOff, int srcPitch, unsigned dstOff, int w, int h,
               int pitch) {
-    const int words = pitch >> 2;
-    const bool active = blockIdx.x * 32 + (int)(threadIdx.x & 31) < words;   // no early exit: the warp shuffles below
-    const int wc = min(blockIdx.x * 32 + (int)(threadIdx.x & 31), words - 1);
+    const int words = pitch >> 2, pairs = words / RS_G;     // pitch is a multiple of 16: words % 4 == 0
+    const int lane = threadIdx.x & 31;
+    const bool active = blockIdx.x * 32 + lane < pairs;     // no early exit: the warp shuffles below
+    const int wc0 = RS_G * min(blockIdx.x * 32 + lane, pairs - 1);
     const int H = h + 2 * ORBFE_YOFF;
     const int py0 = (blockIdx.y * RS_WARPS + (threadIdx.x >> 5)) * RS_ROWS;
     if (py0 >= H) return;
     uint8_t* base = pyr + (size_t)blockIdx.z * pyrStride;
-    int lo = 1 << 30;
-    OrbfeTap tp[4];
+    uint32_t wgt[RS_G][4], sel[RS_G][4];
+    int wi0[RS_G], sh[RS_G];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        tp[i] = xtab[reflect101_clamped(4 * wc - ORBFE_XOFF + i, w)];
-        lo = min(lo, (int)tp[i].s);
-    }
-    uint32_t wgt[4], sel[4];
+    for (int g = 0; g < RS_G; g++) {
+        OrbfeTap tp[4];
+        int lo = 1 << 30;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        wgt[i] = (uint32_t)(uint16_t)tp[i].a0 | ((uint32_t)(uint16_t)tp[i].a1 << 16);
-        sel[i] = (uint32_t)(tp[i].s - lo) | ((uint32_t)(tp[i].s1 - lo) << 4);   // byte0 = src[s], byte1 = src[s1]
+        for (int i = 0; i < 4; i++) {
+            tp[i] = xtab[reflect101_clamped(4 * (wc0 + g) - ORBFE_XOFF + i, w)];
+            lo = min(lo, (int)tp[i].s);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            wgt[g][i] = (uint32_t)(uint16_t)tp[i].a0 | ((uint32_t)(uint16_t)tp[i].a1 << 16);
+            sel[g][i] = (uint32_t)(tp[i].s - lo) | ((uint32_t)(tp[i].s1 - lo) << 4);   // byte0 = src[s], byte1 = src[s1]
+        }
+        const int col = ORBFE_XOFF + lo;
+        wi0[g] = col >> 2;       // the three words wi0..wi0+2 stay inside the source row (19-px border + padding)
+        sh[g] = 8 * (col & 3);
     }
-    const int col = ORBFE_XOFF + lo, sh = 8 * (col & 3);
     const int srcWords = srcPitch >> 2;
-    const int wi0 = col >> 2, wi1 = min(wi0 + 1, srcWords - 1), wi2 = min(wi0 + 2, srcWords - 1);
     const uint32_t* __restrict__ sroi = reinterpret_cast<const uint32_t*>(base + srcOff + (size_t)ORBFE_YOFF * srcPitch);
 
-    // horizontal pass of one source row segment (three words), already >> 4
-    auto hpass = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t* Hs) {
-        const uint32_t lo8 = __funnelshift_r(w0, w1, sh), hi8 = __funnelshift_r(w1, w2, sh);
+    struct Raw { uint32_t w[RS_G][3]; };
+    auto fetch = [&](int r) {
+        Raw x;
+        const uint32_t* rw = sroi + (size_t)r * srcWords;
 #pragma unroll
-        for (int i = 0; i < 4; i++) Hs[i] = __dp2a_lo(wgt[i], __byte_perm(lo8, hi8, sel[i]), 0u) >> 4;
+        for (int g = 0; g < RS_G; g++) { x.w[g][0] = rw[wi0[g]]; x.w[g][1] = rw[wi0[g] + 1]; x.w[g][2] = rw[wi0[g] + 2]; }
+        return x;
+    };
+    // horizontal pass of one fetched source row, already >> 4
+    auto hpass = [&](const Raw& x, uint32_t (*Hs)[4]) {
+#pragma unroll
+        for (int g = 0; g < RS_G; g++) {
+            const uint32_t lo8 = __funnelshift_r(x.w[g][0], x.w[g][1], sh[g]), hi8 = __funnelshift_r(x.w[g][1], x.w[g][2], sh[g]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) Hs[g][i] = __dp2a_lo(wgt[g][i], __byte_perm(lo8, hi8, sel[g][i]), 0u) >> 4;
+        }
     };
 
-    // The y-taps of the strip are fetched once (lane i holds the tap of row py0+i) and handed out
-    // by shuffle; the source words of the NEXT destination row are requested before the current row
-    // is computed, so no global-load latency sits on the row-to-row dependency chain.
-    const int lane = threadIdx.x & 31;
     OrbfeTap myTap = {0, 0, 0, 0};
     if (lane < RS_ROWS) myTap = ytab[reflect101_clamped(min(py0 + lane, H - 1) - ORBFE_YOFF, h)];
     const unsigned tapS = (uint32_t)(uint16_t)myTap.s | ((uint32_t)(uint16_t)myTap.s1 << 16);
     const unsigned tapA = (uint32_t)(uint16_t)myTap.a0 | ((uint32_t)(uint16_t)myTap.a1 << 16);
 
     int c0 = -1, c1 = -1;
-    uint32_t C0[4] = {0, 0, 0, 0}, C1[4] = {0, 0, 0, 0};   // cached horizontal passes of source rows c0, c1
+    uint32_t C0[RS_G][4], C1[RS_G][4];   // cached horizontal passes of source rows c0, c1
     const int n = min(RS_ROWS, H - py0);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(base + dstOff) + wc + (size_t)py0 * words;
+    uint2* dst = reinterpret_cast<uint2*>(base + dstOff + (size_t)py0 * pitch) + (wc0 >> 1);
     unsigned rs = __shfl_sync(0xffffffffu, tapS, 0);
-    uint32_t p0[3], p1[3];   // prefetched words of source rows r0 and r1 of the current row
-    {
-        const uint32_t* ra = sroi + (size_t)(rs & 0xFFFFu) * srcWords;
-        const uint32_t* rb = sroi + (size_t)(rs >> 16) * srcWords;
-        p0[0] = ra[wi0]; p0[1] = ra[wi1]; p0[2] = ra[wi2];
-        p1[0] = rb[wi0]; p1[1] = rb[wi1]; p1[2] = rb[wi2];
-    }
-    for (int i = 0; i < n; i++, dst += words) {
+    int pr = (int)(rs >> 16);            // prefetched source row (the one the first row needs as r1)
+    Raw P = fetch(pr);
+    for (int i = 0; i < n; i++, dst += words >> 1) {
         const int r0 = (int)(rs & 0xFFFFu), r1 = (int)(rs >> 16);
         const unsigned wa = __shfl_sync(0xffffffffu, tapA, i);
-        uint32_t q0[3] = {p0[0], p0[1], p0[2]}, q1[3] = {p1[0], p1[1], p1[2]};
-        if (i + 1 < n) {   // request the next row's source words now
+        const Raw got = P;
+        const int gotRow = pr;
+        if (i + 1 < n) {   // request the source row the next destination row will newly need
             rs = __shfl_sync(0xffffffffu, tapS, i + 1);
-            const uint32_t* ra = sroi + (size_t)(rs & 0xFFFFu) * srcWords;
-            const uint32_t* rb = sroi + (size_t)(rs >> 16) * srcWords;
-            p0[0] = ra[wi0]; p0[1] = ra[wi1]; p0[2] = ra[wi2];
-            p1[0] = rb[wi0]; p1[1] = rb[wi1]; p1[2] = rb[wi2];
+            pr = (int)(rs >> 16);
+            P = fetch(pr);
         }
         // all threads of a warp share the row, hence r0/r1/c0/c1: the branches below are warp-uniform
         if (r0 != c0) {
             if (r0 == c1) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) C0[k] = C1[k];
+                for (int g = 0; g < RS_G; g++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) C0[g][k] = C1[g][k];
+            } else if (r0 == gotRow) {
+                hpass(got, C0);
             } else {
-                hpass(q0[0], q0[1], q0[2], C0);
+                hpass(fetch(r0), C0);
             }
             c0 = r0;
         }
         if (r1 != c1) {
             if (r1 == c0) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) C1[k] = C0[k];
+                for (int g = 0; g < RS_G; g++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) C1[g][k] = C0[g][k];
+            } else if (r1 == gotRow) {
+                hpass(got, C1);
             } else {
-                hpass(q1[0], q1[1], q1[2], C1);
+                hpass(fetch(r1), C1);
             }
             c1 = r1;
         }
         // ((b*(H>>4))>>16) == umulhi(b << 16, H >> 4) for the non-negative 11-bit weights
         const uint32_t b0 = wa << 16, b1 = wa & 0xFFFF0000u;
-        uint32_t v[4];
+        uint32_t o[RS_G];
 #pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, C0[k]) + __umulhi(b1, C1[k]) + 2u) >> 2;
-        if (active) *dst = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        for (int g = 0; g < RS_G; g++) {
+            uint32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, C0[g][k]) + __umulhi(b1, C1[g][k]) + 2u) >> 2;
+            o[g] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        }
+        if (active) *dst = make_uint2(o[0], o[1]);
     }
 }
 
@@ -207,14 +233,15 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
         const int total = (L.pitch >> 2) * (L.h + 2 * ORBFE_YOFF);
         dim3 grid((total + 255) / 256, B);
         if (l == 0) {
-            k_level0<<<grid, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride,
-                                           L.w, L.h, L.pitch);
+            dim3 g0(((L.pitch >> 4) + 63) / 64, (L.h + 2 * ORBFE_YOFF + 3) / 4, B);
+            k_level0<<<g0, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride,
+                                         L.w, L.h, L.pitch);
         } else {
             const OrbfeLevelGeom& S = g.lv[l - 1];
             const OrbfeTap* xt = taps + L.xtab;
             const OrbfeTap* yt = taps + L.ytab;
             if (L.mode == 0 && L.fastTaps) {
-                dim3 gf(((L.pitch >> 2) + 31) / 32, (L.h + 2 * ORBFE_YOFF + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS), B);
+                dim3 gf(((L.pitch >> 2) / RS_G + 31) / 32, (L.h + 2 * ORBFE_YOFF + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS), B);
                 k_resize_fast<<<gf, 32 * RS_WARPS, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
             } else if (L.mode == 0)
                 k_resize<0><<<grid, 256, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
