@@ -127,6 +127,36 @@ def cpu_reference_run(frames_per_thread, threads, frames):
     return threads * frames_per_thread / dt, kind
 
 
+def call_latencies(orbfe, device):
+    """Per-call milliseconds of the matcher entry points at SLAM-frame sizes (host arrays in and out,
+    as the C++ adapter issues them): C2 stereo pair, C3-sized kNN, local-map projection search."""
+    import synth
+
+    def timeit(fn, n=30):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t0) / n * 1e3
+    left, right = synth.stereo_pair(480, 752, 3)
+    gl, gr = orbfe.ORBextractor(1200, device=device), orbfe.ORBextractor(1200, device=device)
+    _, kl, dl = gl(left, None, (0, 0))
+    _, kr, dr = gr(right, None, (0, 0))
+    m = orbfe.ORBmatcher(0.8, True, device=device)
+    out = {"stereo_match_1200x1200": timeit(lambda: orbfe.ORBmatcher.ComputeStereoMatches(gl, gr, kl, dl, kr, dr, 47.9, 0.11)),
+           "knn2_ratio_1200x1200": timeit(lambda: m.knn2(dl, dr))}
+    d = synth.map_vs_frame(3000, 1200, 1, w=752, h=480)
+    pts = dict(u=d["u"], v=d["v"], ur=d["u"], radius=np.full(3000, 10, np.float32), min_level=np.zeros(3000, np.int32),
+               max_level=np.full(3000, -1, np.int32), angle=np.zeros(3000, np.float32), valid=np.ones(3000, np.uint8),
+               blocks=np.ones(3000, np.uint8), desc=d["mdesc"])
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], None)
+    cl, asg = np.zeros(1200, np.uint8), np.full(1200, -1, np.int32)
+    out["search_by_projection_3000pts"] = timeit(lambda: m.SearchByProjection(F, pts, cl, asg))
+    out["search_last_frame_3000pts"] = timeit(lambda: m.SearchByProjectionLastFrame(F, pts, cl, asg))
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -254,6 +284,9 @@ def run_ours(args):
     for _ in range(50):
         ex(one, None, LAP)
     single_ms = (time.perf_counter() - t0) / 50 * 1e3
+    latency = {"extract_1_frame": single_ms}
+    if not args.no_match and rank == 0:
+        latency.update(call_latencies(orbfe, local))
     h2d = B * H * W
     d2h = B * (cap * 28 + cap * 32 + 8)
 
@@ -341,6 +374,7 @@ def run_ours(args):
                    "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around synchronous C-ABI calls, max over ranks"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "single_frame_call_ms": single_ms},
+        "call_latency_ms": latency,
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "matching": matching,
     }))
     if world > 1:

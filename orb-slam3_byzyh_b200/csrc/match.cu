@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "orbfe_internal.h"
+#include "scratch.h"
 
 namespace {
 
@@ -186,13 +187,6 @@ int set_device(int device) {
     return ORBFE_OK;
 }
 
-struct DevBuf {  // RAII device allocation for the host-pointer entry points
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
-    template <class T> T* as() { return (T*)p; }
-};
-
 }  // namespace
 
 // Enqueue kNN-2 on `st`: idx2/dist2 (and match when non-null) for nq queries against nt train rows.
@@ -223,13 +217,13 @@ int orbfe_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!a || !b || !out))) return mfail(ORBFE_ERR_INVALID, "bad arguments");
     if (n == 0) return ORBFE_OK;
-    DevBuf da, db, dout;
-    MCK(da.alloc(32 * (size_t)n)); MCK(db.alloc(32 * (size_t)n)); MCK(dout.alloc(4 * (size_t)n));
-    MCK(cudaMemcpy(da.p, a, 32 * (size_t)n, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(db.p, b, 32 * (size_t)n, cudaMemcpyHostToDevice));
-    k_hamming_pairs<<<(n + 255) / 256, 256>>>(da.as<uint32_t>(), db.as<uint32_t>(), n, dout.as<int32_t>());
+    OrbfeStage S;
+    const size_t ia = S.in(a, 32 * (size_t)n), ib = S.in(b, 32 * (size_t)n), io = S.out(out, 4 * (size_t)n);
+    MCK(S.commit(device));
+    MCK(S.upload());
+    k_hamming_pairs<<<(n + 255) / 256, 256, 0, S.stream()>>>(S.ptr<uint32_t>(ia), S.ptr<uint32_t>(ib), n, S.ptr<int32_t>(io));
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(out, dout.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    MCK(S.download());
     return ORBFE_OK;
 }
 
@@ -254,18 +248,16 @@ int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int t
     if (nq < 0 || nt < 0 || nt >= (1 << KEY_SHIFT)) return mfail(ORBFE_ERR_INVALID, "bad sizes (nt must be < 2^23 per call)");
     if (nq == 0) return ORBFE_OK;
     if (!query || (nt > 0 && !train) || !idx2 || !dist2) return mfail(ORBFE_ERR_INVALID, "null argument");
-    DevBuf dq, dt, di, dd, dm, dp;
-    MCK(dq.alloc(32 * (size_t)nq)); MCK(dt.alloc(32 * (size_t)nt));
-    MCK(di.alloc(8 * (size_t)nq)); MCK(dd.alloc(8 * (size_t)nq)); MCK(dm.alloc(4 * (size_t)nq));
-    MCK(dp.alloc(orbfe_knn2_partial_bytes(nq, nt)));
-    MCK(cudaMemcpy(dq.p, query, 32 * (size_t)nq, cudaMemcpyHostToDevice));
-    if (nt) MCK(cudaMemcpy(dt.p, train, 32 * (size_t)nt, cudaMemcpyHostToDevice));
-    orbfe_knn2_enqueue(dq.as<uint8_t>(), nq, dt.as<uint8_t>(), nt, train_offset, di.as<int32_t>(),
-                       dd.as<int32_t>(), dm.as<int32_t>(), dp.as<uint32_t>(), 0);
+    OrbfeStage S;
+    const size_t iq = S.in(query, 32 * (size_t)nq), it = S.in(train, 32 * (size_t)nt);
+    const size_t wp = S.work(orbfe_knn2_partial_bytes(nq, nt));
+    const size_t oi = S.out(idx2, 8 * (size_t)nq), od = S.out(dist2, 8 * (size_t)nq), om = S.out(match, 4 * (size_t)nq);
+    MCK(S.commit(device));
+    MCK(S.upload());
+    orbfe_knn2_enqueue(S.ptr<uint8_t>(iq), nq, S.ptr<uint8_t>(it), nt, train_offset, S.ptr<int32_t>(oi), S.ptr<int32_t>(od),
+                       S.ptr<int32_t>(om), S.ptr<uint32_t>(wp), S.stream());
     MCK(cudaGetLastError());
-    MCK(cudaMemcpy(idx2, di.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
-    MCK(cudaMemcpy(dist2, dd.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
-    if (match) MCK(cudaMemcpy(match, dm.p, 4 * (size_t)nq, cudaMemcpyDeviceToHost));
+    MCK(S.download());
     return ORBFE_OK;
 }
 
@@ -284,15 +276,15 @@ int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, in
     if (rc) return rc;
     if (nq <= 0 || G <= 0) return ORBFE_OK;
     const size_t tb = 8 * (size_t)nq * G;
-    DevBuf si, sd, di, dd, dm;
-    MCK(si.alloc(tb)); MCK(sd.alloc(tb)); MCK(di.alloc(8 * (size_t)nq)); MCK(dd.alloc(8 * (size_t)nq)); MCK(dm.alloc(4 * (size_t)nq));
-    MCK(cudaMemcpy(si.p, idx2_shards, tb, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(sd.p, dist2_shards, tb, cudaMemcpyHostToDevice));
-    rc = orbfe_knn2_merge_device(si.as<int32_t>(), sd.as<int32_t>(), G, nq, di.as<int32_t>(), dd.as<int32_t>(), dm.as<int32_t>(), 0);
+    OrbfeStage S;
+    const size_t si = S.in(idx2_shards, tb), sd = S.in(dist2_shards, tb);
+    const size_t oi = S.out(idx2, 8 * (size_t)nq), od = S.out(dist2, 8 * (size_t)nq), om = S.out(match, 4 * (size_t)nq);
+    MCK(S.commit(device));
+    MCK(S.upload());
+    rc = orbfe_knn2_merge_device(S.ptr<int32_t>(si), S.ptr<int32_t>(sd), G, nq, S.ptr<int32_t>(oi), S.ptr<int32_t>(od),
+                                 S.ptr<int32_t>(om), S.stream());
     if (rc) return rc;
-    MCK(cudaMemcpy(idx2, di.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
-    MCK(cudaMemcpy(dist2, dd.p, 8 * (size_t)nq, cudaMemcpyDeviceToHost));
-    if (match) MCK(cudaMemcpy(match, dm.p, 4 * (size_t)nq, cudaMemcpyDeviceToHost));
+    MCK(S.download());
     return ORBFE_OK;
 }
 

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "orbfe_internal.h"
+#include "scratch.h"
 
 namespace {
 
@@ -707,33 +708,23 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     if (nl == 0) return ORBFE_OK;
     if (!keys_l || !desc_l || !u_right || !depth || (nr > 0 && (!keys_r || !desc_r))) return fail(ORBFE_ERR_INVALID, "null argument");
     CK(cudaStreamSynchronize(right->sCompute));
-    cudaStream_t st = left->sCompute;
-    OrbfeKeyPoint *dkl = nullptr, *dkr = nullptr;
-    uint32_t *ddl = nullptr, *ddr = nullptr;
-    float *dur = nullptr, *ddp = nullptr;
-    int* dsad = nullptr;
-    cudaError_t e = cudaMalloc(&dkl, sizeof(OrbfeKeyPoint) * (size_t)nl);
-    if (e == cudaSuccess) e = cudaMalloc(&dkr, sizeof(OrbfeKeyPoint) * (size_t)std::max(nr, 1));
-    if (e == cudaSuccess) e = cudaMalloc(&ddl, 32 * (size_t)nl);
-    if (e == cudaSuccess) e = cudaMalloc(&ddr, 32 * (size_t)std::max(nr, 1));
-    if (e == cudaSuccess) e = cudaMalloc(&dur, 4 * (size_t)nl);
-    if (e == cudaSuccess) e = cudaMalloc(&ddp, 4 * (size_t)nl);
-    if (e == cudaSuccess) e = cudaMalloc(&dsad, 4 * (size_t)nl);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dkl, keys_l, sizeof(OrbfeKeyPoint) * (size_t)nl, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ddl, desc_l, 32 * (size_t)nl, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && nr) e = cudaMemcpyAsync(dkr, keys_r, sizeof(OrbfeKeyPoint) * (size_t)nr, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess && nr) e = cudaMemcpyAsync(ddr, desc_r, 32 * (size_t)nr, cudaMemcpyHostToDevice, st);
+    CK(cudaStreamSynchronize(left->sCompute));
+    OrbfeStage S;
+    const size_t ikl = S.in(keys_l, sizeof(OrbfeKeyPoint) * (size_t)nl), idl = S.in(desc_l, 32 * (size_t)nl);
+    const size_t ikr = S.in(keys_r, sizeof(OrbfeKeyPoint) * (size_t)nr), idr = S.in(desc_r, 32 * (size_t)nr);
+    const size_t wsad = S.work(4 * (size_t)nl);
+    const size_t our = S.out(u_right, 4 * (size_t)nl), odp = S.out(depth, 4 * (size_t)nl);
+    CK(S.commit(left->device));
+    cudaError_t e = S.upload();
     if (e == cudaSuccess) {
         orbfe_launch_stereo(left->g, left->bufs.pyr + (size_t)frame * left->g.pyrStride,
-                            right->bufs.pyr + (size_t)frame * right->g.pyrStride, dkl, ddl, nl, dkr, ddr, nr, mbf, mb,
-                            dur, ddp, dsad, st);
+                            right->bufs.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
+                            S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
+                            S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.stream());
         left->launches += 2;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(u_right, dur, 4 * (size_t)nl, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(depth, ddp, 4 * (size_t)nl, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(dkl); cudaFree(dkr); cudaFree(ddl); cudaFree(ddr); cudaFree(dur); cudaFree(ddp); cudaFree(dsad);
+    if (e == cudaSuccess) e = S.download();
     if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "stereo match", e);
     return ORBFE_OK;
 }

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "orbfe_internal.h"
+#include "scratch.h"
 
 namespace {
 
@@ -463,18 +464,6 @@ int sfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbf
         if (e_ != cudaSuccess) return sfail(ORBFE_ERR_CUDA, #call, e_);  \
     } while (0)
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
-    cudaError_t upload(const void* src, size_t n) {
-        cudaError_t e = alloc(n);
-        if (e == cudaSuccess && n) e = cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
-        return e;
-    }
-    template <class T> T* as() { return (T*)p; }
-};
-
 }  // namespace
 
 extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const OrbfeProjPoints* pts,
@@ -484,7 +473,6 @@ extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const Orb
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) return sfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", ce);
     if (device < 0 || device >= ndev) return sfail(ORBFE_ERR_INVALID, "bad device ordinal");
-    SCK(cudaSetDevice(device));
     if (!frame || !pts || !prm || !assigned) return sfail(ORBFE_ERR_INVALID, "null argument");
     const int n = frame->n, m = pts->m;
     if (n < 0 || m < 0 || prm->mode < 0 || prm->mode > 2) return sfail(ORBFE_ERR_INVALID, "bad sizes or mode");
@@ -500,77 +488,75 @@ extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const Orb
         !pts->desc || (useHist && !pts->angle))
         return sfail(ORBFE_ERR_INVALID, "missing frame / map-point array");
 
-    DevBuf dKeys, dUr, dDesc, dCellOf, dCellStart, dCellItems;
-    SCK(dKeys.upload(frame->keys, sizeof(OrbfeKeyPoint) * (size_t)n));
-    SCK(dDesc.upload(frame->desc, 32 * (size_t)n));
-    if (frame->uright) SCK(dUr.upload(frame->uright, 4 * (size_t)n));
-    SCK(dCellOf.alloc(4 * (size_t)n)); SCK(dCellStart.alloc(4 * (GC * GR + 1))); SCK(dCellItems.alloc(4 * (size_t)n));
-    DevBuf pu, pv, pur, prad, pang, pminl, pmaxl, pvalid, pblocks, pdesc;
-    SCK(pu.upload(pts->u, 4 * (size_t)m)); SCK(pv.upload(pts->v, 4 * (size_t)m));
-    if (pts->ur) SCK(pur.upload(pts->ur, 4 * (size_t)m));
-    SCK(prad.upload(pts->radius, 4 * (size_t)m));
-    if (pts->angle) SCK(pang.upload(pts->angle, 4 * (size_t)m));
-    SCK(pminl.upload(pts->min_level, 4 * (size_t)m)); SCK(pmaxl.upload(pts->max_level, 4 * (size_t)m));
+    // one slab: inputs | assigned (in/out) | work | outputs   (scratch.h)
+    OrbfeStage S;
     std::vector<uint8_t> ones;
     if (!pts->valid) ones.assign(m, 1);
-    SCK(pvalid.upload(pts->valid ? pts->valid : ones.data(), (size_t)m));
-    if (pts->blocks) SCK(pblocks.upload(pts->blocks, (size_t)m));
-    SCK(pdesc.upload(pts->desc, 32 * (size_t)m));
-    DevBuf dClaimed, cA, cB, dBestIdx, dBestDist, dAssigned, dHist, dBin, dFlag;
-    if (claimed) SCK(dClaimed.upload(claimed, (size_t)n));
-    SCK(cA.alloc(4 * (size_t)n)); SCK(cB.alloc(4 * (size_t)n));
-    SCK(dBestIdx.alloc(4 * (size_t)m)); SCK(dBestDist.alloc(4 * (size_t)m));
-    SCK(dAssigned.upload(assigned, 4 * (size_t)n));
-    SCK(dHist.alloc(4 * (HISTO + 2))); SCK(dBin.alloc(4 * (size_t)m)); SCK(dFlag.alloc(4));
-    SCK(cudaMemset(dHist.p, 0, 4 * (HISTO + 2)));
+    const size_t N4 = 4 * (size_t)n, M4 = 4 * (size_t)m;
+    const size_t iKeys = S.in(frame->keys, sizeof(OrbfeKeyPoint) * (size_t)n), iDesc = S.in(frame->desc, 32 * (size_t)n);
+    const size_t iUr = S.in(frame->uright, frame->uright ? N4 : 0);
+    const size_t iU = S.in(pts->u, M4), iV = S.in(pts->v, M4), iPur = S.in(pts->ur, pts->ur ? M4 : 0);
+    const size_t iRad = S.in(pts->radius, M4), iAng = S.in(pts->angle, pts->angle ? M4 : 0);
+    const size_t iMin = S.in(pts->min_level, M4), iMax = S.in(pts->max_level, M4);
+    const size_t iVal = S.in(pts->valid ? pts->valid : ones.data(), (size_t)m), iBlk = S.in(pts->blocks, pts->blocks ? (size_t)m : 0);
+    const size_t iPd = S.in(pts->desc, 32 * (size_t)m), iCl = S.in(claimed, claimed ? (size_t)n : 0);
+    const size_t ioAsg = S.inout(assigned, N4);
+    const size_t wCellOf = S.work(N4), wStart = S.work(4 * (GC * GR + 1)), wItems = S.work(N4), wA = S.work(N4), wB = S.work(N4);
+    const size_t wBin = S.work(M4), wFlag = S.work(256);
+    int nmatches = 0;
+    const size_t oBest = S.out(best_idx, M4), oDist = S.out(best_dist, M4), oHist = S.work(4 * (HISTO + 2)), oN = S.out(&nmatches, 4);
+    SCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    SCK(S.upload());
 
     GridDev F;
-    F.keys = dKeys.as<OrbfeKeyPoint>(); F.uright = frame->uright ? dUr.as<float>() : nullptr;
-    F.desc = dDesc.as<uint32_t>(); F.n = n;
+    F.keys = S.ptr<OrbfeKeyPoint>(iKeys); F.uright = frame->uright ? S.ptr<float>(iUr) : nullptr;
+    F.desc = S.ptr<uint32_t>(iDesc); F.n = n;
     F.minX = frame->min_x; F.minY = frame->min_y; F.maxX = frame->max_x; F.maxY = frame->max_y;
     F.wInv = frame->grid_w_inv; F.hInv = frame->grid_h_inv;
-    F.cellStart = dCellStart.as<int>(); F.cellItems = dCellItems.as<int>();
+    F.cellStart = S.ptr<int>(wStart); F.cellItems = S.ptr<int>(wItems);
     PtsDev P;
-    P.m = m; P.u = pu.as<float>(); P.v = pv.as<float>(); P.ur = pts->ur ? pur.as<float>() : nullptr;
-    P.radius = prad.as<float>(); P.angle = pts->angle ? pang.as<float>() : nullptr;
-    P.minLevel = pminl.as<int>(); P.maxLevel = pmaxl.as<int>(); P.valid = pvalid.as<uint8_t>();
-    P.blocks = pts->blocks ? pblocks.as<uint8_t>() : nullptr; P.desc = pdesc.as<uint32_t>();
+    P.m = m; P.u = S.ptr<float>(iU); P.v = S.ptr<float>(iV); P.ur = pts->ur ? S.ptr<float>(iPur) : nullptr;
+    P.radius = S.ptr<float>(iRad); P.angle = pts->angle ? S.ptr<float>(iAng) : nullptr;
+    P.minLevel = S.ptr<int>(iMin); P.maxLevel = S.ptr<int>(iMax); P.valid = S.ptr<uint8_t>(iVal);
+    P.blocks = pts->blocks ? S.ptr<uint8_t>(iBlk) : nullptr; P.desc = S.ptr<uint32_t>(iPd);
+    int* dAssigned = S.ptr<int>(ioAsg);
+    int* dBestIdx = S.ptr<int>(oBest);
+    int* dBestDist = S.ptr<int>(oDist);
+    int* dHist = S.ptr<int>(oHist);
+    int* dN = S.ptr<int>(oN);
+    int* dFlag = S.ptr<int>(wFlag);
 
-    k_build_grid<<<1, 1024>>>(F.keys, n, F.minX, F.minY, F.wInv, F.hInv, dCellOf.as<int>(), dCellStart.as<int>(),
-                              dCellItems.as<int>());
-    const uint8_t* dcl = claimed ? dClaimed.as<uint8_t>() : nullptr;
-    k_claims_init<<<(n + 255) / 256, 256>>>(dcl, n, cA.as<int>(), cB.as<int>());
-    int* cin = cA.as<int>();
-    int* cout = cB.as<int>();
+    SCK(cudaMemsetAsync(dHist, 0, 4 * (HISTO + 2), st));
+    SCK(cudaMemsetAsync(dN, 0, 4, st));
+    k_build_grid<<<1, 1024, 0, st>>>(F.keys, n, F.minX, F.minY, F.wInv, F.hInv, S.ptr<int>(wCellOf), S.ptr<int>(wStart),
+                                     S.ptr<int>(wItems));
+    const uint8_t* dcl = claimed ? S.ptr<uint8_t>(iCl) : nullptr;
+    int* cin = S.ptr<int>(wA);
+    int* cout = S.ptr<int>(wB);
+    k_claims_init<<<(n + 255) / 256, 256, 0, st>>>(dcl, n, cin, cout);
     const int gridM = (m + 127) / 128;
     int passes = 0;
     for (;;) {
         // cout holds the static claims; the pass lowers entries to the first blocking acceptor
-        k_search_pass<<<gridM, 128>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout,
-                                      dBestIdx.as<int>(), dBestDist.as<int>());
-        SCK(cudaMemset(dFlag.p, 0, 4));
-        k_claims_diff<<<(n + 255) / 256, 256>>>(cout, cin, dcl, n, dFlag.as<int>());
+        SCK(cudaMemsetAsync(dFlag, 0, 4, st));
+        k_search_pass<<<gridM, 128, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBestIdx, dBestDist);
+        k_claims_diff<<<(n + 255) / 256, 256, 0, st>>>(cout, cin, dcl, n, dFlag);
         int changed = 0;
-        SCK(cudaMemcpy(&changed, dFlag.p, 4, cudaMemcpyDeviceToHost));
+        SCK(cudaMemcpyAsync(&changed, dFlag, 4, cudaMemcpyDeviceToHost, st));
+        SCK(cudaStreamSynchronize(st));
         passes++;
         std::swap(cin, cout);  // new claims become the input; the old table was reset by the diff
         if (!changed) break;
         if (passes > m + 1) return sfail(ORBFE_ERR_CUDA, "claim fixpoint did not converge");
     }
-    int* dN = dHist.as<int>() + HISTO;
-    k_assign_prepare<<<gridM, 128>>>(dBestIdx.as<int>(), m, dAssigned.as<int>());
-    k_search_assign<<<gridM, 128>>>(F, P, useHist ? 1 : 0, dBestIdx.as<int>(), dAssigned.as<int>(), dHist.as<int>(),
-                                    dBin.as<int>(), dN);
-    if (useHist) k_search_cull<<<gridM, 128>>>(m, dBestIdx.as<int>(), dBin.as<int>(), dHist.as<int>(), dAssigned.as<int>(), dN);
+    k_assign_prepare<<<gridM, 128, 0, st>>>(dBestIdx, m, dAssigned);
+    k_search_assign<<<gridM, 128, 0, st>>>(F, P, useHist ? 1 : 0, dBestIdx, dAssigned, dHist, S.ptr<int>(wBin), dN);
+    if (useHist) k_search_cull<<<gridM, 128, 0, st>>>(m, dBestIdx, S.ptr<int>(wBin), dHist, dAssigned, dN);
     SCK(cudaGetLastError());
-    int nmatches = 0;
-    SCK(cudaMemcpy(&nmatches, dN, 4, cudaMemcpyDeviceToHost));
-    SCK(cudaMemcpy(assigned, dAssigned.p, 4 * (size_t)n, cudaMemcpyDeviceToHost));
-    if (best_idx) SCK(cudaMemcpy(best_idx, dBestIdx.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
-    if (best_dist) SCK(cudaMemcpy(best_dist, dBestDist.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    SCK(S.download());
     return nmatches;
 }
-
 
 // SearchByProjection for a fisheye stereo frame (F.Nleft != -1), modes ORBFE_SEARCH_MAPPOINTS
 // (ORBmatcher.cc:46-240 incl. :171-237) and ORBFE_SEARCH_LASTFRAME (:1951-2185 incl. :2090-2155).
@@ -600,55 +586,61 @@ extern "C" int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, co
         !pr->max_level || (useHist && !pl->angle))
         return sfail(ORBFE_ERR_INVALID, "missing frame / map-point array");
 
-    DevBuf dKl, dKr, dDl, dDr, dL2R, dR2L, gOf, gStartL, gItemsL, gStartR, gItemsR;
-    SCK(dKl.upload(left->keys, sizeof(OrbfeKeyPoint) * (size_t)Nl)); SCK(dKr.upload(right->keys, sizeof(OrbfeKeyPoint) * (size_t)Nr));
-    SCK(dDl.upload(left->desc, 32 * (size_t)Nl)); SCK(dDr.upload(right->desc, 32 * (size_t)Nr));
-    SCK(dL2R.upload(l2r, 4 * (size_t)Nl)); SCK(dR2L.upload(r2l, 4 * (size_t)Nr));
-    SCK(gOf.alloc(4 * (size_t)std::max(Nl, Nr))); SCK(gStartL.alloc(4 * (GC * GR + 1))); SCK(gItemsL.alloc(4 * (size_t)Nl));
-    SCK(gStartR.alloc(4 * (GC * GR + 1))); SCK(gItemsR.alloc(4 * (size_t)Nr));
-    DevBuf lu, lv, lr, lmin, lmax, lval, lang, lblk, ldesc, ru, rv, rr, rmin, rmax, rval;
+    OrbfeStage S;
     std::vector<uint8_t> ones(m, 1);
-    SCK(lu.upload(pl->u, 4 * (size_t)m)); SCK(lv.upload(pl->v, 4 * (size_t)m)); SCK(lr.upload(pl->radius, 4 * (size_t)m));
-    SCK(lmin.upload(pl->min_level, 4 * (size_t)m)); SCK(lmax.upload(pl->max_level, 4 * (size_t)m));
-    SCK(lval.upload(pl->valid ? pl->valid : ones.data(), (size_t)m));
-    if (pl->angle) SCK(lang.upload(pl->angle, 4 * (size_t)m));
-    if (pl->blocks) SCK(lblk.upload(pl->blocks, (size_t)m));
-    SCK(ldesc.upload(pl->desc, 32 * (size_t)m));
-    SCK(ru.upload(pr->u, 4 * (size_t)m)); SCK(rv.upload(pr->v, 4 * (size_t)m)); SCK(rr.upload(pr->radius, 4 * (size_t)m));
-    SCK(rmin.upload(pr->min_level, 4 * (size_t)m)); SCK(rmax.upload(pr->max_level, 4 * (size_t)m));
-    SCK(rval.upload(pr->valid ? pr->valid : ones.data(), (size_t)m));
-    DevBuf dClaimed, cA, cB, dBL, dBR, dAssigned, dTmax, dHist, dBinL, dBinR, dFlag;
-    if (claimed) SCK(dClaimed.upload(claimed, (size_t)N));
-    SCK(cA.alloc(4 * (size_t)N)); SCK(cB.alloc(4 * (size_t)N));
-    SCK(dBL.alloc(4 * (size_t)m)); SCK(dBR.alloc(4 * (size_t)m));
-    SCK(dAssigned.upload(assigned, 4 * (size_t)N));
-    SCK(dTmax.alloc(4 * (size_t)N)); SCK(cudaMemset(dTmax.p, 0xFF, 4 * (size_t)N));
-    SCK(dHist.alloc(4 * (HISTO + 2))); SCK(cudaMemset(dHist.p, 0, 4 * (HISTO + 2)));
-    SCK(dBinL.alloc(4 * (size_t)m)); SCK(dBinR.alloc(4 * (size_t)m)); SCK(dFlag.alloc(4));
+    const size_t M4 = 4 * (size_t)m, N4 = 4 * (size_t)N;
+    const size_t iKl = S.in(left->keys, sizeof(OrbfeKeyPoint) * (size_t)Nl), iKr = S.in(right->keys, sizeof(OrbfeKeyPoint) * (size_t)Nr);
+    const size_t iDl = S.in(left->desc, 32 * (size_t)Nl), iDr = S.in(right->desc, 32 * (size_t)Nr);
+    const size_t iL2R = S.in(l2r, 4 * (size_t)Nl), iR2L = S.in(r2l, 4 * (size_t)Nr);
+    const size_t iLu = S.in(pl->u, M4), iLv = S.in(pl->v, M4), iLr = S.in(pl->radius, M4);
+    const size_t iLmin = S.in(pl->min_level, M4), iLmax = S.in(pl->max_level, M4);
+    const size_t iLval = S.in(pl->valid ? pl->valid : ones.data(), (size_t)m), iLang = S.in(pl->angle, pl->angle ? M4 : 0);
+    const size_t iLblk = S.in(pl->blocks, pl->blocks ? (size_t)m : 0), iLdesc = S.in(pl->desc, 32 * (size_t)m);
+    const size_t iRu = S.in(pr->u, M4), iRv = S.in(pr->v, M4), iRr = S.in(pr->radius, M4);
+    const size_t iRmin = S.in(pr->min_level, M4), iRmax = S.in(pr->max_level, M4);
+    const size_t iRval = S.in(pr->valid ? pr->valid : ones.data(), (size_t)m), iCl = S.in(claimed, claimed ? (size_t)N : 0);
+    const size_t ioAsg = S.inout(assigned, N4);
+    const size_t wOf = S.work(4 * (size_t)std::max(Nl, Nr)), wStL = S.work(4 * (GC * GR + 1)), wItL = S.work(4 * (size_t)Nl);
+    const size_t wStR = S.work(4 * (GC * GR + 1)), wItR = S.work(4 * (size_t)Nr), wA = S.work(N4), wB = S.work(N4);
+    const size_t wTmax = S.work(N4), wHist = S.work(4 * (HISTO + 2)), wBinL = S.work(M4), wBinR = S.work(M4), wFlag = S.work(256);
+    int nmatches = 0;
+    const size_t oBL = S.out(best_idx_left, M4), oBR = S.out(best_idx_right, M4), oN = S.out(&nmatches, 4);
+    SCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    SCK(S.upload());
+    SCK(cudaMemsetAsync(S.ptr<int>(wTmax), 0xFF, N4, st));
+    SCK(cudaMemsetAsync(S.ptr<int>(wHist), 0, 4 * (HISTO + 2), st));
+    SCK(cudaMemsetAsync(S.ptr<int>(oN), 0, 4, st));
 
     FeDev F;
-    auto fill = [](GridDev& G, const OrbfeFrameView* fv, DevBuf& k, DevBuf& d, DevBuf& st, DevBuf& it) {
-        G.keys = k.as<OrbfeKeyPoint>(); G.uright = nullptr; G.desc = d.as<uint32_t>(); G.n = fv->n;
+    auto fill = [&](GridDev& G, const OrbfeFrameView* fv, size_t k, size_t d, size_t stt, size_t it) {
+        G.keys = S.ptr<OrbfeKeyPoint>(k); G.uright = nullptr; G.desc = S.ptr<uint32_t>(d); G.n = fv->n;
         G.minX = fv->min_x; G.minY = fv->min_y; G.maxX = fv->max_x; G.maxY = fv->max_y;
         G.wInv = fv->grid_w_inv; G.hInv = fv->grid_h_inv;
-        G.cellStart = st.as<int>(); G.cellItems = it.as<int>();
+        G.cellStart = S.ptr<int>(stt); G.cellItems = S.ptr<int>(it);
     };
-    fill(F.L, left, dKl, dDl, gStartL, gItemsL);
-    fill(F.R, right, dKr, dDr, gStartR, gItemsR);
-    F.l2r = dL2R.as<int>(); F.r2l = dR2L.as<int>(); F.Nl = Nl;
+    fill(F.L, left, iKl, iDl, wStL, wItL);
+    fill(F.R, right, iKr, iDr, wStR, wItR);
+    F.l2r = S.ptr<int>(iL2R); F.r2l = S.ptr<int>(iR2L); F.Nl = Nl;
     PtsFe P;
-    P.L.m = m; P.L.u = lu.as<float>(); P.L.v = lv.as<float>(); P.L.ur = nullptr; P.L.radius = lr.as<float>();
-    P.L.angle = pl->angle ? lang.as<float>() : nullptr; P.L.minLevel = lmin.as<int>(); P.L.maxLevel = lmax.as<int>();
-    P.L.valid = lval.as<uint8_t>(); P.L.blocks = pl->blocks ? lblk.as<uint8_t>() : nullptr; P.L.desc = ldesc.as<uint32_t>();
-    P.u = ru.as<float>(); P.v = rv.as<float>(); P.radius = rr.as<float>(); P.minLevel = rmin.as<int>();
-    P.maxLevel = rmax.as<int>(); P.valid = rval.as<uint8_t>();
+    P.L.m = m; P.L.u = S.ptr<float>(iLu); P.L.v = S.ptr<float>(iLv); P.L.ur = nullptr; P.L.radius = S.ptr<float>(iLr);
+    P.L.angle = pl->angle ? S.ptr<float>(iLang) : nullptr; P.L.minLevel = S.ptr<int>(iLmin); P.L.maxLevel = S.ptr<int>(iLmax);
+    P.L.valid = S.ptr<uint8_t>(iLval); P.L.blocks = pl->blocks ? S.ptr<uint8_t>(iLblk) : nullptr; P.L.desc = S.ptr<uint32_t>(iLdesc);
+    P.u = S.ptr<float>(iRu); P.v = S.ptr<float>(iRv); P.radius = S.ptr<float>(iRr); P.minLevel = S.ptr<int>(iRmin);
+    P.maxLevel = S.ptr<int>(iRmax); P.valid = S.ptr<uint8_t>(iRval);
+    int* dBL = S.ptr<int>(oBL);
+    int* dBR = S.ptr<int>(oBR);
+    int* dAssigned = S.ptr<int>(ioAsg);
+    int* dN = S.ptr<int>(oN);
+    int* dFlag = S.ptr<int>(wFlag);
 
-    k_build_grid<<<1, 1024>>>(F.L.keys, Nl, F.L.minX, F.L.minY, F.L.wInv, F.L.hInv, gOf.as<int>(), gStartL.as<int>(), gItemsL.as<int>());
-    k_build_grid<<<1, 1024>>>(F.R.keys, Nr, F.R.minX, F.R.minY, F.R.wInv, F.R.hInv, gOf.as<int>(), gStartR.as<int>(), gItemsR.as<int>());
-    const uint8_t* dcl = claimed ? dClaimed.as<uint8_t>() : nullptr;
-    k_claims_init<<<(N + 255) / 256, 256>>>(dcl, N, cA.as<int>(), cB.as<int>());
+    k_build_grid<<<1, 1024, 0, st>>>(F.L.keys, Nl, F.L.minX, F.L.minY, F.L.wInv, F.L.hInv, S.ptr<int>(wOf), S.ptr<int>(wStL), S.ptr<int>(wItL));
+    k_build_grid<<<1, 1024, 0, st>>>(F.R.keys, Nr, F.R.minX, F.R.minY, F.R.wInv, F.R.hInv, S.ptr<int>(wOf), S.ptr<int>(wStR), S.ptr<int>(wItR));
+    const uint8_t* dcl = claimed ? S.ptr<uint8_t>(iCl) : nullptr;
+    int* cin = S.ptr<int>(wA);
+    int* cout = S.ptr<int>(wB);
+    k_claims_init<<<(N + 255) / 256, 256, 0, st>>>(dcl, N, cin, cout);
     const int gridM = (m + 127) / 128;
-    int* dN = dHist.as<int>() + HISTO;
 
     // A non-blocking point that overwrites a slot through a stereo partner write un-blocks it: only
     // the ordered pass expresses that (never happens for local-map points, which are all observed).
@@ -661,35 +653,28 @@ extern "C" int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, co
         sequential = anyFree && anyLink;
     }
     if (sequential) {
-        k_search_fe_sequential<<<1, 32>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cA.as<int>(), dAssigned.as<int>(),
-                                          dBL.as<int>(), dBR.as<int>(), dN);
+        k_search_fe_sequential<<<1, 32, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, dAssigned, dBL, dBR, dN);
     } else {
-        int* cin = cA.as<int>();
-        int* cout = cB.as<int>();
         int passes = 0;
         for (;;) {
-            k_search_pass_fe<<<gridM, 128>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBL.as<int>(), dBR.as<int>());
-            SCK(cudaMemset(dFlag.p, 0, 4));
-            k_claims_diff<<<(N + 255) / 256, 256>>>(cout, cin, dcl, N, dFlag.as<int>());
+            SCK(cudaMemsetAsync(dFlag, 0, 4, st));
+            k_search_pass_fe<<<gridM, 128, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBL, dBR);
+            k_claims_diff<<<(N + 255) / 256, 256, 0, st>>>(cout, cin, dcl, N, dFlag);
             int changed = 0;
-            SCK(cudaMemcpy(&changed, dFlag.p, 4, cudaMemcpyDeviceToHost));
+            SCK(cudaMemcpyAsync(&changed, dFlag, 4, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
             passes++;
             std::swap(cin, cout);
             if (!changed) break;
             if (passes > 2 * m + 2) return sfail(ORBFE_ERR_CUDA, "claim fixpoint did not converge");
         }
-        k_fe_assign<<<gridM, 128>>>(F, P, prm->mode, useHist ? 1 : 0, dBL.as<int>(), dBR.as<int>(), dTmax.as<int>(),
-                                    dHist.as<int>(), dBinL.as<int>(), dBinR.as<int>(), dN);
-        k_fe_commit<<<(N + 255) / 256, 256>>>(N, dTmax.as<int>(), dAssigned.as<int>());
+        k_fe_assign<<<gridM, 128, 0, st>>>(F, P, prm->mode, useHist ? 1 : 0, dBL, dBR, S.ptr<int>(wTmax), S.ptr<int>(wHist),
+                                           S.ptr<int>(wBinL), S.ptr<int>(wBinR), dN);
+        k_fe_commit<<<(N + 255) / 256, 256, 0, st>>>(N, S.ptr<int>(wTmax), dAssigned);
         if (useHist)
-            k_fe_cull<<<gridM, 128>>>(m, Nl, dBL.as<int>(), dBR.as<int>(), dBinL.as<int>(), dBinR.as<int>(), dHist.as<int>(),
-                                      dAssigned.as<int>(), dN);
+            k_fe_cull<<<gridM, 128, 0, st>>>(m, Nl, dBL, dBR, S.ptr<int>(wBinL), S.ptr<int>(wBinR), S.ptr<int>(wHist), dAssigned, dN);
     }
     SCK(cudaGetLastError());
-    int nmatches = 0;
-    SCK(cudaMemcpy(&nmatches, dN, 4, cudaMemcpyDeviceToHost));
-    SCK(cudaMemcpy(assigned, dAssigned.p, 4 * (size_t)N, cudaMemcpyDeviceToHost));
-    if (best_idx_left) SCK(cudaMemcpy(best_idx_left, dBL.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
-    if (best_idx_right) SCK(cudaMemcpy(best_idx_right, dBR.p, 4 * (size_t)m, cudaMemcpyDeviceToHost));
+    SCK(S.download());
     return nmatches;
 }

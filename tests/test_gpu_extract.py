@@ -189,3 +189,11 @@ def test_c4_batch_1280x720(orbfe):
         mo, ko, do = ex_c(frames[i], (0, 1000))
         assert mono[i] == mo and n[i] == len(ko) and 0 < mo < len(ko)       # lapping {0,1000} splits 1280-px frames
         assert kps[i, :n[i]].tobytes() == ko.tobytes() and np.array_equal(desc[i, :n[i]], do)
+
+
+@pytest.mark.parametrize("nf", [5000, 10000, 30000])
+def test_large_nfeatures_octree_tables(orbfe, nf):
+    """mpIniORBextractor uses 5 x nFeatures (Tracking.cc:665).  10000 features still fit the shared-memory
+    quadtree tables (> 48 KB opt-in), 30000 go through the global-memory tables."""
+    img = synth.noise_frame(480, 752, 12)
+    _check_frame(orbfe.ORBextractor(nf), O.Extractor(nf), img, (0, 1000), stages=False)
