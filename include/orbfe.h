@@ -140,6 +140,10 @@ int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, in
 int orbfe_knn2_merge_device(const int32_t* d_idx2_shards, const int32_t* d_dist2_shards, int G,
                             int nq, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match,
                             void* stream);
+/* Same for tables gathered as ONE buffer: packed[s] = { idx2[nq][2], dist2[nq][2] } of shard s, so
+ * that a single all-gather moves both tables of every shard. */
+int orbfe_knn2_merge_packed_device(const int32_t* d_packed, int G, int nq, int32_t* d_idx2,
+                                   int32_t* d_dist2, int32_t* d_match, void* stream);
 
 /* The part of ORB_SLAM3::Frame the projection matchers read (Nleft == -1 layout):
  * mvKeysUn, mvuRight, mDescriptors, mnMinX..mnMaxY, mfGridElement{Width,Height}Inv,

@@ -23,7 +23,7 @@ constexpr int KEY_SHIFT = 23;                   // train indices < 2^23 per laun
 constexpr int KNN_THREADS = 128, KNN_QPT = 2;   // queries per thread
 constexpr int KNN_QB = KNN_THREADS * KNN_QPT;   // queries per CTA
 constexpr int KNN_TILE = 256;                   // train descriptors staged per iteration
-constexpr int KNN_CHUNK = 4096;                 // train descriptors per CTA
+constexpr int KNN_CHUNK_MAX = 4096;             // train descriptors per CTA (upper bound)
 
 __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) {
     int d = 0;
@@ -73,7 +73,7 @@ __global__ void k_hamming_pairs(const uint32_t* __restrict__ a, const uint32_t* 
 // partial[q][chunk][2] = two smallest keys of query q over train chunk `chunk`
 __global__ void __launch_bounds__(KNN_THREADS)
 k_knn2_partial(const uint32_t* __restrict__ query, int nq, const uint32_t* __restrict__ train, int nt,
-               int nchunks, uint32_t* __restrict__ partial) {
+               int chunk, int nchunks, uint32_t* __restrict__ partial) {
     __shared__ __align__(16) uint32_t tile[KNN_TILE * 8];
     const int q0 = blockIdx.x * KNN_QB + threadIdx.x;
     uint32_t qv[KNN_QPT][8];
@@ -87,7 +87,7 @@ k_knn2_partial(const uint32_t* __restrict__ query, int nq, const uint32_t* __res
         b0[r] = KEY_NONE;
         b1[r] = KEY_NONE;
     }
-    const int c0 = blockIdx.y * KNN_CHUNK, c1 = min(c0 + KNN_CHUNK, nt);
+    const int c0 = blockIdx.y * chunk, c1 = min(c0 + chunk, nt);
     for (int t0 = c0; t0 < c1; t0 += KNN_TILE) {
         const int cnt = min(KNN_TILE, c1 - t0);
         __syncthreads();
@@ -149,14 +149,14 @@ k_knn2_merge_keys(const uint32_t* __restrict__ partial, int nq, int nparts, int 
 
 // Merge G per-shard (idx2, dist2) tables [G][nq][2] with global indices: order (dist, idx).
 __global__ void k_knn2_merge_tables(const int32_t* __restrict__ idxS, const int32_t* __restrict__ distS,
-                                    int G, int nq, int32_t* __restrict__ idx2, int32_t* __restrict__ dist2,
-                                    int32_t* __restrict__ match) {
+                                    size_t shardStride, int G, int nq, int32_t* __restrict__ idx2,
+                                    int32_t* __restrict__ dist2, int32_t* __restrict__ match) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     unsigned long long b0 = ~0ull, b1 = ~0ull;
     for (int s = 0; s < G; s++)
         for (int k = 0; k < 2; k++) {
-            const int i = idxS[((size_t)s * nq + q) * 2 + k], d = distS[((size_t)s * nq + q) * 2 + k];
+            const int i = idxS[s * shardStride + (size_t)q * 2 + k], d = distS[s * shardStride + (size_t)q * 2 + k];
             if (i < 0) continue;
             const unsigned long long key = ((unsigned long long)(unsigned)d << 32) | (unsigned)i;
             const unsigned long long hi = b0 > key ? b0 : key;
@@ -189,15 +189,26 @@ int set_device(int device) {
 
 }  // namespace
 
+// Train descriptors per CTA: small enough that the grid covers the 148 SMs several times (a shard of
+// a map split over 8 GPUs is only 125 k descriptors), a multiple of the staging tile.
+static int knn2_chunk(int nq, int nt) {
+    const int qblocks = (nq + KNN_QB - 1) / KNN_QB;
+    const int wantChunks = (148 * 8 + qblocks - 1) / qblocks;
+    int chunk = (nt + wantChunks - 1) / std::max(wantChunks, 1);
+    chunk = (chunk + KNN_TILE - 1) / KNN_TILE * KNN_TILE;
+    return std::min(std::max(chunk, KNN_TILE), KNN_CHUNK_MAX);
+}
+
 // Enqueue kNN-2 on `st`: idx2/dist2 (and match when non-null) for nq queries against nt train rows.
 int orbfe_knn2_enqueue(const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int train_offset,
                        int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, uint32_t* d_partial,
                        cudaStream_t st) {
-    const int nchunks = std::max(1, (nt + KNN_CHUNK - 1) / KNN_CHUNK);
+    const int chunk = knn2_chunk(nq, nt);
+    const int nchunks = std::max(1, (nt + chunk - 1) / chunk);
     if (nt > 0) {
         dim3 grid((nq + KNN_QB - 1) / KNN_QB, nchunks);
         k_knn2_partial<<<grid, KNN_THREADS, 0, st>>>((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt,
-                                                     nchunks, d_partial);
+                                                     chunk, nchunks, d_partial);
     } else {
         cudaMemsetAsync(d_partial, 0xFF, sizeof(uint32_t) * 2 * (size_t)nq, st);
     }
@@ -206,7 +217,8 @@ int orbfe_knn2_enqueue(const uint8_t* d_query, int nq, const uint8_t* d_train, i
 }
 
 size_t orbfe_knn2_partial_bytes(int nq, int nt) {
-    const int nchunks = std::max(1, (nt + KNN_CHUNK - 1) / KNN_CHUNK);
+    const int chunk = knn2_chunk(nq, nt);
+    const int nchunks = std::max(1, (nt + chunk - 1) / chunk);
     return sizeof(uint32_t) * 2 * (size_t)nq * nchunks;
 }
 
@@ -264,8 +276,18 @@ int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int t
 int orbfe_knn2_merge_device(const int32_t* d_idx2_shards, const int32_t* d_dist2_shards, int G, int nq,
                             int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, void* stream) {
     if (nq <= 0 || G <= 0) return ORBFE_OK;
-    k_knn2_merge_tables<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_idx2_shards, d_dist2_shards, G, nq,
-                                                                           d_idx2, d_dist2, d_match);
+    k_knn2_merge_tables<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_idx2_shards, d_dist2_shards, 2 * (size_t)nq, G,
+                                                                           nq, d_idx2, d_dist2, d_match);
+    MCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_merge_packed_device(const int32_t* d_packed, int G, int nq, int32_t* d_idx2, int32_t* d_dist2,
+                                   int32_t* d_match, void* stream) {
+    if (nq <= 0 || G <= 0) return ORBFE_OK;
+    // packed[s] = { idx2[nq][2], dist2[nq][2] } of shard s: one all-gather moves both tables
+    k_knn2_merge_tables<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_packed, d_packed + 2 * (size_t)nq, 4 * (size_t)nq,
+                                                                           G, nq, d_idx2, d_dist2, d_match);
     MCK(cudaGetLastError());
     return ORBFE_OK;
 }

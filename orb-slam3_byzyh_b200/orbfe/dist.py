@@ -50,16 +50,21 @@ class ShardedMap:
         CUDA tensors with GLOBAL map indices, identical on every rank."""
         L = _lib.lib()
         nq = d_query.shape[0]
-        idx = torch.empty((nq, 2), dtype=torch.int32, device=self.device)
-        dst = torch.empty((nq, 2), dtype=torch.int32, device=self.device)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        tab = torch.empty((2, nq, 2), dtype=torch.int32, device=self.device)   # {idx2, dist2} of this shard
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(L.orbfe_knn2_device(_lib.ptr(d_query), nq, _lib.ptr(self.train), self.train.shape[0], self.lo,
-                                       _lib.ptr(idx), _lib.ptr(dst), st))
-        g_idx, g_dist = gather_tables(idx, dst, group)
-        f_idx, f_dist = torch.empty_like(idx), torch.empty_like(dst)
+                                       _lib.ptr(tab[0]), _lib.ptr(tab[1]), st))
+        if world > 1:
+            packed = torch.empty((world, 2, nq, 2), dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(packed, tab, group=group)      # the one exchange step (NCCL / NVLink)
+        else:
+            packed = tab
+        f_idx = torch.empty((nq, 2), dtype=torch.int32, device=self.device)
+        f_dist = torch.empty_like(f_idx)
         match = torch.empty(nq, dtype=torch.int32, device=self.device)
-        _lib.check(L.orbfe_knn2_merge_device(_lib.ptr(g_idx), _lib.ptr(g_dist), g_idx.shape[0], nq, _lib.ptr(f_idx),
-                                             _lib.ptr(f_dist), _lib.ptr(match), st))
+        _lib.check(L.orbfe_knn2_merge_packed_device(_lib.ptr(packed), world, nq, _lib.ptr(f_idx), _lib.ptr(f_dist),
+                                                    _lib.ptr(match), st))
         return f_idx, f_dist, match
 
 

@@ -248,3 +248,17 @@ def test_search_by_projection_fisheye(orbfe, mode, all_block):
                                                         mode, 100, 0.8, True, claimed, assigned)
     assert n == en and n > 300 and (ebr >= 0).sum() > 100
     assert np.array_equal(bl, ebl) and np.array_equal(br, ebr) and np.array_equal(asg, easg)
+
+
+def test_sharded_map_device_path(orbfe):
+    """orbfe.dist.ShardedMap (device-resident shard, packed gather layout) at world size 1 equals knn2."""
+    import torch
+    import orbfe.dist as D
+    q, t = synth.random_descriptors(700, 5), synth.random_descriptors(50000, 6)
+    t[123] = q[9]; t[40000] = q[9]
+    dev = torch.device("cuda:0")
+    smap = D.ShardedMap(t, 0, dev)
+    idx, dist, match = smap.knn2(torch.from_numpy(q).to(dev))
+    eidx, edist, ematch = orbfe.ORBmatcher().knn2(q, t)
+    assert np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)
+    assert np.array_equal(match.cpu().numpy(), ematch)
