@@ -213,6 +213,15 @@ int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, const OrbfeFr
                                        int32_t* assigned, int32_t* best_idx_left,
                                        int32_t* best_idx_right, int device);
 
+/* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ * vector<int>& vnMatches12, int windowSize)   include/ORBmatcher.h:67, src/ORBmatcher.cc:735-891
+ * (monocular initialisation; first of the SURVEY 8(f) "next" matchers).  f1 / f2 = mvKeysUn +
+ * mDescriptors of the two frames (f2 with its grid bounds); prev_matched = vbPrevMatched as n1 x 2
+ * floats (in/out); matches12 = vnMatches12 (out, -1 = none).  Returns nmatches. */
+int orbfe_search_for_initialization(const OrbfeFrameView* f1, const OrbfeFrameView* f2,
+                                    float* prev_matched, int window_size, float nnratio,
+                                    int check_orientation, int32_t* matches12, int device);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

@@ -253,6 +253,64 @@ int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, c
     return nmatches;
 }
 
+// reference src/ORBmatcher.cc:735-891
+int search_for_initialization(const FrameView& F1, FrameView& F2, float* vbPrevMatched, int windowSize,
+                              float mfNNratio, bool mbCheckOrientation, int* vnMatches12) {
+    int nmatches = 0;
+    for (int i = 0; i < F1.N; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float factor = 1.0f / HISTO_LENGTH;
+    std::vector<int> vMatchedDistance(F2.N, INT_MAX);
+    std::vector<int> vnMatches21(F2.N, -1);
+    for (int i1 = 0; i1 < F1.N; i1++) {
+        const OrbKp& kp1 = F1.keys[i1];
+        const int level1 = kp1.octave;
+        if (level1 > 0) continue;
+        const std::vector<int> vIndices2 = F2.features_in_area(vbPrevMatched[2 * i1], vbPrevMatched[2 * i1 + 1],
+                                                               (float)windowSize, level1, level1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = F1.desc + 32 * (size_t)i1;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(d1, F2.desc + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * mfNNratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (mbCheckOrientation) {
+                    float rot = F1.keys[i1].angle - F2.keys[bestIdx2].angle;
+                    if (rot < 0.0) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    rotHist[bin].push_back(i1);
+                }
+            }
+        }
+    }
+    if (mbCheckOrientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < F1.N; i1++)
+        if (vnMatches12[i1] >= 0) {
+            vbPrevMatched[2 * i1] = F2.keys[vnMatches12[i1]].x;
+            vbPrevMatched[2 * i1 + 1] = F2.keys[vnMatches12[i1]].y;
+        }
+    return nmatches;
+}
+
 // reference src/Frame.cc:1102-1358
 void compute_stereo_matches(const OrbKp* keysL, const uint8_t* descL, int N, const OrbKp* keysR,
                             const uint8_t* descR, int Nr, const PyrLevelView* pyrL,

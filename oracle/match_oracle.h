@@ -82,6 +82,12 @@ int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, c
                                  const uint8_t* pdesc, const SearchParams& prm, const uint8_t* claimed,
                                  int* assigned, int* best_idx_l, int* best_idx_r);
 
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+// src/ORBmatcher.cc:735-891.  F1 needs keys / desc only; F2 is searched through its grid.
+// prevMatched: n1 x 2 floats (in/out), matches12: n1 ints (out).  Returns nmatches.
+int search_for_initialization(const FrameView& F1, FrameView& F2, float* prevMatched, int windowSize,
+                              float nnratio, bool checkOrientation, int* matches12);
+
 // Frame::ComputeStereoMatches on two extractor pyramids.
 struct PyrLevelView {
     const uint8_t* roi;

@@ -288,3 +288,15 @@ def search_by_projection_fisheye(keysL, descL, keysR, descR, bounds, l2r, r2l, p
     n = lib().oracle_search_by_projection_fisheye(C.byref(fl), C.byref(fr), _p(l2r), _p(r2l), C.byref(pl), C.byref(pr),
                                                   C.byref(prm), _p(claimed), _p(assigned), _p(bl), _p(br))
     return n, assigned, bl, br
+
+
+def search_for_initialization(keys1, desc1, keys2, desc2, bounds, prev_matched, window_size, nnratio, check_orientation):
+    keep = []
+    f1 = make_frame_view(keys1, desc1, None, bounds, keep)
+    f2 = make_frame_view(keys2, desc2, None, bounds, keep)
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.empty(len(keys1), np.int32)
+    lib().oracle_search_for_initialization.argtypes = None
+    n = lib().oracle_search_for_initialization(C.byref(f1), C.byref(f2), _p(prev), int(window_size), C.c_float(nnratio),
+                                               int(check_orientation), _p(m12))
+    return n, m12, prev

@@ -173,6 +173,14 @@ int oracle_search_by_projection_fisheye(const OrbfeFrameView* fl, const OrbfeFra
                                                       best_l, best_r);
 }
 
+int oracle_search_for_initialization(const OrbfeFrameView* f1, const OrbfeFrameView* f2, float* prev, int windowSize,
+                                     float nnratio, int checkOri, int32_t* matches12) {
+    match_oracle::FrameView F1, F2;
+    F1.N = f1->n; F1.keys = (const OrbKp*)f1->keys; F1.desc = f1->desc;
+    fill_view(F2, f2);
+    return match_oracle::search_for_initialization(F1, F2, prev, windowSize, nnratio, checkOri != 0, matches12);
+}
+
 // Grid query tap: indices returned by GetFeaturesInArea, in the reference's order.
 int oracle_features_in_area(const OrbfeFrameView* fv, float x, float y, float r, int minLevel,
                             int maxLevel, int32_t* out, int cap) {

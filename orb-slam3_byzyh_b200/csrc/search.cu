@@ -457,6 +457,139 @@ __global__ void k_search_fe_sequential(FeDev F, PtsFe P, int mode, int thAccept,
     *nmatches = n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:735-891).  A keypoint of F2 can be taken over by a
+// later keypoint of F1 with a strictly smaller distance (vMatchedDistance), so the loop over F1 is
+// kept in order; ONE warp walks it and spreads the ~100 window candidates of each step over its
+// lanes.  Candidate order (ties under the strict `<`) is carried in the low bits of the packed key.
+__global__ void __launch_bounds__(32)
+k_search_init(const OrbfeKeyPoint* __restrict__ keys1, const uint32_t* __restrict__ desc1, int n1, GridDev F2,
+              float* __restrict__ prev, float window, float nnratio, int checkOri, int thLow,
+              int* __restrict__ m12, int* __restrict__ m21, int* __restrict__ matchedDist, int* __restrict__ binOf,
+              int* __restrict__ nmatchesOut) {
+    const int lane = threadIdx.x;
+    __shared__ int hist[HISTO];
+    for (int i = lane; i < HISTO; i += 32) hist[i] = 0;
+    for (int i = lane; i < n1; i += 32) { m12[i] = -1; binOf[i] = -1; }
+    for (int i = lane; i < F2.n; i += 32) { m21[i] = -1; matchedDist[i] = INT_MAX; }
+    __syncwarp();
+    int nmatches = 0;
+    const float factor = 1.0f / HISTO;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const OrbfeKeyPoint kp1 = keys1[i1];
+        if (kp1.octave > 0) continue;
+        const float x = prev[2 * i1], y = prev[2 * i1 + 1], r = window;
+        const int c0x = max(0, (int)floorf((x - F2.minX - r) * F2.wInv));
+        const int c1x = min(GC - 1, (int)ceilf((x - F2.minX + r) * F2.wInv));
+        const int c0y = max(0, (int)floorf((y - F2.minY - r) * F2.hInv));
+        const int c1y = min(GR - 1, (int)ceilf((y - F2.minY + r) * F2.hInv));
+        if (!(c0x < GC && c1x >= 0 && c0y < GR && c1y >= 0)) continue;
+        uint32_t d[8];
+        const uint4* pd = reinterpret_cast<const uint4*>(desc1 + 8 * (size_t)i1);
+        *reinterpret_cast<uint4*>(d) = pd[0];
+        *reinterpret_cast<uint4*>(d + 4) = pd[1];
+        uint32_t b0 = 0xFFFFFFFFu, b1 = 0xFFFFFFFFu;   // packed (dist << 20 | order), order < 2^20
+        bool had = false;
+        int seq = 0;
+        for (int ix = c0x; ix <= c1x; ix++) {
+            // the cells (ix, c0y..c1y) are consecutive in cellItems: one contiguous run per grid column
+            const int cb = F2.cellStart[ix * GR + c0y], ce = F2.cellStart[ix * GR + c1y + 1];
+            for (int tb = cb; tb < ce; tb += 32, seq += 32) {
+                const int t = tb + lane;
+                if (t < ce) {
+                    const int i2 = F2.cellItems[t];
+                    const OrbfeKeyPoint kp = F2.keys[i2];
+                    // level1 == 0: GetFeaturesInArea(.., 0, 0) keeps octave 0 only (bCheckLevels is true)
+                    if (kp.octave == 0 && fabsf(kp.x - x) < r && fabsf(kp.y - y) < r) {
+                        had = true;
+                        const uint4* kd = reinterpret_cast<const uint4*>(F2.desc + 8 * (size_t)i2);
+                        const int dist = hamming8(d, kd[0], kd[1]);
+                        if (!(matchedDist[i2] <= dist)) {
+                            const uint32_t key = ((uint32_t)dist << 20) | (uint32_t)(seq + lane);
+                            const uint32_t hi = max(b0, key);
+                            b0 = min(b0, key);
+                            b1 = min(b1, hi);
+                        }
+                    }
+                }
+            }
+        }
+        had = __any_sync(0xffffffffu, had);
+        if (!had) continue;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+            uint32_t hi = max(b0, o0);
+            b0 = min(b0, o0);
+            b1 = min(b1, hi);
+            hi = max(b0, o1);   // o1 >= o0 >= new b0 is not guaranteed after the first min: insert again
+            b0 = min(b0, o1);
+            b1 = min(b1, hi);
+        }
+        if (b0 == 0xFFFFFFFFu) continue;                       // bestDist == INT_MAX
+        const int bestDist = (int)(b0 >> 20);
+        const float second = b1 == 0xFFFFFFFFu ? (float)INT_MAX : (float)(int)(b1 >> 20);
+        if (bestDist <= thLow && (float)bestDist < second * nnratio) {
+            // which keypoint carries order (b0 & 0xFFFFF)?  recompute its index from the run layout
+            int best = -1;
+            {
+                int want = (int)(b0 & 0xFFFFFu), s = 0;
+                for (int ix = c0x; ix <= c1x && best < 0; ix++) {
+                    const int cb = F2.cellStart[ix * GR + c0y], ce = F2.cellStart[ix * GR + c1y + 1];
+                    const int len = ce - cb, padded = (len + 31) & ~31;
+                    if (want < s + padded) best = F2.cellItems[cb + (want - s)];
+                    s += padded;
+                }
+            }
+            if (lane == 0) {
+                if (m21[best] >= 0) { m12[m21[best]] = -1; nmatches--; }
+                m12[i1] = best;
+                m21[best] = i1;
+                matchedDist[best] = bestDist;
+                nmatches++;
+                if (checkOri) {
+                    float rot = kp1.angle - F2.keys[best].angle;
+                    if (rot < 0.0f) rot += 360.0f;
+                    int bin = (int)roundf(rot * factor);
+                    if (bin == HISTO) bin = 0;
+                    bin = min(max(bin, 0), HISTO - 1);
+                    binOf[i1] = bin;
+                    hist[bin]++;
+                }
+            }
+            __syncwarp();   // the next steps read matchedDist / m21 written by lane 0
+        }
+    }
+    __syncwarp();
+    if (checkOri) {
+        int keep0, keep1, keep2;
+        {
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < HISTO; i++) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+            else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+            keep0 = ind1; keep1 = ind2; keep2 = ind3;
+        }
+        int removed = 0;
+        for (int i = lane; i < n1; i += 32) {
+            const int b = binOf[i];
+            if (b >= 0 && b != keep0 && b != keep1 && b != keep2 && m12[i] >= 0) { m12[i] = -1; removed++; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+        nmatches -= removed;     // lane 0 holds the running count; every lane now knows `removed`
+    }
+    __syncwarp();
+    for (int i = lane; i < n1; i += 32)
+        if (m12[i] >= 0) { prev[2 * i] = F2.keys[m12[i]].x; prev[2 * i + 1] = F2.keys[m12[i]].y; }
+    if (lane == 0) *nmatchesOut = nmatches;
+}
+
 int sfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
 #define SCK(call)                                                        \
     do {                                                                 \
@@ -674,6 +807,47 @@ extern "C" int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, co
         if (useHist)
             k_fe_cull<<<gridM, 128, 0, st>>>(m, Nl, dBL, dBR, S.ptr<int>(wBinL), S.ptr<int>(wBinR), S.ptr<int>(wHist), dAssigned, dN);
     }
+    SCK(cudaGetLastError());
+    SCK(S.download());
+    return nmatches;
+}
+
+
+// int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+//                                         vector<int>& vnMatches12, int windowSize)   ORBmatcher.cc:735-891
+extern "C" int orbfe_search_for_initialization(const OrbfeFrameView* f1, const OrbfeFrameView* f2, float* prev_matched,
+                                               int window_size, float nnratio, int check_orientation,
+                                               int32_t* matches12, int device) {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return sfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return sfail(ORBFE_ERR_INVALID, "bad device ordinal");
+    if (!f1 || !f2 || !matches12) return sfail(ORBFE_ERR_INVALID, "null argument");
+    const int n1 = f1->n, n2 = f2->n;
+    if (n1 < 0 || n2 < 0) return sfail(ORBFE_ERR_INVALID, "bad sizes");
+    for (int i = 0; i < n1; i++) matches12[i] = -1;
+    if (n1 == 0 || n2 == 0) return 0;
+    if (!f1->keys || !f1->desc || !f2->keys || !f2->desc || !prev_matched) return sfail(ORBFE_ERR_INVALID, "missing array");
+    OrbfeStage S;
+    const size_t iK1 = S.in(f1->keys, sizeof(OrbfeKeyPoint) * (size_t)n1), iD1 = S.in(f1->desc, 32 * (size_t)n1);
+    const size_t iK2 = S.in(f2->keys, sizeof(OrbfeKeyPoint) * (size_t)n2), iD2 = S.in(f2->desc, 32 * (size_t)n2);
+    const size_t ioPrev = S.inout(prev_matched, 8 * (size_t)n1);
+    const size_t wOf = S.work(4 * (size_t)n2), wSt = S.work(4 * (GC * GR + 1)), wIt = S.work(4 * (size_t)n2);
+    const size_t wM21 = S.work(4 * (size_t)n2), wMd = S.work(4 * (size_t)n2), wBin = S.work(4 * (size_t)n1);
+    int nmatches = 0;
+    const size_t oM12 = S.out(matches12, 4 * (size_t)n1), oN = S.out(&nmatches, 4);
+    SCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    SCK(S.upload());
+    GridDev F;
+    F.keys = S.ptr<OrbfeKeyPoint>(iK2); F.uright = nullptr; F.desc = S.ptr<uint32_t>(iD2); F.n = n2;
+    F.minX = f2->min_x; F.minY = f2->min_y; F.maxX = f2->max_x; F.maxY = f2->max_y;
+    F.wInv = f2->grid_w_inv; F.hInv = f2->grid_h_inv;
+    F.cellStart = S.ptr<int>(wSt); F.cellItems = S.ptr<int>(wIt);
+    k_build_grid<<<1, 1024, 0, st>>>(F.keys, n2, F.minX, F.minY, F.wInv, F.hInv, S.ptr<int>(wOf), S.ptr<int>(wSt), S.ptr<int>(wIt));
+    k_search_init<<<1, 32, 0, st>>>(S.ptr<OrbfeKeyPoint>(iK1), S.ptr<uint32_t>(iD1), n1, F, S.ptr<float>(ioPrev),
+                                    (float)window_size, nnratio, check_orientation, 50 /* TH_LOW */, S.ptr<int>(oM12),
+                                    S.ptr<int>(wM21), S.ptr<int>(wMd), S.ptr<int>(wBin), S.ptr<int>(oN));
     SCK(cudaGetLastError());
     SCK(S.download());
     return nmatches;

@@ -83,6 +83,7 @@ _SIGS = {
     "orbfe_search_by_projection_fisheye": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), _vp, _vp,
                                                 C.POINTER(ProjPoints), C.POINTER(ProjPoints), C.POINTER(SearchParams),
                                                 _vp, _vp, _vp, _vp, _i]),
+    "orbfe_search_for_initialization": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), _vp, _i, _f, _i, _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

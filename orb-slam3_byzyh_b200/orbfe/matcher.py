@@ -119,6 +119,17 @@ class ORBmatcher:
                                                            ptr(bl), ptr(br), self.device))
         return n, assigned, bl, br
 
+    # SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:735-891
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=100):
+        keep = []
+        f1, f2 = F1.view(keep), F2.view(keep)
+        prev = np.ascontiguousarray(vbPrevMatched, np.float32).copy()
+        m12 = np.empty(f1.n, np.int32)
+        n = check(lib().orbfe_search_for_initialization(C.byref(f1), C.byref(f2), ptr(prev), int(windowSize),
+                                                        self.mfNNratio, int(self.mbCheckOrientation), ptr(m12),
+                                                        self.device))
+        return n, m12, prev
+
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):
         q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)

@@ -262,3 +262,20 @@ def test_sharded_map_device_path(orbfe):
     eidx, edist, ematch = orbfe.ORBmatcher().knn2(q, t)
     assert np.array_equal(idx.cpu().numpy(), eidx) and np.array_equal(dist.cpu().numpy(), edist)
     assert np.array_equal(match.cpu().numpy(), ematch)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_for_initialization(orbfe, seed):
+    """Monocular initialisation matcher (ORBmatcher.cc:735-891) on two real extractions of a shifted scene:
+    take-over of already matched keypoints, ratio test, rotation histogram, vbPrevMatched update."""
+    a, b = synth.shifted_pair(480, 752, seed)
+    ex = orbfe.ORBextractor(5000)                      # mpIniORBextractor = 5 x nFeatures
+    _, k1, d1 = ex(a, None, (0, 1000))
+    _, k2, d2 = ex(b, None, (0, 1000))
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    m = orbfe.ORBmatcher(nnratio=0.9, checkOri=True)
+    n, m12, pv = m.SearchForInitialization(orbfe.FrameData(k1, d1, bounds), orbfe.FrameData(k2, d2, bounds), prev, 100)
+    en, em12, epv = O.search_for_initialization(k1, d1, k2, d2, bounds, prev, 100, 0.9, True)
+    assert n == en and n > 100
+    assert np.array_equal(m12, em12) and np.array_equal(pv.view(np.uint32), epv.view(np.uint32))
