@@ -94,6 +94,12 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            # a fresh checkout (built artefacts are git-ignored): compile the CUDA sources once
+            import shutil
+            import subprocess
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                subprocess.call(["make", "-s", "-j8", "-C", os.path.join(os.path.dirname(_HERE), "csrc")])
+        if not os.path.exists(LIB_PATH):
             raise OrbfeError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                                        "g.build()'` (there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
