@@ -1,10 +1,35 @@
-// Device-vs-host check of several formulations of the FAST-9/16 arc score (debug tool).
+// Reproducer of the sm_100a miscompile found in round 1 (nvcc 12.9.86): on a B200 the plain-loop FAST score
+// `ref_best` and the `max(best, max(mn, -mx))` formulation (fc_arc_best of the first version, kept below as V1)
+// return wrong values on the DEVICE while V2 (negate once, outside the min/max network) and V4 (packed s16x2)
+// are correct; on the host all four agree.  Output on B200: "V1 bad=7785 V2 bad=0 ref-on-device bad=7769 V4 bad=0".
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include "../orb-slam3_byzyh_b200/csrc/fast_core.h"
 constexpr int P = 72, ROWS = 22, NT = 8192;
+
+// V1: the first formulation (doubling scheme, running max over max(mn9, -mx9)) -- wrong on the device.
+template <int PITCH>
+__host__ __device__ inline int fc_arc_best(const uint8_t* p) {
+    int d[16];
+    const int v = p[0];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = v - (int)p[FC_RING_DX(k) + FC_RING_DY(k) * PITCH];
+    int mn2[16], mx2[16], mn4[16], mx4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; k++) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
+        best = max(best, max(mn9, -mx9));
+    }
+    return best;
+}
 
 __host__ __device__ inline int ref_best(const uint8_t* p) {   // plain loops
     const int dx[16] = {0,1,2,3,3,3,2,1,0,-1,-2,-3,-3,-3,-2,-1};
