@@ -8,7 +8,7 @@
 // a pixel is a corner at threshold t iff best > t and its response is best-1.  The 700 tiny
 // per-cell cv::FAST calls of the reference therefore collapse into three streaming kernels:
 //   k_fast_score : one pass per pyramid level writing the margin max(best - subTh, 0) of every
-//                  pixel of the level's FAST domain as u16 (subTh = max(minThFAST, 1));
+//                  pixel of the level's FAST domain as u16 (subTh = max(min(iniThFAST, minThFAST), 1));
 //   k_fast_nms   : 3x3 non-max suppression with the reference's per-cell semantics (a neighbour
 //                  outside the pixel's own cell interior counts as 0) on 16-bit lanes, two pixels
 //                  per instruction; writes two 1-bit-per-pixel maps: survivors at minThFAST and
@@ -133,14 +133,15 @@ __device__ __forceinline__ void nms_finish_row(const NmsRaw& raw, int lane, cons
 
 // One output row: 3x3 strict maximum test of `cur` against its eight neighbours.
 __device__ __forceinline__ void nms_emit_row(const NmsRow& up, const NmsRow& cur, const NmsRow& dn, bool rowFirst,
-                                             bool rowLast, uint32_t ini2, unsigned grp, int nibShift, uint32_t nibMask, bool writer,
+                                             bool rowLast, uint32_t ini2, uint32_t min2, unsigned grp, int nibShift, uint32_t nibMask, bool writer,
                                              uint32_t* __restrict__ oMin, uint32_t* __restrict__ oIni) {
     const uint32_t uA = rowFirst ? 0u : up.fullA, uB = rowFirst ? 0u : up.fullB;
     const uint32_t dA = rowLast ? 0u : dn.fullA, dB = rowLast ? 0u : dn.fullB;
     const uint32_t nbA = fc_max3u(uA, dA, cur.lrA), nbB = fc_max3u(uB, dB, cur.lrB);
     // bit 15 of a lane of (x | 0x8000) - a is 0  <=>  a > x   (values < 2^15: no cross-lane borrow)
-    const uint32_t kA = (nbA | 0x80008000u) - cur.A, kB = (nbB | 0x80008000u) - cur.B;
+    uint32_t kA = (nbA | 0x80008000u) - cur.A, kB = (nbB | 0x80008000u) - cur.B;
     const uint32_t iA = (ini2 - cur.A) | kA, iB = (ini2 - cur.B) | kB;    // bit 15 set = NOT kept
+    if (min2 != 0x80008000u) { kA |= min2 - cur.A; kB |= min2 - cur.B; }  // warp-uniform, normally skipped
     // gather the four "not kept" flags (bits 15/31 of A, 15/31 of B) into a nibble, then invert
     const uint32_t fMin = __byte_perm(kA, kB, 0x7531) & 0x80808080u;   // bytes: A.b1, A.b3, B.b1, B.b3
     const uint32_t fIni = __byte_perm(iA, iB, 0x7531) & 0x80808080u;
@@ -202,6 +203,9 @@ k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict_
     const bool needL = lane == 0 && colIn && dx0 > 0, needR = lane == 31 && dx0 + 4 < dw;
     const bool writer = (lane & 7) == 0;
     const uint32_t ini2 = ((uint32_t)max(g.iniTh - g.subTh, 0) * 0x00010001u) | 0x80008000u;
+    // minThFAST above iniThFAST (unusual, but the reference just calls cv::FAST with it): the retry map
+    // then needs its own margin test as well; 0 in the usual case iniThFAST >= minThFAST
+    const uint32_t min2 = ((uint32_t)max(g.minTh - g.subTh, 0) * 0x00010001u) | 0x80008000u;
     const unsigned grp = 0xFFu << (lane & 24);
     const int nibShift = 4 * (lane & 3);
     const uint32_t nibMask = colIn ? 0xFu : 0u;            // lanes outside the domain add nothing
@@ -229,7 +233,8 @@ k_fast_nms(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restrict_
             row += pitch;                                                                                         \
             if (i + K + 1 < n) nxt = nms_fetch_row(row, colIn, needL, needR);                                     \
             nms_finish_row(got, lane, m, DN);                                                                     \
-            nms_emit_row(UP, CUR, DN, ry == 0, ry == hLast || dy0 + i + K == dh - 1, ini2, grp, nibShift, nibMask, \
+            nms_emit_row(UP, CUR, DN, ry == 0, ry == hLast || dy0 + i + K == dh - 1, ini2, min2, grp, nibShift,     \
+                         nibMask,                                                                                 \
                          writer, oMin, oIni);                                                                     \
             oMin += bmPitch; oIni += bmPitch;                                                                     \
             ry = ry == hLast ? 0 : ry + 1;                                                                        \

@@ -111,7 +111,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     unsigned slot = 0, tapOff = 0;
     int cell = 0, kpBase = 0, fastTile = 0, blurTile = 0, nmsTile = 0;
     unsigned bmWords = 0;
-    g.subTh = std::max(g.minTh, 1);
+    g.subTh = std::max(std::min(g.minTh, g.iniTh), 1);
     std::vector<OrbfeTap> taps;
     for (int l = 0; l < g.nlevels; l++) {
         OrbfeLevelGeom& L = g.lv[l];

@@ -53,7 +53,7 @@ struct OrbfeFrameGeom {
     int kpCapFrame;
     int fastTiles, blurTiles, nmsTiles;
     unsigned bmWordsPerFrame;
-    int subTh;                      // score map stores max(best - subTh, 0), subTh = max(minTh, 1)
+    int subTh;                      // score map stores max(best - subTh, 0), subTh = max(min(iniTh, minTh), 1)
     int ocShared;                   // dynamic shared bytes of the octree kernel (0 = tables in global)
     int ocMmax;
     OrbfeLevelGeom lv[ORBFE_MAX_LEVELS];

@@ -197,3 +197,12 @@ def test_large_nfeatures_octree_tables(orbfe, nf):
     quadtree tables (> 48 KB opt-in), 30000 go through the global-memory tables."""
     img = synth.noise_frame(480, 752, 12)
     _check_frame(orbfe.ORBextractor(nf), O.Extractor(nf), img, (0, 1000), stages=False)
+
+
+def test_unusual_thresholds_and_full_hd(orbfe):
+    """minThFAST above iniThFAST, a zero threshold (cv::FAST then needs response > 0), and a 1920x1080 frame."""
+    img = synth.synth_frame(480, 640, 31)
+    for (ini, mn) in [(7, 20), (20, 0), (0, 0), (255, 1), (12, 12)]:
+        _check_frame(orbfe.ORBextractor(800, 1.2, 8, ini, mn), O.Extractor(800, 1.2, 8, ini, mn), img, (0, 0))
+    big = synth.synth_frame(1080, 1920, 32)
+    _check_frame(orbfe.ORBextractor(4000), O.Extractor(4000), big, (0, 1000), stages=False)
