@@ -210,6 +210,20 @@ inline void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sx, double
 }
 inline float fastAtan2(float y, float x) { return cvp::fast_atan2(y, x); }
 
+// cv::norm(a, b, NORM_L1) on 8-bit single-channel views (reference src/Frame.cc:1284): sum |a-b|,
+// an exact integer in double.
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+inline double norm(const Mat& a, const Mat& b, int normType) {
+    assert(normType == NORM_L1 && a.rows == b.rows && a.cols == b.cols);
+    (void)normType;
+    long long s = 0;
+    for (int y = 0; y < a.rows; y++) {
+        const uchar *pa = a.ptr(y), *pb = b.ptr(y);
+        for (int x = 0; x < a.cols; x++) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+    }
+    return (double)s;
+}
+
 // Only named by the reference's dead ComputeKeyPointsOld (call commented out at
 // src/ORBextractor.cc:1580); never executed.
 struct KeyPointsFilter {

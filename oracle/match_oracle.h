@@ -2,7 +2,7 @@
 //
 // CPU restatement of the reference's Hamming-matching path.  The reference functions work on
 // Frame / MapPoint / KeyFrame object graphs (Eigen, Sophus, DBoW2 - none of which exist in
-// this image), so nothing here can be compiled verbatim; each function below follows the
+// this image), so their files cannot be compiled as a whole; each function below follows the
 // control flow of the cited lines on plain arrays marshalled at the boundary that
 // SURVEY.md section 8(b) defines (projected coordinates and per-point flags are inputs).
 //   ORBmatcher::DescriptorDistance            /root/reference/src/ORBmatcher.cc:2384-2404
@@ -14,8 +14,10 @@
 //   ORBmatcher::ComputeThreeMaxima            src/ORBmatcher.cc:2336-2378
 //   Frame::ComputeStereoMatches               src/Frame.cc:1102-1358
 //   Frame::ComputeStereoFishEyeMatches        src/Frame.cc:1530-1587 (kNN-2 + 0.7 ratio part)
-// Parity status: unpinned by the reference (it has no tests); pinned against cv2 4.13
-// BFMatcher for the brute-force part, see tests/test_oracle_cvprims.py.
+// Parity status: the reference has no tests for this path; PINNED against the reference's own function
+// bodies compiled verbatim into oracle/_ref/libref_orbmatcher.so (ref_build.sh, ref_slices.py, refshim/)
+// by tests/test_oracle_match_vs_ref.py -- all of the above except the fisheye kNN part, which is pinned
+// against cv2 4.13 BFMatcher (tests/test_oracle_cvprims.py).
 #pragma once
 #include <cstdint>
 #include <vector>

@@ -71,3 +71,147 @@ class RefExtractor:
         out = np.empty((max(len(xys), 8), 3), np.int32)
         n = lib().ref_octree(C.c_void_p(self.h), _p(xys), len(xys), minX, maxX, minY, maxY, N, _p(out), len(out))
         return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref/libref_orbmatcher.so: the reference's own matcher functions (function bodies cut out of
+# src/ORBmatcher.cc, src/Frame.cc, src/MapPoint.cc at build time and compiled verbatim against
+# oracle/refshim; see oracle/ref_build.sh, oracle/ref_slices.py, oracle/ref_match_driver.cpp).
+_MSO = os.path.join(_HERE, "_ref", "libref_orbmatcher.so")
+_MLIB = None
+
+
+def matcher_available():
+    if not os.path.exists(_MSO) and os.path.exists("/root/reference/src/ORBmatcher.cc"):
+        subprocess.call(["sh", os.path.join(_HERE, "ref_build.sh")])
+    return os.path.exists(_MSO)
+
+
+def mlib():
+    global _MLIB
+    if _MLIB is None:
+        if not matcher_available():
+            raise RuntimeError("oracle/_ref/libref_orbmatcher.so not built (needs /root/reference)")
+        _MLIB = C.CDLL(_MSO)
+        _MLIB.refm_frame_create.restype = C.c_void_p
+    return _MLIB
+
+
+def _f(x):
+    return C.c_float(float(x))
+
+
+def _opt(a, dt):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dt)
+    return a, _p(a)
+
+
+def set_bounds(bounds):
+    """bounds = (minX, minY, maxX, maxY): Frame's static image bounds and grid cell inverses (Frame.cc:303-305)."""
+    b = [np.float32(v) for v in bounds]
+    gw = np.float32(64) / np.float32(b[2] - b[0])
+    gh = np.float32(48) / np.float32(b[3] - b[1])
+    mlib().refm_set_bounds(_f(b[0]), _f(b[1]), _f(b[2]), _f(b[3]), _f(gw), _f(gh))
+
+
+class RefFrame:
+    """A reference Frame (shim class, reference member functions) built from plain arrays."""
+
+    def __init__(self, keys, desc, scale_factors, uright=None, right=None, mb=0.0, mbf=0.0, scale=1.2):
+        """right = (keysR, descR, l2r, r2l) makes it a fisheye stereo frame (Nleft != -1)."""
+        keys = np.ascontiguousarray(keys)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        ur, pur = _opt(uright, np.float32)
+        self.n = len(keys)
+        if right is not None:
+            kr = np.ascontiguousarray(right[0]); dr = np.ascontiguousarray(right[1], np.uint8)
+            l2r = np.ascontiguousarray(right[2], np.int32); r2l = np.ascontiguousarray(right[3], np.int32)
+            args = (_p(kr), len(kr), _p(dr), _p(l2r), _p(r2l))
+            self.n += len(kr)
+        else:
+            args = (None, -1, None, None, None)
+        self.h = mlib().refm_frame_create(_p(keys), len(keys), _p(desc), pur, *args, _p(sf), len(sf),
+                                          _f(np.log(np.float32(scale))), _f(mb), _f(mbf))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            mlib().refm_frame_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def set_pose(self, t):
+        mlib().refm_frame_pose(C.c_void_p(self.h), _f(t[0]), _f(t[1]), _f(t[2]))
+
+    def set_trl(self, t):
+        mlib().refm_frame_trl(C.c_void_p(self.h), _f(t[0]), _f(t[1]), _f(t[2]))
+
+    def set_mappoints(self, has, nobs=None, xyz=None, desc=None, outlier=None, bad=None, min_dist=None, max_dist=None):
+        keep = [_opt(has, np.uint8), _opt(nobs, np.int32), _opt(xyz, np.float32), _opt(desc, np.uint8),
+                _opt(outlier, np.uint8), _opt(bad, np.uint8), _opt(min_dist, np.float32), _opt(max_dist, np.float32)]
+        assert len(keep[0][0]) == self.n
+        mlib().refm_frame_mappoints(C.c_void_p(self.h), *[k[1] for k in keep])
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1, right=False):
+        out = np.empty(self.n + 1, np.int32)
+        n = mlib().refm_features_in_area(C.c_void_p(self.h), _f(x), _f(y), _f(r), int(min_level), int(max_level),
+                                         int(right), _p(out), len(out))
+        return out[:n].copy()
+
+    def predict_scale(self, max_distance, dist):
+        return mlib().refm_predict_scale(C.c_void_p(self.h), _f(max_distance), _f(dist))
+
+    def search_mappoints(self, mp, th, far_points, th_far, nnratio):
+        """mp: dict with in_view, in_view_r, depth, bad, nobs, proj_x, proj_y, proj_xr, proj_yr, level, level_r,
+        view_cos, view_cos_r, desc (missing right-camera entries = None)."""
+        order = [("in_view", np.uint8), ("in_view_r", np.uint8), ("depth", np.float32), ("bad", np.uint8),
+                 ("nobs", np.int32), ("proj_x", np.float32), ("proj_y", np.float32), ("proj_xr", np.float32),
+                 ("proj_yr", np.float32), ("level", np.int32), ("level_r", np.int32), ("view_cos", np.float32),
+                 ("view_cos_r", np.float32), ("desc", np.uint8)]
+        keep = [_opt(mp.get(k), dt) for k, dt in order]
+        slots = np.empty(self.n, np.int32)
+        n = mlib().refm_search_mappoints(C.c_void_p(self.h), len(keep[0][0]), *[k[1] for k in keep], _f(th),
+                                         int(far_points), _f(th_far), _f(nnratio), _p(slots))
+        return n, slots
+
+    def search_lastframe(self, last, th, mono, nnratio, check_ori):
+        slots = np.empty(self.n, np.int32)
+        n = mlib().refm_search_lastframe(C.c_void_p(self.h), C.c_void_p(last.h), _f(th), int(mono), _f(nnratio),
+                                         int(check_ori), _p(slots))
+        return n, slots
+
+    def search_keyframe(self, kf, already_found, th, orb_dist, nnratio, check_ori):
+        af, paf = _opt(already_found, np.uint8)
+        slots = np.empty(self.n, np.int32)
+        n = mlib().refm_search_keyframe(C.c_void_p(self.h), C.c_void_p(kf.h), paf, _f(th), int(orb_dist),
+                                        _f(nnratio), int(check_ori), _p(slots))
+        return n, slots
+
+
+def search_for_initialization(f1, f2, prev_matched, window_size, nnratio, check_ori):
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.empty(len(prev), np.int32)
+    n = mlib().refm_search_init(C.c_void_p(f1.h), C.c_void_p(f2.h), _p(prev), _p(m12), int(window_size),
+                                _f(nnratio), int(check_ori))
+    return n, m12, prev
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return mlib().refm_descriptor_distance(_p(a), _p(b))
+
+
+def stereo(img_l, img_r, mbf, mb, nfeatures=1000, scale=1.2, nlevels=8, ini=20, mn=7):
+    """Reference ORBextractor on both images + Frame::ComputeStereoMatches.
+    Returns keysL, descL, keysR, descR, uRight, depth."""
+    img_l = np.ascontiguousarray(img_l, np.uint8); img_r = np.ascontiguousarray(img_r, np.uint8)
+    cap = nfeatures + 64 * nlevels + 64
+    kl, kr = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    nr = C.c_int(0)
+    n = mlib().refm_stereo(_p(img_l), _p(img_r), img_l.shape[0], img_l.shape[1], nfeatures, _f(scale), nlevels, ini, mn,
+                           _f(mbf), _f(mb), _p(kl), _p(dl), _p(kr), _p(dr), cap, C.byref(nr), _p(ur), _p(dp))
+    assert n >= 0
+    return kl[:n].copy(), dl[:n].copy(), kr[:nr.value].copy(), dr[:nr.value].copy(), ur[:n].copy(), dp[:n].copy()

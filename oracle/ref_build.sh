@@ -18,3 +18,16 @@ ${CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
     "$REF/src/ORBextractor.cc" "$HERE/ref_driver.cpp" "$HERE/cvprims.cpp" \
     -o "$HERE/_ref/libref_orbextractor.so"
 echo "built $HERE/_ref/libref_orbextractor.so"
+
+# The reference's matcher functions (ORBmatcher::SearchByProjection x3, SearchForInitialization,
+# DescriptorDistance, Frame::GetFeaturesInArea / ComputeStereoMatches, MapPoint::PredictScale): their files
+# need Eigen/Sophus/DBoW2/g2o as a whole, so ref_slices.py cuts those function bodies out of the tree into a
+# temporary translation unit, compiled verbatim against oracle/refshim and deleted afterwards.
+TMP="$(mktemp -d)"
+trap 'rm -rf "$TMP"' EXIT
+python3 "$HERE/ref_slices.py" "$REF" "$TMP/ref_matcher_slices.cc"
+${CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
+    -I"$HERE/refshim" -I"$HERE/cvshim" -I"$REF/include" \
+    "$TMP/ref_matcher_slices.cc" "$REF/src/ORBextractor.cc" "$HERE/ref_match_driver.cpp" "$HERE/cvprims.cpp" \
+    -o "$HERE/_ref/libref_orbmatcher.so"
+echo "built $HERE/_ref/libref_orbmatcher.so"

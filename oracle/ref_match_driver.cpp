@@ -1,0 +1,248 @@
+// oracle/ref_match_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+// C entry points around the reference's OWN matcher functions: ORBmatcher::SearchByProjection (three
+// Frame overloads), ORBmatcher::SearchForInitialization, ORBmatcher::DescriptorDistance,
+// Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid, Frame::ComputeStereoMatches and
+// MapPoint::PredictScale.  Their bodies are cut out of /root/reference/src at build time by
+// oracle/ref_slices.py and compiled verbatim against oracle/refshim + oracle/cvshim (ref_build.sh);
+// this file only builds the Frame / MapPoint objects they walk from plain arrays and flattens the result.
+// Used by tests/test_oracle_match_vs_ref.py to pin oracle/match_oracle.cpp.
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "refshim.h"
+#include "ORBmatcher.h"
+
+using namespace ORB_SLAM3;
+
+float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0;
+float Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0;
+
+namespace {
+
+struct RefFrame {
+    Frame F;
+    GeometricCamera cam;
+    std::vector<std::unique_ptr<MapPoint>> own;   // map points held by F.mvpMapPoints (slot order, may be null)
+    std::vector<MapPoint*> initial;               // F.mvpMapPoints before a search
+    KeyFrame kf;                                  // keyframe view of the same data (relocalisation overload)
+    std::unique_ptr<ORBextractor> exL, exR;
+};
+
+class Matcher : public ORBmatcher {
+   public:
+    using ORBmatcher::ORBmatcher;
+};
+
+cv::Mat wrap_desc(const uint8_t* d, int n) {
+    cv::Mat m(n > 0 ? n : 1, 32, CV_8UC1);
+    if (n > 0) memcpy(m.data, d, (size_t)n * 32);
+    return m;
+}
+
+// slot_out[i]: index (into `cands`) of the map point now held by slot i; -2 = the slot still holds what it
+// held before the search; -1 = the slot is now NULL but was not before.
+void flatten(RefFrame* rf, const std::vector<MapPoint*>& cands, int* slot_out) {
+    std::map<MapPoint*, int> index;
+    for (size_t i = 0; i < cands.size(); i++)
+        if (cands[i] && !index.count(cands[i])) index[cands[i]] = (int)i;
+    for (int i = 0; i < rf->F.N; i++) {
+        MapPoint* p = rf->F.mvpMapPoints[i];
+        if (p == rf->initial[i]) slot_out[i] = -2;
+        else if (!p) slot_out[i] = -1;
+        else slot_out[i] = index.count(p) ? index[p] : -3;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+void refm_set_bounds(float minX, float minY, float maxX, float maxY, float gwInv, float ghInv) {
+    Frame::mnMinX = minX; Frame::mnMinY = minY; Frame::mnMaxX = maxX; Frame::mnMaxY = maxY;
+    Frame::mfGridElementWidthInv = gwInv; Frame::mfGridElementHeightInv = ghInv;
+}
+
+// keys/desc: the left (or only) view; keysR/descR with nR >= 0: the right view of a fisheye stereo frame
+// (Frame::Nleft != -1).  uRight may be null.  The grid is assigned with the reference's own code.
+void* refm_frame_create(const cv::KeyPoint* keys, int n, const uint8_t* desc, const float* uRight,
+                        const cv::KeyPoint* keysR, int nR, const uint8_t* descR, const int* l2r, const int* r2l,
+                        const float* scaleFactors, int nlevels, float logScaleFactor, float mb, float mbf) {
+    RefFrame* rf = new RefFrame();
+    Frame& F = rf->F;
+    F.mpCamera = &rf->cam;
+    F.mvKeys.assign(keys, keys + n);
+    F.mvKeysUn = F.mvKeys;
+    F.mb = mb; F.mbf = mbf;
+    F.mnScaleLevels = nlevels;
+    F.mfLogScaleFactor = logScaleFactor;
+    F.mvScaleFactors.assign(scaleFactors, scaleFactors + nlevels);
+    F.mvInvScaleFactors.resize(nlevels);
+    for (int i = 0; i < nlevels; i++) F.mvInvScaleFactors[i] = 1.0f / scaleFactors[i];
+    if (nR >= 0) {
+        F.Nleft = n; F.Nright = nR; F.N = n + nR;
+        F.mvKeysRight.assign(keysR, keysR + nR);
+        std::vector<uint8_t> all((size_t)(n + nR) * 32 + 32);
+        if (n) memcpy(all.data(), desc, (size_t)n * 32);
+        if (nR) memcpy(all.data() + (size_t)n * 32, descR, (size_t)nR * 32);
+        F.mDescriptors = wrap_desc(all.data(), n + nR);
+        F.mvLeftToRightMatch.assign(l2r, l2r + n);
+        F.mvRightToLeftMatch.assign(r2l, r2l + nR);
+        F.mvuRight.assign(F.N, -1.f);
+    } else {
+        F.N = n;
+        F.mDescriptors = wrap_desc(desc, n);
+        if (uRight) F.mvuRight.assign(uRight, uRight + n); else F.mvuRight.assign(n, -1.f);
+    }
+    F.mvDepth.assign(F.N, -1.f);
+    F.mvpMapPoints.assign(F.N, nullptr);
+    F.mvbOutlier.assign(F.N, false);
+    rf->own.resize(F.N);
+    F.AssignFeaturesToGrid();
+    rf->initial = F.mvpMapPoints;
+    return rf;
+}
+void refm_frame_destroy(void* h) { delete (RefFrame*)h; }
+void refm_frame_pose(void* h, float tx, float ty, float tz) { ((RefFrame*)h)->F.mTcw = Sophus::SE3f(Eigen::Vector3f(tx, ty, tz)); }
+void refm_frame_trl(void* h, float tx, float ty, float tz) { ((RefFrame*)h)->F.mTrl = Sophus::SE3f(Eigen::Vector3f(tx, ty, tz)); }
+
+// Per slot: has[i] != 0 -> the slot holds a map point with nobs[i] observations, world position xyz[3i..],
+// descriptor desc[32i..], distance range [minDist, maxDist] (MapPoint::mfMinDistance / mfMaxDistance).
+void refm_frame_mappoints(void* h, const uint8_t* has, const int* nobs, const float* xyz, const uint8_t* desc,
+                          const uint8_t* outlier, const uint8_t* bad, const float* minDist, const float* maxDist) {
+    RefFrame* rf = (RefFrame*)h;
+    Frame& F = rf->F;
+    for (int i = 0; i < F.N; i++) {
+        rf->own[i].reset();
+        F.mvpMapPoints[i] = nullptr;
+        if (outlier) F.mvbOutlier[i] = outlier[i] != 0;
+        if (!has[i]) continue;
+        MapPoint* p = new MapPoint();
+        rf->own[i].reset(p);
+        p->nObs = nobs ? nobs[i] : 1;
+        if (xyz) p->pos = Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        p->desc = wrap_desc(desc ? desc + 32 * (size_t)i : nullptr, desc ? 1 : 0);
+        p->bad = bad ? bad[i] != 0 : false;
+        if (minDist) p->mfMinDistance = minDist[i];
+        if (maxDist) p->mfMaxDistance = maxDist[i];
+        F.mvpMapPoints[i] = p;
+    }
+    rf->initial = F.mvpMapPoints;
+}
+
+int refm_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    cv::Mat ma = wrap_desc(a, 1), mb = wrap_desc(b, 1);
+    return ORBmatcher::DescriptorDistance(ma, mb);
+}
+
+int refm_features_in_area(void* h, float x, float y, float r, int minLevel, int maxLevel, int bRight, int* out, int cap) {
+    std::vector<size_t> v = ((RefFrame*)h)->F.GetFeaturesInArea(x, y, r, minLevel, maxLevel, bRight != 0);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
+    return (int)v.size();
+}
+
+int refm_predict_scale(void* h, float maxDistance, float dist) {
+    MapPoint p;
+    p.mfMaxDistance = maxDistance;
+    return p.PredictScale(dist, &((RefFrame*)h)->F);
+}
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+int refm_search_mappoints(void* h, int m, const uint8_t* inView, const uint8_t* inViewR, const float* depth,
+                          const uint8_t* bad, const int* nobs, const float* projX, const float* projY,
+                          const float* projXR, const float* projYR, const int* level, const int* levelR,
+                          const float* viewCos, const float* viewCosR, const uint8_t* desc, float th, int bFar,
+                          float thFar, float nnratio, int* slot_out) {
+    RefFrame* rf = (RefFrame*)h;
+    std::vector<std::unique_ptr<MapPoint>> pts(m);
+    std::vector<MapPoint*> vp(m);
+    for (int i = 0; i < m; i++) {
+        MapPoint* p = new MapPoint();
+        pts[i].reset(p); vp[i] = p;
+        p->mbTrackInView = inView[i] != 0;
+        p->mbTrackInViewR = inViewR ? inViewR[i] != 0 : false;
+        p->mTrackDepth = depth ? depth[i] : 1.f;
+        p->bad = bad ? bad[i] != 0 : false;
+        p->nObs = nobs ? nobs[i] : 1;
+        p->mTrackProjX = projX[i]; p->mTrackProjY = projY[i];
+        p->mTrackProjXR = projXR ? projXR[i] : 0.f; p->mTrackProjYR = projYR ? projYR[i] : 0.f;
+        p->mnTrackScaleLevel = level[i]; p->mnTrackScaleLevelR = levelR ? levelR[i] : -1;
+        p->mTrackViewCos = viewCos[i]; p->mTrackViewCosR = viewCosR ? viewCosR[i] : 1.f;
+        p->desc = wrap_desc(desc + 32 * (size_t)i, 1);
+    }
+    Matcher matcher(nnratio, true);
+    const int n = matcher.SearchByProjection(rf->F, vp, th, bFar != 0, thFar);
+    flatten(rf, vp, slot_out);
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+int refm_search_lastframe(void* cur, void* last, float th, int bMono, float nnratio, int checkOri, int* slot_out) {
+    RefFrame *rc = (RefFrame*)cur, *rl = (RefFrame*)last;
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByProjection(rc->F, rl->F, th, bMono != 0);
+    flatten(rc, rl->F.mvpMapPoints, slot_out);
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist)
+int refm_search_keyframe(void* cur, void* kfFrame, const uint8_t* alreadyFound, float th, int ORBdist,
+                         float nnratio, int checkOri, int* slot_out) {
+    RefFrame *rc = (RefFrame*)cur, *rk = (RefFrame*)kfFrame;
+    rk->kf.mvpMapPoints = rk->F.mvpMapPoints;
+    rk->kf.mvKeysUn = rk->F.mvKeysUn;
+    std::set<MapPoint*> found;
+    for (int i = 0; i < rk->F.N; i++)
+        if (alreadyFound && alreadyFound[i] && rk->F.mvpMapPoints[i]) found.insert(rk->F.mvpMapPoints[i]);
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByProjection(rc->F, &rk->kf, found, th, ORBdist);
+    flatten(rc, rk->F.mvpMapPoints, slot_out);
+    return n;
+}
+
+// ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+int refm_search_init(void* f1, void* f2, float* prevMatched, int* matches12, int windowSize, float nnratio, int checkOri) {
+    RefFrame *r1 = (RefFrame*)f1, *r2 = (RefFrame*)f2;
+    const int n1 = (int)r1->F.mvKeysUn.size();
+    std::vector<cv::Point2f> prev(n1);
+    for (int i = 0; i < n1; i++) prev[i] = cv::Point2f(prevMatched[2 * i], prevMatched[2 * i + 1]);
+    std::vector<int> m12;
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchForInitialization(r1->F, r2->F, prev, m12, windowSize);
+    for (int i = 0; i < n1; i++) { matches12[i] = m12[i]; prevMatched[2 * i] = prev[i].x; prevMatched[2 * i + 1] = prev[i].y; }
+    return n;
+}
+
+// Frame::ComputeStereoMatches() on a rectified pair: both images go through the reference's own
+// ORBextractor (src/ORBextractor.cc, compiled into this library too).  Returns N (left keypoints);
+// keys/desc of both views are written out so that the restatement can be fed the same inputs.
+int refm_stereo(const uint8_t* imgL, const uint8_t* imgR, int rows, int cols, int nfeatures, float scaleFactor,
+                int nlevels, int iniTh, int minTh, float mbf, float mb, cv::KeyPoint* keysL, uint8_t* descL,
+                cv::KeyPoint* keysR, uint8_t* descR, int cap, int* nR_out, float* uRight, float* depth) {
+    RefFrame rf;
+    Frame& F = rf.F;
+    rf.exL.reset(new ORBextractor(nfeatures, scaleFactor, nlevels, iniTh, minTh));
+    rf.exR.reset(new ORBextractor(nfeatures, scaleFactor, nlevels, iniTh, minTh));
+    F.mpORBextractorLeft = rf.exL.get(); F.mpORBextractorRight = rf.exR.get();
+    cv::Mat L(rows, cols, CV_8UC1, (void*)imgL, (size_t)cols), R(rows, cols, CV_8UC1, (void*)imgR, (size_t)cols);
+    std::vector<int> lap = {0, 0};
+    (*rf.exL)(L, cv::Mat(), F.mvKeys, F.mDescriptors, lap);
+    (*rf.exR)(R, cv::Mat(), F.mvKeysRight, F.mDescriptorsRight, lap);
+    F.N = (int)F.mvKeys.size();
+    F.mvScaleFactors = rf.exL->GetScaleFactors();
+    F.mvInvScaleFactors = rf.exL->GetInverseScaleFactors();
+    F.mbf = mbf; F.mb = mb;
+    const int nR = (int)F.mvKeysRight.size();
+    *nR_out = nR;
+    if (F.N > cap || nR > cap) return -1;
+    F.ComputeStereoMatches();
+    for (int i = 0; i < F.N; i++) {
+        keysL[i] = F.mvKeys[i]; memcpy(descL + 32 * (size_t)i, F.mDescriptors.ptr(i), 32);
+        uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i];
+    }
+    for (int i = 0; i < nR; i++) { keysR[i] = F.mvKeysRight[i]; memcpy(descR + 32 * (size_t)i, F.mDescriptorsRight.ptr(i), 32); }
+    return F.N;
+}
+
+}  // extern "C"

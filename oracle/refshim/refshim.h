@@ -1,0 +1,147 @@
+// oracle/refshim/refshim.h -- TEST INFRASTRUCTURE ONLY.
+// Minimal stand-ins for the classes the reference's matcher functions touch (Frame, MapPoint, KeyFrame,
+// Eigen::Vector{2,3}f, Sophus::SE3f, GeometricCamera), so that the reference's OWN function bodies --
+// sliced at build time out of /root/reference/src/{ORBmatcher,Frame,MapPoint}.cc by oracle/ref_slices.py,
+// never copied into this repo -- compile without Eigen/Sophus/DBoW2/g2o, which the image does not have.
+// Only the data members and accessors those bodies read are declared (names as in the reference's
+// include/Frame.h, include/MapPoint.h, include/KeyFrame.h); everything else of the reference is absent.
+// Poses are translation-only and the camera is a plain pinhole: the tests pin the MATCHING logic
+// (windows, level filters, claims, ratio tests, rotation histogram, stereo partners), not the geometry
+// the caller keeps on the host.
+#pragma once
+// The reference's ORBmatcher.h pulls "MapPoint.h", "KeyFrame.h" and "Frame.h" with quote includes, which
+// resolve next to it before any -I path: pre-define their include guards so the real ones are no-ops.
+#define MAPPOINT_H
+#define KEYFRAME_H
+#define FRAME_H
+#include <cmath>
+#include <mutex>
+#include <set>
+#include <vector>
+
+#include <opencv2/core/core.hpp>
+
+#include "ORBextractor.h"
+
+using namespace std;  // the reference's headers rely on this leaking from its own includes
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+namespace Eigen {
+struct Vector3f {
+    float v[3];
+    Vector3f() : v{0, 0, 0} {}
+    Vector3f(float x, float y, float z) : v{x, y, z} {}
+    float& operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+    Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+    Vector3f operator+(const Vector3f& o) const { return Vector3f(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+    float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+};
+struct Vector2f {
+    float v[2];
+    Vector2f() : v{0, 0} {}
+    Vector2f(float x, float y) : v{x, y} {}
+    float& operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
+};
+}  // namespace Eigen
+
+namespace Sophus {
+// translation-only rigid transform
+template <class T>
+struct SE3 {
+    Eigen::Vector3f t;
+    SE3() {}
+    explicit SE3(const Eigen::Vector3f& t_) : t(t_) {}
+    SE3 inverse() const { return SE3(Eigen::Vector3f(-t(0), -t(1), -t(2))); }
+    Eigen::Vector3f translation() const { return t; }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p + t; }
+};
+typedef SE3<float> SE3f;
+template <class T>
+struct Sim3 {};
+typedef Sim3<float> Sim3f;
+}  // namespace Sophus
+
+namespace ORB_SLAM3 {
+
+class Frame;
+class KeyFrame;
+
+class GeometricCamera {
+   public:
+    float fx = 1, fy = 1, cx = 0, cy = 0;
+    Eigen::Vector2f project(const Eigen::Vector3f& p) const {
+        return Eigen::Vector2f(fx * p(0) / p(2) + cx, fy * p(1) / p(2) + cy);
+    }
+};
+
+class MapPoint {
+   public:
+    // members the matchers read directly (include/MapPoint.h)
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+    bool mbTrackInView = false, mbTrackInViewR = false;
+    int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
+    float mTrackViewCos = 1, mTrackViewCosR = 1;
+    // accessors
+    bool isBad() { return bad; }
+    int Observations() { return nObs; }
+    cv::Mat GetDescriptor() { return desc.clone(); }
+    Eigen::Vector3f GetWorldPos() { return pos; }
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+    int PredictScale(const float& currentDist, Frame* pF);  // body sliced from src/MapPoint.cc
+    // state
+    std::mutex mMutexPos;
+    float mfMinDistance = 0, mfMaxDistance = 0;
+    bool bad = false;
+    int nObs = 1;
+    cv::Mat desc;
+    Eigen::Vector3f pos;
+};
+
+class KeyFrame {
+   public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<cv::KeyPoint> mvKeysUn;
+};
+
+class Frame {
+   public:
+    // sliced from src/Frame.cc
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                     const int maxLevel = -1, const bool bRight = false) const;
+    void ComputeStereoMatches();
+    void AssignFeaturesToGrid();
+
+    Sophus::SE3f GetPose() const { return mTcw; }
+    Sophus::SE3f GetRelativePoseTrl() { return mTrl; }
+
+    ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+    GeometricCamera* mpCamera = nullptr;
+    float mbf = 0, mb = 0;
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+    std::vector<float> mvuRight, mvDepth;
+    cv::Mat mDescriptors, mDescriptorsRight;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+    int mnScaleLevels = 0;
+    float mfScaleFactor = 0, mfLogScaleFactor = 0;
+    vector<float> mvScaleFactors, mvInvScaleFactors;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    int Nleft = -1, Nright = -1;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+    std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+
+    Sophus::SE3f mTcw, mTrl;
+};
+
+}  // namespace ORB_SLAM3
