@@ -222,6 +222,44 @@ int orbfe_search_for_initialization(const OrbfeFrameView* f1, const OrbfeFrameVi
                                     float* prev_matched, int window_size, float nnratio,
                                     int check_orientation, int32_t* matches12, int device);
 
+/* Keyframe-side searches.  ORBmatcher::Fuse (include/ORBmatcher.h:83,86;
+ * src/ORBmatcher.cc:1326-1534, 1536-1688), SearchBySim3 (:1690-1940) and the Sim3 SearchByProjection
+ * overloads (:496-733) run, per projected map point, KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:843-892)
+ * + the `[nPredictedLevel-1, nPredictedLevel]` level filter + a strict-`<` Hamming argmin, with no state
+ * carried from point to point.  `kf` = the keyframe's mvKeysUn (mvKeys / mvKeysRight for fisheye), mvuRight,
+ * descriptor rows and grid bounds (KeyFrame::mnMinX.. are the frame's bounds truncated to int);
+ * `pts` as for orbfe_search_by_projection (angle / blocks unused; min_level = nPredictedLevel-1,
+ * max_level = nPredictedLevel).  ORBFE_GATE_FUSE adds Fuse's reprojection gate (:1436-1461): chi2 7.8
+ * on (ex,ey,er) when the keypoint has a stereo coordinate, 5.99 on (ex,ey) otherwise, scaled by
+ * mvInvLevelSigma2[octave]; it reads pts->ur (= uv(0) - bf*invz).
+ * best_idx[j] = keypoint index, or -1 when nothing is within th_accept (TH_LOW for Fuse, TH_HIGH for
+ * SearchBySim3); best_dist[j] (may be NULL) = smallest distance (256 = no candidate).  Returns the number
+ * of points with a match.  The pointer-graph updates (AddObservation / Replace, vpReplacePoint) stay with
+ * the caller: host/ORBmatcher_b200.h shows them.  The Sim3 SearchByProjection overloads additionally skip
+ * keypoints already in vpMatched: that is orbfe_search_by_projection with ORBFE_SEARCH_KEYFRAME,
+ * claimed = (vpMatched[i] != NULL), th_accept = floor(TH_LOW * ratioHamming), check_orientation = 0. */
+#define ORBFE_GATE_NONE 0
+#define ORBFE_GATE_FUSE 1
+typedef struct OrbfeWindowParams {
+    int32_t th_accept;
+    int32_t gate;
+    const float* inv_level_sigma2; /* [n_levels], ORBFE_GATE_FUSE only */
+    int32_t n_levels;
+} OrbfeWindowParams;
+int orbfe_search_window(const OrbfeFrameView* kf, const OrbfeProjPoints* pts,
+                        const OrbfeWindowParams* prm, int32_t* best_idx, int32_t* best_dist,
+                        int device);
+
+/* int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12,
+ * const Sophus::Sim3f& S12, const float th)   include/ORBmatcher.h:80, src/ORBmatcher.cc:1690-1940.
+ * pts12: one entry per KF1 slot = its map point transformed by S21 and projected into KF2 (valid = the
+ * slot has a good, not yet matched point that passes :1736-1765); pts21: the reverse (:1826-1862).
+ * match12[i1] = KF2 keypoint index when both directions agree (:1922-1937), else -1; the caller stores
+ * vpMatches12[i1] = vpMapPoints2[match12[i1]].  Returns nFound. */
+int orbfe_search_by_sim3(const OrbfeFrameView* kf1, const OrbfeFrameView* kf2,
+                         const OrbfeProjPoints* pts12, const OrbfeProjPoints* pts21, int th_accept,
+                         int32_t* match12, int device);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

@@ -253,6 +253,64 @@ int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, c
     return nmatches;
 }
 
+// ORBmatcher.cc:1409-1478 (Fuse), :1592-1616 (Fuse, Sim3), :1755-1780 / :1853-1878 (SearchBySim3),
+// :552-581 (SearchByProjection, Sim3; without its vpMatched skip, which is search_by_projection mode 2).
+void search_window(const FrameView& KF, const std::vector<ProjPoint>& pts, const uint8_t* pdesc,
+                   const WindowParams& prm, int* best_idx, int* best_dist) {
+    for (size_t j = 0; j < pts.size(); j++) {
+        const ProjPoint& p = pts[j];
+        best_idx[j] = -1;
+        best_dist[j] = 256;
+        if (!p.valid) continue;
+        // KeyFrame::GetFeaturesInArea has no level arguments (KeyFrame.cc:843): all levels, then the filter
+        const std::vector<int> vIndices = KF.features_in_area(p.u, p.v, p.radius, -1, -1);
+        if (vIndices.empty()) continue;
+        const uint8_t* dMP = pdesc + 32 * j;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            const OrbKp& kp = KF.keys[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < p.minLevel || kpLevel > p.maxLevel) continue;
+            if (prm.fuseGate) {
+                const float ex = p.u - kp.x;
+                const float ey = p.v - kp.y;
+                if (KF.uright && KF.uright[idx] >= 0) {
+                    const float er = p.ur - KF.uright[idx];
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * prm.invLevelSigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * prm.invLevelSigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(dMP, KF.desc + 32 * (size_t)idx);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        best_dist[j] = bestDist;
+        if (bestDist <= prm.thAccept) best_idx[j] = bestIdx;
+    }
+}
+
+int search_by_sim3(const FrameView& KF1, const FrameView& KF2, const std::vector<ProjPoint>& pts12,
+                   const uint8_t* desc1, const std::vector<ProjPoint>& pts21, const uint8_t* desc2,
+                   int thAccept, int* match12) {
+    const int N1 = (int)pts12.size(), N2 = (int)pts21.size();
+    std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1), d1(N1), d2(N2);
+    const WindowParams wp{thAccept, 0, nullptr, 0};
+    search_window(KF2, pts12, desc1, wp, vnMatch1.data(), d1.data());  // :1729-1812
+    search_window(KF1, pts21, desc2, wp, vnMatch2.data(), d2.data());  // :1826-1909
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {  // :1922-1937
+        match12[i1] = -1;
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = vnMatch2[idx2];
+            if (idx1 == i1) { match12[i1] = idx2; nFound++; }
+        }
+    }
+    return nFound;
+}
+
 // reference src/ORBmatcher.cc:735-891
 int search_for_initialization(const FrameView& F1, FrameView& F2, float* vbPrevMatched, int windowSize,
                               float mfNNratio, bool mbCheckOrientation, int* vnMatches12) {

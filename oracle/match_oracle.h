@@ -90,6 +90,31 @@ int search_by_projection_fisheye(FrameView& FL, FrameView& FR, const int* l2r, c
 int search_for_initialization(const FrameView& F1, FrameView& F2, float* prevMatched, int windowSize,
                               float nnratio, bool checkOrientation, int* matches12);
 
+// ---- keyframe-side searches --------------------------------------------------
+// The inner loop shared by ORBmatcher::Fuse (src/ORBmatcher.cc:1326-1534 and :1536-1688),
+// SearchBySim3 (:1690-1940) and the Sim3 SearchByProjection overloads (:496-733): KeyFrame::
+// GetFeaturesInArea (src/KeyFrame.cc:843-892, same cells and order as Frame's) followed by the
+// `kpLevel < nPredictedLevel-1 || kpLevel > nPredictedLevel` filter, optionally Fuse's reprojection
+// gate (:1436-1461: chi2 7.8 with a stereo coordinate, 5.99 without, on e2 * mvInvLevelSigma2[level]),
+// and a strict-`<` Hamming argmin.  No state is carried from one point to the next.
+// best_idx[j] = keypoint index or -1 (none within thAccept), best_dist[j] = best distance (256 = none).
+struct WindowParams {
+    int thAccept;                   // TH_LOW (Fuse), TH_HIGH (SearchBySim3)
+    int fuseGate;                   // 1 = apply Fuse's chi2 gate
+    const float* invLevelSigma2;    // KeyFrame::mvInvLevelSigma2 (gate only)
+    int nlevels;
+};
+void search_window(const FrameView& KF, const std::vector<ProjPoint>& pts, const uint8_t* pdesc,
+                   const WindowParams& prm, int* best_idx, int* best_dist);
+
+// ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1690-1940) after the caller's projections: pts12[i1] =
+// map point of KF1 slot i1 projected into KF2 (valid = has a good, not yet matched point that passes
+// the depth / image / distance checks), pts21 likewise; desc1 / desc2 = GetDescriptor() of those points.
+// match12[i1] = KF2 keypoint index when both directions agree (:1925-1937), else -1.  Returns nFound.
+int search_by_sim3(const FrameView& KF1, const FrameView& KF2, const std::vector<ProjPoint>& pts12,
+                   const uint8_t* desc1, const std::vector<ProjPoint>& pts21, const uint8_t* desc2,
+                   int thAccept, int* match12);
+
 // Frame::ComputeStereoMatches on two extractor pyramids.
 struct PyrLevelView {
     const uint8_t* roi;

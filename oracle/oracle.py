@@ -300,3 +300,36 @@ def search_for_initialization(keys1, desc1, keys2, desc2, bounds, prev_matched, 
     n = lib().oracle_search_for_initialization(C.byref(f1), C.byref(f2), _p(prev), int(window_size), C.c_float(nnratio),
                                                int(check_orientation), _p(m12))
     return n, m12, prev
+
+
+def search_window(keys, desc, uright, bounds, pts, th_accept, fuse_gate=False, inv_level_sigma2=None):
+    """Stateless keyframe-side window search (Fuse x2, SearchBySim3, Sim3 SearchByProjection inner loop)."""
+    keep = []
+    fv = make_frame_view(keys, desc, uright, bounds, keep)
+    full = dict(pts)
+    m = len(pts["u"])
+    full.setdefault("ur", np.zeros(m, np.float32))
+    full.setdefault("angle", np.zeros(m, np.float32))
+    full.setdefault("blocks", np.ones(m, np.uint8))
+    pp = make_proj_points(full, keep)
+    inv = np.ascontiguousarray(inv_level_sigma2 if inv_level_sigma2 is not None else np.zeros(1), np.float32)
+    bi, bd = np.empty(m, np.int32), np.empty(m, np.int32)
+    lib().oracle_search_window(C.byref(fv), C.byref(pp), int(th_accept), int(fuse_gate), _p(inv), len(inv), _p(bi), _p(bd))
+    return bi, bd
+
+
+def search_by_sim3(keys1, desc1, keys2, desc2, bounds, pts12, pts21, th_accept=100):
+    keep = []
+    f1 = make_frame_view(keys1, desc1, None, bounds, keep)
+    f2 = make_frame_view(keys2, desc2, None, bounds, keep)
+    pps = []
+    for pts in (pts12, pts21):
+        full = dict(pts)
+        m = len(pts["u"])
+        for k, dt in (("ur", np.float32), ("angle", np.float32)):
+            full.setdefault(k, np.zeros(m, dt))
+        full.setdefault("blocks", np.ones(m, np.uint8))
+        pps.append(make_proj_points(full, keep))
+    m12 = np.empty(len(keys1), np.int32)
+    n = lib().oracle_search_by_sim3(C.byref(f1), C.byref(f2), C.byref(pps[0]), C.byref(pps[1]), int(th_accept), _p(m12))
+    return n, m12

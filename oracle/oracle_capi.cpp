@@ -181,6 +181,25 @@ int oracle_search_for_initialization(const OrbfeFrameView* f1, const OrbfeFrameV
     return match_oracle::search_for_initialization(F1, F2, prev, windowSize, nnratio, checkOri != 0, matches12);
 }
 
+void oracle_search_window(const OrbfeFrameView* kf, const OrbfeProjPoints* pp, int thAccept, int fuseGate,
+                          const float* invLevelSigma2, int nlevels, int32_t* best_idx, int32_t* best_dist) {
+    match_oracle::FrameView F;
+    fill_view(F, kf);
+    std::vector<match_oracle::ProjPoint> pts = fill_pts(pp, pp);
+    for (int j = 0; j < pp->m; j++) pts[j].ur = pp->ur ? pp->ur[j] : 0.f;
+    const match_oracle::WindowParams wp{thAccept, fuseGate, invLevelSigma2, nlevels};
+    match_oracle::search_window(F, pts, pp->desc, wp, best_idx, best_dist);
+}
+
+int oracle_search_by_sim3(const OrbfeFrameView* kf1, const OrbfeFrameView* kf2, const OrbfeProjPoints* p12,
+                          const OrbfeProjPoints* p21, int thAccept, int32_t* match12) {
+    match_oracle::FrameView F1, F2;
+    fill_view(F1, kf1);
+    fill_view(F2, kf2);
+    std::vector<match_oracle::ProjPoint> a = fill_pts(p12, p12), b = fill_pts(p21, p21);
+    return match_oracle::search_by_sim3(F1, F2, a, p12->desc, b, p21->desc, thAccept, match12);
+}
+
 // Grid query tap: indices returned by GetFeaturesInArea, in the reference's order.
 int oracle_features_in_area(const OrbfeFrameView* fv, float x, float y, float r, int minLevel,
                             int maxLevel, int32_t* out, int cap) {

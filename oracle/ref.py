@@ -215,3 +215,73 @@ def stereo(img_l, img_r, mbf, mb, nfeatures=1000, scale=1.2, nlevels=8, ini=20, 
                            _f(mbf), _f(mb), _p(kl), _p(dl), _p(kr), _p(dr), cap, C.byref(nr), _p(ur), _p(dp))
     assert n >= 0
     return kl[:n].copy(), dl[:n].copy(), kr[:nr.value].copy(), dr[:nr.value].copy(), ur[:n].copy(), dp[:n].copy()
+
+
+# ---- keyframe-side searches (Fuse x2, SearchBySim3, Sim3 SearchByProjection) ----------------------------
+def _kf_points_args(P, m, with_has=False, with_inkf=False, with_nobs=False):
+    """P: dict of per-candidate arrays (has, bad, in_kf, xyz, normal, min_dist, max_dist, nobs, desc)."""
+    keep = []
+
+    def a(name, dt):
+        arr, p = _opt(P.get(name), dt)
+        keep.append(arr)
+        return p
+    args = []
+    if with_has:
+        args.append(a("has", np.uint8))
+    args.append(a("bad", np.uint8))
+    if with_inkf:
+        args.append(a("in_kf", np.uint8))
+    args += [a("xyz", np.float32), a("normal", np.float32), a("min_dist", np.float32), a("max_dist", np.float32)]
+    if with_nobs:
+        args.append(a("nobs", np.int32))
+    args.append(a("desc", np.uint8))
+    return args, keep
+
+
+def set_camera(frame, fx, fy, cx, cy):
+    mlib().refm_frame_camera(C.c_void_p(frame.h), _f(fx), _f(fy), _f(cx), _f(cy))
+
+
+def kf_predict_scale(frame, max_distance, dist):
+    return mlib().refm_kf_predict_scale(C.c_void_p(frame.h), _f(max_distance), _f(dist))
+
+
+def fuse(kf, P, th):
+    m = len(P["xyz"])
+    args, keep = _kf_points_args(P, m, with_has=True, with_inkf=True, with_nobs=True)
+    cap = 4 * m + 16
+    actions = np.zeros((cap, 3), np.int32)
+    na = C.c_int(0)
+    n = mlib().refm_fuse(C.c_void_p(kf.h), m, *args, _f(th), _p(actions), cap, C.byref(na))
+    return n, actions[:na.value].copy()
+
+
+def fuse_sim3(kf, scw, P, th):
+    m = len(P["xyz"])
+    args, keep = _kf_points_args(P, m)
+    cap = 4 * m + 16
+    actions = np.zeros((cap, 3), np.int32)
+    na = C.c_int(0)
+    repl = np.empty(m, np.int32)
+    n = mlib().refm_fuse_sim3(C.c_void_p(kf.h), _f(scw[0]), _f(scw[1]), _f(scw[2]), _f(scw[3]), m, *args, _f(th),
+                              _p(repl), _p(actions), cap, C.byref(na))
+    return n, repl, actions[:na.value].copy()
+
+
+def search_kf_sim3(kf, scw, P, matched, th, ratio_hamming):
+    m = len(P["xyz"])
+    args, keep = _kf_points_args(P, m)
+    matched = np.ascontiguousarray(matched, np.uint8)
+    slots = np.empty(len(matched), np.int32)
+    n = mlib().refm_search_kf_sim3(C.c_void_p(kf.h), _f(scw[0]), _f(scw[1]), _f(scw[2]), _f(scw[3]), m, *args,
+                                   _p(matched), int(th), _f(ratio_hamming), _p(slots))
+    return n, slots
+
+
+def search_by_sim3(kf1, kf2, s12, pre12, th):
+    pre12 = np.ascontiguousarray(pre12, np.int32)
+    out = np.empty(len(pre12), np.int32)
+    n = mlib().refm_search_by_sim3(C.c_void_p(kf1.h), C.c_void_p(kf2.h), _f(s12[0]), _f(s12[1]), _f(s12[2]), _f(s12[3]),
+                                   _p(pre12), _f(th), _p(out))
+    return n, out

@@ -16,6 +16,7 @@
 
 using namespace ORB_SLAM3;
 
+std::vector<RefAction> ORB_SLAM3::g_refActions;
 float Frame::mfGridElementWidthInv = 0, Frame::mfGridElementHeightInv = 0;
 float Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0;
 
@@ -198,6 +199,151 @@ int refm_search_keyframe(void* cur, void* kfFrame, const uint8_t* alreadyFound, 
     Matcher matcher(nnratio, checkOri != 0);
     const int n = matcher.SearchByProjection(rc->F, &rk->kf, found, th, ORBdist);
     flatten(rc, rk->F.mvpMapPoints, slot_out);
+    return n;
+}
+
+// ---- keyframe-side searches ---------------------------------------------------------------------------
+// The RefFrame's data seen as a KeyFrame, filled the way KeyFrame::KeyFrame(Frame&, ...) does
+// (src/KeyFrame.cc:44-76): keys, descriptors, grid copied cell by cell, bounds truncated to int.
+static KeyFrame* as_keyframe(RefFrame* rf) {
+    KeyFrame& K = rf->kf;
+    const Frame& F = rf->F;
+    K.N = F.N; K.NLeft = F.Nleft;
+    K.mvKeys = F.mvKeys; K.mvKeysUn = F.mvKeysUn; K.mvKeysRight = F.mvKeysRight;
+    K.mvuRight = F.mvuRight; K.mDescriptors = F.mDescriptors;
+    K.mnScaleLevels = F.mnScaleLevels; K.mfLogScaleFactor = F.mfLogScaleFactor;
+    K.mvScaleFactors = F.mvScaleFactors;
+    K.mvInvLevelSigma2.resize(F.mnScaleLevels);
+    for (int i = 0; i < F.mnScaleLevels; i++) K.mvInvLevelSigma2[i] = 1.0f / (F.mvScaleFactors[i] * F.mvScaleFactors[i]);
+    K.mnMinX = Frame::mnMinX; K.mnMinY = Frame::mnMinY; K.mnMaxX = Frame::mnMaxX; K.mnMaxY = Frame::mnMaxY;
+    K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+    K.mGrid.assign(K.mnGridCols, std::vector<std::vector<size_t>>(K.mnGridRows));
+    for (int i = 0; i < K.mnGridCols; i++)
+        for (int j = 0; j < K.mnGridRows; j++) K.mGrid[i][j] = F.mGrid[i][j];
+    K.fx = rf->cam.fx; K.fy = rf->cam.fy; K.cx = rf->cam.cx; K.cy = rf->cam.cy; K.mbf = F.mbf;
+    K.mpCamera = &rf->cam; K.mpCamera2 = &rf->cam;
+    K.mTcw = F.mTcw;
+    K.mvpMapPoints = F.mvpMapPoints;
+    for (int i = 0; i < F.N; i++)
+        if (K.mvpMapPoints[i]) K.mvpMapPoints[i]->id = 1000000 + i;
+    return &K;
+}
+
+static std::vector<std::unique_ptr<MapPoint>> make_points(int m, const uint8_t* has, const uint8_t* bad, const uint8_t* inKF,
+                                                          const float* xyz, const float* normal, const float* minDist,
+                                                          const float* maxDist, const int* nobs, const uint8_t* desc,
+                                                          std::vector<MapPoint*>& vp) {
+    std::vector<std::unique_ptr<MapPoint>> pts(m);
+    vp.assign(m, nullptr);
+    for (int i = 0; i < m; i++) {
+        if (has && !has[i]) continue;
+        MapPoint* p = new MapPoint();
+        pts[i].reset(p); vp[i] = p;
+        p->id = i;
+        p->bad = bad ? bad[i] != 0 : false;
+        p->inKF = inKF ? inKF[i] != 0 : false;
+        p->pos = Eigen::Vector3f(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        if (normal) p->normal = Eigen::Vector3f(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        p->mfMinDistance = minDist[i]; p->mfMaxDistance = maxDist[i];
+        p->nObs = nobs ? nobs[i] : 1;
+        p->desc = wrap_desc(desc + 32 * (size_t)i, 1);
+    }
+    return pts;
+}
+
+static int dump_actions(int* actions, int cap) {
+    int n = 0;
+    for (const RefAction& a : g_refActions) {
+        if (n < cap) { actions[3 * n] = a.kind; actions[3 * n + 1] = a.a; actions[3 * n + 2] = a.b; }
+        n++;
+    }
+    return n;
+}
+
+void refm_frame_camera(void* h, float fx, float fy, float cx, float cy) {
+    RefFrame* rf = (RefFrame*)h;
+    rf->cam.fx = fx; rf->cam.fy = fy; rf->cam.cx = cx; rf->cam.cy = cy;
+}
+
+int refm_kf_predict_scale(void* h, float maxDistance, float dist) {
+    MapPoint p;
+    p.mfMaxDistance = maxDistance;
+    return p.PredictScale(dist, as_keyframe((RefFrame*)h));
+}
+
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight).  Graph updates come back as a list of
+// (kind, a, b): 1 = point a Replace(point b), 2 = point a AddObservation(idx b), 3 = AddMapPoint(point a, idx b);
+// candidate points have id = their index, keyframe slot points id = 1000000 + slot.
+int refm_fuse(void* h, int m, const uint8_t* has, const uint8_t* bad, const uint8_t* inKF, const float* xyz,
+              const float* normal, const float* minDist, const float* maxDist, const int* nobs, const uint8_t* desc,
+              float th, int* actions, int cap, int* nActions) {
+    RefFrame* rf = (RefFrame*)h;
+    KeyFrame* kf = as_keyframe(rf);
+    std::vector<MapPoint*> vp;
+    auto own = make_points(m, has, bad, inKF, xyz, normal, minDist, maxDist, nobs, desc, vp);
+    g_refActions.clear();
+    Matcher matcher(0.6f, true);
+    const int n = matcher.Fuse(kf, vp, th, false);
+    *nActions = dump_actions(actions, cap);
+    return n;
+}
+
+// ORBmatcher::Fuse(KeyFrame*, Sim3f& Scw, vpPoints, th, vpReplacePoint): replace_out[i] = keyframe slot whose
+// point replaces candidate i, or -1.
+int refm_fuse_sim3(void* h, float s, float tx, float ty, float tz, int m, const uint8_t* bad, const float* xyz,
+                   const float* normal, const float* minDist, const float* maxDist, const uint8_t* desc, float th,
+                   int* replace_out, int* actions, int cap, int* nActions) {
+    RefFrame* rf = (RefFrame*)h;
+    KeyFrame* kf = as_keyframe(rf);
+    std::vector<MapPoint*> vp;
+    auto own = make_points(m, nullptr, bad, nullptr, xyz, normal, minDist, maxDist, nullptr, desc, vp);
+    std::vector<MapPoint*> repl(m, nullptr);
+    Sophus::Sim3f Scw(s, Eigen::Vector3f(tx, ty, tz));
+    g_refActions.clear();
+    Matcher matcher(0.6f, true);
+    const int n = matcher.Fuse(kf, Scw, vp, th, repl);
+    for (int i = 0; i < m; i++) replace_out[i] = repl[i] ? repl[i]->id - 1000000 : -1;
+    *nActions = dump_actions(actions, cap);
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame*, Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming):
+// matched_in[i] != 0 <=> vpMatched[i] non-NULL on entry; slot_out[i] = index of the candidate now in vpMatched[i],
+// -2 = unchanged.
+int refm_search_kf_sim3(void* h, float s, float tx, float ty, float tz, int m, const uint8_t* bad, const float* xyz,
+                        const float* normal, const float* minDist, const float* maxDist, const uint8_t* desc,
+                        const uint8_t* matched_in, int th, float ratioHamming, int* slot_out) {
+    RefFrame* rf = (RefFrame*)h;
+    KeyFrame* kf = as_keyframe(rf);
+    std::vector<MapPoint*> vp;
+    auto own = make_points(m, nullptr, bad, nullptr, xyz, normal, minDist, maxDist, nullptr, desc, vp);
+    std::vector<std::unique_ptr<MapPoint>> placeholders;
+    std::vector<MapPoint*> matched(kf->N, nullptr);
+    for (int i = 0; i < kf->N; i++)
+        if (matched_in[i]) { placeholders.emplace_back(new MapPoint()); placeholders.back()->id = -7; matched[i] = placeholders.back().get(); }
+    const std::vector<MapPoint*> before = matched;
+    Sophus::Sim3f Scw(s, Eigen::Vector3f(tx, ty, tz));
+    Matcher matcher(0.6f, true);
+    const int n = matcher.SearchByProjection(kf, Scw, vp, matched, th, ratioHamming);
+    for (int i = 0; i < kf->N; i++) slot_out[i] = matched[i] == before[i] ? -2 : matched[i]->id;
+    return n;
+}
+
+// ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, S12, th): pre12[i1] = KF2 slot whose point is already in
+// vpMatches12[i1] (-1 = NULL); out12[i1] = KF2 slot of the point in vpMatches12[i1] afterwards, or -1.
+int refm_search_by_sim3(void* h1, void* h2, float s, float tx, float ty, float tz, const int* pre12, float th, int* out12) {
+    RefFrame *r1 = (RefFrame*)h1, *r2 = (RefFrame*)h2;
+    KeyFrame* k1 = as_keyframe(r1);
+    KeyFrame* k2 = as_keyframe(r2);
+    for (int i = 0; i < k2->N; i++)
+        if (k2->mvpMapPoints[i]) { k2->mvpMapPoints[i]->id = 2000000 + i; k2->mvpMapPoints[i]->idxInOtherKF = i; }
+    std::vector<MapPoint*> m12(k1->N, nullptr);
+    for (int i = 0; i < k1->N; i++)
+        if (pre12[i] >= 0) m12[i] = k2->mvpMapPoints[pre12[i]];
+    Sophus::Sim3f S12(s, Eigen::Vector3f(tx, ty, tz));
+    Matcher matcher(0.75f, true);
+    const int n = matcher.SearchBySim3(k1, k2, m12, S12, th);
+    for (int i = 0; i < k1->N; i++) out12[i] = m12[i] ? m12[i]->id - 2000000 : -1;
     return n;
 }
 

@@ -37,7 +37,11 @@ struct Vector3f {
     Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
     Vector3f operator+(const Vector3f& o) const { return Vector3f(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
     float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+    Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
+    Vector3f operator*(float s) const { return Vector3f(v[0] * s, v[1] * s, v[2] * s); }
 };
+struct Matrix3f {};  // always the identity here
 struct Vector2f {
     float v[2];
     Vector2f() : v{0, 0} {}
@@ -54,20 +58,38 @@ struct SE3 {
     Eigen::Vector3f t;
     SE3() {}
     explicit SE3(const Eigen::Vector3f& t_) : t(t_) {}
+    SE3(const Eigen::Matrix3f&, const Eigen::Vector3f& t_) : t(t_) {}
     SE3 inverse() const { return SE3(Eigen::Vector3f(-t(0), -t(1), -t(2))); }
     Eigen::Vector3f translation() const { return t; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p + t; }
 };
 typedef SE3<float> SE3f;
+// scale + translation similarity: p -> s*p + t
 template <class T>
-struct Sim3 {};
+struct Sim3 {
+    float s = 1;
+    Eigen::Vector3f t;
+    Sim3() {}
+    Sim3(float s_, const Eigen::Vector3f& t_) : s(s_), t(t_) {}
+    Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
+    Eigen::Vector3f translation() const { return t; }
+    float scale() const { return s; }
+    Sim3 inverse() const { return Sim3(1.0f / s, Eigen::Vector3f(-t(0) / s, -t(1) / s, -t(2) / s)); }
+    Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p * s + t; }
+};
 typedef Sim3<float> Sim3f;
 }  // namespace Sophus
+
+#include <tuple>
 
 namespace ORB_SLAM3 {
 
 class Frame;
 class KeyFrame;
+class MapPoint;
+
+struct RefAction { int kind, a, b; };   // 1: a->Replace(b)   2: a->AddObservation(kf, idx=b)   3: kf->AddMapPoint(a, idx=b)
+extern std::vector<RefAction> g_refActions;
 
 class GeometricCamera {
    public:
@@ -91,7 +113,18 @@ class MapPoint {
     Eigen::Vector3f GetWorldPos() { return pos; }
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
-    int PredictScale(const float& currentDist, Frame* pF);  // body sliced from src/MapPoint.cc
+    int PredictScale(const float& currentDist, Frame* pF);      // bodies sliced from src/MapPoint.cc
+    int PredictScale(const float& currentDist, KeyFrame* pKF);
+    Eigen::Vector3f GetNormal() { return normal; }
+    bool IsInKeyFrame(KeyFrame* pKF) { return inKF; }
+    std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* pKF) { return std::tuple<int, int>(idxInOtherKF, -1); }
+    // graph updates of Fuse are recorded, not performed: (kind, this->id, other id or keypoint index)
+    void Replace(MapPoint* pMP);
+    void AddObservation(KeyFrame* pKF, int idx);
+    int id = -1;
+    bool inKF = false;
+    int idxInOtherKF = -1;
+    Eigen::Vector3f normal;
     // state
     std::mutex mMutexPos;
     float mfMinDistance = 0, mfMaxDistance = 0;
@@ -103,10 +136,46 @@ class MapPoint {
 
 class KeyFrame {
    public:
+    // sliced from src/KeyFrame.cc
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
+
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::set<MapPoint*> GetMapPoints() {   // src/KeyFrame.cc:370-385
+        std::set<MapPoint*> s;
+        for (MapPoint* p : mvpMapPoints)
+            if (p && !p->isBad()) s.insert(p);
+        return s;
+    }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) {
+        mvpMapPoints[idx] = pMP;
+        g_refActions.push_back({3, pMP->id, (int)idx});
+    }
+    Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetRightPose() { return mTcw; }
+    Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
+    Eigen::Vector3f GetRightCameraCenter() { return mTcw.inverse().translation(); }
+
+    float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0;
+    GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+    int N = 0, NLeft = -1;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    int mnScaleLevels = 0;
+    float mfLogScaleFactor = 0;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;      // ints in the reference's KeyFrame (include/KeyFrame.h:403)
+    int mnGridCols = 64, mnGridRows = 48;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
     std::vector<MapPoint*> mvpMapPoints;
-    std::vector<cv::KeyPoint> mvKeysUn;
+    Sophus::SE3f mTcw;
 };
+
+inline void MapPoint::Replace(MapPoint* pMP) { g_refActions.push_back({1, id, pMP->id}); }
+inline void MapPoint::AddObservation(KeyFrame*, int idx) { g_refActions.push_back({2, id, idx}); }
 
 class Frame {
    public:

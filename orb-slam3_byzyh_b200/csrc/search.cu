@@ -590,6 +590,92 @@ k_search_init(const OrbfeKeyPoint* __restrict__ keys1, const uint32_t* __restric
     if (lane == 0) *nmatchesOut = nmatches;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Keyframe-side searches: ORBmatcher::Fuse (ORBmatcher.cc:1326-1534, 1536-1688),
+// SearchBySim3 (:1690-1940) and the inner loop of the Sim3 SearchByProjection overloads (:496-733)
+// carry no state from one map point to the next: KeyFrame::GetFeaturesInArea (KeyFrame.cc:843-892,
+// the same cells and order as Frame's), the `kpLevel < nPredictedLevel-1 || kpLevel > nPredictedLevel`
+// filter, optionally Fuse's reprojection gate (:1436-1461), then the strict-`<` Hamming argmin.
+// One WARP per point (these calls carry a few thousand points: latency, not throughput): lanes
+// stride over the candidates of each cell; the key (distance << 23 | position in GetFeaturesInArea
+// order) makes the warp minimum the candidate the sequential loop would have kept.
+__global__ void __launch_bounds__(128)
+k_window_best(GridDev F, PtsDev P, int thAccept, int fuseGate, const float* __restrict__ invSigma2, int nLevels,
+              int* __restrict__ bestIdx, int* __restrict__ bestDist) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= P.m) return;
+    uint32_t key = 0xFFFFFFFFu;
+    int kIdx = -1;
+    if (P.valid[j]) {
+        const float x = P.u[j], y = P.v[j], r = P.radius[j];
+        const int minLevel = P.minLevel[j], maxLevel = P.maxLevel[j];
+        const int c0x = max(0, (int)floorf((x - F.minX - r) * F.wInv));
+        const int c1x = min(GC - 1, (int)ceilf((x - F.minX + r) * F.wInv));
+        const int c0y = max(0, (int)floorf((y - F.minY - r) * F.hInv));
+        const int c1y = min(GR - 1, (int)ceilf((y - F.minY + r) * F.hInv));
+        if (c0x < GC && c1x >= 0 && c0y < GR && c1y >= 0) {
+            uint32_t d[8];
+            const uint4* pd = reinterpret_cast<const uint4*>(P.desc + 8 * (size_t)j);
+            *reinterpret_cast<uint4*>(d) = pd[0];
+            *reinterpret_cast<uint4*>(d + 4) = pd[1];
+            const float ur = P.ur ? P.ur[j] : 0.f;
+            int order = 0;
+            for (int ix = c0x; ix <= c1x; ix++) {
+                // the cells (ix, c0y..c1y) are contiguous in cellStart (cell id = ix*GR + iy)
+                const int cb = F.cellStart[ix * GR + c0y], ce = F.cellStart[ix * GR + c1y + 1];
+                for (int t = cb + lane; t < ce; t += 32) {
+                    const int idx = F.cellItems[t];
+                    const OrbfeKeyPoint kp = F.keys[idx];
+                    if (!(fabsf(kp.x - x) < r && fabsf(kp.y - y) < r)) continue;
+                    if (kp.octave < minLevel || kp.octave > maxLevel) continue;
+                    if (fuseGate) {
+                        if (kp.octave < 0 || kp.octave >= nLevels) continue;
+                        const float ex = x - kp.x, ey = y - kp.y;
+                        const float inv = invSigma2[kp.octave];
+                        const float uR = F.uright ? F.uright[idx] : -1.f;
+                        if (uR >= 0) {
+                            const float er = ur - uR;
+                            const float e2 = ex * ex + ey * ey + er * er;
+                            if ((double)(e2 * inv) > 7.8) continue;
+                        } else {
+                            const float e2 = ex * ex + ey * ey;
+                            if ((double)(e2 * inv) > 5.99) continue;
+                        }
+                    }
+                    const uint4* kd = reinterpret_cast<const uint4*>(F.desc + 8 * (size_t)idx);
+                    const int dist = hamming8(d, kd[0], kd[1]);
+                    const uint32_t k = ((uint32_t)dist << 23) | (uint32_t)(order + t - cb);
+                    if (k < key) { key = k; kIdx = idx; }
+                }
+                order += ce - cb;
+            }
+        }
+    }
+    const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+    const uint32_t owner = __ballot_sync(0xffffffffu, key == best && kIdx >= 0);
+    if (owner == 0) {   // no candidate, or only candidates at distance 256 (never accepted by any caller)
+        if (lane == 0) { bestIdx[j] = -1; bestDist[j] = 256; }
+        return;
+    }
+    if (lane == __ffs(owner) - 1) {
+        const int dist = (int)(best >> 23);
+        bestDist[j] = dist < 256 ? dist : 256;
+        bestIdx[j] = (dist < 256 && dist <= thAccept) ? kIdx : -1;
+    }
+}
+
+// SearchBySim3, ORBmatcher.cc:1922-1937: keep i1 -> idx2 only when KF2's point at idx2 chose i1.
+__global__ void k_sim3_mutual(int n1, const int* __restrict__ m1, const int* __restrict__ m2, int* __restrict__ match12,
+                              int* __restrict__ nFound) {
+    const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= n1) return;
+    const int idx2 = m1[i1];
+    int out = -1;
+    if (idx2 >= 0 && m2[idx2] == i1) { out = idx2; atomicAdd(nFound, 1); }
+    match12[i1] = out;
+}
+
 int sfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
 #define SCK(call)                                                        \
     do {                                                                 \
@@ -851,4 +937,128 @@ extern "C" int orbfe_search_for_initialization(const OrbfeFrameView* f1, const O
     SCK(cudaGetLastError());
     SCK(S.download());
     return nmatches;
+}
+
+namespace {
+
+// Staging of one keyframe view + one point set for the stateless window searches.
+struct WinStage {
+    size_t iKeys, iDesc, iUr, iU, iV, iPur, iRad, iMin, iMax, iVal, iPd, wCellOf, wStart, wItems;
+    std::vector<uint8_t> ones;
+    void lay(OrbfeStage& S, const OrbfeFrameView* f, const OrbfeProjPoints* p) {
+        const size_t n = (size_t)f->n, m = (size_t)p->m;
+        if (!p->valid) ones.assign(m, 1);
+        iKeys = S.in(f->keys, sizeof(OrbfeKeyPoint) * n); iDesc = S.in(f->desc, 32 * n);
+        iUr = S.in(f->uright, f->uright ? 4 * n : 0);
+        iU = S.in(p->u, 4 * m); iV = S.in(p->v, 4 * m); iPur = S.in(p->ur, p->ur ? 4 * m : 0);
+        iRad = S.in(p->radius, 4 * m); iMin = S.in(p->min_level, 4 * m); iMax = S.in(p->max_level, 4 * m);
+        iVal = S.in(p->valid ? p->valid : ones.data(), m); iPd = S.in(p->desc, 32 * m);
+        wCellOf = S.work(4 * n); wStart = S.work(4 * (GC * GR + 1)); wItems = S.work(4 * n);
+    }
+    void bind(const OrbfeStage& S, const OrbfeFrameView* f, const OrbfeProjPoints* p, GridDev& F, PtsDev& P) const {
+        F.keys = S.ptr<OrbfeKeyPoint>(iKeys); F.uright = f->uright ? S.ptr<float>(iUr) : nullptr;
+        F.desc = S.ptr<uint32_t>(iDesc); F.n = f->n;
+        F.minX = f->min_x; F.minY = f->min_y; F.maxX = f->max_x; F.maxY = f->max_y;
+        F.wInv = f->grid_w_inv; F.hInv = f->grid_h_inv;
+        F.cellStart = S.ptr<int>(wStart); F.cellItems = S.ptr<int>(wItems);
+        P.m = p->m; P.u = S.ptr<float>(iU); P.v = S.ptr<float>(iV); P.ur = p->ur ? S.ptr<float>(iPur) : nullptr;
+        P.radius = S.ptr<float>(iRad); P.angle = nullptr;
+        P.minLevel = S.ptr<int>(iMin); P.maxLevel = S.ptr<int>(iMax); P.valid = S.ptr<uint8_t>(iVal);
+        P.blocks = nullptr; P.desc = S.ptr<uint32_t>(iPd);
+    }
+    void grid(const OrbfeStage& S, const GridDev& F, cudaStream_t st) const {
+        k_build_grid<<<1, 1024, 0, st>>>(F.keys, F.n, F.minX, F.minY, F.wInv, F.hInv, S.ptr<int>(wCellOf),
+                                         S.ptr<int>(wStart), S.ptr<int>(wItems));
+    }
+};
+
+int check_window_args(const OrbfeFrameView* f, const OrbfeProjPoints* p, int device) {
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return sfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return sfail(ORBFE_ERR_INVALID, "bad device ordinal");
+    if (!f || !p) return sfail(ORBFE_ERR_INVALID, "null argument");
+    if (f->n < 0 || p->m < 0 || f->n >= (1 << 23)) return sfail(ORBFE_ERR_INVALID, "bad sizes");
+    if (f->n > 0 && p->m > 0 &&
+        (!f->keys || !f->desc || !p->u || !p->v || !p->radius || !p->min_level || !p->max_level || !p->desc))
+        return sfail(ORBFE_ERR_INVALID, "missing keyframe / map-point array");
+    return ORBFE_OK;
+}
+
+}  // namespace
+
+extern "C" int orbfe_search_window(const OrbfeFrameView* kf, const OrbfeProjPoints* pts, const OrbfeWindowParams* prm,
+                                   int32_t* best_idx, int32_t* best_dist, int device) {
+    if (!prm || !best_idx) return sfail(ORBFE_ERR_INVALID, "null argument");
+    int rc = check_window_args(kf, pts, device);
+    if (rc != ORBFE_OK) return rc;
+    const int m = pts->m;
+    if (prm->gate != ORBFE_GATE_NONE && prm->gate != ORBFE_GATE_FUSE) return sfail(ORBFE_ERR_INVALID, "bad gate");
+    if (prm->gate == ORBFE_GATE_FUSE && (!prm->inv_level_sigma2 || prm->n_levels <= 0))
+        return sfail(ORBFE_ERR_INVALID, "the Fuse gate needs mvInvLevelSigma2");
+    if (m == 0 || kf->n == 0) {
+        for (int j = 0; j < m; j++) {
+            best_idx[j] = -1;
+            if (best_dist) best_dist[j] = 256;
+        }
+        return 0;
+    }
+    OrbfeStage S;
+    WinStage W;
+    W.lay(S, kf, pts);
+    const bool gate = prm->gate == ORBFE_GATE_FUSE;
+    const size_t iInv = S.in(prm->inv_level_sigma2, gate ? 4 * (size_t)prm->n_levels : 0);
+    const size_t oBest = S.out(best_idx, 4 * (size_t)m), oDist = S.out(best_dist, 4 * (size_t)m);
+    SCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    SCK(S.upload());
+    GridDev F;
+    PtsDev P;
+    W.bind(S, kf, pts, F, P);
+    W.grid(S, F, st);
+    k_window_best<<<(m + 3) / 4, 128, 0, st>>>(F, P, prm->th_accept, gate ? 1 : 0, gate ? S.ptr<float>(iInv) : nullptr,
+                                               prm->n_levels, S.ptr<int>(oBest), S.ptr<int>(oDist));
+    SCK(cudaGetLastError());
+    SCK(S.download());
+    int n = 0;
+    for (int j = 0; j < m; j++) n += best_idx[j] >= 0;
+    return n;
+}
+
+extern "C" int orbfe_search_by_sim3(const OrbfeFrameView* kf1, const OrbfeFrameView* kf2, const OrbfeProjPoints* pts12,
+                                    const OrbfeProjPoints* pts21, int th_accept, int32_t* match12, int device) {
+    if (!match12) return sfail(ORBFE_ERR_INVALID, "null argument");
+    int rc = check_window_args(kf2, pts12, device);
+    if (rc == ORBFE_OK) rc = check_window_args(kf1, pts21, device);
+    if (rc != ORBFE_OK) return rc;
+    if (pts12->m != kf1->n || pts21->m != kf2->n)
+        return sfail(ORBFE_ERR_INVALID, "SearchBySim3 takes one projected point per keyframe slot");
+    const int n1 = kf1->n, n2 = kf2->n;
+    if (n1 == 0 || n2 == 0) {
+        for (int i = 0; i < n1; i++) match12[i] = -1;
+        return 0;
+    }
+    OrbfeStage S;
+    WinStage W12, W21;   // W12: KF1's points searched in KF2; W21: the reverse
+    W12.lay(S, kf2, pts12);
+    W21.lay(S, kf1, pts21);
+    const size_t wM1 = S.work(4 * (size_t)n1), wM2 = S.work(4 * (size_t)n2), wD = S.work(4 * (size_t)std::max(n1, n2));
+    int nFound = 0;
+    const size_t oMatch = S.out(match12, 4 * (size_t)n1), oN = S.out(&nFound, 4);
+    SCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    SCK(S.upload());
+    GridDev F1, F2;
+    PtsDev P12, P21;
+    W12.bind(S, kf2, pts12, F2, P12);
+    W21.bind(S, kf1, pts21, F1, P21);
+    W12.grid(S, F2, st);
+    W21.grid(S, F1, st);
+    SCK(cudaMemsetAsync(S.ptr<int>(oN), 0, 4, st));
+    k_window_best<<<(n1 + 3) / 4, 128, 0, st>>>(F2, P12, th_accept, 0, nullptr, 0, S.ptr<int>(wM1), S.ptr<int>(wD));
+    k_window_best<<<(n2 + 3) / 4, 128, 0, st>>>(F1, P21, th_accept, 0, nullptr, 0, S.ptr<int>(wM2), S.ptr<int>(wD));
+    k_sim3_mutual<<<(n1 + 255) / 256, 256, 0, st>>>(n1, S.ptr<int>(wM1), S.ptr<int>(wM2), S.ptr<int>(oMatch), S.ptr<int>(oN));
+    SCK(cudaGetLastError());
+    SCK(S.download());
+    return nFound;
 }

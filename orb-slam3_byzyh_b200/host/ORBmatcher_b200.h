@@ -8,6 +8,7 @@
 #ifndef ORBMATCHER_B200_H
 #define ORBMATCHER_B200_H
 
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -108,6 +109,83 @@ inline int SearchByProjectionFisheye(const std::vector<cv::KeyPoint>& keysL, con
     const int n = orbfe_search_by_projection_fisheye(&fl, &fr, l2r.data(), r2l.data(), &pl, &pr, &prm, claimed.data(),
                                                      assigned.data(), nullptr, nullptr, device());
     if (n < 0) throw std::runtime_error(std::string("SearchByProjection fisheye (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// A keyframe as the keyframe-side searches see it: pKF->mvKeysUn (mvKeys / mvKeysRight for a fisheye
+// keyframe), pKF->mvuRight, pKF->mDescriptors and the KeyFrame's grid bounds (mnMinX.. are ints there).
+struct KeyFrameView {
+    const std::vector<cv::KeyPoint>* keys;
+    const std::vector<float>* uright;   // may be null
+    const uint8_t* desc;
+    float minX, minY, maxX, maxY, wInv, hInv;
+    OrbfeFrameView view() const {
+        OrbfeFrameView fv;
+        fv.n = (int32_t)keys->size();
+        fv.keys = reinterpret_cast<const OrbfeKeyPoint*>(keys->data());
+        fv.uright = (uright && !uright->empty()) ? uright->data() : nullptr;
+        fv.desc = desc;
+        fv.min_x = minX; fv.min_y = minY; fv.max_x = maxX; fv.max_y = maxY;
+        fv.grid_w_inv = wInv; fv.grid_h_inv = hInv;
+        return fv;
+    }
+};
+
+inline OrbfeProjPoints view(const ProjPoints& p) {
+    OrbfeProjPoints pp;
+    pp.m = (int32_t)p.size();
+    pp.u = p.u.data(); pp.v = p.v.data(); pp.ur = p.ur.data(); pp.radius = p.radius.data();
+    pp.min_level = p.minLevel.data(); pp.max_level = p.maxLevel.data(); pp.angle = p.angle.data();
+    pp.valid = p.valid.data(); pp.blocks = p.blocks.data(); pp.desc = p.desc.data();
+    return pp;
+}
+
+// Inner loop of int ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight)  (ORBmatcher.cc:1326-1534,
+// reprojection gate :1436-1461 -> pass pKF->mvInvLevelSigma2) and of Fuse(KeyFrame*, Sim3f&, ...) (:1536-1688,
+// no gate -> pass an empty vector).  pts: one entry per candidate map point (level window [nPredictedLevel-1,
+// nPredictedLevel], ur = uv(0) - bf*invz, valid = passed :1360-1407).  bestIdx[i] = keypoint the point fuses
+// with (bestDist <= TH_LOW) or -1; the caller then runs :1480-1501 / :1645-1661 on its MapPoint graph:
+//     for i in order, bestIdx[i] >= 0:  pMPinKF = pKF->GetMapPoint(bestIdx[i]);
+//         pMPinKF ? (Replace / vpReplacePoint[i] = pMPinKF) : (AddObservation + AddMapPoint);  nFused++
+inline int FuseSearch(const KeyFrameView& kf, const ProjPoints& pts, const std::vector<float>& invLevelSigma2,
+                      std::vector<int32_t>& bestIdx, int thLow = 50) {
+    bestIdx.assign(pts.size(), -1);
+    if (pts.size() == 0) return 0;
+    const OrbfeFrameView fv = kf.view();
+    const OrbfeProjPoints pp = view(pts);
+    OrbfeWindowParams prm = {thLow, invLevelSigma2.empty() ? ORBFE_GATE_NONE : ORBFE_GATE_FUSE,
+                             invLevelSigma2.empty() ? nullptr : invLevelSigma2.data(), (int32_t)invLevelSigma2.size()};
+    const int n = orbfe_search_window(&fv, &pp, &prm, bestIdx.data(), nullptr, device());
+    if (n < 0) throw std::runtime_error(std::string("Fuse (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sim3f& S12, th)
+// (ORBmatcher.cc:1690-1940).  pts12[i1]: KF1's map point i1 through S21 into KF2 (valid = :1731-1765 passed, i.e.
+// not in vbAlreadyMatched1), pts21 the reverse.  match12[i1] = idx2 agreed by both directions or -1; the caller
+// stores vpMatches12[i1] = vpMapPoints2[match12[i1]].  Returns nFound.
+inline int SearchBySim3(const KeyFrameView& kf1, const KeyFrameView& kf2, const ProjPoints& pts12,
+                        const ProjPoints& pts21, std::vector<int32_t>& match12, int thHigh = 100) {
+    match12.assign(kf1.keys->size(), -1);
+    const OrbfeFrameView f1 = kf1.view(), f2 = kf2.view();
+    const OrbfeProjPoints p12 = view(pts12), p21 = view(pts21);
+    const int n = orbfe_search_by_sim3(&f1, &f2, &p12, &p21, thHigh, match12.data(), device());
+    if (n < 0) throw std::runtime_error(std::string("SearchBySim3 (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// int ORBmatcher::SearchByProjection(KeyFrame* pKF, Sim3f& Scw, const vector<MapPoint*>& vpPoints,
+// vector<MapPoint*>& vpMatched, int th, float ratioHamming)  (ORBmatcher.cc:496-610; the overload with
+// vpPointsKFs :612-733 runs the same loop).  matched[i] != 0 <=> vpMatched[i] != NULL on entry; assigned[i]
+// (size pKF->N, initialised to -2) = index into vpPoints of the point now in vpMatched[i].  Returns nmatches.
+inline int SearchByProjectionSim3(const KeyFrameView& kf, const ProjPoints& pts, float ratioHamming,
+                                  const std::vector<uint8_t>& matched, std::vector<int32_t>& assigned, int thLow = 50) {
+    const OrbfeFrameView fv = kf.view();
+    const OrbfeProjPoints pp = view(pts);
+    // bestDist <= TH_LOW*ratioHamming (int vs float, :589)  <=>  bestDist <= floor(TH_LOW*ratioHamming)
+    OrbfeSearchParams prm = {ORBFE_SEARCH_KEYFRAME, (int32_t)std::floor((float)thLow * ratioHamming), 1.0f, 0};
+    const int n = orbfe_search_by_projection(&fv, &pp, &prm, matched.data(), assigned.data(), nullptr, nullptr, device());
+    if (n < 0) throw std::runtime_error(std::string("SearchByProjection Sim3 (B200): ") + orbfe_last_error());
     return n;
 }
 

@@ -44,6 +44,11 @@ class SearchParams(C.Structure):
                 ("check_orientation", C.c_int32)]
 
 
+class WindowParams(C.Structure):
+    _fields_ = [("th_accept", C.c_int32), ("gate", C.c_int32), ("inv_level_sigma2", C.c_void_p),
+                ("n_levels", C.c_int32)]
+
+
 _lib = None
 
 _vp, _i, _f, _sz, _ull = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
@@ -84,6 +89,9 @@ _SIGS = {
                                                 C.POINTER(ProjPoints), C.POINTER(ProjPoints), C.POINTER(SearchParams),
                                                 _vp, _vp, _vp, _vp, _i]),
     "orbfe_search_for_initialization": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), _vp, _i, _f, _i, _vp, _i]),
+    "orbfe_search_window": (_i, [C.POINTER(FrameView), C.POINTER(ProjPoints), C.POINTER(WindowParams), _vp, _vp, _i]),
+    "orbfe_search_by_sim3": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(ProjPoints),
+                                  C.POINTER(ProjPoints), _i, _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -7,7 +7,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import FrameView, ProjPoints, SearchParams, check, lib, ptr
+from ._lib import FrameView, ProjPoints, SearchParams, WindowParams, check, lib, ptr
 
 MODE_MAPPOINTS, MODE_LASTFRAME, MODE_KEYFRAME = 0, 1, 2
 
@@ -129,6 +129,56 @@ class ORBmatcher:
                                                         self.mfNNratio, int(self.mbCheckOrientation), ptr(m12),
                                                         self.device))
         return n, m12, prev
+
+    @staticmethod
+    def _proj(pts, keep):
+        pp = ProjPoints()
+        pp.m = len(pts["u"])
+        for name, dt in [("u", np.float32), ("v", np.float32), ("ur", np.float32), ("radius", np.float32),
+                         ("min_level", np.int32), ("max_level", np.int32), ("angle", np.float32),
+                         ("valid", np.uint8), ("blocks", np.uint8), ("desc", np.uint8)]:
+            if pts.get(name) is None:
+                continue
+            a = np.ascontiguousarray(pts[name], dt)
+            keep.append(a)
+            setattr(pp, name, a.ctypes.data)
+        return pp
+
+    # Inner loop of Fuse(KeyFrame*, vector<MapPoint*>&, th, bRight) (ORBmatcher.cc:1326-1534; pass
+    # inv_level_sigma2 = pKF->mvInvLevelSigma2 for its reprojection gate) and of Fuse(KeyFrame*, Sim3f&, ...)
+    # (:1536-1688, no gate): per point the keypoint it fuses with (or -1) and the best distance.
+    def FuseSearch(self, KF, pts, inv_level_sigma2=None, th=None):
+        keep = []
+        fv = KF.view(keep)
+        pp = self._proj(pts, keep)
+        prm = WindowParams(self.TH_LOW if th is None else int(th), 0, None, 0)
+        if inv_level_sigma2 is not None:
+            inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+            keep.append(inv)
+            prm.gate, prm.inv_level_sigma2, prm.n_levels = 1, inv.ctypes.data, len(inv)
+        bi, bd = np.empty(pp.m, np.int32), np.empty(pp.m, np.int32)
+        n = check(lib().orbfe_search_window(C.byref(fv), C.byref(pp), C.byref(prm), ptr(bi), ptr(bd), self.device))
+        return n, bi, bd
+
+    # SearchBySim3(pKF1, pKF2, vpMatches12, S12, th), ORBmatcher.cc:1690-1940
+    def SearchBySim3(self, KF1, KF2, pts12, pts21):
+        keep = []
+        f1, f2 = KF1.view(keep), KF2.view(keep)
+        p12, p21 = self._proj(pts12, keep), self._proj(pts21, keep)
+        m12 = np.empty(f1.n, np.int32)
+        n = check(lib().orbfe_search_by_sim3(C.byref(f1), C.byref(f2), C.byref(p12), C.byref(p21), self.TH_HIGH,
+                                             ptr(m12), self.device))
+        return n, m12
+
+    # SearchByProjection(KeyFrame*, Sim3f& Scw, vpPoints, vpMatched, th, ratioHamming), ORBmatcher.cc:496-733
+    def SearchByProjectionSim3(self, KF, pts, matched, assigned, ratioHamming=1.0):
+        keep_ori = self.mbCheckOrientation
+        self.mbCheckOrientation = False
+        try:
+            th = int(np.floor(np.float32(self.TH_LOW) * np.float32(ratioHamming)))
+            return self._search(KF, pts, MODE_KEYFRAME, th, matched, assigned)
+        finally:
+            self.mbCheckOrientation = keep_ori
 
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):

@@ -279,3 +279,85 @@ def test_search_for_initialization(orbfe, seed):
     en, em12, epv = O.search_for_initialization(k1, d1, k2, d2, bounds, prev, 100, 0.9, True)
     assert n == en and n > 100
     assert np.array_equal(m12, em12) and np.array_equal(pv.view(np.uint32), epv.view(np.uint32))
+
+
+def _kf_points(d, n_map, rng, th):
+    """Keyframe-side searches: level window [nPredictedLevel-1, nPredictedLevel], radius = th * scale."""
+    sf = d["scale_factors"]
+    lvl = d["level"][:n_map]
+    return dict(u=d["u"][:n_map], v=d["v"][:n_map], ur=(d["u"][:n_map] - 5 + rng.normal(0, 1.5, n_map)).astype(np.float32),
+                radius=(np.float32(th) * sf[lvl]).astype(np.float32), min_level=(lvl - 1).astype(np.int32),
+                max_level=lvl.astype(np.int32), valid=(rng.uniform(size=n_map) < 0.9).astype(np.uint8),
+                desc=d["mdesc"][:n_map])
+
+
+@pytest.mark.parametrize("gate", [True, False])
+@pytest.mark.parametrize("n_map,n_frame,seed", [(2500, 1200, 3), (40000, 3000, 4), (7, 1, 5)])
+def test_fuse_search(orbfe, gate, n_map, n_frame, seed):
+    """Inner loop of both ORBmatcher::Fuse overloads (ORBmatcher.cc:1326-1534 with the chi2 gate, :1536-1688 without)."""
+    d = synth.map_vs_frame(n_map, n_frame, seed)
+    rng = np.random.default_rng(seed + 11)
+    pts = _kf_points(d, n_map, rng, 3.0)
+    uright = np.where(rng.uniform(size=n_frame) < 0.5, d["keys"]["x"] - 5 + rng.normal(0, 1.5, n_frame), -1).astype(np.float32)
+    sf = d["scale_factors"]
+    inv_sigma2 = (np.float32(1.0) / (sf * sf)).astype(np.float32) if gate else None
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], uright)
+    n, bi, bd = orbfe.ORBmatcher().FuseSearch(F, pts, inv_sigma2)
+    ebi, ebd = O.search_window(d["keys"], d["fdesc"], uright, d["bounds"], pts, 50, gate, inv_sigma2)
+    assert np.array_equal(bi, ebi) and np.array_equal(bd, ebd) and n == (ebi >= 0).sum()
+    if n_map > 100:
+        assert n > 0.1 * min(n_map, n_frame)
+        if gate:   # the gate must actually reject candidates the ungated search keeps
+            ubi, _ = O.search_window(d["keys"], d["fdesc"], uright, d["bounds"], pts, 50, False, None)
+            assert (ubi != ebi).sum() > 0
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_sim3(orbfe, seed):
+    """ORBmatcher.cc:1690-1940: both directions + mutual agreement."""
+    from oracle.oracle import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    n1, n2 = 1800, 2100
+    d = synth.map_vs_frame(n1, n2, seed + 30)          # KF2 keypoints = d["keys"]; KF1's map points = the "map"
+    sf = d["scale_factors"]
+    k2, d2 = d["keys"], d["fdesc"]
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"], k1["y"], k1["octave"] = d["u"], d["v"], d["level"]
+    d1 = d["mdesc"]
+    pts12 = _kf_points(d, n1, rng, 7.5)                # KF1 point i1 projected into KF2
+    # reverse direction: KF2's point i2 projects near the KF1 keypoint it came from (if any), else anywhere
+    back = np.full(n2, -1)
+    src = d["src"]
+    for i1 in range(n1):
+        if src[i1] >= 0:
+            back[src[i1]] = i1
+    u21 = rng.uniform(0, 1280, n2).astype(np.float32); v21 = rng.uniform(0, 720, n2).astype(np.float32)
+    has = back >= 0
+    u21[has] = k1["x"][back[has]] + rng.normal(0, 2, has.sum()); v21[has] = k1["y"][back[has]] + rng.normal(0, 2, has.sum())
+    lvl2 = np.clip(k2["octave"] + (rng.uniform(size=n2) < 0.2), 0, 7).astype(np.int32)
+    pts21 = dict(u=u21, v=v21, radius=(np.float32(7.5) * sf[lvl2]).astype(np.float32), min_level=lvl2 - 1, max_level=lvl2,
+                 valid=(rng.uniform(size=n2) < 0.9).astype(np.uint8), desc=d2)
+    F1, F2 = orbfe.FrameData(k1, d1, d["bounds"]), orbfe.FrameData(k2, d2, d["bounds"])
+    n, m12 = orbfe.ORBmatcher().SearchBySim3(F1, F2, pts12, pts21)
+    en, em12 = O.search_by_sim3(k1, d1, k2, d2, d["bounds"], pts12, pts21, 100)
+    assert n == en and n > 200 and np.array_equal(m12, em12)
+
+
+@pytest.mark.parametrize("ratio", [1.0, 1.5, 0.77])
+def test_search_by_projection_sim3(orbfe, ratio):
+    """ORBmatcher.cc:496-610: keyframe-side search that skips keypoints already in vpMatched and accepts
+    bestDist <= TH_LOW*ratioHamming."""
+    n_map, n_frame = 5000, 1500
+    d = synth.map_vs_frame(n_map, n_frame, 8)
+    rng = np.random.default_rng(80)
+    pts = _kf_points(d, n_map, rng, 8.0)
+    matched = (rng.uniform(size=n_frame) < 0.2).astype(np.uint8)
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"])
+    n, asg, bi, bd = orbfe.ORBmatcher().SearchByProjectionSim3(F, pts, matched, np.full(n_frame, -2, np.int32), ratio)
+    th = int(np.floor(np.float32(50) * np.float32(ratio)))
+    full = dict(pts, angle=np.zeros(n_map, np.float32), blocks=np.ones(n_map, np.uint8))
+    en, easg, ebi, ebd = O.search_by_projection(d["keys"], d["fdesc"], None, d["bounds"], full, 2, th, 1.0, False, matched,
+                                                np.full(n_frame, -2, np.int32), d["scale_factors"])
+    assert n == en and n > 300
+    assert np.array_equal(asg, easg) and np.array_equal(bi, ebi) and np.array_equal(bd, ebd)
+    assert not np.any((asg >= 0) & (matched > 0))

@@ -342,3 +342,268 @@ def test_stereo_matches_vs_reference(seed):
     our, odp = O.stereo_match(exL, exR, kl, dl, kr, dr, mbf, mb)
     assert (ur > 0).sum() > 100
     assert np.array_equal(ur.view(np.uint32), our.view(np.uint32)) and np.array_equal(dp.view(np.uint32), odp.view(np.uint32))
+
+
+# ---- keyframe-side searches: Fuse x2, SearchByProjection (Sim3), SearchBySim3 --------------------------------
+F32 = np.float32
+CAM = (F32(458.654), F32(457.296), F32(367.215), F32(248.375))      # EuRoC-like pinhole intrinsics
+
+
+def _world_points(u, v, lvl, t, rng, sf):
+    """World points whose camera-frame position p + t projects near (u, v); MapPoint distance range chosen so
+    that PredictScale lands on `lvl`; some points violate the depth / range / normal checks on purpose."""
+    m = len(u)
+    fx, fy, cx, cy = [float(c) for c in CAM]
+    z = rng.uniform(2.0, 12.0, m)
+    z[::53] = -1.5
+    pc = np.stack([(u - cx) * z / fx, (v - cy) * z / fy, z], 1)
+    xyz = (pc - np.asarray(t, np.float64)).astype(F32)
+    po = pc.astype(F32)
+    dist = np.linalg.norm(po, axis=1)
+    max_d = (dist * 1.2 ** (lvl - 0.5)).astype(F32)
+    max_d[::37] *= F32(0.3)                                  # too far for its invariance range
+    min_d = (max_d / F32(sf[-1])).astype(F32)
+    normal = (po / dist[:, None]).astype(F32)
+    flip = rng.uniform(size=m) < 0.05
+    normal[flip] *= F32(-1)                                   # seen from behind
+    return xyz, normal, min_d, max_d
+
+
+def _project_kf(xyz, t, with_sim3_scale=None):
+    """Float32 mirror of the reference's projection code in Fuse / Fuse(Sim3) / SearchByProjection(Sim3):
+    p3Dc = Tcw * p3Dw, uv = project(p3Dc), invz = 1/z, PO = p3Dw - Ow, dist3D = |PO|."""
+    fx, fy, cx, cy = CAM
+    t = np.asarray(t, F32)
+    if with_sim3_scale is not None:
+        t = (t / F32(with_sim3_scale)).astype(F32)            # SE3f(Scw.rotationMatrix(), Scw.translation()/Scw.scale())
+    pc = (xyz + t).astype(F32)
+    with np.errstate(all="ignore"):
+        u = (fx * pc[:, 0] / pc[:, 2] + cx).astype(F32)
+        v = (fy * pc[:, 1] / pc[:, 2] + cy).astype(F32)
+        invz = (F32(1) / pc[:, 2]).astype(F32)
+    ow = (-t).astype(F32)
+    po = (xyz - ow).astype(F32)
+    dist = np.sqrt((po[:, 0] * po[:, 0] + po[:, 1] * po[:, 1]) + po[:, 2] * po[:, 2]).astype(F32)
+    return pc, u, v, invz, po, dist
+
+
+def _kf_valid(pc, u, v, po, dist, P, bounds_int):
+    x0, y0, x1, y1 = bounds_int
+    dot = ((po[:, 0] * P["normal"][:, 0] + po[:, 1] * P["normal"][:, 1]).astype(F32) + po[:, 2] * P["normal"][:, 2]).astype(F32)
+    ok = ~(pc[:, 2] < 0)
+    ok &= (u >= x0) & (u < x1) & (v >= y0) & (v < y1)                               # KeyFrame::IsInImage
+    ok &= ~((dist < F32(0.8) * P["min_dist"]) | (dist > F32(1.2) * P["max_dist"]))
+    ok &= ~(dot.astype(np.float64) < 0.5 * dist.astype(np.float64))
+    return ok
+
+
+def _kf_case(n_map, n_frame, seed, t):
+    d = synth.map_vs_frame(n_map, n_frame, seed, w=752, h=480)
+    rng = np.random.default_rng(seed + 5)
+    sf = d["scale_factors"]
+    xyz, normal, min_d, max_d = _world_points(d["u"].astype(np.float64), d["v"].astype(np.float64), d["level"], t, rng, sf)
+    P = dict(xyz=xyz, normal=normal, min_dist=min_d, max_dist=max_d, desc=d["mdesc"],
+             bad=(rng.uniform(size=n_map) < 0.03).astype(np.uint8))
+    return d, rng, sf, P
+
+
+def _apply_fuse(best_idx, order_ok, slot_mp, slot_bad, slot_obs, cand_obs, sim3):
+    """The caller's part of Fuse (ORBmatcher.cc:1480-1501 / :1645-1661) on plain arrays, as in host/ORBmatcher_b200.h."""
+    actions, n_fused = [], 0
+    repl = np.full(len(best_idx), -1, np.int32)
+    slot_mp = list(slot_mp)
+    for i in range(len(best_idx)):
+        k = best_idx[i]
+        if k < 0 or not order_ok[i]:
+            continue
+        holder = slot_mp[k]
+        if holder is not None:
+            kind, hid = holder
+            h_bad = slot_bad[hid] if kind == "slot" else False
+            if not h_bad:
+                if sim3:
+                    repl[i] = hid if kind == "slot" else -100 - hid
+                else:
+                    h_id = 1000000 + hid if kind == "slot" else hid
+                    h_obs = slot_obs[hid] if kind == "slot" else cand_obs[hid]
+                    actions.append((1, i, h_id) if h_obs > cand_obs[i] else (1, h_id, i))
+        else:
+            actions += [(2, i, k), (3, i, k)]
+            slot_mp[k] = ("cand", i)
+        n_fused += 1
+    return n_fused, np.array(actions, np.int32).reshape(-1, 3), repl
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False)])
+def test_fuse_vs_reference(seed, stereo):
+    """ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>&, th, bRight=false), ORBmatcher.cc:1326-1534."""
+    n_map, n_frame, th = 3000, 1500, 3.0
+    t = (0.21, -0.13, 0.4)
+    d, rng, sf, P = _kf_case(n_map, n_frame, seed, t)
+    P.update(has=(rng.uniform(size=n_map) < 0.97).astype(np.uint8), in_kf=(rng.uniform(size=n_map) < 0.05).astype(np.uint8),
+             nobs=rng.integers(1, 6, n_map).astype(np.int32))
+    mbf = F32(40.0)
+    uright = (np.where(rng.uniform(size=n_frame) < 0.5, d["keys"]["x"] - 5 + rng.normal(0, 1.5, n_frame), -1).astype(F32)
+              if stereo else np.full(n_frame, -1, F32))
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    R.set_bounds(bounds)
+    kf = R.RefFrame(d["keys"], d["fdesc"], sf, uright=uright, mbf=mbf)
+    R.set_camera(kf, *CAM)
+    kf.set_pose(t)
+    state = rng.choice(3, n_frame, p=[0.6, 0.3, 0.1])          # keyframe slot: empty / good point / bad point
+    slot_obs = rng.integers(1, 6, n_frame).astype(np.int32)
+    kf.set_mappoints(state > 0, nobs=slot_obs, bad=(state == 2))
+    rn, ractions = R.fuse(kf, P, th)
+
+    pc, u, v, invz, po, dist = _project_kf(P["xyz"], t)
+    ok = _kf_valid(pc, u, v, po, dist, P, (0, 0, 752, 480)) & (P["has"] > 0) & (P["bad"] == 0) & (P["in_kf"] == 0)
+    lvl = np.array([R.kf_predict_scale(kf, P["max_dist"][i], dist[i]) if ok[i] else 0 for i in range(n_map)], np.int32)
+    pts = dict(u=u, v=v, ur=(u - (mbf * invz).astype(F32)).astype(F32), radius=(F32(th) * sf[lvl]).astype(F32),
+               min_level=lvl - 1, max_level=lvl, valid=ok.astype(np.uint8), desc=P["desc"])
+    inv_sigma2 = (F32(1.0) / (sf * sf)).astype(F32)
+    bi, bd = O.search_window(d["keys"], d["fdesc"], uright, bounds, pts, 50, True, inv_sigma2)
+    slot_mp = [("slot", i) if state[i] > 0 else None for i in range(n_frame)]
+    n, actions, _ = _apply_fuse(bi, ok, slot_mp, state == 2, slot_obs, P["nobs"], sim3=False)
+    assert rn == n and n > 200
+    assert np.array_equal(ractions, actions)
+    assert (actions[:, 0] == 1).sum() > 20 and (actions[:, 0] == 3).sum() > 20
+
+
+def test_fuse_sim3_vs_reference():
+    """ORBmatcher::Fuse(KeyFrame*, Sim3f& Scw, vpPoints, th, vpReplacePoint), ORBmatcher.cc:1536-1688."""
+    n_map, n_frame, th = 3000, 1500, 4.0
+    scw = (F32(1.25), F32(0.3), F32(-0.2), F32(0.55))
+    t_eff = tuple(float(F32(c) / scw[0]) for c in scw[1:])
+    d, rng, sf, P = _kf_case(n_map, n_frame, 7, t_eff)
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    R.set_bounds(bounds)
+    kf = R.RefFrame(d["keys"], d["fdesc"], sf)
+    R.set_camera(kf, *CAM)
+    state = rng.choice(3, n_frame, p=[0.6, 0.3, 0.1])
+    kf.set_mappoints(state > 0, bad=(state == 2))
+    rn, rrepl, ractions = R.fuse_sim3(kf, scw, P, th)
+
+    pc, u, v, invz, po, dist = _project_kf(P["xyz"], scw[1:], with_sim3_scale=scw[0])
+    ok = _kf_valid(pc, u, v, po, dist, P, (0, 0, 752, 480)) & (P["bad"] == 0)
+    lvl = np.array([R.kf_predict_scale(kf, P["max_dist"][i], dist[i]) if ok[i] else 0 for i in range(n_map)], np.int32)
+    pts = dict(u=u, v=v, radius=(F32(th) * sf[lvl]).astype(F32), min_level=lvl - 1, max_level=lvl, valid=ok.astype(np.uint8),
+               desc=P["desc"])
+    bi, bd = O.search_window(d["keys"], d["fdesc"], None, bounds, pts, 50, False, None)
+    slot_mp = [("slot", i) if state[i] > 0 else None for i in range(n_frame)]
+    n, actions, repl = _apply_fuse(bi, ok, slot_mp, state == 2, None, None, sim3=True)
+    assert rn == n and n > 200
+    # a candidate that lands on a slot filled earlier in the same call by another candidate: the reference stores
+    # that candidate's pointer; the driver reports it as (id - 1000000), mirror it
+    repl_ref_view = np.where(repl <= -100, (-100 - repl) - 1000000, repl)
+    assert np.array_equal(rrepl, repl_ref_view) and np.array_equal(ractions, actions)
+    assert (repl >= 0).sum() > 20
+
+
+@pytest.mark.parametrize("ratio", [1.0, 1.5])
+def test_search_by_projection_sim3_vs_reference(ratio):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming), ORBmatcher.cc:496-610."""
+    n_map, n_frame, th = 4000, 1500, 8
+    scw = (F32(0.8), F32(-0.4), F32(0.1), F32(0.3))
+    t_eff = tuple(float(F32(c) / scw[0]) for c in scw[1:])
+    d, rng, sf, P = _kf_case(n_map, n_frame, 9, t_eff)
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    R.set_bounds(bounds)
+    kf = R.RefFrame(d["keys"], d["fdesc"], sf)
+    R.set_camera(kf, *CAM)
+    matched = (rng.uniform(size=n_frame) < 0.2).astype(np.uint8)
+    rn, rslots = R.search_kf_sim3(kf, scw, P, matched, th, ratio)
+
+    pc, u, v, invz, po, dist = _project_kf(P["xyz"], scw[1:], with_sim3_scale=scw[0])
+    ok = _kf_valid(pc, u, v, po, dist, P, (0, 0, 752, 480)) & (P["bad"] == 0)
+    lvl = np.array([R.kf_predict_scale(kf, P["max_dist"][i], dist[i]) if ok[i] else 0 for i in range(n_map)], np.int32)
+    pts = dict(u=u, v=v, ur=np.zeros(n_map, F32), radius=(F32(th) * sf[lvl]).astype(F32), min_level=lvl - 1, max_level=lvl,
+               angle=np.zeros(n_map, F32), valid=ok.astype(np.uint8), blocks=np.ones(n_map, np.uint8), desc=P["desc"])
+    th_acc = int(np.floor(F32(50) * F32(ratio)))
+    n, asg, _, _ = O.search_by_projection(d["keys"], d["fdesc"], None, bounds, pts, 2, th_acc, 1.0, False, matched,
+                                          np.full(n_frame, UNTOUCHED, np.int32), sf)
+    assert rn == n and n > 200
+    assert np.array_equal(rslots, asg)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_search_by_sim3_vs_reference(seed):
+    """ORBmatcher::SearchBySim3, ORBmatcher.cc:1690-1940."""
+    from oracle.oracle import KP_DTYPE
+    n1, n2, th = 1800, 2100, 7.5
+    fx, fy, cx, cy = CAM
+    rng = np.random.default_rng(seed + 40)
+    d = synth.map_vs_frame(n1, n2, seed + 30, w=752, h=480)      # KF2 = the "frame", KF1's points = the "map"
+    sf = d["scale_factors"]
+    k2, d2 = d["keys"], d["fdesc"]
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"], k1["y"], k1["octave"] = d["u"], d["v"], d["level"]
+    desc1 = d["mdesc"]
+    t1w, t2w = np.array([0.1, 0.05, -0.2], F32), np.array([-0.3, 0.1, 0.25], F32)
+    s12 = (F32(1.1), F32(0.35), F32(-0.1), F32(0.4))
+    s, t12 = s12[0], np.array(s12[1:], F32)
+    s21 = F32(1.0) / s
+    t21 = np.array([-t12[0] / s, -t12[1] / s, -t12[2] / s], F32)
+
+    def world_for(u, v, lvl, t_cam_from_world, sim_s, sim_t):
+        """World points whose image in the OTHER keyframe (through the similarity) lands near (u, v)."""
+        m = len(u)
+        z = rng.uniform(2.0, 12.0, m); z[::47] = -1.0
+        pc_other = np.stack([(u - float(cx)) * z / float(fx), (v - float(cy)) * z / float(fy), z], 1)
+        pc_own = (pc_other - sim_t.astype(np.float64)) / float(sim_s)
+        xyz = (pc_own - t_cam_from_world.astype(np.float64)).astype(F32)
+        dist = np.linalg.norm(pc_other, axis=1)
+        max_d = (dist * 1.2 ** (lvl - 0.5)).astype(F32); max_d[::29] *= F32(0.3)
+        return xyz, (max_d / F32(sf[-1])).astype(F32), max_d
+
+    def mirror(xyz, t_own, sim_s, sim_t):
+        p_own = (xyz + t_own).astype(F32)
+        p_oth = ((p_own * sim_s).astype(F32) + sim_t).astype(F32)
+        with np.errstate(all="ignore"):
+            invz = (1.0 / p_oth[:, 2].astype(np.float64)).astype(F32)
+        x, y = (p_oth[:, 0] * invz).astype(F32), (p_oth[:, 1] * invz).astype(F32)
+        u, v = ((fx * x).astype(F32) + cx).astype(F32), ((fy * y).astype(F32) + cy).astype(F32)
+        dist = np.sqrt((p_oth[:, 0] * p_oth[:, 0] + p_oth[:, 1] * p_oth[:, 1]) + p_oth[:, 2] * p_oth[:, 2]).astype(F32)
+        return p_oth, u, v, dist
+
+    # KF1's map points -> KF2 through S21; KF2's map points -> KF1 through S12 (near their KF1 source keypoint, if any)
+    xyz1, min1, max1 = world_for(d["u"].astype(np.float64), d["v"].astype(np.float64), d["level"], t1w, s21, t21)
+    back = np.full(n2, -1)
+    for i1 in range(n1):
+        if d["src"][i1] >= 0:
+            back[d["src"][i1]] = i1
+    u21 = rng.uniform(0, 752, n2); v21 = rng.uniform(0, 480, n2)
+    hasb = back >= 0
+    u21[hasb] = k1["x"][back[hasb]] + rng.normal(0, 2, hasb.sum()); v21[hasb] = k1["y"][back[hasb]] + rng.normal(0, 2, hasb.sum())
+    lvl2 = np.clip(k2["octave"] + (rng.uniform(size=n2) < 0.2), 0, 7).astype(np.int32)
+    xyz2, min2, max2 = world_for(u21, v21, lvl2, t2w, s, t12)
+    has1, has2 = rng.uniform(size=n1) < 0.9, rng.uniform(size=n2) < 0.9
+    bad1, bad2 = rng.uniform(size=n1) < 0.03, rng.uniform(size=n2) < 0.03
+    pre12 = np.full(n1, -1, np.int32)
+    cand = np.flatnonzero(has2 & ~bad2)
+    pre_idx = rng.choice(n1, 60, replace=False)
+    pre12[pre_idx] = rng.choice(cand, 60, replace=False)
+
+    bounds = (0.0, 0.0, 752.0, 480.0)
+    R.set_bounds(bounds)
+    kf1, kf2 = R.RefFrame(k1, desc1, sf), R.RefFrame(k2, d2, sf)
+    for kf, t, has, bad, xyz, mn, mx, desc in ((kf1, t1w, has1, bad1, xyz1, min1, max1, desc1), (kf2, t2w, has2, bad2, xyz2, min2, max2, d2)):
+        R.set_camera(kf, *CAM)
+        kf.set_pose(t)
+        kf.set_mappoints(has, xyz=xyz, desc=desc, bad=bad, min_dist=mn, max_dist=mx)
+    rn, rout = R.search_by_sim3(kf1, kf2, s12, pre12, th)
+
+    def side(xyz, t_own, sim_s, sim_t, has, bad, already, mn, mx, kf_other, desc):
+        p, u, v, dist = mirror(xyz, t_own, sim_s, sim_t)
+        ok = has & ~already & ~bad & ~(p[:, 2] < 0) & (u >= 0) & (u < 752) & (v >= 0) & (v < 480)
+        ok &= ~((dist < F32(0.8) * mn) | (dist > F32(1.2) * mx))
+        lvl = np.array([R.kf_predict_scale(kf_other, mx[i], dist[i]) if ok[i] else 0 for i in range(len(u))], np.int32)
+        return dict(u=u, v=v, radius=(F32(th) * sf[lvl]).astype(F32), min_level=lvl - 1, max_level=lvl,
+                    valid=ok.astype(np.uint8), desc=desc)
+    already1 = pre12 >= 0
+    already2 = np.zeros(n2, bool); already2[pre12[pre12 >= 0]] = True
+    pts12 = side(xyz1, t1w, s21, t21, has1, bad1, already1, min1, max1, kf2, desc1)
+    pts21 = side(xyz2, t2w, s, t12, has2, bad2, already2, min2, max2, kf1, d2)
+    n, m12 = O.search_by_sim3(k1, desc1, k2, d2, bounds, pts12, pts21, 100)
+    expect = np.where(m12 >= 0, m12, pre12)          # vpMatches12 keeps its earlier entries
+    assert rn == n and n > 150
+    assert np.array_equal(rout, expect)

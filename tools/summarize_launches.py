@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel (count, total,
-share of the step, average).  Usage: summarize_launches.py launches.csv [skip_first_n]"""
+share of the step, average).  Usage: summarize_launches.py launches.csv [skip_first_n [count]]"""
 import collections
 import csv
 import sys
@@ -9,8 +9,9 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+count = int(sys.argv[3]) if len(sys.argv) > 3 else len(rows)
 agg = collections.OrderedDict()
-for r in rows[1 + skip:]:
+for r in rows[1 + skip:1 + skip + count]:
     try:
         v = float(r[vi].replace(",", ""))
     except ValueError:
