@@ -260,6 +260,66 @@ int orbfe_search_by_sim3(const OrbfeFrameView* kf1, const OrbfeFrameView* kf2,
                          const OrbfeProjPoints* pts12, const OrbfeProjPoints* pts21, int th_accept,
                          int32_t* match12, int device);
 
+/* ---- Bag of words ------------------------------------------------------------
+ * ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h:30-31).
+ * orbfe_vocabulary_create uploads the tree: node 0 is the root, node i > 0 has parent[i], descriptor
+ * desc[32*i..] and weight[i] (the leaf weight; ORBvoc.txt columns, TemplatedVocabulary.h:1379-1417).  A
+ * node's children are ordered by ascending id, as loadFromTextFile (:1390) and HKmeansStep push them;
+ * leaves (= nodes without children) get word ids in node order (:1409-1416). */
+typedef struct OrbfeVocabulary OrbfeVocabulary;
+int orbfe_vocabulary_create(int k, int L, int n_nodes, const int32_t* parent, const uint8_t* desc,
+                            const double* weight, int device, OrbfeVocabulary** out);
+void orbfe_vocabulary_destroy(OrbfeVocabulary* voc);
+
+/* Per feature, TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup)
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1226-1258, distance = FORB::distance, FORB.cpp:81-101):
+ * the word the descriptor falls into, its weight, and the node on level L - levelsup of the path
+ * (0 when that level is <= 0; -1 when the leaf lies above it, where the reference leaves it
+ * uninitialised).  The caller folds the three arrays into DBoW2::BowVector / FeatureVector exactly like
+ * transform(features, v, fv, levelsup) (:1125-1197): for i in order, if weight[i] > 0:
+ * v.addWeight(word_id[i], weight[i]); fv.addFeature(node_id[i], i); then v.normalize(L1)
+ * (host/ORBmatcher_b200.h: ComputeBoW).  Replaces the descriptor loop of Frame::ComputeBoW
+ * (src/Frame.cc:984-998) and KeyFrame::ComputeBoW (src/KeyFrame.cc:101-111).  Host pointers. */
+int orbfe_bow_transform(OrbfeVocabulary* voc, const uint8_t* desc, int n, int levelsup,
+                        int32_t* word_id, double* weight, int32_t* node_id);
+/* Same with device pointers on `stream` (cudaStream_t), no synchronisation. */
+int orbfe_bow_transform_device(OrbfeVocabulary* voc, const uint8_t* d_desc, int n, int levelsup,
+                               int32_t* d_word_id, double* d_weight, int32_t* d_node_id,
+                               void* stream);
+
+/* DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) flattened in map order: node ids ascending,
+ * features of node j = feat[start[j] .. start[j+1]) in push_back order. */
+typedef struct OrbfeFeatureVector {
+    int32_t n_nodes;
+    const int32_t* node_id;
+    const int32_t* start; /* n_nodes + 1 */
+    const int32_t* feat;
+} OrbfeFeatureVector;
+
+/* One side of a BoW search: mDescriptors, keypoint angles (rotation histogram; may be NULL when
+ * check_orientation == 0), valid[i] (may be NULL = all) and mFeatVec. */
+typedef struct OrbfeBowSide {
+    int32_t n;
+    const uint8_t* desc;
+    const float* angle;
+    const uint8_t* valid;
+    OrbfeFeatureVector fv;
+} OrbfeBowSide;
+
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ *     include/ORBmatcher.h:58, src/ORBmatcher.cc:260-494:  a = pKF (valid[i] = vpMapPointsKF[i] is a good point),
+ *     b = F (valid NULL), th_low = TH_LOW, strict = 0, n_left_b = F.Nleft;
+ * int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ *     include/ORBmatcher.h:59, src/ORBmatcher.cc:893-1044:  a = pKF1, b = pKF2 (valid = good map point, and
+ *     index < mvKeysUn.size() for fisheye keyframes), strict = 1 (`bestDist1 < TH_LOW`, :973), n_left_b = -1.
+ * match_a[ia] = index in b matched to a's feature ia after the rotation-histogram cull, else -1;
+ * match_a_right[ia] = the right-camera match of the fisheye branch (:374-407), required iff n_left_b != -1.
+ * The caller stores vpMapPointMatches[match_a[ia]] = vpMapPointsKF[ia] (and the right one), resp.
+ * vpMatches12[ia] = vpMapPoints2[match_a[ia]].  Returns nmatches. */
+int orbfe_search_by_bow(const OrbfeBowSide* a, const OrbfeBowSide* b, int th_low, int strict,
+                        float nnratio, int check_orientation, int n_left_b, int32_t* match_a,
+                        int32_t* match_a_right, int device);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

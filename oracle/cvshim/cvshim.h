@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "../cvprims.h"
@@ -223,6 +225,31 @@ inline double norm(const Mat& a, const Mat& b, int normType) {
     }
     return (double)s;
 }
+
+// cv::FileStorage / cv::FileNode: DBoW2's TemplatedVocabulary.h has YAML save/load members (virtual, so they
+// must compile) next to the text-file loader ORB-SLAM3 actually uses (System.cc:105 loadFromTextFile); here
+// they only have to compile and are never called.
+struct FileNode {
+    enum { NONE = 0, SEQ = 5, MAP = 6 };
+    FileNode operator[](const char*) const { abort(); }
+    FileNode operator[](const std::string&) const { abort(); }
+    FileNode operator[](int) const { abort(); }
+    operator int() const { abort(); }
+    operator double() const { abort(); }
+    operator std::string() const { abort(); }
+    size_t size() const { abort(); }
+    int type() const { abort(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage(const char*, int) {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { abort(); }
+    FileNode operator[](const std::string&) const { abort(); }
+    template <class T> FileStorage& operator<<(const T&) { abort(); }
+};
 
 // Only named by the reference's dead ComputeKeyPointsOld (call commented out at
 // src/ORBextractor.cc:1580); never executed.

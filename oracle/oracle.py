@@ -333,3 +333,61 @@ def search_by_sim3(keys1, desc1, keys2, desc2, bounds, pts12, pts21, th_accept=1
     m12 = np.empty(len(keys1), np.int32)
     n = lib().oracle_search_by_sim3(C.byref(f1), C.byref(f2), C.byref(pps[0]), C.byref(pps[1]), int(th_accept), _p(m12))
     return n, m12
+
+
+# ---------------------------------------------------------------- bag of words
+class Vocabulary:
+    """DBoW2 vocabulary tree restated (oracle/bow_oracle.cpp).  parent/desc/weight indexed by node id (0 = root)."""
+
+    def __init__(self, k, L, parent, desc, weight, scoring=0, weighting=0):
+        self.k, self.L = k, L
+        self.parent = np.ascontiguousarray(parent, np.int32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.weight = np.ascontiguousarray(weight, np.float64)
+        self.scoring, self.weighting = scoring, weighting
+        lib().oracle_voc_create.restype = C.c_void_p
+        self.h = lib().oracle_voc_create(k, L, scoring, weighting, len(self.parent), _p(self.parent), _p(self.desc),
+                                         _p(self.weight))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().oracle_voc_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def transform_features(self, desc, levelsup):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        word, nid, w = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
+        lib().oracle_bow_transform_features(C.c_void_p(self.h), _p(desc), n, int(levelsup), _p(word), _p(w), _p(nid))
+        return word, w, nid
+
+    def transform(self, desc, levelsup):
+        """-> (word ids, values), (node ids, start, feat): BowVector and FeatureVector in map order."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        ids, vals = np.empty(n + 1, np.uint32), np.empty(n + 1, np.float64)
+        nodes, start, feat = np.empty(n + 1, np.uint32), np.empty(n + 2, np.int32), np.empty(n + 1, np.uint32)
+        nw, nn = C.c_int(0), C.c_int(0)
+        lib().oracle_bow_transform(C.c_void_p(self.h), _p(desc), n, int(levelsup), C.byref(nw), _p(ids), _p(vals),
+                                   C.byref(nn), _p(nodes), _p(start), _p(feat))
+        nw, nn = nw.value, nn.value
+        return (ids[:nw].copy(), vals[:nw].copy()), (nodes[:nn].astype(np.int32), start[:nn + 1].copy(),
+                                                     feat[:start[nn]].astype(np.int32))
+
+
+def search_by_bow(fvA, descA, angleA, validA, fvB, descB, angleB, validB, th_low=50, strict=False, nnratio=0.6,
+                  check_orientation=True, n_left_b=-1):
+    """fvA / fvB = (nodes, start, feat).  -> nmatches, matchA, matchAR."""
+    a = [np.ascontiguousarray(x, np.int32) for x in fvA]
+    b = [np.ascontiguousarray(x, np.int32) for x in fvB]
+    descA = np.ascontiguousarray(descA, np.uint8); descB = np.ascontiguousarray(descB, np.uint8)
+    angleA = np.ascontiguousarray(angleA, np.float32); angleB = np.ascontiguousarray(angleB, np.float32)
+    validA = np.ascontiguousarray(validA, np.uint8)
+    vb = None if validB is None else np.ascontiguousarray(validB, np.uint8)
+    nA, nB = len(descA), len(descB)
+    mA, mR = np.empty(nA, np.int32), np.empty(nA, np.int32)
+    n = lib().oracle_search_by_bow(len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), _p(descA), _p(angleA), _p(validA), nA,
+                                   len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), _p(descB), _p(angleB),
+                                   None if vb is None else _p(vb), nB, int(th_low), int(strict), C.c_float(nnratio),
+                                   int(check_orientation), int(n_left_b), _p(mA), _p(mR))
+    return n, mA, mR

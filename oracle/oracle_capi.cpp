@@ -6,6 +6,7 @@
 #include "../include/orbfe.h"
 #include "cvprims.h"
 #include "match_oracle.h"
+#include "bow_oracle.h"
 #include "orb_oracle.h"
 
 using orb_oracle::Extractor;
@@ -231,6 +232,60 @@ void oracle_stereo_match(void* hl, void* hr, const OrbKp* kl, const uint8_t* dl,
 void oracle_fisheye_matches(const uint8_t* q, int nq, const uint8_t* t, int nt, int* match,
                             int* idx2, int* dist2) {
     match_oracle::fisheye_ratio_matches(q, nq, t, nt, match, idx2, dist2);
+}
+
+
+// ---- bag of words ---------------------------------------------------------------------------------
+void* oracle_voc_create(int k, int L, int scoring, int weighting, int nNodes, const int32_t* parent,
+                        const uint8_t* desc, const double* weight) {
+    bow_oracle::Vocabulary* V = new bow_oracle::Vocabulary();
+    V->build(k, L, scoring, weighting, nNodes, parent, desc, weight);
+    return V;
+}
+void oracle_voc_destroy(void* h) { delete (bow_oracle::Vocabulary*)h; }
+void oracle_bow_transform_features(void* h, const uint8_t* desc, int n, int levelsup, int32_t* word, double* weight,
+                                   int32_t* nid) {
+    const bow_oracle::Vocabulary& V = *(bow_oracle::Vocabulary*)h;
+    for (int i = 0; i < n; i++) {
+        int w, nd;
+        bow_oracle::transform_feature(V, desc + 32 * (size_t)i, levelsup, w, weight[i], nd);
+        word[i] = w; nid[i] = nd;
+    }
+}
+// BowVector as (ids, values), FeatureVector as CSR (nodes, start, feat); caps: n entries each (+1 for start).
+void oracle_bow_transform(void* h, const uint8_t* desc, int n, int levelsup, int32_t* nWords, uint32_t* ids,
+                          double* values, int32_t* nNodes, uint32_t* nodes, int32_t* start, uint32_t* feat) {
+    const bow_oracle::Vocabulary& V = *(bow_oracle::Vocabulary*)h;
+    std::map<unsigned, double> bow;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    bow_oracle::transform(V, desc, n, levelsup, bow, fv);
+    int i = 0;
+    for (auto& e : bow) { ids[i] = e.first; values[i] = e.second; i++; }
+    *nWords = i;
+    int j = 0, p = 0;
+    for (auto& e : fv) {
+        nodes[j] = e.first; start[j] = p;
+        for (unsigned f : e.second) feat[p++] = f;
+        j++;
+    }
+    start[j] = p;
+    *nNodes = j;
+}
+static bow_oracle::FeatVec fill_fv(int nn, const int32_t* node, const int32_t* start, const int32_t* feat) {
+    bow_oracle::FeatVec f;
+    f.node.assign(node, node + nn);
+    f.start.assign(start, start + nn + 1);
+    f.feat.assign(feat, feat + start[nn]);
+    return f;
+}
+int oracle_search_by_bow(int nnA, const int32_t* nodeA, const int32_t* startA, const int32_t* featA, const uint8_t* descA,
+                         const float* angleA, const uint8_t* validA, int nA, int nnB, const int32_t* nodeB,
+                         const int32_t* startB, const int32_t* featB, const uint8_t* descB, const float* angleB,
+                         const uint8_t* validB, int nB, int thLow, int strict, float nnratio, int checkOri, int nLeftB,
+                         int32_t* matchA, int32_t* matchAR) {
+    const bow_oracle::FeatVec fa = fill_fv(nnA, nodeA, startA, featA), fb = fill_fv(nnB, nodeB, startB, featB);
+    const bow_oracle::BowSearchParams prm{thLow, strict, nnratio, checkOri, nLeftB};
+    return bow_oracle::search_by_bow(fa, descA, angleA, validA, nA, fb, descB, angleB, validB, nB, prm, matchA, matchAR);
 }
 
 }  // extern "C"

@@ -285,3 +285,55 @@ def search_by_sim3(kf1, kf2, s12, pre12, th):
     n = mlib().refm_search_by_sim3(C.c_void_p(kf1.h), C.c_void_p(kf2.h), _f(s12[0]), _f(s12[1]), _f(s12[2]), _f(s12[3]),
                                    _p(pre12), _f(th), _p(out))
     return n, out
+
+
+# ---- DBoW2 itself (compiled verbatim into libref_orbmatcher.so) and the reference's SearchByBoW ------------
+class RefVocabulary:
+    def __init__(self, path):
+        mlib().refd_voc_load.restype = C.c_void_p
+        self.h = mlib().refd_voc_load(path.encode())
+        if not self.h:
+            raise RuntimeError("loadFromTextFile failed: " + path)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            mlib().refd_voc_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def size(self):
+        return mlib().refd_voc_size(C.c_void_p(self.h))
+
+    def transform_features(self, desc, levelsup):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        word, nid, w = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
+        mlib().refd_voc_transform_features(C.c_void_p(self.h), _p(desc), n, int(levelsup), _p(word), _p(w), _p(nid))
+        return word, w, nid
+
+    def transform(self, desc, levelsup):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        ids, vals = np.empty(n + 1, np.uint32), np.empty(n + 1, np.float64)
+        nodes, start, feat = np.empty(n + 1, np.uint32), np.empty(n + 2, np.int32), np.empty(n + 1, np.uint32)
+        nw, nn = C.c_int(0), C.c_int(0)
+        mlib().refd_voc_transform(C.c_void_p(self.h), _p(desc), n, int(levelsup), C.byref(nw), _p(ids), _p(vals),
+                                  C.byref(nn), _p(nodes), _p(start), _p(feat))
+        nw, nn = nw.value, nn.value
+        return (ids[:nw].copy(), vals[:nw].copy()), (nodes[:nn].astype(np.int32), start[:nn + 1].copy(),
+                                                     feat[:start[nn]].astype(np.int32))
+
+
+def compute_bow(frame, voc, levelsup=4):
+    mlib().refm_frame_compute_bow(C.c_void_p(frame.h), C.c_void_p(voc.h), int(levelsup))
+
+
+def search_by_bow_kf_f(kf, f, nnratio, check_ori):
+    out = np.empty(f.n, np.int32)
+    n = mlib().refm_search_by_bow_kf_f(C.c_void_p(kf.h), C.c_void_p(f.h), _f(nnratio), int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_bow_kf_kf(kf1, kf2, nnratio, check_ori):
+    out = np.empty(kf1.n, np.int32)
+    n = mlib().refm_search_by_bow_kf_kf(C.c_void_p(kf1.h), C.c_void_p(kf2.h), _f(nnratio), int(check_ori), _p(out))
+    return n, out

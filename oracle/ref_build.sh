@@ -13,7 +13,7 @@ if [ ! -f "$REF/src/ORBextractor.cc" ]; then
     exit 0
 fi
 mkdir -p "$HERE/_ref"
-${CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
+${ORACLE_CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
     -I"$HERE/cvshim" -I"$REF/include" \
     "$REF/src/ORBextractor.cc" "$HERE/ref_driver.cpp" "$HERE/cvprims.cpp" \
     -o "$HERE/_ref/libref_orbextractor.so"
@@ -22,12 +22,17 @@ echo "built $HERE/_ref/libref_orbextractor.so"
 # The reference's matcher functions (ORBmatcher::SearchByProjection x3, SearchForInitialization,
 # DescriptorDistance, Frame::GetFeaturesInArea / ComputeStereoMatches, MapPoint::PredictScale): their files
 # need Eigen/Sophus/DBoW2/g2o as a whole, so ref_slices.py cuts those function bodies out of the tree into a
-# temporary translation unit, compiled verbatim against oracle/refshim and deleted afterwards.
+# temporary translation unit, compiled verbatim against oracle/refshim and deleted afterwards.  The vendored
+# DBoW2 (Thirdparty/DBoW2: BowVector, FeatureVector, FORB, ScoringObject, TemplatedVocabulary.h, DUtils/Random, DUtils/Timestamp)
+# compiles as whole files; only Boost.Serialization headers and cv::FileStorage are stubbed.
 TMP="$(mktemp -d)"
 trap 'rm -rf "$TMP"' EXIT
 python3 "$HERE/ref_slices.py" "$REF" "$TMP/ref_matcher_slices.cc"
-${CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
-    -I"$HERE/refshim" -I"$HERE/cvshim" -I"$REF/include" \
+${ORACLE_CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
+    -I"$HERE/refshim" -I"$HERE/cvshim" -I"$REF/include" -I"$REF" \
     "$TMP/ref_matcher_slices.cc" "$REF/src/ORBextractor.cc" "$HERE/ref_match_driver.cpp" "$HERE/cvprims.cpp" \
+    "$REF/Thirdparty/DBoW2/DBoW2/BowVector.cpp" "$REF/Thirdparty/DBoW2/DBoW2/FeatureVector.cpp" \
+    "$REF/Thirdparty/DBoW2/DBoW2/FORB.cpp" "$REF/Thirdparty/DBoW2/DBoW2/ScoringObject.cpp" \
+    "$REF/Thirdparty/DBoW2/DUtils/Random.cpp" "$REF/Thirdparty/DBoW2/DUtils/Timestamp.cpp" \
     -o "$HERE/_ref/libref_orbmatcher.so"
 echo "built $HERE/_ref/libref_orbmatcher.so"

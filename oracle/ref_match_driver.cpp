@@ -13,6 +13,8 @@
 
 #include "refshim.h"
 #include "ORBmatcher.h"
+#include "Thirdparty/DBoW2/DBoW2/FORB.h"
+#include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
 
 using namespace ORB_SLAM3;
 
@@ -389,6 +391,102 @@ int refm_stereo(const uint8_t* imgL, const uint8_t* imgR, int rows, int cols, in
     }
     for (int i = 0; i < nR; i++) { keysR[i] = F.mvKeysRight[i]; memcpy(descR + 32 * (size_t)i, F.mDescriptorsRight.ptr(i), 32); }
     return F.N;
+}
+
+
+// ---- bag of words: DBoW2 itself (include/ORBVocabulary.h:30-31 typedef) ------------------------------------
+typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary;
+
+void* refd_voc_load(const char* path) {
+    ORBVocabulary* v = new ORBVocabulary();
+    if (!v->loadFromTextFile(path)) { delete v; return nullptr; }   // System.cc:105
+    return v;
+}
+void refd_voc_destroy(void* h) { delete (ORBVocabulary*)h; }
+int refd_voc_size(void* h) { return (int)((ORBVocabulary*)h)->size(); }
+
+static std::vector<cv::Mat> to_descriptor_vector(const uint8_t* desc, int n, cv::Mat& hold) {
+    hold = wrap_desc(desc, n);
+    std::vector<cv::Mat> v;                       // Converter::toDescriptorVector, src/Converter.cc:27-39
+    for (int j = 0; j < n; j++) v.push_back(hold.row(j));
+    return v;
+}
+
+// per feature: word id (public transform), its weight, and the node `levelsup` levels above the word
+void refd_voc_transform_features(void* h, const uint8_t* desc, int n, int levelsup, int* word, double* weight, int* nid) {
+    ORBVocabulary* voc = (ORBVocabulary*)h;
+    cv::Mat hold;
+    std::vector<cv::Mat> v = to_descriptor_vector(desc, n, hold);
+    for (int i = 0; i < n; i++) {
+        const DBoW2::WordId w = voc->transform(v[i]);
+        word[i] = (int)w; weight[i] = voc->getWordWeight(w); nid[i] = (int)voc->getParentNode(w, levelsup);
+    }
+}
+
+static void flatten_fv(const DBoW2::FeatureVector& fv, int* nNodes, unsigned* nodes, int* start, unsigned* feat) {
+    int j = 0, p = 0;
+    for (auto& e : fv) {
+        nodes[j] = e.first; start[j] = p;
+        for (unsigned f : e.second) feat[p++] = f;
+        j++;
+    }
+    start[j] = p;
+    *nNodes = j;
+}
+
+// Frame::ComputeBoW (src/Frame.cc:984-998): transform(vCurrentDesc, mBowVec, mFeatVec, 4)
+void refd_voc_transform(void* h, const uint8_t* desc, int n, int levelsup, int* nWords, unsigned* ids, double* values,
+                        int* nNodes, unsigned* nodes, int* start, unsigned* feat) {
+    ORBVocabulary* voc = (ORBVocabulary*)h;
+    cv::Mat hold;
+    std::vector<cv::Mat> v = to_descriptor_vector(desc, n, hold);
+    DBoW2::BowVector bow;
+    DBoW2::FeatureVector fv;
+    voc->transform(v, bow, fv, levelsup);
+    int i = 0;
+    for (auto& e : bow) { ids[i] = e.first; values[i] = e.second; i++; }
+    *nWords = i;
+    flatten_fv(fv, nNodes, nodes, start, feat);
+}
+
+// ComputeBoW on a RefFrame (frame and keyframe view) with the given vocabulary
+void refm_frame_compute_bow(void* fh, void* vh, int levelsup) {
+    RefFrame* rf = (RefFrame*)fh;
+    ORBVocabulary* voc = (ORBVocabulary*)vh;
+    std::vector<cv::Mat> v;
+    for (int j = 0; j < rf->F.N; j++) v.push_back(rf->F.mDescriptors.row(j));
+    voc->transform(v, rf->F.mBowVec, rf->F.mFeatVec, levelsup);
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches):
+// out[i] (size F.N) = keyframe slot whose map point is now in vpMapPointMatches[i], or -1.
+int refm_search_by_bow_kf_f(void* kfh, void* fh, float nnratio, int checkOri, int* out) {
+    RefFrame *rk = (RefFrame*)kfh, *rf = (RefFrame*)fh;
+    KeyFrame* kf = as_keyframe(rk);
+    kf->mFeatVec = rk->F.mFeatVec;
+    kf->mpCamera2 = (rk->F.Nleft != -1) ? &rk->cam : nullptr;     // :357, :380: stereo-fisheye keyframes have a second camera
+    rf->F.mpCamera2 = (rf->F.Nleft != -1) ? &rf->cam : nullptr;
+    std::vector<MapPoint*> matches;
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(kf, rf->F, matches);
+    for (int i = 0; i < rf->F.N; i++) out[i] = matches[i] ? matches[i]->id - 1000000 : -1;
+    return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12):
+// out[i1] = KF2 slot of the point in vpMatches12[i1], or -1.
+int refm_search_by_bow_kf_kf(void* h1, void* h2, float nnratio, int checkOri, int* out) {
+    RefFrame *r1 = (RefFrame*)h1, *r2 = (RefFrame*)h2;
+    KeyFrame* k1 = as_keyframe(r1);
+    KeyFrame* k2 = as_keyframe(r2);
+    k1->mFeatVec = r1->F.mFeatVec; k2->mFeatVec = r2->F.mFeatVec;
+    for (int i = 0; i < k2->N; i++)
+        if (k2->mvpMapPoints[i]) k2->mvpMapPoints[i]->id = 2000000 + i;
+    std::vector<MapPoint*> m12;
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchByBoW(k1, k2, m12);
+    for (int i = 0; i < k1->N; i++) out[i] = m12[i] ? m12[i]->id - 2000000 : -1;
+    return n;
 }
 
 }  // extern "C"

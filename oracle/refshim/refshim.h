@@ -22,6 +22,9 @@
 #include <opencv2/core/core.hpp>
 
 #include "ORBextractor.h"
+// DBoW2's own headers (the reference vendors DBoW2; Boost.Serialization is stubbed in refshim/boost)
+#include "Thirdparty/DBoW2/DBoW2/BowVector.h"
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
 
 using namespace std;  // the reference's headers rely on this leaking from its own includes
 
@@ -172,6 +175,8 @@ class KeyFrame {
     std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
     std::vector<MapPoint*> mvpMapPoints;
     Sophus::SE3f mTcw;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
 };
 
 inline void MapPoint::Replace(MapPoint* pMP) { g_refActions.push_back({1, id, pMP->id}); }
@@ -211,6 +216,9 @@ class Frame {
     std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 
     Sophus::SE3f mTcw, mTrl;
+    DBoW2::BowVector mBowVec;
+    DBoW2::FeatureVector mFeatVec;
+    GeometricCamera* mpCamera2 = nullptr;
 };
 
 }  // namespace ORB_SLAM3

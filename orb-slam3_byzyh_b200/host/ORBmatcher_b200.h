@@ -9,6 +9,7 @@
 #define ORBMATCHER_B200_H
 
 #include <cmath>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -186,6 +187,126 @@ inline int SearchByProjectionSim3(const KeyFrameView& kf, const ProjPoints& pts,
     OrbfeSearchParams prm = {ORBFE_SEARCH_KEYFRAME, (int32_t)std::floor((float)thLow * ratioHamming), 1.0f, 0};
     const int n = orbfe_search_by_projection(&fv, &pp, &prm, matched.data(), assigned.data(), nullptr, nullptr, device());
     if (n < 0) throw std::runtime_error(std::string("SearchByProjection Sim3 (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// ---- Bag of words --------------------------------------------------------------------------------------------
+// ORBVocabulary (include/ORBVocabulary.h:30-31) with the tree in HBM.  transform() has the signature of
+// DBoW2::TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) and is generic over the two
+// map types (DBoW2::BowVector = std::map<WordId, WordValue>, DBoW2::FeatureVector = std::map<NodeId, vector<unsigned>>),
+// so this header does not need DBoW2's own headers; Frame::ComputeBoW (Frame.cc:984-998) and KeyFrame::ComputeBoW
+// (KeyFrame.cc:101-111) call it with mDescriptors instead of the vector<cv::Mat> copy.
+class ORBVocabulary {
+   public:
+    ORBVocabulary() {}
+    ~ORBVocabulary() { orbfe_vocabulary_destroy(h_); }
+    ORBVocabulary(const ORBVocabulary&) = delete;
+    ORBVocabulary& operator=(const ORBVocabulary&) = delete;
+
+    // ORBvoc.txt (TemplatedVocabulary::loadFromTextFile, :1338-1424; called at System.cc:105)
+    bool loadFromTextFile(const std::string& filename) {
+        FILE* f = fopen(filename.c_str(), "r");
+        if (!f) return false;
+        int n1 = 0, n2 = 0;
+        if (fscanf(f, "%d %d %d %d", &k_, &L_, &n1, &n2) != 4 || k_ < 0 || k_ > 20 || L_ < 1 || L_ > 10 || n1 < 0 || n1 > 5 ||
+            n2 < 0 || n2 > 3) { fclose(f); return false; }
+        scoring_ = n1; weighting_ = n2;
+        std::vector<int32_t> parent(1, 0);
+        std::vector<uint8_t> desc(32, 0);
+        std::vector<double> weight(1, 0.0);
+        for (;;) {
+            int pid, leaf;
+            if (fscanf(f, "%d %d", &pid, &leaf) != 2) break;     // a trailing empty line ends the file here
+            parent.push_back(pid);
+            for (int i = 0; i < 32; i++) { int b = 0; if (fscanf(f, "%d", &b) != 1) b = 0; desc.push_back((uint8_t)b); }
+            double w = 0;
+            if (fscanf(f, "%lf", &w) != 1) w = 0;
+            weight.push_back(w);
+        }
+        fclose(f);
+        return create(k_, L_, (int)parent.size(), parent.data(), desc.data(), weight.data(), scoring_, weighting_);
+    }
+    bool create(int k, int L, int nNodes, const int32_t* parent, const uint8_t* desc, const double* weight, int scoring = 0,
+                int weighting = 0) {
+        orbfe_vocabulary_destroy(h_);
+        h_ = nullptr;
+        k_ = k; L_ = L; scoring_ = scoring; weighting_ = weighting;
+        return orbfe_vocabulary_create(k, L, nNodes, parent, desc, weight, device(), &h_) == ORBFE_OK;
+    }
+    bool empty() const { return h_ == nullptr; }
+    OrbfeVocabulary* handle() const { return h_; }
+
+    // descriptors: N x 32 continuous (Frame::mDescriptors)
+    template <class BowVector, class FeatureVector>
+    void transform(const cv::Mat& descriptors, BowVector& v, FeatureVector& fv, int levelsup) const {
+        v.clear();
+        fv.clear();
+        const int n = descriptors.rows;
+        if (empty() || n == 0) return;
+        std::vector<int32_t> word(n), node(n);
+        std::vector<double> w(n);
+        if (orbfe_bow_transform(h_, descriptors.ptr(), n, levelsup, word.data(), w.data(), node.data()) != ORBFE_OK)
+            throw std::runtime_error(std::string("ORBVocabulary::transform (B200): ") + orbfe_last_error());
+        const bool tf = weighting_ == 0 || weighting_ == 1;           // TF_IDF, TF  (DBoW2/BowVector.h:39-45)
+        const bool must = scoring_ != 5;                              // every scoring but DOT_PRODUCT normalises
+        for (int i = 0; i < n; i++) {
+            if (!(w[i] > 0)) continue;                                // stopped word
+            if (tf) v[word[i]] += w[i];                               // BowVector::addWeight
+            else v.insert(typename BowVector::value_type(word[i], w[i]));   // addIfNotExist
+            fv[node[i]].push_back((unsigned int)i);                   // FeatureVector::addFeature
+        }
+        if (tf && !v.empty() && !must) {
+            const double nd = (double)v.size();
+            for (auto& e : v) e.second /= nd;
+        }
+        if (must) {                                                   // BowVector::normalize (BowVector.cpp:62-84)
+            double norm = 0.0;
+            if (scoring_ == 1) { for (auto& e : v) norm += e.second * e.second; norm = std::sqrt(norm); }
+            else for (auto& e : v) norm += std::fabs(e.second);
+            if (norm > 0.0) for (auto& e : v) e.second /= norm;
+        }
+    }
+
+   private:
+    OrbfeVocabulary* h_ = nullptr;
+    int k_ = 0, L_ = 0, scoring_ = 0, weighting_ = 0;
+};
+
+// Flattens a DBoW2::FeatureVector for the C ABI (keeps the storage alive).
+struct FlatFeatureVector {
+    std::vector<int32_t> node, start, feat;
+    template <class FeatureVector>
+    explicit FlatFeatureVector(const FeatureVector& fv) {
+        start.push_back(0);
+        for (const auto& e : fv) {
+            node.push_back((int32_t)e.first);
+            for (unsigned int i : e.second) feat.push_back((int32_t)i);
+            start.push_back((int32_t)feat.size());
+        }
+    }
+    OrbfeFeatureVector view() const { return OrbfeFeatureVector{(int32_t)node.size(), node.data(), start.data(), feat.data()}; }
+};
+
+// int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)  (ORBmatcher.cc:260-494)
+//   a: pKF->mDescriptors / keypoint angles / validA[i] = (vpMapPointsKF[i] && !isBad()) / pKF->mFeatVec
+//   b: F.mDescriptors / angles / F.mFeatVec, nLeft = F.Nleft
+// and SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (:893-1044) with strict = true, validB = good points of
+// pKF2.  matchA[ia] = matched index in b (left camera) or -1, matchAR[ia] = right-camera match (fisheye frames).
+// Caller: vpMapPointMatches[matchA[ia]] = vpMapPointsKF[ia]   resp.   vpMatches12[ia] = vpMapPoints2[matchA[ia]].
+template <class FeatureVector>
+inline int SearchByBoW(const cv::Mat& descA, const std::vector<float>& angleA, const std::vector<uint8_t>& validA,
+                       const FeatureVector& fvA, const cv::Mat& descB, const std::vector<float>& angleB,
+                       const std::vector<uint8_t>& validB, const FeatureVector& fvB, float nnratio, bool checkOrientation,
+                       bool strict, int nLeft, std::vector<int32_t>& matchA, std::vector<int32_t>& matchAR,
+                       int thLow = 50) {
+    const FlatFeatureVector fa(fvA), fb(fvB);
+    OrbfeBowSide a = {descA.rows, descA.ptr(), angleA.data(), validA.empty() ? nullptr : validA.data(), fa.view()};
+    OrbfeBowSide b = {descB.rows, descB.ptr(), angleB.data(), validB.empty() ? nullptr : validB.data(), fb.view()};
+    matchA.assign(descA.rows, -1);
+    matchAR.assign(descA.rows, -1);
+    const int n = orbfe_search_by_bow(&a, &b, thLow, strict ? 1 : 0, nnratio, checkOrientation ? 1 : 0, nLeft, matchA.data(),
+                                      matchAR.data(), device());
+    if (n < 0) throw std::runtime_error(std::string("SearchByBoW (B200): ") + orbfe_last_error());
     return n;
 }
 

@@ -49,6 +49,15 @@ class WindowParams(C.Structure):
                 ("n_levels", C.c_int32)]
 
 
+class FeatureVectorC(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("start", C.c_void_p), ("feat", C.c_void_p)]
+
+
+class BowSide(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", C.c_void_p), ("angle", C.c_void_p), ("valid", C.c_void_p),
+                ("fv", FeatureVectorC)]
+
+
 _lib = None
 
 _vp, _i, _f, _sz, _ull = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
@@ -92,6 +101,11 @@ _SIGS = {
     "orbfe_search_window": (_i, [C.POINTER(FrameView), C.POINTER(ProjPoints), C.POINTER(WindowParams), _vp, _vp, _i]),
     "orbfe_search_by_sim3": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(ProjPoints),
                                   C.POINTER(ProjPoints), _i, _vp, _i]),
+    "orbfe_vocabulary_create": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "orbfe_vocabulary_destroy": (None, [_vp]),
+    "orbfe_bow_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "orbfe_bow_transform_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbfe_search_by_bow": (_i, [C.POINTER(BowSide), C.POINTER(BowSide), _i, _i, _f, _i, _i, _vp, _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

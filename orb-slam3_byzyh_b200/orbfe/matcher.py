@@ -7,7 +7,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import FrameView, ProjPoints, SearchParams, WindowParams, check, lib, ptr
+from ._lib import BowSide, FrameView, ProjPoints, SearchParams, WindowParams, check, lib, ptr
 
 MODE_MAPPOINTS, MODE_LASTFRAME, MODE_KEYFRAME = 0, 1, 2
 
@@ -179,6 +179,42 @@ class ORBmatcher:
             return self._search(KF, pts, MODE_KEYFRAME, th, matched, assigned)
         finally:
             self.mbCheckOrientation = keep_ori
+
+    def _bow(self, sideA, sideB, strict, n_left_b):
+        """side = (desc, angle, valid or None, (nodes, start, feat))."""
+        keep = []
+
+        def mk(side):
+            desc, angle, valid, fv = side
+            s = BowSide()
+            desc = np.ascontiguousarray(desc, np.uint8)
+            angle = np.ascontiguousarray(angle, np.float32)
+            nodes, start, feat = [np.ascontiguousarray(x, np.int32) for x in fv]
+            keep.extend([desc, angle, nodes, start, feat])
+            s.n, s.desc, s.angle = len(desc), desc.ctypes.data, angle.ctypes.data
+            if valid is not None:
+                valid = np.ascontiguousarray(valid, np.uint8)
+                keep.append(valid)
+                s.valid = valid.ctypes.data
+            s.fv.n_nodes, s.fv.node_id, s.fv.start, s.fv.feat = len(nodes), nodes.ctypes.data, start.ctypes.data, feat.ctypes.data
+            return s
+        a, b = mk(sideA), mk(sideB)
+        mA = np.empty(a.n, np.int32)
+        mR = np.empty(a.n, np.int32)
+        n = check(lib().orbfe_search_by_bow(C.byref(a), C.byref(b), self.TH_LOW, int(strict), self.mfNNratio,
+                                            int(self.mbCheckOrientation), int(n_left_b), ptr(mA), ptr(mR), self.device))
+        return n, mA, mR
+
+    # SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches), ORBmatcher.cc:260-494.  kf / f = (desc, angles,
+    # valid, feature vector); valid of the keyframe = "slot holds a good map point", of the frame None.
+    # -> nmatches, match[iKF] = frame feature (left camera), matchR[iKF] = right camera (fisheye frames only).
+    def SearchByBoW(self, kf, f, n_left=-1):
+        return self._bow(kf, f, False, n_left)
+
+    # SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12), ORBmatcher.cc:893-1044
+    def SearchByBoWKeyFrames(self, kf1, kf2):
+        n, mA, _ = self._bow(kf1, kf2, True, -1)
+        return n, mA
 
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -35,6 +36,57 @@ int main(int argc, char** argv) {
     f = fopen((p + ".pyr1").c_str(), "wb");
     for (int y = -19; y < l1.rows + 19; y++) fwrite(l1.data + (long)y * (long)(size_t)l1.step - 19, 1, l1.cols + 38, f);
     fclose(f);
+    // matcher adapter: the frame's own keypoints re-projected onto themselves (1 px off), as map points
+    {
+        using namespace ORB_SLAM3::b200;
+        const int n = (int)kps.size();
+        ProjPoints P;
+        for (int i = 0; i < n; i++)
+            P.push(kps[i].pt.x + 1.0f, kps[i].pt.y - 1.0f, kps[i].pt.x - 4.0f, 6.0f * ex.GetScaleFactors()[kps[i].octave],
+                   kps[i].octave - 1, kps[i].octave, kps[i].angle, (i % 17) != 0, true, desc.row(i));
+        std::vector<float> uright(n);
+        for (int i = 0; i < n; i++) uright[i] = (i % 3) ? kps[i].pt.x - 5.0f : -1.0f;
+        const float wInv = 64.0f / cols, hInv = 48.0f / rows;
+        KeyFrameView kv{&kps, &uright, desc.ptr(), 0.f, 0.f, (float)cols, (float)rows, wInv, hInv};
+        std::vector<int32_t> fuse, sim3, assigned(n, -2);
+        std::vector<float> inv = ex.GetInverseScaleSigmaSquares();
+        const int nf1 = FuseSearch(kv, P, inv, fuse);
+        const int ns = SearchBySim3(kv, kv, P, P, sim3);
+        std::vector<uint8_t> claimed(n, 0);
+        const int np = SearchByProjection(kps, uright, desc, 0.f, 0.f, (float)cols, (float)rows, wInv, hInv, P,
+                                          ORBFE_SEARCH_MAPPOINTS, 100, 0.8f, false, claimed, assigned);
+        std::vector<int32_t> asim(n, -2);
+        for (int i = 0; i < n; i++) claimed[i] = (i % 5) == 0;
+        const int nk = SearchByProjectionSim3(kv, P, 1.0f, claimed, asim);
+        f = fopen((p + ".match").c_str(), "wb");
+        fwrite(fuse.data(), 4, n, f); fwrite(sim3.data(), 4, n, f); fwrite(assigned.data(), 4, n, f); fwrite(asim.data(), 4, n, f);
+        fclose(f);
+        fprintf(stderr, "fuse %d sim3 %d proj %d kfsim3 %d\n", nf1, ns, np, nk);
+    }
+    // vocabulary adapter: argv[8] = vocabulary text file (optional); BoW of the frame and a KeyFrame-Frame search
+    // of the frame against itself
+    if (argc > 8) {
+        using namespace ORB_SLAM3::b200;
+        ORBVocabulary voc;
+        if (!voc.loadFromTextFile(argv[8])) return 4;
+        std::map<unsigned, double> bow;
+        std::map<unsigned, std::vector<unsigned>> fv;
+        voc.transform(desc, bow, fv, 2);
+        const int n = (int)kps.size();
+        std::vector<float> ang(n);
+        for (int i = 0; i < n; i++) ang[i] = kps[i].angle;
+        std::vector<uint8_t> valid(n), none;
+        for (int i = 0; i < n; i++) valid[i] = (i % 7) != 0;
+        std::vector<int32_t> mA, mR;
+        const int nb = SearchByBoW(desc, ang, valid, fv, desc, ang, none, fv, 0.9f, true, false, -1, mA, mR);
+        f = fopen((p + ".bow").c_str(), "wb");
+        for (auto& e : bow) { fwrite(&e.first, 4, 1, f); fwrite(&e.second, 8, 1, f); }
+        fclose(f);
+        f = fopen((p + ".bowmatch").c_str(), "wb");
+        fwrite(mA.data(), 4, n, f);
+        fclose(f);
+        fprintf(stderr, "bow words %zu nodes %zu matches %d\n", bow.size(), fv.size(), nb);
+    }
     int self = desc.rows ? ORB_SLAM3::b200::DescriptorDistance(desc.row(0), desc.row(0)) : 0;
     printf("%d %zu %d %d %d %.3f\n", mono, kps.size(), ex.GetLevels(), l1.cols, self, ex.GetScaleFactor());
     return 0;

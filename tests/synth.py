@@ -145,3 +145,80 @@ def map_vs_frame(n_map, n_frame, seed, w=1280, h=720, nlevels=8, scale=1.2):
     view_cos = rng.uniform(0.9, 1.0, n_map).astype(np.float32)
     return dict(keys=keys, fdesc=fdesc, mdesc=mdesc, src=src, u=u, v=v, level=lvl,
                 view_cos=view_cos, scale_factors=sf, bounds=(0.0, 0.0, float(w), float(h)))
+
+
+def make_vocabulary(k, L, seed, stop_frac=0.02, early_leaf_frac=0.0):
+    """A DBoW2-shaped vocabulary tree (k children per node, L levels): node ids in the order DBoW2's
+    HKmeansStep creates them (the k children of a node are consecutive, subtrees follow), child descriptors =
+    parent descriptor with random bit flips, idf-like leaf weights with a few stopped (zero-weight) words.
+    early_leaf_frac > 0 turns some nodes of the last inner level into leaves (unbalanced tree).
+    Returns dict(k, L, parent, desc, weight) indexed by node id (0 = root)."""
+    rng = np.random.default_rng(seed)
+    parent, desc, level = [0], [np.zeros(32, np.uint8)], [0]
+
+    def expand(pid, lvl):
+        first = len(parent)
+        for _ in range(k):
+            if lvl == 1:
+                d = rng.integers(0, 256, 32).astype(np.uint8)
+            else:
+                d = flip_bits(desc[pid], int(rng.integers(20, 60)) // lvl + 4, rng)
+            parent.append(pid); desc.append(d); level.append(lvl)
+        if lvl < L:
+            for c in range(first, first + k):
+                if lvl == L - 1 and rng.uniform() < early_leaf_frac:
+                    continue
+                expand(c, lvl + 1)
+    expand(0, 1)
+    n = len(parent)
+    weight = rng.uniform(0.5, 9.0, n)
+    weight[rng.uniform(size=n) < stop_frac] = 0.0
+    return dict(k=k, L=L, parent=np.array(parent, np.int32), desc=np.stack(desc), weight=weight.astype(np.float64),
+                level=np.array(level, np.int32))
+
+
+def write_vocabulary_text(path, voc, scoring=0, weighting=0):
+    """ORBvoc.txt format (TemplatedVocabulary::loadFromTextFile / saveToTextFile).  No trailing newline: DBoW2's
+    `while(!f.eof())` loop would otherwise append a childless root child with an uninitialised descriptor."""
+    parent, desc, weight = voc["parent"], voc["desc"], voc["weight"]
+    has_child = np.zeros(len(parent), bool)
+    has_child[parent[1:]] = True
+    lines = ["%d %d %d %d" % (voc["k"], voc["L"], scoring, weighting)]
+    for i in range(1, len(parent)):
+        lines.append("%d %d %s %r" % (parent[i], 0 if has_child[i] else 1, " ".join(str(int(b)) for b in desc[i]),
+                                      float(weight[i])))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+def descriptors_near_words(voc, n, seed, noise=12):
+    """n descriptors = randomly chosen leaves of the vocabulary with `noise` bits flipped."""
+    rng = np.random.default_rng(seed)
+    has_child = np.zeros(len(voc["parent"]), bool)
+    has_child[voc["parent"][1:]] = True
+    leaves = np.flatnonzero(~has_child[1:]) + 1
+    pick = rng.choice(leaves, n)
+    return np.stack([flip_bits(voc["desc"][p], int(rng.integers(0, noise + 1)), rng) for p in pick])
+
+
+def make_vocabulary_fast(k, L, seed):
+    """Full-size vocabulary (k=10, L=6: 1.1 M nodes) built level by level with numpy: node ids are breadth-first,
+    child descriptor = parent descriptor XOR a sparse random mask."""
+    rng = np.random.default_rng(seed)
+    parent = [np.zeros(1, np.int32)]
+    desc = [np.zeros((1, 32), np.uint8)]
+    first = 0
+    for lvl in range(1, L + 1):
+        n_prev = len(parent[-1])
+        par = np.repeat(np.arange(first, first + n_prev, dtype=np.int32), k)
+        if lvl == 1:
+            d = rng.integers(0, 256, (len(par), 32)).astype(np.uint8)
+        else:
+            mask = (rng.uniform(size=(len(par), 256)) < 0.12 / lvl + 0.02)
+            d = desc[-1][par - first] ^ np.packbits(mask, axis=1)
+        first += n_prev
+        parent.append(par); desc.append(d)
+    parent = np.concatenate(parent); desc = np.concatenate(desc)
+    weight = rng.uniform(0.5, 9.0, len(parent))
+    weight[rng.uniform(size=len(parent)) < 0.01] = 0.0
+    return dict(k=k, L=L, parent=parent, desc=desc, weight=weight)

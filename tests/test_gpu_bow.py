@@ -1,0 +1,127 @@
+"""GPU parity of the bag-of-words path (csrc/bow.cu) against oracle/bow_oracle.cpp, which
+tests/test_oracle_bow_vs_ref.py pins to DBoW2 itself and to the reference's SearchByBoW."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def orbfe():
+    sys.path.insert(0, os.path.join(ROOT, "orb-slam3_byzyh_b200"))
+    import orbfe as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def vocs(orbfe):
+    voc = synth.make_vocabulary(10, 4, 3)
+    return voc, orbfe.ORBVocabulary(10, 4, voc["parent"], voc["desc"], voc["weight"]), \
+        O.Vocabulary(10, 4, voc["parent"], voc["desc"], voc["weight"])
+
+
+@pytest.mark.parametrize("levelsup", [2, 0, 4, 9])
+def test_transform_small_vocabulary(vocs, levelsup):
+    voc, gv, ov = vocs
+    desc = np.concatenate([synth.descriptors_near_words(voc, 3000, 5), synth.random_descriptors(1000, 6)])
+    gw, gwt, gn = gv.transform_features(desc, levelsup)
+    ow, owt, on = ov.transform_features(desc, levelsup)
+    assert np.array_equal(gw, ow) and np.array_equal(gwt.view(np.uint64), owt.view(np.uint64)) and np.array_equal(gn, on)
+    (gid, gval), gfv = gv.transform(desc, levelsup)
+    (oid, oval), ofv = ov.transform(desc, levelsup)
+    assert np.array_equal(gid, oid) and np.array_equal(gval.view(np.uint64), oval.view(np.uint64))
+    assert all(np.array_equal(a, b) for a, b in zip(gfv, ofv))
+
+
+def test_transform_orbvoc_sized_vocabulary(orbfe):
+    """k = 10, L = 6 (the shape of ORBvoc.txt: 1 111 111 nodes, 10^6 words), levelsup = 4 as in Frame::ComputeBoW."""
+    voc = synth.make_vocabulary_fast(10, 6, 1)
+    gv = orbfe.ORBVocabulary(10, 6, voc["parent"], voc["desc"], voc["weight"])
+    ov = O.Vocabulary(10, 6, voc["parent"], voc["desc"], voc["weight"])
+    rng = np.random.default_rng(2)
+    leaves = rng.integers(len(voc["parent"]) - 10 ** 6, len(voc["parent"]), 4000)
+    desc = np.stack([synth.flip_bits(voc["desc"][p], int(rng.integers(0, 20)), rng) for p in leaves])
+    gw, gwt, gn = gv.transform_features(desc, 4)
+    ow, owt, on = ov.transform_features(desc, 4)
+    assert np.array_equal(gw, ow) and np.array_equal(gwt.view(np.uint64), owt.view(np.uint64)) and np.array_equal(gn, on)
+    assert len(np.unique(gn)) > 50 and gw.max() < 10 ** 6
+
+
+@pytest.mark.parametrize("weighting,scoring", [(1, 1), (2, 0), (3, 5)])
+def test_transform_unbalanced_other_weightings(orbfe, weighting, scoring):
+    voc = synth.make_vocabulary(6, 3, 8, early_leaf_frac=0.2)
+    gv = orbfe.ORBVocabulary(6, 3, voc["parent"], voc["desc"], voc["weight"], scoring, weighting)
+    ov = O.Vocabulary(6, 3, voc["parent"], voc["desc"], voc["weight"], scoring, weighting)
+    desc = synth.descriptors_near_words(voc, 900, 2, noise=30)
+    for levelsup in (0, 1, 2):
+        gw, gwt, gn = gv.transform_features(desc, levelsup)
+        ow, owt, on = ov.transform_features(desc, levelsup)
+        assert np.array_equal(gw, ow) and np.array_equal(gn, on)
+        (gid, gval), gfv = gv.transform(desc, levelsup)
+        (oid, oval), ofv = ov.transform(desc, levelsup)
+        assert np.array_equal(gid, oid) and np.array_equal(gval.view(np.uint64), oval.view(np.uint64))
+        assert all(np.array_equal(a, b) for a, b in zip(gfv, ofv))
+
+
+def _frames(voc, n_a, n_b, seed):
+    rng = np.random.default_rng(seed)
+    da = synth.descriptors_near_words(voc, n_a, seed + 1)
+    src = rng.integers(0, n_a, n_b)
+    db = np.stack([synth.flip_bits(da[s], int(rng.integers(0, 25)), rng) for s in src])
+    db[::11] = synth.random_descriptors(len(db[::11]), seed + 2)
+    ang_a = rng.uniform(0, 360, n_a).astype(np.float32)
+    ang_b = ((ang_a[src] + 25 + rng.normal(0, 10, n_b)) % 360.0).astype(np.float32)
+    return da, ang_a, db, ang_b, rng
+
+
+@pytest.mark.parametrize("seed,check_ori,nnratio,n_left", [(1, True, 0.7, -1), (2, False, 0.9, -1), (3, True, 0.6, 1000),
+                                                           (4, False, 0.75, 700)])
+def test_search_by_bow_keyframe_frame(orbfe, vocs, seed, check_ori, nnratio, n_left):
+    voc, gv, ov = vocs
+    da, ang_a, db, ang_b, rng = _frames(voc, 2000, 1800, seed)
+    valid_a = (rng.uniform(size=len(da)) < 0.75).astype(np.uint8)
+    _, fva = gv.transform(da, 2)
+    _, fvb = gv.transform(db, 2)
+    m = orbfe.ORBmatcher(nnratio, check_ori)
+    n, mA, mR = m.SearchByBoW((da, ang_a, valid_a, fva), (db, ang_b, None, fvb), n_left)
+    en, emA, emR = O.search_by_bow(fva, da, ang_a, valid_a, fvb, db, ang_b, None, 50, False, nnratio, check_ori, n_left)
+    assert n == en and n > 150
+    assert np.array_equal(mA, emA)
+    if n_left != -1:
+        assert np.array_equal(mR, emR) and (emR >= 0).sum() > 20
+
+
+@pytest.mark.parametrize("seed,check_ori", [(6, True), (7, False)])
+def test_search_by_bow_keyframes(orbfe, vocs, seed, check_ori):
+    voc, gv, ov = vocs
+    da, ang_a, db, ang_b, rng = _frames(voc, 2000, 1800, seed)
+    valid_a = (rng.uniform(size=len(da)) < 0.75).astype(np.uint8)
+    valid_b = (rng.uniform(size=len(db)) < 0.75).astype(np.uint8)
+    _, fva = gv.transform(da, 2)
+    _, fvb = gv.transform(db, 2)
+    m = orbfe.ORBmatcher(0.75, check_ori)
+    n, mA = m.SearchByBoWKeyFrames((da, ang_a, valid_a, fva), (db, ang_b, valid_b, fvb))
+    en, emA, _ = O.search_by_bow(fva, da, ang_a, valid_a, fvb, db, ang_b, valid_b, 50, True, 0.75, check_ori)
+    assert n == en and n > 100 and np.array_equal(mA, emA)
+    assert not np.any((mA >= 0) & (valid_a == 0)) and np.all(valid_b[mA[mA >= 0]] == 1)
+
+
+def test_search_by_bow_empty_and_disjoint(orbfe, vocs):
+    voc, gv, ov = vocs
+    da, ang_a, db, ang_b, rng = _frames(voc, 300, 280, 9)
+    _, fva = gv.transform(da, 2)
+    _, fvb = gv.transform(db, 2)
+    m = orbfe.ORBmatcher(0.7, True)
+    empty = (np.zeros(0, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32))
+    n, mA, _ = m.SearchByBoW((da, ang_a, None, fva), (db, ang_b, None, empty))
+    assert n == 0 and np.all(mA == -1)
+    shifted = (fvb[0] + 100000, fvb[1], fvb[2])            # no common node
+    n, mA, _ = m.SearchByBoW((da, ang_a, None, fva), (db, ang_b, None, shifted))
+    assert n == 0 and np.all(mA == -1)
