@@ -320,6 +320,34 @@ int orbfe_search_by_bow(const OrbfeBowSide* a, const OrbfeBowSide* b, int th_low
                         float nnratio, int check_orientation, int n_left_b, int32_t* match_a,
                         int32_t* match_a_right, int device);
 
+/* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
+ * const bool bOnlyStereo, const bool bCoarse)   include/ORBmatcher.h:76-77, src/ORBmatcher.cc:1046-1324, for pinhole
+ * keyframes (mpCamera2 == NULL; the fisheye rig branch :1173-1202 needs KannalaBrandt8::epipolarConstrain, SURVEY 8(f)
+ * rank 4).  Each side: mvKeysUn, mDescriptors, mvuRight (NULL = monocular), has_map_point[i] = (GetMapPoint(i) != NULL),
+ * mFeatVec.  f12 = the fundamental matrix of Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:191-194:
+ * K1^-T * hat(t12) * R12 * K2^-1, row major; it is constant per keyframe pair and stays on the host with Eigen),
+ * epipole = pKF2->mpCamera->project(T2w * Cw) (:1063), scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors /
+ * mvLevelSigma2, th_low = TH_LOW.  matches12[i1] = i2 or -1; vMatchedPairs = those pairs in ascending i1.
+ * Returns nmatches. */
+typedef struct OrbfeTriSide {
+    int32_t n;
+    const OrbfeKeyPoint* keys;
+    const uint8_t* desc;
+    const float* uright;
+    const uint8_t* has_map_point;
+    OrbfeFeatureVector fv;
+} OrbfeTriSide;
+typedef struct OrbfeTriParams {
+    float f12[9];
+    float epipole[2];
+    const float* scale_factors2;
+    const float* level_sigma2_2;
+    int32_t n_levels;
+    int32_t only_stereo, coarse, check_orientation, th_low;
+} OrbfeTriParams;
+int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const OrbfeTriSide* kf2,
+                                   const OrbfeTriParams* prm, int32_t* matches12, int device);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

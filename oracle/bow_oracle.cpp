@@ -163,4 +163,85 @@ int search_by_bow(const FeatVec& fa, const uint8_t* descA, const float* angleA, 
     return nmatches;
 }
 
+// ORBmatcher.cc:1046-1324 (mpCamera2 == NULL branches), Pinhole.cpp:196-215
+int search_for_triangulation(const TriSide& A, const TriSide& B, const float* F12, const float* ep, const float* scaleFactorsB,
+                             const float* levelSigma2B, int onlyStereo, int coarse, int checkOrientation, int thLow,
+                             int* matches12) {
+    enum { HISTO = 30 };
+    for (int i = 0; i < A.n; i++) matches12[i] = -1;
+    std::vector<int> rotHist[HISTO];
+    const float factor = 1.0f / HISTO;
+    int nmatches = 0;
+    const FeatVec &fa = *A.fv, &fb = *B.fv;
+    size_t ia = 0, ib = 0;
+    const size_t na = fa.node.size(), nb = fb.node.size();
+    while (ia < na && ib < nb) {
+        if (fa.node[ia] == fb.node[ib]) {
+            for (int pa = fa.start[ia]; pa < fa.start[ia + 1]; pa++) {
+                const int idx1 = fa.feat[pa];
+                if (A.hasMp[idx1]) continue;
+                const bool bStereo1 = A.uright && A.uright[idx1] >= 0;
+                if (onlyStereo && !bStereo1) continue;
+                const match_oracle::OrbKp& kp1 = A.keys[idx1];
+                const uint8_t* d1 = A.desc + 32 * (size_t)idx1;
+                int bestDist = thLow, bestIdx2 = -1;
+                for (int pb = fb.start[ib]; pb < fb.start[ib + 1]; pb++) {
+                    const int idx2 = fb.feat[pb];
+                    if (B.hasMp[idx2]) continue;                 // vbMatched2 is never set in this version of the loop
+                    const bool bStereo2 = B.uright && B.uright[idx2] >= 0;
+                    if (onlyStereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(d1, B.desc + 32 * (size_t)idx2);
+                    if (dist > thLow || dist > bestDist) continue;
+                    const match_oracle::OrbKp& kp2 = B.keys[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ep[0] - kp2.x;
+                        const float distey = ep[1] - kp2.y;
+                        if (distex * distex + distey * distey < 100 * scaleFactorsB[kp2.octave]) continue;
+                    }
+                    bool ok = coarse != 0;
+                    if (!ok) {   // Pinhole::epipolarConstrain
+                        const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+                        const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+                        const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+                        const float num = a * kp2.x + b * kp2.y + c;
+                        const float den = a * a + b * b;
+                        if (den == 0) ok = false;
+                        else {
+                            const float dsqr = num * num / den;
+                            ok = dsqr < 3.84 * levelSigma2B[kp2.octave];
+                        }
+                    }
+                    if (ok) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    matches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (checkOrientation) {
+                        float rot = kp1.angle - B.keys[bestIdx2].angle;
+                        if (rot < 0.0) rot += 360.0f;
+                        int bin = (int)roundf(rot * factor);
+                        if (bin == HISTO) bin = 0;
+                        rotHist[bin].push_back(idx1);
+                    }
+                }
+            }
+            ia++; ib++;
+        } else if (fa.node[ia] < fb.node[ib]) {
+            while (ia < na && fa.node[ia] < fb.node[ib]) ia++;
+        } else {
+            while (ib < nb && fb.node[ib] < fa.node[ia]) ib++;
+        }
+    }
+    if (checkOrientation) {
+        int cnt[HISTO], ind1, ind2, ind3;
+        for (int i = 0; i < HISTO; i++) cnt[i] = (int)rotHist[i].size();
+        three_maxima(cnt, HISTO, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i]) { matches12[idx1] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
 }  // namespace bow_oracle

@@ -64,4 +64,20 @@ int search_by_bow(const FeatVec& fa, const uint8_t* descA, const float* angleA, 
                   const FeatVec& fb, const uint8_t* descB, const float* angleB, const uint8_t* validB, int nB,
                   const BowSearchParams& prm, int* matchA, int* matchAR);
 
+// ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:1046-1324) for pinhole keyframes (mpCamera2 == NULL), with
+// Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:186-216) given the fundamental matrix F12 (row major) it
+// builds from K1, K2, R12, t12, and the epipole ep (:1063).  hasMp*[i] = the keyframe slot already holds a map point;
+// uright* = mvuRight (NULL = monocular).  matches12[i1] = i2 or -1.  Returns nmatches.
+struct TriSide {
+    const FeatVec* fv;
+    const match_oracle::OrbKp* keys;
+    const uint8_t* desc;
+    const float* uright;
+    const uint8_t* hasMp;
+    int n;
+};
+int search_for_triangulation(const TriSide& A, const TriSide& B, const float* F12, const float* ep, const float* scaleFactorsB,
+                             const float* levelSigma2B, int onlyStereo, int coarse, int checkOrientation, int thLow,
+                             int* matches12);
+
 }  // namespace bow_oracle

@@ -391,3 +391,23 @@ def search_by_bow(fvA, descA, angleA, validA, fvB, descB, angleB, validB, th_low
                                    None if vb is None else _p(vb), nB, int(th_low), int(strict), C.c_float(nnratio),
                                    int(check_orientation), int(n_left_b), _p(mA), _p(mR))
     return n, mA, mR
+
+
+def search_for_triangulation(fvA, keysA, descA, urightA, has_mp_a, fvB, keysB, descB, urightB, has_mp_b, f12, ep,
+                             scale_factors_b, level_sigma2_b, only_stereo=False, coarse=False, check_orientation=True,
+                             th_low=50):
+    a = [np.ascontiguousarray(x, np.int32) for x in fvA]
+    b = [np.ascontiguousarray(x, np.int32) for x in fvB]
+    keysA = np.ascontiguousarray(keysA); keysB = np.ascontiguousarray(keysB)
+    descA = np.ascontiguousarray(descA, np.uint8); descB = np.ascontiguousarray(descB, np.uint8)
+    ura = None if urightA is None else np.ascontiguousarray(urightA, np.float32)
+    urb = None if urightB is None else np.ascontiguousarray(urightB, np.float32)
+    mpa = np.ascontiguousarray(has_mp_a, np.uint8); mpb = np.ascontiguousarray(has_mp_b, np.uint8)
+    f12 = np.ascontiguousarray(f12, np.float32); ep = np.ascontiguousarray(ep, np.float32)
+    sf = np.ascontiguousarray(scale_factors_b, np.float32); s2 = np.ascontiguousarray(level_sigma2_b, np.float32)
+    m12 = np.empty(len(keysA), np.int32)
+    n = lib().oracle_search_for_triangulation(
+        len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), _p(keysA), _p(descA), None if ura is None else _p(ura), _p(mpa), len(keysA),
+        len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), _p(keysB), _p(descB), None if urb is None else _p(urb), _p(mpb), len(keysB),
+        _p(f12), _p(ep), _p(sf), _p(s2), int(only_stereo), int(coarse), int(check_orientation), int(th_low), _p(m12))
+    return n, m12

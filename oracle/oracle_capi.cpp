@@ -287,5 +287,15 @@ int oracle_search_by_bow(int nnA, const int32_t* nodeA, const int32_t* startA, c
     const bow_oracle::BowSearchParams prm{thLow, strict, nnratio, checkOri, nLeftB};
     return bow_oracle::search_by_bow(fa, descA, angleA, validA, nA, fb, descB, angleB, validB, nB, prm, matchA, matchAR);
 }
+int oracle_search_for_triangulation(int nnA, const int32_t* nodeA, const int32_t* startA, const int32_t* featA,
+                                    const OrbKp* keysA, const uint8_t* descA, const float* urA, const uint8_t* mpA, int nA,
+                                    int nnB, const int32_t* nodeB, const int32_t* startB, const int32_t* featB,
+                                    const OrbKp* keysB, const uint8_t* descB, const float* urB, const uint8_t* mpB, int nB,
+                                    const float* F12, const float* ep, const float* sfB, const float* sigma2B, int onlyStereo,
+                                    int coarse, int checkOri, int thLow, int32_t* matches12) {
+    const bow_oracle::FeatVec fa = fill_fv(nnA, nodeA, startA, featA), fb = fill_fv(nnB, nodeB, startB, featB);
+    const bow_oracle::TriSide A{&fa, keysA, descA, urA, mpA, nA}, B{&fb, keysB, descB, urB, mpB, nB};
+    return bow_oracle::search_for_triangulation(A, B, F12, ep, sfB, sigma2B, onlyStereo, coarse, checkOri, thLow, matches12);
+}
 
 }  // extern "C"

@@ -337,3 +337,12 @@ def search_by_bow_kf_kf(kf1, kf2, nnratio, check_ori):
     out = np.empty(kf1.n, np.int32)
     n = mlib().refm_search_by_bow_kf_kf(C.c_void_p(kf1.h), C.c_void_p(kf2.h), _f(nnratio), int(check_ori), _p(out))
     return n, out
+
+
+def search_for_triangulation(kf1, kf2, only_stereo, coarse, check_ori):
+    """-> nmatches, matches12, F12 (3x3), epipole (2)."""
+    out = np.empty(kf1.n, np.int32)
+    f12, ep = np.empty(9, np.float32), np.empty(2, np.float32)
+    n = mlib().refm_search_for_triangulation(C.c_void_p(kf1.h), C.c_void_p(kf2.h), int(only_stereo), int(coarse), _f(0.6),
+                                             int(check_ori), _p(out), _p(f12), _p(ep))
+    return n, out, f12, ep

@@ -26,7 +26,7 @@ namespace {
 
 struct RefFrame {
     Frame F;
-    GeometricCamera cam;
+    Pinhole cam;
     std::vector<std::unique_ptr<MapPoint>> own;   // map points held by F.mvpMapPoints (slot order, may be null)
     std::vector<MapPoint*> initial;               // F.mvpMapPoints before a search
     KeyFrame kf;                                  // keyframe view of the same data (relocalisation overload)
@@ -216,14 +216,18 @@ static KeyFrame* as_keyframe(RefFrame* rf) {
     K.mnScaleLevels = F.mnScaleLevels; K.mfLogScaleFactor = F.mfLogScaleFactor;
     K.mvScaleFactors = F.mvScaleFactors;
     K.mvInvLevelSigma2.resize(F.mnScaleLevels);
-    for (int i = 0; i < F.mnScaleLevels; i++) K.mvInvLevelSigma2[i] = 1.0f / (F.mvScaleFactors[i] * F.mvScaleFactors[i]);
+    K.mvLevelSigma2.resize(F.mnScaleLevels);
+    for (int i = 0; i < F.mnScaleLevels; i++) {   // ORBextractor.cc:426-437
+        K.mvLevelSigma2[i] = F.mvScaleFactors[i] * F.mvScaleFactors[i];
+        K.mvInvLevelSigma2[i] = 1.0f / K.mvLevelSigma2[i];
+    }
     K.mnMinX = Frame::mnMinX; K.mnMinY = Frame::mnMinY; K.mnMaxX = Frame::mnMaxX; K.mnMaxY = Frame::mnMaxY;
     K.mfGridElementWidthInv = Frame::mfGridElementWidthInv; K.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
     K.mGrid.assign(K.mnGridCols, std::vector<std::vector<size_t>>(K.mnGridRows));
     for (int i = 0; i < K.mnGridCols; i++)
         for (int j = 0; j < K.mnGridRows; j++) K.mGrid[i][j] = F.mGrid[i][j];
     K.fx = rf->cam.fx; K.fy = rf->cam.fy; K.cx = rf->cam.cx; K.cy = rf->cam.cy; K.mbf = F.mbf;
-    K.mpCamera = &rf->cam; K.mpCamera2 = &rf->cam;
+    K.mpCamera = &rf->cam; K.mpCamera2 = &rf->cam;   // Fuse(bRight) reads mpCamera2; the BoW / triangulation drivers reset it
     K.mTcw = F.mTcw;
     K.mvpMapPoints = F.mvpMapPoints;
     for (int i = 0; i < F.N; i++)
@@ -486,6 +490,37 @@ int refm_search_by_bow_kf_kf(void* h1, void* h2, float nnratio, int checkOri, in
     Matcher matcher(nnratio, checkOri != 0);
     const int n = matcher.SearchByBoW(k1, k2, m12);
     for (int i = 0; i < k1->N; i++) out[i] = m12[i] ? m12[i]->id - 2000000 : -1;
+    return n;
+}
+
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), pinhole keyframes
+// (mpCamera2 == NULL).  matches12[i1] = i2 or -1 (vMatchedPairs = the pairs with i2 >= 0 in ascending i1).
+// f12 / ep: the fundamental matrix Pinhole::epipolarConstrain builds and the epipole (:1063), for the caller's side.
+int refm_search_for_triangulation(void* h1, void* h2, int onlyStereo, int coarse, float nnratio, int checkOri, int* matches12,
+                                  float* f12, float* ep) {
+    RefFrame *r1 = (RefFrame*)h1, *r2 = (RefFrame*)h2;
+    KeyFrame* k1 = as_keyframe(r1);
+    KeyFrame* k2 = as_keyframe(r2);
+    k1->mFeatVec = r1->F.mFeatVec; k2->mFeatVec = r2->F.mFeatVec;
+    k1->mpCamera2 = nullptr; k2->mpCamera2 = nullptr;
+    std::vector<std::pair<size_t, size_t>> pairs;
+    Matcher matcher(nnratio, checkOri != 0);
+    const int n = matcher.SearchForTriangulation(k1, k2, pairs, onlyStereo != 0, coarse != 0);
+    for (int i = 0; i < k1->N; i++) matches12[i] = -1;
+    size_t prev = 0;
+    for (size_t j = 0; j < pairs.size(); j++) {
+        if (j && pairs[j].first <= prev) return -1000;   // must be ascending in i1
+        prev = pairs[j].first;
+        matches12[pairs[j].first] = (int)pairs[j].second;
+    }
+    // the same expressions as ORBmatcher.cc:1056-1075 and Pinhole.cpp:191-194, with the shim's matrix type
+    Sophus::SE3f T12 = k1->GetPose() * k2->GetPoseInverse();
+    Eigen::Matrix3f t12x = Sophus::SO3f::hat(T12.translation());
+    Eigen::Matrix3f F12 = k1->mpCamera->toK_().transpose().inverse() * t12x * T12.rotationMatrix() * k2->mpCamera->toK_().inverse();
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) f12[3 * i + j] = F12(i, j);
+    Eigen::Vector2f e = k2->mpCamera->project(k2->GetPose() * k1->GetCameraCenter());
+    ep[0] = e(0); ep[1] = e(1);
     return n;
 }
 

@@ -44,7 +44,38 @@ struct Vector3f {
     Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
     Vector3f operator*(float s) const { return Vector3f(v[0] * s, v[1] * s, v[2] * s); }
 };
-struct Matrix3f {};  // always the identity here
+struct Matrix3f {
+    float m[3][3];
+    Matrix3f() : m{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}} {}
+    float& operator()(int i, int j) { return m[i][j]; }
+    float operator()(int i, int j) const { return m[i][j]; }
+    Matrix3f transpose() const {
+        Matrix3f r;
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i][j] = m[j][i];
+        return r;
+    }
+    Matrix3f operator*(const Matrix3f& o) const {
+        Matrix3f r;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) r.m[i][j] = m[i][0] * o.m[0][j] + m[i][1] * o.m[1][j] + m[i][2] * o.m[2][j];
+        return r;
+    }
+    Vector3f operator*(const Vector3f& v) const {
+        return Vector3f(m[0][0] * v(0) + m[0][1] * v(1) + m[0][2] * v(2), m[1][0] * v(0) + m[1][1] * v(1) + m[1][2] * v(2),
+                        m[2][0] * v(0) + m[2][1] * v(1) + m[2][2] * v(2));
+    }
+    Matrix3f inverse() const {   // adjugate / determinant (the tests only need SOME fixed F12, shared by both sides)
+        Matrix3f r;
+        const float d = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                        m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+        r.m[0][0] = (m[1][1] * m[2][2] - m[1][2] * m[2][1]) / d; r.m[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) / d;
+        r.m[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) / d; r.m[1][0] = (m[1][2] * m[2][0] - m[1][0] * m[2][2]) / d;
+        r.m[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) / d; r.m[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) / d;
+        r.m[2][0] = (m[1][0] * m[2][1] - m[1][1] * m[2][0]) / d; r.m[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) / d;
+        r.m[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) / d;
+        return r;
+    }
+};
 struct Vector2f {
     float v[2];
     Vector2f() : v{0, 0} {}
@@ -63,10 +94,21 @@ struct SE3 {
     explicit SE3(const Eigen::Vector3f& t_) : t(t_) {}
     SE3(const Eigen::Matrix3f&, const Eigen::Vector3f& t_) : t(t_) {}
     SE3 inverse() const { return SE3(Eigen::Vector3f(-t(0), -t(1), -t(2))); }
+    SE3 operator*(const SE3& o) const { return SE3(o.t + t); }
+    Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
     Eigen::Vector3f translation() const { return t; }
     Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return p + t; }
 };
 typedef SE3<float> SE3f;
+struct SO3f {
+    static Eigen::Matrix3f hat(const Eigen::Vector3f& v) {
+        Eigen::Matrix3f r;
+        r(0, 0) = 0; r(0, 1) = -v(2); r(0, 2) = v(1);
+        r(1, 0) = v(2); r(1, 1) = 0; r(1, 2) = -v(0);
+        r(2, 0) = -v(1); r(2, 1) = v(0); r(2, 2) = 0;
+        return r;
+    }
+};
 // scale + translation similarity: p -> s*p + t
 template <class T>
 struct Sim3 {
@@ -97,9 +139,26 @@ extern std::vector<RefAction> g_refActions;
 class GeometricCamera {
    public:
     float fx = 1, fy = 1, cx = 0, cy = 0;
+    virtual ~GeometricCamera() {}
     Eigen::Vector2f project(const Eigen::Vector3f& p) const {
         return Eigen::Vector2f(fx * p(0) / p(2) + cx, fy * p(1) / p(2) + cy);
     }
+    virtual Eigen::Matrix3f toK_() = 0;
+    virtual bool epipolarConstrain(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
+                                   const Eigen::Matrix3f& R12, const Eigen::Vector3f& t12, const float sigmaLevel,
+                                   const float unc) = 0;
+};
+class Pinhole : public GeometricCamera {
+   public:
+    Eigen::Matrix3f toK_() override {   // src/CameraModels/Pinhole.cpp:168-173
+        Eigen::Matrix3f K;
+        K(0, 0) = fx; K(0, 1) = 0; K(0, 2) = cx; K(1, 0) = 0; K(1, 1) = fy; K(1, 2) = cy; K(2, 0) = 0; K(2, 1) = 0; K(2, 2) = 1;
+        return K;
+    }
+    // body sliced from src/CameraModels/Pinhole.cpp
+    bool epipolarConstrain(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
+                           const Eigen::Matrix3f& R12, const Eigen::Vector3f& t12, const float sigmaLevel,
+                           const float unc) override;
 };
 
 class MapPoint {
@@ -156,7 +215,9 @@ class KeyFrame {
         g_refActions.push_back({3, pMP->id, (int)idx});
     }
     Sophus::SE3f GetPose() { return mTcw; }
+    Sophus::SE3f GetPoseInverse() { return mTcw.inverse(); }
     Sophus::SE3f GetRightPose() { return mTcw; }
+    Sophus::SE3f GetRightPoseInverse() { return mTcw.inverse(); }
     Eigen::Vector3f GetCameraCenter() { return mTcw.inverse().translation(); }
     Eigen::Vector3f GetRightCameraCenter() { return mTcw.inverse().translation(); }
 
@@ -168,7 +229,7 @@ class KeyFrame {
     cv::Mat mDescriptors;
     int mnScaleLevels = 0;
     float mfLogScaleFactor = 0;
-    std::vector<float> mvScaleFactors, mvInvLevelSigma2;
+    std::vector<float> mvScaleFactors, mvInvLevelSigma2, mvLevelSigma2;
     int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;      // ints in the reference's KeyFrame (include/KeyFrame.h:403)
     int mnGridCols = 64, mnGridRows = 48;
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;

@@ -200,6 +200,103 @@ __global__ void k_bow_cull(int nA, const int* __restrict__ binOf, const int* __r
     }
 }
 
+// ORBmatcher::SearchForTriangulation (:1046-1324), pinhole keyframes: no state is carried between keyframe-1 features
+// (vbMatched2 is never set inside the loop of this version), so one warp serves one keyframe-1 feature: lanes over the
+// keyframe-2 features of the same vocabulary node, Hamming + epipole-distance (:1162-1170) + epipolar-line
+// (Pinhole::epipolarConstrain, Pinhole.cpp:196-215) gates per candidate.  `dist > bestDist` (not >=) lets a LATER
+// candidate of equal distance replace the current best: key = distance << 20 | (0xFFFFF - position).
+struct TriSideDev {
+    int n, nNodes;
+    const OrbfeKeyPoint* keys;
+    const uint32_t* desc;
+    const float* uright;
+    const uint8_t* hasMp;
+    const int *node, *start, *feat;
+};
+struct TriPrm {
+    float F[9], ep[2];
+    const float *sf2, *sigma2;
+    int nLevels, onlyStereo, coarse, thLow;
+};
+
+__global__ void __launch_bounds__(128)
+k_tri_match(TriSideDev A, TriSideDev B, TriPrm P, int nfa, int* __restrict__ matches12) {
+    const int pa = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pa >= nfa) return;
+    int lo = 0, hi = A.nNodes;   // node list index ia with start[ia] <= pa < start[ia+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (A.start[mid] <= pa) lo = mid; else hi = mid;
+    }
+    const int node = A.node[lo];
+    int l2 = 0, h2 = B.nNodes;
+    while (l2 < h2) {
+        const int mid = (l2 + h2) >> 1;
+        if (B.node[mid] < node) l2 = mid + 1; else h2 = mid;
+    }
+    if (l2 >= B.nNodes || B.node[l2] != node) return;
+    const int idx1 = A.feat[pa];
+    if (A.hasMp[idx1]) return;
+    const bool stereo1 = A.uright && A.uright[idx1] >= 0;
+    if (P.onlyStereo && !stereo1) return;
+    const OrbfeKeyPoint kp1 = A.keys[idx1];
+    uint32_t d[8];
+    const uint4* pd = reinterpret_cast<const uint4*>(A.desc + 8 * (size_t)idx1);
+    *reinterpret_cast<uint4*>(d) = pd[0];
+    *reinterpret_cast<uint4*>(d + 4) = pd[1];
+    // epipolar line of kp1 in image 2 (Pinhole.cpp:200-202)
+    const float a = kp1.x * P.F[0] + kp1.y * P.F[3] + P.F[6];
+    const float b = kp1.x * P.F[1] + kp1.y * P.F[4] + P.F[7];
+    const float c = kp1.x * P.F[2] + kp1.y * P.F[5] + P.F[8];
+    const float den = a * a + b * b;
+    const int bb = B.start[l2], be = B.start[l2 + 1];
+    uint32_t key = 0xFFFFFFFFu;
+    for (int pb = bb + lane; pb < be; pb += 32) {
+        const int idx2 = B.feat[pb];
+        if (B.hasMp[idx2]) continue;
+        const bool stereo2 = B.uright && B.uright[idx2] >= 0;
+        if (P.onlyStereo && !stereo2) continue;
+        const uint4* bd = reinterpret_cast<const uint4*>(B.desc + 8 * (size_t)idx2);
+        const int dist = hamming8w(d, bd[0], bd[1]);
+        if (dist > P.thLow) continue;
+        const OrbfeKeyPoint kp2 = B.keys[idx2];
+        if (kp2.octave < 0 || kp2.octave >= P.nLevels) continue;
+        if (!stereo1 && !stereo2) {
+            const float ex = P.ep[0] - kp2.x, ey = P.ep[1] - kp2.y;
+            if (ex * ex + ey * ey < 100.0f * P.sf2[kp2.octave]) continue;
+        }
+        if (!P.coarse) {
+            if (den == 0) continue;
+            const float num = a * kp2.x + b * kp2.y + c;
+            const float dsqr = num * num / den;
+            if (!((double)dsqr < 3.84 * (double)P.sigma2[kp2.octave])) continue;
+        }
+        key = min(key, ((uint32_t)dist << 20) | (uint32_t)(0xFFFFF - (pb - bb)));
+    }
+    key = __reduce_min_sync(0xffffffffu, key);
+    if (lane == 0 && key != 0xFFFFFFFFu) matches12[idx1] = B.feat[bb + (0xFFFFF - (int)(key & 0xFFFFFu))];
+}
+
+__global__ void k_tri_votes(int nA, const OrbfeKeyPoint* __restrict__ keysA, const OrbfeKeyPoint* __restrict__ keysB,
+                            int useHist, const int* __restrict__ m12, int* __restrict__ binOf, int* __restrict__ hist,
+                            int* __restrict__ nmatches) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nA) return;
+    const int j = m12[i];
+    if (j < 0) return;
+    atomicAdd(nmatches, 1);
+    if (useHist) {
+        float rot = keysA[i].angle - keysB[j].angle;
+        if (rot < 0.0f) rot += 360.0f;
+        int bin = (int)roundf(rot * (1.0f / HISTO));
+        if (bin == HISTO) bin = 0;
+        bin = min(max(bin, 0), HISTO - 1);
+        binOf[2 * i] = bin;
+        atomicAdd(&hist[bin], 1);
+    }
+}
+
 int check_device(int device) {
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -346,6 +443,68 @@ extern "C" int orbfe_search_by_bow(const OrbfeBowSide* a, const OrbfeBowSide* b,
     k_bow_votes<<<g, 256, 0, st>>>(a->n, A.angle, B.angle, check_orientation ? 1 : 0, dM, dR, S.ptr<int>(wBin), S.ptr<int>(wHist),
                                    S.ptr<int>(oN));
     if (check_orientation) k_bow_cull<<<g, 256, 0, st>>>(a->n, S.ptr<int>(wBin), S.ptr<int>(wHist), dM, dR, S.ptr<int>(oN));
+    BCK(cudaGetLastError());
+    BCK(S.download());
+    return nmatches;
+}
+
+extern "C" int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const OrbfeTriSide* kf2, const OrbfeTriParams* prm,
+                                              int32_t* matches12, int device) {
+    int rc = check_device(device);
+    if (rc != ORBFE_OK) return rc;
+    if (!kf1 || !kf2 || !prm || !matches12) return bfail(ORBFE_ERR_INVALID, "null argument");
+    if (kf1->n < 0 || kf2->n < 0 || kf1->fv.n_nodes < 0 || kf2->fv.n_nodes < 0 || prm->n_levels <= 0)
+        return bfail(ORBFE_ERR_INVALID, "bad sizes");
+    for (int i = 0; i < kf1->n; i++) matches12[i] = -1;
+    if (kf1->n == 0 || kf2->n == 0 || kf1->fv.n_nodes == 0 || kf2->fv.n_nodes == 0) return 0;
+    if (!kf1->keys || !kf1->desc || !kf1->has_map_point || !kf2->keys || !kf2->desc || !kf2->has_map_point ||
+        !kf1->fv.node_id || !kf1->fv.start || !kf1->fv.feat || !kf2->fv.node_id || !kf2->fv.start || !kf2->fv.feat ||
+        !prm->scale_factors2 || !prm->level_sigma2_2)
+        return bfail(ORBFE_ERR_INVALID, "missing array");
+    const int nfa = kf1->fv.start[kf1->fv.n_nodes], nfb = kf2->fv.start[kf2->fv.n_nodes];
+    if (nfa < 0 || nfb < 0 || nfb >= (1 << 20)) return bfail(ORBFE_ERR_CAPACITY, "feature vector too long");
+    OrbfeStage S;
+    struct Lay { size_t keys, desc, ur, mp, node, start, feat; } la, lb;
+    auto lay = [&](const OrbfeTriSide* s, int nf, Lay& l) {
+        l.keys = S.in(s->keys, sizeof(OrbfeKeyPoint) * (size_t)s->n);
+        l.desc = S.in(s->desc, 32 * (size_t)s->n);
+        l.ur = S.in(s->uright, s->uright ? 4 * (size_t)s->n : 0);
+        l.mp = S.in(s->has_map_point, (size_t)s->n);
+        l.node = S.in(s->fv.node_id, 4 * (size_t)s->fv.n_nodes);
+        l.start = S.in(s->fv.start, 4 * (size_t)(s->fv.n_nodes + 1));
+        l.feat = S.in(s->fv.feat, 4 * (size_t)nf);
+    };
+    lay(kf1, nfa, la);
+    lay(kf2, nfb, lb);
+    const size_t iSf = S.in(prm->scale_factors2, 4 * (size_t)prm->n_levels), iS2 = S.in(prm->level_sigma2_2, 4 * (size_t)prm->n_levels);
+    const size_t wBin = S.work(8 * (size_t)kf1->n), wHist = S.work(4 * (HISTO + 2));
+    int nmatches = 0;
+    const size_t oM = S.out(matches12, 4 * (size_t)kf1->n), oN = S.out(&nmatches, 4);
+    BCK(S.commit(device));
+    cudaStream_t st = S.stream();
+    BCK(S.upload());
+    auto bind = [&](const OrbfeTriSide* s, const Lay& l) {
+        TriSideDev d;
+        d.n = s->n; d.nNodes = s->fv.n_nodes; d.keys = S.ptr<OrbfeKeyPoint>(l.keys); d.desc = S.ptr<uint32_t>(l.desc);
+        d.uright = s->uright ? S.ptr<float>(l.ur) : nullptr; d.hasMp = S.ptr<uint8_t>(l.mp);
+        d.node = S.ptr<int>(l.node); d.start = S.ptr<int>(l.start); d.feat = S.ptr<int>(l.feat);
+        return d;
+    };
+    const TriSideDev A = bind(kf1, la), B = bind(kf2, lb);
+    TriPrm P;
+    for (int i = 0; i < 9; i++) P.F[i] = prm->f12[i];
+    P.ep[0] = prm->epipole[0]; P.ep[1] = prm->epipole[1];
+    P.sf2 = S.ptr<float>(iSf); P.sigma2 = S.ptr<float>(iS2); P.nLevels = prm->n_levels;
+    P.onlyStereo = prm->only_stereo; P.coarse = prm->coarse; P.thLow = prm->th_low;
+    int* dM = S.ptr<int>(oM);
+    BCK(cudaMemsetAsync(dM, 0xFF, 4 * (size_t)kf1->n, st));
+    BCK(cudaMemsetAsync(S.ptr<int>(wHist), 0, 4 * (HISTO + 2), st));
+    BCK(cudaMemsetAsync(S.ptr<int>(oN), 0, 4, st));
+    k_tri_match<<<(nfa + 3) / 4, 128, 0, st>>>(A, B, P, nfa, dM);
+    const int g = (kf1->n + 255) / 256;
+    k_tri_votes<<<g, 256, 0, st>>>(kf1->n, A.keys, B.keys, prm->check_orientation ? 1 : 0, dM, S.ptr<int>(wBin), S.ptr<int>(wHist),
+                                   S.ptr<int>(oN));
+    if (prm->check_orientation) k_bow_cull<<<g, 256, 0, st>>>(kf1->n, S.ptr<int>(wBin), S.ptr<int>(wHist), dM, nullptr, S.ptr<int>(oN));
     BCK(cudaGetLastError());
     BCK(S.download());
     return nmatches;

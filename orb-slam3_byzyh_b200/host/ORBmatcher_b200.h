@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <opencv2/opencv.hpp>
@@ -307,6 +308,38 @@ inline int SearchByBoW(const cv::Mat& descA, const std::vector<float>& angleA, c
     const int n = orbfe_search_by_bow(&a, &b, thLow, strict ? 1 : 0, nnratio, checkOrientation ? 1 : 0, nLeft, matchA.data(),
                                       matchAR.data(), device());
     if (n < 0) throw std::runtime_error(std::string("SearchByBoW (B200): ") + orbfe_last_error());
+    return n;
+}
+
+// int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  (ORBmatcher.cc:1046-1324),
+// pinhole keyframes.  hasMapPoint*[i] = (pKF->GetMapPoint(i) != NULL); F12 = K1^-T * hat(t12) * R12 * K2^-1 (row major,
+// the matrix Pinhole::epipolarConstrain builds, Pinhole.cpp:191-194) and epipole = pKF2->mpCamera->project(T2w * Cw)
+// are computed once per keyframe pair by the caller (Eigen stays on the host).
+template <class FeatureVector>
+inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1, const std::vector<float>& uright1,
+                                  const std::vector<uint8_t>& hasMapPoint1, const FeatureVector& fv1,
+                                  const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2, const std::vector<float>& uright2,
+                                  const std::vector<uint8_t>& hasMapPoint2, const FeatureVector& fv2, const float F12[9],
+                                  const float epipole[2], const std::vector<float>& scaleFactors2,
+                                  const std::vector<float>& levelSigma2_2, bool bOnlyStereo, bool bCoarse, bool checkOrientation,
+                                  std::vector<std::pair<size_t, size_t> >& vMatchedPairs, int thLow = 50) {
+    const FlatFeatureVector f1(fv1), f2(fv2);
+    OrbfeTriSide a = {(int32_t)keys1.size(), reinterpret_cast<const OrbfeKeyPoint*>(keys1.data()), desc1.ptr(),
+                      uright1.empty() ? nullptr : uright1.data(), hasMapPoint1.data(), f1.view()};
+    OrbfeTriSide b = {(int32_t)keys2.size(), reinterpret_cast<const OrbfeKeyPoint*>(keys2.data()), desc2.ptr(),
+                      uright2.empty() ? nullptr : uright2.data(), hasMapPoint2.data(), f2.view()};
+    OrbfeTriParams prm;
+    for (int i = 0; i < 9; i++) prm.f12[i] = F12[i];
+    prm.epipole[0] = epipole[0]; prm.epipole[1] = epipole[1];
+    prm.scale_factors2 = scaleFactors2.data(); prm.level_sigma2_2 = levelSigma2_2.data(); prm.n_levels = (int32_t)scaleFactors2.size();
+    prm.only_stereo = bOnlyStereo; prm.coarse = bCoarse; prm.check_orientation = checkOrientation; prm.th_low = thLow;
+    std::vector<int32_t> m12(keys1.size(), -1);
+    const int n = orbfe_search_for_triangulation(&a, &b, &prm, m12.data(), device());
+    if (n < 0) throw std::runtime_error(std::string("SearchForTriangulation (B200): ") + orbfe_last_error());
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(n);
+    for (size_t i = 0; i < m12.size(); i++)
+        if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));   // :1316-1321
     return n;
 }
 

@@ -58,6 +58,17 @@ class BowSide(C.Structure):
                 ("fv", FeatureVectorC)]
 
 
+class TriSide(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("desc", C.c_void_p), ("uright", C.c_void_p),
+                ("has_map_point", C.c_void_p), ("fv", FeatureVectorC)]
+
+
+class TriParams(C.Structure):
+    _fields_ = [("f12", C.c_float * 9), ("epipole", C.c_float * 2), ("scale_factors2", C.c_void_p),
+                ("level_sigma2_2", C.c_void_p), ("n_levels", C.c_int32), ("only_stereo", C.c_int32),
+                ("coarse", C.c_int32), ("check_orientation", C.c_int32), ("th_low", C.c_int32)]
+
+
 _lib = None
 
 _vp, _i, _f, _sz, _ull = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_ulonglong
@@ -106,6 +117,7 @@ _SIGS = {
     "orbfe_bow_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "orbfe_bow_transform_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_search_by_bow": (_i, [C.POINTER(BowSide), C.POINTER(BowSide), _i, _i, _f, _i, _i, _vp, _vp, _i]),
+    "orbfe_search_for_triangulation": (_i, [C.POINTER(TriSide), C.POINTER(TriSide), C.POINTER(TriParams), _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -7,7 +7,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import BowSide, FrameView, ProjPoints, SearchParams, WindowParams, check, lib, ptr
+from ._lib import BowSide, TriParams, TriSide, FrameView, ProjPoints, SearchParams, WindowParams, check, lib, ptr
 
 MODE_MAPPOINTS, MODE_LASTFRAME, MODE_KEYFRAME = 0, 1, 2
 
@@ -215,6 +215,40 @@ class ORBmatcher:
     def SearchByBoWKeyFrames(self, kf1, kf2):
         n, mA, _ = self._bow(kf1, kf2, True, -1)
         return n, mA
+
+    # SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), ORBmatcher.cc:1046-1324 (pinhole).
+    # kf = (keys, desc, uright or None, has_map_point, feature vector); f12 = 3x3 fundamental matrix of
+    # Pinhole::epipolarConstrain, epipole = project(T2w * Cw).  -> nmatches, matches12
+    def SearchForTriangulation(self, kf1, kf2, f12, epipole, scale_factors2, level_sigma2_2, bOnlyStereo=False, bCoarse=False):
+        keep = []
+
+        def mk(side):
+            keys, desc, uright, has_mp, fv = side
+            t = TriSide()
+            keys = np.ascontiguousarray(keys)
+            desc = np.ascontiguousarray(desc, np.uint8)
+            has_mp = np.ascontiguousarray(has_mp, np.uint8)
+            nodes, start, feat = [np.ascontiguousarray(x, np.int32) for x in fv]
+            keep.extend([keys, desc, has_mp, nodes, start, feat])
+            t.n, t.keys, t.desc, t.has_map_point = len(keys), keys.ctypes.data, desc.ctypes.data, has_mp.ctypes.data
+            if uright is not None:
+                uright = np.ascontiguousarray(uright, np.float32)
+                keep.append(uright)
+                t.uright = uright.ctypes.data
+            t.fv.n_nodes, t.fv.node_id, t.fv.start, t.fv.feat = len(nodes), nodes.ctypes.data, start.ctypes.data, feat.ctypes.data
+            return t
+        a, b = mk(kf1), mk(kf2)
+        sf = np.ascontiguousarray(scale_factors2, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2_2, np.float32)
+        prm = TriParams()
+        prm.f12 = (C.c_float * 9)(*[float(x) for x in np.asarray(f12, np.float32).reshape(-1)])
+        prm.epipole = (C.c_float * 2)(*[float(x) for x in np.asarray(epipole, np.float32).reshape(-1)])
+        prm.scale_factors2, prm.level_sigma2_2, prm.n_levels = sf.ctypes.data, s2.ctypes.data, len(sf)
+        prm.only_stereo, prm.coarse = int(bOnlyStereo), int(bCoarse)
+        prm.check_orientation, prm.th_low = int(self.mbCheckOrientation), self.TH_LOW
+        m12 = np.empty(a.n, np.int32)
+        n = check(lib().orbfe_search_for_triangulation(C.byref(a), C.byref(b), C.byref(prm), ptr(m12), self.device))
+        return n, m12
 
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):

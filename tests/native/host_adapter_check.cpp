@@ -85,7 +85,18 @@ int main(int argc, char** argv) {
         f = fopen((p + ".bowmatch").c_str(), "wb");
         fwrite(mA.data(), 4, n, f);
         fclose(f);
-        fprintf(stderr, "bow words %zu nodes %zu matches %d\n", bow.size(), fv.size(), nb);
+        // SearchForTriangulation of the frame against itself (coarse: no epipolar gate; every other slot "has a point")
+        std::vector<uint8_t> hasMp(n);
+        for (int i = 0; i < n; i++) hasMp[i] = i & 1;
+        std::vector<float> noR, sf = ex.GetScaleFactors(), s2 = ex.GetScaleSigmaSquares();
+        const float F12[9] = {0, 0, 0, 0, 0, -1, 0, 1, 0}, ep[2] = {-1000.f, -1000.f};
+        std::vector<std::pair<size_t, size_t> > pairs;
+        const int nt = SearchForTriangulation(kps, desc, noR, hasMp, fv, kps, desc, noR, hasMp, fv, F12, ep, sf, s2, false, true, true,
+                                              pairs);
+        f = fopen((p + ".tri").c_str(), "wb");
+        for (auto& pr : pairs) { int32_t ab[2] = {(int32_t)pr.first, (int32_t)pr.second}; fwrite(ab, 4, 2, f); }
+        fclose(f);
+        fprintf(stderr, "bow words %zu nodes %zu matches %d tri %d\n", bow.size(), fv.size(), nb, nt);
     }
     int self = desc.rows ? ORB_SLAM3::b200::DescriptorDistance(desc.row(0), desc.row(0)) : 0;
     printf("%d %zu %d %d %d %.3f\n", mono, kps.size(), ex.GetLevels(), l1.cols, self, ex.GetScaleFactor());

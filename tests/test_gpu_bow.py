@@ -125,3 +125,27 @@ def test_search_by_bow_empty_and_disjoint(orbfe, vocs):
     shifted = (fvb[0] + 100000, fvb[1], fvb[2])            # no common node
     n, mA, _ = m.SearchByBoW((da, ang_a, None, fva), (db, ang_b, None, shifted))
     assert n == 0 and np.all(mA == -1)
+
+
+@pytest.mark.parametrize("seed,only_stereo,coarse,check_ori,stereo_frac", [(1, False, False, True, 0.0), (2, False, False, False, 0.5),
+                                                                           (3, True, False, True, 0.6), (4, False, True, True, 0.3)])
+def test_search_for_triangulation(orbfe, vocs, seed, only_stereo, coarse, check_ori, stereo_frac):
+    """ORBmatcher::SearchForTriangulation (ORBmatcher.cc:1046-1324) + Pinhole::epipolarConstrain, pinhole keyframes."""
+    from test_oracle_bow_vs_ref import SF, _tri_case
+    voc, gv, ov = vocs
+    k1, d1, ur1, mp1, k2, d2, ur2, mp2 = _tri_case(voc, seed, stereo_frac)
+    # F12 for K = (458.654, 457.296, 367.215, 248.375), R12 = I, t12 = (0.3, -0.01, -0.02); epipole of camera 1 in image 2
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]])
+    t = np.array([0.3, -0.01, -0.02])
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    f12 = (np.linalg.inv(K).T @ tx @ np.linalg.inv(K)).astype(np.float32)
+    c2 = -t
+    ep = np.array([fx * c2[0] / c2[2] + cx, fy * c2[1] / c2[2] + cy], np.float32)
+    _, fva = gv.transform(d1, 2)
+    _, fvb = gv.transform(d2, 2)
+    m = orbfe.ORBmatcher(0.6, check_ori)
+    n, m12 = m.SearchForTriangulation((k1, d1, ur1, mp1, fva), (k2, d2, ur2, mp2, fvb), f12, ep, SF, SF * SF, only_stereo, coarse)
+    en, em12 = O.search_for_triangulation(fva, k1, d1, ur1, mp1, fvb, k2, d2, ur2, mp2, f12, ep, SF, SF * SF, only_stereo, coarse,
+                                          check_ori)
+    assert n == en and n > 60 and np.array_equal(m12, em12)

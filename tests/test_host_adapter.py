@@ -80,3 +80,10 @@ def test_adapter_matches_oracle(tmp_path):
     _, mA, _ = O.search_by_bow(fv, odesc, okps["angle"], (i % 7) != 0, fv, odesc, okps["angle"], None, 50, False, 0.9, True)
     got = np.frombuffer((tmp_path / "o.bowmatch").read_bytes(), np.int32)
     assert np.array_equal(got, mA) and (mA >= 0).sum() > 0.3 * n
+    sf = ex.tables()["scale"]
+    has_mp = (i & 1).astype(np.uint8)
+    f12 = np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], np.float32)
+    nt, m12 = O.search_for_triangulation(fv, okps, odesc, None, has_mp, fv, okps, odesc, None, has_mp, f12,
+                                         np.array([-1000, -1000], np.float32), sf, ex.tables()["sigma2"], False, True, True)
+    pairs = np.frombuffer((tmp_path / "o.tri").read_bytes(), np.int32).reshape(-1, 2)
+    assert np.array_equal(pairs[:, 0], np.flatnonzero(m12 >= 0)) and np.array_equal(pairs[:, 1], m12[m12 >= 0]) and nt > 100

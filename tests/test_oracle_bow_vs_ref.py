@@ -135,3 +135,58 @@ def test_search_by_bow_kf_kf_vs_reference(voc_pair, seed, check_ori):
     n, mA, _ = O.search_by_bow(fva, d1, k1["angle"], s1 == 1, fvb, d2, k2["angle"], s2 == 1, 50, True, 0.75, check_ori)
     assert rn == n and n > 100
     assert np.array_equal(rout, mA)
+
+
+def _tri_case(voc, seed, stereo_frac):
+    """Two keyframes of one scene related by a sideways translation: KF2's keypoints are KF1's shifted along x by a
+    depth-dependent disparity (so the epipolar constraint holds for true matches) plus unrelated ones."""
+    from oracle.oracle import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    n1, n2 = 1500, 1400
+    d1 = synth.descriptors_near_words(voc, n1, seed + 1)
+    k1 = np.zeros(n1, KP_DTYPE)
+    k1["x"], k1["y"] = rng.uniform(20, 730, n1), rng.uniform(20, 460, n1)
+    k1["angle"] = rng.uniform(0, 360, n1)
+    k1["octave"] = rng.integers(0, 8, n1)
+    src = rng.integers(0, n1, n2)
+    d2 = np.stack([synth.flip_bits(d1[s], int(rng.integers(0, 25)), rng) for s in src])
+    k2 = k1[src].copy()
+    k2["x"] = k2["x"] - rng.uniform(2, 60, n2).astype(np.float32)              # along the epipolar line (pure x translation)
+    k2["y"] = k2["y"] + rng.normal(0, 0.8, n2).astype(np.float32)
+    off = rng.uniform(size=n2) < 0.25                                          # off the epipolar line
+    k2["y"][off] += rng.uniform(5, 40, off.sum()).astype(np.float32)
+    k2["angle"] = (k2["angle"] + 15 + rng.normal(0, 8, n2)) % 360.0
+    k2["octave"] = np.clip(k2["octave"] + rng.integers(-1, 2, n2), 0, 7)
+    ur1 = np.where(rng.uniform(size=n1) < stereo_frac, k1["x"] - 10, -1).astype(np.float32)
+    ur2 = np.where(rng.uniform(size=n2) < stereo_frac, k2["x"] - 10, -1).astype(np.float32)
+    mp1 = rng.uniform(size=n1) < 0.3
+    mp2 = rng.uniform(size=n2) < 0.3
+    return k1, d1, ur1, mp1, k2, d2, ur2, mp2
+
+
+@pytest.mark.parametrize("seed,only_stereo,coarse,check_ori,stereo_frac", [(1, False, False, True, 0.0), (2, False, False, False, 0.5),
+                                                                           (3, True, False, True, 0.6), (4, False, True, True, 0.3)])
+def test_search_for_triangulation_vs_reference(voc_pair, seed, only_stereo, coarse, check_ori, stereo_frac):
+    """ORBmatcher::SearchForTriangulation, ORBmatcher.cc:1046-1324, pinhole keyframes; Pinhole::epipolarConstrain
+    (Pinhole.cpp:186-216) compiled from the reference too."""
+    voc, rv, ov = voc_pair
+    k1, d1, ur1, mp1, k2, d2, ur2, mp2 = _tri_case(voc, seed, stereo_frac)
+    R.set_bounds((0.0, 0.0, 752.0, 480.0))
+    KF1, KF2 = R.RefFrame(k1, d1, SF, uright=ur1), R.RefFrame(k2, d2, SF, uright=ur2)
+    for kf, t in ((KF1, (0.0, 0.0, 0.0)), (KF2, (-0.3, 0.01, 0.02))):
+        R.set_camera(kf, 458.654, 457.296, 367.215, 248.375)
+        kf.set_pose(t)
+    KF1.set_mappoints(mp1); KF2.set_mappoints(mp2)
+    R.compute_bow(KF1, rv, 2); R.compute_bow(KF2, rv, 2)
+    rn, rm12, f12, ep = R.search_for_triangulation(KF1, KF2, only_stereo, coarse, check_ori)
+    assert rn >= 0
+    _, fva = ov.transform(d1, 2)
+    _, fvb = ov.transform(d2, 2)
+    n, m12 = O.search_for_triangulation(fva, k1, d1, ur1, mp1, fvb, k2, d2, ur2, mp2, f12, ep, SF, SF * SF, only_stereo, coarse,
+                                        check_ori)
+    assert rn == n and n > 60
+    assert np.array_equal(rm12, m12)
+    if not coarse:   # the epipolar gate must matter: the coarse search accepts more
+        nc, _ = O.search_for_triangulation(fva, k1, d1, ur1, mp1, fvb, k2, d2, ur2, mp2, f12, ep, SF, SF * SF, only_stereo, True,
+                                           check_ori)
+        assert nc > n
