@@ -154,7 +154,62 @@ def call_latencies(orbfe, device):
     cl, asg = np.zeros(1200, np.uint8), np.full(1200, -1, np.int32)
     out["search_by_projection_3000pts"] = timeit(lambda: m.SearchByProjection(F, pts, cl, asg))
     out["search_last_frame_3000pts"] = timeit(lambda: m.SearchByProjectionLastFrame(F, pts, cl, asg))
+    # keyframe-side searches and the bag-of-words path
+    sf = d["scale_factors"]
+    kpts = dict(pts, min_level=(d["level"] - 1).astype(np.int32), max_level=d["level"].astype(np.int32))
+    inv_s2 = (np.float32(1) / (sf * sf)).astype(np.float32)
+    out["fuse_search_3000pts"] = timeit(lambda: m.FuseSearch(F, kpts, inv_s2))
+    p12 = dict(u=d["keys"]["x"], v=d["keys"]["y"], radius=np.full(1200, 10, np.float32),
+               min_level=(d["keys"]["octave"] - 1).astype(np.int32), max_level=d["keys"]["octave"].astype(np.int32),
+               valid=np.ones(1200, np.uint8), desc=d["fdesc"])
+    out["search_by_sim3_1200x1200"] = timeit(lambda: m.SearchBySim3(F, F, p12, p12))
+    voc = synth.make_vocabulary_fast(10, 6, 1)                    # the shape of ORBvoc.txt: 1.1 M nodes, 10^6 words
+    gv = orbfe.ORBVocabulary(10, 6, voc["parent"], voc["desc"], voc["weight"], device=device)
+    out["bow_transform_1200feat_k10_L6"] = timeit(lambda: gv.transform_features(dl, 4))
+    _, fvl = gv.transform(dl, 4)
+    _, fvr = gv.transform(dr, 4)
+    ones_l = np.ones(len(dl), np.uint8)
+    out["search_by_bow_1200x1200"] = timeit(lambda: m.SearchByBoW((dl, kl["angle"], ones_l, fvl), (dr, kr["angle"], None, fvr)))
+    f12 = np.array([0, 0, 0, 0, 0, -1, 0, 1, 0], np.float32)
+    tri = (lambda: m.SearchForTriangulation((kl, dl, None, np.zeros(len(dl), np.uint8), fvl),
+                                            (kr, dr, None, np.zeros(len(dr), np.uint8), fvr), f12,
+                                            np.array([-1e4, -1e4], np.float32), sf, sf * sf))
+    out["search_for_triangulation_1200x1200"] = timeit(tri)
+    out["cpu_reference"] = cpu_reference_call_latencies(d, pts, dl, dr, kl, kr, timeit)
     return out
+
+
+def cpu_reference_call_latencies(d, pts, dl, dr, kl, kr, timeit):
+    """The reference's own functions (oracle/_ref/libref_orbmatcher.so: ORBmatcher bodies and DBoW2 compiled from the
+    reference tree) on the same inputs, one host thread, as the reference runs them.  Reported beside the GPU call
+    latencies; empty when the library was not built."""
+    try:
+        from oracle import ref as R
+        if not R.matcher_available():
+            return {}
+        import tempfile
+        import synth
+        out = {}
+        R.set_bounds(d["bounds"])
+        F = R.RefFrame(d["keys"], d["fdesc"], d["scale_factors"])
+        n = len(pts["u"])
+        mp = dict(in_view=np.ones(n, np.uint8), proj_x=pts["u"], proj_y=pts["v"], proj_xr=pts["u"], level=d["level"],
+                  view_cos=np.full(n, 0.9, np.float32), desc=pts["desc"])
+        out["search_by_projection_3000pts"] = timeit(lambda: F.search_mappoints(mp, 1.0, False, 0.0, 0.8), 10)
+        voc = synth.make_vocabulary(10, 4, 3)                     # text vocabularies of ORBvoc size are 150 MB: use 10^4 words
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "voc.txt")
+            synth.write_vocabulary_text(path, voc)
+            rv = R.RefVocabulary(path)
+        out["bow_transform_1200feat_k10_L4"] = timeit(lambda: rv.transform(dl, 2), 10)
+        sf = d["scale_factors"]
+        KF, FR = R.RefFrame(kl, dl, sf), R.RefFrame(kr, dr, sf)
+        KF.set_mappoints(np.ones(len(kl), np.uint8))
+        R.compute_bow(KF, rv, 2); R.compute_bow(FR, rv, 2)
+        out["search_by_bow_1200x1200_k10_L4"] = timeit(lambda: R.search_by_bow_kf_f(KF, FR, 0.8, True), 10)
+        return out
+    except Exception as e:                                         # the checker is optional for the bench line
+        return {"error": str(e)[:200]}
 
 
 def run_reference(args):
