@@ -14,6 +14,9 @@
 //   m3_k = min(e_k, e_k+1, e_k+2),  min9_k = min(m3_k, m3_k+3, m3_k+6)
 // an arc minimum costs two 3-input ops.  best = max(0, max_k min9_k - 256, 256 - min_k max9_k).
 //
+// The kernel uses fc_margin2_raw below, which runs the same network on the raw ring values (no differences);
+// fc_margin2 is kept because the host unit test checks both against the oracle.
+//
 // NOTE (measured on B200, nvcc 12.9): a formulation that folds `max(best, -mx)` into the running
 // maximum is MISCOMPILED for sm_100a (ptxas drops the negation when it fuses into VIMNMX3); this
 // formulation negates once, outside the min/max network, and is checked on the device against
@@ -81,6 +84,30 @@ static FC_HD uint32_t fc_margin2(const uint32_t* e, uint32_t sub2) {
     // best = max(0, A-256, 256-B); margin = max(0, best - sub)
     const uint32_t a = fc_sub2(A, fc_add2(FC_BIAS2, sub2));
     const uint32_t b = fc_sub2(fc_sub2(FC_BIAS2, sub2), B);
+    return fc_max3s_relu(a, b, 0u);
+}
+
+// The same margin from the RAW ring values (r[k] = two ring pixels as 16-bit lanes, c2 = the two centres), without
+// forming the 16 differences:  min over an arc of (c - ring) = c - max over the arc of ring, and
+// min over an arc of (ring - c) = (min over the arc of ring) - c, so
+//   best = max(0, c - min_k max9_k(ring), max_k min9_k(ring) - c).
+// 96 packed min/max per pixel pair plus a 5-instruction tail (the differences cost 16 more).
+static FC_HD uint32_t fc_margin2_raw(const uint32_t* r, uint32_t c2, uint32_t sub2) {
+    uint32_t mn3[16], mx3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        mn3[k] = fc_min3u(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+        mx3[k] = fc_max3u(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    }
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;  // min_k max9_k, max_k min9_k
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo = fc_minu(lo, fc_max3u(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+        hi = fc_maxu(hi, fc_min3u(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
+    }
+    // lanes are in [0, 255]; the packed subtractions below may go negative per lane (signed 16-bit)
+    const uint32_t a = fc_sub2(fc_sub2(c2, sub2), lo);   // (c - sub) - min max9
+    const uint32_t b = fc_sub2(hi, fc_add2(c2, sub2));   // max min9 - (c + sub)
     return fc_max3s_relu(a, b, 0u);
 }
 

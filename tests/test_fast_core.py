@@ -43,3 +43,7 @@ def test_margin_map_equals_oracle(core, kind, sub):
     ref[c[:, 1], c[:, 0]] = c[:, 2] + 1
     exp = np.maximum(ref - sub, 0)
     assert np.array_equal(out[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
+    # the raw-value formulation used by k_fast_score (no per-ring differences)
+    out2 = np.zeros((h, w), np.uint8)
+    core.fast_core_margins_raw(img.ctypes.data_as(C.c_void_p), w, h, sub, out2.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out2[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
