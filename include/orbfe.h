@@ -357,6 +357,27 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame,
                        const OrbfeKeyPoint* keys_r, const uint8_t* desc_r, int nr, float mbf,
                        float mb, float* u_right, float* depth);
 
+/* ---- Frame intake: the OpenCV calls ORB-SLAM3 makes on an image before ORBextractor ----
+ * cv::cvtColor(im, im, cv::COLOR_{RGB,BGR,RGBA,BGRA}2GRAY)   src/Tracking.cc:1563-1590, 1623-1636, 1702-1716
+ * channels = 3 or 4, rgb_order != 0 when the first channel is red (mbRGB).  8-bit, OpenCV 4.x fixed point. */
+int orbfe_cvt_gray(const uint8_t* src, int rows, int cols, size_t src_step, int channels,
+                   int rgb_order, uint8_t* dst, size_t dst_step, int device);
+int orbfe_cvt_gray_device(const uint8_t* d_src, int rows, int cols, size_t src_step, int channels,
+                          int rgb_order, uint8_t* d_dst, size_t dst_step, void* stream);
+/* cv::remap(imLeft, imLeftToFeed, M1l, M2l, cv::INTER_LINEAR)   src/System.cc:286-293: 8-bit single channel,
+ * CV_32FC1 maps (x and y, dst_rows x dst_cols, as Settings builds them with initUndistortRectifyMap),
+ * BORDER_CONSTANT with value 0 (cv::remap's defaults). */
+int orbfe_remap_linear(const uint8_t* src, int src_rows, int src_cols, size_t src_step,
+                       const float* map_x, const float* map_y, int dst_rows, int dst_cols,
+                       uint8_t* dst, size_t dst_step, int device);
+int orbfe_remap_linear_device(const uint8_t* d_src, int src_rows, int src_cols, size_t src_step,
+                              const float* d_map_x, const float* d_map_y, size_t map_step_floats,
+                              int dst_rows, int dst_cols, uint8_t* d_dst, size_t dst_step,
+                              void* stream);
+/* cv::resize(im, imToFeed, settings_->newImSize())   src/System.cc:295-297, 371-376, 457-459 (INTER_LINEAR, 8-bit). */
+int orbfe_resize_linear(const uint8_t* src, int src_rows, int src_cols, size_t src_step,
+                        int dst_rows, int dst_cols, uint8_t* dst, size_t dst_step, int device);
+
 /* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
 const char* orbfe_version(void);
 

@@ -239,4 +239,42 @@ void bf_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// cv::cvtColor to gray, 8-bit (OpenCV 4.x color_rgb: RY15 = 9798, GY15 = 19235, BY15 = 3735, shift 15).
+// ---------------------------------------------------------------------------------------
+void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, bool rgb, uint8_t* dst, size_t dstep) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t* p = src + y * sstep + (size_t)x * channels;
+            const int b = rgb ? p[2] : p[0], g = p[1], r = rgb ? p[0] : p[2];
+            dst[y * dstep + x] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// cv::remap INTER_LINEAR, 8UC1, CV_32FC1 maps, BORDER_CONSTANT(0) (OpenCV imgwarp.cpp): coordinates are rounded to
+// 1/32 px (INTER_BITS = 5) with cvRound, the integer part is kept as short, the four weights come from the
+// fixed-point bilinear table (INTER_REMAP_COEF_BITS = 15; for bilinear the products are exact multiples of 32,
+// so the table sums to 2^15 without the correction step), result = (sum + 2^14) >> 15.
+// ---------------------------------------------------------------------------------------
+void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, int dw,
+                     int dh, uint8_t* dst, size_t dstep) {
+    auto fix = [](float v) {
+        const float s = v * 32.0f;
+        if (!(s > -1.0e9f)) return -(1 << 30);
+        if (!(s < 1.0e9f)) return 1 << 30;
+        return cvRound(s);
+    };
+    auto sat16 = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            const int sx = fix(mapx[(size_t)y * dw + x]), sy = fix(mapy[(size_t)y * dw + x]);
+            const int ix = sat16(sx >> 5), iy = sat16(sy >> 5), fx = sx & 31, fy = sy & 31;
+            auto px = [&](int yy, int xx) { return (yy >= 0 && yy < sh && xx >= 0 && xx < sw) ? (int)src[yy * sstep + xx] : 0; };
+            const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+            dst[y * dstep + x] = (uint8_t)((px(iy, ix) * w00 + px(iy, ix + 1) * w01 + px(iy + 1, ix) * w10 +
+                                           px(iy + 1, ix + 1) * w11 + (1 << 14)) >> 15);
+        }
+}
+
 }  // namespace cvp

@@ -75,4 +75,10 @@ int hamming256(const uint8_t* a, const uint8_t* b);
 // ascending distance, ties -> lower train index.  idx/dist are nq x 2; missing = -1.
 void bf_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* idx, int* dist);
 
+// cv::cvtColor(.., COLOR_{BGR,RGB,BGRA,RGBA}2GRAY), 8-bit: (B*3735 + G*19235 + R*9798 + 2^14) >> 15 (OpenCV 4.x).
+void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, bool rgb, uint8_t* dst, size_t dstep);
+// cv::remap(src, dst, mapx, mapy, INTER_LINEAR) with CV_32FC1 maps, BORDER_CONSTANT(0), 8-bit single channel.
+void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, int dw,
+                     int dh, uint8_t* dst, size_t dstep);
+
 }  // namespace cvp

@@ -411,3 +411,21 @@ def search_for_triangulation(fvA, keysA, descA, urightA, has_mp_a, fvB, keysB, d
         len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), _p(keysB), _p(descB), None if urb is None else _p(urb), _p(mpb), len(keysB),
         _p(f12), _p(ep), _p(sf), _p(s2), int(only_stereo), int(coarse), int(check_orientation), int(th_low), _p(m12))
     return n, m12
+
+
+# ---------------------------------------------------------------- frame intake
+def cvt_gray(img, rgb=False):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().oracle_cvt_gray(_p(img), w, h, img.strides[0], c, int(rgb), _p(out), w)
+    return out
+
+
+def remap_linear(src, mapx, mapy):
+    src = np.ascontiguousarray(src, np.uint8)
+    mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().oracle_remap_linear(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(mapx), _p(mapy), dw, dh, _p(out), dw)
+    return out

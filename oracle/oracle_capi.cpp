@@ -235,6 +235,14 @@ void oracle_fisheye_matches(const uint8_t* q, int nq, const uint8_t* t, int nt, 
 }
 
 
+void oracle_cvt_gray(const uint8_t* src, int w, int h, int sstep, int channels, int rgb, uint8_t* dst, int dstep) {
+    cvp::cvt_gray_u8(src, w, h, sstep, channels, rgb != 0, dst, dstep);
+}
+void oracle_remap_linear(const uint8_t* src, int sw, int sh, int sstep, const float* mapx, const float* mapy, int dw, int dh,
+                         uint8_t* dst, int dstep) {
+    cvp::remap_linear_u8(src, sw, sh, sstep, mapx, mapy, dw, dh, dst, dstep);
+}
+
 // ---- bag of words ---------------------------------------------------------------------------------
 void* oracle_voc_create(int k, int L, int scoring, int weighting, int nNodes, const int32_t* parent,
                         const uint8_t* desc, const double* weight) {

@@ -343,6 +343,33 @@ inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const 
     return n;
 }
 
+// ---- Frame intake: the OpenCV calls made on an image before ORBextractor -------------------------------------------
+// cv::cvtColor(im, im, cv::COLOR_{RGB,BGR,RGBA,BGRA}2GRAY)  (Tracking.cc:1563-1590, 1623-1636, 1702-1716)
+inline void cvtColorToGray(const cv::Mat& src, cv::Mat& dst, int channels, bool rgbOrder) {
+    cv::Mat out(src.rows, src.cols, CV_8UC1);
+    if (orbfe_cvt_gray(src.data, src.rows, src.cols, (size_t)src.step, channels, rgbOrder ? 1 : 0, out.data, (size_t)out.step,
+                       device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("cvtColor (B200): ") + orbfe_last_error());
+    dst = out;
+}
+// cv::remap(imLeft, imLeftToFeed, M1l, M2l, cv::INTER_LINEAR)  (System.cc:292-293); M1 / M2 = the CV_32FC1 maps of
+// Settings (x and y), passed as float pointers with rows x cols of the rectified image.
+inline void remap(const cv::Mat& src, cv::Mat& dst, const float* mapX, const float* mapY, int rows, int cols) {
+    cv::Mat out(rows, cols, CV_8UC1);
+    if (orbfe_remap_linear(src.data, src.rows, src.cols, (size_t)src.step, mapX, mapY, rows, cols, out.data, (size_t)out.step,
+                           device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("remap (B200): ") + orbfe_last_error());
+    dst = out;
+}
+// cv::resize(im, imToFeed, settings_->newImSize())  (System.cc:295-297)
+inline void resize(const cv::Mat& src, cv::Mat& dst, cv::Size dsize) {
+    cv::Mat out(dsize.height, dsize.width, CV_8UC1);
+    if (orbfe_resize_linear(src.data, src.rows, src.cols, (size_t)src.step, dsize.height, dsize.width, out.data,
+                            (size_t)out.step, device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("resize (B200): ") + orbfe_last_error());
+    dst = out;
+}
+
 // void Frame::ComputeStereoMatches()   Frame.h:116, Frame.cc:1102-1358
 inline void ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& keysL,
                                  const cv::Mat& descL, const std::vector<cv::KeyPoint>& keysR, const cv::Mat& descR,

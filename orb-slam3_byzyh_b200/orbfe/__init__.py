@@ -18,5 +18,6 @@ from ._lib import (EMPTY_IMAGE, ERR_CAPACITY, ERR_CUDA, ERR_INVALID, EXPORTS, KP
 from .extractor import ORBextractor
 from .matcher import FrameData, ORBmatcher
 from .vocabulary import ORBVocabulary
+from . import intake
 
-__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "FrameData", "KP_DTYPE", "OrbfeError", "lib", "LIB_PATH", "EXPORTS"]
+__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "intake", "FrameData", "KP_DTYPE", "OrbfeError", "lib", "LIB_PATH", "EXPORTS"]

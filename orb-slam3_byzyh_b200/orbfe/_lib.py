@@ -118,6 +118,11 @@ _SIGS = {
     "orbfe_bow_transform_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_search_by_bow": (_i, [C.POINTER(BowSide), C.POINTER(BowSide), _i, _i, _f, _i, _i, _vp, _vp, _i]),
     "orbfe_search_for_triangulation": (_i, [C.POINTER(TriSide), C.POINTER(TriSide), C.POINTER(TriParams), _vp, _i]),
+    "orbfe_cvt_gray": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _i]),
+    "orbfe_cvt_gray_device": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _vp]),
+    "orbfe_remap_linear": (_i, [_vp, _i, _i, _sz, _vp, _vp, _i, _i, _vp, _sz, _i]),
+    "orbfe_remap_linear_device": (_i, [_vp, _i, _i, _sz, _vp, _vp, _sz, _i, _i, _vp, _sz, _vp]),
+    "orbfe_resize_linear": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -1,0 +1,36 @@
+"""The OpenCV calls ORB-SLAM3 makes on a frame before ORBextractor, on the device (csrc/intake.cu):
+cv::cvtColor to gray (Tracking.cc:1563-1590), cv::remap stereo rectification (System.cc:286-293) and cv::resize
+(System.cc:295-297).  Bit-exact with cv2 4.13 for 8-bit images."""
+import numpy as np
+
+from ._lib import check, lib, ptr
+
+
+def cvtColorToGray(img, rgb=False, device=0):
+    """cv::cvtColor(img, gray, COLOR_{BGR,RGB,BGRA,RGBA}2GRAY); rgb = the first channel is red (Tracking::mbRGB)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    check(lib().orbfe_cvt_gray(ptr(img), h, w, img.strides[0], c, int(rgb), ptr(out), w, device))
+    return out
+
+
+def remap(src, map_x, map_y, device=0):
+    """cv::remap(src, dst, M1, M2, cv::INTER_LINEAR) with CV_32FC1 maps and the default constant (0) border."""
+    src = np.ascontiguousarray(src, np.uint8)
+    map_x = np.ascontiguousarray(map_x, np.float32)
+    map_y = np.ascontiguousarray(map_y, np.float32)
+    dh, dw = map_x.shape
+    out = np.empty((dh, dw), np.uint8)
+    check(lib().orbfe_remap_linear(ptr(src), src.shape[0], src.shape[1], src.strides[0], ptr(map_x), ptr(map_y), dh, dw,
+                                   ptr(out), dw, device))
+    return out
+
+
+def resize(src, dsize, device=0):
+    """cv::resize(src, dst, dsize) (INTER_LINEAR); dsize = (width, height) as in OpenCV."""
+    src = np.ascontiguousarray(src, np.uint8)
+    dw, dh = dsize
+    out = np.empty((dh, dw), np.uint8)
+    check(lib().orbfe_resize_linear(ptr(src), src.shape[0], src.shape[1], src.strides[0], dh, dw, ptr(out), dw, device))
+    return out

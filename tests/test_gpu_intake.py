@@ -1,0 +1,86 @@
+"""GPU parity of the frame-intake kernels (csrc/intake.cu: cvtColor to gray, remap, resize) against the oracle's
+restatement AND against cv2 4.13 itself (the OpenCV the reference links)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import oracle as O
+from test_oracle_cvprims import _rectify_like_maps
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def orbfe():
+    sys.path.insert(0, os.path.join(ROOT, "orb-slam3_byzyh_b200"))
+    import orbfe as m
+    return m
+
+
+def _cv2():
+    try:
+        import cv2
+        return cv2
+    except ImportError:
+        return None
+
+
+@pytest.mark.parametrize("channels,rgb,code", [(3, False, "COLOR_BGR2GRAY"), (3, True, "COLOR_RGB2GRAY"),
+                                               (4, False, "COLOR_BGRA2GRAY"), (4, True, "COLOR_RGBA2GRAY")])
+def test_cvt_gray(orbfe, channels, rgb, code):
+    rng = np.random.default_rng(channels * 2 + rgb)
+    img = rng.integers(0, 256, (480, 752, channels)).astype(np.uint8)
+    got = orbfe.intake.cvtColorToGray(img, rgb)
+    assert np.array_equal(got, O.cvt_gray(img, rgb))
+    cv2 = _cv2()
+    if cv2 is not None:
+        assert np.array_equal(got, cv2.cvtColor(img, getattr(cv2, code)))
+    small = img[:7, :5].copy()                               # odd sizes, strided source
+    assert np.array_equal(orbfe.intake.cvtColorToGray(small, rgb), O.cvt_gray(small, rgb))
+
+
+@pytest.mark.parametrize("dh,dw,sh,sw,seed", [(480, 752, 480, 752, 0), (100, 131, 90, 140, 1), (720, 1280, 800, 1400, 2)])
+def test_remap(orbfe, dh, dw, sh, sw, seed):
+    rng = np.random.default_rng(seed)
+    src = synth.synth_frame(sh, sw, seed)
+    mx, my = _rectify_like_maps(dh, dw, sh, sw, seed)
+    got = orbfe.intake.remap(src, mx, my)
+    assert np.array_equal(got, O.remap_linear(src, mx, my))
+    mx2 = (rng.integers(-40 * 64, (sw + 40) * 64, (dh, dw)) / 64.0).astype(np.float32)   # halves, integers, outside
+    my2 = (rng.integers(-40 * 64, (sh + 40) * 64, (dh, dw)) / 64.0).astype(np.float32)
+    mx2[0, :6] = [-1e7, 1e7, -0.5, sw - 0.5, np.nan, np.inf]
+    got2 = orbfe.intake.remap(src, mx2, my2)
+    assert np.array_equal(got2, O.remap_linear(src, mx2, my2))
+    cv2 = _cv2()
+    if cv2 is not None:
+        assert np.array_equal(got, cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+        ok = np.isfinite(mx2)
+        assert np.array_equal(got2[ok], cv2.remap(src, mx2, my2, cv2.INTER_LINEAR)[ok])
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(752, 480, 600, 350), (1280, 720, 640, 360), (640, 480, 752, 480), (100, 60, 300, 180),
+                                          (333, 222, 333, 222)])
+def test_resize(orbfe, sw, sh, dw, dh):
+    src = synth.synth_frame(sh, sw, sw + dh)
+    got = orbfe.intake.resize(src, (dw, dh))
+    assert np.array_equal(got, O.resize_linear(src, dw, dh))
+    cv2 = _cv2()
+    if cv2 is not None:
+        assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_rectify_then_extract_equals_reference_chain(orbfe):
+    """The stereo intake chain of System::TrackStereo: remap on the device, then ORBextractor, equals
+    cv-style remap (oracle) followed by the oracle extractor."""
+    src = synth.synth_frame(480, 752, 5)
+    mx, my = _rectify_like_maps(480, 752, 480, 752, 3)
+    rect = orbfe.intake.remap(src, mx, my)
+    ex = orbfe.ORBextractor(1000)
+    _, k, d = ex(rect, None, (0, 0))
+    oex = O.Extractor(1000)
+    _, ok, od = oex(O.remap_linear(src, mx, my), (0, 0))
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od) and len(k) > 500

@@ -109,3 +109,43 @@ def test_hamming_matches_popcount():
         assert O.hamming(a[i], b[i]) == int(np.unpackbits(a[i] ^ b[i]).sum())
     assert O.hamming(a[0], a[0]) == 0
     assert O.hamming(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+@pytest.mark.parametrize("code,channels,rgb", [("COLOR_BGR2GRAY", 3, False), ("COLOR_RGB2GRAY", 3, True),
+                                               ("COLOR_BGRA2GRAY", 4, False), ("COLOR_RGBA2GRAY", 4, True)])
+def test_cvt_gray(code, channels, rgb):
+    """cv::cvtColor to gray as Tracking::GrabImage* calls it (src/Tracking.cc:1563-1590)."""
+    rng = np.random.default_rng(channels + rgb)
+    img = rng.integers(0, 256, (61, 83, channels)).astype(np.uint8)
+    img[0, :8] = [[0] * channels, [255] * channels] * 4
+    assert np.array_equal(O.cvt_gray(img, rgb), cv2.cvtColor(img, getattr(cv2, code)))
+
+
+def _rectify_like_maps(dh, dw, sh, sw, seed):
+    """Maps shaped like initUndistortRectifyMap output: smooth radial distortion plus a small rotation, reaching
+    outside the source near the corners."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:dh, 0:dw].astype(np.float64)
+    xn, yn = (x - dw / 2) / (0.9 * dw), (y - dh / 2) / (0.9 * dw)
+    r2 = xn * xn + yn * yn
+    k1, k2 = rng.uniform(-0.4, 0.4), rng.uniform(-0.1, 0.2)
+    th = rng.uniform(-0.03, 0.03)
+    f = 1 + k1 * r2 + k2 * r2 * r2
+    xd, yd = xn * f, yn * f
+    mx = (np.cos(th) * xd - np.sin(th) * yd) * 0.9 * dw * sw / dw + sw / 2
+    my = (np.sin(th) * xd + np.cos(th) * yd) * 0.9 * dw * sh / dh + sh / 2
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
+@pytest.mark.parametrize("dh,dw,sh,sw,seed", [(480, 752, 480, 752, 0), (100, 131, 90, 140, 1), (64, 64, 200, 300, 2)])
+def test_remap_linear(dh, dw, sh, sw, seed):
+    """cv::remap(.., INTER_LINEAR) with CV_32FC1 maps and the default constant border (src/System.cc:292-293)."""
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, 256, (sh, sw)).astype(np.uint8)
+    mx, my = _rectify_like_maps(dh, dw, sh, sw, seed)
+    assert np.array_equal(O.remap_linear(src, mx, my), cv2.remap(src, mx, my, cv2.INTER_LINEAR))
+    # exact half positions (round-half-even of x*32), integer positions, far outside, negative fractions
+    mx2 = (rng.integers(-40 * 64, (sw + 40) * 64, (dh, dw)) / 64.0).astype(np.float32)
+    my2 = (rng.integers(-40 * 64, (sh + 40) * 64, (dh, dw)) / 64.0).astype(np.float32)
+    mx2[0, :4] = [-1e7, 1e7, -0.5, sw - 0.5]
+    assert np.array_equal(O.remap_linear(src, mx2, my2), cv2.remap(src, mx2, my2, cv2.INTER_LINEAR))
