@@ -378,6 +378,14 @@ int orbfe_remap_linear_device(const uint8_t* d_src, int src_rows, int src_cols, 
 int orbfe_resize_linear(const uint8_t* src, int src_rows, int src_cols, size_t src_step,
                         int dst_rows, int dst_cols, uint8_t* dst, size_t dst_step, int device);
 
+/* void Frame::UndistortKeyPoints()   include/Frame.h:309, src/Frame.cc:1003-1051: cv::undistortPoints(mat, mat, K,
+ * mDistCoef, cv::Mat(), mK) on the keypoint coordinates (five iterations in double, OpenCV 4.x), every other
+ * KeyPoint field copied; dist_coef = mDistCoef (k1 k2 p1 p2 [k3 ...], up to 14), a zero first coefficient means
+ * "no distortion" and copies the keypoints (:1005-1009).  fx..cy = the float entries of mK. */
+int orbfe_undistort_keypoints(const OrbfeKeyPoint* keys, int n, float fx, float fy, float cx,
+                              float cy, const float* dist_coef, int n_dist, OrbfeKeyPoint* keys_un,
+                              int device);
+
 /* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
 const char* orbfe_version(void);
 

@@ -277,4 +277,31 @@ void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const flo
         }
 }
 
+// ---------------------------------------------------------------------------------------
+// cv::undistortPoints with P = K and no rectification (Frame::UndistortKeyPoints, reference src/Frame.cc:1003-1051).
+// ---------------------------------------------------------------------------------------
+void undistort_points(const float* xy, int n, double fx, double fy, double cx, double cy, const double* dist, int ndist,
+                      float* out) {
+    double k[14] = {0};
+    for (int i = 0; i < ndist && i < 14; i++) k[i] = dist[i];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    for (int i = 0; i < n; i++) {
+        const double u = xy[2 * i], v = xy[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+            const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + 0 * y + cx, yy = 0 * x + fy * y + cy, ww = 1. / (0 * x + 0 * y + 1);
+        out[2 * i] = (float)(xx * ww);
+        out[2 * i + 1] = (float)(yy * ww);
+    }
+}
+
 }  // namespace cvp

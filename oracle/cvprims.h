@@ -81,4 +81,10 @@ void cvt_gray_u8(const uint8_t* src, int w, int h, size_t sstep, int channels, b
 void remap_linear_u8(const uint8_t* src, int sw, int sh, size_t sstep, const float* mapx, const float* mapy, int dw,
                      int dh, uint8_t* dst, size_t dstep);
 
+// cv::undistortPoints(src, dst, K, distCoeffs, noArray(), K) for float points (OpenCV undistort.dispatch.cpp
+// cvUndistortPointsInternal: 5 fixed-point iterations in double, then re-projection with K).  dist = up to 14
+// coefficients in OpenCV order (k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4 ...); xy / out = n x 2 floats.
+void undistort_points(const float* xy, int n, double fx, double fy, double cx, double cy, const double* dist, int ndist,
+                      float* out);
+
 }  // namespace cvp

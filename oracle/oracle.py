@@ -429,3 +429,14 @@ def remap_linear(src, mapx, mapy):
     out = np.empty((dh, dw), np.uint8)
     lib().oracle_remap_linear(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(mapx), _p(mapy), dw, dh, _p(out), dw)
     return out
+
+
+def undistort_points(xy, K, dist):
+    """cv::undistortPoints(xy, K, dist, None, K) for n x 2 float points; K = (fx, fy, cx, cy) as float32 values."""
+    xy = np.ascontiguousarray(xy, np.float32)
+    d = np.ascontiguousarray(np.asarray(dist, np.float32).astype(np.float64))
+    out = np.empty_like(xy)
+    fx, fy, cx, cy = [float(np.float32(v)) for v in K]
+    lib().oracle_undistort_points(_p(xy), len(xy), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), _p(d),
+                                  len(d), _p(out))
+    return out

@@ -242,6 +242,10 @@ void oracle_remap_linear(const uint8_t* src, int sw, int sh, int sstep, const fl
                          uint8_t* dst, int dstep) {
     cvp::remap_linear_u8(src, sw, sh, sstep, mapx, mapy, dw, dh, dst, dstep);
 }
+void oracle_undistort_points(const float* xy, int n, double fx, double fy, double cx, double cy, const double* dist, int ndist,
+                             float* out) {
+    cvp::undistort_points(xy, n, fx, fy, cx, cy, dist, ndist, out);
+}
 
 // ---- bag of words ---------------------------------------------------------------------------------
 void* oracle_voc_create(int k, int L, int scoring, int weighting, int nNodes, const int32_t* parent,

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "orbfe_internal.h"
@@ -89,6 +90,35 @@ k_resize_area2(const uint8_t* __restrict__ src, size_t sstep, int drows, int dco
     const uint8_t* s0 = src + (size_t)(2 * y) * sstep + 2 * x;
     const uint8_t* s1 = s0 + sstep;
     dst[(size_t)y * dstep + x] = (uint8_t)((s0[0] + s0[1] + s1[0] + s1[1] + 2) >> 2);
+}
+
+// Frame::UndistortKeyPoints (src/Frame.cc:1003-1051) = cv::undistortPoints(pts, K, mDistCoef, noArray(), mK): five
+// fixed-point iterations of the distortion model in double, re-projection with K, result stored as float.  Compiled
+// with --fmad=false: every product and sum rounds like OpenCV's scalar code.
+struct UndistPrm { double fx, fy, cx, cy, k[14]; };
+
+__global__ void k_undistort(const OrbfeKeyPoint* __restrict__ in, int n, UndistPrm P, OrbfeKeyPoint* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    OrbfeKeyPoint kp = in[i];
+    const double ifx = 1. / P.fx, ify = 1. / P.fy;
+    const double u = kp.x, v = kp.y;
+    double x = (u - P.cx) * ifx, y = (v - P.cy) * ify;
+    const double x0 = x, y0 = y;
+    const double* k = P.k;
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) { x = (u - P.cx) * ifx; y = (v - P.cy) * ify; break; }
+        const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    const double xx = P.fx * x + 0 * y + P.cx, yy = 0 * x + P.fy * y + P.cy, ww = 1. / (0 * x + 0 * y + 1);
+    kp.x = (float)(xx * ww);
+    kp.y = (float)(yy * ww);
+    out[i] = kp;
 }
 
 inline int cv_floor_f(float v) { return (int)floorf(v); }
@@ -227,5 +257,29 @@ extern "C" int orbfe_resize_linear(const uint8_t* src, int src_rows, int src_col
     ICK(cudaMemcpy2DAsync(dst, dst_step, S.ptr<uint8_t>(oD), (size_t)dst_cols, (size_t)dst_cols, dst_rows,
                           cudaMemcpyDeviceToHost, st));
     ICK(cudaStreamSynchronize(st));
+    return ORBFE_OK;
+}
+
+extern "C" int orbfe_undistort_keypoints(const OrbfeKeyPoint* keys, int n, float fx, float fy, float cx, float cy,
+                                         const float* dist_coef, int n_dist, OrbfeKeyPoint* keys_un, int device) {
+    if (n < 0 || (n > 0 && (!keys || !keys_un)) || n_dist < 0 || n_dist > 14 || (n_dist > 0 && !dist_coef))
+        return ifail(ORBFE_ERR_INVALID, "undistort: bad arguments");
+    if (n == 0) return ORBFE_OK;
+    if (n_dist == 0 || dist_coef[0] == 0.0f) {   // Frame.cc:1005-1009: mvKeysUn = mvKeys
+        if (keys_un != keys) memcpy(keys_un, keys, sizeof(OrbfeKeyPoint) * (size_t)n);
+        return ORBFE_OK;
+    }
+    int rc = check_dev(device);
+    if (rc != ORBFE_OK) return rc;
+    UndistPrm P;
+    P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
+    for (int i = 0; i < 14; i++) P.k[i] = i < n_dist ? (double)dist_coef[i] : 0.0;
+    OrbfeStage S;
+    const size_t iK = S.in(keys, sizeof(OrbfeKeyPoint) * (size_t)n), oK = S.out(keys_un, sizeof(OrbfeKeyPoint) * (size_t)n);
+    ICK(S.commit(device));
+    ICK(S.upload());
+    k_undistort<<<(n + 127) / 128, 128, 0, S.stream()>>>(S.ptr<OrbfeKeyPoint>(iK), n, P, S.ptr<OrbfeKeyPoint>(oK));
+    ICK(cudaGetLastError());
+    ICK(S.download());
     return ORBFE_OK;
 }

@@ -361,6 +361,15 @@ inline void remap(const cv::Mat& src, cv::Mat& dst, const float* mapX, const flo
         throw std::runtime_error(std::string("remap (B200): ") + orbfe_last_error());
     dst = out;
 }
+// void Frame::UndistortKeyPoints()  (Frame.cc:1003-1051): mvKeys -> mvKeysUn with K = mK (float entries), distCoef = mDistCoef
+inline void UndistortKeyPoints(const std::vector<cv::KeyPoint>& keys, float fx, float fy, float cx, float cy,
+                               const std::vector<float>& distCoef, std::vector<cv::KeyPoint>& keysUn) {
+    keysUn.resize(keys.size());
+    if (orbfe_undistort_keypoints(reinterpret_cast<const OrbfeKeyPoint*>(keys.data()), (int)keys.size(), fx, fy, cx, cy,
+                                  distCoef.data(), (int)distCoef.size(), reinterpret_cast<OrbfeKeyPoint*>(keysUn.data()),
+                                  device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("UndistortKeyPoints (B200): ") + orbfe_last_error());
+}
 // cv::resize(im, imToFeed, settings_->newImSize())  (System.cc:295-297)
 inline void resize(const cv::Mat& src, cv::Mat& dst, cv::Size dsize) {
     cv::Mat out(dsize.height, dsize.width, CV_8UC1);

@@ -34,3 +34,14 @@ def resize(src, dsize, device=0):
     out = np.empty((dh, dw), np.uint8)
     check(lib().orbfe_resize_linear(ptr(src), src.shape[0], src.shape[1], src.strides[0], dh, dw, ptr(out), dw, device))
     return out
+
+
+def undistortKeyPoints(keys, K, dist_coef, device=0):
+    """Frame::UndistortKeyPoints (Frame.cc:1003-1051): mvKeys -> mvKeysUn.  K = (fx, fy, cx, cy)."""
+    from ._lib import KP_DTYPE
+    keys = np.ascontiguousarray(keys, KP_DTYPE)
+    d = np.ascontiguousarray(dist_coef, np.float32)
+    out = np.empty_like(keys)
+    check(lib().orbfe_undistort_keypoints(ptr(keys), len(keys), float(K[0]), float(K[1]), float(K[2]), float(K[3]), ptr(d),
+                                          len(d), ptr(out), device))
+    return out

@@ -84,3 +84,32 @@ def test_rectify_then_extract_equals_reference_chain(orbfe):
     oex = O.Extractor(1000)
     _, ok, od = oex(O.remap_linear(src, mx, my), (0, 0))
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od) and len(k) > 500
+
+
+@pytest.mark.parametrize("dist", [[-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05],
+                                  [0.262383, -0.953104, -0.005358, 0.002628, 1.163314],
+                                  [-3.5, 0.2, 0.01, -0.02], [0.0, 0.1, 0.0, 0.0]])
+def test_undistort_keypoints(orbfe, dist):
+    """Frame::UndistortKeyPoints: coordinates bit-equal to cv::undistortPoints, other fields untouched; a zero first
+    coefficient copies (Frame.cc:1005-1009)."""
+    from oracle.oracle import KP_DTYPE
+    rng = np.random.default_rng(7)
+    n = 3000
+    keys = np.zeros(n, KP_DTYPE)
+    keys["x"], keys["y"] = rng.uniform(0, 752, n), rng.uniform(0, 480, n)
+    keys["size"], keys["angle"], keys["response"] = 31.0, rng.uniform(0, 360, n), rng.uniform(1, 200, n)
+    keys["octave"], keys["class_id"] = rng.integers(0, 8, n), -1
+    K = tuple(np.float32(v) for v in (458.654, 457.296, 367.215, 248.375))
+    got = orbfe.intake.undistortKeyPoints(keys, K, dist)
+    exp = keys.copy()
+    if dist[0] != 0.0:
+        xy = O.undistort_points(np.stack([keys["x"], keys["y"]], 1), K, dist)
+        exp["x"], exp["y"] = xy[:, 0], xy[:, 1]
+        cv2 = _cv2()
+        if cv2 is not None:
+            Km = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32)
+            ref = cv2.undistortPoints(np.stack([keys["x"], keys["y"]], 1).reshape(-1, 1, 2), Km, np.array(dist, np.float32), None,
+                                      Km).reshape(-1, 2)
+            assert np.array_equal(got["x"].view(np.uint32), ref[:, 0].view(np.uint32))
+            assert np.array_equal(got["y"].view(np.uint32), ref[:, 1].view(np.uint32))
+    assert got.tobytes() == exp.tobytes()

@@ -149,3 +149,20 @@ def test_remap_linear(dh, dw, sh, sw, seed):
     my2 = (rng.integers(-40 * 64, (sh + 40) * 64, (dh, dw)) / 64.0).astype(np.float32)
     mx2[0, :4] = [-1e7, 1e7, -0.5, sw - 0.5]
     assert np.array_equal(O.remap_linear(src, mx2, my2), cv2.remap(src, mx2, my2, cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize("dist", [[-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05],          # EuRoC cam0
+                                  [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0021],  # with k3
+                                  [0.262383, -0.953104, -0.005358, 0.002628, 1.163314],           # TUM1
+                                  [-3.5, 0.2, 0.01, -0.02]])                                      # icdist < 0 near the borders
+def test_undistort_points(dist):
+    """cv::undistortPoints(mat, mat, K, mDistCoef, cv::Mat(), mK) as Frame::UndistortKeyPoints calls it
+    (src/Frame.cc:1025).  The camera matrix is float (cv::Mat CV_32F), the arithmetic double."""
+    rng = np.random.default_rng(len(dist))
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]], np.float32)
+    D = np.array(dist, np.float32)
+    pts = np.stack([rng.uniform(0, 752, 3000), rng.uniform(0, 480, 3000)], 1).astype(np.float32)
+    pts[:4] = [[0, 0], [751, 0], [0, 479], [751, 479]]
+    ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+    got = O.undistort_points(pts, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), D)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
