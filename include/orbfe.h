@@ -386,6 +386,14 @@ int orbfe_undistort_keypoints(const OrbfeKeyPoint* keys, int n, float fx, float 
                               float cy, const float* dist_coef, int n_dist, OrbfeKeyPoint* keys_un,
                               int device);
 
+/* void MapPoint::ComputeDistinctiveDescriptors()   include/MapPoint.h:138, src/MapPoint.cc:438-529, batched over map
+ * points: the descriptors observed for map point p, in the order the reference pushes them into
+ * vDescriptors (:449-471), are rows start[p] .. start[p+1]-1 of `desc`; best_idx[p] = the row (relative to start[p]) with
+ * the smallest median distance to all rows of the point (:507-521; median = sorted[(N-1)/2] with the row's own 0,
+ * first row wins ties), -1 for a point without descriptors.  The caller stores mDescriptor = that row. */
+int orbfe_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int n_points,
+                                  int32_t* best_idx, int device);
+
 /* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
 const char* orbfe_version(void);
 

@@ -311,6 +311,28 @@ int search_by_sim3(const FrameView& KF1, const FrameView& KF2, const std::vector
     return nFound;
 }
 
+// reference src/MapPoint.cc:476-521
+int distinctive_descriptor(const uint8_t* desc, int N) {
+    if (N <= 0) return -1;
+    std::vector<float> Distances((size_t)N * N);
+    for (int i = 0; i < N; i++) {
+        Distances[(size_t)i * N + i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            const int distij = descriptor_distance(desc + 32 * (size_t)i, desc + 32 * (size_t)j);
+            Distances[(size_t)i * N + j] = (float)distij;
+            Distances[(size_t)j * N + i] = (float)distij;
+        }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> vDists(Distances.begin() + (size_t)i * N, Distances.begin() + (size_t)(i + 1) * N);
+        std::sort(vDists.begin(), vDists.end());
+        const int median = vDists[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
 // reference src/ORBmatcher.cc:735-891
 int search_for_initialization(const FrameView& F1, FrameView& F2, float* vbPrevMatched, int windowSize,
                               float mfNNratio, bool mbCheckOrientation, int* vnMatches12) {

@@ -115,6 +115,10 @@ int search_by_sim3(const FrameView& KF1, const FrameView& KF2, const std::vector
                    const uint8_t* desc1, const std::vector<ProjPoint>& pts21, const uint8_t* desc2,
                    int thAccept, int* match12);
 
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:438-529) for one map point: desc = its N observed
+// descriptors in vDescriptors order.  Returns BestIdx (:507-521), -1 when N == 0.
+int distinctive_descriptor(const uint8_t* desc, int N);
+
 // Frame::ComputeStereoMatches on two extractor pyramids.
 struct PyrLevelView {
     const uint8_t* roi;

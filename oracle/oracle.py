@@ -440,3 +440,11 @@ def undistort_points(xy, K, dist):
     lib().oracle_undistort_points(_p(xy), len(xy), C.c_double(fx), C.c_double(fy), C.c_double(cx), C.c_double(cy), _p(d),
                                   len(d), _p(out))
     return out
+
+
+def distinctive_descriptors(desc, start):
+    desc = np.ascontiguousarray(desc, np.uint8)
+    start = np.ascontiguousarray(start, np.int32)
+    best = np.empty(len(start) - 1, np.int32)
+    lib().oracle_distinctive_descriptors(_p(desc), _p(start), len(start) - 1, _p(best))
+    return best

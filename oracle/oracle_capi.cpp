@@ -246,6 +246,10 @@ void oracle_undistort_points(const float* xy, int n, double fx, double fy, doubl
                              float* out) {
     cvp::undistort_points(xy, n, fx, fy, cx, cy, dist, ndist, out);
 }
+void oracle_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int nPoints, int32_t* best) {
+    for (int p = 0; p < nPoints; p++)
+        best[p] = match_oracle::distinctive_descriptor(desc + 32 * (size_t)start[p], start[p + 1] - start[p]);
+}
 
 // ---- bag of words ---------------------------------------------------------------------------------
 void* oracle_voc_create(int k, int L, int scoring, int weighting, int nNodes, const int32_t* parent,

@@ -346,3 +346,13 @@ def search_for_triangulation(kf1, kf2, only_stereo, coarse, check_ori):
     n = mlib().refm_search_for_triangulation(C.c_void_p(kf1.h), C.c_void_p(kf2.h), int(only_stereo), int(coarse), _f(0.6),
                                              int(check_ori), _p(out), _p(f12), _p(ep))
     return n, out, f12, ep
+
+
+def distinctive(desc, kf_start, rows, kf_bad):
+    """MapPoint::ComputeDistinctiveDescriptors per point -> chosen descriptors (n_points x 32; zeros where none)."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    kf_start = np.ascontiguousarray(kf_start, np.int32); rows = np.ascontiguousarray(rows, np.int32)
+    kf_bad = np.ascontiguousarray(kf_bad, np.uint8)
+    out = np.zeros((len(kf_start) - 1, 32), np.uint8)
+    mlib().refm_distinctive(_p(desc), _p(kf_start), _p(rows), _p(kf_bad), len(kf_start) - 1, _p(out))
+    return out

@@ -398,6 +398,29 @@ int refm_stereo(const uint8_t* imgL, const uint8_t* imgR, int rows, int cols, in
 }
 
 
+// MapPoint::ComputeDistinctiveDescriptors for a batch of map points.  Point p is observed by nkf[p] keyframes (allocated
+// as one array, so that the std::map<KeyFrame*, ...> of observations iterates in index order); keyframe k of the point
+// contributes rows[k] (1 or 2: left only, or left + right index) descriptors, bad keyframes are skipped (:453).
+// desc = all rows in that order; out = the chosen 32-byte mDescriptor per point (untouched when nothing was chosen).
+void refm_distinctive(const uint8_t* desc, const int* kfStart, const int* rows, const uint8_t* kfBad, int nPoints,
+                      uint8_t* out) {
+    size_t row = 0;
+    for (int p = 0; p < nPoints; p++) {
+        const int nk = kfStart[p + 1] - kfStart[p];
+        std::vector<KeyFrame> kfs(nk);
+        MapPoint mp;
+        for (int k = 0; k < nk; k++) {
+            const int g = kfStart[p] + k, r = rows[g];
+            kfs[k].mDescriptors = wrap_desc(desc + 32 * row, r);
+            kfs[k].mbBadKF = kfBad[g] != 0;
+            mp.mObservations[&kfs[k]] = std::make_tuple(0, r == 2 ? 1 : -1);
+            row += r;
+        }
+        mp.ComputeDistinctiveDescriptors();
+        if (!mp.mDescriptor.empty()) memcpy(out + 32 * (size_t)p, mp.mDescriptor.ptr(), 32);
+    }
+}
+
 // ---- bag of words: DBoW2 itself (include/ORBVocabulary.h:30-31 typedef) ------------------------------------
 typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> ORBVocabulary;
 

@@ -15,6 +15,7 @@
 #define KEYFRAME_H
 #define FRAME_H
 #include <cmath>
+#include <map>
 #include <mutex>
 #include <set>
 #include <vector>
@@ -183,6 +184,11 @@ class MapPoint {
     // graph updates of Fuse are recorded, not performed: (kind, this->id, other id or keypoint index)
     void Replace(MapPoint* pMP);
     void AddObservation(KeyFrame* pKF, int idx);
+    void ComputeDistinctiveDescriptors();                       // body sliced from src/MapPoint.cc
+    std::map<KeyFrame*, std::tuple<int, int>> mObservations;
+    std::mutex mMutexFeatures;
+    bool mbBad = false;
+    cv::Mat mDescriptor;
     int id = -1;
     bool inKF = false;
     int idxInOtherKF = -1;
@@ -210,6 +216,8 @@ class KeyFrame {
         return s;
     }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    bool isBad() { return mbBadKF; }
+    bool mbBadKF = false;
     void AddMapPoint(MapPoint* pMP, const size_t& idx) {
         mvpMapPoints[idx] = pMP;
         g_refActions.push_back({3, pMP->id, (int)idx});

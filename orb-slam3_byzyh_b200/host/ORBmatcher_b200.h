@@ -343,6 +343,16 @@ inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const 
     return n;
 }
 
+// void MapPoint::ComputeDistinctiveDescriptors()  (MapPoint.cc:438-529) for many map points at once (LocalMapping calls it
+// per new / fused point): descriptors of point p = rows start[p] .. start[p+1]-1 of `desc` in vDescriptors order;
+// bestIdx[p] = the row to clone into mDescriptor (relative to start[p]), -1 when the point has no descriptor.
+inline void ComputeDistinctiveDescriptors(const cv::Mat& desc, const std::vector<int32_t>& start, std::vector<int32_t>& bestIdx) {
+    bestIdx.assign(start.empty() ? 0 : start.size() - 1, -1);
+    if (bestIdx.empty()) return;
+    if (orbfe_distinctive_descriptors(desc.ptr(), start.data(), (int)bestIdx.size(), bestIdx.data(), device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("ComputeDistinctiveDescriptors (B200): ") + orbfe_last_error());
+}
+
 // ---- Frame intake: the OpenCV calls made on an image before ORBextractor -------------------------------------------
 // cv::cvtColor(im, im, cv::COLOR_{RGB,BGR,RGBA,BGRA}2GRAY)  (Tracking.cc:1563-1590, 1623-1636, 1702-1716)
 inline void cvtColorToGray(const cv::Mat& src, cv::Mat& dst, int channels, bool rgbOrder) {

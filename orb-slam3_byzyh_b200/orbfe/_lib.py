@@ -124,6 +124,7 @@ _SIGS = {
     "orbfe_remap_linear_device": (_i, [_vp, _i, _i, _sz, _vp, _vp, _sz, _i, _i, _vp, _sz, _vp]),
     "orbfe_resize_linear": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _i]),
     "orbfe_undistort_keypoints": (_i, [_vp, _i, _f, _f, _f, _f, _vp, _i, _vp, _i]),
+    "orbfe_distinctive_descriptors": (_i, [_vp, _vp, _i, _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -250,6 +250,16 @@ class ORBmatcher:
         n = check(lib().orbfe_search_for_triangulation(C.byref(a), C.byref(b), C.byref(prm), ptr(m12), self.device))
         return n, m12
 
+    # MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:438-529) for a batch of map points: desc = all observed
+    # descriptors, start[p] .. start[p+1] = the rows of point p.  -> best row per point (relative), -1 = none
+    @staticmethod
+    def ComputeDistinctiveDescriptors(desc, start, device=0):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        start = np.ascontiguousarray(start, np.int32)
+        best = np.empty(len(start) - 1, np.int32)
+        check(lib().orbfe_distinctive_descriptors(ptr(desc), ptr(start), len(start) - 1, ptr(best), device))
+        return best
+
     # cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + 0.7 ratio, Frame.cc:1553-1562
     def knn2(self, query, train, train_offset=0):
         q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)

@@ -361,3 +361,14 @@ def test_search_by_projection_sim3(orbfe, ratio):
     assert n == en and n > 300
     assert np.array_equal(asg, easg) and np.array_equal(bi, ebi) and np.array_equal(bd, ebd)
     assert not np.any((asg >= 0) & (matched > 0))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_distinctive_descriptors(orbfe, seed):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:438-529), batched: best row per map point."""
+    from test_oracle_match_vs_ref import _distinctive_case, flatten_good_observations
+    desc, kf_start, rows, kf_bad = _distinctive_case(seed, n_points=2000)
+    good, start = flatten_good_observations(desc, kf_start, rows, kf_bad)
+    best = orbfe.ORBmatcher.ComputeDistinctiveDescriptors(good, start)
+    assert np.array_equal(best, O.distinctive_descriptors(good, start))
+    assert (best == -1).sum() >= 1 and best.max() > 20

@@ -607,3 +607,51 @@ def test_search_by_sim3_vs_reference(seed):
     expect = np.where(m12 >= 0, m12, pre12)          # vpMatches12 keeps its earlier entries
     assert rn == n and n > 150
     assert np.array_equal(rout, expect)
+
+
+def _distinctive_case(seed, n_points=300):
+    """Map points observed by 1..40 keyframes (a few by 150); observations are noisy copies of a per-point descriptor,
+    with outliers, so medians tie often."""
+    rng = np.random.default_rng(seed)
+    nkf = rng.integers(1, 41, n_points)
+    nkf[::50] = 150
+    nkf[1] = 1
+    kf_start = np.concatenate([[0], np.cumsum(nkf)]).astype(np.int32)
+    rows = rng.choice([1, 2], kf_start[-1], p=[0.8, 0.2]).astype(np.int32)
+    kf_bad = (rng.uniform(size=kf_start[-1]) < 0.1).astype(np.uint8)
+    kf_bad[kf_start[5]:kf_start[6]] = 1                                # a point whose keyframes are all bad
+    descs = []
+    for p in range(n_points):
+        base = rng.integers(0, 256, 32).astype(np.uint8)
+        for k in range(kf_start[p], kf_start[p + 1]):
+            for _ in range(rows[k]):
+                noise = 256 if rng.uniform() < 0.1 else int(rng.integers(0, 40))
+                descs.append(synth.flip_bits(base, min(noise, 256), rng) if noise < 256 else rng.integers(0, 256, 32).astype(np.uint8))
+    return np.stack(descs), kf_start, rows, kf_bad
+
+
+def flatten_good_observations(desc, kf_start, rows, kf_bad):
+    """What the caller hands to the batched API: the rows of the good keyframes, in vDescriptors order."""
+    row_start = np.concatenate([[0], np.cumsum(rows)])
+    keep, start = [], [0]
+    for p in range(len(kf_start) - 1):
+        for k in range(kf_start[p], kf_start[p + 1]):
+            if not kf_bad[k]:
+                keep.extend(range(row_start[k], row_start[k + 1]))
+        start.append(len(keep))
+    return desc[keep], np.array(start, np.int32)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_distinctive_descriptors_vs_reference(seed):
+    """MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:438-529."""
+    desc, kf_start, rows, kf_bad = _distinctive_case(seed)
+    ref = R.distinctive(desc, kf_start, rows, kf_bad)
+    good, start = flatten_good_observations(desc, kf_start, rows, kf_bad)
+    best = O.distinctive_descriptors(good, start)
+    assert best[5] == -1 and (best >= 0).sum() >= len(best) - 3
+    for p in range(len(best)):
+        if best[p] >= 0:
+            assert np.array_equal(good[start[p] + best[p]], ref[p]), p
+        else:
+            assert not ref[p].any()
