@@ -127,6 +127,14 @@ def cpu_reference_run(frames_per_thread, threads, frames):
     return threads * frames_per_thread / dt, kind
 
 
+_JSON_OUT = sys.stdout
+
+
+def emit_json(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def call_latencies(orbfe, device):
     """Per-call milliseconds of the matcher entry points at SLAM-frame sizes (host arrays in and out,
     as the C++ adapter issues them): C2 stereo pair, C3-sized kNN, local-map projection search."""
@@ -229,7 +237,7 @@ def run_reference(args):
         tot += per * cores
     dt = time.perf_counter() - t0
     v = tot / dt
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -238,7 +246,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": f"{per} frames per thread x {cores} threads per step, one ORBextractor per thread"},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def run_ours(args):
@@ -419,7 +427,7 @@ def run_ours(args):
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "single_thread_frames_per_s": one,
                "sample": f"{per} frames per thread x {cores} threads of the same workload, one ORBextractor per thread"}
 
-    print(json.dumps({
+    emit_json({
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -431,7 +439,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps, "single_frame_call_ms": single_ms},
         "call_latency_ms": latency,
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "matching": matching,
-    }))
+    })
     if world > 1:
         dist.destroy_process_group()
 
@@ -447,10 +455,17 @@ def main():
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: keep a private handle to it and point fd 1 at stderr, so that anything a
+    # library prints on stdout (NCCL's version banner under NCCL_DEBUG=VERSION, for one) cannot end up beside it
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    _JSON_OUT.flush()
 
 
 if __name__ == "__main__":
