@@ -47,7 +47,9 @@ k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ 
     extern __shared__ __align__(16) char smem[];
     __shared__ int warpSums[OC_THREADS / 32];
     __shared__ int s_outn;
-    const int level = blockIdx.x, frame = blockIdx.y;
+    // grid = (frame, level): CTAs are dispatched x-fastest, so every frame's level-0 tree (the longest, ~0.2 ms) starts
+    // in the first wave and the launch ends on the short top-level trees instead of on a level-0 straggler
+    const int frame = blockIdx.x, level = blockIdx.y;
     const OrbfeLevelGeom& L = g.lv[level];
     const size_t fs = (size_t)frame * g.slotsPerFrame + L.slotBase;
     const uint32_t* cslots = slots + fs;
@@ -144,10 +146,10 @@ int orbfe_octree_prepare(OrbfeFrameGeom& g) {
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches) {
     if (g.ocShared)
-        k_octree<true><<<dim3(g.nlevels, B), OC_THREADS, g.ocShared, st>>>(
+        k_octree<true><<<dim3(B, g.nlevels), OC_THREADS, g.ocShared, st>>>(
             g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
     else
-        k_octree<false><<<dim3(g.nlevels, B), OC_THREADS, 0, st>>>(
+        k_octree<false><<<dim3(B, g.nlevels), OC_THREADS, 0, st>>>(
             g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
     ++*launches;
 }
