@@ -25,6 +25,7 @@ namespace {
 
 constexpr int GC = 64, GR = 48;          // FRAME_GRID_COLS / ROWS, include/Frame.h:44-45
 constexpr int HISTO = 30;                // HISTO_LENGTH, ORBmatcher.cc:38
+constexpr int kWarpPassMax = 1 << 16;    // up to this many map points a pass uses one warp per point
 
 struct GridDev {
     const OrbfeKeyPoint* keys;
@@ -159,6 +160,82 @@ k_search_pass(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, const 
                 }
         }
     }
+    bool accept = bI >= 0 && bD <= thAccept;
+    if (accept && mode == ORBFE_SEARCH_MAPPOINTS && bL == bL2 && (float)bD > nnratio * (float)bD2) accept = false;
+    bestDist[j] = bD;
+    bestIdx[j] = accept ? bI : -1;
+    if (accept && (mode == ORBFE_SEARCH_KEYFRAME || (P.blocks ? P.blocks[j] != 0 : true))) atomicMin(&claimOut[bI], j);
+}
+
+// The same pass with one WARP per map point, for the per-frame calls of Tracking (a few thousand points: one thread
+// per point leaves the machine empty and walks ~50 candidates serially).  Lanes stride over the candidates of each
+// grid column; best and second best are the two smallest keys (distance << 23 | position in GetFeaturesInArea order),
+// which is exactly what the sequential update rule (:127-149) leaves behind: a later candidate of equal distance
+// becomes the second best, a new best demotes the previous one.
+__global__ void __launch_bounds__(128)
+k_search_pass_warp(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, const int* __restrict__ claimIn,
+                   int* __restrict__ claimOut, int* __restrict__ bestIdx, int* __restrict__ bestDist) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= P.m) return;
+    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    int i1 = -1, i2 = -1;
+    if (P.valid[j]) {
+        const float x = P.u[j], y = P.v[j], r = P.radius[j];
+        const int minLevel = P.minLevel[j], maxLevel = P.maxLevel[j];
+        const int c0x = max(0, (int)floorf((x - F.minX - r) * F.wInv));
+        const int c1x = min(GC - 1, (int)ceilf((x - F.minX + r) * F.wInv));
+        const int c0y = max(0, (int)floorf((y - F.minY - r) * F.hInv));
+        const int c1y = min(GR - 1, (int)ceilf((y - F.minY + r) * F.hInv));
+        if (c0x < GC && c1x >= 0 && c0y < GR && c1y >= 0) {
+            const bool checkLevels = (minLevel > 0) || (maxLevel >= 0);
+            uint32_t d[8];
+            const uint4* pd = reinterpret_cast<const uint4*>(P.desc + 8 * (size_t)j);
+            *reinterpret_cast<uint4*>(d) = pd[0];
+            *reinterpret_cast<uint4*>(d + 4) = pd[1];
+            const float ur = P.ur ? P.ur[j] : 0.f;
+            int order = 0;
+            for (int ix = c0x; ix <= c1x; ix++) {
+                const int cb = F.cellStart[ix * GR + c0y], ce = F.cellStart[ix * GR + c1y + 1];
+                for (int t = cb + lane; t < ce; t += 32) {
+                    const int idx = F.cellItems[t];
+                    const OrbfeKeyPoint kp = F.keys[idx];
+                    if (checkLevels) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    if (!(fabsf(kp.x - x) < r && fabsf(kp.y - y) < r)) continue;
+                    if (claimIn[idx] < j) continue;
+                    if (mode != ORBFE_SEARCH_KEYFRAME && F.uright) {
+                        const float uR = F.uright[idx];
+                        if (uR > 0 && fabsf(ur - uR) > r) continue;
+                    }
+                    const uint4* kd = reinterpret_cast<const uint4*>(F.desc + 8 * (size_t)idx);
+                    const uint32_t k = ((uint32_t)hamming8(d, kd[0], kd[1]) << 23) | (uint32_t)(order + t - cb);
+                    if (k < k1) { k2 = k1; i2 = i1; k1 = k; i1 = idx; }
+                    else if (k < k2) { k2 = k; i2 = idx; }
+                }
+                order += ce - cb;
+            }
+        }
+    }
+    // warp top-2 of unique keys, carrying the keypoint index
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+        const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+        uint32_t hi; int hiI;
+        if (o1 < k1) { hi = k1; hiI = i1; k1 = o1; i1 = j1; } else { hi = o1; hiI = j1; }
+        // second = min(hi, k2, o2)
+        if (o2 < k2) { k2 = o2; i2 = j2; }
+        if (hi < k2) { k2 = hi; i2 = hiI; }
+    }
+    if (lane != 0) return;
+    const int bD = (k1 == 0xFFFFFFFFu || (k1 >> 23) >= 256) ? 256 : (int)(k1 >> 23);
+    const int bI = bD < 256 ? i1 : -1;
+    int bD2 = 256, bL2 = -1;
+    if (mode == ORBFE_SEARCH_MAPPOINTS && k2 != 0xFFFFFFFFu && (k2 >> 23) < 256) { bD2 = (int)(k2 >> 23); bL2 = F.keys[i2].octave; }
+    const int bL = bI >= 0 ? F.keys[bI].octave : -1;
     bool accept = bI >= 0 && bD <= thAccept;
     if (accept && mode == ORBFE_SEARCH_MAPPOINTS && bL == bL2 && (float)bD > nnratio * (float)bD2) accept = false;
     bestDist[j] = bD;
@@ -756,18 +833,28 @@ extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const Orb
     k_claims_init<<<(n + 255) / 256, 256, 0, st>>>(dcl, n, cin, cout);
     const int gridM = (m + 127) / 128;
     int passes = 0;
+    const bool warpPass = m <= kWarpPassMax && n < (1 << 23);
+    // Without conflicts the fixpoint needs two passes (the second confirms the claims of the first).  For the small
+    // per-frame calls a pass costs a few microseconds and a host round trip ~20: enqueue two passes per round trip
+    // (a pass on converged claims reproduces its input, so an extra one is harmless).
+    const int batch = warpPass ? 2 : 1;
     for (;;) {
         // cout holds the static claims; the pass lowers entries to the first blocking acceptor
-        SCK(cudaMemsetAsync(dFlag, 0, 4, st));
-        k_search_pass<<<gridM, 128, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBestIdx, dBestDist);
-        k_claims_diff<<<(n + 255) / 256, 256, 0, st>>>(cout, cin, dcl, n, dFlag);
-        int changed = 0;
-        SCK(cudaMemcpyAsync(&changed, dFlag, 4, cudaMemcpyDeviceToHost, st));
+        SCK(cudaMemsetAsync(dFlag, 0, 4 * batch, st));
+        for (int b = 0; b < batch; b++) {
+            if (warpPass)
+                k_search_pass_warp<<<(m + 3) / 4, 128, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBestIdx, dBestDist);
+            else
+                k_search_pass<<<gridM, 128, 0, st>>>(F, P, prm->mode, prm->th_accept, prm->nnratio, cin, cout, dBestIdx, dBestDist);
+            k_claims_diff<<<(n + 255) / 256, 256, 0, st>>>(cout, cin, dcl, n, dFlag + b);
+            std::swap(cin, cout);  // new claims become the input; the old table was reset by the diff
+        }
+        int changed[2] = {0, 0};
+        SCK(cudaMemcpyAsync(changed, dFlag, 4 * batch, cudaMemcpyDeviceToHost, st));
         SCK(cudaStreamSynchronize(st));
-        passes++;
-        std::swap(cin, cout);  // new claims become the input; the old table was reset by the diff
-        if (!changed) break;
-        if (passes > m + 1) return sfail(ORBFE_ERR_CUDA, "claim fixpoint did not converge");
+        passes += batch;
+        if (!changed[batch - 1]) break;
+        if (passes > m + 2) return sfail(ORBFE_ERR_CUDA, "claim fixpoint did not converge");
     }
     k_assign_prepare<<<gridM, 128, 0, st>>>(dBestIdx, m, dAssigned);
     k_search_assign<<<gridM, 128, 0, st>>>(F, P, useHist ? 1 : 0, dBestIdx, dAssigned, dHist, S.ptr<int>(wBin), dN);
