@@ -11,8 +11,10 @@
 
 namespace {
 
-constexpr int OC_THREADS = 128;
-static_assert(OC_THREADS <= OC_MAX_NT, "oc_rebuild_phase1 scratch");
+// CTA size is chosen at launch: 128 threads per tree give the best throughput on large batches, 256 halve the
+// critical path of the level-0 tree when only a few frames are in flight (single-frame calls: 0.44 -> 0.40 ms).
+constexpr int OC_THREADS = OC_MAX_NT;    // upper bound (launch bounds, scratch sizes)
+constexpr int OC_THREADS_BATCH = 128;
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* warpSums, int* total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -25,7 +27,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warpSums, int* t
     if (lane == 31) warpSums[wid] = incl;
     __syncthreads();
     int base = 0, tot = 0;
-    for (int w = 0; w < OC_THREADS / 32; w++) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
         const int s = warpSums[w];
         if (w < wid) base += s;
         tot += s;
@@ -60,7 +62,7 @@ k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ 
 
     // ---- candidate list in emission order: scan the cell counts, gather the slots ----
     int running = 0;
-    for (int base = 0; base < nCells; base += OC_THREADS) {
+    for (int base = 0; base < nCells; base += blockDim.x) {
         const int c = base + threadIdx.x;
         const int v = c < nCells ? cc[c] : 0;
         int tot;
@@ -72,7 +74,7 @@ k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ 
     __syncthreads();
     {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int c = wid; c < nCells; c += OC_THREADS / 32) {
+        for (int c = wid; c < nCells; c += (int)(blockDim.x >> 5)) {
             const int cnt = cc[c];
             const int off = (int)pn[c];
             const uint32_t* s = cslots + (size_t)c * L.cellCap;
@@ -100,7 +102,7 @@ k_octree(const __grid_constant__ OrbfeFrameGeom g, const uint32_t* __restrict__ 
                   out_idx, &s_outn, best);
     const int outn = s_outn;
     uint32_t* kpo = kp + (size_t)frame * g.kpCapFrame + L.kpBase;
-    for (int k = threadIdx.x; k < outn && k < L.kpCap; k += OC_THREADS) kpo[k] = pk[out_idx[k]];
+    for (int k = threadIdx.x; k < outn && k < L.kpCap; k += blockDim.x) kpo[k] = pk[out_idx[k]];
     if (threadIdx.x == 0) kpCount[frame * g.nlevels + level] = min(outn, L.kpCap);
 }
 
@@ -117,7 +119,7 @@ k_octree_debug(const uint32_t* pk, uint32_t* pnode, int n, int width, int height
     w.n = n;
     __shared__ int s_outn;
     oc_distribute(w, width, height, nIni, hX, N, out_idx, &s_outn, best);
-    for (int k = threadIdx.x; k < s_outn; k += OC_THREADS) out[k] = out_idx[k];
+    for (int k = threadIdx.x; k < s_outn; k += blockDim.x) out[k] = out_idx[k];
     if (threadIdx.x == 0) *outn = s_outn;
 }
 
@@ -145,11 +147,12 @@ int orbfe_octree_prepare(OrbfeFrameGeom& g) {
 
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches) {
+    const int nt = B >= 128 ? OC_THREADS_BATCH : OC_THREADS;
     if (g.ocShared)
-        k_octree<true><<<dim3(B, g.nlevels), OC_THREADS, g.ocShared, st>>>(
+        k_octree<true><<<dim3(B, g.nlevels), nt, g.ocShared, st>>>(
             g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
     else
-        k_octree<false><<<dim3(B, g.nlevels), OC_THREADS, 0, st>>>(
+        k_octree<false><<<dim3(B, g.nlevels), nt, 0, st>>>(
             g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
     ++*launches;
 }

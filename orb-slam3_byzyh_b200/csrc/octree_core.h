@@ -79,7 +79,7 @@ struct OcWork {
     int* part;           // [3 * OC_MAX_NT] per-thread partial sums of the parallel list rebuild
 };
 enum { OC_SIZE = 0, OC_CUR = 1, OC_NV = 2, OC_STATE = 3, OC_NTOEXP = 4 };
-#define OC_MAX_NT 128   // largest CTA size oc_distribute may be called with
+#define OC_MAX_NT 256   // largest CTA size oc_distribute may be called with
 enum { OC_ST_PHASE1 = 0, OC_ST_PHASE2 = 1, OC_ST_DONE = 2 };
 
 static OC_HD size_t oc_shared_bytes(int M) {
