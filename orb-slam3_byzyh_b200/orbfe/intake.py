@@ -45,3 +45,21 @@ def undistortKeyPoints(keys, K, dist_coef, device=0):
     check(lib().orbfe_undistort_keypoints(ptr(keys), len(keys), float(K[0]), float(K[1]), float(K[2]), float(K[3]), ptr(d),
                                           len(d), ptr(out), device))
     return out
+
+
+# ---- device-resident forms: torch CUDA tensors in and out, enqueued on a stream, no synchronisation -------------
+def cvtColorToGray_device(d_img, d_out, rgb=False, stream=None):
+    """d_img: (rows, cols, 3|4) uint8 CUDA tensor, d_out: (rows, cols) uint8 CUDA tensor."""
+    import ctypes as C
+    rows, cols, ch = d_img.shape
+    st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+    check(lib().orbfe_cvt_gray_device(ptr(d_img), rows, cols, d_img.stride(0), ch, int(rgb), ptr(d_out), d_out.stride(0), st))
+
+
+def remap_device(d_src, d_map_x, d_map_y, d_out, stream=None):
+    """d_src: (rows, cols) uint8, d_map_x / d_map_y: (drows, dcols) float32, d_out: (drows, dcols) uint8; CUDA tensors."""
+    import ctypes as C
+    st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+    drows, dcols = d_map_x.shape
+    check(lib().orbfe_remap_linear_device(ptr(d_src), d_src.shape[0], d_src.shape[1], d_src.stride(0), ptr(d_map_x),
+                                          ptr(d_map_y), d_map_x.stride(0), drows, dcols, ptr(d_out), d_out.stride(0), st))

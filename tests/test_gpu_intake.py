@@ -113,3 +113,37 @@ def test_undistort_keypoints(orbfe, dist):
             assert np.array_equal(got["x"].view(np.uint32), ref[:, 0].view(np.uint32))
             assert np.array_equal(got["y"].view(np.uint32), ref[:, 1].view(np.uint32))
     assert got.tobytes() == exp.tobytes()
+
+
+def test_device_resident_chain(orbfe):
+    """A colour stereo frame uploaded once: cvtColor -> remap -> ORBextractor, all with device pointers on one stream
+    (no host round trip), equals the host chain of the oracle."""
+    import torch
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(4)
+    gray = synth.synth_frame(480, 752, 9)
+    bgr = np.stack([np.clip(gray.astype(np.int32) + rng.integers(-20, 21, gray.shape), 0, 255).astype(np.uint8) for _ in range(3)], 2)
+    mx, my = _rectify_like_maps(480, 752, 480, 752, 6)
+    d_bgr = torch.from_numpy(bgr).to(dev)
+    d_mx, d_my = torch.from_numpy(mx).to(dev), torch.from_numpy(my).to(dev)
+    d_gray = torch.empty((480, 752), dtype=torch.uint8, device=dev)
+    d_rect = torch.empty((1, 480, 752), dtype=torch.uint8, device=dev)
+    ex = orbfe.ORBextractor(1000)
+    cap = 1000 + 64 * 8 + 64
+    d_kps = torch.empty((1, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((1, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(1, dtype=torch.int32, device=dev)
+    d_mono = torch.empty(1, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    orbfe.intake.cvtColorToGray_device(d_bgr, d_gray, rgb=False, stream=st)
+    orbfe.intake.remap_device(d_gray, d_mx, d_my, d_rect[0], stream=st)
+    ex.extract_batch_device(d_rect, (0, 0), d_kps, d_desc, d_n, d_mono, stream=st)
+    torch.cuda.synchronize()
+    n = int(d_n[0])
+    from oracle.oracle import KP_DTYPE
+    kps = d_kps[0, :n].cpu().numpy().reshape(-1).view(KP_DTYPE)
+    desc = d_desc[0, :n].cpu().numpy()
+    orect = O.remap_linear(O.cvt_gray(bgr, False), mx, my)
+    assert np.array_equal(d_rect[0].cpu().numpy(), orect)
+    _, ok, od = O.Extractor(1000)(orect, (0, 0))
+    assert n == len(ok) and n > 500 and kps.tobytes() == ok.tobytes() and np.array_equal(desc, od)
