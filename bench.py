@@ -363,25 +363,30 @@ def run_ours(args):
         shard = np.random.default_rng(100 + rank).integers(0, 256, (hi - lo, 32), dtype=np.uint8)
         import orbfe.dist as D
         d_q = torch.from_numpy(q).to(dev)
-        smap = D.ShardedMap(shard, lo, dev)           # this rank's shard, resident in HBM
-
-        def step_match():
-            return smap.knn2(d_q)                     # local kNN-2 -> all_gather (NCCL) -> merge
-        for _ in range(3):
-            step_match()
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        for _ in range(args.steps):
-            step_match()
-        m1.record()
-        torch.cuda.synchronize()
-        barrier()
-        mms = max_over_ranks(m0.elapsed_time(m1))
+        def time_exchange(exchange):
+            smap = D.ShardedMap(shard, lo, dev, exchange=exchange)     # this rank's shard, resident in HBM
+            for _ in range(3):
+                out = smap.knn2(d_q)
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(args.steps):
+                out = smap.knn2(d_q)                   # local kNN-2 -> exchange of the per-shard best two -> merge
+            m1.record()
+            torch.cuda.synchronize()
+            barrier()
+            return max_over_ranks(m0.elapsed_time(m1)), smap.exchange, [t.clone() for t in out]
+        # exchange fused into the merge kernel (peer loads over NVLink, symmetric memory); all-gather form beside it
+        mms, how, res = time_exchange("p2p")
         pairs = nq * nmap * args.steps / (mms / 1e3)
         matching = {"metric": "Hamming matches/s (2000 frame x 1M map descriptors, kNN-2 + ratio)", "value": pairs,
-                    "unit": "descriptor pairs/s", "ms_per_step": mms / args.steps,
-                    "map_shards": world, "gather": "nccl all_gather of per-shard best two" if world > 1 else "none"}
+                    "unit": "descriptor pairs/s", "ms_per_step": mms / args.steps, "map_shards": world, "gather": "none"}
+        if world > 1:
+            nms, _, res2 = time_exchange("nccl")
+            assert all(torch.equal(a, b) for a, b in zip(res, res2)), "p2p and all-gather exchanges disagree"
+            matching["gather"] = ("peer loads inside the merge kernel (symmetric memory over NVLink) + 1 device barrier"
+                                  if how == "p2p" else how)
+            matching["ms_per_step_nccl_all_gather"] = nms / args.steps
 
     if rank != 0:
         if world > 1:

@@ -140,6 +140,13 @@ int orbfe_knn2_merge(const int32_t* idx2_shards, const int32_t* dist2_shards, in
 int orbfe_knn2_merge_device(const int32_t* d_idx2_shards, const int32_t* d_dist2_shards, int G,
                             int nq, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match,
                             void* stream);
+/* The merge with the exchange fused in: peer_tabs[s] (host array of G <= 16 DEVICE pointers) addresses shard s's packed
+ * table { idx2[nq][2], dist2[nq][2] } where GPU s wrote it -- this GPU's own buffer or a peer mapping over NVLink
+ * (torch symmetric memory, cudaIpcOpenMemHandle).  The merge kernel gathers with peer loads, so no all-gather runs;
+ * the caller orders "all shards written" before and "all ranks merged" after (one device barrier per step with
+ * double-buffered tables, orbfe/dist.py). */
+int orbfe_knn2_merge_peers_device(const int32_t* const* peer_tabs, int G, int nq, int32_t* d_idx2,
+                                  int32_t* d_dist2, int32_t* d_match, void* stream);
 /* Same for tables gathered as ONE buffer: packed[s] = { idx2[nq][2], dist2[nq][2] } of shard s, so
  * that a single all-gather moves both tables of every shard. */
 int orbfe_knn2_merge_packed_device(const int32_t* d_packed, int G, int nq, int32_t* d_idx2,

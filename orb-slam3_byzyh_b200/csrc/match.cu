@@ -170,6 +170,38 @@ __global__ void k_knn2_merge_tables(const int32_t* __restrict__ idxS, const int3
     if (match) match[q] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
 }
 
+// The same merge with the exchange fused in: shard s's packed table { idx2[nq][2], dist2[nq][2] } is read where GPU s
+// wrote it, through a peer mapping over NVLink (symmetric memory / CUDA IPC), so no all-gather runs before the merge.
+constexpr int kMaxPeers = 16;
+struct PeerTabs { const int32_t* t[kMaxPeers]; };
+
+__global__ void k_knn2_merge_peers(PeerTabs P, int G, int nq, int32_t* __restrict__ idx2, int32_t* __restrict__ dist2,
+                                   int32_t* __restrict__ match) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long b0 = ~0ull, b1 = ~0ull;
+#pragma unroll 1
+    for (int s = 0; s < G; s++) {
+        const int32_t* tab = P.t[s];
+        // one 8-byte peer load per table and query
+        const int2 ii = *reinterpret_cast<const int2*>(tab + (size_t)q * 2);
+        const int2 dd = *reinterpret_cast<const int2*>(tab + 2 * (size_t)nq + (size_t)q * 2);
+        const int iv[2] = {ii.x, ii.y}, dv[2] = {dd.x, dd.y};
+        for (int k = 0; k < 2; k++) {
+            if (iv[k] < 0) continue;
+            const unsigned long long key = ((unsigned long long)(unsigned)dv[k] << 32) | (unsigned)iv[k];
+            const unsigned long long hi = b0 > key ? b0 : key;
+            b0 = b0 < key ? b0 : key;
+            b1 = b1 < hi ? b1 : hi;
+        }
+    }
+    const int i0 = b0 == ~0ull ? -1 : (int)(b0 & 0xFFFFFFFFu), i1 = b1 == ~0ull ? -1 : (int)(b1 & 0xFFFFFFFFu);
+    const int d0 = b0 == ~0ull ? -1 : (int)(b0 >> 32), d1 = b1 == ~0ull ? -1 : (int)(b1 >> 32);
+    idx2[2 * q] = i0; idx2[2 * q + 1] = i1;
+    dist2[2 * q] = d0; dist2[2 * q + 1] = d1;
+    if (match) match[q] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
+}
+
 int mfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
 #define MCK(call)                                                        \
     do {                                                                 \
@@ -288,6 +320,20 @@ int orbfe_knn2_merge_packed_device(const int32_t* d_packed, int G, int nq, int32
     // packed[s] = { idx2[nq][2], dist2[nq][2] } of shard s: one all-gather moves both tables
     k_knn2_merge_tables<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_packed, d_packed + 2 * (size_t)nq, 4 * (size_t)nq,
                                                                            G, nq, d_idx2, d_dist2, d_match);
+    MCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_merge_peers_device(const int32_t* const* peer_tabs, int G, int nq, int32_t* d_idx2, int32_t* d_dist2,
+                                  int32_t* d_match, void* stream) {
+    if (nq <= 0 || G <= 0) return ORBFE_OK;
+    if (!peer_tabs || !d_idx2 || !d_dist2) return mfail(ORBFE_ERR_INVALID, "null argument");
+    if (G > kMaxPeers) return mfail(ORBFE_ERR_CAPACITY, "more than 16 shards: gather the tables and use orbfe_knn2_merge_packed_device");
+    PeerTabs P;
+    for (int s = 0; s < kMaxPeers; s++) P.t[s] = s < G ? peer_tabs[s] : nullptr;
+    for (int s = 0; s < G; s++)
+        if (!P.t[s]) return mfail(ORBFE_ERR_INVALID, "null peer table");
+    k_knn2_merge_peers<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, G, nq, d_idx2, d_dist2, d_match);
     MCK(cudaGetLastError());
     return ORBFE_OK;
 }

@@ -102,6 +102,7 @@ _SIGS = {
     "orbfe_knn2_device": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "orbfe_knn2_merge": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
     "orbfe_knn2_merge_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbfe_knn2_merge_peers_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_knn2_merge_packed_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_search_by_projection": (_i, [C.POINTER(FrameView), C.POINTER(ProjPoints), C.POINTER(SearchParams),
                                         _vp, _vp, _vp, _vp, _i]),

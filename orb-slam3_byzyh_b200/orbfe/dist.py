@@ -9,6 +9,12 @@ over torch.distributed:
     associative (distance, index) order (orbfe_knn2_merge_device), which reproduces the
     single-GPU tie-breaks exactly.
 
+On GPUs the exchange is fused into the merge: every rank writes its shard's table into a symmetric-memory buffer
+(torch.distributed._symmetric_memory: the same allocation mapped into every process over NVLink), a device barrier
+orders the writes, and the merge kernel of every rank reads all shards' tables with peer loads
+(orbfe_knn2_merge_peers_device) -- no all-gather.  Tables are double-buffered, so one barrier per step also
+guarantees that nobody still reads a buffer when it is written again.  exchange="nccl" keeps the all-gather form.
+
 The compute calls are CUDA only; the host-side logic here (ranges, gather layout) is what the
 world_size-2 gloo tests exercise on CPU."""
 import torch
@@ -39,11 +45,33 @@ def gather_tables(idx2, dist2, group=None):
 class ShardedMap:
     """This rank's shard of a map-point descriptor table, resident in HBM."""
 
-    def __init__(self, map_desc_shard, lo, device):
+    def __init__(self, map_desc_shard, lo, device, exchange="p2p"):
+        """exchange: "p2p" = peer loads inside the merge kernel (symmetric memory over NVLink), "nccl" = all-gather.
+        "p2p" falls back to "nccl" when symmetric memory cannot be set up (reported in self.exchange)."""
         self.device = device
         self.lo = int(lo)
         self.train = map_desc_shard if isinstance(map_desc_shard, torch.Tensor) else torch.from_numpy(map_desc_shard)
         self.train = self.train.to(device).contiguous()
+        self.exchange = exchange
+        self._symm = None      # (capacity nq, [tensor, tensor], [handle, handle], [peer pointer array, ...])
+        self._step = 0
+
+    def _symmetric_tables(self, nq, group):
+        """Two symmetric buffers of {idx2[nq][2], dist2[nq][2]} int32 and the peer pointers of each."""
+        if self._symm is not None and self._symm[0] >= nq:
+            return self._symm
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        bufs, hdls, ptrs = [], [], []
+        for _ in range(2):
+            t = symm_mem.empty((2, nq, 2), dtype=torch.int32, device=self.device)
+            h = symm_mem.rendezvous(t, grp)
+            bufs.append(t)
+            hdls.append(h)
+            ptrs.append((C.c_void_p * h.world_size)(*[int(p) for p in h.buffer_ptrs]))
+        self._symm = (nq, bufs, hdls, ptrs)
+        return self._symm
 
     def knn2(self, d_query, group=None):
         """d_query: [nq,32] uint8 CUDA tensor (same on every rank).  Returns (idx2, dist2, match)
@@ -51,8 +79,27 @@ class ShardedMap:
         L = _lib.lib()
         nq = d_query.shape[0]
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-        tab = torch.empty((2, nq, 2), dtype=torch.int32, device=self.device)   # {idx2, dist2} of this shard
         st = torch.cuda.current_stream(self.device).cuda_stream
+        f_idx = torch.empty((nq, 2), dtype=torch.int32, device=self.device)
+        f_dist = torch.empty_like(f_idx)
+        match = torch.empty(nq, dtype=torch.int32, device=self.device)
+        if world > 1 and self.exchange == "p2p":
+            try:
+                cap, bufs, hdls, ptrs = self._symmetric_tables(nq, group)
+            except Exception as e:      # noqa: BLE001 -- no symmetric memory on this system: keep the all-gather
+                self.exchange = "nccl (symmetric memory unavailable: %s)" % str(e)[:80]
+            else:
+                assert cap == nq, "the symmetric tables are laid out for a fixed query count"
+                k = self._step & 1
+                self._step += 1
+                tab = bufs[k]
+                _lib.check(L.orbfe_knn2_device(_lib.ptr(d_query), nq, _lib.ptr(self.train), self.train.shape[0], self.lo,
+                                               _lib.ptr(tab[0]), _lib.ptr(tab[1]), st))
+                hdls[k].barrier(channel=0)          # every shard's table is written (device-side, on this stream)
+                _lib.check(L.orbfe_knn2_merge_peers_device(ptrs[k], world, nq, _lib.ptr(f_idx), _lib.ptr(f_dist),
+                                                           _lib.ptr(match), st))
+                return f_idx, f_dist, match
+        tab = torch.empty((2, nq, 2), dtype=torch.int32, device=self.device)   # {idx2, dist2} of this shard
         _lib.check(L.orbfe_knn2_device(_lib.ptr(d_query), nq, _lib.ptr(self.train), self.train.shape[0], self.lo,
                                        _lib.ptr(tab[0]), _lib.ptr(tab[1]), st))
         if world > 1:
@@ -60,9 +107,6 @@ class ShardedMap:
             dist.all_gather_into_tensor(packed, tab, group=group)      # the one exchange step (NCCL / NVLink)
         else:
             packed = tab
-        f_idx = torch.empty((nq, 2), dtype=torch.int32, device=self.device)
-        f_dist = torch.empty_like(f_idx)
-        match = torch.empty(nq, dtype=torch.int32, device=self.device)
         _lib.check(L.orbfe_knn2_merge_packed_device(_lib.ptr(packed), world, nq, _lib.ptr(f_idx), _lib.ptr(f_dist),
                                                     _lib.ptr(match), st))
         return f_idx, f_dist, match
