@@ -109,8 +109,9 @@ int orbfe_set_profiling(OrbfeExtractor* h, int enable);
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
 /* Number of kernel launches issued by this extractor since creation. */
 long long orbfe_launch_count(const OrbfeExtractor* h);
-/* Device-memory budget of the per-chunk intermediates (default 6 GiB, env ORBFE_MAX_BYTES);
- * batches larger than one chunk are processed chunk after chunk. */
+/* Device-memory budget of ONE chunk of intermediates (default 6 GiB, env ORBFE_MAX_BYTES); batches larger than
+ * one chunk are processed chunk after chunk.  orbfe_extract_batch (host pointers) keeps two chunks in flight on two
+ * compute streams, so it allocates up to twice this budget. */
 int orbfe_set_max_bytes(OrbfeExtractor* h, unsigned long long bytes);
 /* Geometry of the last image size seen: FAST cells, candidate slots and keypoint slots per
  * frame, bytes of one frame's padded pyramid, device bytes of all intermediates per frame. */

@@ -208,13 +208,16 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
 
     // new geometry invalidates the chunk buffers
     CK(cudaStreamSynchronize(e->sCompute));
+    if (e->sCompute2) CK(cudaStreamSynchronize(e->sCompute2));
     if (e->d_taps) { cudaFree(e->d_taps); e->d_taps = nullptr; }
     if (!taps.empty()) {
         CK(cudaMalloc(&e->d_taps, taps.size() * sizeof(OrbfeTap)));
         CK(cudaMemcpy(e->d_taps, taps.data(), taps.size() * sizeof(OrbfeTap), cudaMemcpyHostToDevice));
     }
     if (e->slab) { cudaFree(e->slab); e->slab = nullptr; }
+    if (e->slab2) { cudaFree(e->slab2); e->slab2 = nullptr; }
     e->chunkCap = 0;
+    e->chunkCap2 = 0;
     e->g = g;
     e->haveGeom = true;
     const size_t ocg = g.ocShared ? 0 : orbfe_octree_table_bytes(g.ocMmax) * g.nlevels;
@@ -224,10 +227,11 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     return ORBFE_OK;
 }
 
-int ensure_chunk(OrbfeExtractor* e, int frames) {
-    if (frames <= e->chunkCap) return ORBFE_OK;
+int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*& slab, int& cap) {
+    if (frames <= cap) return ORBFE_OK;
     CK(cudaStreamSynchronize(e->sCompute));
-    if (e->slab) { cudaFree(e->slab); e->slab = nullptr; e->chunkCap = 0; }
+    if (e->sCompute2) CK(cudaStreamSynchronize(e->sCompute2));
+    if (slab) { cudaFree(slab); slab = nullptr; cap = 0; }
     const OrbfeFrameGeom& g = e->g;
     const size_t B = (size_t)frames;
     size_t sz[13], total = 0;
@@ -238,24 +242,32 @@ int ensure_chunk(OrbfeExtractor* e, int frames) {
     sz[10] = B * g.kpCapFrame * sizeof(OrbfeWork); sz[11] = B * g.nlevels * ocStride;
     size_t offs[13];
     for (int i = 0; i < 13; i++) { offs[i] = total; total += align_up(sz[i], 256); }
-    CK(cudaMalloc(&e->slab, total));
-    char* p = (char*)e->slab;
-    e->bufs.pyr = (uint8_t*)(p + offs[0]);
-    e->bufs.blur = (uint8_t*)(p + offs[1]);
-    e->bufs.score = (uint16_t*)(p + offs[2]);
-    e->bufs.nmsBits = (uint32_t*)(p + offs[12]);
-    e->bufs.slots = (uint32_t*)(p + offs[3]);
-    e->bufs.cellCount = (int*)(p + offs[4]);
-    e->bufs.cand = (uint32_t*)(p + offs[5]);
-    e->bufs.pnode = (uint32_t*)(p + offs[6]);
-    e->bufs.candCount = (int*)(p + offs[7]);
-    e->bufs.kp = (uint32_t*)(p + offs[8]);
-    e->bufs.kpCount = (int*)(p + offs[9]);
-    e->bufs.work = (OrbfeWork*)(p + offs[10]);
-    e->bufs.ocGlobal = ocStride ? p + offs[11] : nullptr;
-    e->bufs.ocGlobalStride = ocStride;
-    e->chunkCap = frames;
+    CK(cudaMalloc(&slab, total));
+    char* p = (char*)slab;
+    bufs.pyr = (uint8_t*)(p + offs[0]);
+    bufs.blur = (uint8_t*)(p + offs[1]);
+    bufs.score = (uint16_t*)(p + offs[2]);
+    bufs.nmsBits = (uint32_t*)(p + offs[12]);
+    bufs.slots = (uint32_t*)(p + offs[3]);
+    bufs.cellCount = (int*)(p + offs[4]);
+    bufs.cand = (uint32_t*)(p + offs[5]);
+    bufs.pnode = (uint32_t*)(p + offs[6]);
+    bufs.candCount = (int*)(p + offs[7]);
+    bufs.kp = (uint32_t*)(p + offs[8]);
+    bufs.kpCount = (int*)(p + offs[9]);
+    bufs.work = (OrbfeWork*)(p + offs[10]);
+    bufs.ocGlobal = ocStride ? p + offs[11] : nullptr;
+    bufs.ocGlobalStride = ocStride;
+    cap = frames;
     return ORBFE_OK;
+}
+
+int ensure_chunk(OrbfeExtractor* e, int frames) { return ensure_chunk_set(e, frames, e->bufs, e->slab, e->chunkCap); }
+
+// The second set, used by the odd chunks of a multi-chunk host batch.
+int ensure_chunk2(OrbfeExtractor* e, int frames) {
+    if (!e->sCompute2) CK(cudaStreamCreateWithFlags(&e->sCompute2, cudaStreamNonBlocking));
+    return ensure_chunk_set(e, frames, e->bufs2, e->slab2, e->chunkCap2);
 }
 
 int chunk_frames(const OrbfeExtractor* e, int B) {
@@ -271,24 +283,25 @@ void stage_mark(OrbfeExtractor* e, int i, cudaStream_t st) {
 // Enqueue the whole extraction of `B` (<= chunkCap) frames on `st`.
 void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size_t frameStride, int B,
                    int lap0, int lap1, OrbfeKeyPoint* d_kps, uint8_t* d_desc, int capacity, int* d_n,
-                   int* d_mono, cudaStream_t st) {
+                   int* d_mono, cudaStream_t st, const OrbfeChunkBufs* set = nullptr) {
     const OrbfeFrameGeom& g = e->g;
+    const OrbfeChunkBufs& bufs = set ? *set : e->bufs;
     stage_mark(e, 1, st);
-    orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, e->bufs, B, st, &e->launches);
+    orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, bufs, B, st, &e->launches);
     stage_mark(e, 2, st);
-    orbfe_launch_fast_score(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_fast_score(g, bufs, B, st, &e->launches);
     stage_mark(e, 3, st);
-    orbfe_launch_fast_nms(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_fast_nms(g, bufs, B, st, &e->launches);
     stage_mark(e, 4, st);
-    orbfe_launch_fast_cells(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_fast_cells(g, bufs, B, st, &e->launches);
     stage_mark(e, 5, st);
-    orbfe_launch_octree(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_octree(g, bufs, B, st, &e->launches);
     stage_mark(e, 6, st);
-    orbfe_launch_layout(g, e->bufs, B, lap0, lap1, d_kps, capacity, d_n, d_mono, st, &e->launches);
+    orbfe_launch_layout(g, bufs, B, lap0, lap1, d_kps, capacity, d_n, d_mono, st, &e->launches);
     stage_mark(e, 7, st);
-    orbfe_launch_blur(g, e->bufs, B, st, &e->launches);
+    orbfe_launch_blur(g, bufs, B, st, &e->launches);
     stage_mark(e, 8, st);
-    orbfe_launch_describe(g, e->bufs, B, d_kps, d_desc, capacity, st, &e->launches);
+    orbfe_launch_describe(g, bufs, B, d_kps, d_desc, capacity, st, &e->launches);
     stage_mark(e, 9, st);
     if (e->profiling) e->profCount++;
     e->lastFrames = B;
@@ -383,9 +396,11 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->sCompute) cudaStreamSynchronize(e->sCompute);
+    if (e->sCompute2) cudaStreamSynchronize(e->sCompute2);
     if (e->sD2H) cudaStreamSynchronize(e->sD2H);
     if (e->sH2D) cudaStreamSynchronize(e->sH2D);
     if (e->slab) cudaFree(e->slab);
+    if (e->slab2) cudaFree(e->slab2);
     if (e->d_taps) cudaFree(e->d_taps);
     for (int s = 0; s < 2; s++) {
         if (e->d_in[s]) cudaFree(e->d_in[s]);
@@ -402,6 +417,7 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
         for (int i = 0; i <= ORBFE_NUM_STAGES; i++)
             if (e->evStage[k][i]) cudaEventDestroy(e->evStage[k][i]);
     if (e->sCompute) cudaStreamDestroy(e->sCompute);
+    if (e->sCompute2) cudaStreamDestroy(e->sCompute2);
     if (e->sH2D) cudaStreamDestroy(e->sH2D);
     if (e->sD2H) cudaStreamDestroy(e->sD2H);
     delete e;
@@ -481,6 +497,10 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
     if ((rc = build_geometry(h, rows, cols))) return rc;
     const int chunk = chunk_frames(h, B);
     if ((rc = ensure_chunk(h, chunk))) return rc;
+    // more than one chunk: odd chunks run on a second stream with their own intermediates (not while profiling:
+    // the stage events belong to one stream)
+    const bool dual = B > chunk && !h->profiling;
+    if (dual && (rc = ensure_chunk2(h, chunk))) return rc;
     if ((rc = ensure_staging(h, chunk, rows, cols, capacity))) return rc;
     const size_t fbytes = (size_t)rows * cols;
     const bool packed = step == (size_t)cols && frame_stride == fbytes;
@@ -503,12 +523,13 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
                                      cols, rows, cudaMemcpyHostToDevice, h->sH2D));
         }
         CK(cudaEventRecord(h->evIn[s], h->sH2D));
-        CK(cudaStreamWaitEvent(h->sCompute, h->evIn[s], 0));
-        if (ci >= 2) CK(cudaStreamWaitEvent(h->sCompute, h->evOutFree[s], 0));
+        cudaStream_t sc = (dual && s) ? h->sCompute2 : h->sCompute;
+        CK(cudaStreamWaitEvent(sc, h->evIn[s], 0));
+        if (ci >= 2) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
         enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
-                      h->d_on[s], h->d_omono[s], h->sCompute);
-        CK(cudaEventRecord(h->evInFree[s], h->sCompute));
-        CK(cudaEventRecord(h->evDone[s], h->sCompute));
+                      h->d_on[s], h->d_omono[s], sc, (dual && s) ? &h->bufs2 : nullptr);
+        CK(cudaEventRecord(h->evInFree[s], sc));
+        CK(cudaEventRecord(h->evDone[s], sc));
         CK(cudaStreamWaitEvent(h->sD2H, h->evDone[s], 0));
         CK(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, h->d_okps[s], (size_t)nb * capacity * sizeof(OrbfeKeyPoint),
                            cudaMemcpyDeviceToHost, h->sD2H));
@@ -520,6 +541,7 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
     }
     CK(cudaStreamSynchronize(h->sD2H));
     CK(cudaStreamSynchronize(h->sCompute));
+    if (dual) CK(cudaStreamSynchronize(h->sCompute2));
     CK(cudaGetLastError());
     for (int b = 0; b < B; b++)
         if (n_out[b] > capacity) return fail(ORBFE_ERR_CAPACITY, "capacity smaller than the keypoint count (see orbfe_max_keypoints)");

@@ -145,6 +145,12 @@ struct OrbfeExtractor {
     OrbfeChunkBufs bufs = {};
     int chunkCap = 0;       // frames the chunk buffers hold
     void* slab = nullptr;   // one allocation behind bufs
+    // Second set of chunk intermediates + compute stream: multi-chunk host batches alternate between the two, so
+    // that the kernels of chunk k+1 fill the SMs while chunk k drains its tails (octree, top pyramid levels).
+    OrbfeChunkBufs bufs2 = {};
+    int chunkCap2 = 0;
+    void* slab2 = nullptr;
+    cudaStream_t sCompute2 = nullptr;
 
     // staging of the host-pointer API (double buffered)
     uint8_t* d_in[2] = {nullptr, nullptr};
