@@ -62,3 +62,38 @@ def test_cuda_small_raw_vectors_and_knn():
     k = np.load(os.path.join(G, "knn2_cv2.npz"))
     idx, dist, match = orbfe.ORBmatcher().knn2(k["query"], k["train"])
     assert np.array_equal(idx, k["idx"]) and np.array_equal(dist, k["dist"]) and np.array_equal(match, k["match"])
+
+
+# ---- matcher / BoW goldens: outputs of the reference's own functions (tests/golden/make_golden_matchers.py) ----------
+import golden_cases  # noqa: E402
+
+MATCHERS = np.load(os.path.join(G, "matchers_ref.npz"))
+
+
+def _stored(name):
+    pre = name + "/"
+    return {k[len(pre):]: MATCHERS[k] for k in MATCHERS.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("cls", golden_cases.CASES, ids=lambda c: c.name)
+def test_matcher_golden_inputs_are_reproducible(cls):
+    """The seeded case builders give the inputs the goldens were generated from (numpy RNG streams are stable)."""
+    assert np.array_equal(cls().inputs(), _stored(cls.name)["inputs"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", golden_cases.CASES, ids=lambda c: c.name)
+def test_cuda_reproduces_reference_matcher_outputs(cls):
+    """CUDA entry points against the stored outputs of the reference's own matcher functions (no oracle in between)."""
+    import orbfe
+    case = cls()
+    stored = _stored(cls.name)
+    assert np.array_equal(case.inputs(), stored.pop("inputs"))
+    got = case.cuda(orbfe, stored)
+    assert set(got) == set(stored)
+    for k, v in stored.items():
+        g = np.asarray(got[k])
+        if v.dtype.kind == "f":
+            assert np.array_equal(g.view(np.uint8), v.view(np.uint8)), (cls.name, k)      # float bit patterns
+        else:
+            assert np.array_equal(g, v), (cls.name, k)
