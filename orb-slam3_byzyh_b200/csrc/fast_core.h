@@ -69,18 +69,32 @@ static inline uint32_t fc_max3s_relu(uint32_t a, uint32_t b, uint32_t c) {
 // e[k] = biased packed differences (centre + 256 - ring_k per lane), k = 0..15 in ring order.
 // Returns per lane  max(best - sub, 0)  where `sub2` holds `sub` in both lanes (sub = minThFAST:
 // the score map stores the margin over the low threshold, 0 = "not a corner at minThFAST").
+// Operand placement: VIMNMX3 reads three registers from a two-bank register file, so an instruction whose operands
+// are all fresh needs two fetch cycles; operands that sit in the SAME source slot as in the previous instruction come
+// from the operand-reuse cache instead.  Sliding triples (v_k, v_k+1, v_k+2) share two values with their successor:
+// keeping value v_j in slot j % 3 makes both reusable (ptxas marks 25 of 32 instead of 13, tools/pipe_bench3.cu).
+#define FC_SLOT3(op, v, k, n)                                                                              \
+    op(((k) % 3 == 0) ? v[(k) % (n)] : ((k) % 3 == 2) ? v[((k) + 1) % (n)] : v[((k) + 2) % (n)],          \
+       ((k) % 3 == 1) ? v[(k) % (n)] : ((k) % 3 == 0) ? v[((k) + 1) % (n)] : v[((k) + 2) % (n)],          \
+       ((k) % 3 == 2) ? v[(k) % (n)] : ((k) % 3 == 1) ? v[((k) + 1) % (n)] : v[((k) + 2) % (n)])
+
 static FC_HD uint32_t fc_margin2(const uint32_t* e, uint32_t sub2) {
     uint32_t mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mn3[k] = fc_min3u(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-        mx3[k] = fc_max3u(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        mn3[k] = FC_SLOT3(fc_min3u, e, k, 16);
+        mx3[k] = FC_SLOT3(fc_max3u, e, k, 16);
     }
+    // arcs of 9 = three triples 3 apart: walk k in steps of 3 (3 is coprime with 16), so that consecutive arcs again
+    // share two operands; b[i] = m3[3i mod 16] turns the arc (m3_k, m3_k+3, m3_k+6) into the sliding triple (b_i, b_i+1, b_i+2)
+    uint32_t bn[16], bx[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { bn[i] = mn3[(3 * i) & 15]; bx[i] = mx3[(3 * i) & 15]; }
     uint32_t A = 0u, B = 0xFFFFFFFFu;  // max_k min9_k, min_k max9_k (biased, unsigned lanes)
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        A = fc_maxu(A, fc_min3u(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));
-        B = fc_minu(B, fc_max3u(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));
+    for (int i = 0; i < 16; i++) {
+        A = fc_maxu(A, FC_SLOT3(fc_min3u, bn, i, 16));
+        B = fc_minu(B, FC_SLOT3(fc_max3u, bx, i, 16));
     }
     // best = max(0, A-256, 256-B); margin = max(0, best - sub)
     const uint32_t a = fc_sub2(A, fc_add2(FC_BIAS2, sub2));
