@@ -270,6 +270,8 @@ int ensure_chunk2(OrbfeExtractor* e, int frames) {
     return ensure_chunk_set(e, frames, e->bufs2, e->slab2, e->chunkCap2);
 }
 
+constexpr int kGraphMaxFrames = 4;   // host-pointer calls of up to this many frames replay a captured CUDA graph
+
 int chunk_frames(const OrbfeExtractor* e, int B) {
     size_t c = e->maxBytes / std::max<size_t>(e->perFrameBytes, 1);
     c = std::max<size_t>(1, std::min<size_t>(c, 4096));
@@ -399,6 +401,7 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
     if (e->sCompute2) cudaStreamSynchronize(e->sCompute2);
     if (e->sD2H) cudaStreamSynchronize(e->sD2H);
     if (e->sH2D) cudaStreamSynchronize(e->sH2D);
+    if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
     if (e->slab) cudaFree(e->slab);
     if (e->slab2) cudaFree(e->slab2);
     if (e->d_taps) cudaFree(e->d_taps);
@@ -526,8 +529,33 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         cudaStream_t sc = (dual && s) ? h->sCompute2 : h->sCompute;
         CK(cudaStreamWaitEvent(sc, h->evIn[s], 0));
         if (ci >= 2) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
-        enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
-                      h->d_on[s], h->d_omono[s], sc, (dual && s) ? &h->bufs2 : nullptr);
+        if (B <= kGraphMaxFrames && !h->profiling) {
+            // per-frame call: one graph launch instead of 15 kernel launches
+            OrbfeExtractor::GraphKey key;
+            key.rows = rows; key.cols = cols; key.B = nb; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
+            key.in = h->d_in[s]; key.kps = h->d_okps[s]; key.desc = h->d_odesc[s]; key.slab = h->slab;
+            if (!h->graphExec || !(key == h->graphKey)) {
+                if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                const long long l0 = h->launches;
+                CK(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
+                enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
+                              h->d_on[s], h->d_omono[s], sc, nullptr);
+                CK(cudaStreamEndCapture(sc, &graph));
+                h->graphLaunches = h->launches - l0;
+                h->launches = l0;
+                cudaError_t ge = cudaGraphInstantiate(&h->graphExec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ge != cudaSuccess) { h->graphExec = nullptr; return fail(ORBFE_ERR_CUDA, "cudaGraphInstantiate", ge); }
+                h->graphKey = key;
+            }
+            CK(cudaGraphLaunch(h->graphExec, sc));
+            h->launches += h->graphLaunches;
+            h->lastFrames = nb;
+        } else {
+            enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
+                          h->d_on[s], h->d_omono[s], sc, (dual && s) ? &h->bufs2 : nullptr);
+        }
         CK(cudaEventRecord(h->evInFree[s], sc));
         CK(cudaEventRecord(h->evDone[s], sc));
         CK(cudaStreamWaitEvent(h->sD2H, h->evDone[s], 0));

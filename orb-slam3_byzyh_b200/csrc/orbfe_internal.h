@@ -172,6 +172,20 @@ struct OrbfeExtractor {
     int lastFrames = 0;
     long long launches = 0;
     size_t maxBytes = (size_t)6 << 30;
+
+    // The per-frame call (Frame::ExtractORB: one or a few frames, host pointers) replays its 15 kernel launches as one
+    // CUDA graph: the launch sequence only depends on the geometry, the lapping area and the staging buffers.
+    struct GraphKey {
+        int rows = 0, cols = 0, B = 0, lap0 = 0, lap1 = 0, capacity = 0;
+        const void *in = nullptr, *kps = nullptr, *desc = nullptr, *slab = nullptr;
+        bool operator==(const GraphKey& o) const {
+            return rows == o.rows && cols == o.cols && B == o.B && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity &&
+                   in == o.in && kps == o.kps && desc == o.desc && slab == o.slab;
+        }
+    };
+    GraphKey graphKey;
+    cudaGraphExec_t graphExec = nullptr;
+    long long graphLaunches = 0;
 };
 
 
