@@ -529,7 +529,7 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         cudaStream_t sc = (dual && s) ? h->sCompute2 : h->sCompute;
         CK(cudaStreamWaitEvent(sc, h->evIn[s], 0));
         if (ci >= 2) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
-        if (B <= kGraphMaxFrames && !h->profiling) {
+        if (B <= kGraphMaxFrames && B <= chunk && !h->profiling) {
             // per-frame call: one graph launch instead of 15 kernel launches
             OrbfeExtractor::GraphKey key;
             key.rows = rows; key.cols = cols; key.B = nb; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
