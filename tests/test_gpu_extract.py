@@ -206,3 +206,27 @@ def test_unusual_thresholds_and_full_hd(orbfe):
         _check_frame(orbfe.ORBextractor(800, 1.2, 8, ini, mn), O.Extractor(800, 1.2, 8, ini, mn), img, (0, 0))
     big = synth.synth_frame(1080, 1920, 32)
     _check_frame(orbfe.ORBextractor(4000), O.Extractor(4000), big, (0, 1000), stages=False)
+
+
+def test_small_host_batches_graph_replay_and_chunking(orbfe):
+    """Host-pointer calls of 1-4 frames replay a captured CUDA graph when they fit one chunk; changing the lapping area,
+    the batch size or the image size re-captures; a 4-frame call that needs several chunks takes the chunked path."""
+    ex_g, ex_c = orbfe.ORBextractor(1000), O.Extractor(1000)
+    frames = np.stack([synth.synth_frame(480, 752, 60 + i) for i in range(4)])
+
+    def check(fr, lap):
+        n, mono, kps, desc = ex_g.extract_batch(fr, lap)
+        for i in range(len(fr)):
+            mo, ko, do = ex_c(fr[i], lap)
+            assert mono[i] == mo and n[i] == len(ko) and kps[i, :n[i]].tobytes() == ko.tobytes()
+            assert np.array_equal(desc[i, :n[i]], do)
+    for lap in ((0, 1000), (0, 1000), (0, 0), (100, 411)):      # second call replays, the others re-capture
+        check(frames[:3], lap)
+    check(frames[:1], (0, 0))
+    check(frames, (0, 1000))
+    big = np.stack([synth.synth_frame(720, 1280, 70 + i) for i in range(4)])
+    ex_g.set_max_bytes(64 << 20)                                 # 22 MB per 1280x720 frame: chunks of 2 -> 1, 1, 2 frames
+    check(big, (0, 1000))
+    ex_g.set_max_bytes(6 << 30)
+    check(big[:2], (0, 1000))                                    # back to one chunk: graph again, new geometry
+    check(frames[:2], (0, 1000))
