@@ -22,6 +22,7 @@
 // is a per-column / per-row mask.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "fast_core.h"
 #include "octree_core.h"  // OC_PACK
@@ -39,78 +40,106 @@ constexpr int TW = ORBFE_FAST_TW, TH = ORBFE_FAST_TH;
 constexpr int TROWS = TH + 6;         // 22 staged rows
 constexpr int TG = TW / 4 + 1;        // 33 four-pixel groups per staged row and copy
 static_assert(TW == 128 && TH == 16, "thread mapping below assumes 128x16 tiles");
+static_assert(3 * 8 >= TH + 6, "three row copies per warp cover the staged rows");
 
-// A CTA walks `tilesPerCta` consecutive tiles of one frame.  The raw bytes of tile i+1 are requested from global
-// memory (into registers) BEFORE tile i is scored and parked in a small raw staging buffer afterwards, so the
-// global-load latency hides behind the min/max network instead of stalling every warp of the CTA at its start
-// (measured, 1024 frames: 4.49 ms with one tile per CTA, 4.34 / 4.27 / 4.24 ms with 4 / 8 / 16; tools/fast_per_sweep.sh).
-constexpr int RAWW = TG + 1;            // 34 words per staged row: 33 groups + the word the last group shifts in
-constexpr int RAWN = TROWS * RAWW;      // 748 words per tile
-constexpr int RAWPT = (RAWN + 255) / 256;
+// A CTA walks `tilesPerCta` consecutive tiles of one frame and keeps the raw bytes of the NEXT TWO tiles in flight:
+// a staged tile (22 rows x 144 bytes of the padded level) is one TMA tensor copy (cp.async.bulk.tensor.3d global ->
+// shared through the level's CUtensorMap, issued by a single thread, completion counted in bytes on an mbarrier) into
+// one of two raw staging buffers.  No thread holds a register or issues a load for the tile data, and the global-load
+// latency hides behind the min/max network instead of stalling every warp of the CTA at its start (measured, 1024
+// frames: 4.49 ms with one tile per CTA and plain loads; tools/fast_per_sweep.sh sweeps the tiles per CTA).
+// Rows / columns of the box that fall outside the padded level are zero-filled by the TMA unit; they never reach the
+// ring of a scored pixel (the FAST domain ends 19 px inside the ROI, the ring reaches 3 px, the border is 19 px).
+constexpr int RAWW = 36;                          // words per staged row: 144 bytes = 33 groups + the shifted-in word, 16-byte multiple
+constexpr uint32_t RAW_ROW_BYTES = 4 * RAWW;
+constexpr uint32_t RAW_TILE_BYTES = RAW_ROW_BYTES * TROWS;
 
-struct FastTile {
-    const uint32_t* src;   // level base (words)
-    int pw, w0, y0, ymax;
-};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ FastTile fast_tile(const OrbfeFrameGeom& g, const uint8_t* pyr, size_t frameOff, int t) {
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a tile that never lands is a bug, and a trap is better than a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Thread 0 requests tile t of frame `frame` into `raw`.
+__device__ __forceinline__ void fast_request(const OrbfeFrameGeom& g, const OrbfeFastMaps& maps, int frame, int t, void* raw,
+                                             uint64_t* bar) {
+    if (threadIdx.x != 0) return;
     int l = 0;
     while (l + 1 < g.nlevels && t >= g.lv[l + 1].fastTileBase) l++;
     const OrbfeLevelGeom& L = g.lv[l];
     const int tl = t - L.fastTileBase;
     const int ty = tl / L.fastTilesX, tx = tl - ty * L.fastTilesX;
-    FastTile T;
-    // FAST domain origin = ROI (19,19).  Staged column 0 = ROI x 16 + 128*tx = padded column
-    // 48 + 128*tx (16-byte aligned); staged row 0 = ROI y 16 + 16*ty.
-    T.src = reinterpret_cast<const uint32_t*>(pyr + frameOff + L.off);
-    T.pw = L.pitch >> 2; T.w0 = (ORBFE_XOFF + 16 + TW * tx) >> 2;
-    T.y0 = ORBFE_YOFF + 16 + TH * ty; T.ymax = L.h + 2 * ORBFE_YOFF - 1;
-    return T;
-}
-
-__device__ __forceinline__ void fast_fetch(const FastTile& T, uint32_t (&v)[RAWPT]) {
-#pragma unroll
-    for (int j = 0; j < RAWPT; j++) {
-        const int i = threadIdx.x + 256 * j;
-        v[j] = 0u;
-        if (i < RAWN) {
-            const int r = i / RAWW, q = i - r * RAWW;
-            v[j] = T.src[(size_t)min(T.y0 + r, T.ymax) * T.pw + min(T.w0 + q, T.pw - 1)];
-        }
-    }
+    mbar_expect_tx(bar, RAW_TILE_BYTES);
+    // FAST domain origin = ROI (19,19).  Staged column 0 = ROI x 16 + 128*tx = padded byte column
+    // 48 + 128*tx (16-byte aligned); staged row 0 = ROI y 16 + 16*ty = padded row 35 + 16*ty.
+    tma_tile_g2s(raw, &maps.m[l], ORBFE_XOFF + 16 + TW * tx, ORBFE_YOFF + 16 + TH * ty, frame, bar);
 }
 
 __global__ void __launch_bounds__(256)
-k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr,
+k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ OrbfeFastMaps maps,
              uint16_t* __restrict__ score, int tilesPerCta) {
     __shared__ __align__(16) uint2 cp[4][TROWS][TG];
-    __shared__ uint32_t raw[RAWN];
+    struct __align__(128) RawTile { uint32_t w[TROWS][RAWW]; };   // TMA destinations are 128-byte aligned: sizeof = 3200
+    __shared__ RawTile raw[2];
+    __shared__ __align__(8) uint64_t bar[2];
     const size_t frameOff = (size_t)blockIdx.y * g.pyrStride;
     const int t0 = blockIdx.x * tilesPerCta, t1 = min(t0 + tilesPerCta, g.fastTiles);
     const uint32_t sub2 = (uint32_t)g.subTh * 0x00010001u;
     const int gq = threadIdx.x & 31, rp = threadIdx.x >> 5;
-    uint32_t nxt[RAWPT];
-    fast_fetch(fast_tile(g, pyr, frameOff, t0), nxt);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    fast_request(g, maps, blockIdx.y, t0, &raw[0], &bar[0]);      // two tiles in flight
+    if (t0 + 1 < t1) fast_request(g, maps, blockIdx.y, t0 + 1, &raw[1], &bar[1]);
     for (int t = t0; t < t1; t++) {
-        if (t > t0) __syncthreads();   // every warp is done reading cp / raw of the previous tile
-#pragma unroll
-        for (int j = 0; j < RAWPT; j++) {
-            const int i = threadIdx.x + 256 * j;
-            if (i < RAWN) raw[i] = nxt[j];
-        }
-        __syncthreads();
+        const int b = (t - t0) & 1;
+        const uint32_t parity = ((t - t0) >> 1) & 1;
+        mbar_wait(&bar[b], parity);                      // tile t has landed in raw[b]
+        if (t > t0) __syncthreads();                     // every warp is done reading cp of the previous tile
         for (int i = threadIdx.x; i < TROWS * TG; i += 256) {
             const int r = i / TG, q = i - r * TG;
-            const uint32_t a = raw[r * RAWW + q], b = raw[r * RAWW + q + 1];
+            const uint32_t a = raw[b].w[r][q], c = raw[b].w[r][q + 1];
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                const uint32_t v = s ? __funnelshift_r(a, b, 8 * s) : a;   // pixels 4q+s .. 4q+s+3
+                const uint32_t v = s ? __funnelshift_r(a, c, 8 * s) : a;   // pixels 4q+s .. 4q+s+3
                 cp[s][r][q] = make_uint2(__byte_perm(v, 0u, 0x4140), __byte_perm(v, 0u, 0x4342));
             }
         }
-        // request the next tile now; it is consumed after this tile's network
-        if (t + 1 < t1) fast_fetch(fast_tile(g, pyr, frameOff, t + 1), nxt);
-        __syncthreads();
+        __syncthreads();                                 // cp is complete; raw[b] is free again
+        if (t + 2 < t1) {
+            // the generic-proxy reads of raw[b] above are ordered before the async-proxy writes of the next request
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fast_request(g, maps, blockIdx.y, t + 2, &raw[b], &bar[b]);
+        }
         int l = 0;
         while (l + 1 < g.nlevels && t >= g.lv[l + 1].fastTileBase) l++;
         const OrbfeLevelGeom& L = g.lv[l];
@@ -380,6 +409,37 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restric
 
 }  // namespace
 
+// One CUtensorMap per pyramid level of this buffer set: a 3-D byte tensor {padded columns (pitch), padded rows, frames}
+// with strides {pitch, pyrStride}; box = one staged FAST tile (144 bytes x 22 rows x 1 frame), no swizzle, zero fill.
+int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess)
+            return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver", cudaGetLastError());
+        encode = (EncodeFn)fn;
+    }
+    memset(&b.fastMaps, 0, sizeof b.fastMaps);
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbfeLevelGeom& L = g.lv[l];
+        if (L.fastTilesX <= 0 || L.fastTilesY <= 0) continue;
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * ORBFE_YOFF), (cuuint64_t)frames};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyrStride};
+        const cuuint32_t box[3] = {RAW_ROW_BYTES, (cuuint32_t)TROWS, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&b.fastMaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, b.pyr + L.off, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for a pyramid level", cudaSuccess);
+    }
+    return ORBFE_OK;
+}
+
 void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches) {
     if (g.fastTiles <= 0) return;
@@ -388,7 +448,7 @@ void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, i
     const long long tiles = (long long)g.fastTiles * B;
     int per = tiles >= 148LL * 4 * 64 ? 16 : tiles >= 148LL * 4 * 32 ? 8 : tiles >= 148LL * 4 * 16 ? 4 : 1;
     if (const char* ev = getenv("ORBFE_FAST_TILES_PER_CTA")) per = std::max(1, atoi(ev));
-    k_fast_score<<<dim3((g.fastTiles + per - 1) / per, B), 256, 0, st>>>(g, b.pyr, b.score, per);
+    k_fast_score<<<dim3((g.fastTiles + per - 1) / per, B), 256, 0, st>>>(g, b.fastMaps, b.score, per);
     ++*launches;
 }
 

@@ -258,6 +258,8 @@ int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*&
     bufs.work = (OrbfeWork*)(p + offs[10]);
     bufs.ocGlobal = ocStride ? p + offs[11] : nullptr;
     bufs.ocGlobalStride = ocStride;
+    const int mrc = orbfe_fast_make_maps(g, bufs, frames);
+    if (mrc != ORBFE_OK) return mrc;
     cap = frames;
     return ORBFE_OK;
 }

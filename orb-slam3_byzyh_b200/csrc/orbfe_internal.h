@@ -1,5 +1,6 @@
 // orbfe_internal.h -- geometry shared by the host planner (orbfe_api.cu) and the kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -83,7 +84,14 @@ struct OrbfeWork {
 #define ORBFE_BLUR_TH 32   // output rows per warp strip
 
 // Device buffers of one chunk of frames (all frame-major).
+// TMA descriptors of the padded pyramid levels of one chunk buffer set: level l as a 3-D byte tensor
+// (padded columns, padded rows, frames); k_fast_score fetches a whole staged tile with one instruction.
+struct OrbfeFastMaps {
+    CUtensorMap m[ORBFE_MAX_LEVELS];
+};
+
 struct OrbfeChunkBufs {
+    OrbfeFastMaps fastMaps;
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
     uint16_t* score;     // [B][pyrStride] u16: FAST margin max(best - subTh, 0), column = ROI x + ORBFE_SXOFF
@@ -108,6 +116,8 @@ int orbfe_fail(int code, const char* what, cudaError_t e);
 void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
                           size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
                           cudaStream_t st, long long* launches);
+// Fills b.fastMaps for the buffer set (needs the driver's cuTensorMapEncodeTiled, resolved at run time).
+int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
 void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches);
 void orbfe_launch_fast_nms(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,

@@ -230,3 +230,14 @@ def test_small_host_batches_graph_replay_and_chunking(orbfe):
     ex_g.set_max_bytes(6 << 30)
     check(big[:2], (0, 1000))                                    # back to one chunk: graph again, new geometry
     check(frames[:2], (0, 1000))
+
+
+@pytest.mark.parametrize("per", [2, 3, 16, 1000])
+def test_fast_score_tiles_per_cta(orbfe, per, monkeypatch):
+    """k_fast_score walks several tiles per CTA with two TMA tile copies in flight (mbarrier phases alternate per
+    buffer); large batches pick 4-16 tiles per CTA on their own, here the count is forced on single frames, including
+    odd counts, a count that crosses pyramid levels and one CTA for the whole frame."""
+    monkeypatch.setenv("ORBFE_FAST_TILES_PER_CTA", str(per))
+    for (h, w, seed) in ((480, 752, 31), (241, 323, 32)):
+        img = synth.synth_frame(h, w, seed)
+        _check_frame(orbfe.ORBextractor(1000), O.Extractor(1000), img, (0, 1000), stages=True)
