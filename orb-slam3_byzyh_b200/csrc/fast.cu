@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "fast_core.h"
+#include "tma.h"
 #include "octree_core.h"  // OC_PACK
 #include "orbfe_internal.h"
 
@@ -53,38 +54,6 @@ static_assert(3 * 8 >= TH + 6, "three row copies per warp cover the staged rows"
 constexpr int RAWW = 36;                          // words per staged row: 144 bytes = 33 groups + the shifted-in word, 16-byte multiple
 constexpr uint32_t RAW_ROW_BYTES = 4 * RAWW;
 constexpr uint32_t RAW_TILE_BYTES = RAW_ROW_BYTES * TROWS;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a tile that never lands is a bug, and a trap is better than a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
-        if (spins > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-        : "memory");
-}
 
 // Thread 0 requests tile t of frame `frame` into `raw`.
 __device__ __forceinline__ void fast_request(const OrbfeFrameGeom& g, const OrbfeFastMaps& maps, int frame, int t, void* raw,
@@ -115,7 +84,7 @@ k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
     fast_request(g, maps, blockIdx.y, t0, &raw[0], &bar[0]);      // two tiles in flight
@@ -137,7 +106,7 @@ k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
         __syncthreads();                                 // cp is complete; raw[b] is free again
         if (t + 2 < t1) {
             // the generic-proxy reads of raw[b] above are ordered before the async-proxy writes of the next request
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fence_proxy_async();
             fast_request(g, maps, blockIdx.y, t + 2, &raw[b], &bar[b]);
         }
         int l = 0;
@@ -409,9 +378,9 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const uint16_t* __restric
 
 }  // namespace
 
-// One CUtensorMap per pyramid level of this buffer set: a 3-D byte tensor {padded columns (pitch), padded rows, frames}
-// with strides {pitch, pyrStride}; box = one staged FAST tile (144 bytes x 22 rows x 1 frame), no swizzle, zero fill.
-int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames) {
+// One CUtensorMap per pyramid level of a buffer set: a 3-D byte tensor {padded columns (pitch), padded rows, frames}
+// with strides {pitch, pyrStride}; box = boxW bytes x boxH rows x 1 frame, no swizzle, zero fill outside the tensor.
+int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, int boxW, int boxH, OrbfeFastMaps& maps) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -424,20 +393,23 @@ int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames)
             return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver", cudaGetLastError());
         encode = (EncodeFn)fn;
     }
-    memset(&b.fastMaps, 0, sizeof b.fastMaps);
+    memset(&maps, 0, sizeof maps);
     for (int l = 0; l < g.nlevels; l++) {
         const OrbfeLevelGeom& L = g.lv[l];
-        if (L.fastTilesX <= 0 || L.fastTilesY <= 0) continue;
         const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(L.h + 2 * ORBFE_YOFF), (cuuint64_t)frames};
         const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyrStride};
-        const cuuint32_t box[3] = {RAW_ROW_BYTES, (cuuint32_t)TROWS, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)std::min(boxH, 256), 1};
         const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = encode(&b.fastMaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, b.pyr + L.off, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+        const CUresult r = encode(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(pyr) + L.off, dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for a pyramid level", cudaSuccess);
     }
     return ORBFE_OK;
+}
+
+int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames) {
+    return orbfe_make_level_maps(g, b.pyr, frames, (int)RAW_ROW_BYTES, TROWS, b.fastMaps);
 }
 
 void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,

@@ -91,7 +91,7 @@ struct OrbfeFastMaps {
 };
 
 struct OrbfeChunkBufs {
-    OrbfeFastMaps fastMaps;
+    OrbfeFastMaps fastMaps;   // boxes of k_fast_score (144 B x 22 rows)
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
     uint16_t* score;     // [B][pyrStride] u16: FAST margin max(best - subTh, 0), column = ROI x + ORBFE_SXOFF
@@ -118,6 +118,7 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
                           cudaStream_t st, long long* launches);
 // Fills b.fastMaps for the buffer set (needs the driver's cuTensorMapEncodeTiled, resolved at run time).
 int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
+int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, int boxW, int boxH, OrbfeFastMaps& maps);
 void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                              long long* launches);
 void orbfe_launch_fast_nms(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
