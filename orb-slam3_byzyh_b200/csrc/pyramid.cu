@@ -105,7 +105,9 @@ k_resize(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict_
 // shuffle; the source row the NEXT destination row will need is requested before the current row
 // is computed.  Border columns/rows are the same computation on the reflected destination
 // coordinate, so resize + copyMakeBorder stay one pass with coalesced 64-bit stores.
-constexpr int RS_ROWS = 16, RS_WARPS = 4, RS_G = 2;   // rows per warp strip, warps per CTA, words per thread
+constexpr int RS_ROWS = 16, RS_WARPS = 4, RS_G = 1;   // rows per warp strip, warps per CTA, words per thread
+// (RS_G = 2 halves the tap setup per pixel but needs 77 registers: 24 resident warps per SM left the row loads exposed;
+//  one word per thread runs in 48 registers, 40 warps per SM: 1.77 -> 1.60 ms per 1024 frames)
 
 __global__ void __launch_bounds__(32 * RS_WARPS)
 k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __restrict__ xtab,
@@ -168,11 +170,11 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
     int c0 = -1, c1 = -1;
     uint32_t C0[RS_G][4], C1[RS_G][4];   // cached horizontal passes of source rows c0, c1
     const int n = min(RS_ROWS, H - py0);
-    uint2* dst = reinterpret_cast<uint2*>(base + dstOff + (size_t)py0 * pitch) + (wc0 >> 1);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(base + dstOff + (size_t)py0 * pitch) + wc0;
     unsigned rs = __shfl_sync(0xffffffffu, tapS, 0);
     int pr = (int)(rs >> 16);            // prefetched source row (the one the first row needs as r1)
     Raw P = fetch(pr);
-    for (int i = 0; i < n; i++, dst += words >> 1) {
+    for (int i = 0; i < n; i++, dst += words) {
         const int r0 = (int)(rs & 0xFFFFu), r1 = (int)(rs >> 16);
         const unsigned wa = __shfl_sync(0xffffffffu, tapA, i);
         const Raw got = P;
@@ -219,7 +221,7 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
             for (int k = 0; k < 4; k++) v[k] = (__umulhi(b0, C0[g][k]) + __umulhi(b1, C1[g][k]) + 2u) >> 2;
             o[g] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         }
-        if (active) *dst = make_uint2(o[0], o[1]);
+        if (active) *dst = o[0];
     }
 }
 
