@@ -109,6 +109,14 @@ int orbfe_set_profiling(OrbfeExtractor* h, int enable);
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
 /* Number of kernel launches issued by this extractor since creation. */
 long long orbfe_launch_count(const OrbfeExtractor* h);
+/* Stereo rectification fused into the extractor: System::TrackStereo remaps both images before it hands them to
+ * Tracking (cv::remap(imLeft, imLeftToFeed, M1l, M2l, cv::INTER_LINEAR), src/System.cc:286-293).  With maps set
+ * (CV_32FC1 x / y maps of the rectified size rows x cols, copied to the device), every orbfe_extract* call takes the RAW
+ * camera frames (rows / cols of the call = raw size) and computes pyramid level 0 as the rectified image, bit-exact
+ * with cv::remap + copyMakeBorder; all outputs are those of ORBextractor run on the rectified image, and
+ * orbfe_pyramid_level(h, frame, 0, ...) returns the rectified image itself.  NULL maps switch it off. */
+int orbfe_extractor_set_rectification(OrbfeExtractor* h, const float* map_x, const float* map_y,
+                                      int rows, int cols);
 /* Device-memory budget of ONE chunk of intermediates (default 6 GiB, env ORBFE_MAX_BYTES); batches larger than
  * one chunk are processed chunk after chunk.  orbfe_extract_batch (host pointers) keeps two chunks in flight on two
  * compute streams, so it allocates up to twice this budget. */

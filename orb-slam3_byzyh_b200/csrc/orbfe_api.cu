@@ -290,8 +290,10 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
                    int* d_mono, cudaStream_t st, const OrbfeChunkBufs* set = nullptr) {
     const OrbfeFrameGeom& g = e->g;
     const OrbfeChunkBufs& bufs = set ? *set : e->bufs;
+    OrbfeRectify rect;
+    rect.mapx = e->d_mapx; rect.mapy = e->d_mapy; rect.srcRows = e->srcRows; rect.srcCols = e->srcCols;
     stage_mark(e, 1, st);
-    orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, bufs, B, st, &e->launches);
+    orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, bufs, B, st, &e->launches, e->d_mapx ? &rect : nullptr);
     stage_mark(e, 2, st);
     orbfe_launch_fast_score(g, bufs, B, st, &e->launches);
     stage_mark(e, 3, st);
@@ -404,6 +406,8 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
     if (e->sD2H) cudaStreamSynchronize(e->sD2H);
     if (e->sH2D) cudaStreamSynchronize(e->sH2D);
     if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
+    if (e->d_mapx) cudaFree(e->d_mapx);
+    if (e->d_mapy) cudaFree(e->d_mapy);
     if (e->slab) cudaFree(e->slab);
     if (e->slab2) cudaFree(e->slab2);
     if (e->d_taps) cudaFree(e->d_taps);
@@ -462,6 +466,26 @@ int orbfe_level_size(const OrbfeExtractor* h, int rows, int cols, int level, int
     return ORBFE_OK;
 }
 
+int orbfe_extractor_set_rectification(OrbfeExtractor* h, const float* map_x, const float* map_y, int rows, int cols) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->sCompute));
+    if (h->sCompute2) CK(cudaStreamSynchronize(h->sCompute2));
+    if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
+    if (h->d_mapx) { cudaFree(h->d_mapx); h->d_mapx = nullptr; }
+    if (h->d_mapy) { cudaFree(h->d_mapy); h->d_mapy = nullptr; }
+    h->rectRows = h->rectCols = 0;
+    if (!map_x && !map_y) return ORBFE_OK;   // rectification off
+    if (!map_x || !map_y || rows <= 0 || cols <= 0) return fail(ORBFE_ERR_INVALID, "rectification maps: bad arguments");
+    const size_t bytes = sizeof(float) * (size_t)rows * cols;
+    CK(cudaMalloc(&h->d_mapx, bytes));
+    CK(cudaMalloc(&h->d_mapy, bytes));
+    CK(cudaMemcpy(h->d_mapx, map_x, bytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_mapy, map_y, bytes, cudaMemcpyHostToDevice));
+    h->rectRows = rows; h->rectCols = cols;
+    return ORBFE_OK;
+}
+
 int orbfe_set_max_bytes(OrbfeExtractor* h, unsigned long long bytes) {
     if (!h) return fail(ORBFE_ERR_INVALID, "null extractor");
     h->maxBytes = std::max<size_t>((size_t)bytes, (size_t)64 << 20);
@@ -477,7 +501,8 @@ int orbfe_extract_batch_device(OrbfeExtractor* h, const uint8_t* d_images, int B
     if (!d_images || rows <= 0 || cols <= 0) return fail(ORBFE_EMPTY_IMAGE, "empty image");
     if (B <= 0 || capacity <= 0 || step < (size_t)cols || !d_keypoints || !d_descriptors || !d_n_out || !d_mono_out)
         return fail(ORBFE_ERR_INVALID, "bad batch arguments");
-    if ((rc = build_geometry(h, rows, cols))) return rc;
+    h->srcRows = rows; h->srcCols = cols;
+    if ((rc = build_geometry(h, h->d_mapx ? h->rectRows : rows, h->d_mapx ? h->rectCols : cols))) return rc;
     const int chunk = chunk_frames(h, B);
     if ((rc = ensure_chunk(h, chunk))) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->sCompute;
@@ -499,7 +524,8 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
     if (!images || rows <= 0 || cols <= 0) return fail(ORBFE_EMPTY_IMAGE, "empty image");
     if (B <= 0 || capacity <= 0 || step < (size_t)cols || !keypoints || !descriptors || !n_out || !mono_out)
         return fail(ORBFE_ERR_INVALID, "bad batch arguments");
-    if ((rc = build_geometry(h, rows, cols))) return rc;
+    h->srcRows = rows; h->srcCols = cols;
+    if ((rc = build_geometry(h, h->d_mapx ? h->rectRows : rows, h->d_mapx ? h->rectCols : cols))) return rc;
     const int chunk = chunk_frames(h, B);
     if ((rc = ensure_chunk(h, chunk))) return rc;
     // more than one chunk: odd chunks run on a second stream with their own intermediates (not while profiling:
@@ -535,7 +561,7 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
             // per-frame call: one graph launch instead of 15 kernel launches
             OrbfeExtractor::GraphKey key;
             key.rows = rows; key.cols = cols; key.B = nb; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
-            key.in = h->d_in[s]; key.kps = h->d_okps[s]; key.desc = h->d_odesc[s]; key.slab = h->slab;
+            key.in = h->d_in[s]; key.kps = h->d_okps[s]; key.desc = h->d_odesc[s]; key.slab = h->slab; key.map = h->d_mapx;
             if (!h->graphExec || !(key == h->graphKey)) {
                 if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
                 cudaGraph_t graph = nullptr;

@@ -113,9 +113,14 @@ struct OrbfeChunkBufs {
 int orbfe_fail(int code, const char* what, cudaError_t e);
 
 // ---- kernel launchers (each enqueues on `st`, no synchronisation) ----------------------------
+// Level 0 source of orbfe_launch_pyramid: the frames as given, or rectified on the fly through CV_32FC1 maps.
+struct OrbfeRectify {
+    const float *mapx = nullptr, *mapy = nullptr;   // rectified rows x cols (= the geometry's level 0), device
+    int srcRows = 0, srcCols = 0;                   // size of the raw input frames
+};
 void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
                           size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
-                          cudaStream_t st, long long* launches);
+                          cudaStream_t st, long long* launches, const OrbfeRectify* rect = nullptr);
 // Fills b.fastMaps for the buffer set (needs the driver's cuTensorMapEncodeTiled, resolved at run time).
 int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
 int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, int boxW, int boxH, OrbfeFastMaps& maps);
@@ -184,14 +189,20 @@ struct OrbfeExtractor {
     long long launches = 0;
     size_t maxBytes = (size_t)6 << 30;
 
+    // Stereo rectification fused into pyramid level 0 (orbfe_extractor_set_rectification): CV_32FC1 maps of the
+    // rectified size on the device; input images then have srcRows x srcCols of their own.
+    float *d_mapx = nullptr, *d_mapy = nullptr;
+    int rectRows = 0, rectCols = 0;
+    int srcRows = 0, srcCols = 0;   // size of the frames of the current call
+
     // The per-frame call (Frame::ExtractORB: one or a few frames, host pointers) replays its 15 kernel launches as one
     // CUDA graph: the launch sequence only depends on the geometry, the lapping area and the staging buffers.
     struct GraphKey {
         int rows = 0, cols = 0, B = 0, lap0 = 0, lap1 = 0, capacity = 0;
-        const void *in = nullptr, *kps = nullptr, *desc = nullptr, *slab = nullptr;
+        const void *in = nullptr, *kps = nullptr, *desc = nullptr, *slab = nullptr, *map = nullptr;
         bool operator==(const GraphKey& o) const {
             return rows == o.rows && cols == o.cols && B == o.B && lap0 == o.lap0 && lap1 == o.lap1 && capacity == o.capacity &&
-                   in == o.in && kps == o.kps && desc == o.desc && slab == o.slab;
+                   in == o.in && kps == o.kps && desc == o.desc && slab == o.slab && map == o.map;
         }
     };
     GraphKey graphKey;

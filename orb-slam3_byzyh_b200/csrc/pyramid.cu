@@ -48,6 +48,43 @@ k_level0(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8
     *reinterpret_cast<uint4*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 16 * gx) = out;
 }
 
+// Level 0 with the stereo rectification of System::TrackStereo fused in (src/System.cc:286-293): every padded pixel is
+// cv::remap(INTER_LINEAR, CV_32FC1 maps, constant 0 border) evaluated at the reflect-101 image of its coordinate, so the
+// rectified image never exists outside the pyramid.  Arithmetic as in intake.cu:k_remap_linear (bit-exact with cv2).
+__device__ __forceinline__ int rect_fix(float v) {
+    const float s = v * 32.0f;
+    if (!(s > -1.0e9f)) return -(1 << 30);
+    if (!(s < 1.0e9f)) return 1 << 30;
+    return __float2int_rn(s);
+}
+__global__ void __launch_bounds__(256)
+k_level0_rect(const uint8_t* __restrict__ img, size_t step, size_t frameStride, int srows, int scols,
+              const float* __restrict__ mapx, const float* __restrict__ mapy, uint8_t* __restrict__ pyr,
+              unsigned long long pyrStride, int w, int h, int pitch) {
+    const int wx = blockIdx.x * 64 + (threadIdx.x & 63);          // 4-byte word inside the padded row
+    const int py = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (wx >= (pitch >> 2) || py >= h + 2 * ORBFE_YOFF) return;
+    const uint8_t* src = img + (size_t)blockIdx.z * frameStride;
+    const int y = reflect101_clamped(py - ORBFE_YOFF, h);
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = reflect101_clamped(4 * wx - ORBFE_XOFF + i, w);
+        const int sx = rect_fix(mapx[(size_t)y * w + x]), sy = rect_fix(mapy[(size_t)y * w + x]);
+        const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
+        const int fx = sx & 31, fy = sy & 31;
+        const bool x0 = ix >= 0 && ix < scols, x1 = ix + 1 >= 0 && ix + 1 < scols;
+        const bool y0 = iy >= 0 && iy < srows, y1 = iy + 1 >= 0 && iy + 1 < srows;
+        const uint8_t* r0 = src + (size_t)max(iy, 0) * step;
+        const uint8_t* r1 = src + (size_t)max(iy + 1, 0) * step;
+        const int p00 = (x0 && y0) ? r0[ix] : 0, p01 = (x1 && y0) ? r0[ix + 1] : 0;
+        const int p10 = (x0 && y1) ? r1[ix] : 0, p11 = (x1 && y1) ? r1[ix + 1] : 0;
+        const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+        out |= (uint32_t)((p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 4 * wx) = out;
+}
+
 // mode 0: bilinear taps; 1: exact 2x2 area average; 2: identity
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -229,12 +266,16 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
 
 void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const uint8_t* d_images,
                           size_t step, size_t frameStride, const OrbfeChunkBufs& b, int B,
-                          cudaStream_t st, long long* launches) {
+                          cudaStream_t st, long long* launches, const OrbfeRectify* rect) {
     for (int l = 0; l < g.nlevels; l++) {
         const OrbfeLevelGeom& L = g.lv[l];
         const int total = (L.pitch >> 2) * (L.h + 2 * ORBFE_YOFF);
         dim3 grid((total + 255) / 256, B);
-        if (l == 0) {
+        if (l == 0 && rect && rect->mapx) {
+            dim3 g0(((L.pitch >> 2) + 63) / 64, (L.h + 2 * ORBFE_YOFF + 3) / 4, B);
+            k_level0_rect<<<g0, 256, 0, st>>>(d_images, step, frameStride, rect->srcRows, rect->srcCols, rect->mapx, rect->mapy,
+                                              b.pyr + L.off, g.pyrStride, L.w, L.h, L.pitch);
+        } else if (l == 0) {
             dim3 g0(((L.pitch >> 4) + 63) / 64, (L.h + 2 * ORBFE_YOFF + 3) / 4, B);
             k_level0<<<g0, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride,
                                          L.w, L.h, L.pitch);

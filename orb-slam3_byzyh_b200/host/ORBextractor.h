@@ -60,7 +60,7 @@ class ORBextractor {
             cv::Mat d = _descriptors.getMat();
             for (int i = 0; i < n; i++) memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
         }
-        if (mbHostPyramid) SyncPyramidToHost(image.rows, image.cols);
+        if (mbHostPyramid) SyncPyramidToHost(rectRows_ ? rectRows_ : image.rows, rectCols_ ? rectCols_ : image.cols);
         return mono;  // :1681
     }
 
@@ -90,12 +90,22 @@ class ORBextractor {
         }
     }
 
+    // Stereo rectification fused into the extractor (System::TrackStereo, System.cc:286-293): with maps set
+    // (M1 / M2 of Settings as CV_32FC1, rows x cols of the rectified image) operator() takes the RAW camera image and
+    // mvImagePyramid[0] is the rectified image.  Null pointers switch it off.
+    void SetRectification(const float* mapX, const float* mapY, int rows, int cols) {
+        if (orbfe_extractor_set_rectification(h_, mapX, mapY, rows, cols) != ORBFE_OK)
+            throw std::runtime_error(std::string("ORBextractor (B200): ") + orbfe_last_error());
+        rectRows_ = mapX ? rows : 0; rectCols_ = mapX ? cols : 0;
+    }
+
     OrbfeExtractor* handle() const { return h_; }  // for ORBmatcher_b200.h
 
    protected:
     OrbfeExtractor* h_;
     int nlevels;
     int capacity_;
+    int rectRows_ = 0, rectCols_ = 0;
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 };
 

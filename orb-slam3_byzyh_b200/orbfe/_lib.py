@@ -95,6 +95,7 @@ _SIGS = {
     "orbfe_set_profiling": (_i, [_vp, _i]),
     "orbfe_stage_ms": (_i, [_vp, _vp]),
     "orbfe_launch_count": (C.c_longlong, [_vp]),
+    "orbfe_extractor_set_rectification": (_i, [_vp, _vp, _vp, _i, _i]),
     "orbfe_set_max_bytes": (_i, [_vp, _ull]),
     "orbfe_frame_geometry": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ull), C.POINTER(_ull)]),
     "orbfe_descriptor_distance": (_i, [_vp, _vp, _i, _vp, _i]),

@@ -31,6 +31,7 @@ class ORBextractor:
         self.capacity = lib().orbfe_max_keypoints(self._h)
         self.mvImagePyramid = _Pyramid(self)
         self._shape = None
+        self._rect = None       # (rows, cols) of the rectified image while rectification maps are set
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -90,7 +91,7 @@ class ORBextractor:
         mono = check(lib().orbfe_extract(self._h, ptr(image), image.shape[0], image.shape[1], image.strides[0],
                                          int(vLappingArea[0]), int(vLappingArea[1]), ptr(kps), ptr(desc), cap,
                                          C.byref(n)))
-        self._shape = image.shape
+        self._shape = self._rect or image.shape
         return mono, kps[:n.value].copy(), desc[:n.value].copy()
 
     def extract_batch(self, images, vLappingArea=(0, 0), out=None):
@@ -108,7 +109,7 @@ class ORBextractor:
             step, fstride = images.stride(1), images.stride(0)
         check(lib().orbfe_extract_batch(self._h, ptr(images), B, rows, cols, step, fstride, int(vLappingArea[0]),
                                         int(vLappingArea[1]), ptr(kps), ptr(desc), cap, ptr(n), ptr(mono)))
-        self._shape = (rows, cols)
+        self._shape = self._rect or (rows, cols)
         return n, mono, kps, desc
 
     def extract_batch_device(self, d_images, vLappingArea, d_kps, d_desc, d_n, d_mono, stream=None):
@@ -120,7 +121,7 @@ class ORBextractor:
         check(lib().orbfe_extract_batch_device(self._h, ptr(d_images), B, rows, cols, d_images.stride(1),
                                                d_images.stride(0), int(vLappingArea[0]), int(vLappingArea[1]),
                                                ptr(d_kps), ptr(d_desc), cap, ptr(d_n), ptr(d_mono), st))
-        self._shape = (rows, cols)
+        self._shape = self._rect or (rows, cols)
 
     # ---- mvImagePyramid and stage taps ----
     def level_size(self, level, shape=None):
@@ -180,6 +181,19 @@ class ORBextractor:
 
     def launch_count(self):
         return lib().orbfe_launch_count(self._h)
+
+    def set_rectification(self, map_x=None, map_y=None):
+        """Fuse cv::remap(frame, M1, M2, INTER_LINEAR) (System.cc:286-293) into pyramid level 0: later calls take the RAW
+        frames.  map_x / map_y: CV_32FC1 maps of the rectified size; None switches rectification off."""
+        if map_x is None:
+            check(lib().orbfe_extractor_set_rectification(self._h, None, None, 0, 0))
+            self._rect = None
+            return
+        mx = np.ascontiguousarray(map_x, np.float32)
+        my = np.ascontiguousarray(map_y, np.float32)
+        assert mx.shape == my.shape and mx.ndim == 2
+        check(lib().orbfe_extractor_set_rectification(self._h, ptr(mx), ptr(my), mx.shape[0], mx.shape[1]))
+        self._rect = tuple(mx.shape)
 
     def set_max_bytes(self, nbytes):
         check(lib().orbfe_set_max_bytes(self._h, int(nbytes)))

@@ -147,3 +147,30 @@ def test_device_resident_chain(orbfe):
     assert np.array_equal(d_rect[0].cpu().numpy(), orect)
     _, ok, od = O.Extractor(1000)(orect, (0, 0))
     assert n == len(ok) and n > 500 and kps.tobytes() == ok.tobytes() and np.array_equal(desc, od)
+
+
+def test_rectification_fused_into_the_extractor(orbfe):
+    """orbfe_extractor_set_rectification: raw frames in, pyramid level 0 = cv::remap(frame) + border, everything else as
+    ORBextractor on the rectified image (System::TrackStereo, System.cc:286-293); single frames, batches, raw size
+    different from the rectified size, and switching it off again."""
+    raw_h, raw_w, h, w = 520, 800, 480, 752
+    frames = np.stack([synth.synth_frame(raw_h, raw_w, 80 + i) for i in range(5)])
+    mx, my = _rectify_like_maps(h, w, raw_h, raw_w, 8)
+    ex = orbfe.ORBextractor(1000)
+    oex = O.Extractor(1000)
+    ex.set_rectification(mx, my)
+    rect0 = O.remap_linear(frames[0], mx, my)
+    mono, k, d = ex(frames[0], None, (0, 1000))
+    omono, ok, od = oex(rect0, (0, 1000))
+    assert mono == omono and k.tobytes() == ok.tobytes() and np.array_equal(d, od) and len(k) > 500
+    assert np.array_equal(ex.pyramid_level(0), rect0)                       # mvImagePyramid[0] is the rectified image
+    assert np.array_equal(ex.pyramid_level(1, with_border=True), oex.level(1)["padded"])
+    n, monos, kps, desc = ex.extract_batch(frames, (0, 1000))
+    for i in range(len(frames)):
+        omono, ok, od = oex(O.remap_linear(frames[i], mx, my), (0, 1000))
+        assert monos[i] == omono and n[i] == len(ok) and kps[i, :n[i]].tobytes() == ok.tobytes()
+        assert np.array_equal(desc[i, :n[i]], od)
+    ex.set_rectification(None)
+    mono, k, d = ex(frames[0], None, (0, 1000))
+    omono, ok, od = oex(frames[0], (0, 1000))
+    assert mono == omono and k.tobytes() == ok.tobytes() and np.array_equal(d, od)
