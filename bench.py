@@ -135,6 +135,11 @@ def emit_json(obj):
     _JSON_OUT.flush()
 
 
+def ctypes_stream(st):
+    import ctypes
+    return ctypes.c_void_p(st.cuda_stream)
+
+
 def call_latencies(orbfe, device):
     """Per-call milliseconds of the matcher entry points at SLAM-frame sizes (host arrays in and out,
     as the C++ adapter issues them): C2 stereo pair, C3-sized kNN, local-map projection search."""
@@ -174,6 +179,32 @@ def call_latencies(orbfe, device):
     voc = synth.make_vocabulary_fast(10, 6, 1)                    # the shape of ORBvoc.txt: 1.1 M nodes, 10^6 words
     gv = orbfe.ORBVocabulary(10, 6, voc["parent"], voc["desc"], voc["weight"], device=device)
     out["bow_transform_1200feat_k10_L6"] = timeit(lambda: gv.transform_features(dl, 4))
+    # batched, device-resident: the descriptors of 1000 frames (1 M) through the ORBvoc-sized tree in one launch
+    try:
+        import torch
+        from orbfe import _lib
+        dev = torch.device("cuda", device)
+        nbig = 1 << 20
+        d_desc = torch.randint(0, 256, (nbig, 32), dtype=torch.uint8, device=dev)
+        d_word = torch.empty(nbig, dtype=torch.int32, device=dev)
+        d_node = torch.empty(nbig, dtype=torch.int32, device=dev)
+        d_w = torch.empty(nbig, dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev)
+
+        def big():
+            _lib.check(_lib.lib().orbfe_bow_transform_device(gv.h, _lib.ptr(d_desc), nbig, 4, _lib.ptr(d_word), _lib.ptr(d_w),
+                                                             _lib.ptr(d_node), ctypes_stream(st)))
+        for _ in range(2):
+            big()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            big()
+        e1.record()
+        torch.cuda.synchronize()
+        out["bow_transform_1M_desc_device_ms"] = e0.elapsed_time(e1) / 5
+    except Exception as e:          # the batched figure is informative only
+        out["bow_transform_1M_desc_device_ms"] = "error: " + str(e)[:120]
     _, fvl = gv.transform(dl, 4)
     _, fvr = gv.transform(dr, 4)
     ones_l = np.ones(len(dl), np.uint8)
