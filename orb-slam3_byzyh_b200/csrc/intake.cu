@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "orbfe_internal.h"
+#include "remap_core.h"
 #include "scratch.h"
 
 namespace {
@@ -41,32 +42,13 @@ k_cvt_gray(const uint8_t* __restrict__ src, int rows, int cols, size_t sstep, in
     dst[(size_t)y * dstep + x] = (uint8_t)((b * 3735 + c1 * 19235 + r * 9798 + (1 << 14)) >> 15);
 }
 
-__device__ __forceinline__ int remap_fix(float v) {
-    // cvRound(v * INTER_TAB_SIZE): float product, round half to even, saturating like lrint on x86 is not needed
-    // for finite in-range maps; NaN / huge values land outside the source and read as border
-    const float s = v * 32.0f;
-    if (!(s > -1.0e9f)) return -(1 << 30);
-    if (!(s < 1.0e9f)) return 1 << 30;
-    return __float2int_rn(s);
-}
-
 __global__ void __launch_bounds__(256)
 k_remap_linear(const uint8_t* __restrict__ src, int srows, int scols, size_t sstep, const float* __restrict__ mapx,
                const float* __restrict__ mapy, size_t mstep, int drows, int dcols, uint8_t* __restrict__ dst, size_t dstep) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dcols || y >= drows) return;
-    const int sx = remap_fix(mapx[(size_t)y * mstep + x]), sy = remap_fix(mapy[(size_t)y * mstep + x]);
-    // the integer part is stored as short by OpenCV (saturate_cast<short>)
-    const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
-    const int fx = sx & 31, fy = sy & 31;
-    const bool x0 = ix >= 0 && ix < scols, x1 = ix + 1 >= 0 && ix + 1 < scols;
-    const bool y0 = iy >= 0 && iy < srows, y1 = iy + 1 >= 0 && iy + 1 < srows;
-    const uint8_t* r0 = src + (size_t)max(iy, 0) * sstep;
-    const uint8_t* r1 = src + (size_t)max(iy + 1, 0) * sstep;
-    const int p00 = (x0 && y0) ? r0[ix] : 0, p01 = (x1 && y0) ? r0[ix + 1] : 0;
-    const int p10 = (x0 && y1) ? r1[ix] : 0, p11 = (x1 && y1) ? r1[ix + 1] : 0;
-    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
-    dst[(size_t)y * dstep + x] = (uint8_t)((p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15);
+    dst[(size_t)y * dstep + x] =
+        (uint8_t)orbfe_remap_sample(src, sstep, srows, scols, mapx[(size_t)y * mstep + x], mapy[(size_t)y * mstep + x]);
 }
 
 struct ITap { int s0, s1; short a0, a1; };

@@ -12,6 +12,7 @@
 // into the ROI and evaluating the same bilinear tap there, so no second pass (and no
 // synchronisation) is needed and every store is a coalesced 32-bit word.
 #include "orbfe_internal.h"
+#include "remap_core.h"
 
 namespace {
 
@@ -50,13 +51,7 @@ k_level0(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8
 
 // Level 0 with the stereo rectification of System::TrackStereo fused in (src/System.cc:286-293): every padded pixel is
 // cv::remap(INTER_LINEAR, CV_32FC1 maps, constant 0 border) evaluated at the reflect-101 image of its coordinate, so the
-// rectified image never exists outside the pyramid.  Arithmetic as in intake.cu:k_remap_linear (bit-exact with cv2).
-__device__ __forceinline__ int rect_fix(float v) {
-    const float s = v * 32.0f;
-    if (!(s > -1.0e9f)) return -(1 << 30);
-    if (!(s < 1.0e9f)) return 1 << 30;
-    return __float2int_rn(s);
-}
+// rectified image never exists outside the pyramid.  Arithmetic: remap_core.h (bit-exact with cv2).
 __global__ void __launch_bounds__(256)
 k_level0_rect(const uint8_t* __restrict__ img, size_t step, size_t frameStride, int srows, int scols,
               const float* __restrict__ mapx, const float* __restrict__ mapy, uint8_t* __restrict__ pyr,
@@ -70,17 +65,7 @@ k_level0_rect(const uint8_t* __restrict__ img, size_t step, size_t frameStride, 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = reflect101_clamped(4 * wx - ORBFE_XOFF + i, w);
-        const int sx = rect_fix(mapx[(size_t)y * w + x]), sy = rect_fix(mapy[(size_t)y * w + x]);
-        const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
-        const int fx = sx & 31, fy = sy & 31;
-        const bool x0 = ix >= 0 && ix < scols, x1 = ix + 1 >= 0 && ix + 1 < scols;
-        const bool y0 = iy >= 0 && iy < srows, y1 = iy + 1 >= 0 && iy + 1 < srows;
-        const uint8_t* r0 = src + (size_t)max(iy, 0) * step;
-        const uint8_t* r1 = src + (size_t)max(iy + 1, 0) * step;
-        const int p00 = (x0 && y0) ? r0[ix] : 0, p01 = (x1 && y0) ? r0[ix + 1] : 0;
-        const int p10 = (x0 && y1) ? r1[ix] : 0, p11 = (x1 && y1) ? r1[ix + 1] : 0;
-        const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
-        out |= (uint32_t)((p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15) << (8 * i);
+        out |= orbfe_remap_sample(src, step, srows, scols, mapx[(size_t)y * w + x], mapy[(size_t)y * w + x]) << (8 * i);
     }
     *reinterpret_cast<uint32_t*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 4 * wx) = out;
 }
