@@ -11,6 +11,8 @@
 // padded destination row; border pixels are produced by reflecting the destination coordinate
 // into the ROI and evaluating the same bilinear tap there, so no second pass (and no
 // synchronisation) is needed and every store is a coalesced 32-bit word.
+#include <algorithm>
+
 #include "orbfe_internal.h"
 #include "remap_core.h"
 
@@ -22,31 +24,51 @@ __device__ __forceinline__ int reflect101_clamped(int p, int len) {
     return max(0, min(p, len - 1));
 }
 
-// Level 0 = copyMakeBorder(image, 19, REFLECT_101): a thread owns 16 bytes of one padded row; interior
-// groups are one aligned 16-byte load + store, border groups gather the reflected bytes.
+// Level 0 = copyMakeBorder(image, 19, REFLECT_101).  A thread owns 16 bytes of one padded row.  The 16-byte groups that
+// lie entirely inside the image are one aligned 16-byte load + store (k_level0: interior groups only, so no warp ever
+// takes the gather path); the two or three groups at either end of a row, which mix reflected border pixels, padding
+// and image pixels, are gathered byte by byte by a second, small launch (k_level0_border).  With both in one kernel
+// every warp contained a border group and paid the ~200-instruction gather (ncu: 0.46 M warp-instructions per frame
+// for a 0.36 MB copy).
+__device__ __forceinline__ uint4 level0_gather(const uint8_t* __restrict__ src, int x0, int w) {
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v[k] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            v[k] |= (uint32_t)__ldg(src + reflect101_clamped(x0 + 4 * k + i, w)) << (8 * i);
+    }
+    return make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// gFirst .. gLast: the groups with 0 <= x0 and x0 + 15 < w
 __global__ void __launch_bounds__(256)
 k_level0(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8_t* __restrict__ pyr,
-         unsigned long long pyrStride, int w, int h, int pitch) {
-    const int gx = blockIdx.x * 64 + (threadIdx.x & 63);          // 16-byte group inside the padded row
+         unsigned long long pyrStride, int w, int h, int pitch, int gFirst, int gLast) {
+    const int gx = gFirst + blockIdx.x * 64 + (threadIdx.x & 63);  // 16-byte group inside the padded row
     const int py = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (gx >= (pitch >> 4) || py >= h + 2 * ORBFE_YOFF) return;
+    if (gx > gLast || py >= h + 2 * ORBFE_YOFF) return;
     const uint8_t* src = img + (size_t)blockIdx.z * frameStride + (size_t)reflect101_clamped(py - ORBFE_YOFF, h) * step;
     const int x0 = 16 * gx - ORBFE_XOFF;
     uint4 out;
-    if (x0 >= 0 && x0 + 15 < w && ((reinterpret_cast<size_t>(src + x0) & 15) == 0)) {
-        out = __ldg(reinterpret_cast<const uint4*>(src + x0));
-    } else {
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            v[k] = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                v[k] |= (uint32_t)__ldg(src + reflect101_clamped(x0 + 4 * k + i, w)) << (8 * i);
-        }
-        out = make_uint4(v[0], v[1], v[2], v[3]);
-    }
+    if ((reinterpret_cast<size_t>(src + x0) & 15) == 0) out = __ldg(reinterpret_cast<const uint4*>(src + x0));
+    else out = level0_gather(src, x0, w);                          // caller's rows are not 16-byte aligned
     *reinterpret_cast<uint4*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 16 * gx) = out;
+}
+
+// The groups left of gFirst and right of gLast of every padded row: thread = (row, border group).
+__global__ void __launch_bounds__(256)
+k_level0_border(const uint8_t* __restrict__ img, size_t step, size_t frameStride, uint8_t* __restrict__ pyr,
+                unsigned long long pyrStride, int w, int h, int pitch, int gFirst, int gLast) {
+    const int groups = pitch >> 4, nb = gFirst + (groups - 1 - gLast);
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int py = t / nb, b = t - py * nb;
+    if (py >= h + 2 * ORBFE_YOFF) return;
+    const int gx = b < gFirst ? b : gLast + 1 + (b - gFirst);
+    const uint8_t* src = img + (size_t)blockIdx.z * frameStride + (size_t)reflect101_clamped(py - ORBFE_YOFF, h) * step;
+    *reinterpret_cast<uint4*>(pyr + (size_t)blockIdx.z * pyrStride + (size_t)py * pitch + 16 * gx) =
+        level0_gather(src, 16 * gx - ORBFE_XOFF, w);
 }
 
 // Level 0 with the stereo rectification of System::TrackStereo fused in (src/System.cc:286-293): every padded pixel is
@@ -261,9 +283,22 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
             k_level0_rect<<<g0, 256, 0, st>>>(d_images, step, frameStride, rect->srcRows, rect->srcCols, rect->mapx, rect->mapy,
                                               b.pyr + L.off, g.pyrStride, L.w, L.h, L.pitch);
         } else if (l == 0) {
-            dim3 g0(((L.pitch >> 4) + 63) / 64, (L.h + 2 * ORBFE_YOFF + 3) / 4, B);
-            k_level0<<<g0, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride,
-                                         L.w, L.h, L.pitch);
+            const int groups = L.pitch >> 4, H = L.h + 2 * ORBFE_YOFF;
+            const int gFirst = (ORBFE_XOFF + 15) / 16;                          // first group with x0 >= 0
+            const int gLast = std::min((L.w - 16 + ORBFE_XOFF) / 16, groups - 1); // last group with x0 + 15 < w
+            if (L.w >= 16 && gLast >= gFirst) {
+                dim3 g0((gLast - gFirst + 1 + 63) / 64, (H + 3) / 4, B);
+                k_level0<<<g0, 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off, g.pyrStride, L.w, L.h, L.pitch, gFirst, gLast);
+                const int nb = gFirst + (groups - 1 - gLast);
+                if (nb > 0) {
+                    k_level0_border<<<dim3((H * nb + 255) / 256, 1, B), 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off,
+                                                                                   g.pyrStride, L.w, L.h, L.pitch, gFirst, gLast);
+                    ++*launches;
+                }
+            } else {   // images narrower than one group: everything is border
+                k_level0_border<<<dim3((H * groups + 255) / 256, 1, B), 256, 0, st>>>(d_images, step, frameStride, b.pyr + L.off,
+                                                                                   g.pyrStride, L.w, L.h, L.pitch, 0, -1);
+            }
         } else {
             const OrbfeLevelGeom& S = g.lv[l - 1];
             const OrbfeTap* xt = taps + L.xtab;
