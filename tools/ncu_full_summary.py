@@ -52,7 +52,7 @@ if len(sys.argv) > 3:
     out = {}
     pyr = dict(dram_bytes_per_frame=0.0, alu_pipe_pct=0.0, warp_instr_per_frame=0.0)
     for k, v in traffic.items():
-        if k in ("k_level0", "k_resize_fast") or k.startswith("k_resize"):
+        if k.startswith("k_level0") or k.startswith("k_resize"):
             pyr["dram_bytes_per_frame"] += v["dram_bytes_per_frame"]
             pyr["warp_instr_per_frame"] += v["warp_instr_per_frame"]
             pyr["alu_pipe_pct"] = max(pyr["alu_pipe_pct"], v["alu_pipe_pct"])
