@@ -122,16 +122,16 @@ k_fast_score(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
             const int orow = 2 * rp + rr, y = 19 + TH * ty + orow;
             if (y >= L.h - 19) break;
             const uint2 c = cp[3][orow + 3][gq];
-            const uint32_t c0 = c.x + FC_BIAS2, c1 = c.y + FC_BIAS2;
-            uint32_t e0[16], e1[16];
+            // raw ring values: the network works on them directly, two pixels per register (fast_core.h)
+            uint32_t r0[16], r1[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const int o = 3 + FC_RING_DX(k);
                 const uint2 v = cp[o & 3][orow + 3 + FC_RING_DY(k)][gq + (o >> 2)];
-                e0[k] = c0 - v.x;   // both lanes stay in [1, 511]: no borrow crosses the lane boundary
-                e1[k] = c1 - v.y;
+                r0[k] = v.x;
+                r1[k] = v.y;
             }
-            const uint32_t m0 = fc_margin2(e0, sub2), m1 = fc_margin2(e1, sub2);
+            const uint32_t m0 = fc_margin2_pair_raw(r0, c.x, sub2), m1 = fc_margin2_pair_raw(r1, c.y, sub2);
             *reinterpret_cast<uint2*>(dst + (size_t)(ORBFE_YOFF + y) * L.pitch) = make_uint2(m0, m1);
         }
     }

@@ -14,9 +14,12 @@
 //   m3_k = min(e_k, e_k+1, e_k+2),  min9_k = min(m3_k, m3_k+3, m3_k+6)
 // an arc minimum costs two 3-input ops.  best = max(0, max_k min9_k - 256, 256 - min_k max9_k).
 //
-// fc_margin2_raw below runs the same network on the raw ring values (no differences, 10 % fewer instructions); on
-// B200 it measured 2.5 % slower inside k_fast_score than this form, so the kernel uses
-// fc_margin2; both are checked against the oracle by the host unit test.
+// Four equivalent formulations live here, all checked against the oracle by the host unit test
+// (tests/test_fast_core.py) and timed inside k_fast_score on B200 (ms per 1024 frames):
+//   fc_margin2          biased differences, 3-wise sliding windows: 80 packed min/max per pixel pair      3.86
+//   fc_margin2_raw      the same on the raw ring values (no differences)                                 +2.5 %
+//   fc_margin2_pair     arcs taken in pairs (k, k+1 share eight ring pixels): 72 per pixel pair           3.57
+//   fc_margin2_pair_raw pairs on the raw ring values -- THE ONE THE KERNEL USES                           3.41
 //
 // NOTE (measured on B200, nvcc 12.9): a formulation that folds `max(best, -mx)` into the running
 // maximum is MISCOMPILED for sm_100a (ptxas drops the negation when it fuses into VIMNMX3); this
@@ -102,7 +105,51 @@ static FC_HD uint32_t fc_margin2(const uint32_t* e, uint32_t sub2) {
     return fc_max3s_relu(a, b, 0u);
 }
 
-// The same margin from the RAW ring values (r[k] = two ring pixels as 16-bit lanes, c2 = the two centres), without
+// The same margin with the arcs taken in PAIRS.  Arcs k and k+1 (k even) share the 8 ring positions k+1..k+8, so
+//   max(min9_k, min9_k+1) = min( min(e_k+1..e_k+8), max(e_k, e_k+9) ).
+// With p_i = min(e_2i+1, e_2i+2) (8 two-input ops) the shared part is the window p_i..p_i+3 of a circular 8-array:
+//   q_i = min3(p_i, p_i+1, p_i+2),  t_i = min3(q_i, p_i+3, max(e_2i, e_2i+9)),  A = max_i t_i
+// i.e. 16 two-input + 16 three-input + 4 for the final maximum = 36 packed min/max per polarity instead of 40, and
+// 16 of them read two registers instead of three.
+static FC_HD void fc_pair_extrema(const uint32_t* e, uint32_t& A, uint32_t& B) {   // A = max_k min9_k, B = min_k max9_k
+    uint32_t pn[8], px[8], xn[8], xx[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t a = e[2 * i + 1], b = e[(2 * i + 2) & 15];
+        pn[i] = fc_minu(a, b);
+        px[i] = fc_maxu(a, b);
+        const uint32_t c = e[2 * i], d = e[(2 * i + 9) & 15];
+        xn[i] = fc_maxu(c, d);   // for the arc minima: the better of the two end pixels
+        xx[i] = fc_minu(c, d);   // for the arc maxima
+    }
+    uint32_t tn[8], tx[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t qn = FC_SLOT3(fc_min3u, pn, i, 8);
+        const uint32_t qx = FC_SLOT3(fc_max3u, px, i, 8);
+        tn[i] = fc_min3u(qn, pn[(i + 3) & 7], xn[i]);
+        tx[i] = fc_max3u(qx, px[(i + 3) & 7], xx[i]);
+    }
+    A = fc_maxu(fc_max3u(fc_max3u(tn[0], tn[1], tn[2]), fc_max3u(tn[3], tn[4], tn[5]), tn[6]), tn[7]);
+    B = fc_minu(fc_min3u(fc_min3u(tx[0], tx[1], tx[2]), fc_min3u(tx[3], tx[4], tx[5]), tx[6]), tx[7]);
+}
+static FC_HD uint32_t fc_margin2_pair(const uint32_t* e, uint32_t sub2) {
+    uint32_t A, B;
+    fc_pair_extrema(e, A, B);
+    const uint32_t a = fc_sub2(A, fc_add2(FC_BIAS2, sub2));
+    const uint32_t b = fc_sub2(fc_sub2(FC_BIAS2, sub2), B);
+    return fc_max3s_relu(a, b, 0u);
+}
+// ... and on the raw ring values (see fc_margin2_raw): best = max(0, c - min_k max9_k(ring), max_k min9_k(ring) - c)
+static FC_HD uint32_t fc_margin2_pair_raw(const uint32_t* r, uint32_t c2, uint32_t sub2) {
+    uint32_t hi, lo;
+    fc_pair_extrema(r, hi, lo);
+    const uint32_t a = fc_sub2(fc_sub2(c2, sub2), lo);
+    const uint32_t b = fc_sub2(hi, fc_add2(c2, sub2));
+    return fc_max3s_relu(a, b, 0u);
+}
+
+// The margin from the RAW ring values (r[k] = two ring pixels as 16-bit lanes, c2 = the two centres), without
 // forming the 16 differences:  min over an arc of (c - ring) = c - max over the arc of ring, and
 // min over an arc of (ring - c) = (min over the arc of ring) - c, so
 //   best = max(0, c - min_k max9_k(ring), max_k min9_k(ring) - c).

@@ -23,6 +23,24 @@ extern "C" void fast_core_margins(const uint8_t* img, int w, int h, int sub, uin
             out[y * w + x + 1] = (uint8_t)(m >> 16);
         }
 }
+// the pair-sharing formulation (arcs k, k+1 share 8 ring positions)
+extern "C" void fast_core_margins_pair(const uint8_t* img, int w, int h, int sub, uint8_t* out) {
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x + 1 < w - 3; x += 2) {
+            const uint8_t* p = img + y * w + x;
+            uint32_t e[16];
+            const uint32_t c = ((uint32_t)p[0] | ((uint32_t)p[1] << 16)) + FC_BIAS2;
+            for (int k = 0; k < 16; k++) {
+                const uint8_t* q = p + dx[k] + dy[k] * w;
+                e[k] = c - ((uint32_t)q[0] | ((uint32_t)q[1] << 16));
+            }
+            const uint32_t m = fc_margin2_pair(e, (uint32_t)sub * 0x00010001u);
+            out[y * w + x] = (uint8_t)(m & 0xFFFF);
+            out[y * w + x + 1] = (uint8_t)(m >> 16);
+        }
+}
 // the raw-value formulation the kernel uses (no per-ring differences)
 extern "C" void fast_core_margins_raw(const uint8_t* img, int w, int h, int sub, uint8_t* out) {
     const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
@@ -37,6 +55,23 @@ extern "C" void fast_core_margins_raw(const uint8_t* img, int w, int h, int sub,
                 r[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 16);
             }
             const uint32_t m = fc_margin2_raw(r, c, (uint32_t)sub * 0x00010001u);
+            out[y * w + x] = (uint8_t)(m & 0xFFFF);
+            out[y * w + x + 1] = (uint8_t)(m >> 16);
+        }
+}
+extern "C" void fast_core_margins_pair_raw(const uint8_t* img, int w, int h, int sub, uint8_t* out) {
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x + 1 < w - 3; x += 2) {
+            const uint8_t* p = img + y * w + x;
+            uint32_t r[16];
+            const uint32_t c = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+            for (int k = 0; k < 16; k++) {
+                const uint8_t* q = p + dx[k] + dy[k] * w;
+                r[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 16);
+            }
+            const uint32_t m = fc_margin2_pair_raw(r, c, (uint32_t)sub * 0x00010001u);
             out[y * w + x] = (uint8_t)(m & 0xFFFF);
             out[y * w + x + 1] = (uint8_t)(m >> 16);
         }

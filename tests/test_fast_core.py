@@ -47,3 +47,10 @@ def test_margin_map_equals_oracle(core, kind, sub):
     out2 = np.zeros((h, w), np.uint8)
     core.fast_core_margins_raw(img.ctypes.data_as(C.c_void_p), w, h, sub, out2.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out2[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
+    # the pair-sharing formulation (arcs k, k+1 share eight ring positions)
+    out3 = np.zeros((h, w), np.uint8)
+    core.fast_core_margins_pair(img.ctypes.data_as(C.c_void_p), w, h, sub, out3.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out3[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
+    out4 = np.zeros((h, w), np.uint8)
+    core.fast_core_margins_pair_raw(img.ctypes.data_as(C.c_void_p), w, h, sub, out4.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out4[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
