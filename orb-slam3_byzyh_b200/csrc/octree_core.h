@@ -33,6 +33,7 @@
 #define OC_NT ((int)blockDim.x)
 #define OC_SYNC() __syncthreads()
 #define OC_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define OC_ATOMIC_ADD_RET(p, v) atomicAdd((p), (v))
 #define OC_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define OC_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define OC_FMUL(a, b) __fmul_rn((a), (b))
@@ -42,12 +43,16 @@
 #define OC_NT 1
 #define OC_SYNC() ((void)0)
 #define OC_ATOMIC_ADD(p, v) (*(p) += (v))
+#define OC_ATOMIC_ADD_RET(p, v) ((*(p) += (v)) - (v))
 #define OC_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
 #define OC_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define OC_FMUL(a, b) ((a) * (b))
 #define OC_FDIV(a, b) ((a) / (b))
 #endif
 #define OC_PAR_FOR(i, n) for (int i = OC_TID; i < (n); i += OC_NT)
+#ifndef OC_MARK   // tools/octree_phase_probe.cu defines it to accumulate clock64() per stage; nothing in the product
+#define OC_MARK(slot) ((void)0)
+#endif
 
 // Packed FAST candidate: score[31:24] | y[23:12] | x[11:0] (window coordinates).
 #define OC_PK_X(p) ((int)((p) & 0xFFFu))
@@ -78,7 +83,7 @@ struct OcWork {
     int* sc;             // [16] shared scalars
     int* part;           // [3 * OC_MAX_NT] per-thread partial sums of the parallel list rebuild
 };
-enum { OC_SIZE = 0, OC_CUR = 1, OC_NV = 2, OC_STATE = 3, OC_NTOEXP = 4 };
+enum { OC_SIZE = 0, OC_CUR = 1, OC_NV = 2, OC_STATE = 3, OC_NTOEXP = 4, OC_P2_NDIV = 5, OC_P2_SIZE = 6, OC_P2_CHILDREN = 7, OC_SORT_CNT = 8 /* 8..10 */ };
 #define OC_MAX_NT 256   // largest CTA size oc_distribute may be called with
 enum { OC_ST_PHASE1 = 0, OC_ST_PHASE2 = 1, OC_ST_DONE = 2 };
 
@@ -158,7 +163,9 @@ static OC_HD void oc_swap(uint64_t* a, int i, int j) {
     a[i] = a[j];
     a[j] = t;
 }
-static OC_HD void oc_std_sort(uint64_t* a, int n) {
+// std::__introsort_loop: after it every element sits inside its final partition of at most 16 elements (or in a
+// heap-sorted range).  The pivot key is read once per partition (the partition never moves a[first]).
+static OC_HD void oc_introsort_loop(uint64_t* a, int n) {
     if (n <= 0) return;
     int lg = 0;
     while ((n >> (lg + 1)) != 0) lg++;
@@ -187,11 +194,12 @@ static OC_HD void oc_std_sort(uint64_t* a, int n) {
                 else if (OC_LESS(a[B], a[C])) oc_swap(a, first, C);
                 else oc_swap(a, first, B);
             }
+            const uint64_t pivot = a[first];
             int lo = first + 1, hi = last;
             while (true) {  // __unguarded_partition(first+1, last, pivot = first)
-                while (OC_LESS(a[lo], a[first])) ++lo;
+                while (OC_LESS(a[lo], pivot)) ++lo;
                 --hi;
-                while (OC_LESS(a[first], a[hi])) --hi;
+                while (OC_LESS(pivot, a[hi])) --hi;
                 if (!(lo < hi)) break;
                 oc_swap(a, lo, hi);
                 ++lo;
@@ -201,6 +209,10 @@ static OC_HD void oc_std_sort(uint64_t* a, int n) {
             last = cut;
         }
     }
+}
+static OC_HD void oc_std_sort(uint64_t* a, int n) {
+    if (n <= 0) return;
+    oc_introsort_loop(a, n);
     // __final_insertion_sort
     if (n > 16) {
         oc_insertion_sort(a, 0, 16);
@@ -208,6 +220,176 @@ static OC_HD void oc_std_sort(uint64_t* a, int n) {
     } else {
         oc_insertion_sort(a, 0, n);
     }
+}
+
+// Exclusive prefix sums (thread order) of three per-thread counters over the CTA; every thread gets the totals.
+// Device: warp shuffles + one shared word per warp and counter (w.part), two barriers.  Host build: one "thread".
+static OC_HD void oc_cta_exscan3(int* part, int& a, int& b, int& c, int& ta, int& tb, int& tc) {
+#if defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (int)((blockDim.x + 31) >> 5);
+    int ia = a, ib = b, ic = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int xa = __shfl_up_sync(0xffffffffu, ia, o), xb = __shfl_up_sync(0xffffffffu, ib, o),
+                  xc = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) { ia += xa; ib += xb; ic += xc; }
+    }
+    if (lane == 31) { part[wid] = ia; part[32 + wid] = ib; part[64 + wid] = ic; }
+    __syncthreads();
+    int pa = 0, pb = 0, pc = 0;
+    ta = tb = tc = 0;
+    for (int k = 0; k < nw; k++) {
+        const int xa = part[k], xb = part[32 + k], xc = part[64 + k];
+        if (k < wid) { pa += xa; pb += xb; pc += xc; }
+        ta += xa; tb += xb; tc += xc;
+    }
+    a = pa + ia - a; b = pb + ib - b; c = pc + ic - c;
+    __syncthreads();   // part is free again
+#else
+    (void)part;
+    ta = a; tb = b; tc = c;
+    a = b = c = 0;
+#endif
+}
+
+// ---- std::__introsort_loop by the whole CTA ------------------------------------------------
+// The partitions of one recursion level are disjoint ranges, so they are independent: one GROUP (a warp; the single
+// host "thread") takes one range, and the levels are separated by a CTA barrier.  Inside a range the Hoare partition
+// of __unguarded_partition is order-free too: its k-th swap exchanges the k-th element from the left that is not
+// below the pivot (L[k]) with the k-th element from the right that is not above it (R[k]), for as long as
+// L[k] < R[k] -- earlier swaps only touch positions outside (L[k], R[k]).  So a group ranks both sets with ballots,
+// counts the swaps K (the condition holds on a prefix: L ascends, R descends), swaps the K pairs at once and takes
+// cut = min(L[K], R[K-1]): the first position after the last swap whose CURRENT value is not below the pivot.
+#if defined(__CUDA_ARCH__)
+#define OC_LANE ((int)(threadIdx.x & 31))
+#define OC_GS 32
+#define OC_GID ((int)(threadIdx.x >> 5))
+#define OC_NG ((int)(blockDim.x >> 5))
+#define OC_GSYNC() __syncwarp()
+#else
+#define OC_LANE 0
+#define OC_GS 1
+#define OC_GID 0
+#define OC_NG 1
+#define OC_GSYNC() ((void)0)
+#endif
+static OC_HD void oc_group_rank(bool f, int& rank, int& total) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    rank = __popc(m & ((1u << (threadIdx.x & 31)) - 1u));
+    total = __popc(m);
+#else
+    rank = 0;
+    total = f ? 1 : 0;
+#endif
+}
+// __unguarded_partition_pivot(first, last) by one group; Lp / Rp: int scratch indexed like a.  Returns the cut.
+static OC_HD int oc_partition_group(uint64_t* a, int* Lp, int* Rp, int first, int last) {
+    const int lane = OC_LANE;
+    if (lane == 0) {   // __move_median_to_first(first, first+1, mid, last-1)
+        const int A = first + 1, B = first + (last - first) / 2, C = last - 1;
+        if (OC_LESS(a[A], a[B])) {
+            if (OC_LESS(a[B], a[C])) oc_swap(a, first, B);
+            else if (OC_LESS(a[A], a[C])) oc_swap(a, first, C);
+            else oc_swap(a, first, A);
+        } else if (OC_LESS(a[A], a[C])) oc_swap(a, first, A);
+        else if (OC_LESS(a[B], a[C])) oc_swap(a, first, C);
+        else oc_swap(a, first, B);
+    }
+    OC_GSYNC();
+    const uint32_t pivot = (uint32_t)(a[first] >> 32);
+    const int s = first + 1, len = last - s;
+    int nL = 0, nR = 0;
+    for (int c = 0; c < len; c += OC_GS) {
+        const int i = c + lane;
+        const int pl = s + i, pr = last - 1 - i;
+        bool ge = false, le = false;
+        if (i < len) {
+            ge = (uint32_t)(a[pl] >> 32) >= pivot;
+            le = (uint32_t)(a[pr] >> 32) <= pivot;
+        }
+        int r, t;
+        oc_group_rank(ge, r, t);
+        if (ge) Lp[s + nL + r] = pl;
+        nL += t;
+        oc_group_rank(le, r, t);
+        if (le) Rp[s + nR + r] = pr;
+        nR += t;
+    }
+    OC_GSYNC();
+    const int m = nL < nR ? nL : nR;
+    int K = 0;
+    for (int c = 0; c < m; c += OC_GS) {
+        const int k = c + lane;
+        int r, t;
+        oc_group_rank(k < m && Lp[s + k] < Rp[s + k], r, t);
+        K += t;
+    }
+    int cut = last;   // the median guarantees an element >= pivot inside the range
+    if (K < nL) cut = Lp[s + K];
+    if (K > 0 && Rp[s + K - 1] < cut) cut = Rp[s + K - 1];
+    for (int k = lane; k < K; k += OC_GS) oc_swap(a, Lp[s + k], Rp[s + k]);
+    OC_GSYNC();
+    return cut;
+}
+
+// std::sort(a, a+n) by the whole CTA, same permutation as libstdc++: the introsort loop runs level by level (above),
+// and __final_insertion_sort is a plain insertion sort over the whole range, i.e. the STABLE sort of what the loop left
+// behind -- every thread ranks one element (keys below it + equal keys before it).  The sorted sequence is returned in
+// `out` (a is left partitioned, not sorted; `out` doubles as the partition scratch).  q: 4 * (n/16 + 2) ints of
+// scratch for the two range queues, cnt: 3 shared counters.  All threads must call; ends with a barrier.
+static OC_HD void oc_std_sort_cta(uint64_t* a, uint64_t* out, int n, int* q, int* cnt) {
+    if (n > 16) {
+        const int qcap = n / 16 + 2;
+        int* Lp = (int*)out;
+        int* Rp = Lp + n;
+        if (OC_TID == 0) {
+            int lg = 0;
+            while ((n >> (lg + 1)) != 0) lg++;
+            q[0] = 0; q[1] = n | ((2 * lg) << 24);
+            cnt[0] = 1; cnt[1] = 0; cnt[2] = 0;
+        }
+        OC_SYNC();
+        for (int level = 0;; level++) {
+            const int rd = level % 3, wr = (level + 1) % 3, zr = (level + 2) % 3;
+            const int ns = cnt[rd];
+            if (ns == 0) break;
+            if (OC_TID == 0) cnt[zr] = 0;
+            const int* qr = q + (level & 1) * 2 * qcap;
+            int* qw = q + ((level + 1) & 1) * 2 * qcap;
+            for (int sg = OC_GID; sg < ns; sg += OC_NG) {
+                const int first = qr[2 * sg], last = qr[2 * sg + 1] & 0xFFFFFF, depth = qr[2 * sg + 1] >> 24;
+                if (depth == 0) {   // __partial_sort(first, last, last)
+                    if (OC_LANE == 0) oc_heap_sort(a + first, last - first);
+                    continue;
+                }
+                const int cut = oc_partition_group(a, Lp, Rp, first, last);
+                if (OC_LANE == 0) {
+                    if (last - cut > 16) {
+                        const int e = OC_ATOMIC_ADD_RET(&cnt[wr], 1);
+                        qw[2 * e] = cut; qw[2 * e + 1] = last | ((depth - 1) << 24);
+                    }
+                    if (cut - first > 16) {
+                        const int e = OC_ATOMIC_ADD_RET(&cnt[wr], 1);
+                        qw[2 * e] = first; qw[2 * e + 1] = cut | ((depth - 1) << 24);
+                    }
+                }
+            }
+            OC_SYNC();
+        }
+    }
+    OC_SYNC();
+    OC_PAR_FOR(i, n) {
+        const uint64_t v = a[i];
+        const uint32_t key = (uint32_t)(v >> 32);
+        int r = 0;
+        for (int j = 0; j < n; j++) {
+            const uint32_t kj = (uint32_t)(a[j] >> 32);
+            r += (kj < key || (kj == key && j < i)) ? 1 : 0;
+        }
+        out[r] = v;
+    }
+    OC_SYNC();
 }
 
 // ---- DivideNode geometry (:608-637) -------------------------------------------------------
@@ -314,14 +496,8 @@ static OC_HD void oc_rebuild_phase1(const OcWork& w, int N) {
             sne++;
         }
     }
-    w.part[tid] = sk; w.part[nt + tid] = sne; w.part[2 * nt + tid] = sm;
-    OC_SYNC();
-    int preK = 0, preNE = 0, preM = 0, totK = 0, totNE = 0, totM = 0;
-    for (int t = 0; t < nt; t++) {
-        const int a = w.part[t], b = w.part[nt + t], c = w.part[2 * nt + t];
-        if (t < tid) { preK += a; preNE += b; preM += c; }
-        totK += a; totNE += b; totM += c;
-    }
+    int preK = sk, preNE = sne, preM = sm, totK, totNE, totM;
+    oc_cta_exscan3(w.part, preK, preNE, preM, totK, totNE, totM);
     for (int j = j0; j < j1; j++) {
         if (nd.cnt[so + j] > 1) {
             int k = 0;
@@ -357,6 +533,92 @@ static OC_HD void oc_rebuild_phase1(const OcWork& w, int N) {
         w.sc[OC_NV] = totM;
         w.sc[OC_SIZE] = newSize;
         w.sc[OC_CUR] = cur ^ 1;
+    }
+}
+
+// One phase-2 step (:934-1015): the expandable nodes are sorted by (population, x) and divided one at a time, largest
+// first, until the list holds N nodes.  Whole CTA: the sort's final pass, the child tables of the divided nodes and the
+// copies of the undivided ones are done by all threads; only the introsort partitioning and the short scan that finds
+// how many nodes get divided run on one thread.
+static OC_HD void oc_phase2(const OcWork& w, int N) {
+    const OcNodes& nd = w.nd;
+    const int cur = w.sc[OC_CUR];
+    const int so = cur * w.M, dof = (cur ^ 1) * w.M;
+    const int size = w.sc[OC_SIZE];
+    const int np = w.sc[OC_NV];
+    oc_std_sort_cta(w.vs, w.vs2, np, w.cpos, w.sc + OC_SORT_CNT);   // sorted sequence in vs2; vs and cpos are scratch
+    OC_MARK(6);   // phase-2: sort
+    int* ne = (int*)w.vs;               // [np] non-empty children of the t-th division (t = 0: largest key)
+    int* off = ne + w.M;                // [np] first list position of its children
+    OC_PAR_FOR(j, size) w.remap[j] = 0;
+    OC_PAR_FOR(t, np) {
+        const int j = (int)(w.vs2[np - 1 - t] & 0xFFFFFFFFu);
+        int c = 0;
+        for (int q = 0; q < 4; q++) c += (w.cc[4 * j + q] > 0);
+        ne[t] = c;
+    }
+    OC_SYNC();
+    if (OC_TID == 0) {
+        int newSize = size, ndiv = 0;
+        for (int t = 0; t < np; t++) {
+            newSize += ne[t] - 1;
+            ndiv++;
+            if (newSize >= N) break;
+        }
+        // the last node divided owns the front of the list
+        int pos = 0;
+        for (int t = ndiv - 1; t >= 0; t--) { off[t] = pos; pos += ne[t]; }
+        w.sc[OC_P2_NDIV] = ndiv;
+        w.sc[OC_P2_SIZE] = newSize;
+        w.sc[OC_P2_CHILDREN] = pos;
+    }
+    OC_SYNC();
+    const int ndiv = w.sc[OC_P2_NDIV], newSize = w.sc[OC_P2_SIZE], nChildren = w.sc[OC_P2_CHILDREN];
+    OC_PAR_FOR(t, ndiv) {
+        const int j = (int)(w.vs2[np - 1 - t] & 0xFFFFFFFFu);
+        w.remap[j] = -1;
+        int pos = off[t];
+        for (int q = 3; q >= 0; q--) {
+            const int c = w.cc[4 * j + q];
+            if (c > 0) { oc_make_child(nd, so + j, q, dof + pos, c); w.cpos[4 * j + q] = pos++; }
+            else w.cpos[4 * j + q] = -1;
+        }
+    }
+    OC_SYNC();
+    OC_MARK(7);   // phase-2: divisions
+    {   // undivided nodes keep their order behind the children
+        const int nt = OC_NT, tid = OC_TID;
+        const int chunk = (size + nt - 1) / nt;
+        const int j0 = tid * chunk < size ? tid * chunk : size, j1 = j0 + chunk < size ? j0 + chunk : size;
+        int pre = 0, d1 = 0, d2 = 0, t0, t1, t2;
+        for (int j = j0; j < j1; j++) pre += (w.remap[j] != -1);
+        oc_cta_exscan3(w.part, pre, d1, d2, t0, t1, t2);
+        int pos = nChildren + pre;
+        for (int j = j0; j < j1; j++)
+            if (w.remap[j] != -1) { oc_copy_node(nd, so + j, dof + pos); w.remap[j] = pos++; }
+    }
+    const bool done = newSize >= N || newSize == size;
+    if (OC_TID == 0) {
+        int nv = 0;
+        if (!done) {
+            // creation-order list of the next step (rare: one step almost always reaches N); ne/off are dead
+            for (int t = 0; t < ndiv; t++) {
+                const int j = (int)(w.vs2[np - 1 - t] & 0xFFFFFFFFu);
+                for (int q = 0; q < 4; q++) {
+                    const int c = w.cc[4 * j + q];
+                    if (c > 1) {
+                        const int cp = w.cpos[4 * j + q];
+                        w.vs[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)nd.x0[dof + cp]) << 32) | (uint32_t)cp;
+                    }
+                }
+            }
+        } else {
+            w.sc[OC_STATE] = OC_ST_DONE;
+        }
+        w.sc[OC_NV] = nv;
+        w.sc[OC_SIZE] = newSize;
+        w.sc[OC_CUR] = cur ^ 1;
+        OC_MARK(3);   // phase-2: copies + new list
     }
 }
 
@@ -400,6 +662,7 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
     }
     OC_SYNC();
     oc_relabel(w);
+    OC_MARK(0);   // roots
 
     // ---- main loop (:805-1020) ----
     while (true) {
@@ -407,60 +670,16 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
         const int state = w.sc[OC_STATE];
         if (state == OC_ST_DONE) break;
         oc_count_children(w);
+        OC_MARK(1);   // child populations
         if (state == OC_ST_PHASE1) {
             oc_rebuild_phase1(w, N);
-        } else if (OC_TID == 0) {
-            const int cur = w.sc[OC_CUR];
-            const OcNodes& nd = w.nd;
-            const int so = cur * w.M, dof = (cur ^ 1) * w.M;
-            const int size = w.sc[OC_SIZE];
-            int pos = 0, nv = 0, newSize = size;
-            {
-                // phase 2 (:934-1015): largest nodes first, one at a time, stop at N
-                const int np = w.sc[OC_NV];
-                oc_std_sort(w.vs, np);
-                int ndiv = 0;
-                for (int k = np - 1; k >= 0; k--) {
-                    const int j = (int)(w.vs[k] & 0xFFFFFFFFu);
-                    int ne = 0;
-                    for (int q = 0; q < 4; q++) ne += (w.cc[4 * j + q] > 0);
-                    newSize += ne - 1;
-                    ndiv++;
-                    if (newSize >= N) break;
-                }
-                // vs[np-1 .. np-ndiv] were divided, in that order; the last one divided owns
-                // the front of the list.
-                for (int j = 0; j < size; j++) w.remap[j] = 0;
-                for (int t = ndiv - 1; t >= 0; t--) {
-                    const int j = (int)(w.vs[np - 1 - t] & 0xFFFFFFFFu);
-                    w.remap[j] = -1;
-                    for (int q = 3; q >= 0; q--) {
-                        const int c = w.cc[4 * j + q];
-                        if (c > 0) { oc_make_child(nd, so + j, q, dof + pos, c); w.cpos[4 * j + q] = pos++; }
-                        else w.cpos[4 * j + q] = -1;
-                    }
-                }
-                for (int j = 0; j < size; j++)
-                    if (w.remap[j] != -1) { oc_copy_node(nd, so + j, dof + pos); w.remap[j] = pos++; }
-                for (int t = 0; t < ndiv; t++) {
-                    const int j = (int)(w.vs[np - 1 - t] & 0xFFFFFFFFu);
-                    for (int q = 0; q < 4; q++) {
-                        const int c = w.cc[4 * j + q];
-                        if (c > 1) {
-                            const int cp = w.cpos[4 * j + q];
-                            w.vs2[nv++] = ((uint64_t)(((uint32_t)c << 13) | (uint32_t)nd.x0[dof + cp]) << 32) | (uint32_t)cp;
-                        }
-                    }
-                }
-                for (int k = 0; k < nv; k++) w.vs[k] = w.vs2[k];
-                if (newSize >= N || newSize == size) w.sc[OC_STATE] = OC_ST_DONE;
-            }
-            w.sc[OC_NV] = nv;
-            w.sc[OC_SIZE] = newSize;
-            w.sc[OC_CUR] = cur ^ 1;
+            OC_MARK(2);   // phase-1 rebuild (thread 0's share)
+        } else {
+            oc_phase2(w, N);
         }
         OC_SYNC();
         oc_relabel(w);
+        OC_MARK(4);   // relabel
     }
 
     // ---- best response per node, first candidate wins ties (:1028-1053) ----
@@ -497,6 +716,7 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
     }
     if (OC_TID == 0) *out_n = size;
     OC_SYNC();
+    OC_MARK(5);   // winners
 }
 
 // Carve the node tables out of one contiguous (shared-memory) block of oc_shared_bytes(M).

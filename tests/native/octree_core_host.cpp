@@ -36,3 +36,10 @@ static bool key_less(const uint64_t& a, const uint64_t& b) { return (a >> 32) < 
 extern "C" void octree_core_sort_ref(uint64_t* a, int n) { std::sort(a, a + n, key_less); }
 extern "C" void octree_core_heapsort(uint64_t* a, int n) { oc_heap_sort(a, n); }
 extern "C" void octree_core_heapsort_ref(uint64_t* a, int n) { std::partial_sort(a, a + n, a + n, key_less); }
+
+// The CTA form of the same sort (level-parallel introsort loop + rank pass), here with one "thread".
+extern "C" void octree_core_sort_cta(uint64_t* a, uint64_t* out, int n) {
+    std::vector<int> q(4 * (n / 16 + 2));
+    int cnt[3];
+    oc_std_sort_cta(a, out, n, q.data(), cnt);
+}

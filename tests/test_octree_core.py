@@ -43,6 +43,10 @@ def test_std_sort_emulation(core, n):
         core.octree_core_sort(a.ctypes.data_as(C.c_void_p), n)
         core.octree_core_sort_ref(b.ctypes.data_as(C.c_void_p), n)
         assert np.array_equal(a, b)
+        e = (keys << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        out = np.zeros(max(n, 1), np.uint64)
+        core.octree_core_sort_cta(e.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n)
+        assert np.array_equal(out[:n], b)
         c, d = b[::-1].copy(), b[::-1].copy()
         core.octree_core_heapsort(c.ctypes.data_as(C.c_void_p), n)
         core.octree_core_heapsort_ref(d.ctypes.data_as(C.c_void_p), n)
@@ -65,6 +69,10 @@ def test_std_sort_depth_limit_path(core):
     core.octree_core_sort(a.ctypes.data_as(C.c_void_p), n)
     core.octree_core_sort_ref(b.ctypes.data_as(C.c_void_p), n)
     assert np.array_equal(a, b)
+    e = (keys << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    out = np.zeros(n, np.uint64)
+    core.octree_core_sort_cta(e.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n)
+    assert np.array_equal(out, b)
 
 
 @pytest.mark.parametrize("seed", range(40))
