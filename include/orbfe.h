@@ -73,6 +73,22 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
                         OrbfeKeyPoint* keypoints, uint8_t* descriptors, int capacity,
                         int* n_out, int* mono_out);
 
+/* Streaming form of orbfe_extract_batch for a caller that produces batch after batch (a dataset
+ * replay, a multi-camera rig): _submit enqueues the whole batch (H2D, kernels, D2H) and returns at
+ * once; _wait blocks until the OLDEST submitted batch has its results in host memory (FIFO) and
+ * returns its status (ORBFE_ERR_CAPACITY as for the synchronous call).  With a second batch
+ * submitted before the first is waited for, its host->device copies run under the kernels of the
+ * first, so the pipeline fill of the synchronous call is paid once instead of once per batch.
+ * Host buffers (pinned, for the copies to be asynchronous) must stay valid and untouched until
+ * the matching _wait; at most 4 batches in flight (ORBFE_ERR_INVALID beyond that).  The
+ * reference has no counterpart: Frame::ExtractORB (src/Frame.cc:513-523) is one blocking call per
+ * frame; orbfe_extract_batch(...) == _submit(...) followed by _wait() until nothing is in flight. */
+int orbfe_extract_batch_submit(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols,
+                               size_t step, size_t frame_stride, int lap0, int lap1,
+                               OrbfeKeyPoint* keypoints, uint8_t* descriptors, int capacity,
+                               int* n_out, int* mono_out);
+int orbfe_extract_batch_wait(OrbfeExtractor* h);
+
 /* Same, with inputs and outputs already resident in device memory (device pointers) and the
  * work enqueued on `stream` (a cudaStream_t; NULL = the extractor's own stream).  Does not
  * synchronise: results are valid after the stream is synchronised. */

@@ -97,6 +97,15 @@ void build_taps(int ssize, int dsize, bool isX, OrbfeTap* out) {
     }
 }
 
+// Every stream of the handle idle: before anything the batches in flight may still touch is freed or re-laid out.
+int quiesce(OrbfeExtractor* e) {
+    if (e->sH2D) CK(cudaStreamSynchronize(e->sH2D));
+    CK(cudaStreamSynchronize(e->sCompute));
+    if (e->sCompute2) CK(cudaStreamSynchronize(e->sCompute2));
+    if (e->sD2H) CK(cudaStreamSynchronize(e->sD2H));
+    return ORBFE_OK;
+}
+
 int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     if (e->haveGeom && e->g.rows == rows && e->g.cols == cols) return ORBFE_OK;
     if (rows > 4096 || cols > 4096) return fail(ORBFE_ERR_INVALID, "image larger than 4096 px");
@@ -207,8 +216,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     if (orbfe_octree_prepare(g) < 0) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(octree)", cudaGetLastError());
 
     // new geometry invalidates the chunk buffers
-    CK(cudaStreamSynchronize(e->sCompute));
-    if (e->sCompute2) CK(cudaStreamSynchronize(e->sCompute2));
+    if (int qrc = quiesce(e)) return qrc;
     if (e->d_taps) { cudaFree(e->d_taps); e->d_taps = nullptr; }
     if (!taps.empty()) {
         CK(cudaMalloc(&e->d_taps, taps.size() * sizeof(OrbfeTap)));
@@ -229,8 +237,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
 
 int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*& slab, int& cap) {
     if (frames <= cap) return ORBFE_OK;
-    CK(cudaStreamSynchronize(e->sCompute));
-    if (e->sCompute2) CK(cudaStreamSynchronize(e->sCompute2));
+    if (int qrc = quiesce(e)) return qrc;
     if (slab) { cudaFree(slab); slab = nullptr; cap = 0; }
     const OrbfeFrameGeom& g = e->g;
     const size_t B = (size_t)frames;
@@ -316,7 +323,7 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
 int ensure_staging(OrbfeExtractor* e, int frames, int rows, int cols, int capacity) {
     const size_t need = (size_t)frames * rows * cols;
     if (need > e->inBytes) {
-        CK(cudaStreamSynchronize(e->sCompute));
+        if (int qrc = quiesce(e)) return qrc;
         for (int s = 0; s < 2; s++) {
             if (e->d_in[s]) cudaFree(e->d_in[s]);
             e->d_in[s] = nullptr;
@@ -326,7 +333,7 @@ int ensure_staging(OrbfeExtractor* e, int frames, int rows, int cols, int capaci
     }
     const size_t elems = (size_t)frames * capacity;
     if (elems > e->outElems || frames > e->outFrames) {
-        CK(cudaStreamSynchronize(e->sCompute));
+        if (int qrc = quiesce(e)) return qrc;
         for (int s = 0; s < 2; s++) {
             if (e->d_okps[s]) cudaFree(e->d_okps[s]);
             if (e->d_odesc[s]) cudaFree(e->d_odesc[s]);
@@ -422,6 +429,9 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
         if (e->evDone[s]) cudaEventDestroy(e->evDone[s]);
         if (e->evOutFree[s]) cudaEventDestroy(e->evOutFree[s]);
     }
+    for (int s = 0; s < OrbfeExtractor::kMaxPending; s++) {
+        if (e->evPending[s]) cudaEventDestroy(e->evPending[s]);
+    }
     for (int k = 0; k < OrbfeExtractor::kProfSets; k++)
         for (int i = 0; i <= ORBFE_NUM_STAGES; i++)
             if (e->evStage[k][i]) cudaEventDestroy(e->evStage[k][i]);
@@ -501,6 +511,7 @@ int orbfe_extract_batch_device(OrbfeExtractor* h, const uint8_t* d_images, int B
     if (!d_images || rows <= 0 || cols <= 0) return fail(ORBFE_EMPTY_IMAGE, "empty image");
     if (B <= 0 || capacity <= 0 || step < (size_t)cols || !d_keypoints || !d_descriptors || !d_n_out || !d_mono_out)
         return fail(ORBFE_ERR_INVALID, "bad batch arguments");
+    if (h->pendCount > 0) return fail(ORBFE_ERR_INVALID, "host batches in flight (orbfe_extract_batch_wait first)");
     h->srcRows = rows; h->srcCols = cols;
     if ((rc = build_geometry(h, h->d_mapx ? h->rectRows : rows, h->d_mapx ? h->rectCols : cols))) return rc;
     const int chunk = chunk_frames(h, B);
@@ -516,35 +527,42 @@ int orbfe_extract_batch_device(OrbfeExtractor* h, const uint8_t* d_images, int B
     return ORBFE_OK;
 }
 
-int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
-                        size_t frame_stride, int lap0, int lap1, OrbfeKeyPoint* keypoints,
-                        uint8_t* descriptors, int capacity, int* n_out, int* mono_out) {
+// Enqueue one host batch: chunked H2D / kernels / D2H over the double-buffered staging slots, completion event on
+// sD2H.  Does not wait.  `h->pendCount > 0` on entry means the pipeline is already full (an earlier submit is still
+// running): the slots keep alternating from where that batch left them and the fill ramp is skipped.
+static int submit_host_batch(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
+                             size_t frame_stride, int lap0, int lap1, OrbfeKeyPoint* keypoints,
+                             uint8_t* descriptors, int capacity, int* n_out, int* mono_out) {
     int rc = check_handle(h);
     if (rc) return rc;
     if (!images || rows <= 0 || cols <= 0) return fail(ORBFE_EMPTY_IMAGE, "empty image");
     if (B <= 0 || capacity <= 0 || step < (size_t)cols || !keypoints || !descriptors || !n_out || !mono_out)
         return fail(ORBFE_ERR_INVALID, "bad batch arguments");
+    if (h->pendCount >= OrbfeExtractor::kMaxPending) return fail(ORBFE_ERR_INVALID, "too many host batches in flight");
     h->srcRows = rows; h->srcCols = cols;
     if ((rc = build_geometry(h, h->d_mapx ? h->rectRows : rows, h->d_mapx ? h->rectCols : cols))) return rc;
     const int chunk = chunk_frames(h, B);
     if ((rc = ensure_chunk(h, chunk))) return rc;
     // more than one chunk: odd chunks run on a second stream with their own intermediates (not while profiling:
     // the stage events belong to one stream)
-    const bool dual = B > chunk && !h->profiling;
+    const bool streaming = h->pendCount > 0;
+    const bool dual = (B > chunk || streaming) && !h->profiling;
     if (dual && (rc = ensure_chunk2(h, chunk))) return rc;
     if ((rc = ensure_staging(h, chunk, rows, cols, capacity))) return rc;
+    if (!streaming) h->chunkSeq = 0;   // idle pipeline: every event of earlier calls has completed
     const size_t fbytes = (size_t)rows * cols;
     const bool packed = step == (size_t)cols && frame_stride == fbytes;
     int ci = 0, nb = 0;
-    for (int b0 = 0; b0 < B; b0 += nb, ci++) {
+    for (int b0 = 0; b0 < B; b0 += nb, ci++, h->chunkSeq++) {
         // Pipeline fill: the H2D of the first chunk overlaps nothing, and the kernels of chunk k cannot start before
         // the H2D of chunk k has landed, so chunk k+1 must not take longer to copy (~7 us per frame over PCIe) than
         // chunk k takes to compute (~12 us per frame): chunk/4, chunk/2, then full chunks.
-        nb = (ci < 2 && B > chunk) ? std::max(chunk >> (2 - ci), 1) : chunk;
+        nb = (ci < 2 && B > chunk && !streaming) ? std::max(chunk >> (2 - ci), 1) : chunk;
         nb = std::min(nb, B - b0);
-        const int s = ci & 1;
+        const int s = (int)(h->chunkSeq & 1);
+        const bool reuse = h->chunkSeq >= 2;   // the slot has been used since the pipeline was last idle
         // H2D of this chunk overlaps the kernels of the previous one
-        if (ci >= 2) CK(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
+        if (reuse) CK(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
         const uint8_t* src = images + (size_t)b0 * frame_stride;
         if (packed) {
             CK(cudaMemcpyAsync(h->d_in[s], src, fbytes * nb, cudaMemcpyHostToDevice, h->sH2D));
@@ -556,8 +574,8 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         CK(cudaEventRecord(h->evIn[s], h->sH2D));
         cudaStream_t sc = (dual && s) ? h->sCompute2 : h->sCompute;
         CK(cudaStreamWaitEvent(sc, h->evIn[s], 0));
-        if (ci >= 2) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
-        if (B <= kGraphMaxFrames && B <= chunk && !h->profiling) {
+        if (reuse) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
+        if (B <= kGraphMaxFrames && B <= chunk && !h->profiling && !streaming) {
             // per-frame call: one graph launch instead of 15 kernel launches
             OrbfeExtractor::GraphKey key;
             key.rows = rows; key.cols = cols; key.B = nb; key.lap0 = lap0; key.lap1 = lap1; key.capacity = capacity;
@@ -595,13 +613,57 @@ int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int row
         CK(cudaMemcpyAsync(mono_out + b0, h->d_omono[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
         CK(cudaEventRecord(h->evOutFree[s], h->sD2H));
     }
-    CK(cudaStreamSynchronize(h->sD2H));
-    CK(cudaStreamSynchronize(h->sCompute));
-    if (dual) CK(cudaStreamSynchronize(h->sCompute2));
+    const int slot = (h->pendHead + h->pendCount) % OrbfeExtractor::kMaxPending;
+    if (!h->evPending[slot]) CK(cudaEventCreateWithFlags(&h->evPending[slot], cudaEventDisableTiming));
+    CK(cudaEventRecord(h->evPending[slot], h->sD2H));
+    h->pending[slot].n_out = n_out; h->pending[slot].B = B; h->pending[slot].capacity = capacity;
+    h->pendCount++;
     CK(cudaGetLastError());
-    for (int b = 0; b < B; b++)
-        if (n_out[b] > capacity) return fail(ORBFE_ERR_CAPACITY, "capacity smaller than the keypoint count (see orbfe_max_keypoints)");
     return ORBFE_OK;
+}
+
+// Wait for the oldest batch in flight (its last D2H is behind everything else it enqueued).
+static int wait_host_batch(OrbfeExtractor* h) {
+    const int slot = h->pendHead;
+    const OrbfeExtractor::Pending p = h->pending[slot];
+    h->pendHead = (h->pendHead + 1) % OrbfeExtractor::kMaxPending;
+    h->pendCount--;
+    CK(cudaEventSynchronize(h->evPending[slot]));
+    CK(cudaGetLastError());
+    for (int b = 0; b < p.B; b++)
+        if (p.n_out[b] > p.capacity) return fail(ORBFE_ERR_CAPACITY, "capacity smaller than the keypoint count (see orbfe_max_keypoints)");
+    return ORBFE_OK;
+}
+
+int orbfe_extract_batch_submit(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
+                               size_t frame_stride, int lap0, int lap1, OrbfeKeyPoint* keypoints,
+                               uint8_t* descriptors, int capacity, int* n_out, int* mono_out) {
+    return submit_host_batch(h, images, B, rows, cols, step, frame_stride, lap0, lap1, keypoints, descriptors, capacity,
+                             n_out, mono_out);
+}
+
+int orbfe_extract_batch_wait(OrbfeExtractor* h) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (h->pendCount <= 0) return fail(ORBFE_ERR_INVALID, "no host batch in flight");
+    return wait_host_batch(h);
+}
+
+int orbfe_extract_batch(OrbfeExtractor* h, const uint8_t* images, int B, int rows, int cols, size_t step,
+                        size_t frame_stride, int lap0, int lap1, OrbfeKeyPoint* keypoints,
+                        uint8_t* descriptors, int capacity, int* n_out, int* mono_out) {
+    int rc = submit_host_batch(h, images, B, rows, cols, step, frame_stride, lap0, lap1, keypoints, descriptors,
+                               capacity, n_out, mono_out);
+    if (rc) return rc;
+    // synchronous call: drain everything in flight, this batch last; the first error wins
+    int first = ORBFE_OK;
+    while (h->pendCount > 0) {
+        rc = wait_host_batch(h);
+        if (first == ORBFE_OK) first = rc;
+    }
+    CK(cudaStreamSynchronize(h->sCompute));
+    if (h->sCompute2) CK(cudaStreamSynchronize(h->sCompute2));
+    return first;
 }
 
 int orbfe_extract(OrbfeExtractor* h, const uint8_t* image, int rows, int cols, size_t step, int lap0,

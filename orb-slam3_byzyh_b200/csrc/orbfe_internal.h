@@ -208,6 +208,16 @@ struct OrbfeExtractor {
     GraphKey graphKey;
     cudaGraphExec_t graphExec = nullptr;
     long long graphLaunches = 0;
+
+    // Host batches in flight (orbfe_extract_batch_submit / orbfe_extract_batch_wait): one completion event on sD2H per
+    // submit, and what the wait has to check.  While batches are in flight the staging slots keep alternating across
+    // submits (chunkSeq), so the H2D of the next batch runs under the kernels of the current one.
+    static const int kMaxPending = 4;
+    struct Pending { const int* n_out = nullptr; int B = 0, capacity = 0; };
+    Pending pending[kMaxPending];
+    cudaEvent_t evPending[kMaxPending] = {};
+    int pendHead = 0, pendCount = 0;
+    long long chunkSeq = 0;
 };
 
 

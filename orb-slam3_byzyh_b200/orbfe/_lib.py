@@ -84,6 +84,8 @@ _SIGS = {
     "orbfe_max_keypoints": (_i, [_vp]),
     "orbfe_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbfe_extract_batch_submit": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "orbfe_extract_batch_wait": (_i, [_vp]),
     "orbfe_extract_batch_device": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "orbfe_level_size": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "orbfe_pyramid_level": (_i, [_vp, _i, _i, _i, _vp, _sz]),

@@ -112,6 +112,23 @@ class ORBextractor:
         self._shape = self._rect or (rows, cols)
         return n, mono, kps, desc
 
+    def extract_batch_submit(self, images, vLappingArea, out):
+        """Streaming form: enqueue the batch and return; `out` = (n, mono, kps, desc) PINNED host arrays that, like
+        `images`, must stay alive and untouched until the matching extract_batch_wait()."""
+        B, rows, cols = images.shape
+        n, mono, kps, desc = out
+        if isinstance(images, np.ndarray):
+            step, fstride = images.strides[1], images.strides[0]
+        else:
+            step, fstride = images.stride(1), images.stride(0)
+        check(lib().orbfe_extract_batch_submit(self._h, ptr(images), B, rows, cols, step, fstride, int(vLappingArea[0]),
+                                               int(vLappingArea[1]), ptr(kps), ptr(desc), self.capacity, ptr(n), ptr(mono)))
+        self._shape = self._rect or (rows, cols)
+
+    def extract_batch_wait(self):
+        """Block until the oldest submitted batch has its results in its host arrays."""
+        check(lib().orbfe_extract_batch_wait(self._h))
+
     def extract_batch_device(self, d_images, vLappingArea, d_kps, d_desc, d_n, d_mono, stream=None):
         """Device-resident form: torch CUDA tensors in, torch CUDA tensors out, enqueued on `stream`
         (a torch.cuda.Stream or None for the extractor's own stream); no synchronisation."""

@@ -241,3 +241,63 @@ def test_fast_score_tiles_per_cta(orbfe, per, monkeypatch):
     for (h, w, seed) in ((480, 752, 31), (241, 323, 32)):
         img = synth.synth_frame(h, w, seed)
         _check_frame(orbfe.ORBextractor(1000), O.Extractor(1000), img, (0, 1000), stages=True)
+
+
+def test_streaming_submit_wait(orbfe):
+    """orbfe_extract_batch_submit / _wait: up to four host batches in flight, waited for in FIFO order, each bit-exact
+    with the oracle; chunked batches (several chunks per submit, slots alternating across submits), single-chunk
+    batches, a size change in mid-stream (the handle drains and re-lays out), and the error paths."""
+    import torch
+    from orbfe._lib import KP_DTYPE
+    ex_g, ex_c = orbfe.ORBextractor(1000), O.Extractor(1000)
+    cap = ex_g.capacity
+    lap = (0, 1000)
+
+    def pinned_out(B):
+        return (torch.empty(B, dtype=torch.int32).pin_memory().numpy(), torch.empty(B, dtype=torch.int32).pin_memory().numpy(),
+                torch.empty((B, cap, 28), dtype=torch.uint8).pin_memory().numpy().view(KP_DTYPE).reshape(B, cap),
+                torch.empty((B, cap, 32), dtype=torch.uint8).pin_memory().numpy())
+
+    def check(frames, out):
+        n, mono, kps, desc = out
+        for i in range(len(frames)):
+            mo, ko, do = ex_c(frames[i], lap)
+            assert mono[i] == mo and n[i] == len(ko) and kps[i, :n[i]].tobytes() == ko.tobytes()
+            assert np.array_equal(desc[i, :n[i]], do)
+
+    with pytest.raises(Exception):
+        ex_g.extract_batch_wait()                                  # nothing in flight
+    batches = [torch.from_numpy(np.stack([synth.synth_frame(480, 752, 300 + 10 * k + i) for i in range(5)])).pin_memory()
+               for k in range(4)]
+    outs = [pinned_out(5) for _ in range(4)]
+    for chunk_bytes in (64 << 20, 6 << 30):                        # 64 MB: chunks of 1-2 frames; 6 GB: one chunk per batch
+        ex_g.set_max_bytes(chunk_bytes)
+        for o in outs:
+            for a in o:
+                a.view(np.uint8)[...] = 0xEE
+        for k in range(4):
+            ex_g.extract_batch_submit(batches[k], lap, outs[k])
+        with pytest.raises(Exception):
+            ex_g.extract_batch_submit(batches[0], lap, pinned_out(5))   # a fifth batch in flight
+        for k in range(4):
+            ex_g.extract_batch_wait()
+            check(batches[k].numpy(), outs[k])
+    # steady state as the bench drives it: submit k+1, then wait for k
+    ex_g.extract_batch_submit(batches[0], lap, outs[0])
+    for k in range(1, 4):
+        ex_g.extract_batch_submit(batches[k], lap, outs[k])
+        ex_g.extract_batch_wait()
+    ex_g.extract_batch_wait()
+    for k in range(4):
+        check(batches[k].numpy(), outs[k])
+    # another image size while a batch is in flight, then a synchronous call that drains everything
+    small = torch.from_numpy(np.stack([synth.synth_frame(240, 320, 400 + i) for i in range(3)])).pin_memory()
+    so = pinned_out(3)
+    ex_g.extract_batch_submit(batches[1], lap, outs[1])
+    ex_g.extract_batch_submit(small, lap, so)
+    res = ex_g.extract_batch(batches[2].numpy()[:2], lap)
+    check(batches[1].numpy(), outs[1])
+    check(small.numpy(), so)
+    check(batches[2].numpy()[:2], res)
+    with pytest.raises(Exception):
+        ex_g.extract_batch_wait()
