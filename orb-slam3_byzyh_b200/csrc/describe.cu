@@ -187,13 +187,19 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256)
+// One warp per keypoint, 8 keypoints per CTA, 32 registers (8 CTAs = 64 warps resident per SM).  The 256 test pairs are
+// staged once per CTA as float4 (x0, y0, x1, y1), laid out [k][lane] so that lane `l` reads its k-th pair (pattern
+// index 8 * l + k) with one conflict-free LDS.128 and no per-keypoint int8 -> float conversions.
+__global__ void __launch_bounds__(256, 8)
 k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr,
            const uint8_t* __restrict__ blur, const OrbfeWork* __restrict__ work,
            OrbfeKeyPoint* __restrict__ outKps, uint8_t* __restrict__ outDesc, int capacity) {
-    __shared__ __align__(16) int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += 256)
-        reinterpret_cast<int*>(pat)[i] = reinterpret_cast<const int*>(d_pattern)[i];
+    __shared__ float4 patf[256];
+    {
+        const int p = 8 * (threadIdx.x & 31) + (threadIdx.x >> 5);
+        const char4 q = reinterpret_cast<const char4*>(d_pattern)[p];
+        patf[threadIdx.x] = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -210,15 +216,17 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
     int m10 = 0, m01 = 0;
     const int u = lane - ORBFE_HALF_PATCH;
     const int au = u < 0 ? -u : u;
+    // rows +v and -v together (as :106-117 does): m10 = u * (sum of the column), m01 += v * (below - above)
+    int sum = au <= 15 ? (int)c[u] : 0;   // row v = 0 (lane 31 has au == 16: idle)
 #pragma unroll
-    for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; v++) {
-        const int d = umax[v < 0 ? -v : v];
-        if (au <= d) {   // lane 31 has au == 16 > 15: idle
-            const int val = c[v * L.pitch + u];
-            m10 += u * val;
-            m01 += v * val;
+    for (int v = 1; v <= ORBFE_HALF_PATCH; v++) {
+        if (au <= umax[v]) {
+            const int vp = c[v * L.pitch + u], vm = c[-v * L.pitch + u];
+            sum += vp + vm;
+            m01 += v * (vp - vm);
         }
     }
+    m10 = u * sum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -231,12 +239,11 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
     const float ang = __fmul_rn(angle, factorPI);
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const uint8_t* bc = blur + co;
-    const int8_t* pp = pat + 32 * lane;
     unsigned val = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const float x0 = (float)pp[4 * k], y0 = (float)pp[4 * k + 1];
-        const float x1 = (float)pp[4 * k + 2], y1 = (float)pp[4 * k + 3];
+        const float4 q = patf[32 * k + lane];
+        const float x0 = q.x, y0 = q.y, x1 = q.z, y1 = q.w;
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
