@@ -8,8 +8,10 @@ One "step" = one pass of the ORB front-end over a batch of synthetic 752x480 fra
 (EuRoC mono settings: nFeatures 1000, scaleFactor 1.2, 8 levels, FAST 20/7, lapping {0,1000}).
   value : frames/s with the batch resident in HBM (orbfe_extract_batch_device on a CUDA stream,
           CUDA events on that stream, max over ranks).
-  e2e   : frames/s through the host-pointer C-ABI call orbfe_extract_batch (pinned host frames
-          in, keypoints + descriptors out; H2D/D2H copies inside the timed region).
+  e2e   : frames/s through the host-pointer C ABI (pinned host frames in, keypoints + descriptors out; the
+          H2D/D2H copies of every step inside the timed region), driven as a streaming caller does:
+          orbfe_extract_batch_submit / _wait with two batches in flight.  e2e.sync_call_value is the
+          same with one blocking orbfe_extract_batch call per step.
 Frames shard over ranks with no collective (weak scaling).  The matching leg (C5: 2000 frame
 descriptors vs a 1 M descriptor map, sharded over ranks, NCCL all-gather of the per-shard best
 two + merge) is reported in the same JSON line under "matching".
