@@ -47,6 +47,12 @@ def test_no_cpu_fallback_without_a_device():
         orbfe.ORBmatcher().knn2(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
     with pytest.raises(orbfe.OrbfeError):
         orbfe.ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
+    # the streaming entry points refuse a null handle instead of touching the buffers
+    lib = orbfe.lib()
+    img, out = np.zeros((1, 64, 64), np.uint8), np.zeros(64, np.uint8)
+    p = lambda a: a.ctypes.data
+    assert lib.orbfe_extract_batch_submit(None, p(img), 1, 64, 64, 64, 64 * 64, 0, 0, p(out), p(out), 1, p(out), p(out)) < 0
+    assert lib.orbfe_extract_batch_wait(None) < 0
 
 
 def test_product_never_imports_the_oracle():
