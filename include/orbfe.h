@@ -426,6 +426,28 @@ int orbfe_undistort_keypoints(const OrbfeKeyPoint* keys, int n, float fx, float 
 int orbfe_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int n_points,
                                   int32_t* best_idx, int device);
 
+/* KannalaBrandt8 geometry behind the fisheye stereo matcher, batched over points / matches.
+ * params = mvParameters {fx, fy, cx, cy, k1, k2, k3, k4} (include/CameraModels/GeometricCamera.h), precision = the
+ * Newton stop of KannalaBrandt8 (include/CameraModels/KannalaBrandt8.h:42-59, 102; 1e-6 by default).  Host arrays.
+ *   cv::Point2f KannalaBrandt8::project(const cv::Point3f&) / Eigen::Vector2f project(const Eigen::Vector3f&)
+ *       include/CameraModels/KannalaBrandt8.h:63-65, src/CameraModels/KannalaBrandt8.cpp:40-55, 84-101
+ *   cv::Point3f KannalaBrandt8::unproject(const cv::Point2f&)   KannalaBrandt8.h:69, .cpp:180-217: rays (x, y, 1) */
+int orbfe_kb8_project(const float* params, const float* p3d, int n, float* uv, int device);
+int orbfe_kb8_unproject(const float* params, float precision, const float* uv, int n, float* rays,
+                        int device);
+/* float KannalaBrandt8::TriangulateMatches(pCamera2, kp1, kp2, R12, t12, sigmaLevel, unc, p3D)
+ *   KannalaBrandt8.h:91-93, .cpp:439-515 (+ ::Triangulate :553-565), once per match: the loop body of
+ *   Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1560-1587, sigma1 / unc2 = mvLevelSigma2 of the two keypoints'
+ *   octaves, R12 / t12 = mRlr / mtlr) and KannalaBrandt8::epipolarConstrain (.cpp:322-328: depth > 0.0001f).
+ * R12 row-major 3x3, pt1 / pt2 = n x 2 keypoint coordinates in camera 1 / camera 2.  depth[i] = the reference's return
+ * value (z of the point in camera 1, or -1 low parallax, -2 / -3 behind a camera, -4 / -5 reprojection error in
+ * camera 1 / 2); p3d[i] = the triangulated point in camera 1 where depth[i] > 0, NaN otherwise.  fp32 with a
+ * double-precision null-vector solve where the reference calls Eigen::JacobiSVD: tolerance-based parity. */
+int orbfe_kb8_triangulate_matches(const float* params1, float precision1, const float* params2,
+                                  float precision2, const float* R12, const float* t12,
+                                  const float* pt1, const float* pt2, const float* sigma1,
+                                  const float* unc2, int n, float* depth, float* p3d, int device);
+
 /* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
 const char* orbfe_version(void);
 

@@ -448,3 +448,32 @@ def distinctive_descriptors(desc, start):
     best = np.empty(len(start) - 1, np.int32)
     lib().oracle_distinctive_descriptors(_p(desc), _p(start), len(start) - 1, _p(best))
     return best
+
+
+# ---- KannalaBrandt8 geometry behind the fisheye stereo matcher (oracle/kb8_oracle.cpp) ----
+def kb8_project(params, p3d):
+    p3d = np.ascontiguousarray(p3d, np.float32)
+    uv = np.empty((len(p3d), 2), np.float32)
+    lib().oracle_kb8_project(_p(np.ascontiguousarray(params, np.float32)), _p(p3d), len(p3d), _p(uv))
+    return uv
+
+
+def kb8_unproject(params, uv, precision=1e-6):
+    uv = np.ascontiguousarray(uv, np.float32)
+    rays = np.empty((len(uv), 3), np.float32)
+    lib().oracle_kb8_unproject(_p(np.ascontiguousarray(params, np.float32)), C.c_float(precision), _p(uv), len(uv), _p(rays))
+    return rays
+
+
+def kb8_triangulate(params1, params2, R12, t12, pt1, pt2, sigma1, unc2, precision1=1e-6, precision2=1e-6):
+    """KannalaBrandt8::TriangulateMatches per match: (depth or the negative rejection code, p3D (NaN where rejected))."""
+    pt1, pt2 = np.ascontiguousarray(pt1, np.float32), np.ascontiguousarray(pt2, np.float32)
+    n = len(pt1)
+    depth = np.empty(n, np.float32)
+    p3d = np.full((n, 3), np.nan, np.float32)
+    lib().oracle_kb8_triangulate(_p(np.ascontiguousarray(params1, np.float32)), C.c_float(precision1),
+                                 _p(np.ascontiguousarray(params2, np.float32)), C.c_float(precision2),
+                                 _p(np.ascontiguousarray(R12, np.float32)), _p(np.ascontiguousarray(t12, np.float32)),
+                                 _p(pt1), _p(pt2), _p(np.ascontiguousarray(sigma1, np.float32)),
+                                 _p(np.ascontiguousarray(unc2, np.float32)), n, _p(depth), _p(p3d))
+    return depth, p3d

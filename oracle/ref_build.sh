@@ -36,3 +36,12 @@ ${ORACLE_CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
     "$REF/Thirdparty/DBoW2/DUtils/Random.cpp" "$REF/Thirdparty/DBoW2/DUtils/Timestamp.cpp" \
     -o "$HERE/_ref/libref_orbmatcher.so"
 echo "built $HERE/_ref/libref_orbmatcher.so"
+
+# KannalaBrandt8::project / unproject (src/CameraModels/KannalaBrandt8.cpp): the file needs Eigen and Boost as a whole;
+# the three float bodies are sliced the same way and compiled against refshim/kb8shim.h.
+python3 "$HERE/ref_slices.py" "$REF" "$TMP/ref_kb8_slices.cc" kb8
+${ORACLE_CXX:-g++} -O2 -std=c++17 -fPIC -ffp-contract=off -w -shared \
+    -I"$HERE/refshim" -I"$HERE/cvshim" \
+    "$TMP/ref_kb8_slices.cc" "$HERE/ref_kb8_driver.cpp" \
+    -o "$HERE/_ref/libref_kb8.so"
+echo "built $HERE/_ref/libref_kb8.so"

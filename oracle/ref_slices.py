@@ -8,7 +8,9 @@ but the matcher functions on the hot path only touch a handful of members, which
 declares.  The output goes to a temporary directory chosen by oracle/ref_build.sh and is deleted after
 compilation: no reference source text is ever stored in this repository.
 
-usage: ref_slices.py <reference root> <output .cc>
+usage: ref_slices.py <reference root> <output .cc> [kb8]
+  kb8: the second, independent unit -- KannalaBrandt8::project (both float overloads) and ::unproject out of
+       src/CameraModels/KannalaBrandt8.cpp, compiled against oracle/refshim/kb8shim.h.
 """
 import re
 import sys
@@ -43,6 +45,13 @@ SLICES = [
     ("src/MapPoint.cc", r"void MapPoint::ComputeDistinctiveDescriptors\("),
     ("src/KeyFrame.cc", r"vector<size_t> KeyFrame::GetFeaturesInArea\("),
     ("src/KeyFrame.cc", r"bool KeyFrame::IsInImage\("),
+]
+
+
+KB8_SLICES = [
+    ("src/CameraModels/KannalaBrandt8.cpp", r"cv::Point2f KannalaBrandt8::project\(const cv::Point3f &p3D\)"),
+    ("src/CameraModels/KannalaBrandt8.cpp", r"Eigen::Vector2f KannalaBrandt8::project\(const Eigen::Vector3f &v3D\)"),
+    ("src/CameraModels/KannalaBrandt8.cpp", r"cv::Point3f KannalaBrandt8::unproject\(const cv::Point2f &p2D\)"),
 ]
 
 
@@ -97,13 +106,15 @@ def cut(text, code, pattern):
     return text[start : i + 1], text.count("\n", 0, start) + 1
 
 
-def main(ref, out_path):
+def main(ref, out_path, mode=""):
     cache = {}
     parts = [
         "// GENERATED by oracle/ref_slices.py from the reference tree; temporary, never committed.\n",
         '#include "refshim.h"\n#include "ORBmatcher.h"\n#include <limits.h>\n#include <stdint.h>\nusing namespace std;\nnamespace ORB_SLAM3 {\n',
     ]
-    for rel, pat in SLICES:
+    if mode == "kb8":   # the reference file has no `using namespace std`
+        parts[1] = '#include "kb8shim.h"\nnamespace ORB_SLAM3 {\n'
+    for rel, pat in (KB8_SLICES if mode == "kb8" else SLICES):
         if rel not in cache:
             t = open("%s/%s" % (ref, rel), encoding="utf-8", errors="replace").read()
             cache[rel] = (t, blank_comments(t))
@@ -115,4 +126,4 @@ def main(ref, out_path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "")

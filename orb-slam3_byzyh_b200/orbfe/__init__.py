@@ -8,6 +8,8 @@ libORBfe_b200.so (CUDA, sm_100a).
                      Frame::ComputeStereoFishEyeMatches; plus the SURVEY 8(f) "next" searches
                      (SearchForInitialization, Fuse, SearchBySim3, Sim3 SearchByProjection, SearchByBoW).
   ORBVocabulary <->  ORB_SLAM3::ORBVocabulary  (/root/reference/include/ORBVocabulary.h:30-31, DBoW2 transform)
+  KannalaBrandt8 <-> ORB_SLAM3::KannalaBrandt8 (/root/reference/include/CameraModels/KannalaBrandt8.h): project,
+                     unproject, TriangulateMatches / epipolarConstrain, batched over points / matches
 
 The reference is C++; the drop-in binding for it is the header-only adapter under host/.  This
 Python mirror exists so that tests/, bench.py and multi-GPU drivers exercise exactly the same C
@@ -19,5 +21,6 @@ from .extractor import ORBextractor
 from .matcher import FrameData, ORBmatcher
 from .vocabulary import ORBVocabulary
 from . import intake
+from .kb8 import KannalaBrandt8
 
-__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "intake", "FrameData", "KP_DTYPE", "OrbfeError", "lib", "LIB_PATH", "EXPORTS"]
+__all__ = ["ORBextractor", "ORBmatcher", "ORBVocabulary", "KannalaBrandt8", "intake", "FrameData", "KP_DTYPE", "OrbfeError", "lib", "LIB_PATH", "EXPORTS"]

@@ -129,6 +129,9 @@ _SIGS = {
     "orbfe_resize_linear": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _i]),
     "orbfe_undistort_keypoints": (_i, [_vp, _i, _f, _f, _f, _f, _vp, _i, _vp, _i]),
     "orbfe_distinctive_descriptors": (_i, [_vp, _vp, _i, _vp, _i]),
+    "orbfe_kb8_project": (_i, [_vp, _vp, _i, _vp, _i]),
+    "orbfe_kb8_unproject": (_i, [_vp, _f, _vp, _i, _vp, _i]),
+    "orbfe_kb8_triangulate_matches": (_i, [_vp, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)
