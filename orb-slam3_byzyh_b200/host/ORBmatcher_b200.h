@@ -414,6 +414,33 @@ inline void KnnRatioMatch(const cv::Mat& query, const cv::Mat& train, std::vecto
         throw std::runtime_error(std::string("KnnRatioMatch (B200): ") + orbfe_last_error());
 }
 
+// The geometry step that follows KnnRatioMatch in Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1560-1587):
+// KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp:439-515) for ALL ratio-test survivors in one
+// call.  params1 / params2 = the two cameras' mvParameters (8 floats), precision = GetPrecision(); R12 row major
+// (Frame::mRlr.data() is column major in Eigen: pass mRlr.transpose().data() or copy), t12 = mtlr; pairs[i] =
+// (index into keysL, index into keysR); levelSigma2 = mvLevelSigma2.  depth[i] / p3D[3i..] as the reference returns
+// them per match; the caller keeps :1580-1586 (depth > 0.0001f -> mvLeftToRightMatch, mvStereo3Dpoints, mvDepth).
+inline void TriangulateFisheyeMatches(const float params1[8], float precision1, const float params2[8], float precision2,
+                                      const float R12[9], const float t12[3], const std::vector<cv::KeyPoint>& keysL,
+                                      const std::vector<cv::KeyPoint>& keysR,
+                                      const std::vector<std::pair<int, int> >& pairs, const std::vector<float>& levelSigma2,
+                                      std::vector<float>& depth, std::vector<float>& p3D) {
+    const size_t n = pairs.size();
+    std::vector<float> pt1(2 * n), pt2(2 * n), s1(n), s2(n);
+    for (size_t i = 0; i < n; i++) {
+        const cv::KeyPoint &a = keysL[pairs[i].first], &b = keysR[pairs[i].second];
+        pt1[2 * i] = a.pt.x; pt1[2 * i + 1] = a.pt.y;
+        pt2[2 * i] = b.pt.x; pt2[2 * i + 1] = b.pt.y;
+        s1[i] = levelSigma2[a.octave];
+        s2[i] = levelSigma2[b.octave];
+    }
+    depth.assign(n, -1.f);
+    p3D.assign(3 * n, 0.f);
+    if (orbfe_kb8_triangulate_matches(params1, precision1, params2, precision2, R12, t12, pt1.data(), pt2.data(), s1.data(),
+                                      s2.data(), (int)n, depth.data(), p3D.data(), device()) != ORBFE_OK)
+        throw std::runtime_error(std::string("TriangulateFisheyeMatches (B200): ") + orbfe_last_error());
+}
+
 }  // namespace b200
 }  // namespace ORB_SLAM3
 

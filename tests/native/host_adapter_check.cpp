@@ -97,6 +97,17 @@ int main(int argc, char** argv) {
         for (auto& pr : pairs) { int32_t ab[2] = {(int32_t)pr.first, (int32_t)pr.second}; fwrite(ab, 4, 2, f); }
         fclose(f);
         fprintf(stderr, "bow words %zu nodes %zu matches %d tri %d\n", bow.size(), fv.size(), nb, nt);
+        {   // fisheye triangulation of the frame's keypoints against themselves shifted along a 10 cm baseline: the call
+            // must go through (every pair is either accepted with a positive depth or carries a rejection code)
+            const float P[8] = {190.97f, 190.97f, 254.93f, 256.89f, 0.0034f, 0.0007f, -0.0020f, 0.0002f};
+            const float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0.1f, 0, 0};
+            std::vector<std::pair<int, int> > fpairs;
+            for (int i = 0; i + 1 < (int)kps.size() && i < 64; i++) fpairs.push_back(std::make_pair(i, i + 1));
+            std::vector<float> depth, p3D;
+            TriangulateFisheyeMatches(P, 1e-6f, P, 1e-6f, R, t, kps, kps, fpairs, s2, depth, p3D);
+            for (size_t i = 0; i < depth.size(); i++)
+                if (!(depth[i] > 0.f || (depth[i] <= -1.f && depth[i] >= -5.f))) return 7;
+        }
     }
     int self = desc.rows ? ORB_SLAM3::b200::DescriptorDistance(desc.row(0), desc.row(0)) : 0;
     printf("%d %zu %d %d %d %.3f\n", mono, kps.size(), ex.GetLevels(), l1.cols, self, ex.GetScaleFactor());
