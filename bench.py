@@ -216,6 +216,20 @@ def call_latencies(orbfe, device):
                                             (kr, dr, None, np.zeros(len(dr), np.uint8), fvr), f12,
                                             np.array([-1e4, -1e4], np.float32), sf, sf * sf))
     out["search_for_triangulation_1200x1200"] = timeit(tri)
+    try:    # fisheye stereo geometry per match (KannalaBrandt8::TriangulateMatches), 1200 ratio-test survivors
+        rng = np.random.default_rng(11)
+        P1 = np.array([190.978477, 190.973307, 254.931706, 256.897442, 0.003482389, 0.000715034, -0.002053236, 0.000202936], np.float32)
+        P2 = np.array([190.442369, 190.434448, 252.598029, 254.917267, 0.003400724, 0.001766232, -0.002663594, 0.000329930], np.float32)
+        c1, c2 = orbfe.KannalaBrandt8(P1, device=device), orbfe.KannalaBrandt8(P2, device=device)
+        R12, t12 = np.eye(3, dtype=np.float32), np.array([0.1, 0.002, -0.001], np.float32)
+        X1 = np.stack([rng.uniform(-2, 2, 1200), rng.uniform(-2, 2, 1200), rng.uniform(0.5, 3, 1200)], 1).astype(np.float32)
+        pt1, pt2 = c1.project(X1), c2.project(X1 - t12)
+        ones = np.ones(1200, np.float32)
+        depth, _ = c1.TriangulateMatches(c2, pt1, pt2, R12, t12, ones, ones)
+        assert (depth > 0).mean() > 0.9, "triangulation of exact projections rejected"
+        out["kb8_triangulate_1200_matches"] = timeit(lambda: c1.TriangulateMatches(c2, pt1, pt2, R12, t12, ones, ones))
+    except Exception as e:          # informative only
+        out["kb8_triangulate_1200_matches"] = "error: " + str(e)[:120]
     out["cpu_reference"] = cpu_reference_call_latencies(d, pts, dl, dr, kl, kr, timeit)
     return out
 

@@ -74,3 +74,14 @@ def test_triangulate_matches(orbfe):
     d_s, _ = c1.TriangulateMatches(c2, pt1[:100], pt2[:100], R12, t12, 1.0, 1.0)
     d_v, _ = c1.TriangulateMatches(c2, pt1[:100], pt2[:100], R12, t12, np.ones(100, np.float32), np.ones(100, np.float32))
     assert np.array_equal(d_s, d_v)
+
+
+def test_against_the_reference_outputs(orbfe):
+    """The CUDA path against outputs of the reference's own KannalaBrandt8::project / unproject
+    (tests/golden/kb8_ref.npz), no oracle in between; same tolerances as above."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kb8_ref.npz"))
+    for name in ("1", "2"):
+        cam = orbfe.KannalaBrandt8(g["P" + name])
+        assert np.abs(cam.project(g["p3d"]) - g["project" + name]).max() < 1e-3
+        assert _ulps(cam.unproject(g["uv"]), np.ascontiguousarray(g["unproject" + name])).max() <= 8

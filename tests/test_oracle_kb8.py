@@ -98,3 +98,13 @@ def test_triangulate_recovers_known_points_and_rejects():
     d, _ = O.kb8_triangulate(P1, P2, R12, t12, pt1, bad, s, s)
     assert set(np.unique(d[d < 0]).tolist()) <= {-1.0, -2.0, -3.0, -4.0, -5.0} and (d < 0).mean() > 0.9
     assert (d == -4).any() or (d == -5).any()
+
+
+def test_oracle_matches_the_committed_reference_outputs():
+    """tests/golden/kb8_ref.npz holds outputs of the reference's own project / unproject (make_golden_kb8.py): this
+    check needs neither /root/reference nor oracle/_ref."""
+    g = np.load(os.path.join(HERE, "golden", "kb8_ref.npz"))
+    for name in ("1", "2"):
+        P = g["P" + name]
+        assert O.kb8_project(P, g["p3d"]).tobytes() == g["project" + name].tobytes()
+        assert O.kb8_unproject(P, g["uv"]).tobytes() == g["unproject" + name].tobytes()
