@@ -33,7 +33,7 @@ __device__ __forceinline__ int hamming256(const uint32_t* a, const uint32_t* b) 
 }
 
 // Same distance with half the POPCs: POPC issues at a quarter of the LOP3 rate on B200 (measured
-// ~16 lanes/clk/SM, tools/pipe_bench.cu), so the eight XOR words are first compressed with a
+// ~16 lanes/clk/SM, tools/pipe_bench2.cu), so the eight XOR words are first compressed with a
 // Harley-Seal carry-save adder tree (LOP3 full adders) into four words of weight 1, 2, 4, 8.
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
     sum = a ^ b ^ c;
