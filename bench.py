@@ -481,7 +481,7 @@ def run_ours(args):
     Ppad = sum((w + 38) * (h + 38) for w, h in sizes)
     K = float(n_kp.mean())
     C = float(cands)
-    alg = {"pyramid": P06 + Ppad, "fast_score": P, "fast_nms": 0.25 * P, "fast_cells": 12 * C, "octree": 12 * C + 12 * K,
+    alg = {"pyramid": P06 + Ppad, "fast": P + 12 * C, "octree": 12 * C + 12 * K,
            "layout": 28 * K, "blur": 2 * P, "describe": (749 + 4 + 512 + 32) * K}
     frame_bytes = 3 * P + P06 + Ppad + 24 * C + 1337 * K
     kern = {k: v for k, v in stage.items() if k in alg}

@@ -110,17 +110,14 @@ int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys
 int orbfe_debug_level_keypoints(OrbfeExtractor* h, int frame, int level, int32_t* xys,
                                 int capacity, int* n_out); /* octree-retained, list order */
 int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step);
-/* FAST arc score map ("best": corner at threshold t <=> best > t, response = best-1; 0 where
- * best <= minThFAST), w x h ROI of the level. */
-int orbfe_debug_score(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step);
 /* Run only DistributeOctTree (src/ORBextractor.cc:711-1057) on caller-supplied candidates. */
 int orbfe_debug_octree(OrbfeExtractor* h, const int32_t* xys, int n, int minX, int maxX, int minY,
                        int maxY, int N, int32_t* keep_idx, int capacity, int* n_out);
 /* Per-kernel device milliseconds of the last chunk of the last batch call (CUDA events on the
- * launching stream; needs orbfe_set_profiling(h,1)).  Order: h2d, pyramid (nlevels launches),
- * fast_score, fast_nms, fast_cells, octree, layout, blur, describe, d2h; h2d/d2h are reported as 0 (they
+ * launching stream; needs orbfe_set_profiling(h,1)).  Order: h2d, pyramid, fast (per-cell FAST + NMS +
+ * retry + emission, one kernel), octree, layout, blur, describe, d2h; h2d/d2h are reported as 0 (they
  * overlap neighbouring chunks on their own streams). */
-#define ORBFE_NUM_STAGES 10
+#define ORBFE_NUM_STAGES 8
 int orbfe_set_profiling(OrbfeExtractor* h, int enable);
 int orbfe_stage_ms(OrbfeExtractor* h, float* ms /*[ORBFE_NUM_STAGES]*/);
 /* Number of kernel launches issued by this extractor since creation. */

@@ -19,7 +19,8 @@
 //   fc_margin2          biased differences, 3-wise sliding windows: 80 packed min/max per pixel pair      3.86
 //   fc_margin2_raw      the same on the raw ring values (no differences)                                 +2.5 %
 //   fc_margin2_pair     arcs taken in pairs (k, k+1 share eight ring pixels): 72 per pixel pair           3.57
-//   fc_margin2_pair_raw pairs on the raw ring values -- THE ONE THE KERNEL USES                           3.41
+//   fc_margin2_pair_raw pairs on the raw ring values (round 1's k_fast_score)                           3.41
+//   fc_margin2_pair_raw_biased  the same, no packed subtraction -- THE ONE k_fast_cells USES
 //
 // NOTE (measured on B200, nvcc 12.9): a formulation that folds `max(best, -mx)` into the running
 // maximum is MISCOMPILED for sm_100a (ptxas drops the negation when it fuses into VIMNMX3); this
@@ -149,6 +150,22 @@ static FC_HD uint32_t fc_margin2_pair_raw(const uint32_t* r, uint32_t c2, uint32
     return fc_max3s_relu(a, b, 0u);
 }
 
+// The same without packed subtractions -- THE ONE k_fast_cells USES.  nvcc 12.9 turns a packed `x - y` into
+// x + (~y + 0x10001) and then folds the +1s of several negations together; in one of the three instantiations of
+// k_fast_cells that folding came out as `VIADD.16x2 R, ~sub2, 0x0` (the +1 lost: every dark-polarity score one too
+// low, found by the parity tests on B200).  Here every lane carries a bias of 1024, so all lanes stay positive and
+// plain 32-bit adds / subtracts are exact per lane (no borrow can cross):
+//   a = c + 1024 - sub - min_k max9_k  in [514, 1279],   b = max_k min9_k + 1024 - sub - c  in [514, 1279]
+//   margin = max(a, b, 1024) - 1024.
+static FC_HD uint32_t fc_margin2_pair_raw_biased(const uint32_t* r, uint32_t c2, uint32_t sub2) {
+    uint32_t hi, lo;
+    fc_pair_extrema(r, hi, lo);
+    const uint32_t K = 0x04000400u, ks = K - sub2;   // sub <= 255 per lane: no borrow
+    const uint32_t a = c2 + ks - lo;
+    const uint32_t b = hi + ks - c2;
+    return fc_max3u(a, b, K) - K;
+}
+
 // The margin from the RAW ring values (r[k] = two ring pixels as 16-bit lanes, c2 = the two centres), without
 // forming the 16 differences:  min over an arc of (c - ring) = c - max over the arc of ring, and
 // min over an arc of (ring - c) = (min over the arc of ring) - c, so
@@ -171,6 +188,39 @@ static FC_HD uint32_t fc_margin2_raw(const uint32_t* r, uint32_t c2, uint32_t su
     const uint32_t a = fc_sub2(fc_sub2(c2, sub2), lo);   // (c - sub) - min max9
     const uint32_t b = fc_sub2(hi, fc_add2(c2, sub2));   // max min9 - (c + sub)
     return fc_max3s_relu(a, b, 0u);
+}
+
+// ---- dense early reject on packed bytes (four pixels per register) ---------------------------------------------
+// Every arc of 9 contiguous ring pixels contains one pixel of each opposite pair {k, k+8} (9 > 8), and all pixels
+// of a corner's arc differ from the centre by more than t with one sign.  So a corner at threshold t, of either
+// polarity, needs |ring - centre| > t on at least one pixel of EVERY opposite pair; the kernel tests the two compass
+// pairs, k = 0/8 (rows y+3 / y-3) and k = 4/12 (columns x+3 / x-3).  Bytes stay packed: the absolute difference is one
+// instruction (VABSDIFF4), the comparison with u = t+1 a SWAR byte compare that is exact for every u in [1, 255].
+#if defined(__CUDA_ARCH__)
+static __device__ __forceinline__ uint32_t fc_absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+#else
+static inline uint32_t fc_absdiff4(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const int x = (a >> (8 * i)) & 0xFF, y = (b >> (8 * i)) & 0xFF;
+        r |= (uint32_t)(x > y ? x - y : y - x) << (8 * i);
+    }
+    return r;
+}
+#endif
+// Bit 7 of every byte of the result: that byte of a is >= u, with uLow = (u & 0x7F) * 0x01010101 and
+// uTop = (u & 0x80) ? ~0 : 0.  (a | 0x80) - low7(u) never borrows across bytes (each byte stays >= 1) and leaves
+// "low7(a) >= low7(u)" in bit 7; the top bits decide when they differ.  The other bits are junk.
+static FC_HD uint32_t fc_ge4(uint32_t a, uint32_t uLow, uint32_t uTop) {
+    const uint32_t z = (a | 0x80808080u) - uLow;
+    return (a & ~uTop) | (~(a ^ uTop) & z);
+}
+// 0x80 in every byte whose pixel passes the compass test (c = four centres, n / s / w / e = the ring pixels
+// 3 px above / below / left / right of each of them).
+static FC_HD uint32_t fc_compass4(uint32_t c, uint32_t n, uint32_t s, uint32_t w, uint32_t e, uint32_t uLow, uint32_t uTop) {
+    const uint32_t v = fc_ge4(fc_absdiff4(n, c), uLow, uTop) | fc_ge4(fc_absdiff4(s, c), uLow, uTop);
+    const uint32_t h = fc_ge4(fc_absdiff4(w, c), uLow, uTop) | fc_ge4(fc_absdiff4(e, c), uLow, uTop);
+    return v & h & 0x80808080u;
 }
 
 // Scalar convenience (host tests, small kernels): best of one pixel of a byte image.

@@ -118,9 +118,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     g.minTh = std::min(std::max(e->minTh, 0), 255);
     size_t off = 0;
     unsigned slot = 0, tapOff = 0;
-    int cell = 0, kpBase = 0, fastTile = 0, blurTile = 0, nmsTile = 0;
-    unsigned bmWords = 0;
-    g.subTh = std::max(std::min(g.minTh, g.iniTh), 1);
+    int cell = 0, kpBase = 0, blurTile = 0;
     std::vector<OrbfeTap> taps;
     for (int l = 0; l < g.nlevels; l++) {
         OrbfeLevelGeom& L = g.lv[l];
@@ -188,18 +186,6 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
                 if (hi - lo > 7) L.fastTaps = 0;
             }
         }
-        L.fastTileBase = fastTile;
-        L.fastTilesX = hasCells ? (L.w - 38 + ORBFE_FAST_TW - 1) / ORBFE_FAST_TW : 0;
-        L.fastTilesY = hasCells ? (L.h - 38 + ORBFE_FAST_TH - 1) / ORBFE_FAST_TH : 0;
-        fastTile += L.fastTilesX * L.fastTilesY;
-        L.nmsTileBase = nmsTile;
-        L.nmsTilesX = hasCells ? (L.w - 38 + 127) / 128 : 0;
-        L.nmsTilesY = hasCells ? (L.h - 38 + 127) / 128 : 0;
-        nmsTile += L.nmsTilesX * L.nmsTilesY;
-        L.bmPitch = 4 * L.nmsTilesX;
-        L.bmMin = bmWords;
-        L.bmIni = bmWords + (hasCells ? (unsigned)(L.h - 38) * L.bmPitch : 0u);
-        bmWords = L.bmIni + (hasCells ? (unsigned)(L.h - 38) * L.bmPitch : 0u);
         L.blurTileBase = blurTile;
         L.blurTilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;
         L.blurTilesY = (L.h + 4 * ORBFE_BLUR_TH - 1) / (4 * ORBFE_BLUR_TH);   // 4 warps (strips) per CTA
@@ -209,10 +195,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     g.cellsPerFrame = cell;
     g.slotsPerFrame = slot;
     g.kpCapFrame = kpBase;
-    g.fastTiles = fastTile;
     g.blurTiles = blurTile;
-    g.nmsTiles = nmsTile;
-    g.bmWordsPerFrame = bmWords;
     if (orbfe_octree_prepare(g) < 0) return fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(octree)", cudaGetLastError());
 
     // new geometry invalidates the chunk buffers
@@ -229,7 +212,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     e->g = g;
     e->haveGeom = true;
     const size_t ocg = g.ocShared ? 0 : orbfe_octree_table_bytes(g.ocMmax) * g.nlevels;
-    e->perFrameBytes = 4 * (size_t)g.pyrStride + 4 * (size_t)g.bmWordsPerFrame + 3 * sizeof(uint32_t) * (size_t)g.slotsPerFrame +
+    e->perFrameBytes = 2 * (size_t)g.pyrStride + 3 * sizeof(uint32_t) * (size_t)g.slotsPerFrame +
                        sizeof(int) * (size_t)g.cellsPerFrame + (sizeof(uint32_t) + sizeof(OrbfeWork)) * (size_t)g.kpCapFrame +
                        2 * sizeof(int) * g.nlevels + ocg + 2048;
     return ORBFE_OK;
@@ -241,20 +224,18 @@ int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*&
     if (slab) { cudaFree(slab); slab = nullptr; cap = 0; }
     const OrbfeFrameGeom& g = e->g;
     const size_t B = (size_t)frames;
-    size_t sz[13], total = 0;
+    size_t sz[12], total = 0;
     const size_t ocStride = g.ocShared ? 0 : orbfe_octree_table_bytes(g.ocMmax);
-    sz[0] = B * g.pyrStride; sz[1] = sz[0]; sz[2] = 2 * sz[0]; sz[12] = B * g.bmWordsPerFrame * 4;
+    sz[0] = B * g.pyrStride; sz[1] = sz[0]; sz[2] = 0;
     sz[3] = B * g.slotsPerFrame * 4; sz[4] = B * g.cellsPerFrame * 4; sz[5] = sz[3]; sz[6] = sz[3];
     sz[7] = B * g.nlevels * 4; sz[8] = B * g.kpCapFrame * 4; sz[9] = sz[7];
     sz[10] = B * g.kpCapFrame * sizeof(OrbfeWork); sz[11] = B * g.nlevels * ocStride;
-    size_t offs[13];
-    for (int i = 0; i < 13; i++) { offs[i] = total; total += align_up(sz[i], 256); }
+    size_t offs[12];
+    for (int i = 0; i < 12; i++) { offs[i] = total; total += align_up(sz[i], 256); }
     CK(cudaMalloc(&slab, total));
     char* p = (char*)slab;
     bufs.pyr = (uint8_t*)(p + offs[0]);
     bufs.blur = (uint8_t*)(p + offs[1]);
-    bufs.score = (uint16_t*)(p + offs[2]);
-    bufs.nmsBits = (uint32_t*)(p + offs[12]);
     bufs.slots = (uint32_t*)(p + offs[3]);
     bufs.cellCount = (int*)(p + offs[4]);
     bufs.cand = (uint32_t*)(p + offs[5]);
@@ -302,20 +283,16 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
     stage_mark(e, 1, st);
     orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, bufs, B, st, &e->launches, e->d_mapx ? &rect : nullptr);
     stage_mark(e, 2, st);
-    orbfe_launch_fast_score(g, bufs, B, st, &e->launches);
+    orbfe_launch_fast(g, bufs, B, st, &e->launches);
     stage_mark(e, 3, st);
-    orbfe_launch_fast_nms(g, bufs, B, st, &e->launches);
-    stage_mark(e, 4, st);
-    orbfe_launch_fast_cells(g, bufs, B, st, &e->launches);
-    stage_mark(e, 5, st);
     orbfe_launch_octree(g, bufs, B, st, &e->launches);
-    stage_mark(e, 6, st);
+    stage_mark(e, 4, st);
     orbfe_launch_layout(g, bufs, B, lap0, lap1, d_kps, capacity, d_n, d_mono, st, &e->launches);
-    stage_mark(e, 7, st);
+    stage_mark(e, 5, st);
     orbfe_launch_blur(g, bufs, B, st, &e->launches);
-    stage_mark(e, 8, st);
+    stage_mark(e, 6, st);
     orbfe_launch_describe(g, bufs, B, d_kps, d_desc, capacity, st, &e->launches);
-    stage_mark(e, 9, st);
+    stage_mark(e, 7, st);
     if (e->profiling) e->profCount++;
     e->lastFrames = B;
 }
@@ -713,27 +690,6 @@ int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, s
     return copy_level(h, h->bufs.blur, frame, level, 0, dst, dst_step);
 }
 
-int orbfe_debug_score(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step) {
-    int rc = tap_check(h, frame, level);
-    if (rc) return rc;
-    // only the FAST domain [19,w-19) x [19,h-19) of the score map is ever written; the map holds
-    // u16 margins max(best - subTh, 0): convert back to `best`
-    const OrbfeLevelGeom& L = h->g.lv[level];
-    for (int y = 0; y < L.h; y++) memset(dst + (size_t)y * dst_step, 0, L.w);
-    if (L.nCols == 0 || L.w <= 38 || L.h <= 38) return ORBFE_OK;
-    const int dw = L.w - 38, dh = L.h - 38;
-    std::vector<uint16_t> tmp((size_t)dw * dh);
-    const uint16_t* base = h->bufs.score + (size_t)frame * h->g.pyrStride + L.off;
-    CK(cudaMemcpy2D(tmp.data(), (size_t)dw * 2, base + (size_t)(ORBFE_YOFF + 19) * L.pitch + ORBFE_SXOFF + 19,
-                    (size_t)L.pitch * 2, (size_t)dw * 2, dh, cudaMemcpyDeviceToHost));
-    for (int y = 0; y < dh; y++)
-        for (int x = 0; x < dw; x++) {
-            const int m = tmp[(size_t)y * dw + x];
-            dst[(size_t)(y + 19) * dst_step + 19 + x] = (uint8_t)(m ? m + h->g.subTh : 0);
-        }
-    return ORBFE_OK;
-}
-
 int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys, int capacity, int* n_out) {
     int rc = tap_check(h, frame, level);
     if (rc) return rc;
@@ -823,8 +779,8 @@ int orbfe_stage_ms(OrbfeExtractor* h, float* ms) {
     const int sets = std::min(h->profCount, (int)OrbfeExtractor::kProfSets);
     if (!h->profiling || sets == 0) return fail(ORBFE_ERR_INVALID, "no profiled call since orbfe_set_profiling(h, 1)");
     for (int k = 0; k < sets; k++) {
-        CK(cudaEventSynchronize(h->evStage[k][9]));
-        for (int i = 1; i <= 8; i++) {
+        CK(cudaEventSynchronize(h->evStage[k][ORBFE_NUM_STAGES - 1]));
+        for (int i = 1; i <= ORBFE_NUM_STAGES - 2; i++) {
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, h->evStage[k][i], h->evStage[k][i + 1]));
             ms[i] += t / sets;

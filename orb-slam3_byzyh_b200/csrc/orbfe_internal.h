@@ -11,7 +11,6 @@
 
 #define ORBFE_XOFF 32  // column of the ROI origin inside a padded row (keeps ROI rows 16B aligned)
 #define ORBFE_YOFF 19  // row of the ROI origin (EDGE_THRESHOLD)
-#define ORBFE_SXOFF 13 // score map only: column of ROI x=0 (FAST domain x=19 lands on column 32)
 #define ORBFE_FAST_BORDER 16  // minBorderX/Y = EDGE_THRESHOLD-3, ORBextractor.cc:1076-1079
 #define ORBFE_HALF_PATCH 15   // HALF_PATCH_SIZE, ORBextractor.cc:77
 
@@ -38,23 +37,17 @@ struct OrbfeLevelGeom {
     unsigned xtab, ytab; // offsets (in entries) of the resize tables of this level
     int mode;            // resize path: 0 = bilinear taps, 1 = exact 2x2 area, 2 = identity copy
     int fastTaps;        // mode 0: every aligned group of 4 destination columns taps <= 8 adjacent source bytes
-    int fastTileBase, fastTilesX, fastTilesY;   // tile numbering of the FAST score kernel
     int blurTileBase, blurTilesX, blurTilesY;   // tile numbering of the blur kernel
-    int nmsTileBase, nmsTilesX, nmsTilesY;      // tile numbering of the NMS kernel (128 x 128 px)
-    int bmPitch;         // words per row of the NMS bitmaps (multiple of 4)
-    unsigned bmMin, bmIni;  // word offsets of the two bitmaps inside one frame's bitmap slab
 };
 
 struct OrbfeFrameGeom {
     int nlevels, rows, cols;
     int iniTh, minTh;
-    unsigned long long pyrStride;   // bytes per frame in the pyramid / blurred / score slabs
+    unsigned long long pyrStride;   // bytes per frame in the pyramid / blurred slabs
     int cellsPerFrame;
     unsigned slotsPerFrame;
     int kpCapFrame;
-    int fastTiles, blurTiles, nmsTiles;
-    unsigned bmWordsPerFrame;
-    int subTh;                      // score map stores max(best - subTh, 0), subTh = max(min(iniTh, minTh), 1)
+    int blurTiles;
     int ocShared;                   // dynamic shared bytes of the octree kernel (0 = tables in global)
     int ocMmax;
     OrbfeLevelGeom lv[ORBFE_MAX_LEVELS];
@@ -78,25 +71,20 @@ struct OrbfeWork {
     float angle;       // degrees
 };
 
-#define ORBFE_FAST_TW 128
-#define ORBFE_FAST_TH 16
 #define ORBFE_BLUR_TW 120  // output columns per warp of the blur kernel
 #define ORBFE_BLUR_TH 32   // output rows per warp strip
 
 // Device buffers of one chunk of frames (all frame-major).
 // TMA descriptors of the padded pyramid levels of one chunk buffer set: level l as a 3-D byte tensor
-// (padded columns, padded rows, frames); k_fast_score fetches a whole staged tile with one instruction.
+// (padded columns, padded rows, frames); k_fast_cells fetches a whole cell (+ ring halo) with one instruction.
 struct OrbfeFastMaps {
     CUtensorMap m[ORBFE_MAX_LEVELS];
 };
 
 struct OrbfeChunkBufs {
-    OrbfeFastMaps fastMaps;   // boxes of k_fast_score (144 B x 22 rows)
+    OrbfeFastMaps fastMaps;   // per level: box = one FAST cell + halo (fast.cu)
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
-    uint16_t* score;     // [B][pyrStride] u16: FAST margin max(best - subTh, 0), column = ROI x + ORBFE_SXOFF
-    uint32_t* nmsBits;   // [B][bmWordsPerFrame] per level two bitmaps over the FAST domain: survives NMS (a) at
-                         //                      minThFAST, (b) at iniThFAST; bit (x-19) of row (y-19)
     uint32_t* slots;     // [B][slotsPerFrame] per-cell candidate slots (packed)
     int* cellCount;      // [B][cellsPerFrame]
     uint32_t* cand;      // [B][slotsPerFrame] per-level compacted candidates (emission order)
@@ -123,13 +111,10 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
                           cudaStream_t st, long long* launches, const OrbfeRectify* rect = nullptr);
 // Fills b.fastMaps for the buffer set (needs the driver's cuTensorMapEncodeTiled, resolved at run time).
 int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
-int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, int boxW, int boxH, OrbfeFastMaps& maps);
-void orbfe_launch_fast_score(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
-                             long long* launches);
-void orbfe_launch_fast_nms(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
-                           long long* launches);
-void orbfe_launch_fast_cells(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
-                             long long* launches);
+int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, const int* boxW, const int* boxH,
+                          OrbfeFastMaps& maps);
+// cv::FAST per cell + NMS + the minThFAST retry + ordered emission, one warp per cell (fast.cu)
+void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st, long long* launches);
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches);
 void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libORBfe_b200.so")
 
 OK, EMPTY_IMAGE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY = 0, -1, -2, -3, -4
 NUM_STAGES = 10
-STAGE_NAMES = ("h2d", "pyramid", "fast_score", "fast_nms", "fast_cells", "octree", "layout", "blur", "describe", "d2h")
+STAGE_NAMES = ("h2d", "pyramid", "fast", "octree", "layout", "blur", "describe", "d2h")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
                      ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])  # == cv::KeyPoint
@@ -92,7 +92,6 @@ _SIGS = {
     "orbfe_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
     "orbfe_debug_level_keypoints": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
     "orbfe_debug_blurred": (_i, [_vp, _i, _i, _vp, _sz]),
-    "orbfe_debug_score": (_i, [_vp, _i, _i, _vp, _sz]),
     "orbfe_debug_octree": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, C.POINTER(_i)]),
     "orbfe_set_profiling": (_i, [_vp, _i]),
     "orbfe_stage_ms": (_i, [_vp, _vp]),

@@ -163,8 +163,6 @@ class ORBextractor:
     def debug_blurred(self, level, frame=0):
         return self._img_tap(lib().orbfe_debug_blurred, level, frame)
 
-    def debug_score(self, level, frame=0):
-        return self._img_tap(lib().orbfe_debug_score, level, frame)
 
     def _list_tap(self, fn, level, frame):
         w, h = self.level_size(level)

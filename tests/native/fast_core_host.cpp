@@ -76,4 +76,37 @@ extern "C" void fast_core_margins_pair_raw(const uint8_t* img, int w, int h, int
             out[y * w + x + 1] = (uint8_t)(m >> 16);
         }
 }
+extern "C" void fast_core_margins_pair_raw_biased(const uint8_t* img, int w, int h, int sub, uint8_t* out) {
+    const int dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x + 1 < w - 3; x += 2) {
+            const uint8_t* p = img + y * w + x;
+            uint32_t r[16];
+            const uint32_t c = (uint32_t)p[0] | ((uint32_t)p[1] << 16);
+            for (int k = 0; k < 16; k++) {
+                const uint8_t* q = p + dx[k] + dy[k] * w;
+                r[k] = (uint32_t)q[0] | ((uint32_t)q[1] << 16);
+            }
+            const uint32_t m = fc_margin2_pair_raw_biased(r, c, (uint32_t)sub * 0x00010001u);
+            out[y * w + x] = (uint8_t)(m & 0xFFFF);
+            out[y * w + x + 1] = (uint8_t)(m >> 16);
+        }
+}
 extern "C" int fast_core_best_scalar72(const uint8_t* p) { return fc_best_scalar<72>(p); }
+
+// The dense early reject of k_fast_cells (fc_compass4), four pixels per call: out[y*w+x] = 1 where the pixel passes.
+extern "C" void fast_core_compass(const uint8_t* img, int w, int h, int t, uint8_t* out) {
+    const int u = t + 1;
+    const uint32_t uLow = (uint32_t)(u & 0x7F) * 0x01010101u, uTop = (u & 0x80) ? 0xFFFFFFFFu : 0u;
+    auto word = [&](int x, int y) {
+        uint32_t v = 0;
+        for (int i = 0; i < 4; i++) v |= (uint32_t)img[y * w + x + i] << (8 * i);
+        return v;
+    };
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x + 3 < w - 3; x += 4) {
+            const uint32_t f = fc_compass4(word(x, y), word(x, y - 3), word(x, y + 3), word(x - 3, y), word(x + 3, y), uLow, uTop);
+            for (int i = 0; i < 4; i++) out[y * w + x + i] = (uint8_t)((f >> (8 * i + 7)) & 1);
+        }
+}

@@ -54,3 +54,27 @@ def test_margin_map_equals_oracle(core, kind, sub):
     out4 = np.zeros((h, w), np.uint8)
     core.fast_core_margins_pair_raw(img.ctypes.data_as(C.c_void_p), w, h, sub, out4.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out4[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
+    out5 = np.zeros((h, w), np.uint8)   # the biased formulation k_fast_cells uses (no packed subtraction)
+    core.fast_core_margins_pair_raw_biased(img.ctypes.data_as(C.c_void_p), w, h, sub, out5.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out5[3:-3, 3:-3].astype(np.int64), exp[3:-3, 3:-3])
+
+
+@pytest.mark.parametrize("t", [0, 1, 7, 20, 126, 127, 128, 200, 254])
+def test_compass_reject_is_exact_and_necessary(core, t):
+    """fc_compass4 (the dense early reject of k_fast_cells): equals the plain statement of the test for every byte
+    value and threshold, and never rejects a pixel that cv::FAST calls a corner at that threshold."""
+    rng = np.random.default_rng(t)
+    h, w = 40, 3 + 4 * 14 + 3
+    imgs = [rng.integers(0, 256, (h, w)), np.where(rng.uniform(size=(h, w)) < 0.5, 255, 0),
+            128 + rng.integers(-2, 3, (h, w)) * (t + 1) // 2]
+    for img in imgs:
+        img = np.ascontiguousarray(np.clip(img, 0, 255), np.uint8)
+        out = np.zeros((h, w), np.uint8)
+        core.fast_core_compass(img.ctypes.data_as(C.c_void_p), w, h, t, out.ctypes.data_as(C.c_void_p))
+        I = img.astype(np.int64)
+        c = I[3:-3, 3:-3]
+        d = lambda dy, dx: np.abs(I[3 + dy:h - 3 + dy, 3 + dx:w - 3 + dx] - c) > t
+        exp = (d(-3, 0) | d(3, 0)) & (d(0, -3) | d(0, 3))
+        assert np.array_equal(out[3:-3, 3:-3].astype(bool), exp)
+        corners = O.fast(img, t, nms=False)
+        assert out[corners[:, 1], corners[:, 0]].all()

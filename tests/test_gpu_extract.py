@@ -202,8 +202,13 @@ def test_large_nfeatures_octree_tables(orbfe, nf):
 def test_unusual_thresholds_and_full_hd(orbfe):
     """minThFAST above iniThFAST, a zero threshold (cv::FAST then needs response > 0), and a 1920x1080 frame."""
     img = synth.synth_frame(480, 640, 31)
-    for (ini, mn) in [(7, 20), (20, 0), (0, 0), (255, 1), (12, 12)]:
+    for (ini, mn) in [(7, 20), (20, 0), (0, 0), (255, 1), (12, 12), (254, 127)]:
         _check_frame(orbfe.ORBextractor(800, 1.2, 8, ini, mn), O.Extractor(800, 1.2, 8, ini, mn), img, (0, 0))
+    # thresholds on both sides of 128 (the dense reject's byte compare handles the top bit separately) on a
+    # high-contrast frame, where such corners exist
+    hc = np.where(synth.noise_frame(480, 640, 33) > 127, 255, 0).astype(np.uint8)
+    for (ini, mn) in [(140, 126), (200, 128), (127, 100)]:
+        _check_frame(orbfe.ORBextractor(800, 1.2, 8, ini, mn), O.Extractor(800, 1.2, 8, ini, mn), hc, (0, 0))
     big = synth.synth_frame(1080, 1920, 32)
     _check_frame(orbfe.ORBextractor(4000), O.Extractor(4000), big, (0, 1000), stages=False)
 
@@ -233,11 +238,11 @@ def test_small_host_batches_graph_replay_and_chunking(orbfe):
 
 
 @pytest.mark.parametrize("per", [2, 3, 16, 1000])
-def test_fast_score_tiles_per_cta(orbfe, per, monkeypatch):
-    """k_fast_score walks several tiles per CTA with two TMA tile copies in flight (mbarrier phases alternate per
-    buffer); large batches pick 4-16 tiles per CTA on their own, here the count is forced on single frames, including
-    odd counts, a count that crosses pyramid levels and one CTA for the whole frame."""
-    monkeypatch.setenv("ORBFE_FAST_TILES_PER_CTA", str(per))
+def test_fast_cells_per_warp(orbfe, per, monkeypatch):
+    """k_fast_cells walks several cells per warp, one TMA box per cell on the warp's own mbarrier (the phase parity
+    alternates per cell); large batches pick 2-8 cells per warp on their own, here the count is forced on single
+    frames, including odd counts, a count that crosses pyramid levels and a handful of warps for the whole frame."""
+    monkeypatch.setenv("ORBFE_FAST_CELLS_PER_WARP", str(per))
     for (h, w, seed) in ((480, 752, 31), (241, 323, 32)):
         img = synth.synth_frame(h, w, seed)
         _check_frame(orbfe.ORBextractor(1000), O.Extractor(1000), img, (0, 1000), stages=True)
