@@ -44,13 +44,13 @@ constexpr int ROW0 = 3;               // staged row of the cell's first interior
 // so the box starts at the 16-byte boundary at or below the left ring pixel.
 constexpr int CSMAX = 18;
 constexpr int QROUND = 64;            // survivors scored per round (two per lane)
-constexpr int QCAP = QROUND + 256;    // queue capacity: < 64 left over + 8 px x 32 lanes of one dense step
-constexpr int CCAP = 512;             // corner list of the NMS fast path (more corners: dense walk over S)
+constexpr int QCAP = 704;             // survivor queue (a whole 36 x 38 cell of the bench frames fits: one flush per cell)
+constexpr int QFLUSH = QCAP - 256;    // flush before a dense step (8 px x 32 lanes) could overflow it
+constexpr int CCAP = 512;             // corner list (more corners than that: the NMS walks the whole interior instead)
 
 struct FastLayout {   // per-warp shared-memory carve-up, derived on the host from the geometry
-    int rawBytes;     // TMA box of the largest cell (multiple of 128); S has the same size and geometry
-    int bmWords;      // words per bitmap row
-    int bmRows;
+    int rawBytes;     // TMA box of the largest cell (multiple of 128)
+    int sBytes;       // score tile: the same geometry without the two outermost rows at either end
     int stride;       // bytes per warp
 };
 
@@ -58,19 +58,19 @@ struct FastLayout {   // per-warp shared-memory carve-up, derived on the host fr
 __host__ __device__ inline int fast_box_w(const OrbfeLevelGeom& L) { return (CSMAX + L.wCell + 3 + 15) & ~15; }
 __host__ __device__ inline int fast_box_h(const OrbfeLevelGeom& L) { return L.hCell + 6; }
 
-__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+__device__ __forceinline__ int warp_incl_scan(int v) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
+    for (int o = 1; o < 32; o <<= 1)   // SHFL.UP with predicate out + predicated add: two instructions per step
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.s32 %0, %0, t;\n\t}"
+                     : "+r"(v) : "r"(o));
     return v;
 }
 
 // Scores up to 64 queued survivors Q[base .. base+n): lane takes entries base+lane and base+32+lane, one per 16-bit
-// half of the packed network.  An entry is the byte offset of the pixel inside the staged tile.
+// half of the packed network.  An entry is the byte offset of the pixel inside the staged tile; Sb is the score tile
+// addressed by the same offsets.  Corners (best > t) are appended to C in queue order.
 template <int P>
-__device__ __forceinline__ void fast_score_round(const uint8_t* __restrict__ raw, uint8_t* __restrict__ S,
+__device__ __forceinline__ void fast_score_round(const uint8_t* __restrict__ raw, uint8_t* __restrict__ Sb,
                                                  const uint16_t* __restrict__ Q, int base, int n, int t,
                                                  uint16_t* __restrict__ C, int& nC, int lane) {
     const bool v0 = lane < n, v1 = lane + 32 < n;
@@ -88,8 +88,9 @@ __device__ __forceinline__ void fast_score_round(const uint8_t* __restrict__ raw
     const uint32_t m = fc_margin2_pair_raw_biased(r, c2, (uint32_t)t * 0x00010001u);   // per half: max(best - t, 0)
     const int m0 = (int)(m & 0xFFFFu), m1 = (int)(m >> 16);
     const bool k0 = v0 && m0 > 0, k1 = v1 && m1 > 0;
-    if (k0) S[e0] = (uint8_t)(m0 + t);
-    if (k1) S[e1] = (uint8_t)(m1 + t);
+    if (k0) Sb[e0] = (uint8_t)(m0 + t);
+    if (k1) Sb[e1] = (uint8_t)(m1 + t);
+    // queue order = entries base .. base+31 (first halves) then base+32 .. base+63 (second halves)
     const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
     const unsigned lt = (1u << lane) - 1u;
     const int q0 = nC + __popc(b0 & lt), q1 = nC + __popc(b0) + __popc(b1 & lt);
@@ -98,28 +99,60 @@ __device__ __forceinline__ void fast_score_round(const uint8_t* __restrict__ raw
     nC += __popc(b0) + __popc(b1);
 }
 
-// cv::FAST(cell, t, nms = true) up to the NMS bitmap: dense reject -> queue -> score -> corner list -> NMS.
-// S and bm are zero on entry.  Returns nothing; the kept corners are the set bits of bm.
+// Scores the queue front to back in rounds of 64.  Not final: the < 64 entries left over move to the front (they
+// keep their order) and their number is returned; final: they get a last, partly filled round.
 template <int P>
-__device__ __forceinline__ void fast_cell_pass(const uint8_t* __restrict__ raw, uint8_t* __restrict__ S,
-                                               uint16_t* __restrict__ Q, uint16_t* __restrict__ C,
-                                               uint32_t* __restrict__ bm, int bmW, int cs, int nbx, int nby, int t, int lane) {
-    if (t >= 255) return;   // best <= 255: no pixel is a corner
-    const int u = t + 1;    // |ring - centre| >= u
+__device__ __forceinline__ int fast_flush(const uint8_t* __restrict__ raw, uint8_t* __restrict__ Sb, uint16_t* __restrict__ Q,
+                                          int tail, bool final, int t, uint16_t* __restrict__ C, int& nC, int lane) {
+    int base = 0;
+    for (; base + QROUND <= tail; base += QROUND) fast_score_round<P>(raw, Sb, Q, base, QROUND, t, C, nC, lane);
+    const int left = tail - base;
+    if (final) {
+        if (left > 0) fast_score_round<P>(raw, Sb, Q, base, left, t, C, nC, lane);
+        return 0;
+    }
+    if (base > 0 && left > 0) {
+        const uint16_t a = lane < left ? Q[base + lane] : (uint16_t)0, b = lane + 32 < left ? Q[base + 32 + lane] : (uint16_t)0;
+        __syncwarp();
+        if (lane < left) Q[lane] = a;
+        if (lane + 32 < left) Q[32 + lane] = b;
+    }
+    return left;
+}
+
+// One corner against its eight neighbours in the score tile (cv::FAST keeps it iff it is strictly greater).
+template <int P>
+__device__ __forceinline__ bool fast_is_max(const uint8_t* __restrict__ s, int v) {
+    const int a = max(max((int)s[-1], (int)s[1]), max((int)s[-P], (int)s[P]));
+    const int b = max(max((int)s[-P - 1], (int)s[-P + 1]), max((int)s[P - 1], (int)s[P + 1]));
+    return v > max(a, b);
+}
+
+// cv::FAST(cell, t, nms = true): dense reject -> queue -> score -> corner list -> NMS + ordered emission into `out`.
+// The score tile is zero on entry.  Returns the number of keypoints.
+template <int P>
+__device__ __forceinline__ int fast_cell_pass(const uint8_t* __restrict__ raw, uint8_t* __restrict__ Sb,
+                                              uint16_t* __restrict__ Q, uint16_t* __restrict__ C, int cs, int nbx, int nby,
+                                              int t, int x0, int y0, uint32_t* __restrict__ out, int cellCap, int lane) {
+    if (t >= 255) return 0;   // best <= 255: no pixel is a corner
+    const int u = t + 1;      // |ring - centre| >= u
     const uint32_t uLow = (uint32_t)(u & 0x7F) * 0x01010101u, uTop = (u & 0x80) ? 0xFFFFFFFFu : 0u;
-    // a lane takes an aligned octet of staged columns (one LDS.64); the interior is the columns [cs, cs + nbx)
+    // A lane takes an aligned octet of staged columns (one LDS.64); the interior is the columns [cs, cs + nbx).  Lane
+    // = (row of the step, octet of the row): the lane's column, and with it the masks of the pixels outside the
+    // interior, stay fixed while the warp walks down the cell `rps` rows per step; queue order is row-major.
     const int a0 = cs & ~7, lo0 = cs - a0;
-    const int opr = (lo0 + nbx + 7) >> 3;                // octets per interior row
-    const int items = nby * opr;
-    const uint32_t rcp = opr > 1 ? 0xFFFFFFFFu / (uint32_t)opr + 1u : 0u;   // item / opr == umulhi(item, rcp) (item * opr < 2^32)
-    int n = 0, nC = 0;
-    for (int it = 0; it < items; it += 32) {
-        const int item = it + lane;
-        const bool valid = item < items;
-        const int ci = valid ? item : 0;
-        const int row = opr > 1 ? (int)__umulhi((uint32_t)ci, rcp) : ci;
-        const int oc = ci - row * opr;
-        const int e = (row + ROW0) * P + a0 + 8 * oc;     // tile offset of the octet's first pixel (8-byte aligned)
+    const int opr = (lo0 + nbx + 7) >> 3;                // octets per interior row (<= 11)
+    const int rps = 32 / opr;                            // rows per step
+    const int r = lane / opr, oc = lane - r * opr;
+    const bool active = r < rps;
+    const int rem = lo0 + nbx - 8 * oc, lo = max(lo0 - 8 * oc, 0);
+    const uint32_t mk0 = active ? __funnelshift_rc(0x80808080u, 0u, 8 * max(4 - rem, 0)) & __funnelshift_lc(0u, 0x80808080u, 8 * min(lo, 4)) : 0u;
+    const uint32_t mk1 = active ? __funnelshift_rc(0x80808080u, 0u, 8 * max(8 - rem, 0)) & __funnelshift_lc(0u, 0x80808080u, 8 * max(lo - 4, 0)) : 0u;
+    int e = ((active ? r : 0) + ROW0) * P + a0 + 8 * oc;  // tile offset of the octet's first pixel (8-byte aligned)
+    int tail = 0, nC = 0;
+    for (int row0 = 0; row0 < nby; row0 += rps, e += rps * P) {
+        // rows past the cell's last one read the rows below the tile (the score tile follows it): masked
+        const bool rowok = row0 + r < nby;
         const uint2 c = *reinterpret_cast<const uint2*>(raw + e);
         const uint2 no = *reinterpret_cast<const uint2*>(raw + e - 3 * P);
         const uint2 so = *reinterpret_cast<const uint2*>(raw + e + 3 * P);
@@ -127,118 +160,87 @@ __device__ __forceinline__ void fast_cell_pass(const uint8_t* __restrict__ raw, 
         const uint32_t wp = *reinterpret_cast<const uint32_t*>(raw + e + 8);
         uint32_t f0 = fc_compass4(c.x, no.x, so.x, __funnelshift_r(wm, c.x, 8), __funnelshift_r(c.x, c.y, 24), uLow, uTop);
         uint32_t f1 = fc_compass4(c.y, no.y, so.y, __funnelshift_r(c.x, c.y, 8), __funnelshift_r(c.y, wp, 24), uLow, uTop);
-        // pixels left of the interior's first / beyond its last column (and the lanes beyond the last item) never survive
-        const int rem = valid ? lo0 + nbx - 8 * oc : 0, lo = max(lo0 - 8 * oc, 0);
-        f0 &= __funnelshift_rc(0x80808080u, 0u, 8 * max(4 - rem, 0)) & __funnelshift_lc(0u, 0x80808080u, 8 * min(lo, 4));
-        f1 &= __funnelshift_rc(0x80808080u, 0u, 8 * max(8 - rem, 0)) & __funnelshift_lc(0u, 0x80808080u, 8 * max(lo - 4, 0));
-        const int cnt = __popc(f0) + __popc(f1);
-        const int incl = warp_incl_scan(cnt, lane);
-        int o = n + incl - cnt;
+        f0 &= rowok ? mk0 : 0u;
+        f1 &= rowok ? mk1 : 0u;
+        const int cnt = __popc(f0 | (f1 >> 1));          // bits 7 and 6 of every byte
+        const int incl = warp_incl_scan(cnt);
+        uint16_t* q = Q + tail + incl - cnt;
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (f0 & (0x80u << (8 * j))) Q[o++] = (uint16_t)(e + j);
+            if (f0 & (0x80u << (8 * j))) *q++ = (uint16_t)(e + j);
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (f1 & (0x80u << (8 * j))) Q[o++] = (uint16_t)(e + 4 + j);
-        n += __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        while (n >= QROUND) {
-            n -= QROUND;
-            fast_score_round<P>(raw, S, Q, n, QROUND, t, C, nC, lane);
+            if (f1 & (0x80u << (8 * j))) *q++ = (uint16_t)(e + 4 + j);
+        tail += __shfl_sync(0xffffffffu, incl, 31);
+        if (tail > QFLUSH) {
+            __syncwarp();
+            tail = fast_flush<P>(raw, Sb, Q, tail, false, t, C, nC, lane);
+            __syncwarp();
         }
-        __syncwarp();   // the round's reads of Q are done before the next step overwrites the slots
     }
-    if (n > 0) fast_score_round<P>(raw, S, Q, 0, n, t, C, nC, lane);
     __syncwarp();
-    // ---- 3x3 non-max suppression: keep a corner iff its score is strictly greater than its 8 neighbours (S is 0
-    // outside the cell interior, which is cv::FAST's rule for a cell-sized image) ----
+    fast_flush<P>(raw, Sb, Q, tail, true, t, C, nC, lane);
+    __syncwarp();
+    // ---- 3x3 non-max suppression + emission.  The score tile is 0 outside the cell interior, which is cv::FAST's
+    // rule for a cell-sized image; C is in row-major order (the queue's), so a ballot ranks the kept corners in
+    // cv::FAST's emission order. ----
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
     if (nC <= CCAP) {
-        for (int i = lane; i < nC; i += 32) {
-            const int e = C[i];
-            const uint8_t* s = S + e;
-            const int v = s[0];
-            const int a = max(max((int)s[-1], (int)s[1]), max((int)s[-P], (int)s[P]));
-            const int b = max(max((int)s[-P - 1], (int)s[-P + 1]), max((int)s[P - 1], (int)s[P + 1]));
-            if (v > max(a, b)) {
-                const int row = e / P, col = e - row * P - cs;
-                atomicOr(&bm[(row - ROW0) * bmW + (col >> 5)], 1u << (col & 31));
-            }
-        }
-    } else {   // more corners than the list holds (noise-like cells): walk the whole interior
-        const int npx = nbx * nby;
-        for (int i = lane; i < npx; i += 32) {
-            const int row = i / nbx, col = i - row * nbx;
-            const uint8_t* s = S + (row + ROW0) * P + cs + col;
-            const int v = s[0];
-            if (v == 0) continue;
-            const int a = max(max((int)s[-1], (int)s[1]), max((int)s[-P], (int)s[P]));
-            const int b = max(max((int)s[-P - 1], (int)s[-P + 1]), max((int)s[P - 1], (int)s[P + 1]));
-            if (v > max(a, b)) atomicOr(&bm[row * bmW + (col >> 5)], 1u << (col & 31));
-        }
-    }
-    __syncwarp();
-}
-
-// Ordered emission of the bitmap (lane = row, rows in blocks of 32): returns the number of kept corners.
-template <int P>
-__device__ __forceinline__ int fast_cell_emit(const uint8_t* __restrict__ S, const uint32_t* __restrict__ bm, int bmW, int cs,
-                                              int nby, int x0, int y0, uint32_t* __restrict__ out, int cellCap, int lane) {
-    int base = 0;
-    for (int rb = 0; rb < nby; rb += 32) {
-        const int row = rb + lane;
-        uint32_t w[3] = {0u, 0u, 0u};
-        if (row < nby) {
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-                if (j < bmW) w[j] = bm[row * bmW + j];
-        }
-        const int cnt = __popc(w[0]) + __popc(w[1]) + __popc(w[2]);
-        const int incl = warp_incl_scan(cnt, lane);
-        int pos = base + incl - cnt;
-        base += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            uint32_t m = w[j];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                const int x = 32 * j + b;
-                const int best = S[(row + ROW0) * P + cs + x];
+        for (int i0 = 0; i0 < nC; i0 += 32) {
+            const bool ok = i0 + lane < nC;
+            const int ec = ok ? (int)C[i0 + lane] : ROW0 * P + 8;
+            const int v = Sb[ec];
+            const bool keep = ok && fast_is_max<P>(Sb + ec, v);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            const int pos = count + __popc(b & lt);
+            if (keep && pos < cellCap) {
+                const int row = ec / P, col = ec - row * P - cs;
                 // window coordinates (origin = minBorder 16): ROI - 16; response = best - 1
-                if (pos < cellCap) out[pos] = OC_PACK(x0 + x - ORBFE_FAST_BORDER, y0 + row - ORBFE_FAST_BORDER, best - 1);
-                pos++;
+                out[pos] = OC_PACK(x0 + col - ORBFE_FAST_BORDER, y0 + row - ROW0 - ORBFE_FAST_BORDER, v - 1);
             }
+            count += __popc(b);
+        }
+    } else {   // more corners than the list holds (noise-like cells): walk the whole interior, row-major
+        const int npx = nbx * nby;
+        for (int i0 = 0; i0 < npx; i0 += 32) {
+            const int i = min(i0 + lane, npx - 1);
+            const int row = i / nbx, col = i - row * nbx;
+            const uint8_t* s = Sb + (row + ROW0) * P + cs + col;
+            const int v = s[0];
+            const bool keep = i0 + lane < npx && v > 0 && fast_is_max<P>(s, v);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            const int pos = count + __popc(b & lt);
+            if (keep && pos < cellCap) out[pos] = OC_PACK(x0 + col - ORBFE_FAST_BORDER, y0 + row - ORBFE_FAST_BORDER, v - 1);
+            count += __popc(b);
         }
     }
-    return base;
+    return count;
 }
 
-__device__ __forceinline__ void fast_zero(uint8_t* S, int bytes16, uint32_t* bm, int bmWordsTotal, int lane) {
+__device__ __forceinline__ void fast_zero(uint8_t* S, int bytes16, int lane) {
     uint4* s4 = reinterpret_cast<uint4*>(S);
     for (int i = lane; i < bytes16; i += 32) s4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = lane; i < bmWordsTotal; i += 32) bm[i] = 0u;
 }
 
 // The reference's per-cell body (:1135-1165) on a staged cell.  Returns the number of candidates.
 template <int P>
 __device__ __forceinline__ int fast_cell(const uint8_t* __restrict__ raw, uint8_t* __restrict__ S, uint16_t* __restrict__ Q,
-                                         uint16_t* __restrict__ C, uint32_t* __restrict__ bm, int bmW, int boxH, int cs, int nbx,
-                                         int nby, int x0, int y0, int iniTh, int minTh, uint32_t* __restrict__ out, int cellCap,
-                                         int lane) {
+                                         uint16_t* __restrict__ C, int boxH, int cs, int nbx, int nby, int x0, int y0,
+                                         int iniTh, int minTh, uint32_t* __restrict__ out, int cellCap, int lane) {
     // cv::FAST's response is best - 1 and its NMS compares responses, so a corner with best == 1 (possible only at
     // threshold 0) scores 0 like a non-corner: it never wins and never blocks.  Threshold 0 therefore acts as 1.
     iniTh = max(iniTh, 1);
     minTh = max(minTh, 1);
-    fast_cell_pass<P>(raw, S, Q, C, bm, bmW, cs, nbx, nby, iniTh, lane);
-    int total = fast_cell_emit<P>(S, bm, bmW, cs, nby, x0, y0, out, cellCap, lane);
+    uint8_t* Sb = S - 2 * P;   // the score tile starts at staged row 2: same offsets as the staged tile
+    int total = fast_cell_pass<P>(raw, Sb, Q, C, cs, nbx, nby, iniTh, x0, y0, out, cellCap, lane);
     // vKeysCell.empty() -> FAST(minThFAST) (:1141-1148).  With minThFAST >= iniThFAST the retry cannot find anything:
     // its corners are a subset and the NMS outcome of a corner does not depend on the threshold.
     if (total == 0 && minTh < iniTh) {
         __syncwarp();
-        fast_zero(S, P * boxH / 16, bm, bmW * nby, lane);
+        fast_zero(S, P * (boxH - 4) / 16, lane);
         __syncwarp();
-        fast_cell_pass<P>(raw, S, Q, C, bm, bmW, cs, nbx, nby, minTh, lane);
-        total = fast_cell_emit<P>(S, bm, bmW, cs, nby, x0, y0, out, cellCap, lane);
+        total = fast_cell_pass<P>(raw, Sb, Q, C, cs, nbx, nby, minTh, x0, y0, out, cellCap, lane);
     }
     return total;
 }
@@ -250,10 +252,9 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t* raw = fsm + (size_t)wid * lay.stride;
     uint8_t* S = raw + lay.rawBytes;
-    uint16_t* Q = reinterpret_cast<uint16_t*>(S + lay.rawBytes);
+    uint16_t* Q = reinterpret_cast<uint16_t*>(S + lay.sBytes);
     uint16_t* C = Q + QCAP;
-    uint32_t* bm = reinterpret_cast<uint32_t*>(C + CCAP);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(bm + lay.bmRows * lay.bmWords);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(C + CCAP);
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
@@ -287,18 +288,18 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
             mbar_expect_tx(bar, (uint32_t)(bw * bh));
             tma_tile_g2s(raw, &maps.m[l], xs, ORBFE_YOFF + y0 - ROW0, frame, bar);
         }
-        fast_zero(S, bw * bh / 16, bm, lay.bmWords * nby, lane);   // under the copy
+        fast_zero(S, bw * (bh - 4) / 16, lane);   // under the copy
         mbar_wait(bar, parity);
         parity ^= 1u;
         __syncwarp();
         uint32_t* out = slots + (size_t)frame * g.slotsPerFrame + L.slotBase + (size_t)ci * L.cellCap;
         int total;
         if (bw == 64)
-            total = fast_cell<64>(raw, S, Q, C, bm, lay.bmWords, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
+            total = fast_cell<64>(raw, S, Q, C, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
         else if (bw == 80)
-            total = fast_cell<80>(raw, S, Q, C, bm, lay.bmWords, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
+            total = fast_cell<80>(raw, S, Q, C, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
         else
-            total = fast_cell<96>(raw, S, Q, C, bm, lay.bmWords, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
+            total = fast_cell<96>(raw, S, Q, C, bh, cs, nbx, nby, x0, y0, g.iniTh, g.minTh, out, L.cellCap, lane);
         if (lane == 0) *cnt = min(total, L.cellCap);
         __syncwarp();
     }
@@ -306,18 +307,16 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
 
 FastLayout fast_layout(const OrbfeFrameGeom& g) {
     FastLayout lay = {};
-    int raw = 128, wmax = 1, hmax = 1;
+    int raw = 128, sb = 128;
     for (int l = 0; l < g.nlevels; l++) {
         const OrbfeLevelGeom& L = g.lv[l];
         if (L.nCols == 0) continue;
         raw = std::max(raw, fast_box_w(L) * fast_box_h(L));
-        wmax = std::max(wmax, L.wCell);
-        hmax = std::max(hmax, L.hCell);
+        sb = std::max(sb, fast_box_w(L) * (fast_box_h(L) - 4));
     }
     lay.rawBytes = (raw + 127) & ~127;
-    lay.bmWords = (wmax + 31) / 32;
-    lay.bmRows = (hmax + 1) & ~1;   // even: the mbarrier behind the bitmap stays 8-byte aligned
-    lay.stride = (2 * lay.rawBytes + 2 * QCAP + 2 * CCAP + 4 * lay.bmRows * lay.bmWords + 16 + 127) & ~127;
+    lay.sBytes = (sb + 15) & ~15;
+    lay.stride = (lay.rawBytes + lay.sBytes + 2 * QCAP + 2 * CCAP + 16 + 127) & ~127;
     return lay;
 }
 
