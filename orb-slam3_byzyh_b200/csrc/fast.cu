@@ -130,7 +130,7 @@ __device__ __forceinline__ bool fast_is_max(const uint8_t* __restrict__ s, int v
 
 // cv::FAST(cell, t, nms = true): dense reject -> queue -> score -> corner list -> NMS + ordered emission into `out`.
 // The score tile is zero on entry.  Returns the number of keypoints.
-template <int P>
+template <int P, bool SMALLU>
 __device__ __forceinline__ int fast_cell_pass(const uint8_t* __restrict__ raw, uint8_t* __restrict__ Sb,
                                               uint16_t* __restrict__ Q, uint16_t* __restrict__ C, int cs, int nbx, int nby,
                                               int t, int x0, int y0, uint32_t* __restrict__ out, int cellCap, int lane) {
@@ -158,8 +158,8 @@ __device__ __forceinline__ int fast_cell_pass(const uint8_t* __restrict__ raw, u
         const uint2 so = *reinterpret_cast<const uint2*>(raw + e + 3 * P);
         const uint32_t wm = *reinterpret_cast<const uint32_t*>(raw + e - 4);
         const uint32_t wp = *reinterpret_cast<const uint32_t*>(raw + e + 8);
-        uint32_t f0 = fc_compass4(c.x, no.x, so.x, __funnelshift_r(wm, c.x, 8), __funnelshift_r(c.x, c.y, 24), uLow, uTop);
-        uint32_t f1 = fc_compass4(c.y, no.y, so.y, __funnelshift_r(c.x, c.y, 8), __funnelshift_r(c.y, wp, 24), uLow, uTop);
+        uint32_t f0 = fc_compass4<SMALLU>(c.x, no.x, so.x, __funnelshift_r(wm, c.x, 8), __funnelshift_r(c.x, c.y, 24), uLow, uTop);
+        uint32_t f1 = fc_compass4<SMALLU>(c.y, no.y, so.y, __funnelshift_r(c.x, c.y, 8), __funnelshift_r(c.y, wp, 24), uLow, uTop);
         f0 &= rowok ? mk0 : 0u;
         f1 &= rowok ? mk1 : 0u;
         const int cnt = __popc(f0 | (f1 >> 1));          // bits 7 and 6 of every byte
@@ -233,21 +233,25 @@ __device__ __forceinline__ int fast_cell(const uint8_t* __restrict__ raw, uint8_
     iniTh = max(iniTh, 1);
     minTh = max(minTh, 1);
     uint8_t* Sb = S - 2 * P;   // the score tile starts at staged row 2: same offsets as the staged tile
-    int total = fast_cell_pass<P>(raw, Sb, Q, C, cs, nbx, nby, iniTh, x0, y0, out, cellCap, lane);
+    // thresholds below 127 (all the reference ever uses) take the cheaper byte compare of the dense reject
+    int total = iniTh < 127 ? fast_cell_pass<P, true>(raw, Sb, Q, C, cs, nbx, nby, iniTh, x0, y0, out, cellCap, lane)
+                            : fast_cell_pass<P, false>(raw, Sb, Q, C, cs, nbx, nby, iniTh, x0, y0, out, cellCap, lane);
     // vKeysCell.empty() -> FAST(minThFAST) (:1141-1148).  With minThFAST >= iniThFAST the retry cannot find anything:
     // its corners are a subset and the NMS outcome of a corner does not depend on the threshold.
     if (total == 0 && minTh < iniTh) {
         __syncwarp();
         fast_zero(S, P * (boxH - 4) / 16, lane);
         __syncwarp();
-        total = fast_cell_pass<P>(raw, Sb, Q, C, cs, nbx, nby, minTh, x0, y0, out, cellCap, lane);
+        total = minTh < 127 ? fast_cell_pass<P, true>(raw, Sb, Q, C, cs, nbx, nby, minTh, x0, y0, out, cellCap, lane)
+                            : fast_cell_pass<P, false>(raw, Sb, Q, C, cs, nbx, nby, minTh, x0, y0, out, cellCap, lane);
     }
     return total;
 }
 
 __global__ void __launch_bounds__(32 * FW, 3)
 k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ OrbfeFastMaps maps,
-             uint32_t* __restrict__ slots, int* __restrict__ cellCount, const FastLayout lay, int cellsPerWarp) {
+             const OrbfeFastCell* __restrict__ cells, uint32_t* __restrict__ slots, int* __restrict__ cellCount,
+             const FastLayout lay, int cellsPerWarp) {
     extern __shared__ __align__(128) uint8_t fsm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint8_t* raw = fsm + (size_t)wid * lay.stride;
@@ -263,22 +267,18 @@ k_fast_cells(const __grid_constant__ OrbfeFrameGeom g, const __grid_constant__ O
     const int frame = blockIdx.y;
     const int c0 = (blockIdx.x * FW + wid) * cellsPerWarp, c1 = min(c0 + cellsPerWarp, g.cellsPerFrame);
     uint32_t parity = 0;
-    int l = 0;
     for (int cell = c0; cell < c1; cell++) {
-        while (l + 1 < g.nlevels && cell >= g.lv[l + 1].cellBase) l++;
-        const OrbfeLevelGeom& L = g.lv[l];
-        const int ci = cell - L.cellBase;
-        const int i = ci / L.nCols, j = ci - i * L.nCols;
+        // cell geometry (ORBextractor.cc:1098-1132), derived once per geometry on the host (orbfe_fast_cell_table)
+        const OrbfeFastCell fc = cells[cell];
         int* cnt = cellCount + (size_t)frame * g.cellsPerFrame + cell;
-        // cell geometry, ORBextractor.cc:1098-1132
-        const int iniY = ORBFE_FAST_BORDER + i * L.hCell, iniX = ORBFE_FAST_BORDER + j * L.wCell;
-        const int maxY = min(iniY + L.hCell + 6, L.maxBY), maxX = min(iniX + L.wCell + 6, L.maxBX);
-        if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || maxX - iniX < 7 || maxY - iniY < 7) {
+        if (fc.nbx == 0) {   // the reference skips the cell, or cv::FAST has no interior pixel in it
             if (lane == 0) *cnt = 0;
             continue;
         }
-        const int x0 = iniX + 3, y0 = iniY + 3;                       // FAST interior (ROI coordinates)
-        const int nbx = maxX - 3 - x0, nby = maxY - 3 - y0;
+        const int l = fc.level;
+        const OrbfeLevelGeom& L = g.lv[l];
+        const int ci = cell - L.cellBase;
+        const int x0 = fc.x0, y0 = fc.y0, nbx = fc.nbx, nby = fc.nby;   // FAST interior (ROI coordinates)
         const int bw = fast_box_w(L), bh = fast_box_h(L);
         const int xs = (ORBFE_XOFF + x0 - 3) & ~15, cs = ORBFE_XOFF + x0 - xs;   // box origin (padded column), staged column of x0
         if (lane == 0) {
@@ -366,14 +366,36 @@ int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames)
     return orbfe_make_level_maps(g, b.pyr, frames, bw, bh, b.fastMaps);
 }
 
-void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st, long long* launches) {
+// The reference's cell loop (:1098-1132) on the host: per cell the FAST interior [x0, x0 + nbx) x [y0, y0 + nby) in ROI
+// coordinates, nbx == 0 where the reference skips the cell (:1108, :1125) or the cell image is narrower than FAST's 7 px.
+void orbfe_fast_cell_table(const OrbfeFrameGeom& g, std::vector<OrbfeFastCell>& out) {
+    out.assign((size_t)std::max(g.cellsPerFrame, 1), OrbfeFastCell{0, 0, 0, 0, 0, 0});
+    for (int l = 0; l < g.nlevels; l++) {
+        const OrbfeLevelGeom& L = g.lv[l];
+        for (int i = 0; i < L.nRows; i++)
+            for (int j = 0; j < L.nCols; j++) {
+                OrbfeFastCell& c = out[(size_t)L.cellBase + (size_t)i * L.nCols + j];
+                c.level = (uint8_t)l;
+                const int iniY = ORBFE_FAST_BORDER + i * L.hCell, iniX = ORBFE_FAST_BORDER + j * L.wCell;
+                const int maxY = std::min(iniY + L.hCell + 6, L.maxBY), maxX = std::min(iniX + L.wCell + 6, L.maxBX);
+                if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || maxX - iniX < 7 || maxY - iniY < 7) continue;
+                c.x0 = (uint16_t)(iniX + 3);
+                c.y0 = (uint16_t)(iniY + 3);
+                c.nbx = (uint8_t)(maxX - iniX - 6);
+                c.nby = (uint8_t)(maxY - iniY - 6);
+            }
+    }
+}
+
+void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeFastCell* cells, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                       long long* launches) {
     if (g.cellsPerFrame <= 0) return;
     const FastLayout lay = fast_layout(g);
     // several cells per warp once the grid fills the machine many times over; single frames keep one cell per warp
-    const long long cells = (long long)g.cellsPerFrame * B;
-    int per = cells >= 148LL * 28 * 64 ? 8 : cells >= 148LL * 28 * 16 ? 4 : cells >= 148LL * 28 * 4 ? 2 : 1;
+    const long long ncell = (long long)g.cellsPerFrame * B;
+    int per = ncell >= 148LL * 28 * 64 ? 8 : ncell >= 148LL * 28 * 16 ? 4 : ncell >= 148LL * 28 * 4 ? 2 : 1;
     if (const char* ev = getenv("ORBFE_FAST_CELLS_PER_WARP")) per = std::max(1, atoi(ev));
     const int gx = (g.cellsPerFrame + FW * per - 1) / (FW * per);
-    k_fast_cells<<<dim3(gx, B), 32 * FW, FW * lay.stride, st>>>(g, b.fastMaps, b.slots, b.cellCount, lay, per);
+    k_fast_cells<<<dim3(gx, B), 32 * FW, FW * lay.stride, st>>>(g, b.fastMaps, cells, b.slots, b.cellCount, lay, per);
     ++*launches;
 }

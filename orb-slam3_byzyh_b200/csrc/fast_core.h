@@ -216,8 +216,18 @@ static FC_HD uint32_t fc_ge4(uint32_t a, uint32_t uLow, uint32_t uTop) {
     return (a & ~uTop) | (~(a ^ uTop) & z);
 }
 // 0x80 in every byte whose pixel passes the compass test (c = four centres, n / s / w / e = the ring pixels
-// 3 px above / below / left / right of each of them).
+// 3 px above / below / left / right of each of them).  SMALLU: u < 128 is known (thresholds up to 126, i.e. every
+// configuration the reference ships): bit 7 of a >= u is then a | z, the OR folds into the pair combination and the
+// byte compare costs two instructions instead of three.
+template <bool SMALLU>
 static FC_HD uint32_t fc_compass4(uint32_t c, uint32_t n, uint32_t s, uint32_t w, uint32_t e, uint32_t uLow, uint32_t uTop) {
+    if (SMALLU) {
+        const uint32_t an = fc_absdiff4(n, c), as = fc_absdiff4(s, c), aw = fc_absdiff4(w, c), ae = fc_absdiff4(e, c);
+        const uint32_t H = 0x80808080u;
+        const uint32_t v = an | as | ((an | H) - uLow) | ((as | H) - uLow);
+        const uint32_t h = aw | ae | ((aw | H) - uLow) | ((ae | H) - uLow);
+        return v & h & H;
+    }
     const uint32_t v = fc_ge4(fc_absdiff4(n, c), uLow, uTop) | fc_ge4(fc_absdiff4(s, c), uLow, uTop);
     const uint32_t h = fc_ge4(fc_absdiff4(w, c), uLow, uTop) | fc_ge4(fc_absdiff4(e, c), uLow, uTop);
     return v & h & 0x80808080u;

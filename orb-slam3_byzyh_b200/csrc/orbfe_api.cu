@@ -205,6 +205,15 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
         CK(cudaMalloc(&e->d_taps, taps.size() * sizeof(OrbfeTap)));
         CK(cudaMemcpy(e->d_taps, taps.data(), taps.size() * sizeof(OrbfeTap), cudaMemcpyHostToDevice));
     }
+    if (e->d_cells) { cudaFree(e->d_cells); e->d_cells = nullptr; }
+    {
+        std::vector<OrbfeFastCell> cells;
+        orbfe_fast_cell_table(g, cells);
+        CK(cudaMalloc(&e->d_cells, cells.size() * sizeof(OrbfeFastCell)));
+        CK(cudaMemcpy(e->d_cells, cells.data(), cells.size() * sizeof(OrbfeFastCell), cudaMemcpyHostToDevice));
+    }
+    // a captured per-frame graph holds the old tap / cell tables and chunk buffers: it dies with them
+    if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
     if (e->slab) { cudaFree(e->slab); e->slab = nullptr; }
     if (e->slab2) { cudaFree(e->slab2); e->slab2 = nullptr; }
     e->chunkCap = 0;
@@ -221,6 +230,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
 int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*& slab, int& cap) {
     if (frames <= cap) return ORBFE_OK;
     if (int qrc = quiesce(e)) return qrc;
+    if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }   // it replays the old buffers
     if (slab) { cudaFree(slab); slab = nullptr; cap = 0; }
     const OrbfeFrameGeom& g = e->g;
     const size_t B = (size_t)frames;
@@ -283,7 +293,7 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
     stage_mark(e, 1, st);
     orbfe_launch_pyramid(g, e->d_taps, d_images, step, frameStride, bufs, B, st, &e->launches, e->d_mapx ? &rect : nullptr);
     stage_mark(e, 2, st);
-    orbfe_launch_fast(g, bufs, B, st, &e->launches);
+    orbfe_launch_fast(g, e->d_cells, bufs, B, st, &e->launches);
     stage_mark(e, 3, st);
     orbfe_launch_octree(g, bufs, B, st, &e->launches);
     stage_mark(e, 4, st);
@@ -301,6 +311,7 @@ int ensure_staging(OrbfeExtractor* e, int frames, int rows, int cols, int capaci
     const size_t need = (size_t)frames * rows * cols;
     if (need > e->inBytes) {
         if (int qrc = quiesce(e)) return qrc;
+        if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
         for (int s = 0; s < 2; s++) {
             if (e->d_in[s]) cudaFree(e->d_in[s]);
             e->d_in[s] = nullptr;
@@ -311,6 +322,7 @@ int ensure_staging(OrbfeExtractor* e, int frames, int rows, int cols, int capaci
     const size_t elems = (size_t)frames * capacity;
     if (elems > e->outElems || frames > e->outFrames) {
         if (int qrc = quiesce(e)) return qrc;
+        if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }
         for (int s = 0; s < 2; s++) {
             if (e->d_okps[s]) cudaFree(e->d_okps[s]);
             if (e->d_odesc[s]) cudaFree(e->d_odesc[s]);
@@ -395,6 +407,7 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
     if (e->slab) cudaFree(e->slab);
     if (e->slab2) cudaFree(e->slab2);
     if (e->d_taps) cudaFree(e->d_taps);
+    if (e->d_cells) cudaFree(e->d_cells);
     for (int s = 0; s < 2; s++) {
         if (e->d_in[s]) cudaFree(e->d_in[s]);
         if (e->d_okps[s]) cudaFree(e->d_okps[s]);

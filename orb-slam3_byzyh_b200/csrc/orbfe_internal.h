@@ -114,7 +114,13 @@ int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames)
 int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, const int* boxW, const int* boxH,
                           OrbfeFastMaps& maps);
 // cv::FAST per cell + NMS + the minThFAST retry + ordered emission, one warp per cell (fast.cu)
-void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st, long long* launches);
+struct OrbfeFastCell {   // one FAST cell of a frame (frame-wide numbering): interior in ROI coordinates, nbx == 0 = skipped
+    uint16_t x0, y0;
+    uint8_t nbx, nby, level, pad;
+};
+void orbfe_fast_cell_table(const OrbfeFrameGeom& g, std::vector<OrbfeFastCell>& out);
+void orbfe_launch_fast(const OrbfeFrameGeom& g, const OrbfeFastCell* cells, const OrbfeChunkBufs& b, int B, cudaStream_t st,
+                       long long* launches);
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches);
 void orbfe_launch_blur(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
@@ -141,6 +147,7 @@ struct OrbfeExtractor {
     bool haveGeom = false;
     OrbfeFrameGeom g;
     OrbfeTap* d_taps = nullptr;
+    OrbfeFastCell* d_cells = nullptr;   // per-cell FAST geometry of the current frame size
     size_t perFrameBytes = 0;
 
     OrbfeChunkBufs bufs = {};

@@ -106,7 +106,11 @@ extern "C" void fast_core_compass(const uint8_t* img, int w, int h, int t, uint8
     };
     for (int y = 3; y < h - 3; y++)
         for (int x = 3; x + 3 < w - 3; x += 4) {
-            const uint32_t f = fc_compass4(word(x, y), word(x, y - 3), word(x, y + 3), word(x - 3, y), word(x + 3, y), uLow, uTop);
+            const uint32_t f = fc_compass4<false>(word(x, y), word(x, y - 3), word(x, y + 3), word(x - 3, y), word(x + 3, y), uLow, uTop);
+            if (u < 128 && f != fc_compass4<true>(word(x, y), word(x, y - 3), word(x, y + 3), word(x - 3, y), word(x + 3, y), uLow, uTop)) {
+                out[0] = 255;   // the two variants disagree: make the test fail loudly
+                return;
+            }
             for (int i = 0; i < 4; i++) out[y * w + x + i] = (uint8_t)((f >> (8 * i + 7)) & 1);
         }
 }
