@@ -36,10 +36,24 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "orb-slam3_byzyh
 H, W, NF = 480, 752, 1000
 LAP = (0, 1000)
 METRIC = "ORB extract frames/s (752x480,1000kp,8lvl)"
+# BASELINE.json configs that are throughput workloads: C1 (the one `metric` is quoted on; the default) and C4.
+WORKLOADS = {
+    "c1": dict(h=480, w=752, nf=1000, frames=1024, metric=METRIC,
+               label="C1 752x480 nFeatures=1000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}"),
+    "c4": dict(h=720, w=1280, nf=2000, frames=384, metric="ORB extract frames/s (1280x720,2000kp,8lvl)",
+               label="C4 1280x720 nFeatures=2000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}"),
+}
+
+
+def set_workload(name):
+    global H, W, NF, METRIC
+    wl = WORKLOADS[name]
+    H, W, NF, METRIC = wl["h"], wl["w"], wl["nf"], wl["metric"]
+    return wl
 
 
 def make_frames(n, seed0=7, nbase=12):
-    """n distinct 752x480 frames: `nbase` synthetic scenes (tests/synth.py), the rest are
+    """n distinct H x W frames: `nbase` synthetic scenes (tests/synth.py), the rest are
     translated / mirrored variants (different pixel content per frame, same statistics)."""
     import synth
     base = [synth.synth_frame(H, W, seed0 + i) for i in range(min(nbase, n))]
@@ -127,6 +141,44 @@ def cpu_reference_run(frames_per_thread, threads, frames):
     [t.join() for t in ths]
     dt = time.perf_counter() - t0
     return threads * frames_per_thread / dt, kind
+
+
+def cv2_primitive_ms(frame, reps=5):
+    """The OpenCV primitives the reference links (resize, copyMakeBorder, FAST, GaussianBlur: ORBextractor.cc:1702,
+    1712, 1135, 1632) through cv2's own SIMD code, ONE thread, whole-level calls: the 'what the reference actually links'
+    figure of SURVEY 8(d).  Not the reference's control flow (it makes one cv::FAST call per 35-px cell, and the octree,
+    orientation and descriptors are its own scalar code): a lower bound for the three stages it covers."""
+    try:
+        import cv2
+    except Exception as e:
+        return {"error": "cv2 not importable: " + str(e)[:80]}
+    cv2.setNumThreads(1)
+    inv = [1.0]
+    for _ in range(7):
+        inv.append(inv[-1] / 1.2)
+    sizes = [(int(round(W * s)), int(round(H * s))) for s in inv]
+    fast20 = cv2.FastFeatureDetector_create(20, True)
+    out = {"pyramid": 0.0, "fast_whole_level": 0.0, "blur": 0.0}
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        levels = [frame]
+        for l in range(1, 8):
+            levels.append(cv2.resize(levels[-1], sizes[l], interpolation=cv2.INTER_LINEAR))
+        padded = [cv2.copyMakeBorder(v, 19, 19, 19, 19, cv2.BORDER_REFLECT_101) for v in levels]
+        t1 = time.perf_counter()
+        n = sum(len(fast20.detect(v[3:-3, 3:-3])) for v in padded)
+        t2 = time.perf_counter()
+        for v in levels:
+            cv2.GaussianBlur(v, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        t3 = time.perf_counter()
+        out["pyramid"] += (t1 - t0) * 1e3 / reps
+        out["fast_whole_level"] += (t2 - t1) * 1e3 / reps
+        out["blur"] += (t3 - t2) * 1e3 / reps
+    out["sum_ms_per_frame"] = out["pyramid"] + out["fast_whole_level"] + out["blur"]
+    out["fast_corners_at_20"] = int(n)
+    out["threads"] = 1
+    out["cv2"] = cv2.__version__
+    return out
 
 
 _JSON_OUT = sys.stdout
@@ -267,10 +319,16 @@ def cpu_reference_call_latencies(d, pts, dl, dr, kl, kr, timeit):
         return {"error": str(e)[:200]}
 
 
+CPU_BUILD = ("reference sources (ORBextractor.cc verbatim) over oracle/cvprims.cpp = scalar restatement of the OpenCV "
+             "primitives (bit-exact with cv2 4.13), g++ -O2 -ffp-contract=off; the reference's own build is -O3 -march=native "
+             "against OpenCV's SIMD code, see cpu_baseline.cv2_primitives for that part")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = set_workload(args.workload)
     cores = os.cpu_count() or 1
     frames = make_frames(16)
     one, kind = cpu_reference_run(1, 1, frames)                 # calibrate: single-thread frames/s
@@ -288,47 +346,31 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C1 752x480 nFeatures=1000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}",
-                   "frames_per_step": per * cores},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{per} frames per thread x {cores} threads per step, one ORBextractor per thread"},
+        "config": {"workload": wl["label"]},
+        "run": {"frames_per_step": per * cores},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "build": CPU_BUILD,
+                         "sample": f"{per} frames per thread x {cores} threads per step, one ORBextractor per thread",
+                         "cv2_primitives": cv2_primitive_ms(frames[0])},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import orbfe
-    from orbfe import _lib
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def hbm_peak():
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        return float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    orbfe.lib()
-    B = args.frames
-    frames = make_frames(B, seed0=7 + 1000 * rank)
-    pinned = torch.from_numpy(frames).pin_memory()
+def device_leg(torch, orbfe, dev, local, frames, steps, warmup, barrier, max_over_ranks, world, min_clock_s=0.0):
+    """Device-resident throughput of one workload (H, W, NF globals): frames already in HBM, K steps of
+    orbfe_extract_batch_device on a stream, CUDA events on that stream.  Returns a dict with the bench figures and the
+    per-kernel roofline block."""
+    B = len(frames)
     ex = orbfe.ORBextractor(NF, 1.2, 8, 20, 7, device=local)
     cap = ex.capacity
     ex.set_max_bytes(64 << 30)                        # one chunk: the whole batch per launch set
-    d_img = pinned.to(dev)
+    d_img = torch.from_numpy(frames).to(dev)
     d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.empty(B, dtype=torch.int32, device=dev)
@@ -338,8 +380,7 @@ def run_ours(args):
     def step_device():
         ex.extract_batch_device(d_img, LAP, d_kps, d_desc, d_n, d_mono, st)
 
-    # ---- device-resident throughput (value) ----
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_device()
     st.synchronize()
     geo = ex.frame_geometry()
@@ -356,7 +397,7 @@ def run_ours(args):
     l0 = ex.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     e1.record(st)
     st.synchronize()
@@ -365,8 +406,121 @@ def run_ours(args):
     launches = ex.launch_count() - l0
     stage = ex.stage_ms()
     ex.set_profiling(False)
+    # the clock sampler keeps running over the same load until it has seen `min_clock_s` of it (untimed steps)
+    t_more = time.time()
+    while time.time() - t_more < min_clock_s:
+        step_device()
+        st.synchronize()
     clk = clocks.stop()
-    value = world * B * args.steps / (ms / 1e3)
+    value = world * B * steps / (ms / 1e3)
+
+    sizes = [ex.level_size(l, (H, W)) for l in range(8)]
+    P = sum(w * h for w, h in sizes)
+    P06 = sum(w * h for w, h in sizes[:7])
+    Ppad = sum((w + 38) * (h + 38) for w, h in sizes)
+    K = float(n_kp.mean())
+    C = float(cands)
+    alg = {"pyramid": P06 + Ppad, "fast": P + 12 * C, "octree": 12 * C + 12 * K,
+           "layout": 28 * K, "blur": 2 * P, "describe": (749 + 4 + 512 + 32) * K}
+    frame_bytes = 3 * P + P06 + Ppad + 24 * C + 1337 * K          # SURVEY 8(d)
+    kern = {k: v for k, v in stage.items() if k in alg}
+    top = max(kern, key=kern.get)
+    peak, peak_src = hbm_peak()
+    achieved = alg[top] * B / (kern[top] / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        ent = json.load(open(tfile)).get(f"{H}x{W}", {}).get(top, {})
+        if ent.get("dram_bytes_per_frame") is not None:
+            traffic = ent["dram_bytes_per_frame"] * B
+            traffic_src = ent.get("source")
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[top] * B, "launch_ms": kern[top],
+                "kernel_ms_per_step": kern, "pipeline_bytes_per_frame": frame_bytes,
+                "pipeline_frac": value / world * frame_bytes / 1e9 / peak}
+    return dict(ex=ex, value=value, ms=ms, launches=launches, clk=clk, geo=geo, n_kp=n_kp, K=K, C=C, cap=cap,
+                roofline=roofline)
+
+
+def copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps, barrier, max_over_ranks):
+    """What the host link alone allows: the step's H2D and D2H volumes copied concurrently on two streams from / into
+    pinned memory, no kernels; with N ranks all ranks copy at the same time (one host, shared root complex / memory)."""
+    src = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def once():
+        with torch.cuda.stream(s1):
+            d_in.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dst.copy_(d_out, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    return max_over_ranks(dt * 1e3) / reps
+
+
+def bind_to_gpu_numa(local):
+    """Pin this rank's threads (and with them its first-touch pinned allocations) to the cores of its GPU's NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"cpus": len(cpus), "first": cpus[0] if cpus else None, "last": cpus[-1] if cpus else None}
+    except Exception as e:
+        return {"error": str(e)[:100]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import orbfe
+    from orbfe import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    orbfe.lib()
+    wl = set_workload(args.workload)
+    B = args.frames or wl["frames"]
+    frames = make_frames(B, seed0=7 + 1000 * rank)
+    pinned = torch.from_numpy(frames).pin_memory()
+
+    # ---- device-resident throughput (value) ----
+    leg = device_leg(torch, orbfe, dev, local, frames, args.steps, args.warmup, barrier, max_over_ranks, world, min_clock_s=2.0)
+    ex, value, ms, launches, clk, geo, n_kp, K, C, cap = (leg[k] for k in ("ex", "value", "ms", "launches", "clk", "geo", "n_kp", "K", "C", "cap"))
+    roofline = leg["roofline"]
 
     # ---- end to end through the host-pointer C ABI (e2e) ----
     ex.set_max_bytes(int(geo["per_frame_bytes"]) * args.chunk)   # pipeline H2D / kernels / D2H per chunk
@@ -415,6 +569,11 @@ def run_ours(args):
         assert outs[0][2][f, :k].tobytes() == outs[1][2][f, :k].tobytes() and \
             np.array_equal(outs[0][3][f, :k], outs[1][3][f, :k]), "streaming results differ"
     assert np.array_equal(out[0].astype(np.int64), n_kp), "host and device paths disagree"
+    h2d = B * H * W
+    d2h = B * (cap * 28 + cap * 32 + 8)
+    # the host link's own ceiling for these copy volumes, all ranks copying at once (no kernels)
+    ceil_ms = copy_ceiling(torch, dev, h2d, d2h, max(3, min(args.steps, 10)), barrier, max_over_ranks)
+    ceil_fps = world * B / (ceil_ms / 1e3)
 
     # ---- one frame per call, as Frame::ExtractORB issues it (latency, not throughput) ----
     one = frames[0]
@@ -427,109 +586,129 @@ def run_ours(args):
     latency = {"extract_1_frame": single_ms}
     if not args.no_match and rank == 0:
         latency.update(call_latencies(orbfe, local))
-    h2d = B * H * W
-    d2h = B * (cap * 28 + cap * 32 + 8)
 
     # ---- matching leg: 2000 frame descriptors vs 1 M map descriptors, map sharded over ranks ----
     matching = None
     if not args.no_match:
-        nq, nmap = 2000, 1000000
-        rng = np.random.default_rng(5)
-        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
-        lo, hi = rank * nmap // world, (rank + 1) * nmap // world
-        shard = np.random.default_rng(100 + rank).integers(0, 256, (hi - lo, 32), dtype=np.uint8)
-        import orbfe.dist as D
-        d_q = torch.from_numpy(q).to(dev)
-        def time_exchange(exchange):
-            smap = D.ShardedMap(shard, lo, dev, exchange=exchange)     # this rank's shard, resident in HBM
-            for _ in range(3):
-                out = smap.knn2(d_q)
-            barrier()
-            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            m0.record()
-            for _ in range(args.steps):
-                out = smap.knn2(d_q)                   # local kNN-2 -> exchange of the per-shard best two -> merge
-            m1.record()
-            torch.cuda.synchronize()
-            barrier()
-            return max_over_ranks(m0.elapsed_time(m1)), smap.exchange, [t.clone() for t in out]
-        # exchange fused into the merge kernel (peer loads over NVLink, symmetric memory); all-gather form beside it.
-        # Both forms are timed twice in alternation and the faster pass of each is reported (sub-millisecond steps).
-        mms, how, res = time_exchange("p2p")
-        if world > 1:
-            nms, _, res2 = time_exchange("nccl")
-            assert all(torch.equal(a, b) for a, b in zip(res, res2)), "p2p and all-gather exchanges disagree"
-            mms = min(mms, time_exchange("p2p")[0])
-            nms = min(nms, time_exchange("nccl")[0])
-        pairs = nq * nmap * args.steps / (mms / 1e3)
-        matching = {"metric": "Hamming matches/s (2000 frame x 1M map descriptors, kNN-2 + ratio)", "value": pairs,
-                    "unit": "descriptor pairs/s", "ms_per_step": mms / args.steps, "map_shards": world, "gather": "none"}
-        if world > 1:
-            matching["gather"] = ("peer loads inside the merge kernel (symmetric memory over NVLink) + 1 device barrier"
-                                  if how == "p2p" else how)
-            matching["ms_per_step_nccl_all_gather"] = nms / args.steps
+        matching = matching_leg(torch, dist, orbfe, dev, rank, world, args.steps, barrier, max_over_ranks)
+
+    # ---- the other throughput workload of BASELINE.json (C4 when the line is C1), device-resident, same method ----
+    extra = None
+    other = "c4" if args.workload == "c1" else None
+    if other and not args.no_extra:
+        del ex, leg
+        torch.cuda.empty_cache()
+        owl = set_workload(other)
+        oframes = make_frames(args.extra_frames or owl["frames"], seed0=7 + 1000 * rank)
+        oleg = device_leg(torch, orbfe, dev, local, oframes, max(3, min(args.steps, 10)), 3, barrier, max_over_ranks, world)
+        extra = {other: {"metric": METRIC, "value": oleg["value"], "unit": "frames/s", "n_gpus": world,
+                         "ms_per_step": oleg["ms"] / max(3, min(args.steps, 10)), "workload": owl["label"],
+                         "frames_per_gpu_per_step": len(oframes), "keypoints_per_frame": oleg["K"],
+                         "fast_candidates_per_frame": oleg["C"], "clocks": oleg["clk"], "roofline": oleg["roofline"],
+                         "residency": "device-resident (frames in HBM), CUDA events on the launching stream, max over ranks"}}
+        set_workload(args.workload)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (algorithmic bytes per launch) ----
-    sizes = [ex.level_size(l, (H, W)) for l in range(8)]
-    P = sum(w * h for w, h in sizes)
-    P06 = sum(w * h for w, h in sizes[:7])
-    Ppad = sum((w + 38) * (h + 38) for w, h in sizes)
-    K = float(n_kp.mean())
-    C = float(cands)
-    alg = {"pyramid": P06 + Ppad, "fast": P + 12 * C, "octree": 12 * C + 12 * K,
-           "layout": 28 * K, "blur": 2 * P, "describe": (749 + 4 + 512 + 32) * K}
-    frame_bytes = 3 * P + P06 + Ppad + 24 * C + 1337 * K          # SURVEY 8(d)
-    kern = {k: v for k, v in stage.items() if k in alg}
-    top = max(kern, key=kern.get)
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_file):
-        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = alg[top] * B / (kern[top] / 1e3) / 1e9
-    traffic = None
-    tfile = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tfile):
-        traffic = json.load(open(tfile)).get(top, {}).get("dram_bytes_per_frame")
-        traffic = traffic * B if traffic is not None else None
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[top] * B, "launch_ms": kern[top],
-                "kernel_ms_per_step": kern, "pipeline_bytes_per_frame": frame_bytes,
-                "pipeline_frac": value / world * frame_bytes / 1e9 / peak}
-
     # ---- CPU baseline: the reference's ORBextractor on the host cores (bounded sample) ----
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        one, kind = cpu_reference_run(1, 1, frames)
-        per = int(max(2, min(64, round(12.0 * one))))
+        one_t, kind = cpu_reference_run(1, 1, frames)
+        per = int(max(2, min(64, round(12.0 * one_t))))
         v, kind = cpu_reference_run(per, cores, frames)
-        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "single_thread_frames_per_s": one,
-               "sample": f"{per} frames per thread x {cores} threads of the same workload, one ORBextractor per thread"}
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "single_thread_frames_per_s": one_t,
+               "build": CPU_BUILD,
+               "sample": f"{per} frames per thread x {cores} threads of the same workload, one ORBextractor per thread",
+               "cv2_primitives": cv2_primitive_ms(frames[0])}
 
     emit_json({
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "C1 752x480 nFeatures=1000 scaleFactor=1.2 nLevels=8 FAST 20/7 lapping {0,1000}",
-                   "frames_per_gpu_per_step": B, "keypoints_per_frame": K, "fast_candidates_per_frame": C,
-                   "l2": f"inputs+intermediates per step = {B * geo['per_frame_bytes'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
-                   "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around the K steps, max over ranks",
-                   "e2e_mode": "orbfe_extract_batch_submit/_wait, 2 host batches in flight (sync_call_value: one blocking orbfe_extract_batch per step)"},
+        "config": {"workload": wl["label"]},
+        "run": {"frames_per_gpu_per_step": B, "keypoints_per_frame": K, "fast_candidates_per_frame": C,
+                "l2": f"inputs+intermediates per step = {B * geo['per_frame_bytes'] / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+                "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around the K steps, max over ranks",
+                "e2e_mode": "orbfe_extract_batch_submit/_wait, 2 host batches in flight (sync_call_value: one blocking orbfe_extract_batch per step)",
+                "cpu_affinity": affinity,
+                "ncu_captures": "profiles/*: ncu runs use --frames 128 (kernel shares and per-frame counters, not absolute times)"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "sync_call_value": e2e_sync,
-                "sync_call_ms_per_step": e2e_sync_ms / args.steps, "single_frame_call_ms": single_ms},
+                "sync_call_ms_per_step": e2e_sync_ms / args.steps, "single_frame_call_ms": single_ms,
+                "copy_ceiling_frames_per_s": ceil_fps, "copy_ceiling_ms_per_step": ceil_ms,
+                "frac_of_ceiling": e2e / ceil_fps,
+                "copy_ceiling_how": "the step's H2D and D2H bytes copied concurrently on two streams, pinned host memory, "
+                                    "no kernels, all ranks at once; device-resident `value` is the other bound"},
         "call_latency_ms": latency,
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "matching": matching,
+        "extra": extra,
     })
     if world > 1:
         dist.destroy_process_group()
+
+
+def matching_leg(torch, dist, orbfe, dev, rank, world, steps, barrier, max_over_ranks):
+    """C5: 2000 frame descriptors against a 1 M descriptor map sharded over the ranks.  Brute-force kNN-2 (exchange of
+    the per-shard best two fused into the merge kernel over NVLink peer loads) and the map-sharded SearchByProjection."""
+    import orbfe.dist as D
+    nq, nmap = 2000, 1000000
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    lo, hi = rank * nmap // world, (rank + 1) * nmap // world
+    shard = np.random.default_rng(100 + rank).integers(0, 256, (hi - lo, 32), dtype=np.uint8)
+    d_q = torch.from_numpy(q).to(dev)
+
+    def time_exchange(exchange):
+        smap = D.ShardedMap(shard, lo, dev, exchange=exchange)     # this rank's shard, resident in HBM
+        for _ in range(3):
+            out = smap.knn2(d_q)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(steps):
+            out = smap.knn2(d_q)                   # local kNN-2 -> exchange of the per-shard best two -> merge
+        m1.record()
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(m0.elapsed_time(m1)), smap.exchange, [t.clone() for t in out]
+    # exchange fused into the merge kernel (peer loads over NVLink, symmetric memory); all-gather form beside it.
+    # Both forms are timed twice in alternation and the faster pass of each is reported (sub-millisecond steps).
+    mms, how, res = time_exchange("p2p")
+    nms = None
+    if world > 1:
+        nms, _, res2 = time_exchange("nccl")
+        assert all(torch.equal(a, b) for a, b in zip(res, res2)), "p2p and all-gather exchanges disagree"
+        mms = min(mms, time_exchange("p2p")[0])
+        nms = min(nms, time_exchange("nccl")[0])
+    pairs = nq * nmap * steps / (mms / 1e3)
+    # INT roofline of the brute force (DESIGN.md section 4): POPC is a quarter-rate unit, measured 25 lanes / clk / SM
+    # (profiles/r1_pipe_bench.txt); the kernel spends 5 POPC per descriptor pair (8 XOR words compressed 8 -> 5 by
+    # carry-save adders), the plain statement of ORBmatcher::DescriptorDistance needs 8.
+    sm_mhz = 1965.0
+    popc_peak = 25.0 * 148 * sm_mhz * 1e6
+    matching = {"metric": "Hamming matches/s (2000 frame x 1M map descriptors, kNN-2 + ratio)", "value": pairs,
+                "unit": "descriptor pairs/s", "ms_per_step": mms / steps, "map_shards": world, "gather": "none",
+                "roofline": {"bound": "int", "unit": "POPC32/s", "peak": popc_peak * world,
+                             "peak_source": "25 POPC lanes/clk/SM measured (profiles/r1_pipe_bench.txt) x 148 SMs x 1965 MHz x GPUs",
+                             "achieved": pairs * 5.0, "frac": pairs * 5.0 / (popc_peak * world),
+                             "executed_popc_per_pair": 5, "algorithmic_popc_per_pair": 8,
+                             "algorithmic_popc32_per_s": pairs * 8.0,
+                             "issue_peak_warp_instr_per_s": 0.884e12 * world,
+                             "ncu": "profiles/r2_match_ncu_summary.txt"}}
+    if world > 1:
+        matching["gather"] = ("peer loads inside the merge kernel (symmetric memory over NVLink) + 1 device barrier"
+                              if how == "p2p" else how)
+        matching["ms_per_step_nccl_all_gather"] = nms / steps
+    try:
+        matching["search_by_projection"] = D.bench_sharded_projection(torch, dist, orbfe, dev, rank, world, steps,
+                                                                      barrier, max_over_ranks)
+    except Exception as e:     # reported, never fatal for the extraction line
+        matching["search_by_projection"] = {"error": str(e)[:200]}
+    return matching
 
 
 def main():
@@ -538,7 +717,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
+    ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS), help="BASELINE.json config the line is measured on")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: 1024 for c1, 384 for c4)")
+    ap.add_argument("--extra-frames", type=int, default=0, help="frames per GPU per step of the extra C4 block")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (C4 device-resident throughput)")
     ap.add_argument("--chunk", type=int, default=256, help="frames per pipelined chunk on the host-pointer path")
     ap.add_argument("--no-match", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

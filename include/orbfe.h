@@ -226,6 +226,33 @@ int orbfe_search_by_projection(const OrbfeFrameView* frame, const OrbfeProjPoint
                                int32_t* assigned, int32_t* best_idx, int32_t* best_dist,
                                int device);
 
+/* The same search against a map that is SHARDED over several GPUs by contiguous index ranges (BASELINE config 5:
+ * "SearchByProjection ... map sharded over 8 GPUs with NVLink best-match gather").  The reference walks the map points
+ * in vector order and a keypoint accepted by point j is skipped by every later point (src/ORBmatcher.cc:54, 103-105,
+ * 156), so the shards cannot simply be searched independently.  A shard holds the projected points [j0, j0+m) in HBM
+ * (orbfe_map_shard_create: host arrays of THIS shard, uploaded once); the frame is set on every shard
+ * (orbfe_map_shard_set_frame).  One search = passes until the claim table stops changing:
+ *   claims (device int32[frame n]): -1 = keypoint held a blocking point on entry, INT_MAX = free, else the GLOBAL index
+ *   of the first accepting point (orbfe_claims_init_device builds the static table from F.mvpMapPoints' flags);
+ *   orbfe_map_shard_pass evaluates the shard's points against claims_in and lowers claims_out (pre-set to the static
+ *   table) to its own first acceptors; the shards' claims_out are combined by an elementwise minimum -- 4 bytes per
+ *   frame keypoint per pass, the only exchange: an all-reduce(MIN), or orbfe_claims_min_peers_device reading the other
+ *   shards' tables with peer loads over NVLink; the result is the next claims_in.
+ * orbfe_map_shard_finish then raises assigned[k] to the (global) index of the last accepting point and adds the
+ * shard's match count; assigned tables combine by elementwise maximum, counts by sum.  Mode ORBFE_SEARCH_MAPPOINTS (and
+ * ORBFE_SEARCH_KEYFRAME without orientation check).  Results equal orbfe_search_by_projection on the whole map. */
+typedef struct OrbfeMapShard OrbfeMapShard;
+int orbfe_map_shard_create(const OrbfeProjPoints* pts_shard, int j0, int device, OrbfeMapShard** out);
+void orbfe_map_shard_destroy(OrbfeMapShard* h);
+int orbfe_map_shard_set_frame(OrbfeMapShard* h, const OrbfeFrameView* frame, void* stream);
+int orbfe_claims_init_device(const uint8_t* d_claimed, int n, int32_t* d_claims, void* stream);
+int orbfe_map_shard_pass(OrbfeMapShard* h, const OrbfeSearchParams* prm, const int32_t* d_claim_in,
+                         int32_t* d_claim_out, void* stream);
+int orbfe_claims_min_peers_device(const int32_t* const* peer_tabs, int n_shards, int n, int32_t* d_out,
+                                  const int32_t* d_prev, int32_t* d_changed, void* stream);
+int orbfe_map_shard_finish(OrbfeMapShard* h, int32_t* d_assigned, int32_t* d_nmatches, void* stream);
+int orbfe_map_shard_results(OrbfeMapShard* h, int32_t* best_idx, int32_t* best_dist, void* stream);
+
 /* The same search on a fisheye stereo frame (F.Nleft != -1): modes ORBFE_SEARCH_MAPPOINTS
  * (src/ORBmatcher.cc:46-240 incl. the right-camera branch :171-237 and the mvLeftToRightMatch /
  * mvRightToLeftMatch partner writes :159-163, :215-219) and ORBFE_SEARCH_LASTFRAME (:1951-2185

@@ -39,6 +39,7 @@ struct GridDev {
 
 struct PtsDev {
     int m;
+    int jOff;   // global index of point 0: claims and assignments speak global indices (a map shard starts above 0)
     const float *u, *v, *ur, *radius, *angle;
     const int *minLevel, *maxLevel;
     const uint8_t *valid, *blocks;
@@ -144,7 +145,7 @@ k_search_pass(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, const 
                             if (maxLevel >= 0 && kp.octave > maxLevel) continue;
                         }
                         if (!(fabsf(kp.x - x) < r && fabsf(kp.y - y) < r)) continue;
-                        if (claimIn[idx] < j) continue;  // ORBmatcher.cc:103-105 / 2040-2042 / 2266-2267
+                        if (claimIn[idx] < j + P.jOff) continue;  // ORBmatcher.cc:103-105 / 2040-2042 / 2266-2267
                         if (mode != ORBFE_SEARCH_KEYFRAME && F.uright) {
                             const float uR = F.uright[idx];
                             if (uR > 0 && fabsf(ur - uR) > r) continue;  // :108-118 / :2044-2050
@@ -164,7 +165,7 @@ k_search_pass(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, const 
     if (accept && mode == ORBFE_SEARCH_MAPPOINTS && bL == bL2 && (float)bD > nnratio * (float)bD2) accept = false;
     bestDist[j] = bD;
     bestIdx[j] = accept ? bI : -1;
-    if (accept && (mode == ORBFE_SEARCH_KEYFRAME || (P.blocks ? P.blocks[j] != 0 : true))) atomicMin(&claimOut[bI], j);
+    if (accept && (mode == ORBFE_SEARCH_KEYFRAME || (P.blocks ? P.blocks[j] != 0 : true))) atomicMin(&claimOut[bI], j + P.jOff);
 }
 
 // The same pass with one WARP per map point, for the per-frame calls of Tracking (a few thousand points: one thread
@@ -205,7 +206,7 @@ k_search_pass_warp(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, c
                         if (maxLevel >= 0 && kp.octave > maxLevel) continue;
                     }
                     if (!(fabsf(kp.x - x) < r && fabsf(kp.y - y) < r)) continue;
-                    if (claimIn[idx] < j) continue;
+                    if (claimIn[idx] < j + P.jOff) continue;
                     if (mode != ORBFE_SEARCH_KEYFRAME && F.uright) {
                         const float uR = F.uright[idx];
                         if (uR > 0 && fabsf(ur - uR) > r) continue;
@@ -240,7 +241,7 @@ k_search_pass_warp(GridDev F, PtsDev P, int mode, int thAccept, float nnratio, c
     if (accept && mode == ORBFE_SEARCH_MAPPOINTS && bL == bL2 && (float)bD > nnratio * (float)bD2) accept = false;
     bestDist[j] = bD;
     bestIdx[j] = accept ? bI : -1;
-    if (accept && (mode == ORBFE_SEARCH_KEYFRAME || (P.blocks ? P.blocks[j] != 0 : true))) atomicMin(&claimOut[bI], j);
+    if (accept && (mode == ORBFE_SEARCH_KEYFRAME || (P.blocks ? P.blocks[j] != 0 : true))) atomicMin(&claimOut[bI], j + P.jOff);
 }
 
 __global__ void k_claims_init(const uint8_t* __restrict__ claimed, int n, int* __restrict__ a, int* __restrict__ b) {
@@ -268,7 +269,7 @@ __global__ void k_search_assign(GridDev F, PtsDev P, int useHist, const int* __r
     if (j >= P.m) return;
     const int k = bestIdx[j];
     if (k < 0) return;
-    atomicMax(&assigned[k], j);
+    atomicMax(&assigned[k], j + P.jOff);
     atomicAdd(nmatches, 1);
     if (useHist) {
         float rot = P.angle[j] - F.keys[k].angle;  // ORBmatcher.cc:2074-2084
@@ -812,6 +813,7 @@ extern "C" int orbfe_search_by_projection(const OrbfeFrameView* frame, const Orb
     F.wInv = frame->grid_w_inv; F.hInv = frame->grid_h_inv;
     F.cellStart = S.ptr<int>(wStart); F.cellItems = S.ptr<int>(wItems);
     PtsDev P;
+    P.jOff = 0;
     P.m = m; P.u = S.ptr<float>(iU); P.v = S.ptr<float>(iV); P.ur = pts->ur ? S.ptr<float>(iPur) : nullptr;
     P.radius = S.ptr<float>(iRad); P.angle = pts->angle ? S.ptr<float>(iAng) : nullptr;
     P.minLevel = S.ptr<int>(iMin); P.maxLevel = S.ptr<int>(iMax); P.valid = S.ptr<uint8_t>(iVal);
@@ -929,6 +931,7 @@ extern "C" int orbfe_search_by_projection_fisheye(const OrbfeFrameView* left, co
     fill(F.R, right, iKr, iDr, wStR, wItR);
     F.l2r = S.ptr<int>(iL2R); F.r2l = S.ptr<int>(iR2L); F.Nl = Nl;
     PtsFe P;
+    P.L.jOff = 0;
     P.L.m = m; P.L.u = S.ptr<float>(iLu); P.L.v = S.ptr<float>(iLv); P.L.ur = nullptr; P.L.radius = S.ptr<float>(iLr);
     P.L.angle = pl->angle ? S.ptr<float>(iLang) : nullptr; P.L.minLevel = S.ptr<int>(iLmin); P.L.maxLevel = S.ptr<int>(iLmax);
     P.L.valid = S.ptr<uint8_t>(iLval); P.L.blocks = pl->blocks ? S.ptr<uint8_t>(iLblk) : nullptr; P.L.desc = S.ptr<uint32_t>(iLdesc);
@@ -1101,6 +1104,7 @@ extern "C" int orbfe_search_window(const OrbfeFrameView* kf, const OrbfeProjPoin
     SCK(S.upload());
     GridDev F;
     PtsDev P;
+    P.jOff = 0;
     W.bind(S, kf, pts, F, P);
     W.grid(S, F, st);
     k_window_best<<<(m + 3) / 4, 128, 0, st>>>(F, P, prm->th_accept, gate ? 1 : 0, gate ? S.ptr<float>(iInv) : nullptr,
@@ -1148,4 +1152,184 @@ extern "C" int orbfe_search_by_sim3(const OrbfeFrameView* kf1, const OrbfeFrameV
     SCK(cudaGetLastError());
     SCK(S.download());
     return nFound;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Map shards: SearchByProjection(Frame&, vector<MapPoint*>&, ...) (ORBmatcher.cc:46-240) against a map that is split
+// over several GPUs by contiguous index ranges (BASELINE config 5).  The reference's loop is sequential over the map
+// points (:54) and a keypoint accepted by point j is skipped by every later point (:103-105); the claim fixpoint above
+// keeps that exact: a claim is the GLOBAL index of the first accepting point, every shard runs the pass over its own
+// points against the same global claim table, the shards' new tables are combined by an elementwise minimum (the only
+// exchange: 4 bytes per frame keypoint per pass), and the passes repeat until the table stops changing -- then every
+// point has seen exactly the claims of the points before it, on whichever GPU they live.
+struct OrbfeMapShard {
+    int device = 0, m = 0, j0 = 0, n = 0;
+    bool hasUr = false, hasBlocks = false, hasAngle = false, hasFrameUr = false;
+    char* dPts = nullptr;     // u, v, ur, radius, minLevel, maxLevel, valid, blocks, desc
+    char* dFrame = nullptr;   // keys, desc, uright, cellOf, cellStart, cellItems
+    size_t frameCap = 0;
+    PtsDev P;
+    GridDev F;
+    int *dBestIdx = nullptr, *dBestDist = nullptr;
+};
+
+namespace {
+struct PeerClaims { const int32_t* t[16]; };
+// Elementwise minimum of the shards' claim tables, read with peer loads (symmetric memory over NVLink): the exchange
+// step of the sharded search fused into the kernel that produces the next pass's input.
+__global__ void k_claims_min_peers(PeerClaims C, int G, int n, int32_t* __restrict__ out, const int32_t* __restrict__ prev,
+                                   int* __restrict__ changed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = INT_MAX;
+    for (int s = 0; s < G; s++) v = min(v, C.t[s][i]);
+    out[i] = v;
+    if (prev && prev[i] != v) *changed = 1;
+}
+size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+extern "C" int orbfe_map_shard_create(const OrbfeProjPoints* pts, int j0, int device, OrbfeMapShard** out) {
+    if (!out) return sfail(ORBFE_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return sfail(ORBFE_ERR_CUDA, "no CUDA device (there is no CPU fallback)", ce);
+    if (device < 0 || device >= ndev) return sfail(ORBFE_ERR_INVALID, "bad device ordinal");
+    if (!pts || pts->m <= 0 || j0 < 0 || !pts->u || !pts->v || !pts->radius || !pts->min_level || !pts->max_level || !pts->desc)
+        return sfail(ORBFE_ERR_INVALID, "missing map-point array");
+    SCK(cudaSetDevice(device));
+    const size_t m = (size_t)pts->m, M4 = 4 * m;
+    OrbfeMapShard* h = new OrbfeMapShard();
+    h->device = device; h->m = pts->m; h->j0 = j0;
+    h->hasUr = pts->ur != nullptr; h->hasBlocks = pts->blocks != nullptr; h->hasAngle = pts->angle != nullptr;
+    size_t off[10], total = 0;
+    const size_t sz[10] = {M4, M4, M4, M4, M4, M4, m, m, 32 * m, M4};
+    for (int i = 0; i < 10; i++) { off[i] = total; total += al256(sz[i]); }
+    cudaError_t e = cudaMalloc(&h->dPts, total + 2 * al256(M4));
+    if (e != cudaSuccess) { delete h; return sfail(ORBFE_ERR_CUDA, "cudaMalloc(map shard)", e); }
+    char* d = h->dPts;
+    std::vector<uint8_t> ones;
+    if (!pts->valid) ones.assign(m, 1);
+    const void* src[10] = {pts->u, pts->v, pts->ur, pts->radius, pts->min_level, pts->max_level,
+                           pts->valid ? pts->valid : ones.data(), pts->blocks, pts->desc, pts->angle};
+    for (int i = 0; i < 10 && e == cudaSuccess; i++)
+        if (src[i]) e = cudaMemcpy(d + off[i], src[i], sz[i], cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->dPts); delete h; return sfail(ORBFE_ERR_CUDA, "upload of the map shard", e); }
+    PtsDev& P = h->P;
+    P.m = pts->m; P.jOff = j0;
+    P.u = (const float*)(d + off[0]); P.v = (const float*)(d + off[1]); P.ur = pts->ur ? (const float*)(d + off[2]) : nullptr;
+    P.radius = (const float*)(d + off[3]); P.minLevel = (const int*)(d + off[4]); P.maxLevel = (const int*)(d + off[5]);
+    P.valid = (const uint8_t*)(d + off[6]); P.blocks = pts->blocks ? (const uint8_t*)(d + off[7]) : nullptr;
+    P.desc = (const uint32_t*)(d + off[8]); P.angle = pts->angle ? (const float*)(d + off[9]) : nullptr;
+    h->dBestIdx = (int*)(d + total);
+    h->dBestDist = (int*)(d + total + al256(M4));
+    *out = h;
+    return ORBFE_OK;
+}
+
+extern "C" void orbfe_map_shard_destroy(OrbfeMapShard* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->dPts) cudaFree(h->dPts);
+    if (h->dFrame) cudaFree(h->dFrame);
+    delete h;
+}
+
+// The frame side, the same on every shard: keypoints, descriptors, stereo coordinates; builds the 64 x 48 grid.
+extern "C" int orbfe_map_shard_set_frame(OrbfeMapShard* h, const OrbfeFrameView* frame, void* stream) {
+    if (!h || !frame || frame->n <= 0 || !frame->keys || !frame->desc) return sfail(ORBFE_ERR_INVALID, "bad frame view");
+    SCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)frame->n, N4 = 4 * n;
+    const size_t sz[6] = {sizeof(OrbfeKeyPoint) * n, 32 * n, N4, N4, 4 * (size_t)(GC * GR + 1), N4};
+    size_t off[6], total = 0;
+    for (int i = 0; i < 6; i++) { off[i] = total; total += al256(sz[i]); }
+    if (total > h->frameCap) {
+        SCK(cudaStreamSynchronize(st));
+        if (h->dFrame) cudaFree(h->dFrame);
+        h->dFrame = nullptr; h->frameCap = 0;
+        SCK(cudaMalloc(&h->dFrame, total));
+        h->frameCap = total;
+    }
+    char* d = h->dFrame;
+    SCK(cudaMemcpyAsync(d + off[0], frame->keys, sz[0], cudaMemcpyHostToDevice, st));
+    SCK(cudaMemcpyAsync(d + off[1], frame->desc, sz[1], cudaMemcpyHostToDevice, st));
+    if (frame->uright) SCK(cudaMemcpyAsync(d + off[2], frame->uright, sz[2], cudaMemcpyHostToDevice, st));
+    GridDev& F = h->F;
+    F.keys = (const OrbfeKeyPoint*)(d + off[0]); F.desc = (const uint32_t*)(d + off[1]);
+    F.uright = frame->uright ? (const float*)(d + off[2]) : nullptr;
+    F.n = frame->n; h->n = frame->n;
+    F.minX = frame->min_x; F.minY = frame->min_y; F.maxX = frame->max_x; F.maxY = frame->max_y;
+    F.wInv = frame->grid_w_inv; F.hInv = frame->grid_h_inv;
+    F.cellStart = (const int*)(d + off[4]); F.cellItems = (const int*)(d + off[5]);
+    k_build_grid<<<1, 1024, 0, st>>>(F.keys, F.n, F.minX, F.minY, F.wInv, F.hInv, (int*)(d + off[3]), (int*)(d + off[4]), (int*)(d + off[5]));
+    SCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+// Static claims of a frame: -1 where the keypoint already holds a blocking map point, INT_MAX elsewhere (device arrays).
+extern "C" int orbfe_claims_init_device(const uint8_t* d_claimed, int n, int32_t* d_claims, void* stream) {
+    if (n <= 0) return ORBFE_OK;
+    if (!d_claims) return sfail(ORBFE_ERR_INVALID, "null claims table");
+    k_claims_init<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_claimed, n, d_claims, d_claims);
+    SCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+// One pass of the shard's points (global indices j0 .. j0+m) against the global claim table d_claim_in; d_claim_out holds
+// the static claims on entry and is lowered to the first accepting point of this shard.
+extern "C" int orbfe_map_shard_pass(OrbfeMapShard* h, const OrbfeSearchParams* prm, const int32_t* d_claim_in,
+                                    int32_t* d_claim_out, void* stream) {
+    if (!h || !prm || !d_claim_in || !d_claim_out || !h->dFrame) return sfail(ORBFE_ERR_INVALID, "map shard: frame not set / null argument");
+    if (prm->mode != ORBFE_SEARCH_MAPPOINTS && !(prm->mode == ORBFE_SEARCH_KEYFRAME && !prm->check_orientation))
+        return sfail(ORBFE_ERR_INVALID, "map shards support SearchByProjection(Frame, map points) and the keyframe mode without orientation check");
+    SCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = h->m;
+    if (m <= kWarpPassMax && h->n < (1 << 23))
+        k_search_pass_warp<<<(m + 3) / 4, 128, 0, st>>>(h->F, h->P, prm->mode, prm->th_accept, prm->nnratio, d_claim_in, d_claim_out,
+                                                       h->dBestIdx, h->dBestDist);
+    else
+        k_search_pass<<<(m + 127) / 128, 128, 0, st>>>(h->F, h->P, prm->mode, prm->th_accept, prm->nnratio, d_claim_in, d_claim_out,
+                                                     h->dBestIdx, h->dBestDist);
+    SCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+// The exchange step over peer memory: d_out[i] = min over the shards' claim tables (peer pointers, e.g. symmetric
+// memory over NVLink); *d_changed is set when the result differs from d_prev (the table the pass just read).
+extern "C" int orbfe_claims_min_peers_device(const int32_t* const* peer_tabs, int G, int n, int32_t* d_out, const int32_t* d_prev,
+                                             int32_t* d_changed, void* stream) {
+    if (n <= 0 || G <= 0) return ORBFE_OK;
+    if (!peer_tabs || !d_out || G > 16) return sfail(ORBFE_ERR_INVALID, "claims exchange: null argument or more than 16 shards");
+    PeerClaims C;
+    for (int s = 0; s < 16; s++) C.t[s] = s < G ? peer_tabs[s] : nullptr;
+    k_claims_min_peers<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(C, G, n, d_out, d_prev, d_changed);
+    SCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+// After the fixpoint: raises d_assigned[k] (global point indices; -1 / the caller's previous content elsewhere) for the
+// keypoints this shard's points accepted and adds the shard's match count to *d_nmatches.  The per-shard tables are
+// combined by an elementwise maximum (the reference's later point overwrites an earlier one, :156) and a sum.
+extern "C" int orbfe_map_shard_finish(OrbfeMapShard* h, int32_t* d_assigned, int32_t* d_nmatches, void* stream) {
+    if (!h || !d_assigned || !d_nmatches || !h->dFrame) return sfail(ORBFE_ERR_INVALID, "map shard: null argument");
+    SCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gridM = (h->m + 127) / 128;
+    k_search_assign<<<gridM, 128, 0, st>>>(h->F, h->P, 0, h->dBestIdx, d_assigned, nullptr, nullptr, d_nmatches);
+    SCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
+// Per-point results of the last pass (host arrays of the shard's m points; indices are frame keypoint indices).
+extern "C" int orbfe_map_shard_results(OrbfeMapShard* h, int32_t* best_idx, int32_t* best_dist, void* stream) {
+    if (!h) return sfail(ORBFE_ERR_INVALID, "null map shard");
+    SCK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (best_idx) SCK(cudaMemcpyAsync(best_idx, h->dBestIdx, 4 * (size_t)h->m, cudaMemcpyDeviceToHost, st));
+    if (best_dist) SCK(cudaMemcpyAsync(best_dist, h->dBestDist, 4 * (size_t)h->m, cudaMemcpyDeviceToHost, st));
+    SCK(cudaStreamSynchronize(st));
+    return ORBFE_OK;
 }

@@ -108,6 +108,14 @@ _SIGS = {
     "orbfe_knn2_merge_packed_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_search_by_projection": (_i, [C.POINTER(FrameView), C.POINTER(ProjPoints), C.POINTER(SearchParams),
                                         _vp, _vp, _vp, _vp, _i]),
+    "orbfe_map_shard_create": (_i, [C.POINTER(ProjPoints), _i, _i, C.POINTER(_vp)]),
+    "orbfe_map_shard_destroy": (None, [_vp]),
+    "orbfe_map_shard_set_frame": (_i, [_vp, C.POINTER(FrameView), _vp]),
+    "orbfe_claims_init_device": (_i, [_vp, _i, _vp, _vp]),
+    "orbfe_map_shard_pass": (_i, [_vp, C.POINTER(SearchParams), _vp, _vp, _vp]),
+    "orbfe_claims_min_peers_device": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbfe_map_shard_finish": (_i, [_vp, _vp, _vp, _vp]),
+    "orbfe_map_shard_results": (_i, [_vp, _vp, _vp, _vp]),
     "orbfe_search_by_projection_fisheye": (_i, [C.POINTER(FrameView), C.POINTER(FrameView), _vp, _vp,
                                                 C.POINTER(ProjPoints), C.POINTER(ProjPoints), C.POINTER(SearchParams),
                                                 _vp, _vp, _vp, _vp, _i]),

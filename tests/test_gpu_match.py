@@ -372,3 +372,79 @@ def test_distinctive_descriptors(orbfe, seed):
     best = orbfe.ORBmatcher.ComputeDistinctiveDescriptors(good, start)
     assert np.array_equal(best, O.distinctive_descriptors(good, start))
     assert (best == -1).sum() >= 1 and best.max() > 20
+
+
+# ---- map-sharded SearchByProjection (BASELINE config 5, second half) -------------------------------------------------
+def _sharded_search_in_process(orbfe, F, pts, bounds_of_shards, claimed, assigned, nnratio):
+    """Several orbfe.dist.ShardedProjection shards of one map driven from ONE process: every pass runs all shards
+    against the same claim table (their atomicMin updates into one table ARE the elementwise minimum)."""
+    import torch
+    import orbfe.dist as D
+    dev = torch.device("cuda:0")
+    shards = []
+    for lo, hi in bounds_of_shards:
+        sp = D.ShardedProjection({k: (v[lo:hi] if v is not None else None) for k, v in pts.items()}, lo, dev, nnratio=nnratio)
+        sp.set_frame(F)
+        shards.append(sp)
+    n = len(F.keys)
+    static = torch.where(torch.from_numpy(claimed).to(dev) != 0, -1, D.INT_MAX).to(torch.int32)
+
+    def run_pass(cin, cout):
+        for sp in shards:
+            sp.run_pass(cin, cout)
+    claims, passes = D.claim_fixpoint(run_pass, static, lambda c: c)
+    mine = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    nm = torch.zeros(1, dtype=torch.int32, device=dev)
+    for sp in shards:
+        sp.finish(mine, nm)
+    out = torch.where(mine >= 0, mine, torch.from_numpy(assigned).to(dev))
+    bi = np.concatenate([sp.results()[0] for sp in shards])
+    bd = np.concatenate([sp.results()[1] for sp in shards])
+    return int(nm.item()), out.cpu().numpy(), bi, bd, passes
+
+
+@pytest.mark.parametrize("n_map,n_frame,seed,cuts", [(3000, 800, 1, (0.5,)), (60000, 2000, 2, (0.1, 0.55, 0.56)),
+                                                     (200000, 2000, 3, (0.25, 0.5, 0.75))])
+def test_sharded_search_by_projection_equals_single_call(orbfe, n_map, n_frame, seed, cuts):
+    """The map split into contiguous shards (unequal, one nearly empty) gives the assignments, per-point results and
+    match count of orbfe_search_by_projection on the whole map -- and of the CPU oracle."""
+    d = synth.map_vs_frame(n_map, n_frame, seed)
+    rng = np.random.default_rng(seed + 50)
+    pts = _pts_from_map(d, n_map, 3.0, d["scale_factors"], rng)
+    uright = np.where(rng.uniform(size=n_frame) < 0.5, d["keys"]["x"] - 5 + rng.normal(0, 3, n_frame), -1).astype(np.float32)
+    claimed = (rng.uniform(size=n_frame) < 0.05).astype(np.uint8)
+    assigned = np.full(n_frame, -1, np.int32)
+    assigned[claimed > 0] = 10 ** 6
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], uright)
+    edges = [0] + [int(c * n_map) for c in cuts] + [n_map]
+    n, asg, bi, bd, passes = _sharded_search_in_process(orbfe, F, pts, list(zip(edges[:-1], edges[1:])), claimed, assigned, 0.8)
+    m = orbfe.ORBmatcher(nnratio=0.8, checkOri=True)
+    en, easg, ebi, ebd = m.SearchByProjection(F, pts, claimed, assigned)
+    assert n == en and n > 0.2 * min(n_frame, n_map) and passes >= 2
+    assert np.array_equal(asg, easg) and np.array_equal(bi, ebi) and np.array_equal(bd, ebd)
+    if n_map <= 60000:
+        on, oasg, obi, obd = O.search_by_projection(d["keys"], d["fdesc"], uright, d["bounds"], pts, 0, 100, 0.8, True,
+                                                    claimed, assigned, d["scale_factors"])
+        assert n == on and np.array_equal(asg, oasg) and np.array_equal(bi, obi) and np.array_equal(bd, obd)
+
+
+def test_sharded_search_conflict_chains(orbfe):
+    """Deep claim chains that cross shard boundaries (4000 points fight for 40 keypoints, 5 shards)."""
+    rng = np.random.default_rng(5)
+    n_frame, n_map = 40, 4000
+    d = synth.map_vs_frame(n_map, n_frame, 9, w=200, h=150)
+    base = d["fdesc"][rng.integers(0, n_frame, n_map)]
+    mdesc = np.stack([synth.flip_bits(b, int(rng.integers(0, 50)), rng) for b in base])
+    pts = dict(u=rng.uniform(0, 200, n_map).astype(np.float32), v=rng.uniform(0, 150, n_map).astype(np.float32),
+               ur=np.zeros(n_map, np.float32), radius=np.full(n_map, 60, np.float32),
+               min_level=np.zeros(n_map, np.int32), max_level=np.full(n_map, -1, np.int32),
+               angle=np.zeros(n_map, np.float32), valid=np.ones(n_map, np.uint8),
+               blocks=(rng.uniform(size=n_map) < 0.5).astype(np.uint8), desc=mdesc)
+    claimed = np.zeros(n_frame, np.uint8)
+    assigned = np.full(n_frame, -1, np.int32)
+    F = orbfe.FrameData(d["keys"], d["fdesc"], d["bounds"], None)
+    edges = [0, 700, 1500, 1501, 3000, n_map]
+    n, asg, bi, bd, passes = _sharded_search_in_process(orbfe, F, pts, list(zip(edges[:-1], edges[1:])), claimed, assigned, 0.9)
+    en, easg, ebi, ebd = orbfe.ORBmatcher(nnratio=0.9, checkOri=False).SearchByProjection(F, pts, claimed, assigned)
+    assert n == en and passes > 2
+    assert np.array_equal(asg, easg) and np.array_equal(bi, ebi) and np.array_equal(bd, ebd)
