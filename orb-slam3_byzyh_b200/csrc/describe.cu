@@ -27,8 +27,9 @@ __device__ const int8_t d_pattern[1024] = {
 // A lane owns 4 adjacent pixels (one aligned 32-bit word of the padded level) and walks down a
 // strip of BLUR_ROWS rows with a 7-row window in registers.  The vertical pass works on 16-bit
 // lanes, two pixels per IMAD (column sums are <= 256*255 < 2^16, so nothing crosses a lane); the
-// horizontal pass needs 24 bits and runs per pixel, its +-3 neighbours coming from the adjacent
-// lanes by shuffle.  Warps overlap by one lane on each side (lanes 0 and 31 only feed halos), so
+// horizontal pass needs 24 bits: it stays on the packed pairs and runs as two-way dot products
+// (IDP2A, 0.85 warp-instructions / clk / SMSP measured, tools/pipe_bench4.cu), its +-3 neighbours
+// coming from the adjacent lanes by shuffle.  Warps overlap by one lane on each side (lanes 0 and 31 only feed halos), so
 // a warp produces 120 columns.  No shared memory, every global access is a coalesced word.
 constexpr int BLUR_ROWS = ORBFE_BLUR_TH, BLUR_WARPS = 4, BLUR_COLS = ORBFE_BLUR_TW;   // 32 rows, 120 columns per warp
 static_assert(BLUR_COLS == 120, "one warp = 30 producing lanes x 4 pixels");
@@ -66,16 +67,30 @@ k_blur(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyr
                       r5 = (i - 1) % 7, r6 = i % 7;
             const uint32_t V01 = 18u * (w01[r0] + w01[r6]) + 34u * (w01[r1] + w01[r5]) + 48u * (w01[r2] + w01[r4]) + 56u * w01[r3];
             const uint32_t V23 = 18u * (w23[r0] + w23[r6]) + 34u * (w23[r1] + w23[r5]) + 48u * (w23[r2] + w23[r4]) + 56u * w23[r3];
+            // horizontal pass on the packed column sums: V[-4..7] as six 16-bit pairs (own, left and right neighbour
+            // lane), every output = four two-way dot products (IDP2A: two 16-bit values x two 8-bit taps, 32-bit
+            // accumulate) starting from the rounding constant -- 16 instructions for 4 pixels, no unpacking
             const uint32_t p01 = __shfl_up_sync(0xffffffffu, V01, 1), p23 = __shfl_up_sync(0xffffffffu, V23, 1);
             const uint32_t n01 = __shfl_down_sync(0xffffffffu, V01, 1), n23 = __shfl_down_sync(0xffffffffu, V23, 1);
-            // V[-3..6] as 32-bit values
-            const uint32_t vm3 = p01 >> 16, vm2 = p23 & 0xFFFFu, vm1 = p23 >> 16;
-            const uint32_t v0 = V01 & 0xFFFFu, v1 = V01 >> 16, v2 = V23 & 0xFFFFu, v3 = V23 >> 16;
-            const uint32_t v4 = n01 & 0xFFFFu, v5 = n01 >> 16, v6 = n23 & 0xFFFFu;
-            const uint32_t o0 = 18u * (vm3 + v3) + 34u * (vm2 + v2) + 48u * (vm1 + v1) + 56u * v0 + 32768u;
-            const uint32_t o1 = 18u * (vm2 + v4) + 34u * (vm1 + v3) + 48u * (v0 + v2) + 56u * v1 + 32768u;
-            const uint32_t o2 = 18u * (vm1 + v5) + 34u * (v0 + v4) + 48u * (v1 + v3) + 56u * v2 + 32768u;
-            const uint32_t o3 = 18u * (v0 + v6) + 34u * (v1 + v5) + 48u * (v2 + v4) + 56u * v3 + 32768u;
+            // tap pairs (low byte = tap of the pair's first value): kA = {(0,18), (34,48)}, kB = {(56,48), (34,18)},
+            // kC = {(18,34), (48,56)}, kD = {(48,34), (18,0)} in the (lo, hi) halves
+            const uint32_t kA = 0x30221200u, kB = 0x12223038u, kC = 0x38302212u, kD = 0x00122230u;
+            uint32_t o0 = __dp2a_lo(p01, kA, 32768u);   // 18 V[-3]
+            o0 = __dp2a_hi(p23, kA, o0);                // 34 V[-2] + 48 V[-1]
+            o0 = __dp2a_lo(V01, kB, o0);                // 56 V[0] + 48 V[1]
+            o0 = __dp2a_hi(V23, kB, o0);                // 34 V[2] + 18 V[3]
+            uint32_t o1 = __dp2a_lo(p23, kC, 32768u);   // 18 V[-2] + 34 V[-1]
+            o1 = __dp2a_hi(V01, kC, o1);                // 48 V[0] + 56 V[1]
+            o1 = __dp2a_lo(V23, kD, o1);                // 48 V[2] + 34 V[3]
+            o1 = __dp2a_hi(n01, kD, o1);                // 18 V[4]
+            uint32_t o2 = __dp2a_lo(p23, kA, 32768u);   // 18 V[-1]
+            o2 = __dp2a_hi(V01, kA, o2);                // 34 V[0] + 48 V[1]
+            o2 = __dp2a_lo(V23, kB, o2);                // 56 V[2] + 48 V[3]
+            o2 = __dp2a_hi(n01, kB, o2);                // 34 V[4] + 18 V[5]
+            uint32_t o3 = __dp2a_lo(V01, kC, 32768u);   // 18 V[0] + 34 V[1]
+            o3 = __dp2a_hi(V23, kC, o3);                // 48 V[2] + 56 V[3]
+            o3 = __dp2a_lo(n01, kD, o3);                // 48 V[4] + 34 V[5]
+            o3 = __dp2a_hi(n23, kD, o3);                // 18 V[6]
             const int y = y0 + i - 6;
             if (store && y < L.h) {
                 // bytes 2 of each accumulator = (acc >> 16) & 255
