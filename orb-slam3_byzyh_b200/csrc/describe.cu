@@ -232,14 +232,20 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
     const int u = lane - ORBFE_HALF_PATCH;
     const int au = u < 0 ? -u : u;
     // rows +v and -v together (as :106-117 does): m10 = u * (sum of the column), m01 += v * (below - above)
-    int sum = au <= 15 ? (int)c[u] : 0;   // row v = 0 (lane 31 has au == 16: idle)
+    // Lane = column: a warp load is 31 adjacent bytes of one row (one cache line).  The two row pointers walk away from
+    // the centre by one pitch per step (no per-row address arithmetic), rows outside the circular patch are read and
+    // masked instead of branched around (they lie inside the level's 19-px border).
+    const uint8_t* pp = c + u;
+    const uint8_t* pm = pp;
+    int sum = au <= 15 ? (int)pp[0] : 0;   // row v = 0 (lane 31 has au == 16: idle)
 #pragma unroll
     for (int v = 1; v <= ORBFE_HALF_PATCH; v++) {
-        if (au <= umax[v]) {
-            const int vp = c[v * L.pitch + u], vm = c[-v * L.pitch + u];
-            sum += vp + vm;
-            m01 += v * (vp - vm);
-        }
+        pp += L.pitch;
+        pm -= L.pitch;
+        const int vp = pp[0], vm = pm[0];
+        const bool in = au <= umax[v];
+        sum += in ? vp + vm : 0;
+        m01 += in ? v * (vp - vm) : 0;
     }
     m10 = u * sum;
 #pragma unroll
@@ -252,7 +258,9 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
     // ---- steered BRIEF on the blurred level (:150-203) ----
     const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :141
     const float ang = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    double sd, cd;
+    sincos((double)ang, &sd, &cd);      // one shared range reduction; the same values as sin() / cos()
+    const float a = (float)cd, b = (float)sd;
     const uint8_t* bc = blur + co;
     unsigned val = 0;
 #pragma unroll

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise `ncu -i X.ncu-rep --page raw --csv` (a `--set full` capture) per kernel and refresh
-profiles/traffic.json.  Usage: ncu_full_summary.py raw.csv frames_per_launch [traffic.json] [source-note]"""
+profiles/traffic.json.  Usage: ncu_full_summary.py raw.csv frames_per_launch [traffic.json] [source-note] [HxW]"""
 import collections
 import csv
 import json
@@ -47,18 +47,29 @@ for k, a in agg.items():
           f"dram={a['dram'] / frames / 1e6:6.3f} MB/frame")
     traffic[k] = dict(dram_bytes_per_frame=a["dram"] / frames, alu_pipe_pct=a["alu"] / t, warp_instr_per_frame=a["inst"] / frames)
 if len(sys.argv) > 3:
-    name = {"k_fast_score": "fast_score", "k_fast_nms": "fast_nms", "k_fast_cells": "fast_cells", "k_blur": "blur",
-            "k_describe": "describe", "k_octree<1>": "octree", "k_octree<0>": "octree", "k_layout": "layout"}
-    out = {}
-    pyr = dict(dram_bytes_per_frame=0.0, alu_pipe_pct=0.0, warp_instr_per_frame=0.0)
+    # MERGE into profiles/traffic.json (keyed by frame size, then by bench stage name): entries of kernels that are not
+    # in this capture stay as they are
+    name = {"k_fast_cells": "fast", "k_blur": "blur", "k_describe": "describe", "k_octree<1>": "octree",
+            "k_octree<0>": "octree", "k_layout": "layout"}
+    size = sys.argv[5] if len(sys.argv) > 5 else "480x752"
+    try:
+        allt = json.load(open(sys.argv[3]))
+    except Exception:
+        allt = {}
+    out = allt.setdefault(size, {})
+    pyr = None
     for k, v in traffic.items():
-        if k.startswith("k_level0") or k.startswith("k_resize"):
+        v["source"] = sys.argv[4] if len(sys.argv) > 4 else sys.argv[1]
+        if k.startswith("k_level0") or k.startswith("k_resize") or k.startswith("k_pyr"):
+            if pyr is None:
+                pyr = dict(dram_bytes_per_frame=0.0, alu_pipe_pct=0.0, warp_instr_per_frame=0.0, source=v["source"])
             pyr["dram_bytes_per_frame"] += v["dram_bytes_per_frame"]
             pyr["warp_instr_per_frame"] += v["warp_instr_per_frame"]
             pyr["alu_pipe_pct"] = max(pyr["alu_pipe_pct"], v["alu_pipe_pct"])
         elif k in name:
             out[name[k]] = v
-    out["pyramid"] = pyr
-    for v in out.values():
-        v["source"] = sys.argv[4] if len(sys.argv) > 4 else sys.argv[1]
-    json.dump(out, open(sys.argv[3], "w"), indent=1)
+        else:
+            out[k] = v
+    if pyr is not None:
+        out["pyramid"] = pyr
+    json.dump(allt, open(sys.argv[3], "w"), indent=1, sort_keys=True)

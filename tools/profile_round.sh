@@ -10,11 +10,11 @@ tail -3 $O/${T}_pytest.log
 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err || { echo "bench failed"; tail -5 $O/${T}_bench.err; exit 1; }
 cat $O/${T}_bench.json
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${T}_bench_ref.json 2> $O/${T}_bench_ref.err; cat $O/${T}_bench_ref.json
-SHORT="bench.py --steps 2 --warmup 3 --frames 128 --no-cpu --no-match"
+SHORT="bench.py --steps 2 --warmup 3 --frames 128 --no-cpu --no-match --no-extra"
 python $SHORT > $O/${T}_short.json 2> $O/${T}_short.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${T}_launches.csv \
     python $SHORT > $O/${T}_ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_ -c 16 -f -o $O/${T}_full \
+ncu --set full --clock-control none --import-source on -k regex:k_ -s 42 -c 14 -f -o $O/${T}_full \
     python $SHORT > $O/${T}_ncu_full.log 2>&1
 ncu -i $O/${T}_full.ncu-rep --page raw --csv > $O/${T}_full_raw.csv 2>/dev/null
 ls -la $O | tail -12
