@@ -185,6 +185,47 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
                 }
                 if (hi - lo > 7) L.fastTaps = 0;
             }
+            // source bounding boxes of the tiled resize's destination blocks
+            L.rzBoxW = L.rzBoxH = 0;
+            if (L.mode == 0 && L.fastTaps) {
+                const int words = L.pitch / 4, nxb = (words + 31) / 32, Hp = L.h + 2 * ORBFE_YOFF;
+                const int nyb = (Hp + ORBFE_RZ_DH - 1) / ORBFE_RZ_DH;
+                L.rzXblk = tapOff;
+                L.rzYblk = tapOff + (unsigned)nxb;
+                taps.resize(tapOff + nxb + nyb);
+                int boxW = 0, boxH = 0;
+                for (int xb = 0; xb < nxb; xb++) {
+                    int lo = 1 << 30, hi = 0;
+                    for (int wc = 32 * xb; wc < std::min(32 * xb + 32, words); wc++)
+                        for (int i = 0; i < 4; i++) {
+                            int p = 4 * wc - ORBFE_XOFF + i;
+                            if (p < 0) p = -p;
+                            if (p >= L.w) p = 2 * (L.w - 1) - p;
+                            p = std::max(0, std::min(p, L.w - 1));
+                            lo = std::min(lo, (int)taps[L.xtab + p].s);
+                            hi = std::max(hi, (int)taps[L.xtab + p].s1);
+                        }
+                    const int cLo = (ORBFE_XOFF + lo) & ~15;
+                    taps[L.rzXblk + xb] = OrbfeTap{(short)cLo, 0, 0, (short)(ORBFE_XOFF + hi)};
+                    boxW = std::max(boxW, ORBFE_XOFF + hi + 1 - cLo + 12);   // + the three-word window of the last thread
+                }
+                for (int yb = 0; yb < nyb; yb++) {
+                    int lo = 1 << 30, hi = 0;
+                    for (int py = ORBFE_RZ_DH * yb; py < std::min(ORBFE_RZ_DH * (yb + 1), Hp); py++) {
+                        int p = py - ORBFE_YOFF;
+                        if (p < 0) p = -p;
+                        if (p >= L.h) p = 2 * (L.h - 1) - p;
+                        p = std::max(0, std::min(p, L.h - 1));
+                        lo = std::min(lo, (int)taps[L.ytab + p].s);
+                        hi = std::max(hi, (int)taps[L.ytab + p].s1);
+                    }
+                    taps[L.rzYblk + yb] = OrbfeTap{(short)lo, 0, 0, (short)hi};
+                    boxH = std::max(boxH, hi - lo + 1);
+                }
+                tapOff += (unsigned)(nxb + nyb);
+                boxW = (boxW + 15) & ~15;
+                if (boxW <= 256 && boxH <= 256) { L.rzBoxW = boxW; L.rzBoxH = boxH; }
+            }
         }
         L.blurTileBase = blurTile;
         L.blurTilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;
@@ -256,8 +297,9 @@ int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*&
     bufs.work = (OrbfeWork*)(p + offs[10]);
     bufs.ocGlobal = ocStride ? p + offs[11] : nullptr;
     bufs.ocGlobalStride = ocStride;
-    const int mrc = orbfe_fast_make_maps(g, bufs, frames);
+    int mrc = orbfe_fast_make_maps(g, bufs, frames);
     if (mrc != ORBFE_OK) return mrc;
+    if ((mrc = orbfe_resize_make_maps(g, bufs, frames)) != ORBFE_OK) return mrc;
     cap = frames;
     return ORBFE_OK;
 }

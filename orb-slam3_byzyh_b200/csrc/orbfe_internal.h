@@ -37,6 +37,11 @@ struct OrbfeLevelGeom {
     unsigned xtab, ytab; // offsets (in entries) of the resize tables of this level
     int mode;            // resize path: 0 = bilinear taps, 1 = exact 2x2 area, 2 = identity copy
     int fastTaps;        // mode 0: every aligned group of 4 destination columns taps <= 8 adjacent source bytes
+    // tiled resize (k_resize_tile): per 128-column / 32-row block of the padded destination the bounding box of its
+    // source taps (entries of the tap table: s = first padded source column, 16-aligned / first source ROW of the
+    // block, s1 = last), and the TMA box that covers the largest of them; rzBoxW == 0: the level uses the older kernels
+    unsigned rzXblk, rzYblk;
+    int rzBoxW, rzBoxH;
     int blurTileBase, blurTilesX, blurTilesY;   // tile numbering of the blur kernel
 };
 
@@ -71,6 +76,8 @@ struct OrbfeWork {
     float angle;       // degrees
 };
 
+#define ORBFE_RZ_DW 128    // destination columns per CTA of the tiled resize (32 lanes x 4)
+#define ORBFE_RZ_DH 32     // destination rows per CTA
 #define ORBFE_BLUR_TW 120  // output columns per warp of the blur kernel
 #define ORBFE_BLUR_TH 32   // output rows per warp strip
 
@@ -83,6 +90,7 @@ struct OrbfeFastMaps {
 
 struct OrbfeChunkBufs {
     OrbfeFastMaps fastMaps;   // per level: box = one FAST cell + halo (fast.cu)
+    OrbfeFastMaps resizeMaps; // m[l]: level l as the SOURCE of level l+1's tiled resize, box = rzBoxW x rzBoxH of level l+1
     uint8_t* pyr;        // [B][pyrStride]  padded pyramid levels
     uint8_t* blur;       // [B][pyrStride]  blurred levels (same geometry, ROI only)
     uint32_t* slots;     // [B][slotsPerFrame] per-cell candidate slots (packed)
@@ -111,6 +119,7 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
                           cudaStream_t st, long long* launches, const OrbfeRectify* rect = nullptr);
 // Fills b.fastMaps for the buffer set (needs the driver's cuTensorMapEncodeTiled, resolved at run time).
 int orbfe_fast_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
+int orbfe_resize_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frames);
 int orbfe_make_level_maps(const OrbfeFrameGeom& g, const uint8_t* pyr, int frames, const int* boxW, const int* boxH,
                           OrbfeFastMaps& maps);
 // cv::FAST per cell + NMS + the minThFAST retry + ordered emission, one warp per cell (fast.cu)
