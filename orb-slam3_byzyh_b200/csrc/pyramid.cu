@@ -287,7 +287,7 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
     extern __shared__ __align__(128) uint8_t rzs[];
     const int srcBytes = (boxW * boxH + 127) & ~127;
     uint32_t* Hb = reinterpret_cast<uint32_t*>(rzs + 2 * srcBytes);          // [boxH][ORBFE_RZ_DW]; two TMA buffers before it
-    __shared__ OrbfeTap ytile[ORBFE_RZ_DH];
+    __shared__ __align__(8) OrbfeTap ytile[ORBFE_RZ_DH];
     __shared__ __align__(8) uint64_t bar[2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int words = pitch >> 2;
@@ -344,6 +344,7 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
         mbar_wait(&bar[k], ((yb - yb0) >> 1) & 1);
         // horizontal pass of every staged source row
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(rzs + k * srcBytes) + wi0;
+#pragma unroll 2
         for (int r = wid; r < nsrc; r += RZ_WARPS) {
             const uint32_t* rw = sw + r * bw4;
             const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
@@ -356,18 +357,30 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
             *reinterpret_cast<uint4*>(Hb + r * ORBFE_RZ_DW + 4 * lane) = hv;
         }
         __syncthreads();             // Hb and ytile are complete
-        // vertical pass: ((b * (H >> 4)) >> 16) == umulhi(b << 12, H & ~15) for the non-negative 11-bit weights
-        for (int i = wid; i < n; i += RZ_WARPS) {
-            const OrbfeTap ty = ytile[i];
-            const uint4 h0 = *reinterpret_cast<const uint4*>(Hb + (ty.s - rLo) * ORBFE_RZ_DW + 4 * lane);
-            const uint4 h1 = *reinterpret_cast<const uint4*>(Hb + (ty.s1 - rLo) * ORBFE_RZ_DW + 4 * lane);
-            const uint32_t b0 = (uint32_t)(uint16_t)ty.a0 << 12, b1 = (uint32_t)(uint16_t)ty.a1 << 12;
-            const uint32_t v0 = (__umulhi(b0, h0.x) + __umulhi(b1, h1.x) + 2u) >> 2;
-            const uint32_t v1 = (__umulhi(b0, h0.y) + __umulhi(b1, h1.y) + 2u) >> 2;
-            const uint32_t v2 = (__umulhi(b0, h0.z) + __umulhi(b1, h1.z) + 2u) >> 2;
-            const uint32_t v3 = (__umulhi(b0, h0.w) + __umulhi(b1, h1.w) + 2u) >> 2;
-            const uint32_t o = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
-            if (active) *reinterpret_cast<uint32_t*>(dbase + (size_t)(py0 + i) * pitch + 4 * wc) = o;
+        // vertical pass: ((b * (H >> 4)) >> 16) == umulhi(b << 12, H & ~15) for the non-negative 11-bit weights; the two
+        // products and the rounding constant are one chain of mad.hi (IMAD.HI with addend)
+        {
+            uint8_t* drow = dbase + (size_t)(py0 + wid) * pitch + 4 * wc;
+            const uint32_t* hl = Hb + 4 * lane - rLo * ORBFE_RZ_DW;
+#pragma unroll 4
+            for (int i = wid; i < n; i += RZ_WARPS, drow += (size_t)RZ_WARPS * pitch) {
+                const uint2 tq = *reinterpret_cast<const uint2*>(&ytile[i]);      // {s, a0}, {a1, s1} as 16-bit halves
+                const uint4 h0 = *reinterpret_cast<const uint4*>(hl + (int)(short)(tq.x & 0xFFFFu) * ORBFE_RZ_DW);
+                const uint4 h1 = *reinterpret_cast<const uint4*>(hl + (int)(short)(tq.y >> 16) * ORBFE_RZ_DW);
+                const uint32_t b0 = (tq.x >> 16) << 12, b1 = (tq.y & 0xFFFFu) << 12;
+                uint32_t v0, v1, v2, v3;
+                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v0) : "r"(b0), "r"(h0.x));
+                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v1) : "r"(b0), "r"(h0.y));
+                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v2) : "r"(b0), "r"(h0.z));
+                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v3) : "r"(b0), "r"(h0.w));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v0) : "r"(b1), "r"(h1.x));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v1) : "r"(b1), "r"(h1.y));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v2) : "r"(b1), "r"(h1.z));
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v3) : "r"(b1), "r"(h1.w));
+                // bytes: (v >> 2) & 255 of the four sums (each < 1024)
+                const uint32_t lo = __byte_perm(v0 >> 2, v1 >> 2, 0x0040), hi = __byte_perm(v2 >> 2, v3 >> 2, 0x0040);
+                if (active) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x5410);
+            }
         }
         __syncthreads();             // Hb / ytile are free for the next block
     }
