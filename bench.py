@@ -456,6 +456,97 @@ def device_leg(torch, orbfe, dev, local, frames, steps, warmup, barrier, max_ove
                 roofline=roofline)
 
 
+def pairs_leg(torch, orbfe, dev, local, kind, B, steps, barrier, max_over_ranks, world, rank):
+    """BASELINE configs 2 / 3 as batches of independent stereo pairs (frame pairs shard over the ranks, no collective):
+    c2 = 752x480 rectified pairs, nFeatures 1200, lapping {0,0}: left + right extraction + Frame::ComputeStereoMatches;
+    c3 = 512x512 fisheye-style pairs, nFeatures 1500, lapping {0,511}: left + right extraction + the kNN-2 / 0.7 ratio
+    matcher of Frame::ComputeStereoFishEyeMatches.  Device-resident (images in HBM) and end to end (pinned host images
+    in, keypoints / descriptors / matches out, copies inside the timed region)."""
+    import synth
+    from orbfe import _lib
+    if kind == "c2":
+        h, w, nf, lap, gen = 480, 752, 1200, (0, 0), synth.stereo_pair
+        label = "C2 752x480 x2 rectified pairs, nFeatures=1200, L/R extraction + ComputeStereoMatches"
+    else:
+        h, w, nf, lap, gen = 512, 512, 1500, (0, 511), synth.shifted_pair
+        label = "C3 512x512 x2 fisheye-style pairs, nFeatures=1500, lapping {0,511}, L/R extraction + kNN-2 + 0.7 ratio"
+    base = [gen(h, w, 11 + i + 100 * rank) for i in range(8)]
+    rng = np.random.default_rng(3 + rank)
+    L, R = np.empty((B, h, w), np.uint8), np.empty((B, h, w), np.uint8)
+    for i in range(B):
+        a, b = base[i % len(base)]
+        k = 0 if i < len(base) else int(rng.integers(1, h))       # the same row shift on both images keeps the geometry
+        L[i], R[i] = np.roll(a, k, axis=0), np.roll(b, k, axis=0)
+    hL, hR = torch.from_numpy(L).pin_memory(), torch.from_numpy(R).pin_memory()
+    exL, exR = orbfe.ORBextractor(nf, device=local), orbfe.ORBextractor(nf, device=local)
+    for ex in (exL, exR):
+        ex.set_max_bytes(64 << 30)
+    cap = exL.capacity
+    st = torch.cuda.Stream(device=dev)
+    mk = lambda *shape, dt=torch.uint8: torch.empty(shape, dtype=dt, device=dev)
+    dL, dR = hL.to(dev), hR.to(dev)
+    oL = (mk(B, cap, 28), mk(B, cap, 32), mk(B, dt=torch.int32), mk(B, dt=torch.int32))
+    oR = (mk(B, cap, 28), mk(B, cap, 32), mk(B, dt=torch.int32), mk(B, dt=torch.int32))
+    mbf, mb = 47.9, 47.9 / 435.2
+    res = {}
+
+    def step(imgL, imgR):
+        exL.extract_batch_device(imgL, lap, oL[0], oL[1], oL[2], oL[3], st)
+        exR.extract_batch_device(imgR, lap, oR[0], oR[1], oR[2], oR[3], st)
+        if kind == "c2":
+            res["m"] = orbfe.ORBmatcher.ComputeStereoMatchesBatchDevice(exL, exR, oL[0], oL[1], oL[2], oR[0], oR[1], oR[2], mbf, mb, st)
+        else:
+            res["m"] = orbfe.ORBmatcher.knn2_batch_device(oL[1], oL[3], oL[2], oR[1], oR[3], oR[2], st)
+    for _ in range(3):
+        step(dL, dR)
+    st.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        step(dL, dR)
+    e1.record(st)
+    st.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    if kind == "c2":
+        matched = float((res["m"][0] >= 0).sum().item()) / B
+    else:
+        matched = float((res["m"][2] >= 0).sum().item()) / B
+    # end to end: pinned host images in, results out, every step
+    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (oL[0], oL[1], oL[2], oR[0], oR[1], oR[2])]
+    host_m = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res["m"]]
+    iL, iR = torch.empty_like(dL), torch.empty_like(dR)
+
+    def e2e_step():
+        with torch.cuda.stream(st):
+            iL.copy_(hL, non_blocking=True)
+            iR.copy_(hR, non_blocking=True)
+        step(iL, iR)
+        with torch.cuda.stream(st):
+            for d, s_ in zip(host_out, (oL[0], oL[1], oL[2], oR[0], oR[1], oR[2])):
+                d.copy_(s_, non_blocking=True)
+            for d, s_ in zip(host_m, res["m"]):
+                d.copy_(s_, non_blocking=True)
+        st.synchronize()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    dt = time.perf_counter() - t0
+    barrier()
+    e2e_ms = max_over_ranks(dt * 1e3) / steps
+    h2d = 2 * B * h * w
+    d2h = sum(t.numel() * t.element_size() for t in host_out + host_m)
+    return {"metric": "stereo pairs/s (" + label + ")", "value": world * B / (ms / 1e3), "unit": "pairs/s", "n_gpus": world,
+            "ms_per_step": ms, "pairs_per_gpu_per_step": B, "matches_per_pair": matched,
+            "keypoints_per_frame": float(oL[2].float().mean().item()),
+            "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "how": "one blocking step: H2D of both image batches, 2 extractions + matcher, D2H of all results"},
+            "residency": "value: images resident in HBM, CUDA events on the launching stream, max over ranks"}
+
+
 def copy_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps, barrier, max_over_ranks):
     """What the host link alone allows: the step's H2D and D2H volumes copied concurrently on two streams from / into
     pinned memory, no kernels; with N ranks all ranks copy at the same time (one host, shared root complex / memory)."""
@@ -620,6 +711,15 @@ def run_ours(args):
                          "fast_candidates_per_frame": oleg["C"], "clocks": oleg["clk"], "roofline": oleg["roofline"],
                          "residency": "device-resident (frames in HBM), CUDA events on the launching stream, max over ranks"}}
         set_workload(args.workload)
+        del oleg
+        torch.cuda.empty_cache()
+        for kind in ("c2", "c3"):
+            try:
+                extra[kind] = pairs_leg(torch, orbfe, dev, local, kind, 256, max(3, min(args.steps, 10)), barrier, max_over_ranks,
+                                        world, rank)
+            except Exception as e:      # reported, never fatal for the headline
+                extra[kind] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:

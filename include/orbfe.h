@@ -404,6 +404,25 @@ typedef struct OrbfeTriParams {
 int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const OrbfeTriSide* kf2,
                                    const OrbfeTriParams* prm, int32_t* matches12, int device);
 
+/* Batches of stereo pairs that never leave the device (the frame-pair shards of BASELINE configs 2 and 3).
+ * orbfe_stereo_match_batch_device: Frame::ComputeStereoMatches (src/Frame.cc:1102-1358) for pairs 0 .. B-1 on the
+ * pyramids both extractors hold from their last orbfe_extract_batch_device call (one chunk) and on that call's output
+ * slabs (`capacity` rows per frame, d_n_l[b] / d_n_r[b] valid rows); writes mvuRight / mvDepth into [B][capacity] float
+ * slabs.  Enqueued on `stream` (0 = the left extractor's stream); the caller orders it after both extractions.
+ * orbfe_knn2_batch_device: the brute-force kNN-2 + 0.7 ratio test of Frame::ComputeStereoFishEyeMatches
+ * (src/Frame.cc:1545-1562: BFMatcher(NORM_HAMMING).knnMatch(left rows [monoLeft, n), right rows [monoRight, n), 2)) for
+ * B pairs: per pair the row ranges [begin, end) of the two descriptor slabs; idx2 / dist2 ([B][capacity][2]) and match
+ * ([B][capacity], -1 = ratio test failed) are indexed by query row - begin, train indices are relative to t_begin
+ * (the row numbers BFMatcher reports). */
+int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right, int B,
+                                    const OrbfeKeyPoint* d_keys_l, const uint8_t* d_desc_l, const int* d_n_l,
+                                    const OrbfeKeyPoint* d_keys_r, const uint8_t* d_desc_r, const int* d_n_r,
+                                    int capacity, float mbf, float mb, float* d_u_right, float* d_depth,
+                                    void* stream);
+int orbfe_knn2_batch_device(const uint8_t* d_desc_q, const int* d_q_begin, const int* d_q_end,
+                            const uint8_t* d_desc_t, const int* d_t_begin, const int* d_t_end, int B,
+                            int capacity, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, void* stream);
+
 /* void Frame::ComputeStereoMatches()  include/Frame.h:116, src/Frame.cc:1102-1358.  Uses the
  * device-resident pyramids (frame `frame` of each extractor's last call) of the left/right
  * extractors, as the reference reads mpORBextractor{Left,Right}->mvImagePyramid.

@@ -202,6 +202,68 @@ __global__ void k_knn2_merge_peers(PeerTabs P, int G, int nq, int32_t* __restric
     if (match) match[q] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
 }
 
+// Frame::ComputeStereoFishEyeMatches' brute force (Frame.cc:1545-1562) for a BATCH of stereo pairs resident in HBM:
+// pair b matches rows [qBegin[b], qEnd[b]) of its left descriptor slab (the lapping-area keypoints: monoIndex .. n)
+// against rows [tBegin[b], tEnd[b]) of the right one.  grid = (query blocks, pairs); a CTA keeps 256 queries in
+// registers and walks the pair's whole train range (a frame holds a few thousand rows: no partial tables to merge).
+// Indices are relative to the range starts, as cv::BFMatcher numbers the rows of the two sub-matrices.
+__global__ void __launch_bounds__(KNN_THREADS)
+k_knn2_batch(const uint32_t* __restrict__ descQ, const int* __restrict__ qBegin, const int* __restrict__ qEnd,
+             const uint32_t* __restrict__ descT, const int* __restrict__ tBegin, const int* __restrict__ tEnd, int capacity,
+             int32_t* __restrict__ idx2, int32_t* __restrict__ dist2, int32_t* __restrict__ match) {
+    __shared__ __align__(16) uint32_t tile[KNN_TILE * 8];
+    const size_t b = blockIdx.y, slab = b * (size_t)capacity;
+    const int qb = max(qBegin[b], 0), nq = min(qEnd[b], capacity) - qb;
+    const int tb = max(tBegin[b], 0), nt = min(tEnd[b], capacity) - tb;
+    if ((int)(blockIdx.x * KNN_QB) >= nq) return;          // uniform per CTA
+    const uint32_t* query = descQ + 8 * (slab + qb);
+    const uint32_t* train = descT + 8 * (slab + tb);
+    const int q0 = blockIdx.x * KNN_QB + threadIdx.x;
+    uint32_t qv[KNN_QPT][8];
+    uint32_t b0[KNN_QPT], b1[KNN_QPT];
+#pragma unroll
+    for (int r = 0; r < KNN_QPT; r++) {
+        const int q = min(q0 + r * KNN_THREADS, nq - 1);
+        const uint4* p = reinterpret_cast<const uint4*>(query + 8 * (size_t)q);
+        *reinterpret_cast<uint4*>(qv[r]) = p[0];
+        *reinterpret_cast<uint4*>(qv[r] + 4) = p[1];
+        b0[r] = KEY_NONE;
+        b1[r] = KEY_NONE;
+    }
+    for (int t0 = 0; t0 < nt; t0 += KNN_TILE) {
+        const int cnt = min(KNN_TILE, nt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += KNN_THREADS)
+            reinterpret_cast<uint4*>(tile)[i] = reinterpret_cast<const uint4*>(train + 8 * (size_t)t0)[i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            uint32_t tv[8];
+            *reinterpret_cast<uint4*>(tv) = reinterpret_cast<const uint4*>(tile)[2 * j];
+            *reinterpret_cast<uint4*>(tv + 4) = reinterpret_cast<const uint4*>(tile)[2 * j + 1];
+            const uint32_t jj = (uint32_t)(t0 + j);
+#pragma unroll
+            for (int r = 0; r < KNN_QPT; r++) {
+                const uint32_t key = ((uint32_t)hamming256_csa(qv[r], tv) << KEY_SHIFT) | jj;
+                top2_insert(b0[r], b1[r], key);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KNN_QPT; r++) {
+        const int q = q0 + r * KNN_THREADS;
+        if (q >= nq) continue;
+        const uint32_t k0 = b0[r], k1 = b1[r];
+        const int i0 = k0 == KEY_NONE ? -1 : (int)(k0 & ((1u << KEY_SHIFT) - 1)), i1 = k1 == KEY_NONE ? -1 : (int)(k1 & ((1u << KEY_SHIFT) - 1));
+        const int d0 = k0 == KEY_NONE ? -1 : (int)(k0 >> KEY_SHIFT), d1 = k1 == KEY_NONE ? -1 : (int)(k1 >> KEY_SHIFT);
+        const size_t o = slab + q;
+        idx2[2 * o] = i0; idx2[2 * o + 1] = i1;
+        dist2[2 * o] = d0; dist2[2 * o + 1] = d1;
+        // Frame.cc:1562  `(*it)[0].distance < (*it)[1].distance * 0.7` (float * double)
+        if (match) match[o] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
+    }
+}
+
 int mfail(int code, const char* what, cudaError_t e = cudaSuccess) { return orbfe_fail(code, what, e); }
 #define MCK(call)                                                        \
     do {                                                                 \
@@ -282,6 +344,20 @@ int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, in
     orbfe_knn2_enqueue(d_query, nq, d_train, nt, train_offset, d_idx2, d_dist2, nullptr, partial, st);
     MCK(cudaGetLastError());
     MCK(cudaFreeAsync(partial, st));
+    return ORBFE_OK;
+}
+
+int orbfe_knn2_batch_device(const uint8_t* d_desc_q, const int* d_q_begin, const int* d_q_end, const uint8_t* d_desc_t,
+                            const int* d_t_begin, const int* d_t_end, int B, int capacity, int32_t* d_idx2, int32_t* d_dist2,
+                            int32_t* d_match, void* stream) {
+    if (B <= 0) return ORBFE_OK;
+    if (capacity <= 0 || capacity >= (1 << KEY_SHIFT) || !d_desc_q || !d_q_begin || !d_q_end || !d_desc_t || !d_t_begin || !d_t_end ||
+        !d_idx2 || !d_dist2)
+        return mfail(ORBFE_ERR_INVALID, "bad arguments");
+    k_knn2_batch<<<dim3((capacity + KNN_QB - 1) / KNN_QB, B), KNN_THREADS, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)d_desc_q, d_q_begin, d_q_end, (const uint32_t*)d_desc_t, d_t_begin, d_t_end, capacity, d_idx2, d_dist2,
+        d_match);
+    MCK(cudaGetLastError());
     return ORBFE_OK;
 }
 

@@ -450,6 +450,7 @@ void orbfe_extractor_destroy(OrbfeExtractor* e) {
     if (e->slab2) cudaFree(e->slab2);
     if (e->d_taps) cudaFree(e->d_taps);
     if (e->d_cells) cudaFree(e->d_cells);
+    if (e->d_stereoSad) cudaFree(e->d_stereoSad);
     for (int s = 0; s < 2; s++) {
         if (e->d_in[s]) cudaFree(e->d_in[s]);
         if (e->d_okps[s]) cudaFree(e->d_okps[s]);
@@ -880,6 +881,38 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     }
     if (e == cudaSuccess) e = S.download();
     if (e != cudaSuccess) return fail(ORBFE_ERR_CUDA, "stereo match", e);
+    return ORBFE_OK;
+}
+
+// Frame::ComputeStereoMatches for a BATCH of rectified pairs that never leaves the device: the pyramids both extractors
+// hold from their last orbfe_extract_batch_device call (one chunk: frames 0 .. B-1) and that call's output slabs.
+int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right, int B, const OrbfeKeyPoint* d_keys_l,
+                                    const uint8_t* d_desc_l, const int* d_n_l, const OrbfeKeyPoint* d_keys_r,
+                                    const uint8_t* d_desc_r, const int* d_n_r, int capacity, float mbf, float mb,
+                                    float* d_u_right, float* d_depth, void* stream) {
+    int rc = check_handle(left);
+    if (rc) return rc;
+    if (!right || right->device != left->device) return fail(ORBFE_ERR_INVALID, "left/right extractors must live on one device");
+    if (!left->haveGeom || !right->haveGeom || left->g.rows != right->g.rows || left->g.cols != right->g.cols ||
+        left->nlevels != right->nlevels || left->scaleFactor != right->scaleFactor)
+        return fail(ORBFE_ERR_INVALID, "left/right extractors hold different pyramid geometries");
+    if (B <= 0 || B > left->lastFrames || B > right->lastFrames || B > left->chunkCap || B > right->chunkCap)
+        return fail(ORBFE_ERR_INVALID, "the pairs must be the frames of the last (single-chunk) extract call of both extractors");
+    if (capacity <= 0 || capacity >= 65536 || !d_keys_l || !d_desc_l || !d_n_l || !d_keys_r || !d_desc_r || !d_n_r || !d_u_right || !d_depth)
+        return fail(ORBFE_ERR_INVALID, "bad arguments (capacity must be < 65536)");
+    cudaStream_t st = stream ? (cudaStream_t)stream : left->sCompute;
+    const size_t need = (size_t)B * capacity;
+    if (need > left->stereoSadElems) {
+        CK(cudaStreamSynchronize(st));
+        if (left->d_stereoSad) cudaFree(left->d_stereoSad);
+        left->d_stereoSad = nullptr; left->stereoSadElems = 0;
+        CK(cudaMalloc(&left->d_stereoSad, need * sizeof(int)));
+        left->stereoSadElems = need;
+    }
+    orbfe_launch_stereo_batch(left->g, left->bufs.pyr, right->bufs.pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
+                              (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad, st);
+    left->launches += 2;
+    CK(cudaGetLastError());
     return ORBFE_OK;
 }
 

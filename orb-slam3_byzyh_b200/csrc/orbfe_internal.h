@@ -157,6 +157,8 @@ struct OrbfeExtractor {
     OrbfeFrameGeom g;
     OrbfeTap* d_taps = nullptr;
     OrbfeFastCell* d_cells = nullptr;   // per-cell FAST geometry of the current frame size
+    int* d_stereoSad = nullptr;          // scratch of orbfe_stereo_match_batch_device (grow only)
+    size_t stereoSadElems = 0;
     size_t perFrameBytes = 0;
 
     OrbfeChunkBufs bufs = {};
@@ -227,3 +229,7 @@ void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uin
                          const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
                          const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
                          int* sad, cudaStream_t st);
+void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
+                               const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
+                               const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
+                               float* depth, int* sad, cudaStream_t st);

@@ -18,8 +18,7 @@ namespace {
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;  // ORBmatcher.cc:36-37
 
-__global__ void __launch_bounds__(256)
-k_stereo(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL,
+__device__ __forceinline__ void stereo_one(const OrbfeFrameGeom& g, const uint8_t* __restrict__ pyrL,
          const uint8_t* __restrict__ pyrR, const OrbfeKeyPoint* __restrict__ keysL,
          const uint32_t* __restrict__ descL, int N, const OrbfeKeyPoint* __restrict__ keysR,
          const uint32_t* __restrict__ descR, int Nr, float mbf, float mb, float* __restrict__ uRight,
@@ -128,9 +127,43 @@ k_stereo(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ p
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_stereo(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL,
+         const uint8_t* __restrict__ pyrR, const OrbfeKeyPoint* __restrict__ keysL,
+         const uint32_t* __restrict__ descL, int N, const OrbfeKeyPoint* __restrict__ keysR,
+         const uint32_t* __restrict__ descR, int Nr, float mbf, float mb, float* __restrict__ uRight,
+         float* __restrict__ depth, int* __restrict__ sadOut) {
+    stereo_one(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sadOut);
+}
+
+// The same for a batch of rectified pairs whose pyramids, keypoints and descriptors are resident in HBM (the output
+// slabs of orbfe_extract_batch_device: `capacity` rows per frame, nL[b] / nR[b] valid): grid.y = pair.
+__global__ void __launch_bounds__(256)
+k_stereo_batch(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
+               const OrbfeKeyPoint* __restrict__ keysL, const uint32_t* __restrict__ descL, const int* __restrict__ nL,
+               const OrbfeKeyPoint* __restrict__ keysR, const uint32_t* __restrict__ descR, const int* __restrict__ nR,
+               int capacity, float mbf, float mb, float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sadOut) {
+    const size_t b = blockIdx.y, o = b * (size_t)capacity;
+    stereo_one(g, pyrL + b * g.pyrStride, pyrR + b * g.pyrStride, keysL + o, descL + 8 * o, min(nL[b], capacity), keysR + o,
+               descR + 8 * o, min(nR[b], capacity), mbf, mb, uRight + o, depth + o, sadOut + o);
+}
+
+__device__ __forceinline__ void stereo_median_one(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad);
+
 // Median-based outlier cut (:1343-1357): median = sorted (SAD, iL) pairs [size/2].first.
 __global__ void __launch_bounds__(1024)
 k_stereo_median(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad) {
+    stereo_median_one(N, uRight, depth, sad);
+}
+
+__global__ void __launch_bounds__(1024)
+k_stereo_median_batch(const int* __restrict__ nL, int capacity, float* __restrict__ uRight, float* __restrict__ depth,
+                      const int* __restrict__ sad) {
+    const size_t o = (size_t)blockIdx.x * capacity;
+    stereo_median_one(min(nL[blockIdx.x], capacity), uRight + o, depth + o, sad + o);
+}
+
+__device__ __forceinline__ void stereo_median_one(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad) {
     __shared__ int s_cnt, s_median;
     if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
     __syncthreads();
@@ -170,4 +203,13 @@ void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uin
                          int* sad, cudaStream_t st) {
     k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad);
     k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+}
+
+void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
+                               const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
+                               const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
+                               float* depth, int* sad, cudaStream_t st) {
+    k_stereo_batch<<<dim3((capacity + 7) / 8, B), 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, nL, keysR, descR, nR, capacity, mbf,
+                                                              mb, uRight, depth, sad);
+    k_stereo_median_batch<<<B, 1024, 0, st>>>(nL, capacity, uRight, depth, sad);
 }

@@ -139,6 +139,8 @@ _SIGS = {
     "orbfe_kb8_project": (_i, [_vp, _vp, _i, _vp, _i]),
     "orbfe_kb8_unproject": (_i, [_vp, _f, _vp, _i, _vp, _i]),
     "orbfe_kb8_triangulate_matches": (_i, [_vp, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
+    "orbfe_stereo_match_batch_device": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
+    "orbfe_knn2_batch_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),
 }
 EXPORTS = tuple(_SIGS)

@@ -290,3 +290,30 @@ class ORBmatcher:
         check(lib().orbfe_stereo_match(exL.handle, exR.handle, frame, ptr(keysL), ptr(descL), len(keysL), ptr(keysR),
                                        ptr(descR), len(keysR), mbf, mb, ptr(ur), ptr(dp)))
         return ur, dp
+
+    # The same for a batch of rectified pairs resident in HBM (device tensors: the output slabs of two
+    # ORBextractor.extract_batch_device calls on the same stream) -> (uRight, depth) [B, capacity] float32 CUDA tensors
+    @staticmethod
+    def ComputeStereoMatchesBatchDevice(exL, exR, d_kpsL, d_descL, d_nL, d_kpsR, d_descR, d_nR, mbf, mb, stream=None):
+        import torch
+        B, cap = d_kpsL.shape[0], d_kpsL.shape[1]
+        ur = torch.empty((B, cap), dtype=torch.float32, device=d_kpsL.device)
+        dp = torch.empty_like(ur)
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        check(lib().orbfe_stereo_match_batch_device(exL.handle, exR.handle, B, ptr(d_kpsL), ptr(d_descL), ptr(d_nL), ptr(d_kpsR),
+                                                    ptr(d_descR), ptr(d_nR), cap, mbf, mb, ptr(ur), ptr(dp), st))
+        return ur, dp
+
+    # Frame::ComputeStereoFishEyeMatches' kNN-2 + ratio test (Frame.cc:1545-1562) for a batch of pairs resident in HBM:
+    # queries = left rows [monoL[b], nL[b]), train = right rows [monoR[b], nR[b]) -> idx2, dist2 [B, cap, 2], match [B, cap]
+    @staticmethod
+    def knn2_batch_device(d_descL, d_monoL, d_nL, d_descR, d_monoR, d_nR, stream=None):
+        import torch
+        B, cap = d_descL.shape[0], d_descL.shape[1]
+        idx2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
+        dist2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
+        match = torch.full((B, cap), -1, dtype=torch.int32, device=d_descL.device)
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        check(lib().orbfe_knn2_batch_device(ptr(d_descL), ptr(d_monoL), ptr(d_nL), ptr(d_descR), ptr(d_monoR), ptr(d_nR), B, cap,
+                                            ptr(idx2), ptr(dist2), ptr(match), st))
+        return idx2, dist2, match

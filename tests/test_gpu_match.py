@@ -448,3 +448,73 @@ def test_sharded_search_conflict_chains(orbfe):
     en, easg, ebi, ebd = orbfe.ORBmatcher(nnratio=0.9, checkOri=False).SearchByProjection(F, pts, claimed, assigned)
     assert n == en and passes > 2
     assert np.array_equal(asg, easg) and np.array_equal(bi, ebi) and np.array_equal(bd, ebd)
+
+
+# ---- batched, device-resident stereo (BASELINE configs 2 and 3 as frame-pair batches) ---------------------------------
+def _extract_pairs_device(orbfe, lefts, rights, nf, lap):
+    import torch
+    from orbfe._lib import KP_DTYPE
+    dev = torch.device("cuda:0")
+    exL, exR = orbfe.ORBextractor(nf), orbfe.ORBextractor(nf)
+    cap = exL.capacity
+    st = torch.cuda.Stream(device=dev)
+    out = []
+    for ex, frames in ((exL, lefts), (exR, rights)):
+        B = len(frames)
+        d_img = torch.from_numpy(np.stack(frames)).to(dev)
+        d_kps = torch.empty((B, cap, 28), dtype=torch.uint8, device=dev)
+        d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+        d_n = torch.empty(B, dtype=torch.int32, device=dev)
+        d_mono = torch.empty(B, dtype=torch.int32, device=dev)
+        ex.extract_batch_device(d_img, lap, d_kps, d_desc, d_n, d_mono, st)
+        out.append((d_img, d_kps, d_desc, d_n, d_mono))
+    return exL, exR, st, out[0], out[1], KP_DTYPE
+
+
+def test_stereo_match_batch_device_equals_per_pair_calls(orbfe):
+    """64 rectified pairs: orbfe_stereo_match_batch_device on the device-resident pyramids / output slabs equals the
+    per-pair host call (orbfe_stereo_match, itself pinned to the reference's ComputeStereoMatches) bit for bit."""
+    B = 64
+    pairs = [synth.stereo_pair(240, 376, 100 + i) for i in range(B)]
+    exL, exR, st, L, R, KP = _extract_pairs_device(orbfe, [p[0] for p in pairs], [p[1] for p in pairs], 600, (0, 0))
+    mbf, mb = 47.9, 47.9 / 435.2
+    ur, dp = orbfe.ORBmatcher.ComputeStereoMatchesBatchDevice(exL, exR, L[1], L[2], L[3], R[1], R[2], R[3], mbf, mb, st)
+    st.synchronize()
+    ur, dp = ur.cpu().numpy(), dp.cpu().numpy()
+    nL, nR = L[3].cpu().numpy(), R[3].cpu().numpy()
+    kL, kR = L[1].cpu().numpy().view(KP).reshape(B, -1), R[1].cpu().numpy().view(KP).reshape(B, -1)
+    dL, dR = L[2].cpu().numpy(), R[2].cpu().numpy()
+    matched = 0
+    for b in range(B):
+        eur, edp = orbfe.ORBmatcher.ComputeStereoMatches(exL, exR, kL[b, :nL[b]], dL[b, :nL[b]], kR[b, :nR[b]], dR[b, :nR[b]],
+                                                         mbf, mb, frame=b)
+        assert np.array_equal(ur[b, :nL[b]].view(np.uint32), eur.view(np.uint32)), b
+        assert np.array_equal(dp[b, :nL[b]].view(np.uint32), edp.view(np.uint32)), b
+        matched += int((eur >= 0).sum())
+    assert matched > 20 * B
+
+
+def test_knn2_batch_device_equals_per_pair_calls(orbfe):
+    """32 fisheye-style pairs with a lapping area: the batched kNN-2 + ratio test over rows [mono, n) of both sides equals
+    the per-pair orbfe_knn2 (pinned to cv2's BFMatcher) and the CPU oracle."""
+    B = 32
+    pairs = [synth.shifted_pair(256, 256, 200 + i) for i in range(B)]
+    exL, exR, st, L, R, KP = _extract_pairs_device(orbfe, [p[0] for p in pairs], [p[1] for p in pairs], 700, (60, 200))
+    idx2, dist2, match = orbfe.ORBmatcher.knn2_batch_device(L[2], L[4], L[3], R[2], R[4], R[3], st)
+    st.synchronize()
+    idx2, dist2, match = idx2.cpu().numpy(), dist2.cpu().numpy(), match.cpu().numpy()
+    nL, nR, mL, mR = (t.cpu().numpy() for t in (L[3], R[3], L[4], R[4]))
+    dL, dR = L[2].cpu().numpy(), R[2].cpu().numpy()
+    m = orbfe.ORBmatcher()
+    total = 0
+    for b in range(B):
+        q, t = dL[b, mL[b]:nL[b]], dR[b, mR[b]:nR[b]]
+        assert len(q) > 50 and len(t) > 50 and mL[b] > 0
+        eidx, edist, ematch = m.knn2(q, t)
+        k = len(q)
+        assert np.array_equal(idx2[b, :k], eidx) and np.array_equal(dist2[b, :k], edist) and np.array_equal(match[b, :k], ematch)
+        if b < 4:
+            om, oidx, odist = O.fisheye_matches(q, t)
+            assert np.array_equal(eidx, oidx) and np.array_equal(edist, odist) and np.array_equal(ematch, om)
+        total += int((ematch >= 0).sum())
+    assert total > 10 * B
