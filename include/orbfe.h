@@ -377,9 +377,8 @@ int orbfe_search_by_bow(const OrbfeBowSide* a, const OrbfeBowSide* b, int th_low
                         int32_t* match_a_right, int device);
 
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
- * const bool bOnlyStereo, const bool bCoarse)   include/ORBmatcher.h:76-77, src/ORBmatcher.cc:1046-1324, for pinhole
- * keyframes (mpCamera2 == NULL; the fisheye rig branch :1173-1202 needs KannalaBrandt8::epipolarConstrain, SURVEY 8(f)
- * rank 4).  Each side: mvKeysUn, mDescriptors, mvuRight (NULL = monocular), has_map_point[i] = (GetMapPoint(i) != NULL),
+ * const bool bOnlyStereo, const bool bCoarse)   include/ORBmatcher.h:76-77, src/ORBmatcher.cc:1046-1324; pinhole
+ * keyframes (mpCamera2 == NULL) with prm->rig == NULL, fisheye stereo rigs with prm->rig set (below).  Each side: mvKeysUn, mDescriptors, mvuRight (NULL = monocular), has_map_point[i] = (GetMapPoint(i) != NULL),
  * mFeatVec.  f12 = the fundamental matrix of Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:191-194:
  * K1^-T * hat(t12) * R12 * K2^-1, row major; it is constant per keyframe pair and stays on the host with Eigen),
  * epipole = pKF2->mpCamera->project(T2w * Cw) (:1063), scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors /
@@ -393,6 +392,22 @@ typedef struct OrbfeTriSide {
     const uint8_t* has_map_point;
     OrbfeFeatureVector fv;
 } OrbfeTriSide;
+/* The two-camera branch (pKF1->mpCamera2 && pKF2->mpCamera2: KannalaBrandt8 stereo rigs, src/ORBmatcher.cc:1071-1095,
+ * 1160-1241): each side's keys / desc rows are [mvKeys (left camera, n_left of them) | mvKeysRight], no keypoint is
+ * "stereo" (:1121, :1175), the epipole-distance gate is skipped (:1196) and the epipolar gate is
+ * KannalaBrandt8::epipolarConstrain (src/CameraModels/KannalaBrandt8.cpp:322-328: TriangulateMatches(...) > 0.0001f) with
+ * the cameras and the relative pose of the (bRight1, bRight2) combination: pair[2 * bRight1 + bRight2] = {camera of kp1,
+ * camera of kp2, R12, t12} = {ll, lr, rl, rr} (:1205-1239).  level_sigma2_1 = pKF1->mvLevelSigma2. */
+typedef struct OrbfeTriCameraPair {
+    float params1[8], params2[8];
+    float precision1, precision2;
+    float R12[9], t12[3];
+} OrbfeTriCameraPair;
+typedef struct OrbfeTriRig {
+    int32_t n_left1, n_left2;
+    const float* level_sigma2_1;
+    OrbfeTriCameraPair pair[4];
+} OrbfeTriRig;
 typedef struct OrbfeTriParams {
     float f12[9];
     float epipole[2];
@@ -400,6 +415,7 @@ typedef struct OrbfeTriParams {
     const float* level_sigma2_2;
     int32_t n_levels;
     int32_t only_stereo, coarse, check_orientation, th_low;
+    const OrbfeTriRig* rig; /* NULL: pinhole keyframes (mpCamera2 == NULL) */
 } OrbfeTriParams;
 int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const OrbfeTriSide* kf2,
                                    const OrbfeTriParams* prm, int32_t* matches12, int device);
@@ -490,6 +506,11 @@ int orbfe_kb8_triangulate_matches(const float* params1, float precision1, const 
                                   float precision2, const float* R12, const float* t12,
                                   const float* pt1, const float* pt2, const float* sigma1,
                                   const float* unc2, int n, float* depth, float* p3d, int device);
+
+/* Stage tap of the triangulation: the homogeneous solutions x (4 doubles each, the right singular vector of the smallest
+ * singular value) of n row-major 4 x 4 float systems -- the step where the reference calls Eigen::JacobiSVD<Matrix4f>
+ * (KannalaBrandt8.cpp:566-568); the oracle's restatement of that step is compared with it bit for bit. */
+int orbfe_debug_kb8_null_vectors(const float* A, int n, double* x, int device);
 
 /* Library/build identification: "orbfe-b200 sm_100a <git-describe-or-date>" */
 const char* orbfe_version(void);

@@ -163,10 +163,17 @@ int search_by_bow(const FeatVec& fa, const uint8_t* descA, const float* angleA, 
     return nmatches;
 }
 
-// ORBmatcher.cc:1046-1324 (mpCamera2 == NULL branches), Pinhole.cpp:196-215
+}  // namespace bow_oracle
+namespace kb8_oracle {   // kb8_oracle.cpp
+float triangulate_matches(const float* P1, float prec1, const float* P2, float prec2, const float* R12, const float* t12,
+                          const float* pt1, const float* pt2, float sigmaLevel, float unc, float* p3D);
+}
+namespace bow_oracle {
+
+// ORBmatcher.cc:1046-1324; Pinhole.cpp:196-215 for mpCamera2 == NULL, KannalaBrandt8.cpp:322-328 for two-camera keyframes
 int search_for_triangulation(const TriSide& A, const TriSide& B, const float* F12, const float* ep, const float* scaleFactorsB,
                              const float* levelSigma2B, int onlyStereo, int coarse, int checkOrientation, int thLow,
-                             int* matches12) {
+                             int* matches12, const TriRig* rig) {
     enum { HISTO = 30 };
     for (int i = 0; i < A.n; i++) matches12[i] = -1;
     std::vector<int> rotHist[HISTO];
@@ -180,26 +187,34 @@ int search_for_triangulation(const TriSide& A, const TriSide& B, const float* F1
             for (int pa = fa.start[ia]; pa < fa.start[ia + 1]; pa++) {
                 const int idx1 = fa.feat[pa];
                 if (A.hasMp[idx1]) continue;
-                const bool bStereo1 = A.uright && A.uright[idx1] >= 0;
+                const bool bStereo1 = !rig && A.uright && A.uright[idx1] >= 0;   // :1121 (!pKF1->mpCamera2 && mvuRight >= 0)
                 if (onlyStereo && !bStereo1) continue;
+                const bool bRight1 = rig && idx1 >= rig->nLeft1;                 // :1126-1128
                 const match_oracle::OrbKp& kp1 = A.keys[idx1];
                 const uint8_t* d1 = A.desc + 32 * (size_t)idx1;
                 int bestDist = thLow, bestIdx2 = -1;
                 for (int pb = fb.start[ib]; pb < fb.start[ib + 1]; pb++) {
                     const int idx2 = fb.feat[pb];
                     if (B.hasMp[idx2]) continue;                 // vbMatched2 is never set in this version of the loop
-                    const bool bStereo2 = B.uright && B.uright[idx2] >= 0;
+                    const bool bStereo2 = !rig && B.uright && B.uright[idx2] >= 0;
                     if (onlyStereo && !bStereo2) continue;
                     const int dist = descriptor_distance(d1, B.desc + 32 * (size_t)idx2);
                     if (dist > thLow || dist > bestDist) continue;
                     const match_oracle::OrbKp& kp2 = B.keys[idx2];
-                    if (!bStereo1 && !bStereo2) {
+                    if (!bStereo1 && !bStereo2 && !rig) {                        // :1196
                         const float distex = ep[0] - kp2.x;
                         const float distey = ep[1] - kp2.y;
                         if (distex * distex + distey * distey < 100 * scaleFactorsB[kp2.octave]) continue;
                     }
                     bool ok = coarse != 0;
-                    if (!ok) {   // Pinhole::epipolarConstrain
+                    if (!ok && rig) {   // :1205-1241 camera / pose selection, then KannalaBrandt8::epipolarConstrain
+                        const bool bRight2 = idx2 >= rig->nLeft2;
+                        const int k = 2 * (bRight1 ? 1 : 0) + (bRight2 ? 1 : 0);
+                        const float pt1[2] = {kp1.x, kp1.y}, pt2[2] = {kp2.x, kp2.y};
+                        float p3D[3];
+                        ok = kb8_oracle::triangulate_matches(rig->P1[k], rig->prec1[k], rig->P2[k], rig->prec2[k], rig->R12[k], rig->t12[k],
+                                                             pt1, pt2, rig->levelSigma2A[kp1.octave], levelSigma2B[kp2.octave], p3D) > 0.0001f;
+                    } else if (!ok) {   // Pinhole::epipolarConstrain
                         const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
                         const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
                         const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];

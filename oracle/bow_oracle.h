@@ -76,8 +76,16 @@ struct TriSide {
     const uint8_t* hasMp;
     int n;
 };
+// Two-camera keyframes (mpCamera2 != NULL, :1071-1095, :1160-1241): keys / desc rows = [mvKeys | mvKeysRight]; per
+// (bRight1, bRight2) combination k = 2 * bRight1 + bRight2 the KB8 parameters of the two cameras and R12 / t12
+// (Tll, Tlr, Trl, Trr); the epipolar gate is KannalaBrandt8::epipolarConstrain (KannalaBrandt8.cpp:322-328).
+struct TriRig {
+    int nLeft1, nLeft2;
+    const float* levelSigma2A;
+    float P1[4][8], P2[4][8], prec1[4], prec2[4], R12[4][9], t12[4][3];
+};
 int search_for_triangulation(const TriSide& A, const TriSide& B, const float* F12, const float* ep, const float* scaleFactorsB,
                              const float* levelSigma2B, int onlyStereo, int coarse, int checkOrientation, int thLow,
-                             int* matches12);
+                             int* matches12, const TriRig* rig = nullptr);
 
 }  // namespace bow_oracle

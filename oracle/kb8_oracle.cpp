@@ -66,7 +66,7 @@ void unproject(const float* P, float precision, const float* uv, float* ray) {  
 
 // Null vector (right singular vector of the smallest singular value) of a 4x4 matrix: eigenvector of A^T A for its
 // smallest eigenvalue, cyclic Jacobi in fp64.
-static void null_vector4(const float A[4][4], double x[4]) {
+void null_vector4(const float A[4][4], double x[4]) {
     double S[4][4], V[4][4];
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++) {
@@ -168,6 +168,14 @@ void oracle_kb8_project(const float* P, const float* p3d, int n, float* uv) {
 }
 void oracle_kb8_unproject(const float* P, float precision, const float* uv, int n, float* rays) {
     for (int i = 0; i < n; i++) kb8_oracle::unproject(P, precision, uv + 2 * i, rays + 3 * i);
+}
+void oracle_kb8_null_vectors(const float* A, int n, double* x) {
+    for (int i = 0; i < n; i++) {
+        float M[4][4];
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) M[r][c] = A[16 * (size_t)i + 4 * r + c];
+        kb8_oracle::null_vector4(M, x + 4 * (size_t)i);
+    }
 }
 void oracle_kb8_triangulate(const float* P1, float prec1, const float* P2, float prec2, const float* R12,
                             const float* t12, const float* pt1, const float* pt2, const float* sigma1,

@@ -413,6 +413,36 @@ def search_for_triangulation(fvA, keysA, descA, urightA, has_mp_a, fvB, keysB, d
     return n, m12
 
 
+def kb8_null_vectors(A):
+    """The null-vector step of KannalaBrandt8::Triangulate on n 4x4 float systems -> [n, 4] float64."""
+    A = np.ascontiguousarray(A, np.float32).reshape(-1, 16)
+    x = np.empty((len(A), 4), np.float64)
+    lib().oracle_kb8_null_vectors(_p(A), len(A), _p(x))
+    return x
+
+
+def search_for_triangulation_rig(fvA, keysA, descA, has_mp_a, fvB, keysB, descB, has_mp_b, scale_factors_b, level_sigma2_a,
+                                 level_sigma2_b, n_left1, n_left2, pairs, only_stereo=False, coarse=False,
+                                 check_orientation=True, th_low=50):
+    """Two-camera keyframes (ORBmatcher.cc:1071-1095, 1160-1241).  pairs: float32 [4, 30] = per (bRight1, bRight2)
+    combination {P1[8], P2[8], prec1, prec2, R12[9] row-major, t12[3]}."""
+    a = [np.ascontiguousarray(x, np.int32) for x in fvA]
+    b = [np.ascontiguousarray(x, np.int32) for x in fvB]
+    keysA = np.ascontiguousarray(keysA); keysB = np.ascontiguousarray(keysB)
+    descA = np.ascontiguousarray(descA, np.uint8); descB = np.ascontiguousarray(descB, np.uint8)
+    mpa = np.ascontiguousarray(has_mp_a, np.uint8); mpb = np.ascontiguousarray(has_mp_b, np.uint8)
+    sf = np.ascontiguousarray(scale_factors_b, np.float32)
+    s2a = np.ascontiguousarray(level_sigma2_a, np.float32); s2b = np.ascontiguousarray(level_sigma2_b, np.float32)
+    pairs = np.ascontiguousarray(pairs, np.float32).reshape(4, 30)
+    m12 = np.empty(len(keysA), np.int32)
+    n = lib().oracle_search_for_triangulation_rig(
+        len(a[0]), _p(a[0]), _p(a[1]), _p(a[2]), _p(keysA), _p(descA), _p(mpa), len(keysA),
+        len(b[0]), _p(b[0]), _p(b[1]), _p(b[2]), _p(keysB), _p(descB), _p(mpb), len(keysB),
+        _p(sf), _p(s2a), _p(s2b), int(n_left1), int(n_left2), _p(pairs), int(only_stereo), int(coarse), int(check_orientation),
+        int(th_low), _p(m12))
+    return n, m12
+
+
 # ---------------------------------------------------------------- frame intake
 def cvt_gray(img, rgb=False):
     img = np.ascontiguousarray(img, np.uint8)

@@ -314,4 +314,26 @@ int oracle_search_for_triangulation(int nnA, const int32_t* nodeA, const int32_t
     return bow_oracle::search_for_triangulation(A, B, F12, ep, sfB, sigma2B, onlyStereo, coarse, checkOri, thLow, matches12);
 }
 
+// the two-camera form: rig = {nLeft1, nLeft2} + per combination {P1[8], P2[8], prec1, prec2, R12[9], t12[3]} x 4 as flat floats
+int oracle_search_for_triangulation_rig(int nnA, const int32_t* nodeA, const int32_t* startA, const int32_t* featA,
+                                        const OrbKp* keysA, const uint8_t* descA, const uint8_t* mpA, int nA, int nnB,
+                                        const int32_t* nodeB, const int32_t* startB, const int32_t* featB, const OrbKp* keysB,
+                                        const uint8_t* descB, const uint8_t* mpB, int nB, const float* sfB, const float* sigma2A,
+                                        const float* sigma2B, int nLeft1, int nLeft2, const float* pairs /*[4][30]*/,
+                                        int onlyStereo, int coarse, int checkOri, int thLow, int32_t* matches12) {
+    const bow_oracle::FeatVec fa = fill_fv(nnA, nodeA, startA, featA), fb = fill_fv(nnB, nodeB, startB, featB);
+    const bow_oracle::TriSide A{&fa, keysA, descA, nullptr, mpA, nA}, B{&fb, keysB, descB, nullptr, mpB, nB};
+    bow_oracle::TriRig rig;
+    rig.nLeft1 = nLeft1; rig.nLeft2 = nLeft2; rig.levelSigma2A = sigma2A;
+    for (int k = 0; k < 4; k++) {
+        const float* p = pairs + 30 * k;
+        for (int i = 0; i < 8; i++) { rig.P1[k][i] = p[i]; rig.P2[k][i] = p[8 + i]; }
+        rig.prec1[k] = p[16]; rig.prec2[k] = p[17];
+        for (int i = 0; i < 9; i++) rig.R12[k][i] = p[18 + i];
+        for (int i = 0; i < 3; i++) rig.t12[k][i] = p[27 + i];
+    }
+    const float F12[9] = {0}, ep[2] = {0, 0};
+    return bow_oracle::search_for_triangulation(A, B, F12, ep, sfB, sigma2B, onlyStereo, coarse, checkOri, thLow, matches12, &rig);
+}
+
 }  // extern "C"

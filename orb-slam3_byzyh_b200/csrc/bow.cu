@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "kb8_core.h"
 #include "orbfe_internal.h"
 #include "scratch.h"
 
@@ -217,6 +218,10 @@ struct TriPrm {
     float F[9], ep[2];
     const float *sf2, *sigma2;
     int nLevels, onlyStereo, coarse, thLow;
+    // two-camera keyframes (mpCamera2 != NULL, :1071-1095, :1160-1241): rigs = Kb8Rig[4] {ll, lr, rl, rr} on the device
+    const Kb8Rig* rigs;
+    const float* sigma2A;
+    int nLeftA, nLeftB;
 };
 
 __global__ void __launch_bounds__(128)
@@ -238,8 +243,9 @@ k_tri_match(TriSideDev A, TriSideDev B, TriPrm P, int nfa, int* __restrict__ mat
     if (l2 >= B.nNodes || B.node[l2] != node) return;
     const int idx1 = A.feat[pa];
     if (A.hasMp[idx1]) return;
-    const bool stereo1 = A.uright && A.uright[idx1] >= 0;
+    const bool stereo1 = !P.rigs && A.uright && A.uright[idx1] >= 0;   // :1121 bStereo1 = !mpCamera2 && mvuRight >= 0
     if (P.onlyStereo && !stereo1) return;
+    const int right1 = P.rigs && idx1 >= P.nLeftA ? 1 : 0;
     const OrbfeKeyPoint kp1 = A.keys[idx1];
     uint32_t d[8];
     const uint4* pd = reinterpret_cast<const uint4*>(A.desc + 8 * (size_t)idx1);
@@ -255,18 +261,27 @@ k_tri_match(TriSideDev A, TriSideDev B, TriPrm P, int nfa, int* __restrict__ mat
     for (int pb = bb + lane; pb < be; pb += 32) {
         const int idx2 = B.feat[pb];
         if (B.hasMp[idx2]) continue;
-        const bool stereo2 = B.uright && B.uright[idx2] >= 0;
+        const bool stereo2 = !P.rigs && B.uright && B.uright[idx2] >= 0;
         if (P.onlyStereo && !stereo2) continue;
         const uint4* bd = reinterpret_cast<const uint4*>(B.desc + 8 * (size_t)idx2);
         const int dist = hamming8w(d, bd[0], bd[1]);
         if (dist > P.thLow) continue;
         const OrbfeKeyPoint kp2 = B.keys[idx2];
         if (kp2.octave < 0 || kp2.octave >= P.nLevels) continue;
-        if (!stereo1 && !stereo2) {
+        if (!stereo1 && !stereo2 && !P.rigs) {                            // :1196 ... && !pKF1->mpCamera2
             const float ex = P.ep[0] - kp2.x, ey = P.ep[1] - kp2.y;
             if (ex * ex + ey * ey < 100.0f * P.sf2[kp2.octave]) continue;
         }
-        if (!P.coarse) {
+        if (!P.coarse && P.rigs) {
+            // KannalaBrandt8::epipolarConstrain (KannalaBrandt8.cpp:322-328) with the (bRight1, bRight2) cameras and pose
+            if (kp1.octave < 0 || kp1.octave >= P.nLevels) continue;
+            const int right2 = idx2 >= P.nLeftB ? 1 : 0;
+            const float a1[2] = {kp1.x, kp1.y}, a2[2] = {kp2.x, kp2.y};
+            float x3D[3];
+            bool okTri;
+            const float z = kb8_triangulate_one(P.rigs[2 * right1 + right2], a1, a2, P.sigma2A[kp1.octave], P.sigma2[kp2.octave], x3D, okTri);
+            if (!(z > 0.0001f)) continue;
+        } else if (!P.coarse) {
             if (den == 0) continue;
             const float num = a * kp2.x + b * kp2.y + c;
             const float dsqr = num * num / den;
@@ -477,6 +492,20 @@ extern "C" int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const Orb
     lay(kf1, nfa, la);
     lay(kf2, nfb, lb);
     const size_t iSf = S.in(prm->scale_factors2, 4 * (size_t)prm->n_levels), iS2 = S.in(prm->level_sigma2_2, 4 * (size_t)prm->n_levels);
+    Kb8Rig rigs[4];
+    size_t iRig = 0, iS1 = 0;
+    if (prm->rig) {
+        if (!prm->rig->level_sigma2_1) return bfail(ORBFE_ERR_INVALID, "two-camera search: level_sigma2_1 missing");
+        for (int k = 0; k < 4; k++) {
+            const OrbfeTriCameraPair& c = prm->rig->pair[k];
+            for (int i = 0; i < 8; i++) { rigs[k].c1.p[i] = c.params1[i]; rigs[k].c2.p[i] = c.params2[i]; }
+            rigs[k].c1.precision = c.precision1; rigs[k].c2.precision = c.precision2;
+            for (int i = 0; i < 9; i++) rigs[k].R12[i] = c.R12[i];
+            for (int i = 0; i < 3; i++) rigs[k].t12[i] = c.t12[i];
+        }
+        iRig = S.in(rigs, sizeof rigs);
+        iS1 = S.in(prm->rig->level_sigma2_1, 4 * (size_t)prm->n_levels);
+    }
     const size_t wBin = S.work(8 * (size_t)kf1->n), wHist = S.work(4 * (HISTO + 2));
     int nmatches = 0;
     const size_t oM = S.out(matches12, 4 * (size_t)kf1->n), oN = S.out(&nmatches, 4);
@@ -496,6 +525,10 @@ extern "C" int orbfe_search_for_triangulation(const OrbfeTriSide* kf1, const Orb
     P.ep[0] = prm->epipole[0]; P.ep[1] = prm->epipole[1];
     P.sf2 = S.ptr<float>(iSf); P.sigma2 = S.ptr<float>(iS2); P.nLevels = prm->n_levels;
     P.onlyStereo = prm->only_stereo; P.coarse = prm->coarse; P.thLow = prm->th_low;
+    P.rigs = prm->rig ? S.ptr<Kb8Rig>(iRig) : nullptr;
+    P.sigma2A = prm->rig ? S.ptr<float>(iS1) : nullptr;
+    P.nLeftA = prm->rig ? prm->rig->n_left1 : -1;
+    P.nLeftB = prm->rig ? prm->rig->n_left2 : -1;
     int* dM = S.ptr<int>(oM);
     BCK(cudaMemsetAsync(dM, 0xFF, 4 * (size_t)kf1->n, st));
     BCK(cudaMemsetAsync(S.ptr<int>(wHist), 0, 4 * (HISTO + 2), st));

@@ -111,6 +111,38 @@ extern "C" int orbfe_kb8_unproject(const float* params, float precision, const f
     return ORBFE_OK;
 }
 
+// The step that stands where the reference calls Eigen::JacobiSVD<Matrix4f> (KannalaBrandt8.cpp:566-568), on its own: the
+// homogeneous solution of n 4 x 4 systems.  A stage tap: the oracle restates the same fp64 cyclic Jacobi, and with
+// IEEE add / mul / div / sqrt and no contraction on either side the two must agree bit for bit (tests/test_gpu_kb8.py).
+__global__ void k_kb8_null_vectors(const float* __restrict__ A, int n, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float M[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) M[r][c] = A[16 * (size_t)i + 4 * r + c];
+    double v[4];
+    null_vector4(M, v);
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[4 * (size_t)i + k] = v[k];
+}
+
+extern "C" int orbfe_debug_kb8_null_vectors(const float* A, int n, double* x, int device) {
+    if (n < 0 || (n > 0 && (!A || !x))) return kfail(ORBFE_ERR_INVALID, "kb8_null_vectors: bad arguments");
+    int rc = kb8_check_dev(device);
+    if (rc != ORBFE_OK) return rc;
+    if (n == 0) return ORBFE_OK;
+    OrbfeStage S;
+    const size_t iA = S.in(A, sizeof(float) * 16 * (size_t)n), oX = S.out(x, sizeof(double) * 4 * (size_t)n);
+    KCK(S.commit(device));
+    KCK(S.upload());
+    k_kb8_null_vectors<<<(n + 63) / 64, 64, 0, S.stream()>>>(S.ptr<float>(iA), n, S.ptr<double>(oX));
+    KCK(cudaGetLastError());
+    KCK(S.download());
+    return ORBFE_OK;
+}
+
 extern "C" int orbfe_kb8_triangulate_matches(const float* params1, float precision1, const float* params2,
                                              float precision2, const float* R12, const float* t12, const float* pt1,
                                              const float* pt2, const float* sigma1, const float* unc2, int n,

@@ -311,10 +311,13 @@ inline int SearchByBoW(const cv::Mat& descA, const std::vector<float>& angleA, c
     return n;
 }
 
-// int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  (ORBmatcher.cc:1046-1324),
-// pinhole keyframes.  hasMapPoint*[i] = (pKF->GetMapPoint(i) != NULL); F12 = K1^-T * hat(t12) * R12 * K2^-1 (row major,
+// int ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse)  (ORBmatcher.cc:1046-1324).
+// hasMapPoint*[i] = (pKF->GetMapPoint(i) != NULL); F12 = K1^-T * hat(t12) * R12 * K2^-1 (row major,
 // the matrix Pinhole::epipolarConstrain builds, Pinhole.cpp:191-194) and epipole = pKF2->mpCamera->project(T2w * Cw)
 // are computed once per keyframe pair by the caller (Eigen stays on the host).
+// rig == nullptr: pinhole keyframes (mpCamera2 == NULL).  Two-camera keyframes (:1071-1095, :1160-1241): keys / desc =
+// [mvKeys | mvKeysRight], uright empty, and rig = {NLeft of both keyframes, pKF1->mvLevelSigma2, and for ll, lr, rl, rr the
+// KannalaBrandt8 parameters of the two cameras with R12 / t12 of Tll, Tlr, Trl, Trr}; F12 / epipole are then unused.
 template <class FeatureVector>
 inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1, const std::vector<float>& uright1,
                                   const std::vector<uint8_t>& hasMapPoint1, const FeatureVector& fv1,
@@ -322,7 +325,8 @@ inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const 
                                   const std::vector<uint8_t>& hasMapPoint2, const FeatureVector& fv2, const float F12[9],
                                   const float epipole[2], const std::vector<float>& scaleFactors2,
                                   const std::vector<float>& levelSigma2_2, bool bOnlyStereo, bool bCoarse, bool checkOrientation,
-                                  std::vector<std::pair<size_t, size_t> >& vMatchedPairs, int thLow = 50) {
+                                  std::vector<std::pair<size_t, size_t> >& vMatchedPairs, int thLow = 50,
+                                  const OrbfeTriRig* rig = nullptr) {
     const FlatFeatureVector f1(fv1), f2(fv2);
     OrbfeTriSide a = {(int32_t)keys1.size(), reinterpret_cast<const OrbfeKeyPoint*>(keys1.data()), desc1.ptr(),
                       uright1.empty() ? nullptr : uright1.data(), hasMapPoint1.data(), f1.view()};
@@ -333,6 +337,7 @@ inline int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const 
     prm.epipole[0] = epipole[0]; prm.epipole[1] = epipole[1];
     prm.scale_factors2 = scaleFactors2.data(); prm.level_sigma2_2 = levelSigma2_2.data(); prm.n_levels = (int32_t)scaleFactors2.size();
     prm.only_stereo = bOnlyStereo; prm.coarse = bCoarse; prm.check_orientation = checkOrientation; prm.th_low = thLow;
+    prm.rig = rig;
     std::vector<int32_t> m12(keys1.size(), -1);
     const int n = orbfe_search_for_triangulation(&a, &b, &prm, m12.data(), device());
     if (n < 0) throw std::runtime_error(std::string("SearchForTriangulation (B200): ") + orbfe_last_error());

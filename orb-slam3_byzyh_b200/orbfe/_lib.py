@@ -63,10 +63,20 @@ class TriSide(C.Structure):
                 ("has_map_point", C.c_void_p), ("fv", FeatureVectorC)]
 
 
+class TriCameraPair(C.Structure):
+    _fields_ = [("params1", C.c_float * 8), ("params2", C.c_float * 8), ("precision1", C.c_float),
+                ("precision2", C.c_float), ("R12", C.c_float * 9), ("t12", C.c_float * 3)]
+
+
+class TriRig(C.Structure):
+    _fields_ = [("n_left1", C.c_int32), ("n_left2", C.c_int32), ("level_sigma2_1", C.c_void_p), ("pair", TriCameraPair * 4)]
+
+
 class TriParams(C.Structure):
     _fields_ = [("f12", C.c_float * 9), ("epipole", C.c_float * 2), ("scale_factors2", C.c_void_p),
                 ("level_sigma2_2", C.c_void_p), ("n_levels", C.c_int32), ("only_stereo", C.c_int32),
-                ("coarse", C.c_int32), ("check_orientation", C.c_int32), ("th_low", C.c_int32)]
+                ("coarse", C.c_int32), ("check_orientation", C.c_int32), ("th_low", C.c_int32),
+                ("rig", C.POINTER(TriRig))]
 
 
 _lib = None
@@ -139,6 +149,7 @@ _SIGS = {
     "orbfe_kb8_project": (_i, [_vp, _vp, _i, _vp, _i]),
     "orbfe_kb8_unproject": (_i, [_vp, _f, _vp, _i, _vp, _i]),
     "orbfe_kb8_triangulate_matches": (_i, [_vp, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i]),
+    "orbfe_debug_kb8_null_vectors": (_i, [_vp, _i, _vp, _i]),
     "orbfe_stereo_match_batch_device": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _vp, _vp, _vp]),
     "orbfe_knn2_batch_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "orbfe_stereo_match": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _f, _f, _vp, _vp]),

@@ -219,7 +219,11 @@ class ORBmatcher:
     # SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), ORBmatcher.cc:1046-1324 (pinhole).
     # kf = (keys, desc, uright or None, has_map_point, feature vector); f12 = 3x3 fundamental matrix of
     # Pinhole::epipolarConstrain, epipole = project(T2w * Cw).  -> nmatches, matches12
-    def SearchForTriangulation(self, kf1, kf2, f12, epipole, scale_factors2, level_sigma2_2, bOnlyStereo=False, bCoarse=False):
+    def SearchForTriangulation(self, kf1, kf2, f12, epipole, scale_factors2, level_sigma2_2, bOnlyStereo=False, bCoarse=False,
+                               rig=None):
+        """rig (two-camera keyframes, ORBmatcher.cc:1071-1095, 1160-1241): dict(n_left1, n_left2, level_sigma2_1,
+        pairs=[(params1[8], params2[8], precision1, precision2, R12 3x3, t12 3)] x 4 for ll, lr, rl, rr); the sides'
+        keys / desc are then [mvKeys | mvKeysRight] and uright is None."""
         keep = []
 
         def mk(side):
@@ -246,6 +250,22 @@ class ORBmatcher:
         prm.scale_factors2, prm.level_sigma2_2, prm.n_levels = sf.ctypes.data, s2.ctypes.data, len(sf)
         prm.only_stereo, prm.coarse = int(bOnlyStereo), int(bCoarse)
         prm.check_orientation, prm.th_low = int(self.mbCheckOrientation), self.TH_LOW
+        if rig is not None:
+            from ._lib import TriRig
+            r = TriRig()
+            r.n_left1, r.n_left2 = int(rig["n_left1"]), int(rig["n_left2"])
+            s1 = np.ascontiguousarray(rig["level_sigma2_1"], np.float32)
+            keep.append(s1)
+            r.level_sigma2_1 = s1.ctypes.data
+            for k, (p1, p2, pr1, pr2, R12, t12) in enumerate(rig["pairs"]):
+                c = r.pair[k]
+                c.params1 = (C.c_float * 8)(*[float(x) for x in p1])
+                c.params2 = (C.c_float * 8)(*[float(x) for x in p2])
+                c.precision1, c.precision2 = float(pr1), float(pr2)
+                c.R12 = (C.c_float * 9)(*[float(x) for x in np.asarray(R12, np.float32).reshape(-1)])
+                c.t12 = (C.c_float * 3)(*[float(x) for x in np.asarray(t12, np.float32).reshape(-1)])
+            keep.append(r)
+            prm.rig = C.pointer(r)
         m12 = np.empty(a.n, np.int32)
         n = check(lib().orbfe_search_for_triangulation(C.byref(a), C.byref(b), C.byref(prm), ptr(m12), self.device))
         return n, m12

@@ -149,3 +149,85 @@ def test_search_for_triangulation(orbfe, vocs, seed, only_stereo, coarse, check_
     en, em12 = O.search_for_triangulation(fva, k1, d1, ur1, mp1, fvb, k2, d2, ur2, mp2, f12, ep, SF, SF * SF, only_stereo, coarse,
                                           check_ori)
     assert n == en and n > 60 and np.array_equal(m12, em12)
+
+
+def _rig_keyframes(voc, seed, npts=1400):
+    """Two KannalaBrandt8 stereo-rig keyframes observing one cloud of 3-D points: every point is seen by some of the four
+    cameras (left / right of keyframe 1 and 2) at its projection (+ noise, a quarter far off), with descriptors that are
+    noisy copies of one word-near descriptor per point.  Returns the two sides in the reference's layout
+    ([mvKeys | mvKeysRight]) and the four (bRight1, bRight2) camera pairs with their relative poses."""
+    from oracle.oracle import KP_DTYPE
+    from test_oracle_kb8 import P1, P2
+    rng = np.random.default_rng(seed)
+
+    def rot(ax, ang):
+        c, s = np.cos(ang), np.sin(ang)
+        R = np.eye(3)
+        i, j = [(1, 2), (0, 2), (0, 1)][ax]
+        R[i, i], R[i, j], R[j, i], R[j, j] = c, -s, s, c
+        return R
+    Rlr, tlr = rot(1, 0.02), np.array([0.1, 0.002, -0.001])        # right -> left of a rig: X_l = Rlr X_r + tlr
+    Rk, tk = rot(1, -0.05) @ rot(0, 0.01), np.array([0.35, -0.02, 0.05])   # keyframe 2 left -> keyframe 1 left
+    X1l = np.stack([rng.uniform(-2, 2, npts), rng.uniform(-1.5, 1.5, npts), rng.uniform(0.6, 4, npts)], 1)
+    cams = {"1l": X1l, "1r": (X1l - tlr) @ Rlr}                  # Rlr^T (X - tlr)
+    X2l = (X1l - tk) @ Rk
+    cams["2l"], cams["2r"] = X2l, (X2l - tlr) @ Rlr
+    base = synth.descriptors_near_words(voc, npts, seed + 1)
+    sides = {}
+    for kf in ("1", "2"):
+        keys, desc, src = [], [], []
+        nleft = 0
+        for cam, P in (("l", P1), ("r", P2)):
+            seen = np.flatnonzero(rng.uniform(size=npts) < 0.6)
+            uv = O.kb8_project(P, np.ascontiguousarray(cams[kf + cam][seen], np.float32))
+            uv = uv + rng.normal(0, 0.4, uv.shape).astype(np.float32)
+            off = rng.uniform(size=len(seen)) < 0.25
+            uv[off, 1] += rng.uniform(6, 40, off.sum()).astype(np.float32)
+            k = np.zeros(len(seen), KP_DTYPE)
+            k["x"], k["y"] = uv[:, 0], uv[:, 1]
+            k["angle"] = rng.uniform(0, 360, len(seen))
+            k["octave"] = rng.integers(0, 8, len(seen))
+            keys.append(k)
+            desc.append(np.stack([synth.flip_bits(base[s], int(rng.integers(0, 20)), rng) for s in seen]))
+            src.append(seen)
+            if cam == "l":
+                nleft = len(seen)
+        sides[kf] = (np.concatenate(keys), np.concatenate(desc), nleft, np.concatenate(src))
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    pairs = [(P1, P1, 1e-6, 1e-6, f32(Rk), f32(tk)),                                                  # ll
+             (P1, P2, 1e-6, 1e-6, f32(Rk @ Rlr), f32(Rk @ tlr + tk)),                                 # lr
+             (P2, P1, 1e-6, 1e-6, f32(Rlr.T @ Rk), f32(Rlr.T @ (tk - tlr))),                          # rl
+             (P2, P2, 1e-6, 1e-6, f32(Rlr.T @ Rk @ Rlr), f32(Rlr.T @ (Rk @ tlr + tk - tlr)))]         # rr
+    return sides, pairs
+
+
+@pytest.mark.parametrize("seed,coarse,check_ori", [(1, False, False), (2, False, True), (3, True, True)])
+def test_search_for_triangulation_two_camera_keyframes(orbfe, vocs, seed, coarse, check_ori):
+    """The mpCamera2 branch of ORBmatcher::SearchForTriangulation (ORBmatcher.cc:1071-1095, 1160-1241): per (bRight1,
+    bRight2) combination the cameras and the relative pose change and the gate is KannalaBrandt8::epipolarConstrain.
+    Against the oracle's restatement; KB8's float transcendentals make the gate tolerance-based (tests/test_gpu_kb8.py), so
+    a handful of matches may differ -- the bar is > 99.5 % identical entries; with bCoarse (no gate) everything is exact."""
+    from test_oracle_bow_vs_ref import SF
+    voc, gv, ov = vocs
+    sides, pairs = _rig_keyframes(voc, seed)
+    (k1, d1, nl1, s1), (k2, d2, nl2, s2) = sides["1"], sides["2"]
+    rng = np.random.default_rng(seed + 9)
+    mp1, mp2 = rng.uniform(size=len(k1)) < 0.2, rng.uniform(size=len(k2)) < 0.2
+    _, fva = gv.transform(d1, 2)
+    _, fvb = gv.transform(d2, 2)
+    S2 = (SF * SF).astype(np.float32)
+    flat = np.stack([np.concatenate([p[0], p[1], [p[2], p[3]], p[4].reshape(-1), p[5]]) for p in pairs]).astype(np.float32)
+    en, em12 = O.search_for_triangulation_rig(fva, k1, d1, mp1, fvb, k2, d2, mp2, SF, S2, S2, nl1, nl2, flat, False, coarse, check_ori)
+    m = orbfe.ORBmatcher(0.6, check_ori)
+    n, m12 = m.SearchForTriangulation((k1, d1, None, mp1, fva), (k2, d2, None, mp2, fvb), np.zeros(9, np.float32), np.zeros(2, np.float32),
+                                      SF, S2, False, coarse, rig=dict(n_left1=nl1, n_left2=nl2, level_sigma2_1=S2, pairs=pairs))
+    assert en > 150
+    if coarse:
+        assert n == en and np.array_equal(m12, em12)
+    else:
+        assert abs(n - en) <= 3 and (m12 == em12).mean() > 0.995
+        good = (m12 >= 0) & (m12 == em12)
+        assert (s1[good] == s2[m12[good]]).mean() > 0.9          # the gate keeps true correspondences
+    # all four camera combinations occur among the matches
+    r1, r2 = np.flatnonzero(m12 >= 0) >= nl1, m12[m12 >= 0] >= nl2
+    assert len({(bool(a), bool(b)) for a, b in zip(r1, r2)}) == 4

@@ -85,3 +85,31 @@ def test_against_the_reference_outputs(orbfe):
         cam = orbfe.KannalaBrandt8(g["P" + name])
         assert np.abs(cam.project(g["p3d"]) - g["project" + name]).max() < 1e-3
         assert _ulps(cam.unproject(g["uv"]), np.ascontiguousarray(g["unproject" + name])).max() <= 8
+
+
+def test_null_vector_step_is_bit_exact(orbfe):
+    """The step that replaces Eigen::JacobiSVD<Matrix4f> (KannalaBrandt8.cpp:566-568; Eigen is not in the image, so this
+    step is "parity unpinned" against the reference): the CUDA kernel and the oracle restate the same fp64 cyclic Jacobi
+    and must agree to the last bit -- triangulation-shaped systems, random ones, rank-deficient and zero matrices."""
+    import ctypes as C
+    from orbfe import _lib
+    rng = np.random.default_rng(7)
+    n = 20000
+    A = rng.normal(size=(n, 4, 4)).astype(np.float32)
+    r = rng.normal(size=(n // 2, 2, 2)).astype(np.float32)                  # rows x * T.row(2) - T.row(0): the reference's shape
+    T2 = np.concatenate([np.tile(np.eye(3, dtype=np.float32), (n // 2, 1, 1)), rng.normal(size=(n // 2, 3, 1)).astype(np.float32)], 2)
+    T1 = np.tile(np.concatenate([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)], 1), (n // 2, 1, 1))
+    for k, (T, j) in enumerate(((T1, 0), (T1, 0), (T2, 1), (T2, 1))):
+        A[: n // 2, k] = r[:, j, k % 2, None] * T[:, 2] - T[:, k % 2]
+    A[-1] = 0
+    A[-2, 3] = A[-2, 2]                                                        # rank deficient
+    A[-3] = np.eye(4)
+    x = np.empty((n, 4), np.float64)
+    _lib.check(_lib.lib().orbfe_debug_kb8_null_vectors(_lib.ptr(np.ascontiguousarray(A)), n, _lib.ptr(x), 0))
+    ex = O.kb8_null_vectors(A)
+    assert np.array_equal(x.view(np.uint64), ex.view(np.uint64))
+    # and it is the direction of the smallest singular value: |A x| = sigma_min for a unit x
+    sel = slice(n // 2, n // 2 + 2000)
+    res = np.linalg.norm(np.einsum("nij,nj->ni", A[sel].astype(np.float64), x[sel]), axis=1)
+    sv = np.linalg.svd(A[sel].astype(np.float64), compute_uv=False)
+    assert np.allclose(np.linalg.norm(x[sel], axis=1), 1.0, atol=1e-12) and np.allclose(res, sv[:, 3], rtol=1e-6, atol=1e-9)
