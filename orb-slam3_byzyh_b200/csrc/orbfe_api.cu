@@ -273,6 +273,8 @@ int ensure_chunk_set(OrbfeExtractor* e, int frames, OrbfeChunkBufs& bufs, void*&
     if (int qrc = quiesce(e)) return qrc;
     if (e->graphExec) { cudaGraphExecDestroy(e->graphExec); e->graphExec = nullptr; }   // it replays the old buffers
     if (slab) { cudaFree(slab); slab = nullptr; cap = 0; }
+    e->lastFrames = 0;       // nothing the taps could read any more
+    e->lastBufs = nullptr;
     const OrbfeFrameGeom& g = e->g;
     const size_t B = (size_t)frames;
     size_t sz[12], total = 0;
@@ -347,6 +349,7 @@ void enqueue_chunk(OrbfeExtractor* e, const uint8_t* d_images, size_t step, size
     stage_mark(e, 7, st);
     if (e->profiling) e->profCount++;
     e->lastFrames = B;
+    e->lastBufs = &bufs;     // the taps (mvImagePyramid, stage taps, stereo matcher) read the set the last chunk used
 }
 
 int ensure_staging(OrbfeExtractor* e, int frames, int rows, int cols, int capacity) {
@@ -586,6 +589,23 @@ static int submit_host_batch(OrbfeExtractor* h, const uint8_t* images, int B, in
     const size_t fbytes = (size_t)rows * cols;
     const bool packed = step == (size_t)cols && frame_stride == fbytes;
     int ci = 0, nb = 0;
+    // a failure from here on leaves chunks in flight that nobody will wait for: drain the handle before reporting it
+#define CKQ(call)                                                          \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) {                                           \
+            cudaStreamCaptureStatus cs_ = cudaStreamCaptureStatusNone;     \
+            for (cudaStream_t s_ : {h->sCompute, h->sCompute2}) {          \
+                cudaGraph_t g_ = nullptr;                                  \
+                if (s_ && cudaStreamIsCapturing(s_, &cs_) == cudaSuccess && cs_ != cudaStreamCaptureStatusNone) { \
+                    cudaStreamEndCapture(s_, &g_);                         \
+                    if (g_) cudaGraphDestroy(g_);                          \
+                }                                                          \
+            }                                                              \
+            quiesce(h);                                                    \
+            return fail(ORBFE_ERR_CUDA, #call, e_);                        \
+        }                                                                  \
+    } while (0)
     for (int b0 = 0; b0 < B; b0 += nb, ci++, h->chunkSeq++) {
         // Pipeline fill: the H2D of the first chunk overlaps nothing, and the kernels of chunk k cannot start before
         // the H2D of chunk k has landed, so chunk k+1 must not take longer to copy (~7 us per frame over PCIe) than
@@ -595,19 +615,19 @@ static int submit_host_batch(OrbfeExtractor* h, const uint8_t* images, int B, in
         const int s = (int)(h->chunkSeq & 1);
         const bool reuse = h->chunkSeq >= 2;   // the slot has been used since the pipeline was last idle
         // H2D of this chunk overlaps the kernels of the previous one
-        if (reuse) CK(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
+        if (reuse) CKQ(cudaStreamWaitEvent(h->sH2D, h->evInFree[s], 0));
         const uint8_t* src = images + (size_t)b0 * frame_stride;
         if (packed) {
-            CK(cudaMemcpyAsync(h->d_in[s], src, fbytes * nb, cudaMemcpyHostToDevice, h->sH2D));
+            CKQ(cudaMemcpyAsync(h->d_in[s], src, fbytes * nb, cudaMemcpyHostToDevice, h->sH2D));
         } else {
             for (int f = 0; f < nb; f++)
-                CK(cudaMemcpy2DAsync(h->d_in[s] + f * fbytes, cols, src + (size_t)f * frame_stride, step,
+                CKQ(cudaMemcpy2DAsync(h->d_in[s] + f * fbytes, cols, src + (size_t)f * frame_stride, step,
                                      cols, rows, cudaMemcpyHostToDevice, h->sH2D));
         }
-        CK(cudaEventRecord(h->evIn[s], h->sH2D));
+        CKQ(cudaEventRecord(h->evIn[s], h->sH2D));
         cudaStream_t sc = (dual && s) ? h->sCompute2 : h->sCompute;
-        CK(cudaStreamWaitEvent(sc, h->evIn[s], 0));
-        if (reuse) CK(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
+        CKQ(cudaStreamWaitEvent(sc, h->evIn[s], 0));
+        if (reuse) CKQ(cudaStreamWaitEvent(sc, h->evOutFree[s], 0));
         if (B <= kGraphMaxFrames && B <= chunk && !h->profiling && !streaming) {
             // per-frame call: one graph launch instead of 15 kernel launches
             OrbfeExtractor::GraphKey key;
@@ -617,10 +637,10 @@ static int submit_host_batch(OrbfeExtractor* h, const uint8_t* images, int B, in
                 if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 const long long l0 = h->launches;
-                CK(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
+                CKQ(cudaStreamBeginCapture(sc, cudaStreamCaptureModeThreadLocal));
                 enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
                               h->d_on[s], h->d_omono[s], sc, nullptr);
-                CK(cudaStreamEndCapture(sc, &graph));
+                CKQ(cudaStreamEndCapture(sc, &graph));
                 h->graphLaunches = h->launches - l0;
                 h->launches = l0;
                 cudaError_t ge = cudaGraphInstantiate(&h->graphExec, graph, 0);
@@ -628,24 +648,26 @@ static int submit_host_batch(OrbfeExtractor* h, const uint8_t* images, int B, in
                 if (ge != cudaSuccess) { h->graphExec = nullptr; return fail(ORBFE_ERR_CUDA, "cudaGraphInstantiate", ge); }
                 h->graphKey = key;
             }
-            CK(cudaGraphLaunch(h->graphExec, sc));
+            CKQ(cudaGraphLaunch(h->graphExec, sc));
             h->launches += h->graphLaunches;
             h->lastFrames = nb;
+            h->lastBufs = &h->bufs;
         } else {
             enqueue_chunk(h, h->d_in[s], cols, fbytes, nb, lap0, lap1, h->d_okps[s], h->d_odesc[s], capacity,
                           h->d_on[s], h->d_omono[s], sc, (dual && s) ? &h->bufs2 : nullptr);
         }
-        CK(cudaEventRecord(h->evInFree[s], sc));
-        CK(cudaEventRecord(h->evDone[s], sc));
-        CK(cudaStreamWaitEvent(h->sD2H, h->evDone[s], 0));
-        CK(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, h->d_okps[s], (size_t)nb * capacity * sizeof(OrbfeKeyPoint),
+        CKQ(cudaEventRecord(h->evInFree[s], sc));
+        CKQ(cudaEventRecord(h->evDone[s], sc));
+        CKQ(cudaStreamWaitEvent(h->sD2H, h->evDone[s], 0));
+        CKQ(cudaMemcpyAsync(keypoints + (size_t)b0 * capacity, h->d_okps[s], (size_t)nb * capacity * sizeof(OrbfeKeyPoint),
                            cudaMemcpyDeviceToHost, h->sD2H));
-        CK(cudaMemcpyAsync(descriptors + (size_t)b0 * capacity * 32, h->d_odesc[s], (size_t)nb * capacity * 32,
+        CKQ(cudaMemcpyAsync(descriptors + (size_t)b0 * capacity * 32, h->d_odesc[s], (size_t)nb * capacity * 32,
                            cudaMemcpyDeviceToHost, h->sD2H));
-        CK(cudaMemcpyAsync(n_out + b0, h->d_on[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
-        CK(cudaMemcpyAsync(mono_out + b0, h->d_omono[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
-        CK(cudaEventRecord(h->evOutFree[s], h->sD2H));
+        CKQ(cudaMemcpyAsync(n_out + b0, h->d_on[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
+        CKQ(cudaMemcpyAsync(mono_out + b0, h->d_omono[s], nb * sizeof(int), cudaMemcpyDeviceToHost, h->sD2H));
+        CKQ(cudaEventRecord(h->evOutFree[s], h->sD2H));
     }
+#undef CKQ
     const int slot = (h->pendHead + h->pendCount) % OrbfeExtractor::kMaxPending;
     if (!h->evPending[slot]) CK(cudaEventCreateWithFlags(&h->evPending[slot], cudaEventDisableTiming));
     CK(cudaEventRecord(h->evPending[slot], h->sD2H));
@@ -717,6 +739,7 @@ static int tap_check(OrbfeExtractor* h, int frame, int level) {
     if (!h->haveGeom || frame < 0 || frame >= h->lastFrames || level < 0 || level >= h->nlevels)
         return fail(ORBFE_ERR_INVALID, "no such frame/level in the last extract call");
     CK(cudaStreamSynchronize(h->sCompute));
+    if (h->sCompute2) CK(cudaStreamSynchronize(h->sCompute2));   // odd chunks of a multi-chunk batch ran there
     return ORBFE_OK;
 }
 
@@ -737,13 +760,13 @@ static int copy_level(OrbfeExtractor* h, const uint8_t* slab, int frame, int lev
 int orbfe_pyramid_level(OrbfeExtractor* h, int frame, int level, int with_border, uint8_t* dst, size_t dst_step) {
     int rc = tap_check(h, frame, level);
     if (rc) return rc;
-    return copy_level(h, h->bufs.pyr, frame, level, with_border, dst, dst_step);
+    return copy_level(h, (h->lastBufs ? h->lastBufs : &h->bufs)->pyr, frame, level, with_border, dst, dst_step);
 }
 
 int orbfe_debug_blurred(OrbfeExtractor* h, int frame, int level, uint8_t* dst, size_t dst_step) {
     int rc = tap_check(h, frame, level);
     if (rc) return rc;
-    return copy_level(h, h->bufs.blur, frame, level, 0, dst, dst_step);
+    return copy_level(h, (h->lastBufs ? h->lastBufs : &h->bufs)->blur, frame, level, 0, dst, dst_step);
 }
 
 int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys, int capacity, int* n_out) {
@@ -752,11 +775,12 @@ int orbfe_debug_candidates(OrbfeExtractor* h, int frame, int level, int32_t* xys
     const OrbfeFrameGeom& g = h->g;
     const OrbfeLevelGeom& L = g.lv[level];
     int n = 0;
-    CK(cudaMemcpy(&n, h->bufs.candCount + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    const OrbfeChunkBufs& lb = h->lastBufs ? *h->lastBufs : h->bufs;
+    CK(cudaMemcpy(&n, lb.candCount + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = n;
     const int m = std::min(n, capacity);
     std::vector<uint32_t> pk(std::max(m, 1));
-    if (m) CK(cudaMemcpy(pk.data(), h->bufs.cand + (size_t)frame * g.slotsPerFrame + L.slotBase, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+    if (m) CK(cudaMemcpy(pk.data(), lb.cand + (size_t)frame * g.slotsPerFrame + L.slotBase, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
     for (int i = 0; i < m; i++) {
         xys[3 * i] = (int)(pk[i] & 0xFFF);
         xys[3 * i + 1] = (int)((pk[i] >> 12) & 0xFFF);
@@ -771,11 +795,12 @@ int orbfe_debug_level_keypoints(OrbfeExtractor* h, int frame, int level, int32_t
     const OrbfeFrameGeom& g = h->g;
     const OrbfeLevelGeom& L = g.lv[level];
     int n = 0;
-    CK(cudaMemcpy(&n, h->bufs.kpCount + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    const OrbfeChunkBufs& lb = h->lastBufs ? *h->lastBufs : h->bufs;
+    CK(cudaMemcpy(&n, lb.kpCount + frame * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = n;
     const int m = std::min(n, capacity);
     std::vector<uint32_t> pk(std::max(m, 1));
-    if (m) CK(cudaMemcpy(pk.data(), h->bufs.kp + (size_t)frame * g.kpCapFrame + L.kpBase, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+    if (m) CK(cudaMemcpy(pk.data(), lb.kp + (size_t)frame * g.kpCapFrame + L.kpBase, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
     for (int i = 0; i < m; i++) {
         xys[3 * i] = (int)(pk[i] & 0xFFF);
         xys[3 * i + 1] = (int)((pk[i] >> 12) & 0xFFF);
@@ -864,6 +889,10 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     if (!keys_l || !desc_l || !u_right || !depth || (nr > 0 && (!keys_r || !desc_r))) return fail(ORBFE_ERR_INVALID, "null argument");
     CK(cudaStreamSynchronize(right->sCompute));
     CK(cudaStreamSynchronize(left->sCompute));
+    if (right->sCompute2) CK(cudaStreamSynchronize(right->sCompute2));
+    if (left->sCompute2) CK(cudaStreamSynchronize(left->sCompute2));
+    const OrbfeChunkBufs& lbL = left->lastBufs ? *left->lastBufs : left->bufs;
+    const OrbfeChunkBufs& lbR = right->lastBufs ? *right->lastBufs : right->bufs;
     OrbfeStage S;
     const size_t ikl = S.in(keys_l, sizeof(OrbfeKeyPoint) * (size_t)nl), idl = S.in(desc_l, 32 * (size_t)nl);
     const size_t ikr = S.in(keys_r, sizeof(OrbfeKeyPoint) * (size_t)nr), idr = S.in(desc_r, 32 * (size_t)nr);
@@ -872,8 +901,8 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     CK(S.commit(left->device));
     cudaError_t e = S.upload();
     if (e == cudaSuccess) {
-        orbfe_launch_stereo(left->g, left->bufs.pyr + (size_t)frame * left->g.pyrStride,
-                            right->bufs.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
+        orbfe_launch_stereo(left->g, lbL.pyr + (size_t)frame * left->g.pyrStride,
+                            lbR.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
                             S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
                             S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.stream());
         left->launches += 2;
@@ -909,7 +938,8 @@ int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right,
         CK(cudaMalloc(&left->d_stereoSad, need * sizeof(int)));
         left->stereoSadElems = need;
     }
-    orbfe_launch_stereo_batch(left->g, left->bufs.pyr, right->bufs.pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
+    orbfe_launch_stereo_batch(left->g, (left->lastBufs ? left->lastBufs : &left->bufs)->pyr,
+                              (right->lastBufs ? right->lastBufs : &right->bufs)->pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
                               (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad, st);
     left->launches += 2;
     CK(cudaGetLastError());

@@ -189,6 +189,7 @@ struct OrbfeExtractor {
     cudaEvent_t evStage[kProfSets][ORBFE_NUM_STAGES + 1] = {};
     int profCount = 0;      // chunks recorded since profiling was switched on
     int lastFrames = 0;
+    const OrbfeChunkBufs* lastBufs = nullptr;   // buffer set of the last enqueued chunk (bufs or bufs2)
     long long launches = 0;
     size_t maxBytes = (size_t)6 << 30;
 
