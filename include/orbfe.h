@@ -343,6 +343,17 @@ int orbfe_bow_transform_device(OrbfeVocabulary* voc, const uint8_t* d_desc, int 
                                int32_t* d_word_id, double* d_weight, int32_t* d_node_id,
                                void* stream);
 
+/* The fold itself on the device, for batches of frames whose descriptors stay in HBM (TF_IDF weighting, L1_NORM scoring:
+ * the configuration of ORBvoc.txt).  Frame b owns the features [frame_start[b], frame_start[b+1]) of the per-feature arrays
+ * (at most `capacity` <= 4096 of them) and the output slabs [b * capacity ...): bow_word / bow_value = the BowVector in map
+ * order (n_bow[b] entries; values are DBoW2's doubles bit for bit: weights added in feature order, L1 norm added in key
+ * order), fv_node / fv_feat = the FeatureVector in map order (n_fv[b] nodes, NodeId compared as unsigned; node j holds
+ * fv_feat[fv_start[b * (capacity + 1) + j] .. fv_start[.. + j + 1]), feature indices relative to the frame). */
+int orbfe_bow_fold_device(const int32_t* d_word_id, const double* d_weight, const int32_t* d_node_id,
+                          const int32_t* d_frame_start, int B, int capacity, uint32_t* d_bow_word,
+                          double* d_bow_value, int32_t* d_n_bow, uint32_t* d_fv_node, int32_t* d_fv_start,
+                          int32_t* d_fv_feat, int32_t* d_n_fv, void* stream);
+
 /* DBoW2::FeatureVector (std::map<NodeId, vector<unsigned>>) flattened in map order: node ids ascending,
  * features of node j = feat[start[j] .. start[j+1]) in push_back order. */
 typedef struct OrbfeFeatureVector {

@@ -387,6 +387,122 @@ extern "C" int orbfe_bow_transform_device(OrbfeVocabulary* V, const uint8_t* d_d
     return ORBFE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BowVector / FeatureVector folding on the device: transform(features, v, fv, levelsup) (TemplatedVocabulary.h:1125-1197)
+// after the per-feature descent, for the TF_IDF / L1_NORM vocabulary ORB-SLAM3 ships (ORBvoc.txt).  DBoW2 folds into two
+// std::maps in feature order: v[word] += weight (BowVector::addWeight), fv[node].push_back(i), then v.normalize(L1)
+// sums |value| in key order and divides.  Here, one CTA per frame: the (word, i) and (node, i) keys are sorted in shared
+// memory (bitonic; a key is unique, so the order inside a word / node is the feature order), one thread per word adds its
+// weights in that order (the same sequence of double additions as the map's +=), ONE thread adds the norm in key order
+// (the only way to reproduce the reference's rounding), every thread divides.
+constexpr int FOLD_CAP = 4096;     // features per frame (shared-memory sort)
+constexpr int FOLD_THREADS = 256;
+
+__device__ __forceinline__ void fold_sort(unsigned long long* key, int n2) {
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += FOLD_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = key[i], b = key[l];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(FOLD_THREADS)
+k_bow_fold(const int32_t* __restrict__ word, const double* __restrict__ weight, const int32_t* __restrict__ node,
+           const int32_t* __restrict__ fstart, int cap, uint32_t* __restrict__ bowWord, double* __restrict__ bowVal,
+           int32_t* __restrict__ nBow, uint32_t* __restrict__ fvNode, int32_t* __restrict__ fvStart, int32_t* __restrict__ fvFeat,
+           int32_t* __restrict__ nFv) {
+    __shared__ unsigned long long key[FOLD_CAP];
+    __shared__ unsigned short headPos[FOLD_CAP];   // slot -> position of its first key
+    __shared__ int s_n, s_slots;
+    __shared__ double s_norm;
+    const int b = blockIdx.x, f0 = fstart[b], n = min(fstart[b + 1] - f0, min(cap, FOLD_CAP));
+    const size_t o = (size_t)b * cap;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int pass = 0; pass < 2; pass++) {          // 0: BowVector (keys = word), 1: FeatureVector (keys = node)
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n2; i += FOLD_THREADS) {
+            unsigned long long k = ~0ull;
+            if (i < n && weight[f0 + i] > 0.0)      // stopped words are skipped in both maps (:1170)
+                k = ((unsigned long long)(uint32_t)(pass ? node[f0 + i] : word[f0 + i]) << 32) | (uint32_t)i;
+            key[i] = k;
+            if (k != ~0ull) atomicAdd(&s_n, 1);
+        }
+        __syncthreads();
+        fold_sort(key, n2);
+        const int m = s_n;                          // valid keys are the first m
+        // segment heads -> slots (block scan by one pass of warp ballots is overkill for <= 4096: two-level count)
+        if (threadIdx.x == 0) s_slots = 0;
+        __syncthreads();
+        for (int base = 0; base < m; base += FOLD_THREADS) {
+            const int i = base + threadIdx.x;
+            const bool head = i < m && (i == 0 || (key[i] >> 32) != (key[i - 1] >> 32));
+            // ordered slot numbers: count the heads before i inside this chunk with ballots
+            const unsigned bal = __ballot_sync(0xffffffffu, head);
+            __shared__ int wcnt[FOLD_THREADS / 32];
+            if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = __popc(bal);
+            __syncthreads();
+            int before = s_slots;
+            for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += wcnt[w];
+            if (head) headPos[before + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = (unsigned short)i;
+            __syncthreads();
+            if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < FOLD_THREADS / 32; w++) t += wcnt[w]; s_slots += t; }
+            __syncthreads();
+        }
+        const int slots = s_slots;
+        if (pass == 0) {
+            for (int sl = threadIdx.x; sl < slots; sl += FOLD_THREADS) {
+                const int p0 = headPos[sl], p1 = sl + 1 < slots ? headPos[sl + 1] : m;
+                double v = weight[f0 + (int)(uint32_t)key[p0]];                    // insert(value_type(id, v))
+                for (int p = p0 + 1; p < p1; p++) v += weight[f0 + (int)(uint32_t)key[p]];   // vit->second += v, feature order
+                bowWord[o + sl] = (uint32_t)(key[p0] >> 32);
+                bowVal[o + sl] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                 // BowVector::normalize(L1), BowVector.cpp:62-84: key order, one accumulator
+                double norm = 0.0;
+                for (int sl = 0; sl < slots; sl++) norm += fabs(bowVal[o + sl]);
+                s_norm = norm;
+                nBow[b] = slots;
+            }
+            __syncthreads();
+            const double norm = s_norm;
+            if (norm > 0.0)
+                for (int sl = threadIdx.x; sl < slots; sl += FOLD_THREADS) bowVal[o + sl] = bowVal[o + sl] / norm;
+        } else {
+            for (int sl = threadIdx.x; sl < slots; sl += FOLD_THREADS) {
+                fvNode[o + sl] = (uint32_t)(key[headPos[sl]] >> 32);
+                fvStart[(size_t)b * (cap + 1) + sl] = headPos[sl];
+            }
+            for (int i = threadIdx.x; i < m; i += FOLD_THREADS) fvFeat[o + i] = (int32_t)(uint32_t)key[i];
+            if (threadIdx.x == 0) { fvStart[(size_t)b * (cap + 1) + slots] = m; nFv[b] = slots; }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int orbfe_bow_fold_device(const int32_t* d_word_id, const double* d_weight, const int32_t* d_node_id,
+                                     const int32_t* d_frame_start, int B, int capacity, uint32_t* d_bow_word,
+                                     double* d_bow_value, int32_t* d_n_bow, uint32_t* d_fv_node, int32_t* d_fv_start,
+                                     int32_t* d_fv_feat, int32_t* d_n_fv, void* stream) {
+    if (B <= 0) return ORBFE_OK;
+    if (!d_word_id || !d_weight || !d_node_id || !d_frame_start || !d_bow_word || !d_bow_value || !d_n_bow || !d_fv_node ||
+        !d_fv_start || !d_fv_feat || !d_n_fv)
+        return bfail(ORBFE_ERR_INVALID, "null argument");
+    if (capacity <= 0 || capacity > FOLD_CAP) return bfail(ORBFE_ERR_CAPACITY, "bow fold: at most 4096 features per frame");
+    k_bow_fold<<<B, FOLD_THREADS, 0, (cudaStream_t)stream>>>(d_word_id, d_weight, d_node_id, d_frame_start, capacity, d_bow_word,
+                                                          d_bow_value, d_n_bow, d_fv_node, d_fv_start, d_fv_feat, d_n_fv);
+    BCK(cudaGetLastError());
+    return ORBFE_OK;
+}
+
 extern "C" int orbfe_bow_transform(OrbfeVocabulary* V, const uint8_t* desc, int n, int levelsup, int32_t* word_id,
                                    double* weight, int32_t* node_id) {
     if (!V || !word_id || !weight || !node_id || n < 0 || (n > 0 && !desc)) return bfail(ORBFE_ERR_INVALID, "null argument");

@@ -137,6 +137,7 @@ _SIGS = {
     "orbfe_vocabulary_destroy": (None, [_vp]),
     "orbfe_bow_transform": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "orbfe_bow_transform_device": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "orbfe_bow_fold_device": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "orbfe_search_by_bow": (_i, [C.POINTER(BowSide), C.POINTER(BowSide), _i, _i, _f, _i, _i, _vp, _vp, _i]),
     "orbfe_search_for_triangulation": (_i, [C.POINTER(TriSide), C.POINTER(TriSide), C.POINTER(TriParams), _vp, _i]),
     "orbfe_cvt_gray": (_i, [_vp, _i, _i, _sz, _i, _i, _vp, _sz, _i]),

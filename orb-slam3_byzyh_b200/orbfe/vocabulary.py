@@ -91,3 +91,31 @@ class ORBVocabulary:
         nodes, counts = np.unique(nodeu, return_counts=True)
         start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
         return (ids.astype(np.uint32), vals), (nodes.astype(np.int32), start, keep[order].astype(np.int32))
+
+    def transform_batch_device(self, d_desc, frame_start, capacity, levelsup=4, stream=None):
+        """Frame::ComputeBoW for a batch of frames whose descriptors are resident in HBM: d_desc [N, 32] uint8 CUDA tensor,
+        frame b = rows frame_start[b] .. frame_start[b+1].  Descent and fold both run on the device (TF_IDF / L1_NORM).
+        -> dict of CUDA tensors: bow_word [B, cap], bow_value [B, cap], n_bow [B], fv_node [B, cap], fv_start [B, cap+1],
+        fv_feat [B, cap], n_fv [B]."""
+        import torch
+        assert self.weighting == TF_IDF and self.scoring == L1_NORM
+        dev = d_desc.device
+        n = d_desc.shape[0]
+        fs = torch.as_tensor(np.ascontiguousarray(frame_start, np.int32), device=dev)
+        B = len(frame_start) - 1
+        word = torch.empty(n, dtype=torch.int32, device=dev)
+        node = torch.empty(n, dtype=torch.int32, device=dev)
+        w = torch.empty(n, dtype=torch.float64, device=dev)
+        st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+        check(lib().orbfe_bow_transform_device(self.h, ptr(d_desc), n, int(levelsup), ptr(word), ptr(w), ptr(node), st))
+        out = dict(bow_word=torch.empty((B, capacity), dtype=torch.int32, device=dev),
+                   bow_value=torch.empty((B, capacity), dtype=torch.float64, device=dev),
+                   n_bow=torch.empty(B, dtype=torch.int32, device=dev),
+                   fv_node=torch.empty((B, capacity), dtype=torch.int32, device=dev),
+                   fv_start=torch.empty((B, capacity + 1), dtype=torch.int32, device=dev),
+                   fv_feat=torch.empty((B, capacity), dtype=torch.int32, device=dev),
+                   n_fv=torch.empty(B, dtype=torch.int32, device=dev))
+        check(lib().orbfe_bow_fold_device(ptr(word), ptr(w), ptr(node), ptr(fs), B, int(capacity), ptr(out["bow_word"]),
+                                          ptr(out["bow_value"]), ptr(out["n_bow"]), ptr(out["fv_node"]), ptr(out["fv_start"]),
+                                          ptr(out["fv_feat"]), ptr(out["n_fv"]), st))
+        return out

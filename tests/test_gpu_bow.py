@@ -231,3 +231,32 @@ def test_search_for_triangulation_two_camera_keyframes(orbfe, vocs, seed, coarse
     # all four camera combinations occur among the matches
     r1, r2 = np.flatnonzero(m12 >= 0) >= nl1, m12[m12 >= 0] >= nl2
     assert len({(bool(a), bool(b)) for a, b in zip(r1, r2)}) == 4
+
+
+def test_bow_fold_on_the_device(orbfe, vocs):
+    """Frame::ComputeBoW for a batch of frames without leaving the device: descent + fold (orbfe_bow_fold_device) against the
+    oracle's transform(features, v, fv, levelsup) (pinned to DBoW2 compiled verbatim): BowVector word ids and values (double
+    bit patterns: the additions run in DBoW2's order), FeatureVector nodes / features; stopped words, repeated words, an
+    empty frame, a frame of one feature and one at the 4096-feature capacity."""
+    import torch
+    voc, gv, ov = vocs
+    rng = np.random.default_rng(3)
+    sizes = [1500, 0, 1, 700, 4096, 2300]
+    frames = []
+    for k, n in enumerate(sizes):
+        d = np.concatenate([synth.descriptors_near_words(voc, n - n // 4, 50 + k), synth.random_descriptors(n // 4, 60 + k)]) if n else np.zeros((0, 32), np.uint8)
+        if n > 10:
+            d[5] = d[2]; d[9] = d[2]                       # the same word several times: weights add up in feature order
+        frames.append(np.ascontiguousarray(d[rng.permutation(len(d))] if n else d))
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    d_desc = torch.from_numpy(np.concatenate(frames)).cuda()
+    for levelsup in (2, 4):
+        out = {k: v.cpu().numpy() for k, v in gv.transform_batch_device(d_desc, start, 4096, levelsup).items()}
+        for b, d in enumerate(frames):
+            (ids, vals), (nodes, fstart, feat) = ov.transform(d, levelsup)
+            nb, nf = out["n_bow"][b], out["n_fv"][b]
+            assert nb == len(ids) and nf == len(nodes), (b, levelsup)
+            assert np.array_equal(out["bow_word"][b, :nb].view(np.uint32), ids)
+            assert np.array_equal(out["bow_value"][b, :nb].view(np.uint64), vals.view(np.uint64)), (b, levelsup)
+            assert np.array_equal(out["fv_node"][b, :nf], nodes) and np.array_equal(out["fv_start"][b, :nf + 1], fstart)
+            assert np.array_equal(out["fv_feat"][b, :fstart[-1]], feat)
