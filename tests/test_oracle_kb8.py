@@ -108,3 +108,22 @@ def test_oracle_matches_the_committed_reference_outputs():
         P = g["P" + name]
         assert O.kb8_project(P, g["p3d"]).tobytes() == g["project" + name].tobytes()
         assert O.kb8_unproject(P, g["uv"]).tobytes() == g["unproject" + name].tobytes()
+
+
+def test_null_vector_step_against_lapack():
+    """The restated replacement of Eigen::JacobiSVD<Matrix4f> (KannalaBrandt8.cpp:566-568) against LAPACK's SVD: the
+    unit vector it returns is the right singular vector of the smallest singular value (|A x| = sigma_min), and where
+    that value is well separated it is LAPACK's vector up to sign."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    A = rng.normal(size=(n, 4, 4)).astype(np.float32)
+    A[-1, 3] = A[-1, 2]                                                      # rank deficient
+    x = O.kb8_null_vectors(A)
+    A64 = A.astype(np.float64)
+    _, sv, vt = np.linalg.svd(A64)
+    res = np.linalg.norm(np.einsum("nij,nj->ni", A64, x), axis=1)
+    assert np.allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-12)
+    assert np.allclose(res, sv[:, 3], rtol=1e-6, atol=1e-9)
+    sep = sv[:, 2] - sv[:, 3] > 1e-3
+    dot = np.abs(np.einsum("nj,nj->n", x, vt[:, 3]))
+    assert sep.mean() > 0.95 and np.allclose(dot[sep], 1.0, atol=1e-8)
