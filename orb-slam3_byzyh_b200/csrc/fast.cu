@@ -82,9 +82,9 @@ __device__ __forceinline__ void fast_score_round(const uint8_t* __restrict__ raw
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const int o = FC_RING_DX(k) + FC_RING_DY(k) * P;
-        r[k] = __byte_perm((uint32_t)p0[o], (uint32_t)p1[o], 0x5410);
+        r[k] = (uint32_t)p0[o] + ((uint32_t)p1[o] << 16);   // multiply-add: keeps the pack off the ALU pipe of the network
     }
-    const uint32_t c2 = __byte_perm((uint32_t)p0[0], (uint32_t)p1[0], 0x5410);
+    const uint32_t c2 = (uint32_t)p0[0] + ((uint32_t)p1[0] << 16);
     const uint32_t m = fc_margin2_pair_raw_biased(r, c2, (uint32_t)t * 0x00010001u);   // per half: max(best - t, 0)
     const int m0 = (int)(m & 0xFFFFu), m1 = (int)(m >> 16);
     const bool k0 = v0 && m0 > 0, k1 = v1 && m1 > 0;

@@ -272,6 +272,12 @@ k_resize_fast(uint8_t* pyr, unsigned long long pyrStride, const OrbfeTap* __rest
     }
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
 // Tiled bilinear resize: a CTA produces ORBFE_RZ_DW x ORBFE_RZ_DH pixels of the PADDED destination level (border
 // columns / rows are the same computation on the reflected coordinate, as above).  The bounding box of the block's
 // source taps arrives as ONE TMA tensor copy of the previous level (box origin 16-byte aligned, host-computed per
@@ -287,7 +293,8 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
     extern __shared__ __align__(128) uint8_t rzs[];
     const int srcBytes = (boxW * boxH + 127) & ~127;
     uint32_t* Hb = reinterpret_cast<uint32_t*>(rzs + 2 * srcBytes);          // [boxH][ORBFE_RZ_DW]; two TMA buffers before it
-    __shared__ __align__(8) OrbfeTap ytile[ORBFE_RZ_DH];
+    // per destination row of the block: byte offsets of its two source rows inside Hb and the two weights << 12
+    __shared__ __align__(16) uint4 ytile[ORBFE_RZ_DH];
     __shared__ __align__(8) uint64_t bar[2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int words = pitch >> 2;
@@ -340,7 +347,11 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
             mbar_expect_tx(&bar[k ^ 1], (uint32_t)(boxW * boxH));
             tma_tile_g2s(rzs + (k ^ 1) * srcBytes, &srcMap, cLo, ORBFE_YOFF + yblk[yb + 1].s, blockIdx.z, &bar[k ^ 1]);
         }
-        if (threadIdx.x < n) ytile[threadIdx.x] = ytab[reflect101_clamped(py0 + threadIdx.x - ORBFE_YOFF, h)];
+        if (threadIdx.x < n) {
+            const OrbfeTap t = ytab[reflect101_clamped(py0 + threadIdx.x - ORBFE_YOFF, h)];
+            ytile[threadIdx.x] = make_uint4((uint32_t)(t.s - rLo) * (ORBFE_RZ_DW * 4), (uint32_t)(t.s1 - rLo) * (ORBFE_RZ_DW * 4),
+                                            (uint32_t)(uint16_t)t.a0 << 12, (uint32_t)(uint16_t)t.a1 << 12);
+        }
         mbar_wait(&bar[k], ((yb - yb0) >> 1) & 1);
         // horizontal pass of every staged source row
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(rzs + k * srcBytes) + wi0;
@@ -357,29 +368,24 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
             *reinterpret_cast<uint4*>(Hb + r * ORBFE_RZ_DW + 4 * lane) = hv;
         }
         __syncthreads();             // Hb and ytile are complete
-        // vertical pass: ((b * (H >> 4)) >> 16) == umulhi(b << 12, H & ~15) for the non-negative 11-bit weights; the two
-        // products and the rounding constant are one chain of mad.hi (IMAD.HI with addend)
+        // vertical pass: ((b * (H >> 4)) >> 16) == umulhi(b << 12, H & ~15) for the non-negative 11-bit weights.  The two
+        // products and the rounding constant meet in one three-input add; pixel pairs are packed before the >> 2 (every
+        // sum is < 1024, so the byte wanted from each 16-bit half survives the shared shift)
         {
             uint8_t* drow = dbase + (size_t)(py0 + wid) * pitch + 4 * wc;
-            const uint32_t* hl = Hb + 4 * lane - rLo * ORBFE_RZ_DW;
+            const uint32_t hl = (uint32_t)__cvta_generic_to_shared(Hb + 4 * lane);
+            const uint32_t yt = (uint32_t)__cvta_generic_to_shared(ytile);
 #pragma unroll 4
             for (int i = wid; i < n; i += RZ_WARPS, drow += (size_t)RZ_WARPS * pitch) {
-                const uint2 tq = *reinterpret_cast<const uint2*>(&ytile[i]);      // {s, a0}, {a1, s1} as 16-bit halves
-                const uint4 h0 = *reinterpret_cast<const uint4*>(hl + (int)(short)(tq.x & 0xFFFFu) * ORBFE_RZ_DW);
-                const uint4 h1 = *reinterpret_cast<const uint4*>(hl + (int)(short)(tq.y >> 16) * ORBFE_RZ_DW);
-                const uint32_t b0 = (tq.x >> 16) << 12, b1 = (tq.y & 0xFFFFu) << 12;
-                uint32_t v0, v1, v2, v3;
-                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v0) : "r"(b0), "r"(h0.x));
-                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v1) : "r"(b0), "r"(h0.y));
-                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v2) : "r"(b0), "r"(h0.z));
-                asm("mad.hi.u32 %0, %1, %2, 2;" : "=r"(v3) : "r"(b0), "r"(h0.w));
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v0) : "r"(b1), "r"(h1.x));
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v1) : "r"(b1), "r"(h1.y));
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v2) : "r"(b1), "r"(h1.z));
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(v3) : "r"(b1), "r"(h1.w));
-                // bytes: (v >> 2) & 255 of the four sums (each < 1024)
-                const uint32_t lo = __byte_perm(v0 >> 2, v1 >> 2, 0x0040), hi = __byte_perm(v2 >> 2, v3 >> 2, 0x0040);
-                if (active) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x5410);
+                const uint4 tq = lds128(yt + 16 * i);
+                const uint4 h0 = lds128(hl + tq.x), h1 = lds128(hl + tq.y);
+                // pairs first ((x1 << 16) + x0 is one LEA), then both products and the two rounding constants in one add
+                const uint32_t a01 = __umulhi(tq.z, h0.x) + (__umulhi(tq.z, h0.y) << 16);
+                const uint32_t b01 = __umulhi(tq.w, h1.x) + (__umulhi(tq.w, h1.y) << 16);
+                const uint32_t a23 = __umulhi(tq.z, h0.z) + (__umulhi(tq.z, h0.w) << 16);
+                const uint32_t b23 = __umulhi(tq.w, h1.z) + (__umulhi(tq.w, h1.w) << 16);
+                const uint32_t lo = (a01 + b01 + 0x00020002u) >> 2, hi = (a23 + b23 + 0x00020002u) >> 2;
+                if (active) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x6420);
             }
         }
         __syncthreads();             // Hb / ytile are free for the next block
@@ -439,8 +445,11 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
             const OrbfeTap* yt = taps + L.ytab;
             if (L.mode == 0 && L.fastTaps && L.rzBoxW > 0 && !getenv("ORBFE_RESIZE_OLD")) {
                 const int nyb = (L.h + 2 * ORBFE_YOFF + ORBFE_RZ_DH - 1) / ORBFE_RZ_DH, nxb = ((L.pitch >> 2) + 31) / 32;
-                // several row blocks per CTA (source box of the next one prefetched) once there is enough work to fill the machine
-                const int per = (long long)nxb * nyb * B >= 148LL * 7 * 16 ? 4 : (long long)nxb * nyb * B >= 148LL * 7 * 4 ? 2 : 1;
+                // several row blocks per CTA (x taps set up once, source box of the next block prefetched) as long as the
+                // launch keeps about four waves of CTAs; ORBFE_RZ_PER overrides (tuning)
+                static const int perEnv = getenv("ORBFE_RZ_PER") ? atoi(getenv("ORBFE_RZ_PER")) : 0;
+                const long long blocks = (long long)nxb * nyb * B;
+                const int per = perEnv > 0 ? std::min(perEnv, nyb) : (int)std::max(1LL, std::min((long long)nyb, blocks / (148LL * 24)));
                 dim3 gt(nxb, (nyb + per - 1) / per, B);
                 const size_t sm = 2 * (size_t)((L.rzBoxW * L.rzBoxH + 127) & ~127) + (size_t)L.rzBoxH * ORBFE_RZ_DW * 4;
                 k_resize_tile<<<gt, 32 * RZ_WARPS, sm, st>>>(b.pyr, g.pyrStride, b.resizeMaps.m[l - 1], xt, yt, taps + L.rzXblk,
