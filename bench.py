@@ -777,7 +777,7 @@ def matching_leg(torch, dist, orbfe, dev, rank, world, steps, barrier, max_over_
 
     def time_exchange(exchange):
         smap = D.ShardedMap(shard, lo, dev, exchange=exchange)     # this rank's shard, resident in HBM
-        for _ in range(3):
+        for _ in range(4):
             out = smap.knn2(d_q)
         barrier()
         m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -787,30 +787,71 @@ def matching_leg(torch, dist, orbfe, dev, rank, world, steps, barrier, max_over_
         m1.record()
         torch.cuda.synchronize()
         barrier()
-        return max_over_ranks(m0.elapsed_time(m1)), smap.exchange, [t.clone() for t in out]
+        eager = max_over_ranks(m0.elapsed_time(m1))
+        res = [t.clone() for t in out]
+        # The step is a few hundred microseconds of device work issued from Python (tensor allocations, ctypes): the
+        # eager loop above measures the interpreter as much as the GPU.  The same two steps (both symmetric buffers)
+        # captured once into a CUDA graph and replayed give the device-side rate; both are reported.
+        graph_ms = None
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                smap.knn2(d_q)
+                gout = smap.knn2(d_q)
+            reps = max(1, steps // 2)
+            g.replay()
+            torch.cuda.synchronize()
+            barrier()
+            m0.record()
+            for _ in range(reps):
+                g.replay()
+            m1.record()
+            torch.cuda.synchronize()
+            barrier()
+            ok = all(torch.equal(a_, b_) for a_, b_ in zip(res, gout))
+            ok = max_over_ranks(0.0 if ok else 1.0) == 0.0
+            if ok:
+                graph_ms = max_over_ranks(m0.elapsed_time(m1)) * steps / (2 * reps)
+        except Exception as e:      # noqa: BLE001 -- capture not possible on this setup: the eager number stands
+            sys.stderr.write("bench: CUDA graph capture of the kNN step failed (%s); eager timing only\n" % str(e)[:120])
+            torch.cuda.synchronize()
+        return (graph_ms if graph_ms is not None else eager), smap.exchange, res, eager, graph_ms is not None
     # exchange fused into the merge kernel (peer loads over NVLink, symmetric memory); all-gather form beside it.
     # Both forms are timed twice in alternation and the faster pass of each is reported (sub-millisecond steps).
-    mms, how, res = time_exchange("p2p")
+    mms, how, res, eager_ms, graphed = time_exchange("p2p")
     nms = None
     if world > 1:
-        nms, _, res2 = time_exchange("nccl")
+        nms, _, res2, _, _ = time_exchange("nccl")
         assert all(torch.equal(a, b) for a, b in zip(res, res2)), "p2p and all-gather exchanges disagree"
-        mms = min(mms, time_exchange("p2p")[0])
+        r2 = time_exchange("p2p")
+        if r2[0] < mms:
+            mms, eager_ms, graphed = r2[0], r2[3], r2[4]
         nms = min(nms, time_exchange("nccl")[0])
     pairs = nq * nmap * steps / (mms / 1e3)
-    # INT roofline of the brute force: POPC is a quarter-rate unit, measured 25 lanes / clk / SM
-    # (profiles/r1_pipe_bench.txt); the kernel spends 5 POPC per descriptor pair (8 XOR words compressed 8 -> 5 by
-    # carry-save adders), the plain statement of ORBmatcher::DescriptorDistance needs 8.
-    sm_mhz = 1965.0
-    popc_peak = 25.0 * 148 * sm_mhz * 1e6
+    # Roofline of the brute force.  The kernel is csrc/knn_umma.cu: one signed byte per descriptor
+    # bit, S = 256 - 2 * hamming from tcgen05.mma kind::i8, 2 * 256 integer operations per descriptor pair.  Peak: the
+    # dense int8 rate of the tensor cores = 2 x the dense bf16 rate the driver measured on this pool (MEASURED_PEAKS.json
+    # has no int8 figure; nominal 4500 TOP/s).  Under it sits the read of the accumulators: 4 B of tensor memory per pair
+    # at 64 B / clk / SM (B300_MICROARCH.md, "LDTM throughput"), which the packed 16-bit tcgen05.ld halves on the
+    # register side.  The scalar kernel it replaces ran at 0.68 T pairs/s = 0.46 of the POPC pipe (profiles/r2_match_ncu_summary.txt).
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = float(json.load(open(peaks_file)).get("bf16_tflops", 0.0)) if os.path.exists(peaks_file) else 0.0
+    int8_peak, peak_src = (2.0 * bf16, "2 x MEASURED_PEAKS.json bf16_tflops (dense int8 = 2 x dense bf16)") if bf16 > 0 else (4500.0, "nominal dense int8, 4500 TOP/s")
+    tops = pairs * 512.0 / 1e12
     matching = {"metric": "Hamming matches/s (2000 frame x 1M map descriptors, kNN-2 + ratio)", "value": pairs,
                 "unit": "descriptor pairs/s", "ms_per_step": mms / steps, "map_shards": world, "gather": "none",
-                "roofline": {"bound": "int", "unit": "POPC32/s", "peak": popc_peak * world,
-                             "peak_source": "25 POPC lanes/clk/SM measured (profiles/r1_pipe_bench.txt) x 148 SMs x 1965 MHz x GPUs",
-                             "achieved": pairs * 5.0, "frac": pairs * 5.0 / (popc_peak * world),
-                             "executed_popc_per_pair": 5, "algorithmic_popc_per_pair": 8,
-                             "algorithmic_popc32_per_s": pairs * 8.0,
-                             "issue_peak_warp_instr_per_s": 0.884e12 * world,
+                "timing": ("two steps captured in a CUDA graph and replayed (device-side rate)" if graphed
+                           else "eager Python calls"),
+                "ms_per_step_eager_python_calls": eager_ms / steps,
+                "roofline": {"bound": "tensor", "unit": "TOP/s (int8)", "kernel": "k_knn2_umma", "peak": int8_peak * world,
+                             "peak_source": peak_src, "achieved": tops, "frac": tops / (int8_peak * world),
+                             "ops_per_pair": 512,
+                             "accumulator_read": {"bytes_per_pair": 4, "achieved_GBs": pairs * 4.0 / 1e9,
+                                                  "peak_GBs": 64.0 * 148 * 1965e6 * world / 1e9,
+                                                  "frac": pairs * 4.0 / (64.0 * 148 * 1965e6 * world)},
+                             "scalar_kernel_pairs_per_s_1gpu": 0.68e12,
                              "ncu": "profiles/r2_match_ncu_summary.txt"}}
     if world > 1:
         matching["gather"] = ("peer loads inside the merge kernel (symmetric memory over NVLink) + 1 device barrier"

@@ -298,8 +298,12 @@ int orbfe_knn2_enqueue(const uint8_t* d_query, int nq, const uint8_t* d_train, i
                        int32_t* d_idx2, int32_t* d_dist2, int32_t* d_match, uint32_t* d_partial,
                        cudaStream_t st) {
     const int chunk = knn2_chunk(nq, nt);
-    const int nchunks = std::max(1, (nt + chunk - 1) / chunk);
-    if (nt > 0) {
+    int nchunks = std::max(1, (nt + chunk - 1) / chunk);
+    if (orbfe_knn2_umma_parts(nq, nt) > 0) {
+        // large maps: the same partial tables from the tensor cores (knn_umma.cu), same merge
+        nchunks = orbfe_knn2_umma_enqueue((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt, d_partial, st);
+        if (nchunks < 0) return nchunks;
+    } else if (nt > 0) {
         dim3 grid((nq + KNN_QB - 1) / KNN_QB, nchunks);
         k_knn2_partial<<<grid, KNN_THREADS, 0, st>>>((const uint32_t*)d_query, nq, (const uint32_t*)d_train, nt,
                                                      chunk, nchunks, d_partial);
@@ -312,7 +316,7 @@ int orbfe_knn2_enqueue(const uint8_t* d_query, int nq, const uint8_t* d_train, i
 
 size_t orbfe_knn2_partial_bytes(int nq, int nt) {
     const int chunk = knn2_chunk(nq, nt);
-    const int nchunks = std::max(1, (nt + chunk - 1) / chunk);
+    const int nchunks = std::max(std::max(1, (nt + chunk - 1) / chunk), orbfe_knn2_umma_parts(nq, nt));
     return sizeof(uint32_t) * 2 * (size_t)nq * nchunks;
 }
 
@@ -341,7 +345,8 @@ int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, in
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* partial = nullptr;
     MCK(cudaMallocAsync((void**)&partial, orbfe_knn2_partial_bytes(nq, nt), st));
-    orbfe_knn2_enqueue(d_query, nq, d_train, nt, train_offset, d_idx2, d_dist2, nullptr, partial, st);
+    const int erc = orbfe_knn2_enqueue(d_query, nq, d_train, nt, train_offset, d_idx2, d_dist2, nullptr, partial, st);
+    if (erc < 0) { cudaFreeAsync(partial, st); return erc; }
     MCK(cudaGetLastError());
     MCK(cudaFreeAsync(partial, st));
     return ORBFE_OK;
@@ -374,8 +379,9 @@ int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int t
     const size_t oi = S.out(idx2, 8 * (size_t)nq), od = S.out(dist2, 8 * (size_t)nq), om = S.out(match, 4 * (size_t)nq);
     MCK(S.commit(device));
     MCK(S.upload());
-    orbfe_knn2_enqueue(S.ptr<uint8_t>(iq), nq, S.ptr<uint8_t>(it), nt, train_offset, S.ptr<int32_t>(oi), S.ptr<int32_t>(od),
-                       S.ptr<int32_t>(om), S.ptr<uint32_t>(wp), S.stream());
+    rc = orbfe_knn2_enqueue(S.ptr<uint8_t>(iq), nq, S.ptr<uint8_t>(it), nt, train_offset, S.ptr<int32_t>(oi), S.ptr<int32_t>(od),
+                            S.ptr<int32_t>(om), S.ptr<uint32_t>(wp), S.stream());
+    if (rc < 0) return rc;
     MCK(cudaGetLastError());
     MCK(S.download());
     return ORBFE_OK;

@@ -108,6 +108,11 @@ struct OrbfeChunkBufs {
 // Records the thread's last error string (orbfe_last_error) and returns `code`.
 int orbfe_fail(int code, const char* what, cudaError_t e);
 
+// knn_umma.cu: the kNN-2 partial pass on the tensor cores.  _parts: (key0, key1) pairs per query the kernel writes for this
+// size, 0 = size left to the scalar kernel; _enqueue: returns that number, or a negative ORBFE error code.
+int orbfe_knn2_umma_parts(int nq, int nt);
+int orbfe_knn2_umma_enqueue(const uint32_t* d_query, int nq, const uint32_t* d_train, int nt, uint32_t* d_partial, cudaStream_t st);
+
 // ---- kernel launchers (each enqueues on `st`, no synchronisation) ----------------------------
 // Level 0 source of orbfe_launch_pyramid: the frames as given, or rectified on the fly through CV_32FC1 maps.
 struct OrbfeRectify {

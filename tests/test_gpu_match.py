@@ -27,7 +27,10 @@ def test_descriptor_distance(orbfe):
     assert orbfe.ORBmatcher.DescriptorDistance(a[3], b[77]) == O.hamming(a[3], b[77])
 
 
-@pytest.mark.parametrize("nq,nt", [(1, 1), (3, 2), (300, 1), (1500, 1500), (257, 4097), (2000, 20000), (40, 0)])
+# sizes on both sides of the switch from the scalar kernel to the tensor-core kernel (csrc/knn_umma.cu: nt >= 512 and
+# nq * nt >= 2^18), ragged against its 128-query / 256-point tiles, and one map large enough for several tiles per CTA
+@pytest.mark.parametrize("nq,nt", [(1, 1), (3, 2), (300, 1), (1500, 1500), (257, 4097), (2000, 20000), (40, 0), (511, 513), (129, 2049),
+                                   (777, 100001), (2000, 250000)])
 def test_knn2_vs_oracle(orbfe, nq, nt):
     rng = np.random.default_rng(nq * 7 + nt)
     q, t = synth.random_descriptors(nq, nq), synth.random_descriptors(nt, nt + 1)

@@ -1,0 +1,658 @@
+// tools/umma_knn.cu -- experiment: the 256-bit Hamming kNN-2 (BASELINE config 5: 2000 query descriptors x 1 M map
+// descriptors) on the 5th-generation tensor cores.  Every descriptor bit becomes one signed byte (+1 / -1), so the
+// int8 dot product of two descriptors is S = 256 - 2 * hamming: a (queries x 256) . (256 x map points) contraction,
+// tcgen05.mma kind::i8 with the accumulator in TMEM.  A CTA owns 128 queries (A, expanded once) and a range of the
+// map; producer warps expand map tiles of 256 points from their bits (32 B per point in HBM, 256 B in shared memory),
+// one thread issues the MMAs, four warps read the accumulators back (tcgen05.ld) and keep the best two keys per query.
+// Checked against the scalar kernel of csrc/match.cu (re-stated here): identical best-two tables.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo tools/umma_knn.cu -o tools/umma_knn
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int KEY_SHIFT = 23;
+
+// ------------------------------------------------------------------ scalar reference (csrc/match.cu:k_knn2_partial)
+__device__ __forceinline__ void top2_insert(uint32_t& b0, uint32_t& b1, uint32_t k) {
+    const uint32_t hi = max(b0, k);
+    b0 = min(b0, k);
+    b1 = min(b1, hi);
+}
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
+}
+__device__ __forceinline__ int hamming256_csa(const uint32_t* a, const uint32_t* b) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = a[i] ^ b[i];
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x[0], x[1], x[2], s1, c1);
+    csa(x[3], x[4], x[5], s2, c2);
+    csa(x[6], s1, s2, s3, c3);
+    return (__popc(s3) + __popc(x[7])) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+__global__ void __launch_bounds__(128) k_scalar(const uint32_t* __restrict__ query, int nq, const uint32_t* __restrict__ train,
+                                                int nt, int chunk, int nchunks, uint32_t* __restrict__ partial) {
+    __shared__ __align__(16) uint32_t tile[256 * 8];
+    const int q0 = blockIdx.x * 256 + threadIdx.x;
+    uint32_t qv[2][8], b0[2], b1[2];
+    for (int r = 0; r < 2; r++) {
+        const int q = min(q0 + r * 128, nq - 1);
+        for (int i = 0; i < 8; i++) qv[r][i] = query[8 * (size_t)q + i];
+        b0[r] = b1[r] = KEY_NONE;
+    }
+    const int c0 = blockIdx.y * chunk, c1 = min(c0 + chunk, nt);
+    for (int t0 = c0; t0 < c1; t0 += 256) {
+        const int cnt = min(256, c1 - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 2; i += 128) reinterpret_cast<uint4*>(tile)[i] = reinterpret_cast<const uint4*>(train + 8 * (size_t)t0)[i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            uint32_t tv[8];
+            *reinterpret_cast<uint4*>(tv) = reinterpret_cast<const uint4*>(tile)[2 * j];
+            *reinterpret_cast<uint4*>(tv + 4) = reinterpret_cast<const uint4*>(tile)[2 * j + 1];
+#pragma unroll
+            for (int r = 0; r < 2; r++) top2_insert(b0[r], b1[r], ((uint32_t)hamming256_csa(qv[r], tv) << KEY_SHIFT) | (uint32_t)(t0 + j));
+        }
+    }
+    for (int r = 0; r < 2; r++) {
+        const int q = q0 + r * 128;
+        if (q < nq) {
+            partial[((size_t)q * nchunks + blockIdx.y) * 2] = b0[r];
+            partial[((size_t)q * nchunks + blockIdx.y) * 2 + 1] = b1[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ tensor-core kernel
+constexpr int QT = 128;                 // queries per CTA = UMMA M
+constexpr int MT = 256;                 // map points per tile = UMMA N
+constexpr int KBYTES = 256;             // one signed byte per descriptor bit
+constexpr int A_BYTES = QT * KBYTES, B_BYTES = MT * KBYTES;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8, NWARPS = EPI_WARPS + 1 + PROD_WARPS;   // epilogue: 2 column halves x 4 lane quadrants
+constexpr int SMEM_BYTES = A_BYTES + 2 * B_BYTES + 128 + 1024;
+// operand tiles are stored as 8-row x 16-byte core matrices (128 contiguous bytes), K chunks next to each other:
+// core (row group g, K chunk c) at (g * 16 + c) * 128
+constexpr uint32_t CORE = 128, LBO = CORE, SBO = 16 * CORE;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {   // bounded (2 s): a trap is better than a hung GPU
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_ns();
+    while (!mbar_try_wait(bar, parity))
+        if (global_ns() - t0 > 2000000000ull) __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// 64 accumulator columns as 32 registers: the low 16 bits of two adjacent columns per register (|S| <= 256)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void top2_insert_s(int& b0, int& b1, int k) {
+    const int hi = max(b0, k);
+    b0 = min(b0, k);
+    b1 = min(b1, hi);
+}
+
+// the registers of the load are operands of the wait, so that nothing that reads them can move above it
+__device__ __forceinline__ void tmem_wait_ld(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// 64 accumulator columns (first column index c0 inside the tile; register r = columns 2 r, 2 r + 1 as signed 16-bit
+// halves) against the kept keys.  key' = -S * 2^22 + column: a column can only enter the best two if S > sThr =
+// floor(-b1 / 2^22), so the common case is a tree of packed 16-bit max and one compare.  thr2 = sThr in both halves.
+__device__ __forceinline__ uint32_t pack_thr(int sThr) {
+    const uint32_t t = (uint32_t)max(min(sThr, 32767), -32768) & 0xFFFFu;
+    return t | (t << 16);
+}
+__device__ __forceinline__ void epi_chunk(const uint32_t* v, int c0, int valid, int& b0, int& b1, uint32_t& thr2, bool live) {
+    if (valid == MT) {
+        uint32_t m[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) m[g] = __vmaxs2(__vimax3_s16x2(v[4 * g], v[4 * g + 1], v[4 * g + 2]), v[4 * g + 3]);
+        const uint32_t mAll = __vimax3_s16x2(__vimax3_s16x2(m[0], m[1], m[2]), __vimax3_s16x2(m[3], m[4], m[5]), __vmaxs2(m[6], m[7]));
+        if (__vmaxs2(mAll, thr2) != thr2) {
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                if (__vmaxs2(m[g], thr2) != thr2) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int sLo = (int)(short)(v[4 * g + i] & 0xFFFFu), sHi = (int)v[4 * g + i] >> 16;
+                        top2_insert_s(b0, b1, sLo * -(1 << 22) + (c0 + 8 * g + 2 * i));
+                        top2_insert_s(b0, b1, sHi * -(1 << 22) + (c0 + 8 * g + 2 * i + 1));
+                    }
+                    thr2 = pack_thr((-b1) >> 22);
+                }
+            }
+        }
+    } else if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const int sLo = (int)(short)(v[j] & 0xFFFFu), sHi = (int)v[j] >> 16;
+            if (c0 + 2 * j < valid) top2_insert_s(b0, b1, sLo * -(1 << 22) + (c0 + 2 * j));
+            if (c0 + 2 * j + 1 < valid) top2_insert_s(b0, b1, sHi * -(1 << 22) + (c0 + 2 * j + 1));
+        }
+        thr2 = pack_thr((-b1) >> 22);
+    }
+}
+
+// K-major operand descriptor, no swizzle: start address, leading (K direction) and stride (row group) byte offsets in
+// units of 16 bytes, descriptor version 1 (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+
+// rows [0, rows) of an operand tile from descriptor bits (8 words per row), +1 for a set bit, -1 for a clear one; rows
+// >= valid are zero.  Any fixed assignment of bits to K positions serves (both operands use this one): bit 4 j + i of a
+// word goes to byte j of output word i, so (w >> i) & 0x11111111 is at once the PRMT selector that picks 0x01 or 0xFF.
+__device__ __forceinline__ void expand_row(uint8_t* dst, int p, uint4 w0, uint4 w1, bool ok) {
+    uint8_t* rb = dst + (p >> 3) * SBO + (p & 7) * 16;
+    if (ok) {
+        const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = (w[i] >> k) & 0x11111111u;
+                lo[k] = __byte_perm(0x000001FFu, 0u, t);
+                hi[k] = __byte_perm(0x000001FFu, 0u, t >> 16);
+            }
+            *reinterpret_cast<uint4*>(rb + (2 * i) * LBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(rb + (2 * i + 1) * LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) *reinterpret_cast<uint4*>(rb + i * LBO) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+__device__ __forceinline__ void expand_rows(uint8_t* dst, const uint32_t* __restrict__ src, int rows, int valid, int tid, int nthr) {
+    for (int p = tid; p < rows; p += nthr) {
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        if (p < valid) { w0 = __ldg(reinterpret_cast<const uint4*>(src + 8 * (size_t)p)); w1 = __ldg(reinterpret_cast<const uint4*>(src + 8 * (size_t)p) + 1); }
+        expand_row(dst, p, w0, w1, p < valid);
+    }
+}
+
+
+// grid = (query tiles, map splits); partial[q][split][2] = the two smallest (distance << 23 | map index) keys
+__global__ void __launch_bounds__(32 * NWARPS, 1)
+k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restrict__ train, int nt, int nsplit,
+           uint32_t* __restrict__ partial, int swapOffsets, int mode, long long* dbg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + 2 * B_BYTES);
+    uint64_t *bFull = bars, *bEmpty = bars + 2, *accFull = bars + 4, *accEmpty = bars + 6;
+    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // map tiles of this CTA
+    const int tilesAll = (nt + MT - 1) / MT;
+    const int tile0 = (int)((long long)tilesAll * blockIdx.y / nsplit), tile1 = (int)((long long)tilesAll * (blockIdx.y + 1) / nsplit);
+    const int ntiles = tile1 - tile0;
+    const int q0 = blockIdx.x * QT;
+
+    if (tid == 0) {
+        mbar_init(&bFull[0], 32 * PROD_WARPS); mbar_init(&bFull[1], 32 * PROD_WARPS);
+        mbar_init(&bEmpty[0], 1); mbar_init(&bEmpty[1], 1);
+        mbar_init(&accFull[0], 1); mbar_init(&accFull[1], 1);
+        mbar_init(&accEmpty[0], 32 * EPI_WARPS); mbar_init(&accEmpty[1], 32 * EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {   // the whole tensor memory: two 256-column accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemPtr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    expand_rows(sA, query + 8 * (size_t)q0, QT, min(QT, nq - q0), tid, 32 * NWARPS);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemPtr;
+
+    if (warp < EPI_WARPS) {
+        // ===== accumulators -> best two keys.  key' = -S * 2^22 + (column - tile base) = (distance - 128) * 2^23 + relative
+        // index; after every tile the kept keys move by -256, so they stay relative to the base of the current tile =====
+        // rows past the last query (their operand rows are zero) never take the update path
+        const int quad = warp & 3, half = warp >> 2;      // TMEM lanes 32 quad .. 32 quad + 31, columns 128 half .. 128 half + 127
+        const bool live = q0 + quad * 32 + lane < nq;
+        int b0 = INT_MAX, b1 = INT_MAX;
+        uint32_t thr2 = pack_thr(live ? INT_MIN : INT_MAX);
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1, ph = (t >> 1) & 1;
+            const long long c_a = clock64();
+            mbar_wait(&accFull[s], ph);
+            tc_fence_after();
+            const long long c_b = clock64();
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * MT + half * (MT / 2));
+            const int valid = min(MT, nt - (tile0 + t) * MT);
+            const int cb = half * (MT / 2);
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld32(taddr + 64, vb);
+            tmem_wait_ld(va);
+            tmem_wait_ld(vb);
+            tc_fence_before();
+            mbar_arrive(&accEmpty[s]);     // the accumulator is in registers: the next MMA may overwrite it
+            if (!(mode & 2)) epi_chunk(va, cb, valid, b0, b1, thr2, live);
+            if (!(mode & 2)) epi_chunk(vb, cb + 64, valid, b0, b1, thr2, live);
+            if (dbg && tid == 0) { dbg[blockIdx.x * 16 + 0] += c_b - c_a; dbg[blockIdx.x * 16 + 1] += clock64() - c_b; }
+            if (b0 != INT_MAX) b0 -= MT;
+            if (b1 != INT_MAX) { b1 -= MT; thr2 = pack_thr((-b1) >> 22); }   // (dead rows keep b1 == INT_MAX)
+        }
+        const int q = q0 + quad * 32 + lane;
+        if (q < nq) {
+            const int baseEnd = tile1 * MT;
+            uint32_t o[2];
+            const int b[2] = {b0, b1};
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (b[i] == INT_MAX) { o[i] = KEY_NONE; continue; }
+                const int D = (b[i] + (1 << 22)) >> 23, rel = b[i] - D * (1 << 23);
+                o[i] = ((uint32_t)(D + 128) << KEY_SHIFT) | (uint32_t)(baseEnd + rel);
+            }
+            partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2] = o[0];
+            partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2 + 1] = o[1];
+        }
+    } else if (warp == EPI_WARPS) {
+        // ===== one thread issues the MMAs: 8 x (128 x 256 x 32) per tile =====
+        if (lane == 0) {
+            // instruction descriptor: D = s32, A = B = signed 8 bit, both K-major, N = 256, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+            const uint32_t lbo = swapOffsets ? SBO : LBO, sbo = swapOffsets ? LBO : SBO;
+            const uint64_t dA = umma_desc(smem_u32(sA), lbo, sbo);
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t & 1, ph = (t >> 1) & 1;
+                const long long c_a = clock64();
+                mbar_wait(&bFull[s], ph);
+                const long long c_b = clock64();
+                mbar_wait(&accEmpty[s], ph ^ 1);
+                tc_fence_after();
+                if (dbg) { dbg[blockIdx.x * 16 + 2] += c_b - c_a; dbg[blockIdx.x * 16 + 3] += clock64() - c_b; }
+                const uint64_t dB = umma_desc(smem_u32(sB + s * B_BYTES), lbo, sbo);
+#pragma unroll
+                for (int k = 0; k < KBYTES / 32; k++)   // 32 K bytes = two 16-byte chunks per instruction
+                    umma_i8(tmem + (uint32_t)(s * MT), dA + (uint64_t)((k * 2 * CORE) >> 4), dB + (uint64_t)((k * 2 * CORE) >> 4), idesc, k > 0);
+                umma_commit(&bEmpty[s]);
+                umma_commit(&accFull[s]);
+            }
+        }
+    } else {
+        // ===== producers: map tile bits -> signed bytes in the operand layout =====
+        const int ptid = tid - 32 * (EPI_WARPS + 1);     // = row of the tile (PROD_WARPS * 32 == MT)
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        {
+            const int m = tile0 * MT + ptid;
+            if (ntiles > 0 && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
+        }
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1, ph = (t >> 1) & 1;
+            const uint4 c0 = w0, c1 = w1;
+            const bool ok = (tile0 + t) * MT + ptid < nt;
+            {   // the bits of the next tile travel while this one is expanded
+                const int m = (tile0 + t + 1) * MT + ptid;
+                if (t + 1 < ntiles && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
+            }
+            const long long c_a = clock64();
+            mbar_wait(&bEmpty[s], ph ^ 1);
+            const long long c_b = clock64();
+            if (!(mode & 1)) expand_row(sB + s * B_BYTES, ptid, c0, c1, ok);
+            fence_proxy_async();
+            mbar_arrive(&bFull[s]);
+            if (dbg && ptid == 0) { dbg[blockIdx.x * 16 + 4] += c_b - c_a; dbg[blockIdx.x * 16 + 5] += clock64() - c_b; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+
+// ------------------------------------------------------------------ second arrangement: the map tile stays, the queries stream
+// A CTA owns a range of map tiles.  Each tile is expanded ONCE into shared memory (double buffered: the next tile is
+// expanded while the current one is used) and multiplied with every query tile; the query tiles were expanded once per
+// call by k_expand_queries into global memory in the exact shared-memory image (32 KB per 128 queries), so one bulk copy
+// (cp.async.bulk, completion on an mbarrier) brings a tile in.  The kept keys of all queries live in shared memory.
+constexpr int XQ_MAX = 16;                                   // query tiles per launch (2048 queries)
+constexpr int X_EPI = 8, X_PROD = 8, X_WARPS = X_EPI + 2 + X_PROD;   // + MMA issuer + query loader
+constexpr int X_STATE_BYTES = 2 * XQ_MAX * QT * 8;           // (b0, b1) per (column half, query)
+constexpr int X_SMEM_BYTES = 2 * B_BYTES + 2 * A_BYTES + X_STATE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(QT) k_expand_queries(const uint32_t* __restrict__ query, int nq, uint8_t* __restrict__ img) {
+    const int p = threadIdx.x, q = blockIdx.x * QT + p;
+    uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+    if (q < nq) { w0 = __ldg(reinterpret_cast<const uint4*>(query + 8 * (size_t)q)); w1 = __ldg(reinterpret_cast<const uint4*>(query + 8 * (size_t)q) + 1); }
+    expand_row(img + (size_t)blockIdx.x * A_BYTES, p, w0, w1, q < nq);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// grid = CTAs over the map tiles; partial[q][2 cta + half][2]
+__global__ void __launch_bounds__(32 * X_WARPS, 1)
+k_umma_knn_x(const uint8_t* __restrict__ qimg, int nq, const uint32_t* __restrict__ train, int nt, uint32_t* __restrict__ partial,
+             int mode, long long* dbg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;
+    uint8_t* sA = smem + 2 * B_BYTES;
+    int2* state = reinterpret_cast<int2*>(smem + 2 * B_BYTES + 2 * A_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * B_BYTES + 2 * A_BYTES + X_STATE_BYTES);
+    uint64_t *aFull = bars, *aEmpty = bars + 2, *bFull = bars + 4, *bEmpty = bars + 6, *accFull = bars + 8, *accEmpty = bars + 10;
+    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 12);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qtiles = (nq + QT - 1) / QT;
+    const int tilesAll = (nt + MT - 1) / MT;
+    const int tile0 = (int)((long long)tilesAll * blockIdx.x / gridDim.x), tile1 = (int)((long long)tilesAll * (blockIdx.x + 1) / gridDim.x);
+    const int ntiles = tile1 - tile0;
+    const int nparts = 2 * gridDim.x;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&aFull[i], 1); mbar_init(&aEmpty[i], 1);
+            mbar_init(&bFull[i], 32 * X_PROD); mbar_init(&bEmpty[i], 1);
+            mbar_init(&accFull[i], 1); mbar_init(&accEmpty[i], 32 * X_EPI);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemPtr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // kept keys: live queries start empty, rows past the last query with a key that no column beats (S <= 256)
+    for (int i = tid; i < 2 * XQ_MAX * QT; i += 32 * X_WARPS) {
+        const int q = i % (XQ_MAX * QT);
+        state[i] = q < nq ? make_int2(INT_MAX, INT_MAX) : make_int2(-(1 << 30), -(1 << 30));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemPtr;
+
+    if (warp < X_EPI) {
+        const int quad = warp & 3, half = warp >> 2;
+        const int cb = half * (MT / 2);
+        int n = 0;
+        for (int mt = 0; mt < ntiles; mt++) {
+            const int valid = min(MT, nt - (tile0 + mt) * MT);
+            for (int qt = 0; qt < qtiles; qt++, n++) {
+                const int slot = n & 1, ph = (n >> 1) & 1;
+                const long long c_a = clock64();
+                mbar_wait(&accFull[slot], ph);
+                tc_fence_after();
+                const long long c_b = clock64();
+                const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * MT + cb);
+                uint32_t va[32], vb[32];
+                tmem_ld32(taddr, va);
+                tmem_ld32(taddr + 64, vb);
+                int2* st = &state[half * (XQ_MAX * QT) + qt * QT + quad * 32 + lane];
+                int2 b = *st;
+                if (mt > 0) {    // the keys were relative to the previous map tile
+                    if (b.x != INT_MAX) b.x -= MT;
+                    if (b.y != INT_MAX) b.y -= MT;
+                }
+                uint32_t thr2 = pack_thr((-b.y) >> 22);
+                tmem_wait_ld(va);
+                tmem_wait_ld(vb);
+                tc_fence_before();
+                mbar_arrive(&accEmpty[slot]);
+                if (!(mode & 2)) {
+                    epi_chunk(va, cb, valid, b.x, b.y, thr2, true);
+                    epi_chunk(vb, cb + 64, valid, b.x, b.y, thr2, true);
+                }
+                *st = b;
+                if (dbg && tid == 0) { dbg[0] += c_b - c_a; dbg[1] += clock64() - c_b; }
+            }
+        }
+        // keys -> (distance << 23 | map index); they are relative to the base of the last tile
+        const int baseLast = (tile1 - 1) * MT;
+        for (int qt = 0; qt < qtiles; qt++) {
+            const int q = qt * QT + quad * 32 + lane;
+            if (q >= nq) continue;
+            const int2 b2 = state[half * (XQ_MAX * QT) + q];
+            const int b[2] = {b2.x, b2.y};
+            uint32_t o[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (ntiles == 0 || b[i] == INT_MAX) { o[i] = KEY_NONE; continue; }
+                const int D = (b[i] + (1 << 22)) >> 23, rel = b[i] - D * (1 << 23);
+                o[i] = ((uint32_t)(D + 128) << KEY_SHIFT) | (uint32_t)(baseLast + rel);
+            }
+            uint32_t* out = partial + ((size_t)q * nparts + 2 * blockIdx.x + half) * 2;
+            out[0] = o[0];
+            out[1] = o[1];
+        }
+    } else if (warp == X_EPI) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+            int n = 0;
+            for (int mt = 0; mt < ntiles; mt++) {
+                const int sb = mt & 1;
+                mbar_wait(&bFull[sb], (mt >> 1) & 1);
+                const uint64_t dB = umma_desc(smem_u32(sB + sb * B_BYTES), LBO, SBO);
+                for (int qt = 0; qt < qtiles; qt++, n++) {
+                    const int s = n & 1, ph = (n >> 1) & 1;
+                    const long long c_a = clock64();
+                    mbar_wait(&aFull[s], ph);
+                    const long long c_b = clock64();
+                    mbar_wait(&accEmpty[s], ph ^ 1);
+                    tc_fence_after();
+                    if (dbg) { dbg[2] += c_b - c_a; dbg[3] += clock64() - c_b; }
+                    const uint64_t dA = umma_desc(smem_u32(sA + s * A_BYTES), LBO, SBO);
+#pragma unroll
+                    for (int k = 0; k < KBYTES / 32; k++)
+                        umma_i8(tmem + (uint32_t)(s * MT), dA + (uint64_t)((k * 2 * CORE) >> 4), dB + (uint64_t)((k * 2 * CORE) >> 4), idesc, k > 0);
+                    umma_commit(&aEmpty[s]);
+                    umma_commit(&accFull[s]);
+                }
+                umma_commit(&bEmpty[sb]);
+            }
+        }
+    } else if (warp == X_EPI + 1) {
+        if (lane == 0) {
+            const int steps = ntiles * qtiles;
+            int qt = 0;
+            for (int n = 0; n < steps; n++) {
+                const int s = n & 1, ph = (n >> 1) & 1;
+                mbar_wait(&aEmpty[s], ph ^ 1);
+                mbar_expect_tx(&aFull[s], A_BYTES);
+                bulk_g2s(sA + s * A_BYTES, qimg + (size_t)qt * A_BYTES, A_BYTES, &aFull[s]);
+                if (++qt == qtiles) qt = 0;
+            }
+        }
+    } else {
+        const int ptid = tid - 32 * (X_EPI + 2);
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        {
+            const int m = tile0 * MT + ptid;
+            if (ntiles > 0 && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
+        }
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1, ph = (t >> 1) & 1;
+            const uint4 c0 = w0, c1 = w1;
+            const bool ok = (tile0 + t) * MT + ptid < nt;
+            {
+                const int m = (tile0 + t + 1) * MT + ptid;
+                if (t + 1 < ntiles && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
+            }
+            mbar_wait(&bEmpty[s], ph ^ 1);
+            expand_row(sB + s * B_BYTES, ptid, c0, c1, ok);
+            fence_proxy_async();
+            mbar_arrive(&bFull[s]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static void merge_host(const std::vector<uint32_t>& part, int nq, int nparts, std::vector<uint32_t>& out) {
+    out.assign((size_t)nq * 2, KEY_NONE);
+    for (int q = 0; q < nq; q++) {
+        uint32_t b0 = KEY_NONE, b1 = KEY_NONE;
+        for (int i = 0; i < nparts * 2; i++) {
+            const uint32_t k = part[(size_t)q * nparts * 2 + i];
+            const uint32_t hi = b0 > k ? b0 : k;
+            b0 = b0 < k ? b0 : k;
+            b1 = b1 < hi ? b1 : hi;
+        }
+        out[2 * q] = b0;
+        out[2 * q + 1] = b1;
+    }
+}
+
+int main(int argc, char** argv) {
+    const int nq = argc > 1 ? atoi(argv[1]) : 2000, nt = argc > 2 ? atoi(argv[2]) : 1000000;
+    const int swapOffsets = argc > 3 ? atoi(argv[3]) : 0;
+    const int mode = argc > 5 ? atoi(argv[5]) : 0;   // timing probes: 1 = no expansion, 2 = no epilogue compare (results invalid)
+    std::vector<uint32_t> q(8 * (size_t)nq), tr(8 * (size_t)nt);
+    uint64_t s = 88172645463325252ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 16); };
+    for (auto& v : q) v = rnd();
+    for (auto& v : tr) v = rnd();
+    if (nt > 90001 && nq > 5)
+        for (int i = 0; i < 8; i++) { tr[8 * 777 + i] = q[8 * 5 + i]; tr[8 * 90001 + i] = q[8 * 5 + i]; }   // ties: lower index first
+    for (int k = 0; k < nq && k < nt; k += 7) {   // planted near matches at scattered map positions
+        const size_t m = ((size_t)k * 7919u + 13u) % (size_t)nt;
+        for (int i = 0; i < 8; i++) tr[8 * m + i] = q[8 * (size_t)k + i] ^ (i == (k & 7) ? 0x00010010u << (k % 11) : 0u);
+    }
+    uint32_t *dq, *dt, *p1, *p2;
+    const int chunk = 2048, nch = (nt + chunk - 1) / chunk;
+    const int qtiles = (nq + QT - 1) / QT;
+    int nsplit = argc > 4 ? atoi(argv[4]) : 148 / qtiles;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > (nt + MT - 1) / MT) nsplit = (nt + MT - 1) / MT;
+    CK(cudaMalloc(&dq, q.size() * 4)); CK(cudaMalloc(&dt, tr.size() * 4));
+    CK(cudaMalloc(&p1, (size_t)nq * nch * 8)); CK(cudaMalloc(&p2, (size_t)nq * nsplit * 16));
+    CK(cudaMemcpy(dq, q.data(), q.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(p2, 0xEE, (size_t)nq * nsplit * 16));
+    CK(cudaFuncSetAttribute(k_umma_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    dim3 grid((nq + 255) / 256, nch), grid2(qtiles, nsplit);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms1 = 0, ms2 = 0;
+    k_umma_knn<<<grid2, 32 * NWARPS, SMEM_BYTES>>>(dq, nq, dt, nt, nsplit, p2, swapOffsets, mode, nullptr);
+    CK(cudaDeviceSynchronize());
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0); for (int i = 0; i < 10; i++) k_scalar<<<grid, 128>>>(dq, nq, dt, nt, chunk, nch, p1); cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms1, e0, e1);
+        cudaEventRecord(e0); for (int i = 0; i < 10; i++) k_umma_knn<<<grid2, 32 * NWARPS, SMEM_BYTES>>>(dq, nq, dt, nt, nsplit, p2, swapOffsets, mode, nullptr); cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms2, e0, e1);
+    }
+    CK(cudaGetLastError());
+    {   // where the cycles of one CTA row (blockIdx.y = 0) go, per role
+        long long* dbg; CK(cudaMalloc(&dbg, 16 * 8 * qtiles)); CK(cudaMemset(dbg, 0, 16 * 8 * qtiles));
+        k_umma_knn<<<dim3(qtiles, 1), 32 * NWARPS, SMEM_BYTES>>>(dq, nq, dt, nt / nsplit, 1, p2, swapOffsets, mode, dbg);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> h(16 * qtiles); CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+        const double tl = (nt / nsplit + MT - 1) / MT;
+        printf("  cycles per tile (CTA 0): epilogue wait %.0f work %.0f | mma wait-B %.0f wait-acc %.0f | producer wait %.0f work %.0f\n",
+               h[0] / tl, h[1] / tl, h[2] / tl, h[3] / tl, h[4] / tl, h[5] / tl);
+        k_umma_knn<<<grid2, 32 * NWARPS, SMEM_BYTES>>>(dq, nq, dt, nt, nsplit, p2, swapOffsets, mode, nullptr);
+        CK(cudaDeviceSynchronize());
+    }
+    std::vector<uint32_t> h1((size_t)nq * nch * 2), h2((size_t)nq * nsplit * 4), m1, m2;
+    CK(cudaMemcpy(h1.data(), p1, h1.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(h2.data(), p2, h2.size() * 4, cudaMemcpyDeviceToHost));
+    merge_host(h1, nq, nch, m1);
+    merge_host(h2, nq, nsplit * 2, m2);
+    size_t bad = 0;
+    for (size_t i = 0; i < m1.size(); i++) {
+        if (m1[i] != m2[i] && bad < 6) printf("  q %zu[%zu]: scalar dist %u idx %u | umma dist %u idx %u\n", i / 2, i % 2, m1[i] >> 23, m1[i] & 0x7FFFFF, m2[i] >> 23, m2[i] & 0x7FFFFF);
+        bad += m1[i] != m2[i];
+    }
+    if (qtiles <= XQ_MAX) {   // second arrangement
+        int ctas = argc > 6 ? atoi(argv[6]) : 148;
+        if (ctas > (nt + MT - 1) / MT) ctas = (nt + MT - 1) / MT;
+        uint8_t* img; uint32_t* p3; long long* dbg;
+        CK(cudaMalloc(&img, (size_t)qtiles * A_BYTES)); CK(cudaMalloc(&p3, (size_t)nq * ctas * 16)); CK(cudaMalloc(&dbg, 128)); CK(cudaMemset(dbg, 0, 128));
+        CK(cudaFuncSetAttribute(k_umma_knn_x, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES));
+        float ms3 = 0;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0);
+            for (int i = 0; i < 10; i++) {
+                k_expand_queries<<<qtiles, QT>>>(dq, nq, img);
+                k_umma_knn_x<<<ctas, 32 * X_WARPS, X_SMEM_BYTES>>>(img, nq, dt, nt, p3, mode, nullptr);
+            }
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms3, e0, e1);
+        }
+        k_umma_knn_x<<<1, 32 * X_WARPS, X_SMEM_BYTES>>>(img, nq, dt, nt < 27 * MT ? nt : 27 * MT, p3, mode, dbg);
+        CK(cudaDeviceSynchronize());
+        long long hd[6]; CK(cudaMemcpy(hd, dbg, 48, cudaMemcpyDeviceToHost));
+        const double steps = (double)((nt < 27 * MT ? nt : 27 * MT) + MT - 1) / MT * qtiles;
+        printf("  map-resident: cycles per step (1 CTA): epilogue wait %.0f work %.0f | mma wait-A %.0f wait-acc %.0f\n", hd[0] / steps, hd[1] / steps, hd[2] / steps, hd[3] / steps);
+        k_expand_queries<<<qtiles, QT>>>(dq, nq, img);
+        k_umma_knn_x<<<ctas, 32 * X_WARPS, X_SMEM_BYTES>>>(img, nq, dt, nt, p3, mode, nullptr);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> h3((size_t)nq * ctas * 4), m3;
+        CK(cudaMemcpy(h3.data(), p3, h3.size() * 4, cudaMemcpyDeviceToHost));
+        merge_host(h3, nq, ctas * 2, m3);
+        size_t bad3 = 0;
+        for (size_t i = 0; i < m1.size(); i++) {
+            if (m1[i] != m3[i] && bad3 < 6) printf("  x q %zu[%zu]: scalar dist %u idx %u | umma dist %u idx %u\n", i / 2, i % 2, m1[i] >> 23, m1[i] & 0x7FFFFF, m3[i] >> 23, m3[i] & 0x7FFFFF);
+            bad3 += m1[i] != m3[i];
+        }
+        printf("  map-resident arrangement, %d CTAs: %.3f ms = %.1f G pairs/s (query expansion included) | best-two tables %s (%zu differ)\n",
+               ctas, ms3 / 10, (double)nq * nt / (ms3 / 10) / 1e6, bad3 ? "DIFFER" : "identical", bad3);
+        bad += bad3;
+    }
+    const double pairs = (double)nq * nt;
+    printf("nq %d nt %d grid %d x %d swap %d mode %d: scalar (5 POPC + 14 LOP3 per pair) %.3f ms = %.1f G pairs/s | tcgen05 i8 %.3f ms = %.1f G pairs/s | "
+           "best-two tables %s (%zu of %zu entries differ)\n", nq, nt, qtiles, nsplit, swapOffsets, mode, ms1 / 10, pairs / (ms1 / 10) / 1e6, ms2 / 10,
+           pairs / (ms2 / 10) / 1e6, bad ? "DIFFER" : "identical", bad, m1.size());
+    return bad != 0;
+}
