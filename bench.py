@@ -850,7 +850,8 @@ def matching_leg(torch, dist, orbfe, dev, rank, world, steps, barrier, max_over_
                              "ops_per_pair": 512,
                              "accumulator_read": {"bytes_per_pair": 4, "achieved_GBs": pairs * 4.0 / 1e9,
                                                   "peak_GBs": 64.0 * 148 * 1965e6 * world / 1e9,
-                                                  "frac": pairs * 4.0 / (64.0 * 148 * 1965e6 * world)},
+                                                  "frac": pairs * 4.0 / (64.0 * 148 * 1965e6 * world),
+                                                  "note": "peak = 64 B/clk/SM of 32-bit tcgen05.ld; the kernel reads with .pack::16b (two columns per register), which is how it can sit above 1.0"},
                              "scalar_kernel_pairs_per_s_1gpu": 0.68e12,
                              "ncu": "profiles/r2_match_ncu_summary.txt"}}
     if world > 1:

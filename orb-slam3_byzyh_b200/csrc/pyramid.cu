@@ -284,8 +284,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 // block); the horizontal pass runs once per needed source row into shared memory (32-bit, low 4 bits cleared = the
 // reference's H >> 4 kept in place), the vertical pass reads its two rows from there.  No row caching logic, no
 // per-row address arithmetic and no global loads in the loops: 31 -> ~11 instructions per pixel.
-constexpr int RZ_WARPS = 4;
+constexpr int RZ_WARPS_MAX = 8;
 
+template <int RZ_WARPS>
 __global__ void __launch_bounds__(32 * RZ_WARPS)
 k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __grid_constant__ CUtensorMap srcMap,
               const OrbfeTap* __restrict__ xtab, const OrbfeTap* __restrict__ ytab, const OrbfeTap* __restrict__ xblk,
@@ -406,7 +407,8 @@ int orbfe_resize_make_maps(const OrbfeFrameGeom& g, OrbfeChunkBufs& b, int frame
     }
     if (smem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "tiled resize: source box too large", cudaSuccess);
     if (smem > 40 * 1024 &&
-        cudaFuncSetAttribute(k_resize_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        (cudaFuncSetAttribute(k_resize_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+         cudaFuncSetAttribute(k_resize_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess))
         return orbfe_fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(k_resize_tile)", cudaGetLastError());
     return orbfe_make_level_maps(g, b.pyr, frames, bw, bh, b.resizeMaps);
 }
@@ -452,8 +454,13 @@ void orbfe_launch_pyramid(const OrbfeFrameGeom& g, const OrbfeTap* taps, const u
                 const int per = perEnv > 0 ? std::min(perEnv, nyb) : (int)std::max(1LL, std::min((long long)nyb, blocks / (148LL * 24)));
                 dim3 gt(nxb, (nyb + per - 1) / per, B);
                 const size_t sm = 2 * (size_t)((L.rzBoxW * L.rzBoxH + 127) & ~127) + (size_t)L.rzBoxH * ORBFE_RZ_DW * 4;
-                k_resize_tile<<<gt, 32 * RZ_WARPS, sm, st>>>(b.pyr, g.pyrStride, b.resizeMaps.m[l - 1], xt, yt, taps + L.rzXblk,
-                                                           taps + L.rzYblk, L.off, L.w, L.h, L.pitch, L.rzBoxW, L.rzBoxH, per);
+                static const int rzWarps = getenv("ORBFE_RZ_WARPS") ? atoi(getenv("ORBFE_RZ_WARPS")) : 4;
+                if (rzWarps == 8)
+                    k_resize_tile<8><<<gt, 256, sm, st>>>(b.pyr, g.pyrStride, b.resizeMaps.m[l - 1], xt, yt, taps + L.rzXblk,
+                                                        taps + L.rzYblk, L.off, L.w, L.h, L.pitch, L.rzBoxW, L.rzBoxH, per);
+                else
+                    k_resize_tile<4><<<gt, 128, sm, st>>>(b.pyr, g.pyrStride, b.resizeMaps.m[l - 1], xt, yt, taps + L.rzXblk,
+                                                        taps + L.rzYblk, L.off, L.w, L.h, L.pitch, L.rzBoxW, L.rzBoxH, per);
             } else if (L.mode == 0 && L.fastTaps) {
                 dim3 gf(((L.pitch >> 2) / RS_G + 31) / 32, (L.h + 2 * ORBFE_YOFF + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS), B);
                 k_resize_fast<<<gf, 32 * RS_WARPS, 0, st>>>(b.pyr, g.pyrStride, xt, yt, S.off, S.pitch, L.off, L.w, L.h, L.pitch);
