@@ -29,7 +29,7 @@ constexpr int MT = 256;                 // map points per tile = UMMA N
 constexpr int KBYTES = 256;             // one signed byte per descriptor bit
 constexpr int A_BYTES = QT * KBYTES, B_BYTES = MT * KBYTES;
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8, NWARPS = EPI_WARPS + 1 + PROD_WARPS;   // epilogue: 2 column halves x 4 lane quadrants
-constexpr int SMEM_BYTES = A_BYTES + 2 * B_BYTES + 128 + 1024;
+constexpr int SMEM_BYTES = A_BYTES + 2 * B_BYTES + 128 + QT * 8 + 1024;
 // operand tiles are stored as 8-row x 16-byte core matrices (128 contiguous bytes), K chunks next to each other:
 // core (row group g, K chunk c) at (g * 16 + c) * 128
 constexpr uint32_t CORE = 128, LBO = CORE, SBO = 16 * CORE;
@@ -179,9 +179,31 @@ __device__ __forceinline__ void expand_rows(uint8_t* dst, const uint32_t* __rest
 
 
 // grid = (query tiles, map splits); partial[q][split][2] = the two smallest (distance << 23 | map index) keys
+// Batch form (kBatch): blockIdx.y = stereo pair; the pair's query / train row ranges come from device arrays (as in
+// k_knn2_batch of match.cu), one CTA walks the pair's whole train range, and the two column halves are merged inside the
+// CTA, so idx2 / dist2 / match are written directly.
+struct KnnBatchArgs {
+    const int *qBegin, *qEnd, *tBegin, *tEnd;
+    int capacity;
+    int32_t *idx2, *dist2, *match;
+};
+
+template <bool kBatch>
 __global__ void __launch_bounds__(32 * NWARPS, 1)
 k_knn2_umma(const uint32_t* __restrict__ query, int nq, const uint32_t* __restrict__ train, int nt, int nsplit,
-           uint32_t* __restrict__ partial) {
+            uint32_t* __restrict__ partial, const KnnBatchArgs ba) {
+    size_t slab = 0;
+    if constexpr (kBatch) {
+        const int b = blockIdx.y;
+        slab = (size_t)b * ba.capacity;
+        const int qb = max(ba.qBegin[b], 0), tb = max(ba.tBegin[b], 0);
+        nq = min(ba.qEnd[b], ba.capacity) - qb;
+        nt = max(min(ba.tEnd[b], ba.capacity) - tb, 0);
+        if ((int)(blockIdx.x * QT) >= nq) return;          // uniform per CTA, before anything is allocated
+        query += 8 * (slab + qb);
+        train += 8 * (slab + tb);
+        nsplit = 1;
+    }
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -189,11 +211,13 @@ k_knn2_umma(const uint32_t* __restrict__ query, int nq, const uint32_t* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + 2 * B_BYTES);
     uint64_t *bFull = bars, *bEmpty = bars + 2, *accFull = bars + 4, *accEmpty = bars + 6;
     uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* halfKeys = reinterpret_cast<uint32_t*>(bars + 10);        // batch form: [QT][2] keys of column half 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // map tiles of this CTA
     const int tilesAll = (nt + MT - 1) / MT;
-    const int tile0 = (int)((long long)tilesAll * blockIdx.y / nsplit), tile1 = (int)((long long)tilesAll * (blockIdx.y + 1) / nsplit);
+    const int split = kBatch ? 0 : (int)blockIdx.y;
+    const int tile0 = (int)((long long)tilesAll * split / nsplit), tile1 = (int)((long long)tilesAll * (split + 1) / nsplit);
     const int ntiles = tile1 - tile0;
     const int q0 = blockIdx.x * QT;
 
@@ -214,6 +238,7 @@ k_knn2_umma(const uint32_t* __restrict__ query, int nq, const uint32_t* __restri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmemPtr;
+    uint32_t mine0 = KEY_NONE, mine1 = KEY_NONE;     // batch form: keys of column half 0 of this thread's query
 
     if (warp < EPI_WARPS) {
         // ===== accumulators -> best two keys.  key' = -S * 2^22 + (column - tile base) = (distance - 128) * 2^23 + relative
@@ -253,8 +278,13 @@ k_knn2_umma(const uint32_t* __restrict__ query, int nq, const uint32_t* __restri
                 const int D = (b[i] + (1 << 22)) >> 23, rel = b[i] - D * (1 << 23);
                 o[i] = ((uint32_t)(D + 128) << KEY_SHIFT) | (uint32_t)(baseEnd + rel);
             }
-            partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2] = o[0];
-            partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2 + 1] = o[1];
+            if constexpr (kBatch) {
+                if (half == 1) { halfKeys[2 * (quad * 32 + lane)] = o[0]; halfKeys[2 * (quad * 32 + lane) + 1] = o[1]; }
+                else { mine0 = o[0]; mine1 = o[1]; }
+            } else {
+                partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2] = o[0];
+                partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2 + 1] = o[1];
+            }
         }
     } else if (warp == EPI_WARPS) {
         // ===== one thread issues the MMAs: 8 x (128 x 256 x 32) per tile =====
@@ -299,6 +329,25 @@ k_knn2_umma(const uint32_t* __restrict__ query, int nq, const uint32_t* __restri
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kBatch) {
+        const int q = q0 + warp * 32 + lane;
+        if (warp < 4 && q < nq) {
+            uint32_t k0 = mine0, k1 = mine1;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const uint32_t k = halfKeys[2 * (warp * 32 + lane) + i], hi = max(k0, k);
+                k0 = min(k0, k);
+                k1 = min(k1, hi);
+            }
+            const int i0 = k0 == KEY_NONE ? -1 : (int)(k0 & ((1u << KEY_SHIFT) - 1)), i1 = k1 == KEY_NONE ? -1 : (int)(k1 & ((1u << KEY_SHIFT) - 1));
+            const int d0 = k0 == KEY_NONE ? -1 : (int)(k0 >> KEY_SHIFT), d1 = k1 == KEY_NONE ? -1 : (int)(k1 >> KEY_SHIFT);
+            const size_t o = slab + q;
+            ba.idx2[2 * o] = i0; ba.idx2[2 * o + 1] = i1;
+            ba.dist2[2 * o] = d0; ba.dist2[2 * o + 1] = d1;
+            // Frame.cc:1562  `(*it)[0].distance < (*it)[1].distance * 0.7` (float * double)
+            if (ba.match) ba.match[o] = (i0 >= 0 && i1 >= 0 && (double)(float)d0 < (double)(float)d1 * 0.7) ? i0 : -1;
+        }
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
@@ -333,11 +382,26 @@ int orbfe_knn2_umma_enqueue(const uint32_t* d_query, int nq, const uint32_t* d_t
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return orbfe_fail(ORBFE_ERR_CUDA, "cudaGetDevice", cudaGetLastError());
     if (dev < 64 && !attr[dev]) {
-        if (cudaFuncSetAttribute(k_knn2_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_knn2_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(k_knn2_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
             return orbfe_fail(ORBFE_ERR_CUDA, "cudaFuncSetAttribute(k_knn2_umma)", cudaGetLastError());
         attr[dev] = true;
     }
+    if (d_partial == nullptr) return 0;   // attribute set-up only (the batch entry point)
     const int ns = umma_splits(nq, nt);
-    k_knn2_umma<<<dim3((nq + QT - 1) / QT, ns), 32 * NWARPS, SMEM_BYTES, st>>>(d_query, nq, d_train, nt, ns, d_partial);
+    k_knn2_umma<false><<<dim3((nq + QT - 1) / QT, ns), 32 * NWARPS, SMEM_BYTES, st>>>(d_query, nq, d_train, nt, ns, d_partial, KnnBatchArgs{});
     return 2 * ns;
+}
+
+// The batched stereo form (orbfe_knn2_batch_device): 1 when the tensor-core kernel took the call, 0 when the sizes are left
+// to the scalar kernel (frames with fewer than 512 descriptor rows), negative on error.
+int orbfe_knn2_umma_batch_enqueue(const uint32_t* d_desc_q, const int* d_q_begin, const int* d_q_end, const uint32_t* d_desc_t,
+                                  const int* d_t_begin, const int* d_t_end, int B, int capacity, int32_t* d_idx2, int32_t* d_dist2,
+                                  int32_t* d_match, cudaStream_t st) {
+    if (capacity < 512 || orbfe_knn2_umma_parts(capacity, capacity) == 0) return 0;
+    const int rc = orbfe_knn2_umma_enqueue(nullptr, 0, nullptr, 0, nullptr, st);
+    if (rc < 0) return rc;
+    const KnnBatchArgs ba = {d_q_begin, d_q_end, d_t_begin, d_t_end, capacity, d_idx2, d_dist2, d_match};
+    k_knn2_umma<true><<<dim3((capacity + QT - 1) / QT, B), 32 * NWARPS, SMEM_BYTES, st>>>(d_desc_q, 0, d_desc_t, 0, 1, nullptr, ba);
+    return 1;
 }

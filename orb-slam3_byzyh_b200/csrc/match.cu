@@ -359,6 +359,13 @@ int orbfe_knn2_batch_device(const uint8_t* d_desc_q, const int* d_q_begin, const
     if (capacity <= 0 || capacity >= (1 << KEY_SHIFT) || !d_desc_q || !d_q_begin || !d_q_end || !d_desc_t || !d_t_begin || !d_t_end ||
         !d_idx2 || !d_dist2)
         return mfail(ORBFE_ERR_INVALID, "bad arguments");
+    const int urc = orbfe_knn2_umma_batch_enqueue((const uint32_t*)d_desc_q, d_q_begin, d_q_end, (const uint32_t*)d_desc_t, d_t_begin, d_t_end, B,
+                                                  capacity, d_idx2, d_dist2, d_match, (cudaStream_t)stream);
+    if (urc < 0) return urc;
+    if (urc > 0) {      // frames of >= 512 rows: the tensor-core kernel (knn_umma.cu)
+        MCK(cudaGetLastError());
+        return ORBFE_OK;
+    }
     k_knn2_batch<<<dim3((capacity + KNN_QB - 1) / KNN_QB, B), KNN_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint32_t*)d_desc_q, d_q_begin, d_q_end, (const uint32_t*)d_desc_t, d_t_begin, d_t_end, capacity, d_idx2, d_dist2,
         d_match);

@@ -112,6 +112,9 @@ int orbfe_fail(int code, const char* what, cudaError_t e);
 // size, 0 = size left to the scalar kernel; _enqueue: returns that number, or a negative ORBFE error code.
 int orbfe_knn2_umma_parts(int nq, int nt);
 int orbfe_knn2_umma_enqueue(const uint32_t* d_query, int nq, const uint32_t* d_train, int nt, uint32_t* d_partial, cudaStream_t st);
+int orbfe_knn2_umma_batch_enqueue(const uint32_t* d_desc_q, const int* d_q_begin, const int* d_q_end, const uint32_t* d_desc_t,
+                                  const int* d_t_begin, const int* d_t_end, int B, int capacity, int32_t* d_idx2, int32_t* d_dist2,
+                                  int32_t* d_match, cudaStream_t st);
 
 // ---- kernel launchers (each enqueues on `st`, no synchronisation) ----------------------------
 // Level 0 source of orbfe_launch_pyramid: the frames as given, or rectified on the fly through CV_32FC1 maps.

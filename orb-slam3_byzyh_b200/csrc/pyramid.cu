@@ -284,7 +284,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
 // block); the horizontal pass runs once per needed source row into shared memory (32-bit, low 4 bits cleared = the
 // reference's H >> 4 kept in place), the vertical pass reads its two rows from there.  No row caching logic, no
 // per-row address arithmetic and no global loads in the loops: 31 -> ~11 instructions per pixel.
-constexpr int RZ_WARPS_MAX = 8;
 
 template <int RZ_WARPS>
 __global__ void __launch_bounds__(32 * RZ_WARPS)

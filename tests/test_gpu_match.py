@@ -497,12 +497,13 @@ def test_stereo_match_batch_device_equals_per_pair_calls(orbfe):
     assert matched > 20 * B
 
 
-def test_knn2_batch_device_equals_per_pair_calls(orbfe):
+@pytest.mark.parametrize("nf", [700, 300])     # >= 512 rows per frame: tensor-core kernel (knn_umma.cu), below: scalar kernel
+def test_knn2_batch_device_equals_per_pair_calls(orbfe, nf):
     """32 fisheye-style pairs with a lapping area: the batched kNN-2 + ratio test over rows [mono, n) of both sides equals
     the per-pair orbfe_knn2 (pinned to cv2's BFMatcher) and the CPU oracle."""
     B = 32
     pairs = [synth.shifted_pair(256, 256, 200 + i) for i in range(B)]
-    exL, exR, st, L, R, KP = _extract_pairs_device(orbfe, [p[0] for p in pairs], [p[1] for p in pairs], 700, (60, 200))
+    exL, exR, st, L, R, KP = _extract_pairs_device(orbfe, [p[0] for p in pairs], [p[1] for p in pairs], nf, (60, 200))
     idx2, dist2, match = orbfe.ORBmatcher.knn2_batch_device(L[2], L[4], L[3], R[2], R[4], R[3], st)
     st.synchronize()
     idx2, dist2, match = idx2.cpu().numpy(), dist2.cpu().numpy(), match.cpu().numpy()
@@ -520,4 +521,4 @@ def test_knn2_batch_device_equals_per_pair_calls(orbfe):
             om, oidx, odist = O.fisheye_matches(q, t)
             assert np.array_equal(eidx, oidx) and np.array_equal(edist, odist) and np.array_equal(ematch, om)
         total += int((ematch >= 0).sum())
-    assert total > 10 * B
+    assert total > (10 if nf >= 700 else 3) * B
