@@ -901,11 +901,12 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     CK(S.commit(left->device));
     cudaError_t e = S.upload();
     if (e == cudaSuccess) {
-        orbfe_launch_stereo(left->g, lbL.pyr + (size_t)frame * left->g.pyrStride,
-                            lbR.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
-                            S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
-                            S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.stream());
-        left->launches += 2;
+        if (orbfe_launch_stereo(left->g, lbL.pyr + (size_t)frame * left->g.pyrStride,
+                                lbR.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
+                                S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
+                                S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.stream()) != 0)
+            return fail(ORBFE_ERR_CUDA, "stereo match: candidate index allocation", cudaGetLastError());
+        left->launches += 3;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = S.download();
@@ -938,10 +939,11 @@ int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right,
         CK(cudaMalloc(&left->d_stereoSad, need * sizeof(int)));
         left->stereoSadElems = need;
     }
-    orbfe_launch_stereo_batch(left->g, (left->lastBufs ? left->lastBufs : &left->bufs)->pyr,
-                              (right->lastBufs ? right->lastBufs : &right->bufs)->pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
-                              (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad, st);
-    left->launches += 2;
+    if (orbfe_launch_stereo_batch(left->g, (left->lastBufs ? left->lastBufs : &left->bufs)->pyr,
+                                  (right->lastBufs ? right->lastBufs : &right->bufs)->pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
+                                  (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad, st) != 0)
+        return fail(ORBFE_ERR_CUDA, "stereo match: candidate index allocation", cudaGetLastError());
+    left->launches += 3;
     CK(cudaGetLastError());
     return ORBFE_OK;
 }

@@ -4,25 +4,30 @@
 //
 // One warp per LEFT keypoint.  The reference's per-row candidate table (:1132-1155) is only an
 // index: right keypoint iR is a candidate of row (int)vL iff floor(yR-r) <= row <= ceil(yR+r),
-// r = 2*mvScaleFactors[octave].  The warp evaluates that predicate plus the octave and disparity
-// gates for all right keypoints (lanes stride iR), takes the Hamming minimum as a packed key
+// r = 2*mvScaleFactors[octave].  k_stereo_rows builds the same index per band of 16 image rows
+// (count, scan, fill by one CTA per pair); the warp then evaluates the exact predicate plus the octave
+// and disparity gates for the right keypoints of its band only, takes the Hamming minimum as a packed key
 // (dist << 16 | iR: strict `<` in ascending-iR order == lowest iR among equal distances, start
 // value TH_HIGH), then slides the 11x11 SAD window (+-5 px) with the 121 pixels spread over the
 // lanes, fits the parabola and writes mvuRight / mvDepth.  A second single-CTA kernel applies
 // the median-based outlier cut (:1343-1357) with a rank selection instead of a sort.
 #include <limits.h>
 
+#include <algorithm>
+
 #include "orbfe_internal.h"
 
 namespace {
 
 constexpr int TH_HIGH = 100, TH_LOW = 50;  // ORBmatcher.cc:36-37
+constexpr int SB_H = 16;                   // image rows per candidate band
 
 __device__ __forceinline__ void stereo_one(const OrbfeFrameGeom& g, const uint8_t* __restrict__ pyrL,
          const uint8_t* __restrict__ pyrR, const OrbfeKeyPoint* __restrict__ keysL,
          const uint32_t* __restrict__ descL, int N, const OrbfeKeyPoint* __restrict__ keysR,
          const uint32_t* __restrict__ descR, int Nr, float mbf, float mb, float* __restrict__ uRight,
-         float* __restrict__ depth, int* __restrict__ sadOut) {
+         float* __restrict__ depth, int* __restrict__ sadOut, const int* __restrict__ bandStart,
+         const int* __restrict__ bandList) {
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (iL >= N) return;
@@ -44,7 +49,9 @@ __device__ __forceinline__ void stereo_one(const OrbfeFrameGeom& g, const uint8_
         *reinterpret_cast<uint4*>(dl + 4) = p[1];
     }
     uint32_t key = (uint32_t)TH_HIGH << 16;
-    for (int iR = lane; iR < Nr; iR += 32) {
+    const int c0 = bandStart[row / SB_H], c1 = bandStart[row / SB_H + 1];
+    for (int c = c0 + lane; c < c1; c += 32) {
+        const int iR = bandList[c];
         const OrbfeKeyPoint kpR = keysR[iR];
         if (kpR.octave < 0 || kpR.octave >= g.nlevels) continue;
         const float r = 2.0f * g.lv[kpR.octave].scale;
@@ -127,13 +134,58 @@ __device__ __forceinline__ void stereo_one(const OrbfeFrameGeom& g, const uint8_
     }
 }
 
+// Candidate index of the right keypoints of one pair (blockIdx.x): bandList[bandStart[b] .. bandStart[b + 1]) = the right
+// keypoints whose row range [floor(y - r), ceil(y + r)] meets rows [16 b, 16 b + 15] (any order: the matcher's key
+// carries the index).  At most `span` entries per keypoint, so span * capacity entries per pair.
+__global__ void __launch_bounds__(256)
+k_stereo_rows(const __grid_constant__ OrbfeFrameGeom g, const OrbfeKeyPoint* __restrict__ keysR, const int* __restrict__ nR,
+              int NrHost, int capacity, int nb, int span, int* __restrict__ bandStart, int* __restrict__ bandList) {
+    extern __shared__ int sb[];      // counts / cursors [nb], starts [nb + 1]
+    int* cnt = sb;
+    int* start = sb + nb;
+    const size_t b = blockIdx.x;
+    const int Nr = nR ? min(nR[b], capacity) : NrHost;
+    const OrbfeKeyPoint* kr = keysR + b * (size_t)capacity;
+    const int nRows = g.lv[0].h;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; pass++) {
+        for (int iR = threadIdx.x; iR < Nr; iR += blockDim.x) {
+            const OrbfeKeyPoint kp = kr[iR];
+            if (kp.octave < 0 || kp.octave >= g.nlevels) continue;
+            const float r = 2.0f * g.lv[kp.octave].scale;
+            const int maxr = (int)ceilf(kp.y + r), minr = (int)floorf(kp.y - r);
+            if (maxr < 0 || minr > nRows - 1) continue;
+            const int b0 = max(minr, 0) / SB_H, b1 = min(min(maxr, nRows - 1) / SB_H, b0 + span - 1);
+            for (int k = b0; k <= b1; k++) {
+                const int pos = atomicAdd(&cnt[k], 1);
+                if (pass == 1) bandList[b * (size_t)capacity * span + start[k] + pos] = iR;
+            }
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (threadIdx.x == 0) {
+                int acc = 0;
+                for (int k = 0; k < nb; k++) { start[k] = acc; acc += cnt[k]; }
+                start[nb] = acc;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i <= nb; i += blockDim.x) {
+                bandStart[b * (size_t)(nb + 1) + i] = start[i];
+                if (i < nb) cnt[i] = 0;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_stereo(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL,
          const uint8_t* __restrict__ pyrR, const OrbfeKeyPoint* __restrict__ keysL,
          const uint32_t* __restrict__ descL, int N, const OrbfeKeyPoint* __restrict__ keysR,
          const uint32_t* __restrict__ descR, int Nr, float mbf, float mb, float* __restrict__ uRight,
-         float* __restrict__ depth, int* __restrict__ sadOut) {
-    stereo_one(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sadOut);
+         float* __restrict__ depth, int* __restrict__ sadOut, const int* __restrict__ bandStart, const int* __restrict__ bandList) {
+    stereo_one(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sadOut, bandStart, bandList);
 }
 
 // The same for a batch of rectified pairs whose pyramids, keypoints and descriptors are resident in HBM (the output
@@ -142,10 +194,12 @@ __global__ void __launch_bounds__(256)
 k_stereo_batch(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__ pyrL, const uint8_t* __restrict__ pyrR,
                const OrbfeKeyPoint* __restrict__ keysL, const uint32_t* __restrict__ descL, const int* __restrict__ nL,
                const OrbfeKeyPoint* __restrict__ keysR, const uint32_t* __restrict__ descR, const int* __restrict__ nR,
-               int capacity, float mbf, float mb, float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sadOut) {
+               int capacity, float mbf, float mb, float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sadOut,
+               int nb, int span, const int* __restrict__ bandStart, const int* __restrict__ bandList) {
     const size_t b = blockIdx.y, o = b * (size_t)capacity;
     stereo_one(g, pyrL + b * g.pyrStride, pyrR + b * g.pyrStride, keysL + o, descL + 8 * o, min(nL[b], capacity), keysR + o,
-               descR + 8 * o, min(nR[b], capacity), mbf, mb, uRight + o, depth + o, sadOut + o);
+               descR + 8 * o, min(nR[b], capacity), mbf, mb, uRight + o, depth + o, sadOut + o, bandStart + b * (size_t)(nb + 1),
+               bandList + o * span);
 }
 
 __device__ __forceinline__ void stereo_median_one(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad);
@@ -197,19 +251,43 @@ __device__ __forceinline__ void stereo_median_one(int N, float* __restrict__ uRi
 
 }  // namespace
 
-void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
-                         const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
-                         const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
-                         int* sad, cudaStream_t st) {
-    k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad);
-    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+// bands of the candidate index and the most bands one right keypoint can meet (row range <= 2 * 2 * scale + 2 rows)
+static void stereo_band_geometry(const OrbfeFrameGeom& g, int* nb, int* span) {
+    float smax = 1.f;
+    for (int l = 0; l < g.nlevels; l++) smax = g.lv[l].scale > smax ? g.lv[l].scale : smax;
+    *nb = (g.lv[0].h + SB_H - 1) / SB_H;
+    *span = (int)((4.f * smax + 2.f) / SB_H) + 2;
 }
 
-void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
-                               const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
-                               const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
-                               float* depth, int* sad, cudaStream_t st) {
+int orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
+                        const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
+                        const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
+                        int* sad, cudaStream_t st) {
+    int nb, span;
+    stereo_band_geometry(g, &nb, &span);
+    int* idx = nullptr;
+    if (cudaMallocAsync((void**)&idx, sizeof(int) * ((size_t)(nb + 1) + (size_t)std::max(Nr, 1) * span), st) != cudaSuccess) return -1;
+    int* list = idx + (nb + 1);
+    k_stereo_rows<<<1, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nullptr, Nr, Nr, nb, span, idx, list);
+    k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad, idx, list);
+    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+    cudaFreeAsync(idx, st);
+    return 0;
+}
+
+int orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
+                              const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
+                              const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
+                              float* depth, int* sad, cudaStream_t st) {
+    int nb, span;
+    stereo_band_geometry(g, &nb, &span);
+    int* idx = nullptr;
+    if (cudaMallocAsync((void**)&idx, sizeof(int) * (size_t)B * ((size_t)(nb + 1) + (size_t)capacity * span), st) != cudaSuccess) return -1;
+    int* list = idx + (size_t)B * (nb + 1);
+    k_stereo_rows<<<B, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nR, 0, capacity, nb, span, idx, list);
     k_stereo_batch<<<dim3((capacity + 7) / 8, B), 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, nL, keysR, descR, nR, capacity, mbf,
-                                                              mb, uRight, depth, sad);
+                                                              mb, uRight, depth, sad, nb, span, idx, list);
     k_stereo_median_batch<<<B, 1024, 0, st>>>(nL, capacity, uRight, depth, sad);
+    cudaFreeAsync(idx, st);
+    return 0;
 }
