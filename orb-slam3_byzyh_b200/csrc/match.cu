@@ -344,6 +344,18 @@ int orbfe_knn2_device(const uint8_t* d_query, int nq, const uint8_t* d_train, in
         return mfail(ORBFE_ERR_INVALID, "bad arguments (nt must be < 2^23 per call: shard larger maps)");
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* partial = nullptr;
+    {   // the scratch comes from the device's stream-ordered pool: keep freed blocks in the pool across synchronisations
+        // (the default threshold of 0 hands them back to the driver at every sync, and every call pays a fresh allocation)
+        static bool kept[64] = {};
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev < 64 && !kept[dev] && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = 1ull << 30, cur = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            kept[dev] = true;
+        }
+    }
     MCK(cudaMallocAsync((void**)&partial, orbfe_knn2_partial_bytes(nq, nt), st));
     const int erc = orbfe_knn2_enqueue(d_query, nq, d_train, nt, train_offset, d_idx2, d_dist2, nullptr, partial, st);
     if (erc < 0) { cudaFreeAsync(partial, st); return erc; }

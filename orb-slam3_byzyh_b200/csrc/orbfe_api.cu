@@ -897,15 +897,15 @@ int orbfe_stereo_match(OrbfeExtractor* left, OrbfeExtractor* right, int frame, c
     const size_t ikl = S.in(keys_l, sizeof(OrbfeKeyPoint) * (size_t)nl), idl = S.in(desc_l, 32 * (size_t)nl);
     const size_t ikr = S.in(keys_r, sizeof(OrbfeKeyPoint) * (size_t)nr), idr = S.in(desc_r, 32 * (size_t)nr);
     const size_t wsad = S.work(4 * (size_t)nl);
+    const size_t widx = S.work(4 * orbfe_stereo_index_ints(left->g, 1, nr));   // candidate index per band of rows
     const size_t our = S.out(u_right, 4 * (size_t)nl), odp = S.out(depth, 4 * (size_t)nl);
     CK(S.commit(left->device));
     cudaError_t e = S.upload();
     if (e == cudaSuccess) {
-        if (orbfe_launch_stereo(left->g, lbL.pyr + (size_t)frame * left->g.pyrStride,
-                                lbR.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
-                                S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
-                                S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.stream()) != 0)
-            return fail(ORBFE_ERR_CUDA, "stereo match: candidate index allocation", cudaGetLastError());
+        orbfe_launch_stereo(left->g, lbL.pyr + (size_t)frame * left->g.pyrStride,
+                            lbR.pyr + (size_t)frame * right->g.pyrStride, S.ptr<OrbfeKeyPoint>(ikl),
+                            S.ptr<uint32_t>(idl), nl, S.ptr<OrbfeKeyPoint>(ikr), S.ptr<uint32_t>(idr), nr, mbf, mb,
+                            S.ptr<float>(our), S.ptr<float>(odp), S.ptr<int>(wsad), S.ptr<int>(widx), S.stream());
         left->launches += 3;
         e = cudaGetLastError();
     }
@@ -931,7 +931,8 @@ int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right,
     if (capacity <= 0 || capacity >= 65536 || !d_keys_l || !d_desc_l || !d_n_l || !d_keys_r || !d_desc_r || !d_n_r || !d_u_right || !d_depth)
         return fail(ORBFE_ERR_INVALID, "bad arguments (capacity must be < 65536)");
     cudaStream_t st = stream ? (cudaStream_t)stream : left->sCompute;
-    const size_t need = (size_t)B * capacity;
+    const size_t nsad = (size_t)B * capacity;                 // SAD per left keypoint, then the candidate index
+    const size_t need = nsad + orbfe_stereo_index_ints(left->g, B, capacity);
     if (need > left->stereoSadElems) {
         CK(cudaStreamSynchronize(st));
         if (left->d_stereoSad) cudaFree(left->d_stereoSad);
@@ -939,10 +940,10 @@ int orbfe_stereo_match_batch_device(OrbfeExtractor* left, OrbfeExtractor* right,
         CK(cudaMalloc(&left->d_stereoSad, need * sizeof(int)));
         left->stereoSadElems = need;
     }
-    if (orbfe_launch_stereo_batch(left->g, (left->lastBufs ? left->lastBufs : &left->bufs)->pyr,
-                                  (right->lastBufs ? right->lastBufs : &right->bufs)->pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
-                                  (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad, st) != 0)
-        return fail(ORBFE_ERR_CUDA, "stereo match: candidate index allocation", cudaGetLastError());
+    orbfe_launch_stereo_batch(left->g, (left->lastBufs ? left->lastBufs : &left->bufs)->pyr,
+                              (right->lastBufs ? right->lastBufs : &right->bufs)->pyr, B, d_keys_l, (const uint32_t*)d_desc_l, d_n_l, d_keys_r,
+                              (const uint32_t*)d_desc_r, d_n_r, capacity, mbf, mb, d_u_right, d_depth, left->d_stereoSad,
+                              left->d_stereoSad + nsad, st);
     left->launches += 3;
     CK(cudaGetLastError());
     return ORBFE_OK;

@@ -234,11 +234,12 @@ struct OrbfeExtractor {
 
 
 // Frame::ComputeStereoMatches kernels (stereo.cu); pointers are device pointers.
-int orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
+size_t orbfe_stereo_index_ints(const OrbfeFrameGeom& g, int B, int capacity);   // scratch ints of the candidate index
+void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
                          const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
                          const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
-                         int* sad, cudaStream_t st);
-int orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
+                         int* sad, int* idx, cudaStream_t st);
+void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
                                const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
                                const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
-                               float* depth, int* sad, cudaStream_t st);
+                               float* depth, int* sad, int* idx, cudaStream_t st);

@@ -259,35 +259,34 @@ static void stereo_band_geometry(const OrbfeFrameGeom& g, int* nb, int* span) {
     *span = (int)((4.f * smax + 2.f) / SB_H) + 2;
 }
 
-int orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
-                        const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
-                        const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
-                        int* sad, cudaStream_t st) {
+// ints of scratch the candidate index of B pairs of `capacity` keypoints needs
+size_t orbfe_stereo_index_ints(const OrbfeFrameGeom& g, int B, int capacity) {
     int nb, span;
     stereo_band_geometry(g, &nb, &span);
-    int* idx = nullptr;
-    if (cudaMallocAsync((void**)&idx, sizeof(int) * ((size_t)(nb + 1) + (size_t)std::max(Nr, 1) * span), st) != cudaSuccess) return -1;
-    int* list = idx + (nb + 1);
-    k_stereo_rows<<<1, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nullptr, Nr, Nr, nb, span, idx, list);
-    k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad, idx, list);
-    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
-    cudaFreeAsync(idx, st);
-    return 0;
+    return (size_t)B * ((size_t)(nb + 1) + (size_t)std::max(capacity, 1) * span);
 }
 
-int orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
-                              const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
-                              const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
-                              float* depth, int* sad, cudaStream_t st) {
+void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR,
+                         const OrbfeKeyPoint* keysL, const uint32_t* descL, int N, const OrbfeKeyPoint* keysR,
+                         const uint32_t* descR, int Nr, float mbf, float mb, float* uRight, float* depth,
+                         int* sad, int* idx, cudaStream_t st) {
     int nb, span;
     stereo_band_geometry(g, &nb, &span);
-    int* idx = nullptr;
-    if (cudaMallocAsync((void**)&idx, sizeof(int) * (size_t)B * ((size_t)(nb + 1) + (size_t)capacity * span), st) != cudaSuccess) return -1;
+    int* list = idx + (nb + 1);
+    k_stereo_rows<<<1, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nullptr, Nr, std::max(Nr, 1), nb, span, idx, list);
+    k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad, idx, list);
+    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+}
+
+void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
+                               const OrbfeKeyPoint* keysL, const uint32_t* descL, const int* nL, const OrbfeKeyPoint* keysR,
+                               const uint32_t* descR, const int* nR, int capacity, float mbf, float mb, float* uRight,
+                               float* depth, int* sad, int* idx, cudaStream_t st) {
+    int nb, span;
+    stereo_band_geometry(g, &nb, &span);
     int* list = idx + (size_t)B * (nb + 1);
     k_stereo_rows<<<B, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nR, 0, capacity, nb, span, idx, list);
     k_stereo_batch<<<dim3((capacity + 7) / 8, B), 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, nL, keysR, descR, nR, capacity, mbf,
                                                               mb, uRight, depth, sad, nb, span, idx, list);
     k_stereo_median_batch<<<B, 1024, 0, st>>>(nL, capacity, uRight, depth, sad);
-    cudaFreeAsync(idx, st);
-    return 0;
 }

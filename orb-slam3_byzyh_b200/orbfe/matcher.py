@@ -330,9 +330,11 @@ class ORBmatcher:
     def knn2_batch_device(d_descL, d_monoL, d_nL, d_descR, d_monoR, d_nR, stream=None):
         import torch
         B, cap = d_descL.shape[0], d_descL.shape[1]
-        idx2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
-        dist2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
-        match = torch.full((B, cap), -1, dtype=torch.int32, device=d_descL.device)
+        with torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream(d_descL.device)):
+            # the fills are ordered before the kernel: same stream
+            idx2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
+            dist2 = torch.full((B, cap, 2), -1, dtype=torch.int32, device=d_descL.device)
+            match = torch.full((B, cap), -1, dtype=torch.int32, device=d_descL.device)
         st = C.c_void_p(stream.cuda_stream) if stream is not None else None
         check(lib().orbfe_knn2_batch_device(ptr(d_descL), ptr(d_monoL), ptr(d_nL), ptr(d_descR), ptr(d_monoR), ptr(d_nR), B, cap,
                                             ptr(idx2), ptr(dist2), ptr(match), st))
