@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(128) k_scalar(const uint32_t* __restrict__ que
 }
 
 // ------------------------------------------------------------------ tensor-core kernel
+#ifndef ENC
+#define ENC 0                           // 1: A = +1 / -1, B = 0 / -1 (unmasked PRMT selectors); 0: both +1 / -1
+#endif
 constexpr int QT = 128;                 // queries per CTA = UMMA M
 constexpr int MT = 256;                 // map points per tile = UMMA N
 constexpr int KBYTES = 256;             // one signed byte per descriptor bit
@@ -193,6 +196,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 // rows [0, rows) of an operand tile from descriptor bits (8 words per row), +1 for a set bit, -1 for a clear one; rows
 // >= valid are zero.  Any fixed assignment of bits to K positions serves (both operands use this one): bit 4 j + i of a
 // word goes to byte j of output word i, so (w >> i) & 0x11111111 is at once the PRMT selector that picks 0x01 or 0xFF.
+// MODE 0: +1 / -1 for a set / clear bit (masked selectors).  MODE 1: the A side of the second encoding, +1 for a CLEAR bit
+// and -1 for a set one.  MODE 2: its B side, 0 / -1 for a clear / set bit: with the byte table {00, FF, 00, FF, ...} the
+// PRMT result depends on the lowest bit of a selector nibble only -- in the generic mode by construction, and in the
+// sign-replicate mode (nibble bit 3 set) because replicating the sign of 00 / FF gives 00 / FF again -- so the shifted
+// word is the selector as it is, no mask.  Then sum_k a_k b_k = popc(q) - hamming.
+template <int MODE>
 __device__ __forceinline__ void expand_row(uint8_t* dst, int p, uint4 w0, uint4 w1, bool ok) {
     uint8_t* rb = dst + (p >> 3) * SBO + (p & 7) * 16;
     if (ok) {
@@ -202,9 +211,14 @@ __device__ __forceinline__ void expand_row(uint8_t* dst, int p, uint4 w0, uint4 
             uint32_t lo[4], hi[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t t = (w[i] >> k) & 0x11111111u;
-                lo[k] = __byte_perm(0x000001FFu, 0u, t);
-                hi[k] = __byte_perm(0x000001FFu, 0u, t >> 16);
+                if (MODE == 2) {
+                    lo[k] = __byte_perm(0xFF00FF00u, 0xFF00FF00u, w[i] >> k);
+                    hi[k] = __byte_perm(0xFF00FF00u, 0xFF00FF00u, w[i] >> (16 + k));
+                } else {
+                    const uint32_t t = (w[i] >> k) & 0x11111111u;
+                    lo[k] = __byte_perm(MODE == 1 ? 0x0000FF01u : 0x000001FFu, 0u, t);
+                    hi[k] = __byte_perm(MODE == 1 ? 0x0000FF01u : 0x000001FFu, 0u, t >> 16);
+                }
             }
             *reinterpret_cast<uint4*>(rb + (2 * i) * LBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<uint4*>(rb + (2 * i + 1) * LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -214,11 +228,12 @@ __device__ __forceinline__ void expand_row(uint8_t* dst, int p, uint4 w0, uint4 
         for (int i = 0; i < 16; i++) *reinterpret_cast<uint4*>(rb + i * LBO) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
+template <int MODE>
 __device__ __forceinline__ void expand_rows(uint8_t* dst, const uint32_t* __restrict__ src, int rows, int valid, int tid, int nthr) {
     for (int p = tid; p < rows; p += nthr) {
         uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
         if (p < valid) { w0 = __ldg(reinterpret_cast<const uint4*>(src + 8 * (size_t)p)); w1 = __ldg(reinterpret_cast<const uint4*>(src + 8 * (size_t)p) + 1); }
-        expand_row(dst, p, w0, w1, p < valid);
+        expand_row<MODE>(dst, p, w0, w1, p < valid);
     }
 }
 
@@ -253,7 +268,7 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemPtr)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    expand_rows(sA, query + 8 * (size_t)q0, QT, min(QT, nq - q0), tid, 32 * NWARPS);
+    expand_rows<ENC ? 1 : 0>(sA, query + 8 * (size_t)q0, QT, min(QT, nq - q0), tid, 32 * NWARPS);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -293,13 +308,21 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
         const int q = q0 + quad * 32 + lane;
         if (q < nq) {
             const int baseEnd = tile1 * MT;
+            int pq = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) pq += __popc(query[8 * (size_t)q + i]);
             uint32_t o[2];
             const int b[2] = {b0, b1};
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 if (b[i] == INT_MAX) { o[i] = KEY_NONE; continue; }
-                const int D = (b[i] + (1 << 22)) >> 23, rel = b[i] - D * (1 << 23);
-                o[i] = ((uint32_t)(D + 128) << KEY_SHIFT) | (uint32_t)(baseEnd + rel);
+                if (ENC) {      // key' = (distance - popc(query)) * 2^22 + relative index
+                    const int D = (b[i] + (1 << 21)) >> 22, rel = b[i] - D * (1 << 22);
+                    o[i] = ((uint32_t)(D + pq) << KEY_SHIFT) | (uint32_t)(baseEnd + rel);
+                } else {        // key' = (distance - 128) * 2^23 + relative index
+                    const int D = (b[i] + (1 << 22)) >> 23, rel = b[i] - D * (1 << 23);
+                    o[i] = ((uint32_t)(D + 128) << KEY_SHIFT) | (uint32_t)(baseEnd + rel);
+                }
             }
             partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2] = o[0];
             partial[((size_t)q * nsplit * 2 + blockIdx.y * 2 + half) * 2 + 1] = o[1];
@@ -346,7 +369,7 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
             const long long c_a = clock64();
             mbar_wait(&bEmpty[s], ph ^ 1);
             const long long c_b = clock64();
-            if (!(mode & 1)) expand_row(sB + s * B_BYTES, ptid, c0, c1, ok);
+            if (!(mode & 1)) expand_row<ENC ? 2 : 0>(sB + s * B_BYTES, ptid, c0, c1, ok);
             fence_proxy_async();
             mbar_arrive(&bFull[s]);
             if (dbg && ptid == 0) { dbg[blockIdx.x * 16 + 4] += c_b - c_a; dbg[blockIdx.x * 16 + 5] += clock64() - c_b; }
@@ -372,7 +395,7 @@ __global__ void __launch_bounds__(QT) k_expand_queries(const uint32_t* __restric
     const int p = threadIdx.x, q = blockIdx.x * QT + p;
     uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
     if (q < nq) { w0 = __ldg(reinterpret_cast<const uint4*>(query + 8 * (size_t)q)); w1 = __ldg(reinterpret_cast<const uint4*>(query + 8 * (size_t)q) + 1); }
-    expand_row(img + (size_t)blockIdx.x * A_BYTES, p, w0, w1, q < nq);
+    expand_row<0>(img + (size_t)blockIdx.x * A_BYTES, p, w0, w1, q < nq);
 }
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -531,7 +554,7 @@ k_umma_knn_x(const uint8_t* __restrict__ qimg, int nq, const uint32_t* __restric
                 if (t + 1 < ntiles && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
             }
             mbar_wait(&bEmpty[s], ph ^ 1);
-            expand_row(sB + s * B_BYTES, ptid, c0, c1, ok);
+            expand_row<0>(sB + s * B_BYTES, ptid, c0, c1, ok);
             fence_proxy_async();
             mbar_arrive(&bFull[s]);
         }
