@@ -90,10 +90,12 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires) instead
+// of spinning through the loop -- spinning warps would take issue slots from the warps that work
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ uint64_t global_ns() {
@@ -104,8 +106,8 @@ __device__ __forceinline__ uint64_t global_ns() {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {   // bounded (2 s): a trap is better than a hung GPU
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = global_ns();
-    while (!mbar_try_wait(bar, parity))
-        if (global_ns() - t0 > 2000000000ull) __trap();
+    for (uint32_t it = 1; !mbar_try_wait(bar, parity); it++)
+        if ((it & 63u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -370,9 +372,11 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
             mbar_wait(&bEmpty[s], ph ^ 1);
             const long long c_b = clock64();
             if (!(mode & 1)) expand_row<ENC ? 2 : 0>(sB + s * B_BYTES, ptid, c0, c1, ok);
+            const long long c_c = clock64();
             fence_proxy_async();
+            const long long c_d = clock64();
             mbar_arrive(&bFull[s]);
-            if (dbg && ptid == 0) { dbg[blockIdx.x * 16 + 4] += c_b - c_a; dbg[blockIdx.x * 16 + 5] += clock64() - c_b; }
+            if (dbg && ptid == 0) { dbg[blockIdx.x * 16 + 4] += c_b - c_a; dbg[blockIdx.x * 16 + 5] += clock64() - c_b; dbg[blockIdx.x * 16 + 6] += c_c - c_b; dbg[blockIdx.x * 16 + 7] += c_d - c_c; }
         }
     }
     tc_fence_before();
@@ -623,8 +627,8 @@ int main(int argc, char** argv) {
         CK(cudaDeviceSynchronize());
         std::vector<long long> h(16 * qtiles); CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
         const double tl = (nt / nsplit + MT - 1) / MT;
-        printf("  cycles per tile (CTA 0): epilogue wait %.0f work %.0f | mma wait-B %.0f wait-acc %.0f | producer wait %.0f work %.0f\n",
-               h[0] / tl, h[1] / tl, h[2] / tl, h[3] / tl, h[4] / tl, h[5] / tl);
+        printf("  cycles per tile (CTA 0): epilogue wait %.0f work %.0f | mma wait-B %.0f wait-acc %.0f | producer wait %.0f work %.0f (expansion %.0f, proxy fence %.0f)\n",
+               h[0] / tl, h[1] / tl, h[2] / tl, h[3] / tl, h[4] / tl, h[5] / tl, h[6] / tl, h[7] / tl);
         k_umma_knn<<<grid2, 32 * NWARPS, SMEM_BYTES>>>(dq, nq, dt, nt, nsplit, p2, swapOffsets, mode, nullptr);
         CK(cudaDeviceSynchronize());
     }
