@@ -893,6 +893,11 @@ def matching_leg(torch, dist, orbfe, dev, rank, world, steps, barrier, max_over_
                                                   "peak_GBs": 64.0 * 148 * 1965e6 * world / 1e9,
                                                   "frac": pairs * 4.0 / (64.0 * 148 * 1965e6 * world),
                                                   "note": "peak = 64 B/clk/SM of 32-bit tcgen05.ld; the kernel reads with .pack::16b (two columns per register), which is how it can sit above 1.0"},
+                             # north_star's INT view of the same number: the plain statement of DescriptorDistance needs
+                             # 8 POPC32 per pair; the POPC pipe (25 lanes/clk/SM measured, profiles/r1_pipe_bench.txt) caps a
+                             # popcount kernel at peak / 8 pairs/s (the scalar kernel reached 0.46 of it with 5 POPC per pair)
+                             "int_view": {"algorithmic_popc32_per_s": pairs * 8.0, "popc_pipe_peak_per_s": 25.0 * 148 * 1965e6 * world,
+                                          "ratio_to_popc_pipe_peak": pairs * 8.0 / (25.0 * 148 * 1965e6 * world)},
                              "scalar_kernel_pairs_per_s_1gpu": 0.68e12,
                              "ncu": "profiles/r2_match_ncu_summary.txt"}}
     if world > 1:
