@@ -46,6 +46,25 @@ def test_knn2_vs_oracle(orbfe, nq, nt):
     assert np.array_equal(idx, eidx) and np.array_equal(dist, edist) and np.array_equal(match, em)
 
 
+def test_knn2_ragged_sizes_on_the_tensor_core_kernel(orbfe):
+    """Sixteen random problem sizes that are ragged against the 128-query / 256-point tiles of csrc/knn_umma.cu (every
+    one above its size switch), with duplicates of query rows planted at both ends of the map and ties between map rows:
+    idx2 / dist2 / match equal the oracle's (cv2 BFMatcher order)."""
+    rng = np.random.default_rng(2024)
+    m = orbfe.ORBmatcher()
+    for case in range(16):
+        nq, nt = int(rng.integers(33, 700)), int(rng.integers(8200, 30000))
+        q, t = synth.random_descriptors(nq, 1000 + case), synth.random_descriptors(nt, 2000 + case)
+        t[0] = q[nq - 1]
+        t[nt - 1] = q[0]
+        t[nt // 2] = t[nt // 2 + 1]                       # equal rows: the lower index first
+        for i in range(0, nq, 5):
+            t[int(rng.integers(0, nt))] = synth.flip_bits(q[i], int(rng.integers(0, 90)), rng)
+        idx, dist, match = m.knn2(q, t)
+        em, eidx, edist = O.fisheye_matches(q, t)
+        assert np.array_equal(idx, eidx) and np.array_equal(dist, edist) and np.array_equal(match, em), (nq, nt)
+
+
 def test_knn2_sharded_merge_equals_whole(orbfe):
     q, t = synth.random_descriptors(500, 3), synth.random_descriptors(30000, 4)
     t[100] = q[7]; t[25000] = q[7]
