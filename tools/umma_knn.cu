@@ -78,7 +78,10 @@ constexpr int MT = 256;                 // map points per tile = UMMA N
 constexpr int KBYTES = 256;             // one signed byte per descriptor bit
 constexpr int A_BYTES = QT * KBYTES, B_BYTES = MT * KBYTES;
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8, NWARPS = EPI_WARPS + 1 + PROD_WARPS;   // epilogue: 2 column halves x 4 lane quadrants
-constexpr int SMEM_BYTES = A_BYTES + 2 * B_BYTES + 128 + 1024;
+#ifndef NSTAGE
+#define NSTAGE 2                        // shared-memory buffers of expanded map tiles
+#endif
+constexpr int SMEM_BYTES = A_BYTES + NSTAGE * B_BYTES + 128 + 1024;
 // operand tiles are stored as 8-row x 16-byte core matrices (128 contiguous bytes), K chunks next to each other:
 // core (row group g, K chunk c) at (g * 16 + c) * 128
 constexpr uint32_t CORE = 128, LBO = CORE, SBO = 16 * CORE;
@@ -248,9 +251,9 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + 2 * B_BYTES);
-    uint64_t *bFull = bars, *bEmpty = bars + 2, *accFull = bars + 4, *accEmpty = bars + 6;
-    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A_BYTES + NSTAGE * B_BYTES);
+    uint64_t *bFull = bars, *bEmpty = bars + 3, *accFull = bars + 6, *accEmpty = bars + 8;
+    uint32_t* tmemPtr = reinterpret_cast<uint32_t*>(bars + 10);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // map tiles of this CTA
@@ -260,8 +263,7 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
     const int q0 = blockIdx.x * QT;
 
     if (tid == 0) {
-        mbar_init(&bFull[0], 32 * PROD_WARPS); mbar_init(&bFull[1], 32 * PROD_WARPS);
-        mbar_init(&bEmpty[0], 1); mbar_init(&bEmpty[1], 1);
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(&bFull[i], 32 * PROD_WARPS); mbar_init(&bEmpty[i], 1); }
         mbar_init(&accFull[0], 1); mbar_init(&accFull[1], 1);
         mbar_init(&accEmpty[0], 32 * EPI_WARPS); mbar_init(&accEmpty[1], 32 * EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -337,18 +339,19 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
             const uint32_t lbo = swapOffsets ? SBO : LBO, sbo = swapOffsets ? LBO : SBO;
             const uint64_t dA = umma_desc(smem_u32(sA), lbo, sbo);
             for (int t = 0; t < ntiles; t++) {
-                const int s = t & 1, ph = (t >> 1) & 1;
+                const int s = t & 1, ph = (t >> 1) & 1;           // accumulator slot
+                const int sb = t % NSTAGE, phb = (t / NSTAGE) & 1;  // map tile buffer
                 const long long c_a = clock64();
-                mbar_wait(&bFull[s], ph);
+                mbar_wait(&bFull[sb], phb);
                 const long long c_b = clock64();
                 mbar_wait(&accEmpty[s], ph ^ 1);
                 tc_fence_after();
                 if (dbg) { dbg[blockIdx.x * 16 + 2] += c_b - c_a; dbg[blockIdx.x * 16 + 3] += clock64() - c_b; }
-                const uint64_t dB = umma_desc(smem_u32(sB + s * B_BYTES), lbo, sbo);
+                const uint64_t dB = umma_desc(smem_u32(sB + sb * B_BYTES), lbo, sbo);
 #pragma unroll
                 for (int k = 0; k < KBYTES / 32; k++)   // 32 K bytes = two 16-byte chunks per instruction
                     umma_i8(tmem + (uint32_t)(s * MT), dA + (uint64_t)((k * 2 * CORE) >> 4), dB + (uint64_t)((k * 2 * CORE) >> 4), idesc, k > 0);
-                umma_commit(&bEmpty[s]);
+                umma_commit(&bEmpty[sb]);
                 umma_commit(&accFull[s]);
             }
         }
@@ -361,7 +364,7 @@ k_umma_knn(const uint32_t* __restrict__ query, int nq, const uint32_t* __restric
             if (ntiles > 0 && m < nt) { w0 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m)); w1 = __ldg(reinterpret_cast<const uint4*>(train + 8 * (size_t)m) + 1); }
         }
         for (int t = 0; t < ntiles; t++) {
-            const int s = t & 1, ph = (t >> 1) & 1;
+            const int s = t % NSTAGE, ph = (t / NSTAGE) & 1;
             const uint4 c0 = w0, c1 = w1;
             const bool ok = (tile0 + t) * MT + ptid < nt;
             {   // the bits of the next tile travel while this one is expanded
