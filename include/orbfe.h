@@ -148,7 +148,9 @@ int orbfe_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t
 /* cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k=2) + the `d0 < d1*0.7` ratio test of
  * Frame::ComputeStereoFishEyeMatches, src/Frame.cc:47,1553,1562.  idx2/dist2 are nq x 2
  * (best, second; -1 when train has < 2 rows); match[i] = accepted train index or -1.
- * `train_offset` is added to every returned index (map sharding). Host pointers. */
+ * `train_offset` is added to every returned index (map sharding). Host pointers.
+ * nt < 2^23 per call and rows 16-byte aligned.  From 2^18 descriptor pairs on the search runs on the tensor cores
+ * (tcgen05.mma on one signed byte per descriptor bit, csrc/knn_umma.cu) with the same result bit for bit. */
 int orbfe_knn2(const uint8_t* query, int nq, const uint8_t* train, int nt, int train_offset,
                int32_t* idx2, int32_t* dist2, int32_t* match, int device);
 /* Device-pointer form on `stream`, no synchronisation. */
