@@ -10,7 +10,7 @@
 // (dist << 16 | iR: strict `<` in ascending-iR order == lowest iR among equal distances, start
 // value TH_HIGH), then slides the 11x11 SAD window (+-5 px) with the 121 pixels spread over the
 // lanes, fits the parabola and writes mvuRight / mvDepth.  A second single-CTA kernel applies
-// the median-based outlier cut (:1343-1357) with a rank selection instead of a sort.
+// the median-based outlier cut (:1343-1357) with a radix selection of the median instead of a sort.
 #include <limits.h>
 
 #include <algorithm>
@@ -217,33 +217,56 @@ k_stereo_median_batch(const int* __restrict__ nL, int capacity, float* __restric
     stereo_median_one(min(nL[blockIdx.x], capacity), uRight + o, depth + o, sad + o);
 }
 
+// median = the element of rank n / 2 (0-based) of the n valid SADs, found by a two-level radix selection: a SAD of an
+// 11 x 11 window of bytes is < 2^15, so 256 bins of the upper 8 bits, then 128 bins of the lower 7 inside the chosen bin.
 __device__ __forceinline__ void stereo_median_one(int N, float* __restrict__ uRight, float* __restrict__ depth, const int* __restrict__ sad) {
-    __shared__ int s_cnt, s_median;
-    if (threadIdx.x == 0) { s_cnt = 0; s_median = -1; }
+    __shared__ int hist[256];
+    __shared__ int s_bin, s_rank, s_median;
+    const int nt = blockDim.x;
+    for (int i = threadIdx.x; i < 256; i += nt) hist[i] = 0;
+    if (threadIdx.x == 0) s_median = -1;
     __syncthreads();
-    int local = 0;
-    for (int i = threadIdx.x; i < N; i += 1024) local += sad[i] >= 0;
-    atomicAdd(&s_cnt, local);
-    __syncthreads();
-    const int n = s_cnt;
-    if (n == 0) return;
-    const int k = n / 2;
-    for (int i = threadIdx.x; i < N; i += 1024) {
+    for (int i = threadIdx.x; i < N; i += nt) {
         const int v = sad[i];
-        if (v < 0) continue;
-        int less = 0, leq = 0;
-        for (int j = 0; j < N; j++) {
-            const int o = sad[j];
-            if (o < 0) continue;
-            less += o < v;
-            leq += o <= v;
+        if (v >= 0) atomicAdd(&hist[min(v >> 7, 255)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int k = 0; k < 256; k++) n += hist[k];
+        s_bin = -1;
+        if (n > 0) {
+            int k = n / 2, acc = 0, bsel = 0;
+            for (; bsel < 256; bsel++) {
+                if (k < acc + hist[bsel]) break;
+                acc += hist[bsel];
+            }
+            s_bin = bsel;
+            s_rank = k - acc;
         }
-        if (less <= k && k < leq) s_median = v;  // all writers store the same value
+    }
+    __syncthreads();
+    const int bin = s_bin;
+    if (bin < 0) return;     // no match at all (the reference would index an empty vector)
+    for (int i = threadIdx.x; i < 128; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += nt) {
+        const int v = sad[i];
+        if (v >= 0 && min(v >> 7, 255) == bin) atomicAdd(&hist[v & 127], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0, lo = 0;
+        for (; lo < 128; lo++) {
+            if (s_rank < acc + hist[lo]) break;
+            acc += hist[lo];
+        }
+        s_median = (bin << 7) | lo;
     }
     __syncthreads();
     const float median = (float)s_median;
     const float thDist = 1.5f * 1.4f * median;
-    for (int i = threadIdx.x; i < N; i += 1024) {
+    for (int i = threadIdx.x; i < N; i += nt) {
         const int v = sad[i];
         if (v >= 0 && !((float)v < thDist)) { uRight[i] = -1.f; depth[i] = -1.f; }
     }
@@ -275,7 +298,7 @@ void orbfe_launch_stereo(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uin
     int* list = idx + (nb + 1);
     k_stereo_rows<<<1, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nullptr, Nr, std::max(Nr, 1), nb, span, idx, list);
     k_stereo<<<(N + 7) / 8, 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, N, keysR, descR, Nr, mbf, mb, uRight, depth, sad, idx, list);
-    k_stereo_median<<<1, 1024, 0, st>>>(N, uRight, depth, sad);
+    k_stereo_median<<<1, 256, 0, st>>>(N, uRight, depth, sad);
 }
 
 void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, const uint8_t* pyrR, int B,
@@ -288,5 +311,5 @@ void orbfe_launch_stereo_batch(const OrbfeFrameGeom& g, const uint8_t* pyrL, con
     k_stereo_rows<<<B, 256, sizeof(int) * (2 * nb + 1), st>>>(g, keysR, nR, 0, capacity, nb, span, idx, list);
     k_stereo_batch<<<dim3((capacity + 7) / 8, B), 256, 0, st>>>(g, pyrL, pyrR, keysL, descL, nL, keysR, descR, nR, capacity, mbf,
                                                               mb, uRight, depth, sad, nb, span, idx, list);
-    k_stereo_median_batch<<<B, 1024, 0, st>>>(nL, capacity, uRight, depth, sad);
+    k_stereo_median_batch<<<B, 256, 0, st>>>(nL, capacity, uRight, depth, sad);
 }
