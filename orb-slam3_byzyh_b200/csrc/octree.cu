@@ -6,6 +6,9 @@
 // coalesced gather), then runs the CTA-parallel quadtree of octree_core.h on it.  Node tables
 // live in shared memory (or in a global scratch block when nfeatures is so large that they do
 // not fit); the points and their labels stay in global memory (L2 resident).
+#include <algorithm>
+#include <cstdlib>
+
 #include "octree_core.h"
 #include "orbfe_internal.h"
 
@@ -147,7 +150,8 @@ int orbfe_octree_prepare(OrbfeFrameGeom& g) {
 
 void orbfe_launch_octree(const OrbfeFrameGeom& g, const OrbfeChunkBufs& b, int B, cudaStream_t st,
                          long long* launches) {
-    const int nt = B >= 128 ? OC_THREADS_BATCH : OC_THREADS;
+    int nt = B >= 128 ? OC_THREADS_BATCH : OC_THREADS;
+    if (const char* ev = getenv("ORBFE_OC_THREADS")) nt = std::min(OC_THREADS, std::max(32, atoi(ev) & ~31));   // tuning
     if (g.ocShared)
         k_octree<true><<<dim3(B, g.nlevels), nt, g.ocShared, st>>>(
             g, b.slots, b.cellCount, b.cand, b.pnode, b.candCount, b.kp, b.kpCount, b.ocGlobal, b.ocGlobalStride);
