@@ -417,12 +417,17 @@ static OC_HD void oc_copy_node(const OcNodes& nd, int j, int pos) {
 // live in global memory (L2) and a dependent load chain per point would expose its latency.
 #define OC_ILP 4
 
-// One sweep over the points: quadrant of every point that sits in an expandable node.
-static OC_HD void oc_count_children(const OcWork& w) {
+// One sweep over the points per pass.  After the node list was rebuilt every point takes the index its node (or its
+// child) has in the new list, and -- unless the distribution is finished -- is counted straight away into the child
+// populations of the NEXT pass: its quadrant inside the new node, if that node is still expandable.  (Two sweeps per
+// pass, one to count and one to re-label, read and wrote the labels twice and exposed the L2 latency twice.)
+static OC_HD void oc_relabel_count(const OcWork& w, int* win) {
     const OcNodes& nd = w.nd;
-    const int so = w.sc[OC_CUR] * w.M;     // offset of the current list buffer
+    const int so = w.sc[OC_CUR] * w.M;     // offset of the (new) current list buffer
     const int size = w.sc[OC_SIZE];
-    OC_PAR_FOR(k, 4 * size) w.cc[k] = 0;
+    const bool count = w.sc[OC_STATE] != OC_ST_DONE;
+    if (count) OC_PAR_FOR(k, 4 * size) w.cc[k] = 0;
+    else OC_PAR_FOR(k, size) win[k] = 0;
     OC_SYNC();
     for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
         uint32_t lab[OC_ILP], p[OC_ILP];
@@ -435,35 +440,22 @@ static OC_HD void oc_count_children(const OcWork& w) {
 #pragma unroll
         for (int u = 0; u < OC_ILP; u++) {
             const int i = i0 + u * OC_NT;
-            const int j = (int)(lab[u] & 0xFFFFFFu);
-            if (i < w.n && nd.cnt[so + j] > 1) {
-                const int X0 = nd.x0[so + j], X1 = nd.x1[so + j], Y0 = nd.y0[so + j], Y1 = nd.y1[so + j];
-                const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
-                const int q = (OC_PK_X(p[u]) < mx ? 0 : 1) + (OC_PK_Y(p[u]) < my ? 0 : 2);
-                w.pnode[i] = (uint32_t)j | ((uint32_t)q << 30);
-                OC_ATOMIC_ADD(&w.cc[4 * j + q], 1);
-            }
-        }
-    }
-    OC_SYNC();
-}
-
-// Re-label every point after the list was rebuilt by thread 0.
-static OC_HD void oc_relabel(const OcWork& w) {
-    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
-        uint32_t v[OC_ILP];
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++) {
-            const int i = i0 + u * OC_NT;
-            v[u] = i < w.n ? w.pnode[i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++) {
-            const int i = i0 + u * OC_NT;
             if (i < w.n) {
-                const int j = (int)(v[u] & 0xFFFFFFu);
-                const int r = w.remap[j];
-                w.pnode[i] = (uint32_t)(r >= 0 ? r : w.cpos[4 * j + (int)(v[u] >> 30)]);
+                const int jo = (int)(lab[u] & 0xFFFFFFu);
+                const int r = w.remap[jo];
+                const int j = r >= 0 ? r : w.cpos[4 * jo + (int)(lab[u] >> 30)];
+                uint32_t out = (uint32_t)j;
+                if (count && nd.cnt[so + j] > 1) {
+                    const int X0 = nd.x0[so + j], X1 = nd.x1[so + j], Y0 = nd.y0[so + j], Y1 = nd.y1[so + j];
+                    const int mx = X0 + oc_half(X0, X1), my = Y0 + oc_half(Y0, Y1);
+                    const int q = (OC_PK_X(p[u]) < mx ? 0 : 1) + (OC_PK_Y(p[u]) < my ? 0 : 2);
+                    out |= (uint32_t)q << 30;
+                    OC_ATOMIC_ADD(&w.cc[4 * j + q], 1);
+                }
+                // last pass: the node's winner (:1028-1053) is the maximum of response << 24 | (2^24 - 1 - index), i.e.
+                // the best response and, among equals, the first candidate
+                if (!count) OC_ATOMIC_MAX((unsigned int*)&win[j], ((unsigned int)OC_PK_S(p[u]) << 24) | (unsigned int)(0xFFFFFF - i));
+                w.pnode[i] = out;
             }
         }
     }
@@ -627,7 +619,7 @@ static OC_HD void oc_phase2(const OcWork& w, int N) {
 // writes it; visible to all threads after the final OC_SYNC).
 //   width/height = maxX-minX / maxY-minY of the level window, N = mnFeaturesPerLevel[level].
 static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni, float hX, int N,
-                                int* out_idx, int* out_n, int* best_score /*[M] scratch*/) {
+                                int* out_idx, int* out_n, int* /*scratch, unused*/) {
     // ---- roots (:718-790) ----
     if (OC_TID == 0) {
         const OcNodes& nd = w.nd;
@@ -661,16 +653,13 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
         w.sc[OC_NV] = 0;
     }
     OC_SYNC();
-    oc_relabel(w);
+    oc_relabel_count(w, out_idx);
     OC_MARK(0);   // roots
 
     // ---- main loop (:805-1020) ----
     while (true) {
-        OC_SYNC();
         const int state = w.sc[OC_STATE];
-        if (state == OC_ST_DONE) break;
-        oc_count_children(w);
-        OC_MARK(1);   // child populations
+        if (state == OC_ST_DONE) break;   // (thread 0 rewrites the state only behind a barrier inside the rebuild)
         if (state == OC_ST_PHASE1) {
             oc_rebuild_phase1(w, N);
             OC_MARK(2);   // phase-1 rebuild (thread 0's share)
@@ -678,42 +667,13 @@ static OC_HD void oc_distribute(const OcWork& w, int width, int height, int nIni
             oc_phase2(w, N);
         }
         OC_SYNC();
-        oc_relabel(w);
-        OC_MARK(4);   // relabel
+        oc_relabel_count(w, out_idx);
+        OC_MARK(4);   // relabel + child populations of the next pass
     }
 
-    // ---- best response per node, first candidate wins ties (:1028-1053) ----
+    // ---- best response per node, first candidate wins ties (:1028-1053): selected by the last sweep ----
     const int size = w.sc[OC_SIZE];
-    OC_PAR_FOR(k, size) { best_score[k] = -1; out_idx[k] = 0x7FFFFFFF; }
-    OC_SYNC();
-    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
-        uint32_t lab[OC_ILP], p[OC_ILP];
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++) {
-            const int i = i0 + u * OC_NT;
-            lab[u] = i < w.n ? w.pnode[i] : 0u;
-            p[u] = i < w.n ? w.pk[i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++)
-            if (i0 + u * OC_NT < w.n) OC_ATOMIC_MAX(&best_score[lab[u] & 0xFFFFFFu], OC_PK_S(p[u]));
-    }
-    OC_SYNC();
-    for (int i0 = OC_TID; i0 < w.n; i0 += OC_ILP * OC_NT) {
-        uint32_t lab[OC_ILP], p[OC_ILP];
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++) {
-            const int i = i0 + u * OC_NT;
-            lab[u] = i < w.n ? w.pnode[i] : 0u;
-            p[u] = i < w.n ? w.pk[i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < OC_ILP; u++) {
-            const int i = i0 + u * OC_NT;
-            const int j = (int)(lab[u] & 0xFFFFFFu);
-            if (i < w.n && OC_PK_S(p[u]) == best_score[j]) OC_ATOMIC_MIN(&out_idx[j], i);
-        }
-    }
+    OC_PAR_FOR(k, size) out_idx[k] = 0xFFFFFF - (out_idx[k] & 0xFFFFFF);
     if (OC_TID == 0) *out_n = size;
     OC_SYNC();
     OC_MARK(5);   // winners

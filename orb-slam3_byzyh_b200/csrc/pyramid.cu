@@ -312,8 +312,7 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
         tma_tile_g2s(rzs, &srcMap, cLo, ORBFE_YOFF + yblk[yb0].s, blockIdx.z, &bar[0]);
     }
     // this thread's four destination columns: x taps in registers
-    const int wc = min(blockIdx.x * 32 + lane, words - 1);
-    const bool active = blockIdx.x * 32 + lane < words;
+    const int wc = min(blockIdx.x * 32 + lane, words - 1);   // lanes past the row end redo its last word
     uint32_t wgt[4], sel[4];
     int wi0, sh;
     {
@@ -355,7 +354,7 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
         mbar_wait(&bar[k], ((yb - yb0) >> 1) & 1);
         // horizontal pass of every staged source row
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(rzs + k * srcBytes) + wi0;
-#pragma unroll 2
+#pragma unroll 4
         for (int r = wid; r < nsrc; r += RZ_WARPS) {
             const uint32_t* rw = sw + r * bw4;
             const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
@@ -385,7 +384,10 @@ k_resize_tile(uint8_t* __restrict__ pyr, unsigned long long pyrStride, const __g
                 const uint32_t a23 = __umulhi(tq.z, h0.z) + (__umulhi(tq.z, h0.w) << 16);
                 const uint32_t b23 = __umulhi(tq.w, h1.z) + (__umulhi(tq.w, h1.w) << 16);
                 const uint32_t lo = (a01 + b01 + 0x00020002u) >> 2, hi = (a23 + b23 + 0x00020002u) >> 2;
-                if (active) *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x6420);
+                // lanes past the last word repeat the last word's columns (wc is clamped) and store the same value to the
+                // same address: no divergent branch around the store, so the unrolled rows are one basic block and the
+                // shared-memory loads of the next rows are issued under the arithmetic of the current one
+                *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x6420);
             }
         }
         __syncthreads();             // Hb / ytile are free for the next block
