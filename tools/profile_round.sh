@@ -14,6 +14,9 @@ SHORT="bench.py --steps 2 --warmup 3 --frames 128 --no-cpu --no-match --no-extra
 python $SHORT > $O/${T}_short.json 2> $O/${T}_short.err || { echo "short bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${T}_launches.csv \
     python $SHORT > $O/${T}_ncu_launch.log 2>&1
+# launch list of the bench command at its own batch size (first five steps = 70 launches of 1024 frames)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv --log-file $O/${T}_launches_1024.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-match --no-extra > $O/${T}_ncu_launch_1024.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_ -s 42 -c 14 -f -o $O/${T}_full \
     python $SHORT > $O/${T}_ncu_full.log 2>&1
 ncu -i $O/${T}_full.ncu-rep --page raw --csv > $O/${T}_full_raw.csv 2>/dev/null
