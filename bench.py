@@ -789,7 +789,7 @@ def run_ours(args):
                 "e2e_chunk_frames": args.chunk, "e2e_timer": "host perf_counter around the K steps, max over ranks",
                 "e2e_mode": "orbfe_extract_batch_submit/_wait, 2 host batches in flight (sync_call_value: one blocking orbfe_extract_batch per step)",
                 "cpu_affinity": affinity,
-                "ncu_captures": "profiles/*: ncu runs use --frames 128 (kernel shares and per-frame counters, not absolute times)"},
+                "ncu_captures": "profiles/*_launches_1024.txt = launch list of this command at 1024 frames per launch (kernel shares of the step); --set full captures run at --frames 128 (per-frame counters, not absolute times)"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "sync_call_value": e2e_sync,
                 "sync_call_ms_per_step": e2e_sync_ms / args.steps, "single_frame_call_ms": single_ms,
