@@ -52,8 +52,13 @@ float orbfe_get_scale_factor(const OrbfeExtractor* h);
 int orbfe_scale_tables(const OrbfeExtractor* h, float* scale, float* inv_scale, float* sigma2,
                        float* inv_sigma2);
 int orbfe_features_per_level(const OrbfeExtractor* h, int* n_per_level);
-/* Upper bound of keypoints one frame can return (octree may overshoot the per-level target). */
+/* Upper bound of keypoints one frame can return (octree may overshoot the per-level target); holds for frames whose
+ * levels start DistributeOctTree from at most 8 roots (ORBextractor.cc:718: round(width / height) of the level), i.e.
+ * aspect ratios up to 8.5 : 1.  orbfe_max_keypoints_for is the bound for a rows x cols frame whatever its shape (the
+ * rectified size when rectification maps are set); a call whose `capacity` is smaller than the keypoint count of a
+ * frame returns ORBFE_ERR_CAPACITY. */
 int orbfe_max_keypoints(const OrbfeExtractor* h);
+int orbfe_max_keypoints_for(const OrbfeExtractor* h, int rows, int cols);
 
 /* int ORBextractor::operator()(image, mask, keypoints, descriptors, vLappingArea)
  * include/ORBextractor.h:57-59, src/ORBextractor.cc:1557-1682.  image = rows x cols CV_8UC1,

@@ -106,6 +106,15 @@ int quiesce(OrbfeExtractor* e) {
     return ORBFE_OK;
 }
 
+// Root nodes of DistributeOctTree on level l of a rows x cols frame (:718: round(width / height) of the level's FAST
+// window); 1 for a level without a full 35-px cell (no keypoints there), < 1 where the reference divides by zero.
+int level_roots(const OrbfeExtractor* e, int rows, int cols, int l) {
+    const int w = cv_round((float)cols * e->invScale[l]), h = cv_round((float)rows * e->invScale[l]);
+    const float width = (float)(w - 2 * ORBFE_FAST_BORDER), height = (float)(h - 2 * ORBFE_FAST_BORDER);
+    if (!(width >= 35.f && height >= 35.f)) return 1;
+    return (int)roundf(width / height);
+}
+
 int build_geometry(OrbfeExtractor* e, int rows, int cols) {
     if (e->haveGeom && e->g.rows == rows && e->g.cols == cols) return ORBFE_OK;
     if (rows > 4096 || cols > 4096) return fail(ORBFE_ERR_INVALID, "image larger than 4096 px");
@@ -148,7 +157,7 @@ int build_geometry(OrbfeExtractor* e, int rows, int cols) {
         L.candCap = L.nCols * L.nRows * L.cellCap;
         slot += (unsigned)L.candCap;
         L.nfeat = e->nfeat[l];
-        L.nIni = hasCells ? (int)roundf(width / (float)(L.maxBY - ORBFE_FAST_BORDER)) : 1;  // :718
+        L.nIni = level_roots(e, rows, cols, l);  // :718
         if (L.nIni < 1) return fail(ORBFE_ERR_INVALID, "aspect ratio < 0.5 (the reference divides by zero)");
         L.hX = hasCells ? width / L.nIni : 1.f;
         L.ocM = std::max(L.nfeat + 3, 4 * L.nIni) + 1;
@@ -500,8 +509,18 @@ int orbfe_features_per_level(const OrbfeExtractor* h, int* n_per_level) {
 
 int orbfe_max_keypoints(const OrbfeExtractor* h) {
     if (!h) return ORBFE_ERR_INVALID;
-    int n = 0;  // per level: DistributeOctTree stops at >= N after adding <= 3 nodes, or at 4 per root
+    int n = 0;  // per level: DistributeOctTree stops at >= N after adding <= 3 nodes, or at 4 per root (<= 8 roots here)
     for (int i = 0; i < h->nlevels; i++) n += std::max(h->nfeat[i] + 3, 4 * 8) + 1;
+    return n;
+}
+
+// The same bound with the root count of the actual frame size: a level of a very wide frame starts from
+// round(width / height) roots, each of which can leave four nodes behind even when the level's target is smaller.
+int orbfe_max_keypoints_for(const OrbfeExtractor* h, int rows, int cols) {
+    if (!h || rows <= 0 || cols <= 0) return ORBFE_ERR_INVALID;
+    if (h->d_mapx) { rows = h->rectRows; cols = h->rectCols; }   // the frames are rectified to this size first
+    int n = 0;
+    for (int l = 0; l < h->nlevels; l++) n += std::max(h->nfeat[l] + 3, 4 * std::max(level_roots(h, rows, cols, l), 1)) + 1;
     return n;
 }
 

@@ -7,6 +7,7 @@
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,12 +45,14 @@ class ORBextractor {
         cv::Mat image = _image.getMat();
         assert(image.type() == CV_8UC1);  // :1567
         static_assert(sizeof(cv::KeyPoint) == sizeof(OrbfeKeyPoint), "cv::KeyPoint layout");
-        std::vector<cv::KeyPoint> kps(capacity_);
-        std::vector<unsigned char> desc((size_t)capacity_ * 32);
+        // frames wider than 8.5 : 1 start the quadtree from more roots than capacity_ allows for
+        const int cap = std::max(capacity_, orbfe_max_keypoints_for(h_, image.rows, image.cols));
+        std::vector<cv::KeyPoint> kps(cap);
+        std::vector<unsigned char> desc((size_t)cap * 32);
         int n = 0;
         const int mono = orbfe_extract(h_, image.data, image.rows, image.cols, (size_t)image.step, vLappingArea[0],
                                        vLappingArea[1], reinterpret_cast<OrbfeKeyPoint*>(kps.data()), desc.data(),
-                                       capacity_, &n);
+                                       cap, &n);
         if (mono < 0) throw std::runtime_error(std::string("ORBextractor (B200): ") + orbfe_last_error());
         kps.resize(n);
         _keypoints.swap(kps);

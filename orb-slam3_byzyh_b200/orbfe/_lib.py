@@ -92,6 +92,7 @@ _SIGS = {
     "orbfe_scale_tables": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "orbfe_features_per_level": (_i, [_vp, _vp]),
     "orbfe_max_keypoints": (_i, [_vp]),
+    "orbfe_max_keypoints_for": (_i, [_vp, _i, _i]),
     "orbfe_extract": (_i, [_vp, _vp, _i, _i, _sz, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "orbfe_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "orbfe_extract_batch_submit": (_i, [_vp, _vp, _i, _i, _i, _sz, _sz, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -84,7 +84,7 @@ class ORBextractor:
         assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 expected (ORBextractor.cc:1567)"
         if image.strides[1] != 1:
             image = np.ascontiguousarray(image)
-        cap = self.capacity
+        cap = self.capacity_for(*image.shape)
         kps = np.empty(cap, KP_DTYPE)
         desc = np.empty((cap, 32), np.uint8)
         n = C.c_int(0)
@@ -94,11 +94,15 @@ class ORBextractor:
         self._shape = self._rect or image.shape
         return mono, kps[:n.value].copy(), desc[:n.value].copy()
 
+    def capacity_for(self, rows, cols):
+        """Keypoint capacity a rows x cols frame needs: `capacity`, or more for frames wider than 8.5 : 1."""
+        return max(self.capacity, lib().orbfe_max_keypoints_for(self._h, int(rows), int(cols)))
+
     def extract_batch(self, images, vLappingArea=(0, 0), out=None):
         """images: [B, rows, cols] uint8 host array (numpy, or a pinned torch CPU tensor).  Returns
         (n[B], mono[B], keypoints[B, cap], descriptors[B, cap, 32]) host arrays."""
         B, rows, cols = images.shape
-        cap = self.capacity
+        cap = self.capacity_for(rows, cols)
         if out is None:
             out = (np.empty(B, np.int32), np.empty(B, np.int32), np.empty((B, cap), KP_DTYPE),
                    np.empty((B, cap, 32), np.uint8))

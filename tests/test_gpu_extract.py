@@ -70,6 +70,24 @@ def test_noise_frames_and_odd_sizes(orbfe):
         _check_frame(orbfe.ORBextractor(nf), O.Extractor(nf), img, (0, 0))
 
 
+def test_very_wide_frame_more_roots_than_features(orbfe):
+    # 9 quadtree roots per level (ORBextractor.cc:718) with a per-level target of ~20 features: the levels return up to
+    # 4 nodes per root, more than orbfe_max_keypoints() allows for -- the wrappers size the outputs with
+    # orbfe_max_keypoints_for (found by tools/parity_stress.py)
+    from orbfe._lib import ptr
+    import ctypes as C
+    ex_g, ex_c = orbfe.ORBextractor(50, 1.2, 3), O.Extractor(50, 1.2, 3)
+    img = synth.noise_frame(175, 1373, 468400454)
+    assert ex_g.capacity_for(175, 1373) > ex_g.capacity
+    _check_frame(ex_g, ex_c, img, (0, 1000))
+    n = C.c_int(0)
+    kps = np.empty(ex_g.capacity, orbfe.KP_DTYPE)
+    desc = np.empty((ex_g.capacity, 32), np.uint8)
+    rc = orbfe.lib().orbfe_extract(ex_g.handle, ptr(img), 175, 1373, 1373, 0, 1000, ptr(kps), ptr(desc),
+                                   ex_g.capacity, C.byref(n))
+    assert rc == orbfe.ERR_CAPACITY       # reported, never truncated silently
+
+
 def test_other_pyramid_parameters(orbfe):
     img = synth.synth_frame(480, 640, 9)
     for (nf, sf, nl, ini, mn) in [(800, 2.0, 3, 20, 7), (600, 1.5, 4, 30, 10), (500, 1.1, 10, 12, 5), (400, 1.2, 1, 20, 7)]:
