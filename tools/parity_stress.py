@@ -67,5 +67,35 @@ for c in range(cases):
         print("ERROR", tag, "->", str(e)[:120])
         bad += 1
     done += 1
+
+# ---- handle reuse and batch paths: one extractor over changing frame sizes, single calls and host batches mixed,
+# random chunk budgets (several chunks per batch, CUDA-graph replay for small batches, re-layout on size changes) ----
+sessions = max(1, cases // 15)
+for c in range(sessions):
+    nf = int(rng.choice([300, 1000, 2000]))
+    exg, exc = orbfe.ORBextractor(nf), O.Extractor(nf)
+    sizes = [(int(rng.integers(200, 760)), int(rng.integers(760, 1300))) for _ in range(2)]
+    for step in range(6):
+        h, w = sizes[int(rng.integers(0, 2))]
+        lap = [(0, 1000), (0, 0), (w // 4, 3 * w // 4)][int(rng.integers(0, 3))]
+        B = int(rng.choice([1, 1, 2, 3, 4, 7, 12]))
+        mb = int(rng.choice([48 << 20, 100 << 20, 6 << 30]))
+        frames = np.stack([image(h, w, int(rng.integers(0, 5)), int(rng.integers(0, 1 << 30))) for _ in range(B)])
+        tag = f"session {c} step {step}: {B} x {h}x{w} nf={nf} lap={lap} max_bytes={mb >> 20} MB"
+        try:
+            exg.set_max_bytes(mb)
+            if B == 1 and step % 2:
+                _check_frame(exg, exc, frames[0], lap, stages=False)
+            else:
+                n, mono, kps, desc = exg.extract_batch(frames, lap)
+                for i in range(B):
+                    mo, ko, do = exc(frames[i], lap)
+                    assert mono[i] == mo and n[i] == len(ko), f"frame {i}: counts"
+                    assert kps[i, :n[i]].tobytes() == ko.tobytes(), f"frame {i}: keypoints"
+                    assert np.array_equal(desc[i, :n[i]], do), f"frame {i}: descriptors"
+        except (AssertionError, orbfe.OrbfeError) as e:
+            print("MISMATCH", tag, "->", str(e)[:120])
+            bad += 1
+        done += 1
 print(f"{done} cases compared, {bad} failing, {time.time() - t0:.1f} s")
 sys.exit(1 if bad else 0)
