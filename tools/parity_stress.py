@@ -12,6 +12,7 @@ from test_gpu_extract import _check_frame
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 orbfe.lib()
+MAXH, MAXW = int(os.environ.get("STRESS_MAXH", "800")), int(os.environ.get("STRESS_MAXW", "1400"))
 
 
 def image(h, w, kind, seed):
@@ -33,14 +34,14 @@ def image(h, w, kind, seed):
 
 bad, t0, done = 0, time.time(), 0
 for c in range(cases):
-    h, w = int(rng.integers(160, 800)), int(rng.integers(200, 1400))
+    h, w = int(rng.integers(160, MAXH)), int(rng.integers(200, MAXW))
     if w < h:
         h, w = w, h                             # portrait levels can round width / height to 0 roots: the reference divides by zero there
-    nf = int(rng.choice([50, 200, 500, 1000, 1500, 2000, 4000]))
+    nf = int(rng.choice([5, 50, 200, 500, 1000, 1500, 2000, 4000, 12000]))
     sf = float(rng.choice([1.2, 1.2, 1.2, 1.1, 1.3, 1.5, 2.0]))
     nl = int(rng.integers(1, 9))
-    ini = int(rng.choice([20, 20, 12, 30, 40, 7]))
-    mn = int(rng.choice([7, 7, 5, 10, 2]))
+    ini = int(rng.choice([20, 20, 12, 30, 40, 7, 100, 0]))
+    mn = int(rng.choice([7, 7, 5, 10, 2, 0, 25]))
     while nl > 1 and round(min(h, w) / sf ** (nl - 1)) < 48:
         nl -= 1                                  # the reference itself breaks on levels smaller than its 16-px border window
     lap = [(0, 1000), (0, 0), (0, w - 1), (w // 4, 3 * w // 4)][int(rng.integers(0, 4))]
