@@ -15,6 +15,7 @@
 
 #include "octree_core.h"  // OC_PK_*
 #include "orbfe_internal.h"
+#include "sincosf_core.h"
 
 namespace {
 
@@ -258,9 +259,8 @@ k_describe(const __grid_constant__ OrbfeFrameGeom g, const uint8_t* __restrict__
     // ---- steered BRIEF on the blurred level (:150-203) ----
     const float factorPI = (float)(3.14159265358979323846 / 180.0);  // (float)(CV_PI/180.f), :141
     const float ang = __fmul_rn(angle, factorPI);
-    double sd, cd;
-    sincos((double)ang, &sd, &cd);      // one shared range reduction; the same values as sin() / cos()
-    const float a = (float)cd, b = (float)sd;
+    float a, b;                         // a = cosf(ang), b = sinf(ang) of the reference's libm
+    glibc_sincosf(ang, &b, &a);
     const uint8_t* bc = blur + co;
     unsigned val = 0;
 #pragma unroll

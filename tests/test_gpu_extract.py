@@ -88,6 +88,14 @@ def test_very_wide_frame_more_roots_than_features(orbfe):
     assert rc == orbfe.ERR_CAPACITY       # reported, never truncated silently
 
 
+def test_descriptor_on_an_angle_where_libm_sinf_is_not_correctly_rounded(orbfe):
+    # tools/parity_stress.py, seed 5 case 60: keypoint 165 of this frame has sinf(angle) 0.517 ulp off in glibc; with the
+    # rounded fp64 value a BRIEF sample moved from row 3 to row 4 and bit 198 of its descriptor flipped.  k_describe
+    # restates glibc's routine (csrc/sincosf_core.h), so every descriptor is equal.
+    img = synth.synth_frame(630, 1185, 75409971)
+    assert _check_frame(orbfe.ORBextractor(4000, 1.2, 7, 12, 7), O.Extractor(4000, 1.2, 7, 12, 7), img, (0, 1000), stages=False) == 0
+
+
 def test_other_pyramid_parameters(orbfe):
     img = synth.synth_frame(480, 640, 9)
     for (nf, sf, nl, ini, mn) in [(800, 2.0, 3, 20, 7), (600, 1.5, 4, 30, 10), (500, 1.1, 10, 12, 5), (400, 1.2, 1, 20, 7)]:
