@@ -25,7 +25,7 @@ def run(name, fn, *args):
         fn(*args)
     except Exception as e:
         bad += 1
-        print("MISMATCH", name, args, "->", (str(e) or traceback.format_exc(limit=1))[:160], flush=True)
+        print("MISMATCH", name, [a for a in args if not isinstance(a, tuple)], "->", (str(e) or traceback.format_exc(limit=1))[:160], flush=True)
 
 
 for r in range(rounds):
@@ -38,5 +38,23 @@ for r in range(rounds):
     run("fuse", T.test_fuse_vs_reference, s, bool(r & 1))
     run("search_by_sim3", T.test_search_by_sim3_vs_reference, s)
     run("distinctive", T.test_distinctive_descriptors_vs_reference, s)
+
+# ---- BoW matchers and the triangulation search against DBoW2 / the reference bodies compiled verbatim ----
+if R.matcher_available():
+    import tempfile
+    import synth
+    from oracle import oracle as O
+    import test_oracle_bow_vs_ref as TB
+    voc = synth.make_vocabulary(10, 4, 3)
+    path = os.path.join(tempfile.mkdtemp(), "voc.txt")
+    synth.write_vocabulary_text(path, voc)
+    vp = (voc, R.RefVocabulary(path), O.Vocabulary(10, 4, voc["parent"], voc["desc"], voc["weight"]))
+    for r in range(rounds):
+        s = int(rng.integers(100, 1 << 20))
+        run("search_by_bow", TB.test_search_by_bow_kf_frame_vs_reference, vp, s, bool(r & 1), float(rng.choice([0.6, 0.7, 0.9])))
+        run("search_by_bow_fisheye", TB.test_search_by_bow_kf_frame_fisheye_vs_reference, vp, s, bool(r & 1))
+        run("search_by_bow_keyframes", TB.test_search_by_bow_kf_kf_vs_reference, vp, s, bool(r & 1))
+        run("search_for_triangulation", TB.test_search_for_triangulation_vs_reference, vp, s, bool(rng.integers(0, 2)),
+            bool(rng.integers(0, 2)), bool(r & 1), float(rng.uniform(0, 0.7)))
 print(f"{done} cases compared, {bad} failing, {time.time() - t0:.1f} s")
 sys.exit(1 if bad else 0)
